@@ -1,0 +1,8 @@
+"""Import shim: `import a2f_b200` resolves to the package directory `audio2face-pytorch_b200/` (whose name, fixed by
+the repo layout, is not a valid Python identifier)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "audio2face-pytorch_b200")
+__path__.insert(0, _real)
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

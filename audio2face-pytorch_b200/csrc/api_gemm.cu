@@ -1,0 +1,189 @@
+// C-ABI: a2f_gemm, a2f_posconv and the weight packers / casts that feed them.
+#include "a2f_common.cuh"
+#include "gemm_params.cuh"
+
+namespace a2f {
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __bfloat162float(in[i]);
+}
+
+// [Cout,Cin,taps] -> [Cout, taps*Cin] with k = tap*Cin + cin (the order in which a channels-last im2col row is laid out)
+template <typename TO>
+__global__ void pack_conv1d_kernel(const float* __restrict__ w, TO* __restrict__ out, int cout, int cin, int taps) {
+    long long n = (long long)cout * cin * taps;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int tap = (int)(i % taps);
+        long long r = i / taps;
+        int ci = (int)(r % cin);
+        int co = (int)(r / cin);
+        st_from_float(out + ((long long)co * taps + tap) * cin + ci, w[i]);
+    }
+}
+
+// weight_norm(dim=2): norm[tap] = sqrt(sum_{o,c} v[o,c,tap]^2)   (fp64 accumulation, one block per tap)
+__global__ void posconv_norm_kernel(const float* __restrict__ v, float* __restrict__ norm) {
+    const int tap = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < 768 * 48; i += blockDim.x) {
+        double x = v[(long long)i * 128 + tap];
+        s += x * x;
+    }
+    __shared__ double sh[32];
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+        t = warp_sum_d(t);
+        if (threadIdx.x == 0) norm[tap] = (float)sqrt(t);
+    }
+}
+// out[g][n][tap][c (kpad)] = g[tap] * v[g*48+n, c, tap] / norm[tap]   (c >= 48 -> 0)
+// torch's _weight_norm computes v * (g / norm): same association here.
+template <typename TO>
+__global__ void posconv_pack_kernel(const float* __restrict__ gw, const float* __restrict__ v,
+                                    const float* __restrict__ norm, TO* __restrict__ out, int kpad) {
+    const long long n = (long long)768 * 128 * kpad;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int c = (int)(i % kpad);
+        long long r = i / kpad;
+        int tap = (int)(r % 128);
+        int o = (int)(r / 128);   // g*48 + n
+        float val = 0.f;
+        if (c < 48) val = v[((long long)o * 48 + c) * 128 + tap] * (gw[tap] / norm[tap]);
+        st_from_float(out + i, val);
+    }
+}
+
+static int fill_params(const a2f_gemm_args* a, GemmParams* p) {
+    A2F_REQUIRE(a != nullptr, "a2f_gemm: args is NULL");
+    A2F_REQUIRE(a->M >= 0 && a->N >= 0 && a->K > 0, "a2f_gemm: bad M/N/K");
+    A2F_REQUIRE(a->A && a->W && a->C, "a2f_gemm: A, W and C must be non-NULL");
+    A2F_REQUIRE(a->rows_per_batch > 0, "a2f_gemm: rows_per_batch must be positive");
+    A2F_REQUIRE(a->tmpl == nullptr || a->rows_per_tmpl > 0, "a2f_gemm: rows_per_tmpl must be positive with tmpl");
+    A2F_REQUIRE(a->a_dtype == A2F_F32 || a->a_dtype == A2F_BF16, "a2f_gemm: bad a_dtype");
+    A2F_REQUIRE(a->c_dtype == A2F_F32 || a->c_dtype == A2F_BF16, "a2f_gemm: bad c_dtype");
+    p->M = a->M; p->N = a->N; p->K = a->K;
+    p->A = a->A; p->a_row_stride = a->a_row_stride; p->a_batch_stride = a->a_batch_stride;
+    p->rows_per_batch = a->rows_per_batch;
+    p->W = a->W; p->ldw = a->ldw;
+    p->bias = a->bias; p->act = a->act;
+    p->resid = a->resid; p->resid_bf16 = (a->resid_dtype == A2F_BF16); p->ldr = a->ldr;
+    p->tmpl = a->tmpl; p->rows_per_tmpl = a->rows_per_tmpl > 0 ? a->rows_per_tmpl : 1;
+    p->C = a->C; p->ldc = a->ldc;
+    return A2F_OK;
+}
+
+}  // namespace a2f
+
+using namespace a2f;
+
+extern "C" {
+
+int a2f_gemm(const a2f_gemm_args* args, int backend, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    GemmParams p;
+    rc = fill_params(args, &p);
+    if (rc != A2F_OK) return rc;
+    if (backend == A2F_BACKEND_SIMT_F32) {
+        return gemm_simt(p, args->a_dtype == A2F_BF16, args->c_dtype == A2F_BF16, as_stream(stream));
+    } else if (backend == A2F_BACKEND_TCGEN05) {
+        A2F_REQUIRE(args->a_dtype == A2F_BF16, "a2f_gemm: the tcgen05 backend takes bf16 operands");
+        return gemm_tc(p, args->c_dtype == A2F_BF16, 0, as_stream(stream));
+    }
+    return set_error(A2F_EINVAL, "a2f_gemm: unknown backend");
+}
+
+int a2f_posconv(const void* h, int h_dtype, const void* Wp, const float* bias, void* out, int out_dtype, int B, int T,
+                int backend, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(h && Wp && out && B > 0 && T > 0, "a2f_posconv: bad arguments");
+    GemmParams p;
+    p.M = B * T; p.N = 48;
+    p.A = h; p.a_row_stride = 768; p.a_batch_stride = (long long)T * 768; p.rows_per_batch = T;
+    p.W = Wp;
+    p.bias = bias; p.act = A2F_ACT_GELU;
+    p.resid = h; p.resid_bf16 = (h_dtype == A2F_BF16); p.ldr = 768;
+    p.tmpl = nullptr; p.rows_per_tmpl = 1;
+    p.C = out; p.ldc = 768;
+    if (backend == A2F_BACKEND_SIMT_F32) {
+        p.K = 128 * 48; p.ldw = 128 * 48;
+        return posconv_simt(p, h_dtype == A2F_BF16, out_dtype == A2F_BF16, as_stream(stream));
+    } else if (backend == A2F_BACKEND_TCGEN05) {
+        A2F_REQUIRE(h_dtype == A2F_BF16, "a2f_posconv: the tcgen05 backend takes bf16 activations");
+        p.K = 128 * 64; p.ldw = 128 * 64;
+        return gemm_tc(p, out_dtype == A2F_BF16, 2, as_stream(stream));
+    }
+    return set_error(A2F_EINVAL, "a2f_posconv: unknown backend");
+}
+
+int a2f_pack_posconv_weight(const float* g, const float* v, void* out, int out_dtype, int kpad, float* norm_scratch,
+                            void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(g && v && out && norm_scratch && (kpad == 48 || kpad == 64), "a2f_pack_posconv_weight: bad arguments");
+    float* norm = norm_scratch;
+    posconv_norm_kernel<<<128, 256, 0, as_stream(stream)>>>(v, norm);
+    A2F_CHECK_LAUNCH("posconv_norm_kernel");
+    const long long n = (long long)768 * 128 * kpad;
+    const int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+    if (out_dtype == A2F_BF16)
+        posconv_pack_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(g, v, norm, static_cast<bf16*>(out), kpad);
+    else
+        posconv_pack_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(g, v, norm, static_cast<float*>(out), kpad);
+    A2F_CHECK_LAUNCH("posconv_pack_kernel");
+    count_launch(2);
+    return A2F_OK;
+}
+
+int a2f_pack_conv1d_weight(const float* w, void* out, int out_dtype, int cout, int cin, int taps, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(w && out && cout > 0 && cin > 0 && taps > 0, "a2f_pack_conv1d_weight: bad arguments");
+    const long long n = (long long)cout * cin * taps;
+    const int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+    if (out_dtype == A2F_BF16)
+        pack_conv1d_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(w, static_cast<bf16*>(out), cout, cin, taps);
+    else
+        pack_conv1d_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w, static_cast<float*>(out), cout, cin, taps);
+    A2F_CHECK_LAUNCH("pack_conv1d_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    if (n <= 0) return A2F_OK;
+    const int grid = (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256);
+    cast_f32_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, static_cast<bf16*>(out), n);
+    A2F_CHECK_LAUNCH("cast_f32_bf16_kernel");
+    count_launch();
+    return A2F_OK;
+}
+int a2f_cast_bf16_to_f32(const void* in, float* out, long long n, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    if (n <= 0) return A2F_OK;
+    const int grid = (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256);
+    cast_bf16_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const bf16*>(in), out, n);
+    A2F_CHECK_LAUNCH("cast_bf16_f32_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+}  // extern "C"

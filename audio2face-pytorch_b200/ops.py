@@ -1,0 +1,105 @@
+"""Thin torch-tensor wrappers over the C-ABI (lib.py): argument checking, struct filling, stream plumbing.
+
+torch is used for device memory and streams only; every op here launches kernels of liba2f_sm100.so and raises
+A2FError on any non-zero status (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return L.F32
+    if t.dtype == torch.bfloat16:
+        return L.BF16
+    raise L.A2FError(f"unsupported dtype {t.dtype}")
+
+
+def _dev(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.A2FError("a2f ops need CUDA tensors (there is no CPU path)")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+         act: int = L.ACT_NONE, resid: Optional[torch.Tensor] = None, tmpl: Optional[torch.Tensor] = None,
+         rows_per_tmpl: int = 1, backend: int = L.SIMT_F32, M: Optional[int] = None, K: Optional[int] = None,
+         a_row_stride: Optional[int] = None, a_batch_stride: int = 0, rows_per_batch: Optional[int] = None,
+         N: Optional[int] = None, ldw: Optional[int] = None, ldc: Optional[int] = None) -> torch.Tensor:
+    """out[m,n] = act(sum_k a[m,k] w[n,k] + bias[n]) + resid[m,n] + tmpl[m // rows_per_tmpl, n]  (a2f_gemm)."""
+    _dev(a, w, out, bias, resid, tmpl)
+    lib = L.load()
+    g = L.GemmArgs()
+    g.M = int(M if M is not None else a.shape[0])
+    g.N = int(N if N is not None else w.shape[0])
+    g.K = int(K if K is not None else a.shape[-1])
+    g.A, g.a_dtype = a.data_ptr(), _dt(a)
+    g.a_row_stride = int(a_row_stride if a_row_stride is not None else a.stride(0))
+    g.a_batch_stride = int(a_batch_stride)
+    g.rows_per_batch = int(rows_per_batch if rows_per_batch is not None else g.M)
+    g.W, g.ldw = w.data_ptr(), int(ldw if ldw is not None else w.stride(0))
+    g.bias = L.ptr(bias)
+    g.act = act
+    if resid is not None:
+        g.resid, g.resid_dtype, g.ldr = resid.data_ptr(), _dt(resid), int(resid.stride(0))
+    if tmpl is not None:
+        g.tmpl, g.rows_per_tmpl = tmpl.data_ptr(), int(rows_per_tmpl)
+    g.C, g.c_dtype = out.data_ptr(), _dt(out)
+    g.ldc = int(ldc if ldc is not None else out.stride(0))
+    if bias is not None and bias.dtype != torch.float32:
+        raise L.A2FError("bias must be fp32")
+    if tmpl is not None and tmpl.dtype != torch.float32:
+        raise L.A2FError("tmpl must be fp32")
+    if a.dtype != w.dtype:
+        raise L.A2FError("A and W must share a dtype")
+    L.check(lib.a2f_gemm(C.byref(g), backend, _stream()), "a2f_gemm")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _dev(x)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().a2f_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "a2f_cast_f32_to_bf16")
+    return out
+
+
+def voca_trunk(wptrs: "L.VocaWeights", x: torch.Tensor, one_hot: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    _dev(x, one_hot, z)
+    L.check(L.load().a2f_voca_trunk(C.byref(wptrs), x.data_ptr(), one_hot.data_ptr(), one_hot.shape[1], z.data_ptr(),
+                                    _dt(z), z.stride(0), x.shape[0], _stream()), "a2f_voca_trunk")
+    return z
+
+
+def loss_workspace(device) -> torch.Tensor:
+    n = L.load().a2f_voca_loss_workspace_bytes()
+    return torch.empty((n + 7) // 8, dtype=torch.float64, device=device)
+
+
+def voca_loss_fwd(pred: torch.Tensor, gt: torch.Tensor, rows: int, v3: int, k_rec: float, k_vel: float,
+                  ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(pred, gt)
+    out3 = torch.empty(3, dtype=torch.float32, device=pred.device)
+    if ws is None:
+        ws = loss_workspace(pred.device)
+    L.check(L.load().a2f_voca_loss_fwd(pred.data_ptr(), gt.data_ptr(), rows, v3, k_rec, k_vel, out3.data_ptr(),
+                                       ws.data_ptr(), ws.numel() * 8, _stream()), "a2f_voca_loss_fwd")
+    return out3
+
+
+def voca_loss_bwd(pred: torch.Tensor, gt: torch.Tensor, rows: int, v3: int, k_rec: float, k_vel: float,
+                  gscale: Optional[torch.Tensor], dpred: torch.Tensor) -> torch.Tensor:
+    _dev(pred, gt, dpred, gscale)
+    L.check(L.load().a2f_voca_loss_bwd(pred.data_ptr(), gt.data_ptr(), rows, v3, k_rec, k_vel, L.ptr(gscale),
+                                       dpred.data_ptr(), _stream()), "a2f_voca_loss_bwd")
+    return dpred

@@ -1,0 +1,221 @@
+/*
+ * a2f.h -- C-ABI of liba2f_sm100.so: the B200 (sm_100a) audio->mesh hot path of
+ * xtliu97/audio2face-pytorch (reference checked out at /root/reference, cited below as ref:<file>:<line>).
+ *
+ * The reference has no FFI layer: its boundary is the Python nn.Module contract of
+ * ref:src/model/lightning_model.py:50-73,111-117 (get_model / forward(x, one_hot, template)).  The drop-in
+ * Python modules of this repo (audio2face-pytorch_b200/modules.py) keep that contract and call the entry points
+ * below through ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates), unless the name ends in _host;
+ *  - nothing is allocated or freed inside the library; scratch space is passed in as `workspace`
+ *    (size from the matching *_workspace_bytes call);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *  - return value: A2F_OK or a negative a2f status; a2f_last_error() gives the message of the calling thread;
+ *  - there is NO CPU fallback: on a device that is not sm_100 every compute call returns A2F_EARCH.
+ *  - matrices are row-major; "[N,K]" weights are exactly torch's nn.Linear.weight layout.
+ */
+#ifndef A2F_H_
+#define A2F_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A2F_VERSION 100
+
+#define A2F_OK 0
+#define A2F_EINVAL (-1) /* bad shape / alignment / argument */
+#define A2F_EARCH (-2)  /* device is not sm_100 */
+#define A2F_ECUDA (-3)  /* CUDA runtime error, message kept in a2f_last_error() */
+
+#define A2F_F32 0
+#define A2F_BF16 1
+
+#define A2F_ACT_NONE 0
+#define A2F_ACT_RELU 1
+#define A2F_ACT_GELU 2 /* exact erf GELU (HF activations "gelu" == torch F.gelu) */
+#define A2F_ACT_TANH 3
+
+#define A2F_BACKEND_SIMT_F32 0 /* true fp32 FMA path: the 1e-5 parity path */
+#define A2F_BACKEND_TCGEN05 1  /* bf16 operands via TMA, fp32 accumulate in TMEM */
+
+int a2f_version(void);
+const char* a2f_status_string(int status);
+const char* a2f_last_error(void);
+/* A2F_OK when the current CUDA device is compute capability 10.x, else A2F_EARCH / A2F_ECUDA. */
+int a2f_device_check(void);
+/* number of kernels this library has launched from the calling process since load (bench.py's gpu_launches). */
+long long a2f_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Generic fused GEMM:  C[m,n] = act( sum_k A[m,k] * W[n,k] + bias[n] ) + resid[m,n] + tmpl[m / rows_per_tmpl, n]
+ * Replaces every nn.Linear / F.linear on the path (ref:src/model/voca.py:30-36, ref:src/model/audio2face.py:49-55,
+ * ref:src/model/faceformer.py:112,129, HF modeling_wav2vec2.py:422-434,466-573) and, through the A-row addressing
+ * below, the stride-2 Conv1d stack of the wav2vec2 feature encoder as an implicit GEMM
+ * (HF modeling_wav2vec2.py:254-272) with activations kept channels-last.
+ *
+ * A-row addressing: logical row m -> (b, r) = (m / rows_per_batch, m % rows_per_batch);
+ *   element (m,k) lives at A + b*a_batch_stride + r*a_row_stride + k   (strides in elements).
+ *   Plain matrix: rows_per_batch = M, a_row_stride = lda.  Conv1d(k taps, stride s) over channels-last [B,L,C]:
+ *   K = k*C, a_row_stride = s*C, a_batch_stride = L*C, rows_per_batch = L_out  (rows overlap, nothing is copied).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct a2f_gemm_args {
+    int M, N, K;
+    const void* A;
+    int a_dtype; /* A2F_F32 (SIMT backend) or A2F_BF16 (either backend) */
+    long long a_row_stride, a_batch_stride;
+    int rows_per_batch;
+    const void* W; /* [N,K], same dtype as A */
+    long long ldw;
+    const float* bias; /* [N] or NULL */
+    int act;
+    const void* resid; /* [M,N] added after the activation, or NULL */
+    int resid_dtype;
+    long long ldr;
+    const float* tmpl; /* [ceil(M/rows_per_tmpl), N] fp32 added last (template mesh), or NULL */
+    int rows_per_tmpl;
+    void* C;
+    int c_dtype;
+    long long ldc;
+} a2f_gemm_args;
+
+int a2f_gemm(const a2f_gemm_args* args, int backend, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * wav2vec2 positional conv embedding (HF modeling_wav2vec2.py:326-379,690-693 via ref:src/model/wav2vec.py:174):
+ *   out[b,t,:] = h[b,t,:] + gelu( grouped_conv1d_k128_pad64_g16(h)[b,t,:] + bias )      (last conv step dropped)
+ * h, out: channels-last [B,T,768].  Wp: packed weight [16 groups][48 out][128 taps][kpad in] produced by
+ * a2f_pack_posconv_weight (kpad = 48 for the SIMT backend, 64 zero-padded for the tcgen05 backend).
+ * ---------------------------------------------------------------------------------------------------------- */
+int a2f_posconv(const void* h, int h_dtype, const void* Wp, const float* bias, void* out, int out_dtype, int B, int T,
+                int backend, void* stream);
+/* weight_norm fold g*v/||v|| (norm over dims (0,1) per tap; HF weight_norm(dim=2)) + regroup.
+ * g: [128] (original0), v: [768,48,128] (original1) fp32.  out dtype fp32 (kpad=48) or bf16 (kpad=64). */
+int a2f_pack_posconv_weight(const float* g, const float* v, void* out, int out_dtype, int kpad,
+                            float* norm_scratch /* [128] device floats */, void* stream);
+/* Conv1d weight [Cout,Cin,taps] fp32 -> implicit-GEMM W [Cout, taps*Cin] (k = tap*Cin + cin), fp32 or bf16 */
+int a2f_pack_conv1d_weight(const float* w, void* out, int out_dtype, int cout, int cin, int taps, void* stream);
+/* elementwise cast fp32 -> bf16 (n elements) */
+int a2f_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream);
+int a2f_cast_bf16_to_f32(const void* in, float* out, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * wav2vec2 front end.
+ *  a2f_audio_stats: per-utterance mean and 1/sqrt(var+1e-7) (population variance) of raw audio [B,N]
+ *     (the Wav2Vec2Processor zero-mean/unit-variance step the reference runs in numpy on the host,
+ *      ref:src/model/faceformer.py:142-144 -> HF feature_extraction_wav2vec2.py:78-98). stats: [B,2] fp32.
+ *  a2f_conv0_gn_gelu: normalise + Conv1d(1->512,k10,s5,no bias) + GroupNorm(512 groups, eps 1e-5, affine) + GELU
+ *     (HF modeling_wav2vec2.py:302-323).  out: channels-last [B,L0,512], L0 = (N-10)/5+1.
+ *     workspace: a2f_conv0_workspace_bytes(B,N).
+ *  a2f_interp_ln: linear_interpolation(align_corners=True) S->T frames (ref:src/model/wav2vec.py:76-84,126-128)
+ *     followed by LayerNorm(C, eps) of the feature projection (HF modeling_wav2vec2.py:429-431).
+ *     in [B,S,C] -> out [B,T,C].
+ * ---------------------------------------------------------------------------------------------------------- */
+int a2f_audio_stats(const float* audio, int B, long long N, float* stats, void* stream);
+size_t a2f_conv0_workspace_bytes(int B, long long N);
+int a2f_conv0_gn_gelu(const float* audio, const float* stats, const float* w /*[512,10]*/, const float* gamma,
+                      const float* beta, void* out, int out_dtype, int B, long long N, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int a2f_interp_ln(const void* in, int in_dtype, const float* gamma, const float* beta, float eps, void* out,
+                  int out_dtype, int B, int S, int T, int C, void* stream);
+/* LayerNorm over the last dim (C <= 4096, C % 4 == 0): out = (x-mean)*rstd*gamma+beta, stats in fp32.
+ * Optional second output out2 (e.g. fp32 master + bf16 GEMM operand in one pass). */
+int a2f_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, float eps, void* out,
+                  int out_dtype, void* out2, int out2_dtype, long long rows, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Encoder self-attention (HF modeling_wav2vec2.py:438-549): softmax(Q K^T * scale) V, no mask, never
+ * materialising the [T,T] probabilities.  qkv: [B,T,3*H*D] (q | k | v blocks, each head-major), out: [B,T,H*D].
+ * D must be 64.  fp32 in/out -> SIMT fp32 kernel; bf16 in/out -> tensor-core kernel.
+ * ---------------------------------------------------------------------------------------------------------- */
+int a2f_mha_fwd(const void* qkv, void* out, int dtype, int B, int T, int H, int D, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * FaceFormer autoregressive decoder (ref:src/model/faceformer.py:154-185; torch nn.TransformerDecoderLayer
+ * post-norm, d=64, 4 heads, ffn 128) as ONE persistent kernel, one CTA per utterance, KV-cached O(T) decode:
+ *   e_0 = style;  d_i = DecLayer(PPE(e_0..e_i), mem)[i];  e_{i+1} = Wc d_i + bc + style
+ * with Wc = vertice_map.weight @ vertice_map_r.weight, bc = vertice_map.weight @ vertice_map_r.bias +
+ * vertice_map.bias (a2f_pack_feedback) -- algebraically the reference's 64->15069->64 feedback.
+ * The ALiBi-style bias -slope_h*floor((i-j)/period) (ref:faceformer.py:22-54) and the diagonal memory mask
+ * (ref:faceformer.py:58-66, which reduces cross-attention to out_proj(v_proj(mem_i))) are generated in-register.
+ * Output D: [B,T,64] fp32 decoder states; the vertices follow from a2f_gemm with the template epilogue.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct a2f_decoder_weights {
+    const float* sa_in_w;  /* [192,64] self_attn.in_proj_weight */
+    const float* sa_in_b;  /* [192] */
+    const float* sa_out_w; /* [64,64] */
+    const float* sa_out_b; /* [64] */
+    const float* ca_in_w;  /* [192,64] multihead_attn.in_proj_weight (only rows 128:192 are live) */
+    const float* ca_in_b;  /* [192] */
+    const float* ca_out_w; /* [64,64] */
+    const float* ca_out_b; /* [64] */
+    const float* lin1_w;   /* [128,64] */
+    const float* lin1_b;   /* [128] */
+    const float* lin2_w;   /* [64,128] */
+    const float* lin2_b;   /* [64] */
+    const float* n1_w;     /* norm1..3 weight/bias [64] */
+    const float* n1_b;
+    const float* n2_w;
+    const float* n2_b;
+    const float* n3_w;
+    const float* n3_b;
+    const float* fb_w;  /* [64,64] Wc from a2f_pack_feedback */
+    const float* fb_b;  /* [64] bc */
+    const float* obj_w; /* [64,n_onehot] obj_vector.weight (no bias) */
+    const float* pe;    /* [period,64] first period rows of PPE.pe */
+} a2f_decoder_weights;
+
+size_t a2f_decoder_workspace_bytes(int B, int T);
+int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory /*[B,T,64]*/, const float* one_hot
+                        /*[B,n_onehot]*/, int n_onehot, int period, float* D /*[B,T,64]*/, int B, int T,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* Wc[64,64], bc[64] from vertice_map {weight [64,V3], bias [64]} and vertice_map_r {weight [V3,64], bias [V3]};
+ * accumulation in fp64. */
+int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, const float* vmr_b, int V3, float* Wc,
+                      float* bc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * VOCA trunk (ref:src/model/voca.py:19-46): one-hot tiling + 4 x (Conv2d(3x1,s2,p1)+ReLU) + concat(one_hot[:8])
+ * + Linear 72->72 -> Linear 72->128 -> tanh -> Linear 128->50, fused in one kernel (one warp-group per window).
+ * x: [B,29,16], one_hot: [B,n_onehot] (first 8 used), z: [B,ldz] fp32 or bf16 with the 50 live columns first and
+ * columns 50..ldz-1 zeroed (ldz = 64 feeds the vertex-head GEMM with K padded to a UMMA-friendly 64).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct a2f_voca_weights {
+    const float* conv_w[4]; /* time_conv.{0,2,4,6}.weight [32,37,3,1] [32,32,3,1] [64,32,3,1] [64,64,3,1] */
+    const float* conv_b[4];
+    const float* fc_w[3]; /* decoder.{0,1,3}.weight [72,72] [128,72] [50,128] */
+    const float* fc_b[3];
+} a2f_voca_weights;
+int a2f_voca_trunk(const a2f_voca_weights* w, const float* x, const float* one_hot, int n_onehot, void* z, int z_dtype,
+                   int ldz, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Losses (ref:src/loss/loss.py:24-55; FaceFormerLoss :4-17 is the same with bs = T after dropping an odd last
+ * frame -- done by the caller through `rows`).  pred, gt: [rows, V3] fp32, rows even.
+ *   rec = mean_{row,v} sum_xyz (p-g)^2 ; vel = same on non-overlapping row pairs (2k,2k+1) ; loss = k_rec*rec+k_vel*vel
+ * out3 = {loss, rec, vel} fp32 (zeroed inside).  Optional grad: dpred = d loss / d pred * gscale (one pass).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t a2f_voca_loss_workspace_bytes(void);
+int a2f_voca_loss_fwd(const float* pred, const float* gt, long long rows, int V3, float k_rec, float k_vel,
+                      float* out3, void* workspace, size_t workspace_bytes, void* stream);
+int a2f_voca_loss_bwd(const float* pred, const float* gt, long long rows, int V3, float k_rec, float k_vel,
+                      const float* gscale /* device scalar d(out)/d(loss), or NULL = 1 */, float* dpred,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-buffer entry points (what a non-PyTorch caller binds; also bench.py's e2e leg): pinned or pageable HOST
+ * pointers in, HOST pointers out; H2D, compute and D2H are all enqueued on `stream`, then the stream is synchronised.
+ * `dev_scratch` is a caller-owned DEVICE buffer of at least *_scratch_bytes.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* debug/bring-up knobs of the tcgen05 path (tests only). field: 0=LBO enc, 1=SBO enc, 2=version, 3=layout type */
+int a2f_debug_set_umma_field(int field, unsigned value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A2F_H_ */
