@@ -67,6 +67,28 @@ __global__ void posconv_pack_kernel(const float* __restrict__ gw, const float* _
     }
 }
 
+// Error-compensated bf16 split of an fp32 matrix for the tensor-core vertex head:
+//   x = hi + lo (+ O(2^-17 |x|)),  hi = bf16(x), lo = bf16(x - hi)
+// activations are laid out [hi | lo | hi], weights [hi | hi | lo], so that one K=3k bf16 GEMM evaluates
+// a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  (everything but the lo*lo term) with fp32 accumulation.
+__global__ void split_bf16x3_kernel(const float* __restrict__ in, long long ld_in, bf16* __restrict__ out, long long rows,
+                                    int K, int is_weight) {
+    const long long n = rows * K;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const long long r = i / K;
+        const int k = (int)(i - r * K);
+        const float x = in[r * ld_in + k];
+        const bf16 hi = __float2bfloat16_rn(x);
+        const bf16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+        bf16* o = out + r * 3 * K;
+        o[k] = hi;
+        o[K + k] = is_weight ? hi : lo;
+        o[2 * K + k] = is_weight ? lo : hi;
+    }
+}
+
 static int fill_params(const a2f_gemm_args* a, GemmParams* p) {
     A2F_REQUIRE(a != nullptr, "a2f_gemm: args is NULL");
     A2F_REQUIRE(a->M >= 0 && a->N >= 0 && a->K > 0, "a2f_gemm: bad M/N/K");
@@ -172,6 +194,18 @@ int a2f_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream) 
     const int grid = (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256);
     cast_f32_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, static_cast<bf16*>(out), n);
     A2F_CHECK_LAUNCH("cast_f32_bf16_kernel");
+    count_launch();
+    return A2F_OK;
+}
+int a2f_split_bf16x3(const float* in, long long ld_in, void* out, long long rows, int K, int is_weight, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(in && out && rows >= 0 && K > 0 && ld_in >= K, "a2f_split_bf16x3: bad arguments");
+    if (rows == 0) return A2F_OK;
+    const long long n = rows * K;
+    const int grid = (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256);
+    split_bf16x3_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, ld_in, static_cast<bf16*>(out), rows, K, is_weight);
+    A2F_CHECK_LAUNCH("split_bf16x3_kernel");
     count_launch();
     return A2F_OK;
 }

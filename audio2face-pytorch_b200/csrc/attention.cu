@@ -1,0 +1,292 @@
+// Encoder self-attention of wav2vec2 (HF modeling_wav2vec2.py:438-549): softmax(Q K^T * scale) V per (batch, head),
+// no mask, head_dim 64.  The reference materialises and returns the [B,12,T,T] probabilities of all 12 layers
+// (ref:src/model/wav2vec.py:101 forces output_attentions=True) although nothing reads them
+// (ref:src/model/faceformer.py:149-151 keeps only last_hidden_state); here the probabilities never leave the SM.
+//
+//   fp32  : SIMT online-softmax kernel, one warp per query row (the 1e-5 parity path)
+//   bf16  : flash-style kernel on mma.sync.m16n8k16 bf16 tensor-core tiles, 64 queries x 64 keys per step,
+//           K/V tiles streamed through shared memory with cp.async double buffering, fp32 softmax statistics.
+//           (A tcgen05/TMEM version of this kernel is the planned replacement; at T=300 attention is 4% of the
+//            encoder FLOPs, SURVEY.md App. C.)
+#include "a2f_common.cuh"
+
+namespace a2f {
+
+// ------------------------------------------------------------------------------------------------ fp32 SIMT
+// qkv: [B,T,3*H*64] fp32.  One warp per (b,h,query).  Lane l scores keys j = j0+l; output dims (2l, 2l+1).
+__global__ void __launch_bounds__(256) mha_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int B,
+                                                      int T, int H, float scale) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total = B * H * T;
+    if (warp_global >= total) return;
+    const int t = warp_global % T;
+    const int h = (warp_global / T) % H;
+    const int b = warp_global / (T * H);
+    const int ld = 3 * H * 64;
+    const float* base = qkv + (long long)b * T * ld;
+    const float* qp = base + (long long)t * ld + h * 64;
+    float q[64];
+#pragma unroll
+    for (int d = 0; d < 64; d += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(qp + d);
+        q[d] = f.x; q[d + 1] = f.y; q[d + 2] = f.z; q[d + 3] = f.w;
+    }
+    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int j0 = 0; j0 < T; j0 += 32) {
+        const int j = j0 + lane;
+        float s = -INFINITY;
+        if (j < T) {
+            const float* kp = base + (long long)j * ld + H * 64 + h * 64;
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < 64; d += 4) {
+                const float4 f = *reinterpret_cast<const float4*>(kp + d);
+                acc = fmaf(q[d], f.x, acc);
+                acc = fmaf(q[d + 1], f.y, acc);
+                acc = fmaf(q[d + 2], f.z, acc);
+                acc = fmaf(q[d + 3], f.w, acc);
+            }
+            s = acc * scale;
+        }
+        const float m_new = fmaxf(m, warp_max(s));
+        const float corr = __expf(m - m_new);      // first chunk: exp(-inf) = 0
+        const float pj = (j < T) ? __expf(s - m_new) : 0.f;
+        l = l * corr + warp_sum(pj);
+        o0 *= corr;
+        o1 *= corr;
+        const int nj = min(32, T - j0);
+        for (int jj = 0; jj < nj; ++jj) {
+            const float pv = __shfl_sync(0xffffffffu, pj, jj);
+            const float2 vv = *reinterpret_cast<const float2*>(base + (long long)(j0 + jj) * ld + 2 * H * 64 + h * 64 + 2 * lane);
+            o0 = fmaf(pv, vv.x, o0);
+            o1 = fmaf(pv, vv.y, o1);
+        }
+        m = m_new;
+    }
+    const float inv = 1.f / l;
+    float* op = out + ((long long)b * T + t) * (H * 64) + h * 64 + 2 * lane;
+    *reinterpret_cast<float2*>(op) = make_float2(o0 * inv, o1 * inv);
+}
+
+// ------------------------------------------------------------------------------------------------ bf16 tensor-core
+constexpr int FA_BM = 64;      // queries per CTA (4 warps x 16 rows)
+constexpr int FA_BN = 64;      // keys per step
+constexpr int FA_D = 64;
+constexpr int FA_LD = 72;      // padded smem row (bf16 elements): 144-byte pitch -> conflict-free ldmatrix
+
+A2F_D void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(smem_u32(p)));
+}
+A2F_D void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(smem_u32(p)));
+}
+A2F_D void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+A2F_D void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+    const int sz = valid ? 16 : 0;     // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+A2F_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> A2F_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// grid: (ceil(T/64), H, B); 128 threads.
+__global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T,
+                                                       int H, float scale_log2) {
+    __shared__ __align__(16) bf16 sQ[FA_BM * FA_LD];
+    __shared__ __align__(16) bf16 sK[2][FA_BN * FA_LD];
+    __shared__ __align__(16) bf16 sV[2][FA_BN * FA_LD];
+
+    const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ld = 3 * H * FA_D;
+    const bf16* base = qkv + (long long)b * T * ld;
+    const bf16* gQ = base + h * FA_D;
+    const bf16* gK = base + H * FA_D + h * FA_D;
+    const bf16* gV = base + 2 * H * FA_D + h * FA_D;
+
+    // 64 rows x 64 cols bf16 = 512 chunks of 16 B; 128 threads x 4
+    auto load_tile = [&](bf16* dst, const bf16* src, int row0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = threadIdx.x + i * 128;
+            const int r = idx >> 3, c = (idx & 7) * 8;
+            const bool ok = (row0 + r) < T;
+            cp_async_16(dst + r * FA_LD + c, src + (long long)(ok ? row0 + r : 0) * ld + c, ok);
+        }
+    };
+
+    load_tile(sQ, gQ, q0);
+    load_tile(sK[0], gK, 0);
+    load_tile(sV[0], gV, 0);
+    cp_async_commit();
+
+    const int ntiles = (T + FA_BN - 1) / FA_BN;
+    uint32_t qf[4][4];                 // Q fragments: 4 k-steps (16 dims each)
+    float o[8][4];                     // 16 x 64 output accumulator: 8 n-tiles
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+    for (int it = 0; it < ntiles; ++it) {
+        const int cur = it & 1;
+        if (it + 1 < ntiles) {
+            load_tile(sK[cur ^ 1], gK, (it + 1) * FA_BN);
+            load_tile(sV[cur ^ 1], gV, (it + 1) * FA_BN);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (it == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = ks * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sQ + r * FA_LD + c);
+            }
+        }
+        // S = Q K^T : 16 x 64 per warp
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {     // pairs of 8-key n-tiles
+                uint32_t b0, b1, b2, b3;
+                // matrices: (keys np*16+0..7, d ks*16+0..7), (same keys, d +8), (keys +8, d), (keys +8, d +8)
+                const int r = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+                ldmatrix_x4(b0, b1, b2, b3, sK[cur] + r * FA_LD + c);
+                mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+            }
+        }
+        // mask keys beyond T (last tile only) and online softmax; rows g = lane/4 and g+8
+        const int key0 = it * FA_BN;
+        if (key0 + FA_BN > T) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int kc = key0 + nt * 8 + (lane & 3) * 2;
+                if (kc >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+                if (kc + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+            }
+        }
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        }
+        float corr[2], msc[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            corr[r] = exp2f((m_run[r] - m_new) * scale_log2);
+            m_run[r] = m_new;
+            msc[r] = m_new * scale_log2;
+        }
+        float rs[2] = {0.f, 0.f};
+        uint32_t pf[4][4];                 // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p0 = exp2f(fmaf(s[nt][0], scale_log2, -msc[0]));
+            const float p1 = exp2f(fmaf(s[nt][1], scale_log2, -msc[0]));
+            const float p2 = exp2f(fmaf(s[nt][2], scale_log2, -msc[1]));
+            const float p3 = exp2f(fmaf(s[nt][3], scale_log2, -msc[1]));
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            const int ks = nt >> 1, hi = nt & 1;
+            pf[ks][hi * 2 + 0] = pack_bf16x2(p0, p1);
+            pf[ks][hi * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            o[nt][0] *= corr[0]; o[nt][1] *= corr[0];
+            o[nt][2] *= corr[1]; o[nt][3] *= corr[1];
+        }
+        // O += P V : B fragments of V (k = key, n = d) through ldmatrix.trans on the row-major [key][d] tile
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {    // pairs of 8-wide d tiles
+                uint32_t b0, b1, b2, b3;
+                // matrices: (keys ks*16+0..7, d dp*16+0..7), (keys +8, same d), (keys, d +8), (keys +8, d +8)
+                const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = dp * 16 + (lane >> 4) * 8;
+                ldmatrix_x4_trans(b0, b1, b2, b3, sV[cur] + r * FA_LD + c);
+                mma_bf16_16816(o[2 * dp], pf[ks], b0, b1);
+                mma_bf16_16816(o[2 * dp + 1], pf[ks], b2, b3);
+            }
+        }
+        __syncthreads();     // everyone is done with buffer `cur` before it is refilled two iterations later
+    }
+
+    // finalise: row sums across the 4 lanes of a quad, normalise, store bf16
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const int row0 = q0 + warp * 16 + (lane >> 2);
+    const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+    bf16* ob = out + (long long)b * T * (H * FA_D) + h * FA_D;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + (lane & 3) * 2;
+        if (row0 < T)
+            *reinterpret_cast<uint32_t*>(ob + (long long)row0 * (H * FA_D) + c) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+        if (row0 + 8 < T)
+            *reinterpret_cast<uint32_t*>(ob + (long long)(row0 + 8) * (H * FA_D) + c) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+}
+
+}  // namespace a2f
+
+using namespace a2f;
+
+extern "C" int a2f_mha_fwd(const void* qkv, void* out, int dtype, int B, int T, int H, int D, float scale,
+                           void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, "a2f_mha_fwd: bad arguments");
+    A2F_REQUIRE(D == 64, "a2f_mha_fwd: head_dim must be 64");
+    cudaStream_t s = as_stream(stream);
+    if (dtype == A2F_F32) {
+        const long long warps = (long long)B * H * T;
+        const int grid = (int)((warps * 32 + 255) / 256);
+        mha_f32_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(qkv), static_cast<float*>(out), B, T, H, scale);
+        A2F_CHECK_LAUNCH("mha_f32_kernel");
+    } else if (dtype == A2F_BF16) {
+        A2F_REQUIRE(reinterpret_cast<uintptr_t>(qkv) % 16 == 0, "a2f_mha_fwd: qkv must be 16-byte aligned");
+        const dim3 grid((T + FA_BM - 1) / FA_BM, H, B);
+        mha_bf16_kernel<<<grid, 128, 0, s>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), T, H,
+                                              scale * 1.4426950408889634f);
+        A2F_CHECK_LAUNCH("mha_bf16_kernel");
+    } else {
+        return set_error(A2F_EINVAL, "a2f_mha_fwd: bad dtype");
+    }
+    count_launch();
+    return A2F_OK;
+}

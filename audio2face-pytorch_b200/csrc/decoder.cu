@@ -1,0 +1,356 @@
+// FaceFormer's autoregressive decoder (ref:src/model/faceformer.py:154-185) as one persistent kernel.
+//
+// The reference re-runs nn.TransformerDecoder on the whole prefix (and the 64->15069 head on the whole prefix) for
+// every new frame, uploading a fresh [4,t,t] bias mask and a python-built [t,T] memory mask each step.  In eval mode
+// this is mathematically a KV-cached decode (causal self-attention => token i only depends on e_0..e_i), and the
+// diagonal memory mask (ref:faceformer.py:58-66, dataset "vocaset") leaves one visible key per query so that
+// cross-attention collapses to  out_proj(v_proj(memory_i))  -- computed for all frames up front by two small GEMMs.
+//
+// One CTA per utterance, 512 threads.  Every thread keeps one 64-wide weight row slice in REGISTERS for the whole
+// rollout (50k parameters live in the register file, none are re-read from memory inside the T-step loop):
+//   tid   0..191  self-attn in_proj rows (q | k | v)          tid 192..255  self-attn out_proj rows
+//   tid 256..383  linear1 rows (ffn 64->128, ReLU)            tid 384..511  linear2 rows, two 64-wide halves per row
+// The 64x64 feedback matrix Wc = vertice_map.weight @ vertice_map_r.weight (a2f_pack_feedback) sits transposed in
+// shared memory and is applied by threads 192..255.
+// K/V cache rows live in shared memory (padded to 68 floats: conflict-free float4 reads) when T <= 384, otherwise in
+// the L2-resident workspace.  The temporal bias -2^{-2(h+1)} * floor((i-j)/period) (ref:faceformer.py:22-54) and the
+// periodic positional encoding row (i mod period) (ref:faceformer.py:70-88) are generated from indices.
+#include "a2f_common.cuh"
+#include "gemm_params.cuh"
+
+namespace a2f {
+
+constexpr int DEC_THREADS = 512;
+constexpr int KV_LD = 68;
+constexpr int DEC_SMEM_T = 360;     // longest clip whose K/V cache fits in shared memory
+
+struct DecW {
+    const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b;
+    const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b, *fb_w, *fb_b, *obj_w, *pe;
+};
+
+A2F_D float dot64_smem(const float* w, const float* __restrict__ x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 64; k += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(x + k);
+        acc = fmaf(w[k], f.x, acc);
+        acc = fmaf(w[k + 1], f.y, acc);
+        acc = fmaf(w[k + 2], f.z, acc);
+        acc = fmaf(w[k + 3], f.w, acc);
+    }
+    return acc;
+}
+
+// LayerNorm(64) of the vector whose elements (lane, lane+32) this warp's lanes hold; eps 1e-5, biased variance.
+A2F_D void warp_ln64(float& a, float& b, float g0, float g1, float b0, float b1) {
+    const float mean = warp_sum(a + b) * (1.f / 64.f);
+    const float da = a - mean, db = b - mean;
+    const float var = warp_sum(da * da + db * db) * (1.f / 64.f);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    a = da * rstd * g0 + b0;
+    b = db * rstd * g1 + b1;
+}
+
+__global__ void __launch_bounds__(DEC_THREADS, 1)
+decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-attn vectors*/,
+                       const float* __restrict__ one_hot, int n_onehot, int period, float* __restrict__ D, int T,
+                       float* __restrict__ kv_global /* [B][2][T][KV_LD] or NULL */) {
+    extern __shared__ __align__(16) float dsm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x;
+    const int Tpad = (T + 3) & ~3;
+
+    // ---- shared memory carve-up ----
+    float* xs = dsm;                 // [64]  decoder input of the current step (e_i + pe)
+    float* qs = xs + 64;             // [64]  scaled query
+    float* os = qs + 64;             // [64]  attention output (heads concatenated)
+    float* ys = os + 64;             // [64]  x + self_attn (pre-LN1)
+    float* x2 = ys + 64;             // [4][64] per-FFN1-warp copies of LN2 output
+    float* f1 = x2 + 256;            // [128] relu(linear1)
+    float* y3 = f1 + 128;            // [64]  pre-LN3
+    float* dcp = y3 + 64;            // [2][64] per-feedback-warp copies of d_i
+    float* style = dcp + 128;        // [64]
+    float* red = style + 64;         // [4][8] group reductions (max, sum) ; [4][4][16] PV partials after it
+    float* pvp = red + 32;           // [4][4][16]
+    float* wct = pvp + 256;          // [64][64] feedback matrix transposed: wct[k*64+r] = Wc[r][k]
+    float* sc = wct + 4096;          // [4][Tpad] scores / probabilities
+    float* Kc;
+    float* Vc;
+    if (kv_global) {
+        Kc = kv_global + (long long)b * 2 * T * KV_LD;
+        Vc = Kc + (long long)T * KV_LD;
+    } else {
+        Kc = sc + 4 * Tpad;
+        Vc = Kc + (long long)T * KV_LD;
+    }
+
+    // ---- weights into registers ----
+    float wr[64];
+    float bias_r = 0.f;
+    {
+        const float* src;
+        if (tid < 192) { src = w.sa_in_w + tid * 64; bias_r = w.sa_in_b[tid]; }
+        else if (tid < 256) { src = w.sa_out_w + (tid - 192) * 64; bias_r = w.sa_out_b[tid - 192]; }
+        else if (tid < 384) { src = w.lin1_w + (tid - 256) * 64; bias_r = w.lin1_b[tid - 256]; }
+        else {
+            const int u = tid - 384, row = u >> 1, half = u & 1;
+            src = w.lin2_w + row * 128 + half * 64;
+            bias_r = half == 0 ? w.lin2_b[row] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 64; k += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(src + k);
+            wr[k] = f.x; wr[k + 1] = f.y; wr[k + 2] = f.z; wr[k + 3] = f.w;
+        }
+    }
+    // feedback matrix (a2f_pack_feedback) transposed into shared memory; its rows are applied by threads 192..255
+    for (int idx = tid; idx < 4096; idx += DEC_THREADS) wct[(idx & 63) * 64 + (idx >> 6)] = w.fb_w[idx];
+    const float fb_bias = (tid >= 192 && tid < 256) ? w.fb_b[tid - 192] : 0.f;
+    // style embedding: obj_vector(one_hot), no bias (ref:faceformer.py:131,148); token 0 = style
+    if (tid < 64) {
+        float acc = 0.f;
+        for (int k = 0; k < n_onehot; ++k) acc = fmaf(w.obj_w[tid * n_onehot + k], one_hot[(long long)b * n_onehot + k], acc);
+        style[tid] = acc;
+        xs[tid] = acc + w.pe[tid];       // position 0
+    }
+    __syncthreads();
+
+    const float* ca_b = ca + (long long)b * T * 64;
+    float* D_b = D + (long long)b * T * 64;
+
+    // loop-invariant LayerNorm parameters of the lanes that apply them (norm1/norm2: FFN1 warps, norm3: feedback warps)
+    float lnA[4] = {0.f, 0.f, 0.f, 0.f}, lnB[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tid >= 256 && tid < 384) {
+        lnA[0] = w.n1_w[lane]; lnA[1] = w.n1_w[lane + 32]; lnA[2] = w.n1_b[lane]; lnA[3] = w.n1_b[lane + 32];
+        lnB[0] = w.n2_w[lane]; lnB[1] = w.n2_w[lane + 32]; lnB[2] = w.n2_b[lane]; lnB[3] = w.n2_b[lane + 32];
+    } else if (tid >= 192 && tid < 256) {
+        lnA[0] = w.n3_w[lane]; lnA[1] = w.n3_w[lane + 32]; lnA[2] = w.n3_b[lane]; lnA[3] = w.n3_b[lane + 32];
+    }
+
+    for (int i = 0; i < T; ++i) {
+        // prefetch this step's global operands so that their latency hides behind phases 1-3
+        float pre0 = 0.f, pre1 = 0.f;
+        if (tid >= 256 && tid < 384) {
+            pre0 = __ldg(ca_b + (long long)i * 64 + lane);
+            pre1 = __ldg(ca_b + (long long)i * 64 + lane + 32);
+        } else if (tid >= 192 && tid < 256) {
+            pre0 = __ldg(w.pe + ((i + 1) % period) * 64 + (tid - 192));
+        }
+        // ---------- phase 1: q, k, v of the new token ----------
+        if (tid < 192) {
+            const float acc = bias_r + dot64_smem(wr, xs);
+            if (tid < 64) qs[tid] = acc * 0.25f;                  // 1/sqrt(head_dim 16), exact power of two
+            else if (tid < 128) Kc[(long long)i * KV_LD + (tid - 64)] = acc;
+            else Vc[(long long)i * KV_LD + (tid - 128)] = acc;
+        }
+        __syncthreads();
+
+        // ---------- phase 2: biased causal attention over keys 0..i (threads 0..511, 128 per head) ----------
+        if (tid < 512) {
+            const int h = tid >> 7, u = tid & 127, wq = (tid >> 5) & 3;
+            const float slope = (h == 0) ? 0.25f : (h == 1) ? 0.0625f : (h == 2) ? 0.015625f : 0.00390625f;
+            float qh[16];
+#pragma unroll
+            for (int d = 0; d < 16; d += 4) {
+                const float4 f = *reinterpret_cast<const float4*>(qs + h * 16 + d);
+                qh[d] = f.x; qh[d + 1] = f.y; qh[d + 2] = f.z; qh[d + 3] = f.w;
+            }
+            float* sch = sc + h * Tpad;
+            float lmax = -INFINITY;
+            for (int j = u; j <= i; j += 128) {
+                const float* kp = Kc + (long long)j * KV_LD + h * 16;
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < 16; d += 4) {
+                    const float4 f = *reinterpret_cast<const float4*>(kp + d);
+                    acc = fmaf(qh[d], f.x, acc);
+                    acc = fmaf(qh[d + 1], f.y, acc);
+                    acc = fmaf(qh[d + 2], f.z, acc);
+                    acc = fmaf(qh[d + 3], f.w, acc);
+                }
+                const float s = acc - slope * (float)((i - j) / period);
+                sch[j] = s;
+                lmax = fmaxf(lmax, s);
+            }
+            lmax = warp_max(lmax);
+            if (lane == 0) red[h * 8 + wq] = lmax;
+            named_bar_sync(1 + h, 128);
+            const float m = fmaxf(fmaxf(red[h * 8], red[h * 8 + 1]), fmaxf(red[h * 8 + 2], red[h * 8 + 3]));
+            float lsum = 0.f;
+            for (int j = u; j <= i; j += 128) {
+                const float pj = expf(sch[j] - m);
+                sch[j] = pj;
+                lsum += pj;
+            }
+            lsum = warp_sum(lsum);
+            if (lane == 0) red[h * 8 + 4 + wq] = lsum;
+            named_bar_sync(1 + h, 128);
+            const float l = (red[h * 8 + 4] + red[h * 8 + 5]) + (red[h * 8 + 6] + red[h * 8 + 7]);
+            // P V: thread (jg, d) accumulates keys j = jg (mod 8)
+            const int d = u & 15, jg = u >> 4;
+            float acc = 0.f;
+            for (int j = jg; j <= i; j += 8) acc = fmaf(sch[j], Vc[(long long)j * KV_LD + h * 16 + d], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (lane < 16) pvp[(h * 4 + wq) * 16 + lane] = acc;
+            named_bar_sync(1 + h, 128);
+            if (u < 16) {
+                const float* pp = pvp + h * 64 + u;
+                os[h * 16 + u] = ((pp[0] + pp[16]) + (pp[32] + pp[48])) / l;
+            }
+        }
+        __syncthreads();
+
+        // ---------- phase 3: self-attn out_proj + residual ----------
+        if (tid >= 192 && tid < 256) {
+            const int r = tid - 192;
+            ys[r] = xs[r] + (bias_r + dot64_smem(wr, os));
+        }
+        __syncthreads();
+
+        // ---------- phase 4: LN1, + cross-attention vector, LN2 (each FFN1 warp redundantly), linear1 + ReLU ----------
+        if (tid >= 256 && tid < 384) {
+            const int wl = warp - 8;
+            float a = ys[lane], c = ys[lane + 32];
+            warp_ln64(a, c, lnA[0], lnA[1], lnA[2], lnA[3]);
+            a += pre0;
+            c += pre1;
+            warp_ln64(a, c, lnB[0], lnB[1], lnB[2], lnB[3]);
+            float* xc = x2 + wl * 64;
+            xc[lane] = a;
+            xc[lane + 32] = c;
+            __syncwarp();
+            f1[tid - 256] = relu(bias_r + dot64_smem(wr, xc));
+        }
+        __syncthreads();
+
+        // ---------- phase 5: linear2 (two half-rows per output) + residual ----------
+        if (tid >= 384 && tid < 512) {
+            const int u = tid - 384, row = u >> 1, half = u & 1;
+            float part = bias_r + dot64_smem(wr, f1 + half * 64);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            if (half == 0) y3[row] = x2[row] + part;
+        }
+        __syncthreads();
+
+        // ---------- phase 6: LN3 -> d_i (each feedback warp redundantly), store, feedback to the next input ----------
+        if (tid >= 192 && tid < 256) {
+            const int wl = warp - 6;
+            float a = y3[lane], c = y3[lane + 32];
+            warp_ln64(a, c, lnA[0], lnA[1], lnA[2], lnA[3]);
+            float* dc = dcp + wl * 64;
+            dc[lane] = a;
+            dc[lane + 32] = c;
+            if (wl == 0) {
+                D_b[(long long)i * 64 + lane] = a;
+                D_b[(long long)i * 64 + lane + 32] = c;
+            }
+            __syncwarp();
+            const int r = tid - 192;
+            float acc = 0.f;
+#pragma unroll 16
+            for (int k = 0; k < 64; ++k) acc = fmaf(wct[k * 64 + r], dc[k], acc);
+            const float e = (fb_bias + acc) + style[r];
+            xs[r] = e + pre0;
+        }
+        __syncthreads();
+    }
+}
+
+// Wc = Wm @ Wr ([64,V3] @ [V3,64]) and bc = Wm @ br + bm, fp64 accumulation.  One CTA per output row of Wc.
+__global__ void __launch_bounds__(256) pack_feedback_kernel(const float* __restrict__ vm_w, const float* __restrict__ vm_b,
+                                                            const float* __restrict__ vmr_w,
+                                                            const float* __restrict__ vmr_b, int V3,
+                                                            float* __restrict__ Wc, float* __restrict__ bc) {
+    const int r = blockIdx.x;                  // row of Wc
+    const int c = threadIdx.x & 63, part = threadIdx.x >> 6;   // 4 partial sums per column
+    __shared__ double sh[4][65];
+    double acc = 0.0, accb = 0.0;
+    for (int v = part; v < V3; v += 4) {
+        const double a = (double)vm_w[(long long)r * V3 + v];
+        acc += a * (double)vmr_w[(long long)v * 64 + c];
+        if (c == 0) accb += a * (double)vmr_b[v];
+    }
+    sh[part][c] = acc;
+    if (c == 0) sh[part][64] = accb;
+    __syncthreads();
+    if (threadIdx.x < 64) Wc[r * 64 + c] = (float)((sh[0][c] + sh[1][c]) + (sh[2][c] + sh[3][c]));
+    if (threadIdx.x == 64) bc[r] = (float)(((sh[0][64] + sh[1][64]) + (sh[2][64] + sh[3][64])) + (double)vm_b[r]);
+}
+
+static size_t dec_smem_bytes(int T, bool kv_in_smem) {
+    const int Tpad = (T + 3) & ~3;
+    size_t fl = 64 * 4 + 256 + 128 + 64 + 128 + 64 + 32 + 256 + 4096 + (size_t)4 * Tpad;
+    if (kv_in_smem) fl += (size_t)2 * T * KV_LD;
+    return fl * sizeof(float);
+}
+
+}  // namespace a2f
+
+using namespace a2f;
+
+extern "C" {
+
+size_t a2f_decoder_workspace_bytes(int B, int T) {
+    if (B <= 0 || T <= 0) return 0;
+    size_t n = (size_t)2 * B * T * 64;                        // v_proj(mem), cross-attn vectors
+    if (T > DEC_SMEM_T) n += (size_t)2 * B * T * KV_LD;       // K/V cache
+    return n * sizeof(float);
+}
+
+int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
+                        int period, float* D, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(w && memory && one_hot && D && workspace, "a2f_decoder_rollout: NULL argument");
+    A2F_REQUIRE(B > 0 && T > 0 && n_onehot > 0 && period > 0, "a2f_decoder_rollout: bad sizes");
+    A2F_REQUIRE(T <= 8192, "a2f_decoder_rollout: T above 8192 frames is not supported");
+    A2F_REQUIRE(workspace_bytes >= a2f_decoder_workspace_bytes(B, T), "a2f_decoder_rollout: workspace too small");
+    A2F_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "a2f_decoder_rollout: workspace must be 16-byte aligned");
+    const void* all[] = {w->sa_in_w, w->sa_in_b, w->sa_out_w, w->sa_out_b, w->ca_in_w, w->ca_in_b, w->ca_out_w, w->ca_out_b,
+                         w->lin1_w, w->lin1_b, w->lin2_w, w->lin2_b, w->n1_w, w->n1_b, w->n2_w, w->n2_b, w->n3_w, w->n3_b,
+                         w->fb_w, w->fb_b, w->obj_w, w->pe};
+    for (const void* p : all) A2F_REQUIRE(p != nullptr, "a2f_decoder_rollout: NULL weight pointer");
+    cudaStream_t s = as_stream(stream);
+    float* tmp = static_cast<float*>(workspace);
+    float* ca = tmp + (size_t)B * T * 64;
+    float* kv = (T > DEC_SMEM_T) ? ca + (size_t)B * T * 64 : nullptr;
+
+    // cross-attention with the diagonal memory mask: ca_t = out_proj(v_proj(memory_t))   
+    GemmParams g;
+    g.M = B * T; g.N = 64; g.K = 64;
+    g.A = memory; g.a_row_stride = 64; g.a_batch_stride = 0; g.rows_per_batch = B * T;
+    g.W = w->ca_in_w + 128 * 64; g.ldw = 64; g.bias = w->ca_in_b + 128; g.act = A2F_ACT_NONE;
+    g.resid = nullptr; g.resid_bf16 = 0; g.ldr = 0; g.tmpl = nullptr; g.rows_per_tmpl = 1;
+    g.C = tmp; g.ldc = 64;
+    rc = gemm_simt(g, 0, 0, s);
+    if (rc != A2F_OK) return rc;
+    g.A = tmp; g.W = w->ca_out_w; g.bias = w->ca_out_b; g.C = ca;
+    rc = gemm_simt(g, 0, 0, s);
+    if (rc != A2F_OK) return rc;
+
+    DecW dw;
+    dw.sa_in_w = w->sa_in_w; dw.sa_in_b = w->sa_in_b; dw.sa_out_w = w->sa_out_w; dw.sa_out_b = w->sa_out_b;
+    dw.lin1_w = w->lin1_w; dw.lin1_b = w->lin1_b; dw.lin2_w = w->lin2_w; dw.lin2_b = w->lin2_b;
+    dw.n1_w = w->n1_w; dw.n1_b = w->n1_b; dw.n2_w = w->n2_w; dw.n2_b = w->n2_b; dw.n3_w = w->n3_w; dw.n3_b = w->n3_b;
+    dw.fb_w = w->fb_w; dw.fb_b = w->fb_b; dw.obj_w = w->obj_w; dw.pe = w->pe;
+    const size_t smem = dec_smem_bytes(T, kv == nullptr);
+    A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    decoder_rollout_kernel<<<B, DEC_THREADS, smem, s>>>(dw, ca, one_hot, n_onehot, period, D, T, kv);
+    A2F_CHECK_LAUNCH("decoder_rollout_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, const float* vmr_b, int V3, float* Wc,
+                      float* bc, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(vm_w && vm_b && vmr_w && vmr_b && Wc && bc && V3 > 0, "a2f_pack_feedback: bad arguments");
+    pack_feedback_kernel<<<64, 256, 0, as_stream(stream)>>>(vm_w, vm_b, vmr_w, vmr_b, V3, Wc, bc);
+    A2F_CHECK_LAUNCH("pack_feedback_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+}  // extern "C"

@@ -1,13 +1,19 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a: C = act(A W^T + bias) + resid + tmpl, bf16 operands, fp32 accumulate.
 //
-// Persistent, warp-specialised, one CTA per SM:
+// Persistent, warp-specialised, one CTA per SM (320 threads):
 //   warp 0      TMA producer   (cp.async.bulk.tensor into a STAGES-deep 128B-swizzled smem ring)
-//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, accumulators double-buffered in TMEM)
-//   warps 2..5  epilogue       (tcgen05.ld -> bias/act/residual/template -> global), overlaps the next tile's mainloop
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma; accumulators double-buffered in TMEM)
+//   warps 2..9  epilogue       (tcgen05.ld -> bias/act/residual -> smem -> global), overlaps the next tile's mainloop;
+//                               warp%4 selects the TMEM lane quarter, (warp-2)/4 the column half of the tile
+// Two epilogue flavours:
+//   TMA store   16-byte-aligned outputs: results are staged in 128B-swizzled smem blocks and written with
+//               cp.async.bulk.tensor stores (full-line writes, ragged M/N edges clipped by the tensor map)
+//   scalar      the 15069-wide vertex head (rows only 4-byte aligned) and the template-add epilogue: 32x32
+//               transposes through smem so that each warp store covers 32 consecutive floats of one row.
 // A is addressed through <=3-D tensor maps so that the same mainloop serves
 //   mode 0: plain [M,K] matrices and the stride-2 Conv1d stack as an implicit GEMM over channels-last activations
-//           (rows of the im2col matrix are strided/overlapping views of the activation, split into K segments so that
-//            every tensor map has non-overlapping rows),
+//           (rows of the im2col matrix are strided views of the activation, split into K segments so that every
+//            tensor map has non-overlapping rows),
 //   mode 2: the k=128 grouped positional conv (K block = one tap, A box shifted by one time step per block).
 #include "a2f_common.cuh"
 #include "gemm_params.cuh"
@@ -17,20 +23,23 @@ namespace a2f {
 constexpr int TBM = 128;          // tile rows (UMMA M)
 constexpr int TBK = 64;           // K per stage: 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 constexpr int A_STAGE_BYTES = TBM * TBK * 2;
 constexpr int MAX_SEGS = 4;
+constexpr int EPI_STAGE_BYTES = 16384;   // one 128-row x 128-byte store block (or 4 warps x 32x32 fp32 transposes)
 
 struct TmapSet {
     CUtensorMap a[MAX_SEGS];
     CUtensorMap b;
+    CUtensorMap c;
 };
 
 struct TcParams {
     GemmParams g;
     int mode;
     int tiles_m_per_batch, num_batches, tiles_n, num_k_blocks, kb_per_seg;
-    int vec_ok;                     // 16-byte vector epilogue stores/loads are legal
+    int resid_vec_ok;               // 16-byte vector residual loads are legal
+    int fast_gelu;                  // bf16 output: A-S erf approximation instead of erff
     uint32_t lbo_enc, sbo_enc, desc_version, desc_layout;
 };
 
@@ -43,32 +52,31 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, const TcParam
            ((uint64_t)(p.desc_layout & 7u) << 61);
 }
 
-template <int BN> struct TcCfg {
-    static constexpr int CH = (BN % 32 == 0) ? 32 : 16;             // epilogue column chunk
+template <int BN, typename TC> struct TcCfg {
     static constexpr int ACC_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static constexpr int B_STAGE_BYTES = BN * TBK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128) ? 6 : 8;
-    static constexpr int EPI_STAGE_FLOATS = 4 * 32 * 33;            // per-warp transpose buffers (staged epilogue)
-    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
-                                         EPI_STAGE_FLOATS * 4 + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+    // TMA-store block width (columns): 128 bytes of output per row, except for the 48-wide posconv tiles
+    static constexpr int SBW = (BN % 32 != 0) ? ((sizeof(TC) == 2) ? BN : 16) : (int)(128 / sizeof(TC));
+    static constexpr int NBLK = BN / SBW;
+    static constexpr int ROW_PITCH = SBW * (int)sizeof(TC);
+    static constexpr bool SWZ = (ROW_PITCH == 128);
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 2 * EPI_STAGE_BYTES + 256 /*barriers*/;
 };
 
-template <int BN, typename TC, bool STAGED>
+template <int BN, typename TC, bool SCALAR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, TC>;
     constexpr int STAGES = Cfg::STAGES;
-    constexpr int CH = Cfg::CH;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)STAGES * A_STAGE_BYTES;
-    float* sEpi = reinterpret_cast<float*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
-    float* sBias = sEpi + Cfg::EPI_STAGE_FLOATS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
+    uint8_t* sEpi = smem + (size_t)STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 2 * EPI_STAGE_BYTES);
     uint64_t* full_bar = bars;                 // [STAGES]
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -78,9 +86,11 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GemmParams& g = p.g;
 
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B needs 1024-byte alignment
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b);
+        if (!SCALAR) tma_prefetch_desc(&maps.c);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -89,7 +99,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], 8);
         }
         fence_mbar_init();
     }
@@ -163,10 +173,13 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (4 warps, TMEM lane quarter = warp % 4) =====================
-        const int q = warp & 3;
-        const int epi_tid = threadIdx.x - 64;     // 0..127
-        float* stg = sEpi + (warp - 2) * (32 * 33);
+        // ===================== epilogue: 8 warps =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = ew >> 2;          // column half of the tile
+        const bool leader = ((ew & 3) == 0) && lane == 0;
+        const int bar_id = 1 + half;
+        uint8_t* stage_buf = sEpi + half * EPI_STAGE_BYTES;
         int acc = 0;
         uint32_t acc_phase = 0;
         TC* __restrict__ C = static_cast<TC*>(g.C);
@@ -175,115 +188,156 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
             const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
             const int n_tile0 = (p.mode == 2) ? nb * 48 : nb * BN;          // first global column of this tile
             const int n_lim = (p.mode == 2) ? 48 : min(BN, g.N - n_tile0);   // live columns in this tile
-            // stage the bias slice for this tile (double-buffered with the accumulator index)
-            float* bias_s = sBias + acc * BN;
-            for (int i = epi_tid; i < BN; i += 128)
-                bias_s[i] = (g.bias != nullptr && i < n_lim) ? g.bias[n_tile0 + i] : 0.f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int n_end = n_tile0 + n_lim;
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
 
-            const int r_in_batch = lt * TBM + q * 32 + lane;                 // this thread's row (direct mode)
+            const int r_tile = q * 32 + lane;
+            const int r_in_batch = lt * TBM + r_tile;
             const bool row_ok = r_in_batch < g.rows_per_batch;
             const long long m = (long long)b * g.rows_per_batch + r_in_batch;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
 
+            if (!SCALAR) {
+                constexpr int SBW = Cfg::SBW;
+                constexpr int CH = (SBW % 32 == 0) ? 32 : 16;
 #pragma unroll 1
-            for (int c = 0; c < BN / CH; ++c) {
-                if (c * CH >= n_lim) break;     // warp-uniform
-                float v[CH];
-                if (CH == 32) tmem_ld_32x32(t_row + c * CH, v);
-                else tmem_ld_32x16(t_row + c * CH, v);
-                tmem_ld_wait();
-                const int ncol0 = n_tile0 + c * CH;   // global column of v[0]
-                if (!STAGED) {
+                for (int blk = half; blk < Cfg::NBLK; blk += 2) {
+                    const int col0 = blk * SBW;          // within the tile
+                    if (col0 >= n_lim) break;            // uniform across the CTA
+                    float v[SBW];
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) v[j] = apply_act_rt(v[j] + bias_s[c * CH + j], g.act);
-                    if (row_ok) {
-                        const bool full = (c * CH + CH <= n_lim) && p.vec_ok;
-                        if (g.resid) {
-                            if (g.resid_bf16) {
-                                const bf16* rp = static_cast<const bf16*>(g.resid) + m * g.ldr + ncol0;
-                                if (full) {
+                    for (int cc = 0; cc < SBW / CH; ++cc) {
+                        if (CH == 32) tmem_ld_32x32(t_row + col0 + cc * CH, v + cc * CH);
+                        else tmem_ld_32x16(t_row + col0 + cc * CH, v + cc * CH);
+                    }
+                    tmem_ld_wait();
+                    const int ncol0 = n_tile0 + col0;    // global column of v[0]
 #pragma unroll
-                                    for (int j = 0; j < CH; j += 8) {
-                                        uint4 u = *reinterpret_cast<const uint4*>(rp + j);
-                                        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    for (int j = 0; j < SBW; ++j) {
+                        float x = v[j];
+                        if (g.bias) x += (ncol0 + j < n_end) ? __ldg(g.bias + ncol0 + j) : 0.f;
+                        if (g.act == A2F_ACT_GELU) x = p.fast_gelu ? gelu_fast(x) : gelu_erf(x);
+                        else if (g.act == A2F_ACT_RELU) x = relu(x);
+                        else if (g.act == A2F_ACT_TANH) x = tanhf(x);
+                        v[j] = x;
+                    }
+                    if (g.resid && row_ok) {
+                        const bool full = (ncol0 + SBW <= n_end) && p.resid_vec_ok;
+                        if (g.resid_bf16) {
+                            const bf16* rp = static_cast<const bf16*>(g.resid) + m * g.ldr + ncol0;
+                            if (full) {
 #pragma unroll
-                                        for (int e = 0; e < 4; ++e) {
-                                            float2 f = __bfloat1622float2(h2[e]);
-                                            v[j + 2 * e] += f.x;
-                                            v[j + 2 * e + 1] += f.y;
-                                        }
+                                for (int j = 0; j < SBW; j += 8) {
+                                    const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
+                                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = __bfloat1622float2(h2[e]);
+                                        v[j + 2 * e] += f.x;
+                                        v[j + 2 * e + 1] += f.y;
                                     }
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < CH; ++j)
-                                        if (c * CH + j < n_lim) v[j] += __bfloat162float(rp[j]);
-                                }
-                            } else {
-                                const float* rp = static_cast<const float*>(g.resid) + m * g.ldr + ncol0;
-                                if (full) {
-#pragma unroll
-                                    for (int j = 0; j < CH; j += 4) {
-                                        float4 f = *reinterpret_cast<const float4*>(rp + j);
-                                        v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < CH; ++j)
-                                        if (c * CH + j < n_lim) v[j] += rp[j];
-                                }
-                            }
-                        }
-                        TC* cp = C + m * g.ldc + ncol0;
-                        if (full) {
-                            if (sizeof(TC) == 2) {
-#pragma unroll
-                                for (int j = 0; j < CH; j += 8) {
-                                    uint4 u;
-                                    u.x = pack_bf16x2(v[j], v[j + 1]);
-                                    u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                                    u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                                    u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                                    *reinterpret_cast<uint4*>(cp + j) = u;
                                 }
                             } else {
 #pragma unroll
-                                for (int j = 0; j < CH; j += 4)
-                                    *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                for (int j = 0; j < SBW; ++j)
+                                    if (ncol0 + j < n_end) v[j] += __bfloat162float(rp[j]);
                             }
                         } else {
+                            const float* rp = static_cast<const float*>(g.resid) + m * g.ldr + ncol0;
+                            if (full) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j)
-                                if (c * CH + j < n_lim) st_from_float(cp + j, v[j]);
+                                for (int j = 0; j < SBW; j += 4) {
+                                    const float4 f = *reinterpret_cast<const float4*>(rp + j);
+                                    v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < SBW; ++j)
+                                    if (ncol0 + j < n_end) v[j] += rp[j];
+                            }
                         }
                     }
-                } else {
-                    // staged: transpose through smem so that one warp store covers 32 consecutive columns of a row
+                    // the previous TMA store of this half must have finished reading the staging block
+                    if (leader) tma_store_wait_read();
+                    named_bar_sync(bar_id, 128);
+                    uint8_t* rowp = stage_buf + r_tile * Cfg::ROW_PITCH;
+                    constexpr int EPC = 16 / (int)sizeof(TC);      // elements per 16-byte chunk
+#pragma unroll
+                    for (int ch = 0; ch < SBW / EPC; ++ch) {
+                        const int pch = Cfg::SWZ ? (ch ^ (r_tile & 7)) : ch;
+                        uint4 u;
+                        if (sizeof(TC) == 2) {
+                            u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+                            u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+                            u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+                            u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+                        } else {
+                            u.x = __float_as_uint(v[ch * EPC + 0]);
+                            u.y = __float_as_uint(v[ch * EPC + 1]);
+                            u.z = __float_as_uint(v[ch * EPC + 2]);
+                            u.w = __float_as_uint(v[ch * EPC + 3]);
+                        }
+                        *reinterpret_cast<uint4*>(rowp + pch * 16) = u;
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (leader) {
+                        tma_store_3d(&maps.c, stage_buf, ncol0, lt * TBM, b);
+                        tma_store_commit();
+                    }
+                }
+            } else {
+                // scalar epilogue: 32x32 fp32 transposes, coalesced 4-byte stores, template add
+                float* tr = reinterpret_cast<float*>(sEpi) + ew * 1024;
+                constexpr int NCH = BN / 32;
+                const int rows_left = g.rows_per_batch - (lt * TBM + q * 32);   // rows of this warp that exist
+                const long long m0w = (long long)b * g.rows_per_batch + lt * TBM + q * 32;
+                // template row of the warp's first output row; later rows advance it incrementally (no per-element
+                // 64-bit division in the store loop)
+                const long long trow0 = g.tmpl ? m0w / g.rows_per_tmpl : 0;
+                const int trem0 = g.tmpl ? (int)(m0w - trow0 * g.rows_per_tmpl) : 0;
+#pragma unroll 1
+                for (int c = half; c < NCH; c += 2) {
+                    if (c * 32 >= n_lim) break;
+                    float v[32];
+                    tmem_ld_32x32(t_row + c * 32, v);
+                    tmem_ld_wait();
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) stg[lane * 33 + j] = v[j];
+                    for (int j = 0; j < 32; ++j) tr[lane * 32 + ((j + lane) & 31)] = v[j];
                     __syncwarp();
-                    const int ncol = ncol0 + (lane % CH);
-                    const bool col_ok = (c * CH + (lane % CH)) < n_lim && lane < CH;
-                    const float bj = bias_s[c * CH + (lane % CH)];
-                    const int rows_left = g.rows_per_batch - (lt * TBM + q * 32);   // rows of this warp that exist
-                    const long long m0w = (long long)b * g.rows_per_batch + lt * TBM + q * 32;
-#pragma unroll 8
+                    const int ncol = n_tile0 + c * 32 + lane;
+                    const bool col_ok = ncol < n_end;
+                    const float bj = (g.bias && col_ok) ? __ldg(g.bias + ncol) : 0.f;
+                    // batch the template / residual loads so that their latencies overlap
+                    float add[32];
+                    const float* tp = g.tmpl ? g.tmpl + trow0 * (long long)g.N + ncol : nullptr;
+                    int trem = trem0;
+#pragma unroll
                     for (int r = 0; r < 32; ++r) {
-                        if (r >= rows_left) break;
-                        if (col_ok) {
+                        float a = 0.f;
+                        if (col_ok && r < rows_left) {
                             const long long mr = m0w + r;
-                            float o = apply_act_rt(stg[r * 33 + (lane % CH)] + bj, g.act);
+                            if (g.tmpl) a = __ldg(tp);
                             if (g.resid) {
                                 const long long ri = mr * g.ldr + ncol;
-                                o += g.resid_bf16 ? __bfloat162float(static_cast<const bf16*>(g.resid)[ri])
+                                a += g.resid_bf16 ? __bfloat162float(static_cast<const bf16*>(g.resid)[ri])
                                                   : static_cast<const float*>(g.resid)[ri];
                             }
-                            if (g.tmpl) o += __ldg(g.tmpl + (mr / g.rows_per_tmpl) * (long long)g.N + ncol);
-                            st_from_float(C + mr * g.ldc + ncol, o);
+                        }
+                        add[r] = a;
+                        if (g.tmpl && ++trem == g.rows_per_tmpl) {   // next output row belongs to the next template
+                            trem = 0;
+                            tp += g.N;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        if (col_ok && r < rows_left) {
+                            const float o = apply_act_rt(tr[r * 32 + ((lane + r) & 31)] + bj, g.act) + add[r];
+                            st_from_float(C + (m0w + r) * g.ldc + ncol, o);
                         }
                     }
                 }
@@ -294,6 +348,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (!SCALAR && leader) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -304,10 +359,10 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     }
 }
 
-template <int BN, typename TC, bool STAGED>
+template <int BN, typename TC, bool SCALAR>
 static int launch_tc(const TmapSet& maps, const TcParams& p, cudaStream_t s) {
-    using Cfg = TcCfg<BN>;
-    auto kern = gemm_tc_kernel<BN, TC, STAGED>;
+    using Cfg = TcCfg<BN, TC>;
+    auto kern = gemm_tc_kernel<BN, TC, SCALAR>;
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
         A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -321,9 +376,23 @@ static int launch_tc(const TmapSet& maps, const TcParams& p, cudaStream_t s) {
     return A2F_OK;
 }
 
-template <int BN> static int dispatch_out(const TmapSet& maps, const TcParams& p, int c_bf16, bool staged, cudaStream_t s) {
-    if (c_bf16) return staged ? launch_tc<BN, bf16, true>(maps, p, s) : launch_tc<BN, bf16, false>(maps, p, s);
-    return staged ? launch_tc<BN, float, true>(maps, p, s) : launch_tc<BN, float, false>(maps, p, s);
+template <int BN, typename TC>
+static int encode_c_and_launch(TmapSet& maps, const TcParams& p, bool scalar, cudaStream_t s) {
+    using Cfg = TcCfg<BN, TC>;
+    if (scalar) return launch_tc<BN, TC, true>(maps, p, s);
+    const GemmParams& g = p.g;
+    const int ncols_total = (p.mode == 2) ? 768 : g.N;
+    uint64_t dims[3] = {(uint64_t)ncols_total, (uint64_t)g.rows_per_batch, (uint64_t)p.num_batches};
+    uint64_t strides[2] = {(uint64_t)g.ldc * sizeof(TC), (uint64_t)g.ldc * g.rows_per_batch * sizeof(TC)};
+    uint32_t box[3] = {(uint32_t)Cfg::SBW, TBM, 1};
+    int rc = encode_tmap(&maps.c, g.C, (int)sizeof(TC), 3, dims, strides, box, Cfg::SWZ ? 1 : 0);
+    if (rc != A2F_OK) return rc;
+    return launch_tc<BN, TC, false>(maps, p, s);
+}
+
+template <int BN> static int dispatch_out(TmapSet& maps, const TcParams& p, int c_bf16, bool scalar, cudaStream_t s) {
+    if (c_bf16) return encode_c_and_launch<BN, bf16>(maps, p, scalar, s);
+    return encode_c_and_launch<BN, float>(maps, p, scalar, s);
 }
 
 static int g_force_bn = 0;   // debug: force a tile width (tests exercise every instantiation)
@@ -337,6 +406,7 @@ int gemm_tc(const GemmParams& g, int c_bf16, int mode, cudaStream_t s) {
     p.sbo_enc = g_umma_fields[1];
     p.desc_version = g_umma_fields[2];
     p.desc_layout = g_umma_fields[3];
+    p.fast_gelu = c_bf16 ? 1 : 0;
     TmapSet maps;
     memset(&maps, 0, sizeof(maps));
 
@@ -396,22 +466,25 @@ int gemm_tc(const GemmParams& g, int c_bf16, int mode, cudaStream_t s) {
     }
 
     const size_t csz = c_bf16 ? 2 : 4;
-    const size_t vec_elems = 16 / csz;
-    bool vec_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && (g.ldc % (long long)vec_elems == 0);
+    const bool c_tma_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((g.ldc * (long long)csz) % 16 == 0);
+    p.resid_vec_ok = 0;
     if (g.resid) {
         const size_t rsz = g.resid_bf16 ? 2 : 4;
-        vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(g.resid) % 16 == 0) && (g.ldr % (long long)(16 / rsz) == 0);
+        p.resid_vec_ok = (reinterpret_cast<uintptr_t>(g.resid) % 16 == 0) && ((g.ldr * (long long)rsz) % 16 == 0);
     }
-    p.vec_ok = vec_ok ? 1 : 0;
-    // staged (transposing) epilogue: coalesced 4-byte stores for outputs whose rows are not 16-byte aligned
-    // (the 15069-wide vertex head) and for the template-add epilogue.
-    const bool staged = (g.tmpl != nullptr) || !vec_ok;
+    // scalar (transposing) epilogue: outputs whose rows are not 16-byte aligned (the 15069-wide vertex head) and the
+    // template-add epilogue.  fp32 output only.
+    const bool scalar = (g.tmpl != nullptr) || !c_tma_ok;
+    if (scalar) {
+        A2F_REQUIRE(!c_bf16, "gemm_tc: template-add / unaligned outputs are fp32 only");
+        A2F_REQUIRE(mode != 2, "gemm_tc: posconv output must be 16-byte aligned");
+    }
 
     switch (BN) {
-        case 256: return dispatch_out<256>(maps, p, c_bf16, staged, s);
-        case 128: return dispatch_out<128>(maps, p, c_bf16, staged, s);
-        case 64: return dispatch_out<64>(maps, p, c_bf16, staged, s);
-        case 48: return dispatch_out<48>(maps, p, c_bf16, staged, s);
+        case 256: return dispatch_out<256>(maps, p, c_bf16, scalar, s);
+        case 128: return dispatch_out<128>(maps, p, c_bf16, scalar, s);
+        case 64: return dispatch_out<64>(maps, p, c_bf16, scalar, s);
+        case 48: return dispatch_out<48>(maps, p, c_bf16, scalar, s);
         default: return set_error(A2F_EINVAL, "gemm_tc: unsupported tile width");
     }
 }

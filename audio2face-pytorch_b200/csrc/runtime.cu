@@ -65,8 +65,8 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle128) {
+int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) return set_error(A2F_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(A2F_EINVAL, "TMA base must be 16-byte aligned");
@@ -83,7 +83,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
         if (strides_bytes[i] % 16 != 0) return set_error(A2F_EINVAL, "TMA global strides must be multiples of 16 bytes");
         gstr[i] = strides_bytes[i];
     }
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

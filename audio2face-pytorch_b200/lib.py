@@ -66,6 +66,7 @@ _SIGNATURES = {
     "a2f_pack_conv1d_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "a2f_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "a2f_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "a2f_split_bf16x3": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "a2f_audio_stats": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p]),
     "a2f_conv0_workspace_bytes": (c_size_t, [c_int, c_ll]),
     "a2f_conv0_gn_gelu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll,

@@ -70,16 +70,20 @@ class _A2FModule(nn.Module):
 
     def _vertex_head(self, z: torch.Tensor, weight: nn.Parameter, bias: nn.Parameter, template2d: torch.Tensor,
                      rows_per_tmpl: int, k_live: int) -> torch.Tensor:
-        """Shared K11 head: out = z @ W^T + b + template, out [M, V3] fp32.  z: [M, 64] (columns >= k_live zero)."""
+        """Shared K11 head: out = z @ W^T + b + template, out [M, V3] fp32.  z: fp32 [M, 64] (columns >= k_live zero).
+
+        bf16 precision runs the tcgen05 GEMM on an error-compensated bf16 split (K' = 192: hi*hi + lo*hi + hi*lo), so
+        the HBM-bound head keeps ~2^-16 relative accuracy while using the tensor cores."""
         M, v3 = z.shape[0], weight.shape[0]
         out = torch.empty((M, v3), dtype=torch.float32, device=z.device)
         if self.precision == "bf16":
             def build():
                 w = torch.zeros((v3, 64), dtype=torch.float32, device=weight.device)
                 w[:, :k_live] = weight.detach()
-                return ops.cast_bf16(w)
-            wp = self._cache.get("head_bf16", (weight,), build)
-            ops.gemm(z, wp, out, bias=bias.detach(), tmpl=template2d, rows_per_tmpl=rows_per_tmpl, backend=L.TCGEN05, K=64)
+                return ops.split_bf16x3(w, True)
+            wp = self._cache.get("head_bf16x3", (weight,), build)
+            z3 = ops.split_bf16x3(z, False)
+            ops.gemm(z3, wp, out, bias=bias.detach(), tmpl=template2d, rows_per_tmpl=rows_per_tmpl, backend=L.TCGEN05, K=192)
         else:
             ops.gemm(z, weight.detach(), out, bias=bias.detach(), tmpl=template2d, rows_per_tmpl=rows_per_tmpl,
                      backend=L.SIMT_F32, K=k_live)
@@ -126,13 +130,226 @@ class Voca(_A2FModule):
         x = x.contiguous().float()
         one_hot = one_hot.contiguous().float()
         tmpl = template.reshape(bs, -1).contiguous().float()
-        z = torch.empty((bs, 64), dtype=torch.bfloat16 if self.precision == "bf16" else torch.float32, device=x.device)
+        z = torch.empty((bs, 64), dtype=torch.float32, device=x.device)
         ops.voca_trunk(self._weights_struct(), x, one_hot, z)
         out = self._vertex_head(z, self.decoder[4].weight, self.decoder[4].bias, tmpl, 1, 50)
         return out.view(bs, -1, 3)
 
     def predict(self, x, one_hot, template, **kwargs):
         return self(x, one_hot, template, **kwargs)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _Box(nn.Module):
+    """Plain namespace module: owns parameters / sub-modules under reference-compatible names, never called."""
+
+
+def _w2v_param_tree() -> nn.Module:
+    """Parameter container with the state_dict keys of the reference's Wav2Vec2Model subclass
+    (ref:src/model/wav2vec.py:87; transformers Wav2Vec2Config() base architecture)."""
+    enc = _Box()
+    enc.masked_spec_embed = nn.Parameter(torch.empty(768).uniform_())
+    fe = _Box()
+    layers = []
+    for i, k in enumerate((10, 3, 3, 3, 3, 2, 2)):
+        lay = _Box()
+        lay.conv = nn.Conv1d(1 if i == 0 else 512, 512, kernel_size=k, stride=5 if i == 0 else 2, bias=False)
+        if i == 0:
+            lay.layer_norm = nn.GroupNorm(num_groups=512, num_channels=512, affine=True)
+        layers.append(lay)
+    fe.conv_layers = nn.ModuleList(layers)
+    enc.feature_extractor = fe
+    fp = _Box()
+    fp.layer_norm = nn.LayerNorm(512, eps=1e-5)
+    fp.projection = nn.Linear(512, 768)
+    enc.feature_projection = fp
+    e = _Box()
+    pc = _Box()
+    pc.conv = nn.utils.parametrizations.weight_norm(nn.Conv1d(768, 768, kernel_size=128, padding=64, groups=16),
+                                                    name="weight", dim=2)
+    e.pos_conv_embed = pc
+    e.layer_norm = nn.LayerNorm(768, eps=1e-5)
+    blocks = []
+    for _ in range(12):
+        blk = _Box()
+        att = _Box()
+        for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            setattr(att, nm, nn.Linear(768, 768))
+        blk.attention = att
+        blk.layer_norm = nn.LayerNorm(768, eps=1e-5)
+        ff = _Box()
+        ff.intermediate_dense = nn.Linear(768, 3072)
+        ff.output_dense = nn.Linear(3072, 768)
+        blk.feed_forward = ff
+        blk.final_layer_norm = nn.LayerNorm(768, eps=1e-5)
+        blocks.append(blk)
+    e.layers = nn.ModuleList(blocks)
+    enc.encoder = e
+    return enc
+
+
+class PeriodicPositionalEncoding(nn.Module):
+    """Buffer-compatible stand-in for ref:src/model/faceformer.py:70-88 (`pe` [1, (max_seq_len//period+1)*period, d]);
+    the decoder kernel indexes row (position mod period) directly, so there is no 600-frame cap."""
+
+    def __init__(self, d_model, dropout=0.1, period=25, max_seq_len=600):
+        super().__init__()
+        import math
+        pe = torch.zeros(period, d_model)
+        position = torch.arange(0, period, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0).repeat(1, (max_seq_len // period) + 1, 1))
+
+
+class Faceformer(_A2FModule):
+    """Drop-in for ref:src/model/faceformer.py:91-191 (inference; eval-mode semantics: dropout / LayerDrop /
+    SpecAugment inactive).  Extensions over the reference, all opt-in: batches of B utterances [B,N] (the reference is
+    batch-1 only), `fps` other than the hard-coded 60 (fact 0.9), clips longer than 600 frames
+    (fact 0.8)."""
+
+    def __init__(self, n_verts: int, n_onehot: int):
+        super().__init__()
+        self.feature_dim = 64
+        self.n_onehot = n_onehot
+        self.dataset = "vocaset"
+        self.period = 60
+        self.fps = 60
+        self.vertice_dim = n_verts
+        self.audio_encoder = _w2v_param_tree()
+        self.audio_feature_map = nn.Linear(768, self.feature_dim)
+        self.vertice_map = nn.Linear(self.vertice_dim, self.feature_dim)
+        self.PPE = PeriodicPositionalEncoding(self.feature_dim, period=self.period)
+        layer = nn.TransformerDecoderLayer(d_model=self.feature_dim, nhead=4, dim_feedforward=2 * self.feature_dim,
+                                           batch_first=True)
+        self.transformer_decoder = nn.TransformerDecoder(layer, num_layers=1)
+        self.vertice_map_r = nn.Linear(self.feature_dim, self.vertice_dim)
+        self.obj_vector = nn.Linear(self.n_onehot, self.feature_dim, bias=False)
+        for p in (self.vertice_map_r.weight, self.vertice_map_r.bias, self.vertice_map.weight, self.vertice_map.bias):
+            nn.init.constant_(p, 0)        # ref:faceformer.py:132-135
+
+    # -- derived weights --------------------------------------------------------------------------------------
+    def _packed(self):
+        bf = self.precision == "bf16"
+        dt = torch.bfloat16 if bf else torch.float32
+        ae = self.audio_encoder
+
+        def build():
+            P = {}
+            cl = ae.feature_extractor.conv_layers
+            P["conv0_w"] = cl[0].conv.weight.detach().reshape(512, 10).contiguous()
+            P["convs"] = [ops.pack_conv1d_weight(cl[i].conv.weight.detach(), dt) for i in range(1, 7)]
+            cast = (lambda t: ops.cast_bf16(t.detach())) if bf else (lambda t: t.detach().contiguous())
+            P["proj_w"] = cast(ae.feature_projection.projection.weight)
+            pz = ae.encoder.pos_conv_embed.conv.parametrizations.weight
+            P["pos_w"] = ops.pack_posconv_weight(pz.original0.detach().reshape(-1), pz.original1.detach(), dt)
+            lay = []
+            for blk in ae.encoder.layers:
+                a = blk.attention
+                qkv_w = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).detach()
+                qkv_b = torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0).detach().contiguous()
+                lay.append({
+                    "qkv_w": cast(qkv_w), "qkv_b": qkv_b,
+                    "o_w": cast(a.out_proj.weight),
+                    "f1_w": cast(blk.feed_forward.intermediate_dense.weight),
+                    "f2_w": cast(blk.feed_forward.output_dense.weight),
+                })
+            P["layers"] = lay
+            P["afm_w"] = cast(self.audio_feature_map.weight)
+            wc, bc = ops.pack_feedback(self.vertice_map.weight.detach().contiguous(), self.vertice_map.bias.detach(),
+                                       self.vertice_map_r.weight.detach().contiguous(), self.vertice_map_r.bias.detach())
+            P["fb"] = (wc, bc)
+            d = self.transformer_decoder.layers[0]
+            dw = L.DecoderWeights()
+            keep = {
+                "sa_in_w": d.self_attn.in_proj_weight, "sa_in_b": d.self_attn.in_proj_bias,
+                "sa_out_w": d.self_attn.out_proj.weight, "sa_out_b": d.self_attn.out_proj.bias,
+                "ca_in_w": d.multihead_attn.in_proj_weight, "ca_in_b": d.multihead_attn.in_proj_bias,
+                "ca_out_w": d.multihead_attn.out_proj.weight, "ca_out_b": d.multihead_attn.out_proj.bias,
+                "lin1_w": d.linear1.weight, "lin1_b": d.linear1.bias, "lin2_w": d.linear2.weight, "lin2_b": d.linear2.bias,
+                "n1_w": d.norm1.weight, "n1_b": d.norm1.bias, "n2_w": d.norm2.weight, "n2_b": d.norm2.bias,
+                "n3_w": d.norm3.weight, "n3_b": d.norm3.bias, "fb_w": wc, "fb_b": bc,
+                "obj_w": self.obj_vector.weight, "pe": self.PPE.pe,
+            }
+            keep = {k: v.detach().contiguous() for k, v in keep.items()}
+            for k, v in keep.items():
+                setattr(dw, k, v.data_ptr())
+            P["dec"] = (dw, keep)
+            return P
+
+        srcs = list(self.parameters()) + [self.PPE.pe]
+        return self._cache.get("ff_" + self.precision, srcs, build)
+
+    # -- forward ----------------------------------------------------------------------------------------------
+    def encode(self, audio: torch.Tensor, frame_num: int) -> torch.Tensor:
+        """Wav2Vec2Model.forward of ref:src/model/wav2vec.py:91-187 (processor normalisation included):
+        raw audio [B,N] -> last_hidden_state [B*T,768] (bf16 or fp32 by precision)."""
+        P = self._packed()
+        bf = self.precision == "bf16"
+        dt = torch.bfloat16 if bf else torch.float32
+        be = self._backend()
+        ae = self.audio_encoder
+        B, N = audio.shape
+        dev = audio.device
+        stats = ops.audio_stats(audio)
+        gn = ae.feature_extractor.conv_layers[0].layer_norm
+        x = ops.conv0_gn_gelu(audio, stats, P["conv0_w"], gn.weight.detach(), gn.bias.detach(), dt)   # [B,L0,512]
+        L_in = x.shape[1]
+        for i, k in enumerate((3, 3, 3, 3, 2, 2)):
+            L_out = (L_in - k) // 2 + 1
+            y = torch.empty((B, L_out, 512), dtype=dt, device=dev)
+            ops.gemm(x, P["convs"][i], y, act=L.ACT_GELU, backend=be, M=B * L_out, K=k * 512, a_row_stride=1024,
+                     a_batch_stride=L_in * 512, rows_per_batch=L_out, ldc=512)
+            x, L_in = y, L_out
+        T = frame_num
+        fp = ae.feature_projection
+        xi = ops.interp_ln(x, fp.layer_norm.weight.detach(), fp.layer_norm.bias.detach(), T, dt)       # [B,T,512]
+        M = B * T
+        h0 = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.gemm(xi.view(M, 512), P["proj_w"], h0, bias=fp.projection.bias.detach(), backend=be)
+        pre = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.posconv(h0, P["pos_w"], ae.encoder.pos_conv_embed.conv.bias.detach(), pre, B, T, be)
+        h = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.layernorm(pre, ae.encoder.layer_norm.weight.detach(), ae.encoder.layer_norm.bias.detach(), h)
+        qkv = torch.empty((M, 2304), dtype=dt, device=dev)
+        att = torch.empty((M, 768), dtype=dt, device=dev)
+        pre32 = torch.empty((M, 768), dtype=torch.float32, device=dev)
+        ffn = torch.empty((M, 3072), dtype=dt, device=dev)
+        for blk, W in zip(ae.encoder.layers, P["layers"]):
+            ops.gemm(h, W["qkv_w"], qkv, bias=W["qkv_b"], backend=be)
+            ops.mha(qkv, att, B, T)
+            ops.gemm(att, W["o_w"], pre32, bias=blk.attention.out_proj.bias.detach(), resid=h, backend=be)
+            ops.layernorm(pre32, blk.layer_norm.weight.detach(), blk.layer_norm.bias.detach(), h)
+            ops.gemm(h, W["f1_w"], ffn, bias=blk.feed_forward.intermediate_dense.bias.detach(), act=L.ACT_GELU, backend=be)
+            ops.gemm(ffn, W["f2_w"], pre32, bias=blk.feed_forward.output_dense.bias.detach(), resid=h, backend=be)
+            ops.layernorm(pre32, blk.final_layer_norm.weight.detach(), blk.final_layer_norm.bias.detach(), h)
+        return h
+
+    def forward(self, audio, one_hot, template, **kwargs):
+        self._need_cuda(audio, one_hot, template)
+        self._no_grad_guard(audio, template, *self.parameters())
+        fps = int(kwargs.get("fps", self.fps))
+        audio = audio.contiguous().float()
+        if audio.dim() != 2:
+            raise L.A2FError("audio must be [B, N] raw 16 kHz samples")
+        B, N = audio.shape
+        frame_num = N * fps // 16000                                   # ref:faceformer.py:141
+        if frame_num < 1:
+            raise L.A2FError("audio too short for one output frame")
+        one_hot = one_hot.reshape(B, -1).contiguous().float()
+        tmpl = template.reshape(B, -1).contiguous().float()            # ref:faceformer.py:147
+        P = self._packed()
+        h = self.encode(audio, frame_num)
+        M = B * frame_num
+        memory = torch.empty((M, 64), dtype=torch.float32, device=audio.device)
+        ops.gemm(h, P["afm_w"], memory, bias=self.audio_feature_map.bias.detach(), backend=self._backend())
+        D = ops.decoder_rollout(P["dec"][0], memory, one_hot, self.period, B, frame_num)
+        out = self._vertex_head(D.view(M, 64), self.vertice_map_r.weight, self.vertice_map_r.bias, tmpl, frame_num, 64)
+        return out.view(B, frame_num, -1, 3)                           # ref:faceformer.py:187-188
+
+    def predict(self, audio, one_hot, template, **kwargs):
+        return self(audio, one_hot, template, **kwargs)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -103,3 +103,109 @@ def voca_loss_bwd(pred: torch.Tensor, gt: torch.Tensor, rows: int, v3: int, k_re
     L.check(L.load().a2f_voca_loss_bwd(pred.data_ptr(), gt.data_ptr(), rows, v3, k_rec, k_vel, L.ptr(gscale),
                                        dpred.data_ptr(), _stream()), "a2f_voca_loss_bwd")
     return dpred
+
+
+def split_bf16x3(x: torch.Tensor, is_weight: bool) -> torch.Tensor:
+    """fp32 [rows,K] -> bf16 [rows,3K] error-compensated split (a2f_split_bf16x3)."""
+    _dev(x)
+    rows, K = x.shape
+    out = torch.empty((rows, 3 * K), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().a2f_split_bf16x3(x.data_ptr(), x.stride(0), out.data_ptr(), rows, K, 1 if is_weight else 0, _stream()),
+            "a2f_split_bf16x3")
+    return out
+
+
+def pack_conv1d_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _dev(w)
+    cout, cin, taps = w.shape
+    out = torch.empty((cout, taps * cin), dtype=dtype, device=w.device)
+    L.check(L.load().a2f_pack_conv1d_weight(w.contiguous().data_ptr(), out.data_ptr(), _dt(out), cout, cin, taps, _stream()),
+            "a2f_pack_conv1d_weight")
+    return out
+
+
+def pack_posconv_weight(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    _dev(g, v)
+    kpad = 64 if dtype == torch.bfloat16 else 48
+    out = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+    norm = torch.empty(128, dtype=torch.float32, device=v.device)
+    L.check(L.load().a2f_pack_posconv_weight(g.contiguous().data_ptr(), v.contiguous().data_ptr(), out.data_ptr(), _dt(out),
+                                             kpad, norm.data_ptr(), _stream()), "a2f_pack_posconv_weight")
+    return out
+
+
+def posconv(h: torch.Tensor, wp: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, B: int, T: int, backend: int):
+    _dev(h, wp, bias, out)
+    L.check(L.load().a2f_posconv(h.data_ptr(), _dt(h), wp.data_ptr(), bias.data_ptr(), out.data_ptr(), _dt(out), B, T,
+                                 backend, _stream()), "a2f_posconv")
+    return out
+
+
+def audio_stats(audio: torch.Tensor) -> torch.Tensor:
+    _dev(audio)
+    B, N = audio.shape
+    stats = torch.empty((B, 2), dtype=torch.float32, device=audio.device)
+    L.check(L.load().a2f_audio_stats(audio.data_ptr(), B, N, stats.data_ptr(), _stream()), "a2f_audio_stats")
+    return stats
+
+
+def conv0_gn_gelu(audio: torch.Tensor, stats: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  dtype: torch.dtype) -> torch.Tensor:
+    """-> channels-last [B, L0, 512]"""
+    _dev(audio, stats, w, gamma, beta)
+    B, N = audio.shape
+    L0 = (N - 10) // 5 + 1
+    lib = L.load()
+    nbytes = lib.a2f_conv0_workspace_bytes(B, N)
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=audio.device)
+    out = torch.empty((B, L0, 512), dtype=dtype, device=audio.device)
+    L.check(lib.a2f_conv0_gn_gelu(audio.data_ptr(), stats.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                  out.data_ptr(), _dt(out), B, N, ws.data_ptr(), ws.numel() * 8, _stream()),
+            "a2f_conv0_gn_gelu")
+    return out
+
+
+def interp_ln(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, T: int, out_dtype: torch.dtype, eps: float = 1e-5):
+    """[B,S,512] -> LayerNorm(linear_interpolation to T frames) [B,T,512]"""
+    _dev(x, gamma, beta)
+    B, S, Cc = x.shape
+    out = torch.empty((B, T, Cc), dtype=out_dtype, device=x.device)
+    L.check(L.load().a2f_interp_ln(x.data_ptr(), _dt(x), gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), _dt(out),
+                                   B, S, T, Cc, _stream()), "a2f_interp_ln")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5,
+              out2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(x, gamma, beta, out, out2)
+    rows, Cc = x.shape
+    L.check(L.load().a2f_layernorm(x.data_ptr(), _dt(x), gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), _dt(out),
+                                   L.ptr(out2), _dt(out2) if out2 is not None else 0, rows, Cc, _stream()), "a2f_layernorm")
+    return out
+
+
+def mha(qkv: torch.Tensor, out: torch.Tensor, B: int, T: int, H: int = 12, D: int = 64, scale: float = 0.125):
+    _dev(qkv, out)
+    L.check(L.load().a2f_mha_fwd(qkv.data_ptr(), out.data_ptr(), _dt(qkv), B, T, H, D, scale, _stream()), "a2f_mha_fwd")
+    return out
+
+
+def pack_feedback(vm_w, vm_b, vmr_w, vmr_b):
+    _dev(vm_w, vm_b, vmr_w, vmr_b)
+    wc = torch.empty((64, 64), dtype=torch.float32, device=vm_w.device)
+    bc = torch.empty((64,), dtype=torch.float32, device=vm_w.device)
+    L.check(L.load().a2f_pack_feedback(vm_w.data_ptr(), vm_b.data_ptr(), vmr_w.data_ptr(), vmr_b.data_ptr(),
+                                       vmr_w.shape[0], wc.data_ptr(), bc.data_ptr(), _stream()), "a2f_pack_feedback")
+    return wc, bc
+
+
+def decoder_rollout(wstruct: "L.DecoderWeights", memory: torch.Tensor, one_hot: torch.Tensor, period: int, B: int, T: int):
+    """memory [B,T,64] fp32 -> decoder states D [B,T,64] fp32 (a2f_decoder_rollout)."""
+    _dev(memory, one_hot)
+    lib = L.load()
+    nbytes = lib.a2f_decoder_workspace_bytes(B, T)
+    ws = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.float32, device=memory.device)
+    D = torch.empty((B, T, 64), dtype=torch.float32, device=memory.device)
+    L.check(lib.a2f_decoder_rollout(C.byref(wstruct), memory.data_ptr(), one_hot.data_ptr(), one_hot.shape[1], period,
+                                    D.data_ptr(), B, T, ws.data_ptr(), ws.numel() * 4, _stream()), "a2f_decoder_rollout")
+    return D

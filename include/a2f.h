@@ -103,6 +103,10 @@ int a2f_pack_conv1d_weight(const float* w, void* out, int out_dtype, int cout, i
 /* elementwise cast fp32 -> bf16 (n elements) */
 int a2f_cast_f32_to_bf16(const float* in, void* out, long long n, void* stream);
 int a2f_cast_bf16_to_f32(const void* in, float* out, long long n, void* stream);
+/* Error-compensated split for the tensor-core vertex head (K11): fp32 [rows,K] (row stride ld_in) -> bf16 [rows,3K],
+ * activations as [hi | lo | hi], weights (is_weight=1) as [hi | hi | lo], hi = bf16(x), lo = bf16(x - hi): one bf16
+ * GEMM with K' = 3K then evaluates a*w to ~2^-16 relative error with fp32 accumulation. */
+int a2f_split_bf16x3(const float* in, long long ld_in, void* out, long long rows, int K, int is_weight, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * wav2vec2 front end.

@@ -1,0 +1,156 @@
+"""GPU parity of a2f_gemm / a2f_posconv (SIMT fp32 and tcgen05 back ends) against fp64 CPU matmuls of the same
+(bf16-rounded where applicable) operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, w, bias=None, act=0, resid=None, tmpl=None, rows_per_tmpl=1):
+    y = a.double().cpu() @ w.double().cpu().T
+    if bias is not None:
+        y = y + bias.double().cpu()
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = F.gelu(y)
+    elif act == 3:
+        y = torch.tanh(y)
+    if resid is not None:
+        y = y + resid.double().cpu()
+    if tmpl is not None:
+        idx = torch.arange(y.shape[0]) // rows_per_tmpl
+        y = y + tmpl.double().cpu()[idx]
+    return y
+
+
+def _rand(shape, dev, seed, dtype=torch.float32, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (scale * torch.randn(shape, generator=g)).to(dev).to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (130, 70, 50), (257, 333, 129), (9, 15069, 50)])
+def test_simt_fp32_plain(a2f_lib, dev, M, N, K):
+    from a2f_b200 import ops, lib as L
+    a, w, b = _rand((M, K), dev, 1), _rand((N, K), dev, 2), _rand((N,), dev, 3)
+    out = torch.empty((M, N), device=dev)
+    ops.gemm(a, w, out, bias=b, act=L.ACT_TANH, backend=L.SIMT_F32)
+    want = _ref(a, w, b, 3)
+    assert float((out.cpu().double() - want).abs().max()) < 2e-5
+
+
+def test_simt_fp32_epilogue_resid_tmpl(a2f_lib, dev):
+    from a2f_b200 import ops, lib as L
+    M, N, K = 40, 301, 64
+    a, w, b = _rand((M, K), dev, 4), _rand((N, K), dev, 5), _rand((N,), dev, 6)
+    r, t = _rand((M, N), dev, 7), _rand((4, N), dev, 8)
+    out = torch.empty((M, N), device=dev)
+    ops.gemm(a, w, out, bias=b, act=L.ACT_GELU, resid=r, tmpl=t, rows_per_tmpl=10, backend=L.SIMT_F32)
+    want = _ref(a, w, b, 2, r, t, 10)
+    assert float((out.cpu().double() - want).abs().max()) < 2e-5
+
+
+TC_CASES = [
+    # M, N, K, act, use_resid, out_bf16, use_tmpl
+    (128, 256, 64, 0, False, False, False),
+    (256, 512, 256, 0, False, True, False),
+    (300, 768, 512, 2, True, True, False),
+    (1000, 100, 72, 1, False, False, False),
+    (77, 40, 128, 3, True, False, False),
+    (513, 2304, 768, 0, False, True, False),
+    (200, 333, 64, 0, False, False, True),
+    (384, 768, 3072, 0, True, False, False),
+]
+
+
+@pytest.mark.parametrize("M,N,K,act,use_resid,out_bf16,use_tmpl", TC_CASES)
+def test_tcgen05_plain(a2f_lib, dev, M, N, K, act, use_resid, out_bf16, use_tmpl):
+    from a2f_b200 import ops, lib as L
+    a = _rand((M, K), dev, 11, torch.bfloat16)
+    w = _rand((N, K), dev, 12, torch.bfloat16, scale=K ** -0.5)
+    b = _rand((N,), dev, 13)
+    r = _rand((M, N), dev, 14, torch.bfloat16) if use_resid else None
+    t = _rand((7, N), dev, 15) if use_tmpl else None
+    rpt = (M + 6) // 7
+    out = torch.empty((M, N), device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    ops.gemm(a, w, out, bias=b, act=act, resid=r, tmpl=t, rows_per_tmpl=rpt, backend=L.TCGEN05)
+    torch.cuda.synchronize()
+    want = _ref(a, w, b, act, r, t, rpt)
+    err = float((out.cpu().double() - want).abs().max())
+    tol = 3e-2 if out_bf16 else 2e-4
+    assert err < tol, (err, tol)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_tcgen05_forced_tile_widths(a2f_lib, dev, bn):
+    from a2f_b200 import ops, lib as L
+    M, N, K = 390, 520, 192
+    a = _rand((M, K), dev, 21, torch.bfloat16)
+    w = _rand((N, K), dev, 22, torch.bfloat16, scale=K ** -0.5)
+    out = torch.empty((M, N), device=dev)
+    try:
+        L.check(a2f_lib.a2f_debug_set_umma_field(4, bn))
+        ops.gemm(a, w, out, backend=L.TCGEN05)
+        torch.cuda.synchronize()
+    finally:
+        a2f_lib.a2f_debug_set_umma_field(4, 0)
+    assert float((out.cpu().double() - _ref(a, w)).abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("taps,L_in,B", [(3, 41, 2), (3, 40, 3), (2, 38, 2), (3, 515, 2)])
+def test_conv1d_implicit_gemm(a2f_lib, dev, taps, L_in, B):
+    """Conv1d(512->512, k taps, stride 2, no bias)+GELU over channels-last activations == F.conv1d on NCL."""
+    from a2f_b200 import ops, lib as L
+    C = 512
+    L_out = (L_in - taps) // 2 + 1
+    L_pad = L_in + (L_in % 2)         # batch stride kept a multiple of the row stride
+    x = _rand((B, L_pad, C), dev, 31)
+    x[:, L_in:] = 0
+    w = _rand((C, C, taps), dev, 32, scale=(C * taps) ** -0.5)
+    want = F.gelu(F.conv1d(x[:, :L_in].transpose(1, 2).double().cpu(), w.double().cpu(), stride=2)).transpose(1, 2)
+    for backend, dt, tol in ((L.SIMT_F32, torch.float32, 2e-5), (L.TCGEN05, torch.bfloat16, 3e-2)):
+        wp = torch.empty((C, taps * C), device=dev, dtype=dt)
+        L.check(a2f_lib.a2f_pack_conv1d_weight(w.data_ptr(), wp.data_ptr(), 1 if dt == torch.bfloat16 else 0, C, C, taps,
+                                                torch.cuda.current_stream().cuda_stream))
+        xa = x.to(dt)
+        out = torch.empty((B * L_out, C), device=dev, dtype=dt)
+        ops.gemm(xa, wp, out, act=L.ACT_GELU, backend=backend, M=B * L_out, K=taps * C, a_row_stride=2 * C,
+                 a_batch_stride=L_pad * C, rows_per_batch=L_out)
+        torch.cuda.synchronize()
+        ref = want if dt == torch.float32 else F.gelu(
+            F.conv1d(xa[:, :L_in].transpose(1, 2).double().cpu(), wp.double().cpu().view(C, taps, C).permute(0, 2, 1),
+                     stride=2)).transpose(1, 2)
+        err = float((out.view(B, L_out, C).cpu().double() - ref).abs().max())
+        assert err < tol, (backend, err)
+
+
+@pytest.mark.parametrize("B,T", [(1, 60), (2, 150), (1, 300)])
+def test_posconv(a2f_lib, dev, B, T):
+    """h + gelu(weight-normed grouped conv k=128 pad 64 groups 16, last step dropped) vs torch."""
+    from a2f_b200 import lib as L
+    st = torch.cuda.current_stream().cuda_stream
+    h = _rand((B, T, 768), dev, 41)
+    g = (0.5 + torch.rand(1, 1, 128, generator=torch.Generator().manual_seed(42))).to(dev)
+    v = _rand((768, 48, 128), dev, 43, scale=(48 * 128) ** -0.5)
+    bias = _rand((768,), dev, 44, scale=0.05)
+    wfull = torch._weight_norm(v.cpu(), g.cpu(), 2)
+    norm = torch.empty(128, device=dev)
+    for backend, dt, kpad, tol in ((L.SIMT_F32, torch.float32, 48, 3e-5), (L.TCGEN05, torch.bfloat16, 64, 5e-2)):
+        wp = torch.empty((16, 48, 128, kpad), device=dev, dtype=dt)
+        L.check(a2f_lib.a2f_pack_posconv_weight(g.data_ptr(), v.data_ptr(), wp.data_ptr(), 1 if dt == torch.bfloat16 else 0,
+                                                 kpad, norm.data_ptr(), st))
+        ha = h.to(dt).contiguous()
+        out = torch.empty((B, T, 768), device=dev, dtype=dt)
+        L.check(a2f_lib.a2f_posconv(ha.data_ptr(), 1 if dt == torch.bfloat16 else 0, wp.data_ptr(), bias.data_ptr(),
+                                     out.data_ptr(), 1 if dt == torch.bfloat16 else 0, B, T, backend, st), "a2f_posconv")
+        torch.cuda.synchronize()
+        hh = ha.double().cpu()
+        if dt == torch.bfloat16:   # reference on the bf16-rounded packed weights
+            wq = wp[..., :48].double().cpu().permute(0, 1, 3, 2).reshape(768, 48, 128)
+        else:
+            wq = wfull.double()
+        pos = F.conv1d(hh.transpose(1, 2), wq, bias.double().cpu(), padding=64, groups=16)[:, :, :-1]
+        want = hh + F.gelu(pos).transpose(1, 2)
+        err = float((out.cpu().double() - want).abs().max())
+        assert err < tol, (backend, err)

@@ -9,7 +9,12 @@ import torch
 from oracle import inputs as oin, ref_models as orm, weights as ow
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    with torch.no_grad():
+        yield
 
 
 def _sub(t, step):
