@@ -39,6 +39,7 @@ struct TcParams {
     int mode;
     int tiles_m_per_batch, num_batches, tiles_n, num_k_blocks, kb_per_seg;
     int resid_vec_ok;               // 16-byte vector residual loads are legal
+    int bias_vec_ok;                // 16-byte vector bias loads are legal
     int fast_gelu;                  // bf16 output: A-S erf approximation instead of erff
     uint32_t lbo_enc, sbo_enc, desc_version, desc_layout;
 };
@@ -65,6 +66,79 @@ template <int BN, typename TC> struct TcCfg {
     static constexpr bool SWZ = (ROW_PITCH == 128);
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 2 * EPI_STAGE_BYTES + 256 /*barriers*/;
 };
+
+// ---- epilogue helpers: every data-independent condition is tested once per chunk, never per element ----
+template <int CH>
+__device__ __forceinline__ void epi_bias_act(float* v, const float* __restrict__ bias, int bias_vec_ok, int nc, int n_end,
+                                             int act, int fast_gelu) {
+    if (bias != nullptr) {
+        if (bias_vec_ok && nc + CH <= n_end) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(bias + nc + j));
+                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+                if (nc + j < n_end) v[j] += __ldg(bias + nc + j);
+        }
+    }
+    if (act == A2F_ACT_GELU) {
+        if (fast_gelu) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+        }
+    } else if (act == A2F_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = relu(v[j]);
+    } else if (act == A2F_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = tanhf(v[j]);
+    }
+}
+
+template <int CH>
+__device__ __forceinline__ void epi_resid(float* v, const void* __restrict__ resid, int resid_bf16, long long off, int nc,
+                                          int n_end, int vec_ok) {
+    const bool full = vec_ok && (nc + CH <= n_end);
+    if (resid_bf16) {
+        const bf16* rp = static_cast<const bf16*>(resid) + off;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    v[j + 2 * e] += f.x;
+                    v[j + 2 * e + 1] += f.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+                if (nc + j < n_end) v[j] += __bfloat162float(rp[j]);
+        }
+    } else {
+        const float* rp = static_cast<const float*>(resid) + off;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+                const float4 f = *reinterpret_cast<const float4*>(rp + j);
+                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+                if (nc + j < n_end) v[j] += rp[j];
+        }
+    }
+}
 
 template <int BN, typename TC, bool SCALAR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -202,84 +276,44 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
             if (!SCALAR) {
                 constexpr int SBW = Cfg::SBW;
                 constexpr int CH = (SBW % 32 == 0) ? 32 : 16;
+                constexpr int EPC = 16 / (int)sizeof(TC);      // elements per 16-byte chunk
+                uint8_t* rowp = stage_buf + r_tile * Cfg::ROW_PITCH;
 #pragma unroll 1
                 for (int blk = half; blk < Cfg::NBLK; blk += 2) {
                     const int col0 = blk * SBW;          // within the tile
                     if (col0 >= n_lim) break;            // uniform across the CTA
-                    float v[SBW];
-#pragma unroll
-                    for (int cc = 0; cc < SBW / CH; ++cc) {
-                        if (CH == 32) tmem_ld_32x32(t_row + col0 + cc * CH, v + cc * CH);
-                        else tmem_ld_32x16(t_row + col0 + cc * CH, v + cc * CH);
-                    }
-                    tmem_ld_wait();
-                    const int ncol0 = n_tile0 + col0;    // global column of v[0]
-#pragma unroll
-                    for (int j = 0; j < SBW; ++j) {
-                        float x = v[j];
-                        if (g.bias) x += (ncol0 + j < n_end) ? __ldg(g.bias + ncol0 + j) : 0.f;
-                        if (g.act == A2F_ACT_GELU) x = p.fast_gelu ? gelu_fast(x) : gelu_erf(x);
-                        else if (g.act == A2F_ACT_RELU) x = relu(x);
-                        else if (g.act == A2F_ACT_TANH) x = tanhf(x);
-                        v[j] = x;
-                    }
-                    if (g.resid && row_ok) {
-                        const bool full = (ncol0 + SBW <= n_end) && p.resid_vec_ok;
-                        if (g.resid_bf16) {
-                            const bf16* rp = static_cast<const bf16*>(g.resid) + m * g.ldr + ncol0;
-                            if (full) {
-#pragma unroll
-                                for (int j = 0; j < SBW; j += 8) {
-                                    const uint4 u = *reinterpret_cast<const uint4*>(rp + j);
-                                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const float2 f = __bfloat1622float2(h2[e]);
-                                        v[j + 2 * e] += f.x;
-                                        v[j + 2 * e + 1] += f.y;
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < SBW; ++j)
-                                    if (ncol0 + j < n_end) v[j] += __bfloat162float(rp[j]);
-                            }
-                        } else {
-                            const float* rp = static_cast<const float*>(g.resid) + m * g.ldr + ncol0;
-                            if (full) {
-#pragma unroll
-                                for (int j = 0; j < SBW; j += 4) {
-                                    const float4 f = *reinterpret_cast<const float4*>(rp + j);
-                                    v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < SBW; ++j)
-                                    if (ncol0 + j < n_end) v[j] += rp[j];
-                            }
-                        }
-                    }
+                    const int ncol0 = n_tile0 + col0;    // global column of the block
                     // the previous TMA store of this half must have finished reading the staging block
                     if (leader) tma_store_wait_read();
                     named_bar_sync(bar_id, 128);
-                    uint8_t* rowp = stage_buf + r_tile * Cfg::ROW_PITCH;
-                    constexpr int EPC = 16 / (int)sizeof(TC);      // elements per 16-byte chunk
+#pragma unroll 1
+                    for (int cc = 0; cc < SBW / CH; ++cc) {
+                        float v[CH];
+                        if (CH == 32) tmem_ld_32x32(t_row + col0 + cc * CH, v);
+                        else tmem_ld_32x16(t_row + col0 + cc * CH, v);
+                        tmem_ld_wait();
+                        const int nc = ncol0 + cc * CH;
+                        epi_bias_act<CH>(v, g.bias, p.bias_vec_ok, nc, n_end, g.act, p.fast_gelu);
+                        if (g.resid != nullptr && row_ok)
+                            epi_resid<CH>(v, g.resid, g.resid_bf16, m * g.ldr + nc, nc, n_end, p.resid_vec_ok);
 #pragma unroll
-                    for (int ch = 0; ch < SBW / EPC; ++ch) {
-                        const int pch = Cfg::SWZ ? (ch ^ (r_tile & 7)) : ch;
-                        uint4 u;
-                        if (sizeof(TC) == 2) {
-                            u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
-                            u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
-                            u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
-                            u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
-                        } else {
-                            u.x = __float_as_uint(v[ch * EPC + 0]);
-                            u.y = __float_as_uint(v[ch * EPC + 1]);
-                            u.z = __float_as_uint(v[ch * EPC + 2]);
-                            u.w = __float_as_uint(v[ch * EPC + 3]);
+                        for (int k = 0; k < CH / EPC; ++k) {
+                            const int ch = cc * (CH / EPC) + k;
+                            const int pch = Cfg::SWZ ? (ch ^ (r_tile & 7)) : ch;
+                            uint4 u;
+                            if (sizeof(TC) == 2) {
+                                u.x = pack_bf16x2(v[k * 8 + 0], v[k * 8 + 1]);
+                                u.y = pack_bf16x2(v[k * 8 + 2], v[k * 8 + 3]);
+                                u.z = pack_bf16x2(v[k * 8 + 4], v[k * 8 + 5]);
+                                u.w = pack_bf16x2(v[k * 8 + 6], v[k * 8 + 7]);
+                            } else {
+                                u.x = __float_as_uint(v[k * EPC + 0]);
+                                u.y = __float_as_uint(v[k * EPC + 1]);
+                                u.z = __float_as_uint(v[k * EPC + 2]);
+                                u.w = __float_as_uint(v[k * EPC + 3]);
+                            }
+                            *reinterpret_cast<uint4*>(rowp + pch * 16) = u;
                         }
-                        *reinterpret_cast<uint4*>(rowp + pch * 16) = u;
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(bar_id, 128);
@@ -311,35 +345,75 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     const int ncol = n_tile0 + c * 32 + lane;
                     const bool col_ok = ncol < n_end;
                     const float bj = (g.bias && col_ok) ? __ldg(g.bias + ncol) : 0.f;
-                    // batch the template / residual loads so that their latencies overlap
-                    float add[32];
-                    const float* tp = g.tmpl ? g.tmpl + trow0 * (long long)g.N + ncol : nullptr;
-                    int trem = trem0;
+                    const bool fast = (n_tile0 + c * 32 + 32 <= n_end) && rows_left >= 32 && g.resid == nullptr &&
+                                      g.act == A2F_ACT_NONE;      // warp-uniform: whole 32x32 chunk live, plain epilogue
+                    if (fast) {
+                        // common case of the vertex head: no predicates, one 64-bit address per chunk, 32 independent
+                        // rows in flight.  Template rows: one shared row (FaceFormer: T frames per utterance) or one per
+                        // output row (VOCA / Audio2Mesh).
+                        float* cp = reinterpret_cast<float*>(C) + m0w * g.ldc + ncol;
+                        const int ldc_i = (int)g.ldc;
+                        if (g.tmpl == nullptr) {
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        float a = 0.f;
-                        if (col_ok && r < rows_left) {
-                            const long long mr = m0w + r;
-                            if (g.tmpl) a = __ldg(tp);
-                            if (g.resid) {
-                                const long long ri = mr * g.ldr + ncol;
-                                a += g.resid_bf16 ? __bfloat162float(static_cast<const bf16*>(g.resid)[ri])
-                                                  : static_cast<const float*>(g.resid)[ri];
+                            for (int r = 0; r < 32; ++r) cp[(long long)(r * ldc_i)] = tr[r * 32 + ((lane + r) & 31)] + bj;
+                        } else if (trem0 + 32 <= g.rows_per_tmpl) {
+                            const float tb = __ldg(g.tmpl + trow0 * (long long)g.N + ncol) + bj;
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) cp[(long long)(r * ldc_i)] = tr[r * 32 + ((lane + r) & 31)] + tb;
+                        } else if (g.rows_per_tmpl == 1) {
+                            const float* tp = g.tmpl + m0w * (long long)g.N + ncol;
+                            float add[32];
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) add[r] = __ldg(tp + (long long)(r * g.N));
+#pragma unroll
+                            for (int r = 0; r < 32; ++r)
+                                cp[(long long)(r * ldc_i)] = (tr[r * 32 + ((lane + r) & 31)] + bj) + add[r];
+                        } else {
+                            const float* tp = g.tmpl + trow0 * (long long)g.N + ncol;
+                            int trem = trem0;
+                            float add[32];
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) {
+                                add[r] = __ldg(tp);
+                                if (++trem == g.rows_per_tmpl) { trem = 0; tp += g.N; }
+                            }
+#pragma unroll
+                            for (int r = 0; r < 32; ++r)
+                                cp[(long long)(r * ldc_i)] = (tr[r * 32 + ((lane + r) & 31)] + bj) + add[r];
+                        }
+                        continue;
+                    }
+                    // general path (ragged edges, residual, activation)
+                    float add[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) add[r] = 0.f;
+                    if (g.tmpl != nullptr) {
+                        const float* tp = g.tmpl + trow0 * (long long)g.N + ncol;
+                        int trem = trem0;
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            if (col_ok && r < rows_left) add[r] = __ldg(tp);
+                            if (++trem == g.rows_per_tmpl) {   // next output row belongs to the next template
+                                trem = 0;
+                                tp += g.N;
                             }
                         }
-                        add[r] = a;
-                        if (g.tmpl && ++trem == g.rows_per_tmpl) {   // next output row belongs to the next template
-                            trem = 0;
-                            tp += g.N;
+                    }
+                    if (g.resid != nullptr) {
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            if (col_ok && r < rows_left) {
+                                const long long ri = (m0w + r) * g.ldr + ncol;
+                                add[r] += g.resid_bf16 ? __bfloat162float(static_cast<const bf16*>(g.resid)[ri])
+                                                       : static_cast<const float*>(g.resid)[ri];
+                            }
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        if (col_ok && r < rows_left) {
-                            const float o = apply_act_rt(tr[r * 32 + ((lane + r) & 31)] + bj, g.act) + add[r];
-                            st_from_float(C + (m0w + r) * g.ldc + ncol, o);
-                        }
-                    }
+                    for (int r = 0; r < 32; ++r)
+                        if (col_ok && r < rows_left)
+                            st_from_float(C + (m0w + r) * g.ldc + ncol,
+                                          apply_act_rt(tr[r * 32 + ((lane + r) & 31)] + bj, g.act) + add[r]);
                 }
             }
             tc_fence_before();
@@ -468,6 +542,7 @@ int gemm_tc(const GemmParams& g, int c_bf16, int mode, cudaStream_t s) {
     const size_t csz = c_bf16 ? 2 : 4;
     const bool c_tma_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((g.ldc * (long long)csz) % 16 == 0);
     p.resid_vec_ok = 0;
+    p.bias_vec_ok = (g.bias != nullptr) && (reinterpret_cast<uintptr_t>(g.bias) % 16 == 0);
     if (g.resid) {
         const size_t rsz = g.resid_bf16 ? 2 : 4;
         p.resid_vec_ok = (reinterpret_cast<uintptr_t>(g.resid) % 16 == 0) && ((g.ldr * (long long)rsz) % 16 == 0);
@@ -477,6 +552,7 @@ int gemm_tc(const GemmParams& g, int c_bf16, int mode, cudaStream_t s) {
     const bool scalar = (g.tmpl != nullptr) || !c_tma_ok;
     if (scalar) {
         A2F_REQUIRE(!c_bf16, "gemm_tc: template-add / unaligned outputs are fp32 only");
+        A2F_REQUIRE(g.ldc < (1LL << 25) && g.N < (1 << 25), "gemm_tc: scalar epilogue needs ldc, N < 2^25");
         A2F_REQUIRE(mode != 2, "gemm_tc: posconv output must be 16-byte aligned");
     }
 

@@ -13,6 +13,11 @@ import torch
 from . import lib as L
 
 
+# bench.py's roofline pass: when set to a list, every tcgen05 GEMM launch is bracketed by CUDA events on the launch
+# stream and recorded as (kind, algorithmic_flops, start_event, end_event).  None (default) = no instrumentation.
+PROFILE = None
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -62,6 +67,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         raise L.A2FError("tmpl must be fp32")
     if a.dtype != w.dtype:
         raise L.A2FError("A and W must share a dtype")
+    if PROFILE is not None and backend == L.TCGEN05:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        L.check(lib.a2f_gemm(C.byref(g), backend, _stream()), "a2f_gemm")
+        e.record()
+        PROFILE.append(("gemm_tc", 2.0 * g.M * g.N * g.K, s, e))
+        return out
     L.check(lib.a2f_gemm(C.byref(g), backend, _stream()), "a2f_gemm")
     return out
 
@@ -136,8 +148,15 @@ def pack_posconv_weight(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype) ->
 
 def posconv(h: torch.Tensor, wp: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, B: int, T: int, backend: int):
     _dev(h, wp, bias, out)
+    prof = PROFILE is not None and backend == L.TCGEN05
+    if prof:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
     L.check(L.load().a2f_posconv(h.data_ptr(), _dt(h), wp.data_ptr(), bias.data_ptr(), out.data_ptr(), _dt(out), B, T,
                                  backend, _stream()), "a2f_posconv")
+    if prof:
+        e.record()
+        PROFILE.append(("gemm_tc", 2.0 * B * T * 768 * 48 * 128, s, e))
     return out
 
 

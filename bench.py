@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 audio->mesh hot path (contract in the task prompt / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload faceformer|voca]
+
+Workload (BASELINE.json configs[2], the largest single-GPU inference configuration): FaceFormer inference,
+random-init wav2vec2-base encoder + 1-layer biased causal decoder, batch 32 x 5 s synthetic 16 kHz audio at 30 fps,
+5023-vertex FLAME output.  One "step" = one forward of the drop-in module over one batch.  Metric: mesh frames/sec.
+
+For N > 1 the driver launches this file under torch.distributed.run (one rank per GPU, NCCL); the path shards over
+independent utterances, so there is no data-path collective (weak scaling: 32 utterances per GPU); only the timing
+reduction (max over ranks) uses the process group.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# FLOP model of SURVEY.md App. C (2*MAC, KV-cached decode, no padding)
+def ff_flops_per_utt(n_samples: int, T: int) -> float:
+    L = [(n_samples - 10) // 5 + 1]
+    for k in (3, 3, 3, 3, 2, 2):
+        L.append((L[-1] - k) // 2 + 1)
+    fe = 2 * 512 * (10 * L[0] + 512 * 3 * sum(L[1:5]) + 512 * 2 * (L[5] + L[6]))
+    proj = 2 * 512 * 768 * T
+    pos = 2 * 768 * 48 * 128 * T
+    enc_lin = 12 * (8 * 768 ** 2 + 4 * 768 * 3072) * T
+    enc_att = 12 * 4 * 768 * T * T
+    afm = 2 * 768 * 64 * T
+    dec = 81920 * T + 256 * T * (T + 1) / 2
+    head = 2 * (2 * 64 * 15069 * T)
+    return float(fe + proj + pos + enc_lin + enc_att + afm + dec + head)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+_SD_CACHE = {}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: int, threads: int):
+    """Times the oracle (CPU restatement of the reference path, reference O(T^2) decode loop included) on the host."""
+    import torch
+    from oracle import inputs as oin, ref_models as orm, weights as ow
+
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        if workload == "faceformer":
+            sd = _SD_CACHE.get("faceformer") or _SD_CACHE.setdefault("faceformer", ow.make_state_dict("faceformer", 13))
+            n = int(16000 * seconds)
+            audio, oh, tp = oin.audio(n_utt, n, 1), oin.one_hot(n_utt, 12, 1), oin.batch_templates(n_utt, 1, scale=100.0)
+            orm.faceformer_forward(sd, audio[:1, :16000], oh[:1], tp[:1], fps)          # warm-up
+            t0 = time.perf_counter()
+            frames = 0
+            for b in range(n_utt):
+                y = orm.faceformer_forward(sd, audio[b:b + 1], oh[b:b + 1], tp[b:b + 1], fps)
+                frames += y.shape[1]
+            dt = time.perf_counter() - t0
+            return frames / dt, f"{n_utt} utterance(s) x {seconds:g} s @ {fps} fps, fp32, reference O(T^2) decode loop"
+        sd = ow.make_state_dict("voca", 11)
+        B = 4096
+        x, oh, tp = oin.voca_features(B, 1), oin.one_hot(B, 12, 1), oin.batch_templates(B, 1)
+        orm.voca_forward(sd, x[:64], oh[:64], tp[:64])
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 5.0:
+            orm.voca_forward(sd, x, oh, tp)
+            reps += 1
+        dt = time.perf_counter() - t0
+        return reps * B / dt, f"{reps} x {B} windows, fp32"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself does not
+    import: ref:src/model/lightning_model.py:14 needs a missing module, and /root/reference is absent on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        pass
+    for _ in range(max(1, args.steps)):
+        v, sample = cpu_reference_frames_per_s(args.workload, args.fps, args.seconds, 1, threads)
+        vals.append(v)
+    value = statistics.mean(vals)
+    T = int(16000 * args.seconds) * args.fps // 16000
+    line = {
+        "impl": "reference", "metric": "mesh frames/sec (5023-vert FLAME)", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (T / value if args.workload == "faceformer" else 4096 / value),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    if args.workload == "faceformer":
+        T = int(16000 * args.seconds) * args.fps // 16000
+        return {"workload": f"faceformer_inference_b{args.batch}x{args.seconds:g}s_{args.fps}fps (BASELINE.json configs[2])",
+                "batch_per_gpu": args.batch, "audio_seconds": args.seconds, "sample_rate": 16000, "fps": args.fps,
+                "frames_per_utterance": T, "vertices": 5023, "weights": "random-init (oracle.weights seed 13, heads de-zeroed)",
+                "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
+                "template_units": "centimetres (x100, ref lightning_model.py:145-148)"}
+    return {"workload": f"voca_inference_b{args.batch} (BASELINE.json configs[0] shape)", "batch_per_gpu": args.batch,
+            "vertices": 5023, "weights": "random-init (oracle.weights seed 11)",
+            "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import a2f_b200
+    from a2f_b200 import modules, ops, lib as L
+    from oracle import inputs as oin, weights as ow       # input / weight generators only (not the timed path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    L.check(lib.a2f_device_check(), "a2f_device_check")
+
+    B = args.batch
+    if args.workload == "faceformer":
+        n = int(16000 * args.seconds)
+        T = n * args.fps // 16000
+        model = modules.Faceformer(15069, 12)
+        model.load_state_dict(ow.make_state_dict("faceformer", 13), strict=True)
+        model = model.to(dev).eval().set_precision("bf16")
+        h_in = [oin.audio(B, n, 100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(),
+                oin.batch_templates(B, 100 + rank, scale=100.0).pin_memory()]
+        units = B * T
+        flops_step = B * ff_flops_per_utt(n, T)
+        call = lambda a, o, t: model(a, o, t, fps=args.fps)      # noqa: E731
+        out_shape = (B, T, 5023, 3)
+    else:
+        model = modules.Voca(15069, 12)
+        model.load_state_dict(ow.make_state_dict("voca", 11), strict=True)
+        model = model.to(dev).eval().set_precision("bf16")
+        h_in = [oin.voca_features(B, 100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(),
+                oin.batch_templates(B, 100 + rank).pin_memory()]
+        units = B
+        flops_step = B * 1.679e6
+        call = lambda a, o, t: model(a, o, t)                    # noqa: E731
+        out_shape = (B, 5023, 3)
+    d_in = [t.to(dev) for t in h_in]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            out = call(*d_in)
+        barrier()
+        # ------------------------------ device-resident timing (value) ------------------------------
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        launches0 = lib.a2f_launch_count()
+        barrier()
+        for s, e in ev:
+            flush.zero_()                       # L2 flush, outside the event pair
+            s.record()
+            out = call(*d_in)
+            e.record()
+        barrier()
+        launches = lib.a2f_launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        dev_s = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
+        # ------------------------------ end-to-end timing (host buffers) ----------------------------
+        # every step: H2D of the step's inputs from pinned memory, forward, D2H of the step's result into pinned
+        # memory.  Copies run on a side stream so that step i's D2H overlaps step i+1's compute (double-buffered).
+        h_out = [torch.empty(out_shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        comp = torch.cuda.current_stream()
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        outs = [None, None]
+        barrier()
+        t_e2e0 = torch.cuda.Event(enable_timing=True)
+        t_e2e1 = torch.cuda.Event(enable_timing=True)
+        t_e2e0.record()
+        for i in range(args.steps):
+            slot = i & 1
+            comp.wait_event(done[slot])                         # the slot's previous D2H has drained
+            di = [t.to(dev, non_blocking=True) for t in h_in]   # H2D of this step's inputs
+            outs[slot] = call(*di)
+            ready = torch.cuda.Event()
+            ready.record(comp)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                h_out[slot].copy_(outs[slot], non_blocking=True)
+                done[slot].record(copy_stream)
+        comp.wait_stream(copy_stream)
+        t_e2e1.record()
+        barrier()
+        e2e_s = t_e2e0.elapsed_time(t_e2e1) * 1e-3
+        # ------------------------------ per-kernel roofline pass (instrumented, untimed) -------------
+        ops.PROFILE = []
+        for _ in range(2):
+            call(*d_in)
+        torch.cuda.synchronize()
+        prof = ops.PROFILE
+        ops.PROFILE = None
+
+    if world > 1:
+        t = torch.tensor([dev_s, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    total_units = units * world
+    value = total_units * args.steps / dev_s
+    e2e_value = total_units * args.steps / e2e_s
+    h2d = sum(t.numel() * t.element_size() for t in h_in)
+    d2h = 1
+    for d in out_shape:
+        d2h *= d
+    d2h *= 4
+
+    if args.workload == "faceformer":
+        # dominant kernel: the tcgen05 GEMM (all bf16 launches of one forward)
+        gem = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind == "gemm_tc"]
+        g_flops = sum(f for f, _ in gem)
+        g_time = sum(t for _, t in gem)
+        achieved = g_flops / g_time / 1e12
+        roofline = {"bound": "tensor", "kernel": "a2f::gemm_tc_kernel (tcgen05/TMEM/TMA GEMM, all launches of a step)",
+                    "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                    "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                    "launches_per_step": len(gem) // 2, "kernel_share_of_step": (g_time / 2) / (dev_s / args.steps),
+                    "whole_step_tflops": flops_step * world * args.steps / dev_s / 1e12,
+                    "whole_step_frac": flops_step * world * args.steps / dev_s / 1e12 / (pk["bf16_sustained"] * world)}
+    else:
+        head = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind == "gemm_tc"]
+        byts = 2 * (B * 15069 * 4) * len(head)            # template read + vertex write per launch
+        t_head = sum(t for _, t in head)
+        achieved = byts / t_head / 1e9
+        roofline = {"bound": "hbm", "kernel": "a2f::gemm_tc_kernel<256,float,scalar> (vertex head + template add)",
+                    "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                    "traffic": None, "peak_source": pk["source"]}
+
+    threads = os.cpu_count() or 1
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample = cpu_reference_frames_per_s(args.workload, args.fps, args.seconds, 2, threads)
+        cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}
+    else:
+        cpu_baseline = None
+
+    line = {
+        "metric": "mesh frames/sec (5023-vert FLAME)", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dev_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "pinned host buffers in and out through the drop-in module; D2H of step i overlaps step i+1"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--seconds", type=float, default=5.0)
+    ap.add_argument("--fps", type=int, default=30)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 32 if args.workload == "faceformer" else 16384
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
