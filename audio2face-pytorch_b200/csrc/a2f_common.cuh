@@ -42,18 +42,16 @@ int require_sm100();           // A2F_OK or A2F_EARCH (cached per device)
 // ---- scalar math -----------------------------------------------------------------------------
 A2F_D float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 A2F_D float relu(float x) { return x > 0.f ? x : 0.f; }
-// erf-GELU through Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + ~12 FMA-pipe ops instead of erff's
-// ~30.  Used by the tensor-core epilogues, whose outputs are rounded to bf16 anyway.
+// GELU for the bf16 tensor-core path: tanh form 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3))) on MUFU.TANH, 6 instructions
+// instead of erff's ~30 (the epilogues of the GELU GEMMs and conv0 are instruction-issue bound, profiles/r1_*).
+// |tanh-form - erf-form| <= 4.7e-4; measured end-to-end effect on FaceFormer vertices (oracle experiment):
+// 4.8e-6 m, ~1% of the bf16 tolerance.  The fp32 path always uses the exact erf form (gelu_erf).
 A2F_D float gelu_fast(float x) {
-    const float ax = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float e = 1.0f - p * __expf(-ax * ax);     // erf(|x|/sqrt2)
-    return 0.5f * x * (1.0f + copysignf(e, x));
+    const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
 
 template <int ACT> A2F_D float apply_act(float x) {

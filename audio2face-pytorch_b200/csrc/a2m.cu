@@ -1,0 +1,89 @@
+// Audio2Mesh (ref:src/model/audio2face.py:5-69) helpers.  The ten convolutions run as implicit GEMMs (a2f_gemm) over
+// channels-last activations that carry one zero row/column of left padding, so that the im2col row of output position
+// p of a (k=3, stride 2, pad 1) conv is the contiguous slice starting at padded position 2p:
+//   analysis net     [B, 64, W+1, C]  conv along W (formant analysis, ref audio2face.py:13-29)
+//   articulation net [B, H+1, 256]    conv along H (ref audio2face.py:31-47)
+// Each GEMM writes straight into the padded layout of its successor (a2f_gemm_args.c_batch_stride).  Eval-mode
+// BatchNorm that FOLLOWS a conv is folded into the packed weights/bias on the host; the two BatchNorms that PRECEDE a
+// conv (layers 4 and 5 of the articulation net, ref audio2face.py:41-46) cannot be folded because the zero padding is
+// applied after them, so they run as a per-channel affine pass over the un-padded rows (a2f_channel_affine).
+#include "a2f_common.cuh"
+
+namespace a2f {
+
+// x [B,52,32] + tiled one-hot -> out [B,64,33] (single channel), column 0 = left zero pad.
+// ref audio2face.py:59: one_hot.repeat(1,32).view(bs,1,-1,32)  =>  emb[r][c] = one_hot[(32 r + c) % n_onehot]
+__global__ void a2m_assemble_kernel(const float* __restrict__ x, const float* __restrict__ one_hot, int n_onehot,
+                                    float* __restrict__ out, int B) {
+    const long long n = (long long)B * 64 * 33;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int c = (int)(i % 33);
+        const int h = (int)((i / 33) % 64);
+        const long long b = i / (33 * 64);
+        float v = 0.f;
+        if (c > 0) {
+            const int w = c - 1;
+            if (h < 52) v = x[(b * 52 + h) * 32 + w];
+            else v = one_hot[b * n_onehot + ((32 * (h - 52) + w) % n_onehot)];
+        }
+        out[i] = v;
+    }
+}
+
+template <typename T>
+__global__ void channel_affine_kernel(T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                      int C, long long rows_per_batch, long long ld, long long batch_stride,
+                                      long long batches) {
+    const long long n = batches * rows_per_batch * C;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int c = (int)(i % C);
+        const long long row = i / C;
+        const long long b = row / rows_per_batch, r = row % rows_per_batch;
+        T* p = x + b * batch_stride + r * ld + c;
+        st_from_float(p, ld_as_float(p) * scale[c] + shift[c]);
+    }
+}
+
+}  // namespace a2f
+
+using namespace a2f;
+
+extern "C" {
+
+int a2f_a2m_assemble(const float* x, const float* one_hot, int n_onehot, float* out, int B, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(x && one_hot && out && n_onehot > 0, "a2f_a2m_assemble: bad arguments");
+    if (B <= 0) return A2F_OK;
+    const long long n = (long long)B * 64 * 33;
+    const int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+    a2m_assemble_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, one_hot, n_onehot, out, B);
+    A2F_CHECK_LAUNCH("a2m_assemble_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_channel_affine(void* x, int dtype, const float* scale, const float* shift, int C, long long rows_per_batch,
+                       long long ld, long long batch_stride, long long batches, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(x && scale && shift && C > 0 && rows_per_batch > 0 && batches >= 0, "a2f_channel_affine: bad arguments");
+    if (batches == 0) return A2F_OK;
+    const long long n = batches * rows_per_batch * C;
+    const int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+    if (dtype == A2F_BF16)
+        channel_affine_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(static_cast<bf16*>(x), scale, shift, C, rows_per_batch,
+                                                                         ld, batch_stride, batches);
+    else
+        channel_affine_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(static_cast<float*>(x), scale, shift, C,
+                                                                          rows_per_batch, ld, batch_stride, batches);
+    A2F_CHECK_LAUNCH("channel_affine_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+}  // extern "C"

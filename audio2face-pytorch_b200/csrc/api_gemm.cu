@@ -105,6 +105,7 @@ static int fill_params(const a2f_gemm_args* a, GemmParams* p) {
     p->resid = a->resid; p->resid_bf16 = (a->resid_dtype == A2F_BF16); p->ldr = a->ldr;
     p->tmpl = a->tmpl; p->rows_per_tmpl = a->rows_per_tmpl > 0 ? a->rows_per_tmpl : 1;
     p->C = a->C; p->ldc = a->ldc;
+    p->c_batch_stride = a->c_batch_stride > 0 ? a->c_batch_stride : (long long)a->rows_per_batch * a->ldc;
     return A2F_OK;
 }
 
@@ -141,7 +142,7 @@ int a2f_posconv(const void* h, int h_dtype, const void* Wp, const float* bias, v
     p.bias = bias; p.act = A2F_ACT_GELU;
     p.resid = h; p.resid_bf16 = (h_dtype == A2F_BF16); p.ldr = 768;
     p.tmpl = nullptr; p.rows_per_tmpl = 1;
-    p.C = out; p.ldc = 768;
+    p.C = out; p.ldc = 768; p.c_batch_stride = (long long)T * 768;
     if (backend == A2F_BACKEND_SIMT_F32) {
         p.K = 128 * 48; p.ldw = 128 * 48;
         return posconv_simt(p, h_dtype == A2F_BF16, out_dtype == A2F_BF16, as_stream(stream));

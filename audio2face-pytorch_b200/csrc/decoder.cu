@@ -30,26 +30,33 @@ struct DecW {
 };
 
 A2F_D float dot64_smem(const float* w, const float* __restrict__ x) {
-    float acc = 0.f;
+    // four independent accumulators: the 64-term dependent FMA chain (64 x 4 cycles) was the matvec critical path
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int k = 0; k < 64; k += 4) {
         const float4 f = *reinterpret_cast<const float4*>(x + k);
-        acc = fmaf(w[k], f.x, acc);
-        acc = fmaf(w[k + 1], f.y, acc);
-        acc = fmaf(w[k + 2], f.z, acc);
-        acc = fmaf(w[k + 3], f.w, acc);
+        a0 = fmaf(w[k], f.x, a0);
+        a1 = fmaf(w[k + 1], f.y, a1);
+        a2 = fmaf(w[k + 2], f.z, a2);
+        a3 = fmaf(w[k + 3], f.w, a3);
     }
-    return acc;
+    return (a0 + a1) + (a2 + a3);
 }
 
 // LayerNorm(64) of the vector whose elements (lane, lane+32) this warp's lanes hold; eps 1e-5, biased variance.
+// Sum and sum of squares are reduced in the same five shuffle rounds (two independent chains); var = E[x^2] - mean^2.
 A2F_D void warp_ln64(float& a, float& b, float g0, float g1, float b0, float b1) {
-    const float mean = warp_sum(a + b) * (1.f / 64.f);
-    const float da = a - mean, db = b - mean;
-    const float var = warp_sum(da * da + db * db) * (1.f / 64.f);
+    float s1 = a + b, s2 = fmaf(a, a, b * b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float mean = s1 * (1.f / 64.f);
+    const float var = fmaxf(fmaf(-mean, mean, s2 * (1.f / 64.f)), 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
-    a = da * rstd * g0 + b0;
-    b = db * rstd * g1 + b1;
+    a = (a - mean) * rstd * g0 + b0;
+    b = (b - mean) * rstd * g1 + b1;
 }
 
 __global__ void __launch_bounds__(DEC_THREADS, 1)
@@ -247,10 +254,16 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             }
             __syncwarp();
             const int r = tid - 192;
-            float acc = 0.f;
-#pragma unroll 16
-            for (int k = 0; k < 64; ++k) acc = fmaf(wct[k * 64 + r], dc[k], acc);
-            const float e = (fb_bias + acc) + style[r];
+            float f0 = 0.f, f1v = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 64; k += 4) {
+                const float4 dv = *reinterpret_cast<const float4*>(dc + k);
+                f0 = fmaf(wct[k * 64 + r], dv.x, f0);
+                f1v = fmaf(wct[(k + 1) * 64 + r], dv.y, f1v);
+                f2 = fmaf(wct[(k + 2) * 64 + r], dv.z, f2);
+                f3 = fmaf(wct[(k + 3) * 64 + r], dv.w, f3);
+            }
+            const float e = (fb_bias + ((f0 + f1v) + (f2 + f3))) + style[r];
             xs[r] = e + pre0;
         }
         __syncthreads();
@@ -322,7 +335,7 @@ int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory, const
     g.A = memory; g.a_row_stride = 64; g.a_batch_stride = 0; g.rows_per_batch = B * T;
     g.W = w->ca_in_w + 128 * 64; g.ldw = 64; g.bias = w->ca_in_b + 128; g.act = A2F_ACT_NONE;
     g.resid = nullptr; g.resid_bf16 = 0; g.ldr = 0; g.tmpl = nullptr; g.rows_per_tmpl = 1;
-    g.C = tmp; g.ldc = 64;
+    g.C = tmp; g.ldc = 64; g.c_batch_stride = (long long)B * T * 64;
     rc = gemm_simt(g, 0, 0, s);
     if (rc != A2F_OK) return rc;
     g.A = tmp; g.W = w->ca_out_w; g.bias = w->ca_out_b; g.C = ca;

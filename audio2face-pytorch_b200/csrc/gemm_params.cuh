@@ -20,6 +20,7 @@ struct GemmParams {
     int rows_per_tmpl;
     void* C;
     long long ldc;
+    long long c_batch_stride;   // elements between the output blocks of consecutive batches (rows_per_batch*ldc when dense)
 };
 
 int gemm_simt(const GemmParams& p, int a_bf16, int c_bf16, cudaStream_t s);

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
                                   : static_cast<const float*>(p.resid)[ri];
             }
             if (p.tmpl) v += p.tmpl[(long long)(m / p.rows_per_tmpl) * p.N + n];
-            st_from_float(C + (long long)m * p.ldc + nc, v);
+            const long long crow = (long long)(m / p.rows_per_batch) * p.c_batch_stride + (long long)(m % p.rows_per_batch) * p.ldc;
+            st_from_float(C + crow + nc, v);
         }
     }
 }

@@ -257,6 +257,10 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         int acc = 0;
         uint32_t acc_phase = 0;
         TC* __restrict__ C = static_cast<TC*>(g.C);
+        // kernel parameters used per element live in registers (constant-bank reads showed up as stalls, profiles/r1_ffn1)
+        const float* __restrict__ e_bias = g.bias;
+        const void* __restrict__ e_resid = g.resid;
+        const int e_act = g.act;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
             const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
@@ -283,37 +287,36 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     const int col0 = blk * SBW;          // within the tile
                     if (col0 >= n_lim) break;            // uniform across the CTA
                     const int ncol0 = n_tile0 + col0;    // global column of the block
+                    // accumulator -> registers, bias / activation / residual (overlaps the previous block's TMA store)
+                    float v[SBW];
+#pragma unroll
+                    for (int cc = 0; cc < SBW / CH; ++cc) {
+                        if (CH == 32) tmem_ld_32x32(t_row + col0 + cc * CH, v + cc * CH);
+                        else tmem_ld_32x16(t_row + col0 + cc * CH, v + cc * CH);
+                    }
+                    tmem_ld_wait();
+                    epi_bias_act<SBW>(v, e_bias, p.bias_vec_ok, ncol0, n_end, e_act, p.fast_gelu);
+                    if (e_resid != nullptr && row_ok)
+                        epi_resid<SBW>(v, e_resid, g.resid_bf16, m * g.ldr + ncol0, ncol0, n_end, p.resid_vec_ok);
                     // the previous TMA store of this half must have finished reading the staging block
                     if (leader) tma_store_wait_read();
                     named_bar_sync(bar_id, 128);
-#pragma unroll 1
-                    for (int cc = 0; cc < SBW / CH; ++cc) {
-                        float v[CH];
-                        if (CH == 32) tmem_ld_32x32(t_row + col0 + cc * CH, v);
-                        else tmem_ld_32x16(t_row + col0 + cc * CH, v);
-                        tmem_ld_wait();
-                        const int nc = ncol0 + cc * CH;
-                        epi_bias_act<CH>(v, g.bias, p.bias_vec_ok, nc, n_end, g.act, p.fast_gelu);
-                        if (g.resid != nullptr && row_ok)
-                            epi_resid<CH>(v, g.resid, g.resid_bf16, m * g.ldr + nc, nc, n_end, p.resid_vec_ok);
 #pragma unroll
-                        for (int k = 0; k < CH / EPC; ++k) {
-                            const int ch = cc * (CH / EPC) + k;
-                            const int pch = Cfg::SWZ ? (ch ^ (r_tile & 7)) : ch;
-                            uint4 u;
-                            if (sizeof(TC) == 2) {
-                                u.x = pack_bf16x2(v[k * 8 + 0], v[k * 8 + 1]);
-                                u.y = pack_bf16x2(v[k * 8 + 2], v[k * 8 + 3]);
-                                u.z = pack_bf16x2(v[k * 8 + 4], v[k * 8 + 5]);
-                                u.w = pack_bf16x2(v[k * 8 + 6], v[k * 8 + 7]);
-                            } else {
-                                u.x = __float_as_uint(v[k * EPC + 0]);
-                                u.y = __float_as_uint(v[k * EPC + 1]);
-                                u.z = __float_as_uint(v[k * EPC + 2]);
-                                u.w = __float_as_uint(v[k * EPC + 3]);
-                            }
-                            *reinterpret_cast<uint4*>(rowp + pch * 16) = u;
+                    for (int ch = 0; ch < SBW / EPC; ++ch) {
+                        const int pch = Cfg::SWZ ? (ch ^ (r_tile & 7)) : ch;
+                        uint4 u;
+                        if (sizeof(TC) == 2) {
+                            u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+                            u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+                            u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+                            u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+                        } else {
+                            u.x = __float_as_uint(v[ch * EPC + 0]);
+                            u.y = __float_as_uint(v[ch * EPC + 1]);
+                            u.z = __float_as_uint(v[ch * EPC + 2]);
+                            u.w = __float_as_uint(v[ch * EPC + 3]);
                         }
+                        *reinterpret_cast<uint4*>(rowp + pch * 16) = u;
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(bar_id, 128);
@@ -328,6 +331,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                 constexpr int NCH = BN / 32;
                 const int rows_left = g.rows_per_batch - (lt * TBM + q * 32);   // rows of this warp that exist
                 const long long m0w = (long long)b * g.rows_per_batch + lt * TBM + q * 32;
+                const long long c_row0 = (long long)b * g.c_batch_stride + (long long)(lt * TBM + q * 32) * g.ldc;
                 // template row of the warp's first output row; later rows advance it incrementally (no per-element
                 // 64-bit division in the store loop)
                 const long long trow0 = g.tmpl ? m0w / g.rows_per_tmpl : 0;
@@ -351,7 +355,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                         // common case of the vertex head: no predicates, one 64-bit address per chunk, 32 independent
                         // rows in flight.  Template rows: one shared row (FaceFormer: T frames per utterance) or one per
                         // output row (VOCA / Audio2Mesh).
-                        float* cp = reinterpret_cast<float*>(C) + m0w * g.ldc + ncol;
+                        float* cp = reinterpret_cast<float*>(C) + c_row0 + ncol;
                         const int ldc_i = (int)g.ldc;
                         if (g.tmpl == nullptr) {
 #pragma unroll
@@ -412,7 +416,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
 #pragma unroll
                     for (int r = 0; r < 32; ++r)
                         if (col_ok && r < rows_left)
-                            st_from_float(C + (m0w + r) * g.ldc + ncol,
+                            st_from_float(C + c_row0 + (long long)r * g.ldc + ncol,
                                           apply_act_rt(tr[r * 32 + ((lane + r) & 31)] + bj, g.act) + add[r]);
                 }
             }
@@ -457,7 +461,7 @@ static int encode_c_and_launch(TmapSet& maps, const TcParams& p, bool scalar, cu
     const GemmParams& g = p.g;
     const int ncols_total = (p.mode == 2) ? 768 : g.N;
     uint64_t dims[3] = {(uint64_t)ncols_total, (uint64_t)g.rows_per_batch, (uint64_t)p.num_batches};
-    uint64_t strides[2] = {(uint64_t)g.ldc * sizeof(TC), (uint64_t)g.ldc * g.rows_per_batch * sizeof(TC)};
+    uint64_t strides[2] = {(uint64_t)g.ldc * sizeof(TC), (uint64_t)g.c_batch_stride * sizeof(TC)};
     uint32_t box[3] = {(uint32_t)Cfg::SBW, TBM, 1};
     int rc = encode_tmap(&maps.c, g.C, (int)sizeof(TC), 3, dims, strides, box, Cfg::SWZ ? 1 : 0);
     if (rc != A2F_OK) return rc;
@@ -540,7 +544,8 @@ int gemm_tc(const GemmParams& g, int c_bf16, int mode, cudaStream_t s) {
     }
 
     const size_t csz = c_bf16 ? 2 : 4;
-    const bool c_tma_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((g.ldc * (long long)csz) % 16 == 0);
+    const bool c_tma_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((g.ldc * (long long)csz) % 16 == 0) &&
+                          ((g.c_batch_stride * (long long)csz) % 16 == 0);
     p.resid_vec_ok = 0;
     p.bias_vec_ok = (g.bias != nullptr) && (reinterpret_cast<uintptr_t>(g.bias) % 16 == 0);
     if (g.resid) {

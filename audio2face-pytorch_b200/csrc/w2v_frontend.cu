@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
                                                           const float* __restrict__ beta, TO* __restrict__ out,
                                                           long long N, int L0, long long out_batch_stride) {
     const int b = blockIdx.y, t0 = blockIdx.x * C0_TCH;
-    __shared__ float xs[5 * C0_TCH + 8];
+    __shared__ __align__(16) float xs[5 * C0_TCH + 8];
     const float* x = audio + (long long)b * N;
     const float mean = stats[2 * b], rstd = stats[2 * b + 1];
-    const int nx = 5 * C0_TCH + 5;
+    const int nx = 5 * C0_TCH + 8;       // 5 extra taps of the last window + float4 over-read, zero filled
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
         const long long gi = 5LL * t0 + i;
-        xs[i] = gi < N ? (x[gi] - mean) * rstd : 0.f;
+        xs[i] = (gi < N && i < 5 * C0_TCH + 5) ? (x[gi] - mean) * rstd : 0.f;
     }
     // each thread owns two adjacent channels (one packed 4-byte store in bf16, coalesced either way)
     const int c = threadIdx.x * 2;
@@ -159,22 +159,40 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
     }
     const float2 g0 = gn[b * 512 + c], g1 = gn[b * 512 + c + 1];
     const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
+    // bf16 path: GroupNorm affine folded to one FMA (y = conv*A + Bc) and the MUFU.TANH GELU; fp32 path: literal form
+    const float A0 = g0.y * ga0, A1 = g1.y * ga1;
+    const float B0 = be0 - g0.x * A0, B1 = be1 - g1.x * A1;
     __syncthreads();
     TO* o = out + (long long)b * out_batch_stride;
     const int tn = min(C0_TCH, L0 - t0);
-    for (int tt = 0; tt < tn; ++tt) {
-        float a0 = 0.f, a1 = 0.f;
+    for (int t4 = 0; t4 < tn; t4 += 4) {
+        // four output steps share one 28-float window of the audio (7 LDS.128 instead of 40 scalar LDS)
+        float xw[28];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            const float xv = xs[5 * tt + k];
-            a0 = fmaf(w0[k], xv, a0);
-            a1 = fmaf(w1[k], xv, a1);
+        for (int qd = 0; qd < 7; ++qd) {
+            const float4 f = *reinterpret_cast<const float4*>(xs + 5 * t4 + 4 * qd);
+            xw[4 * qd] = f.x; xw[4 * qd + 1] = f.y; xw[4 * qd + 2] = f.z; xw[4 * qd + 3] = f.w;
         }
-        const float y0 = gelu_erf((a0 - g0.x) * g0.y * ga0 + be0);
-        const float y1 = gelu_erf((a1 - g1.x) * g1.y * ga1 + be1);
-        TO* p = o + (long long)(t0 + tt) * 512 + c;
-        if (sizeof(TO) == 2) *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(y0, y1);
-        else *reinterpret_cast<float2*>(p) = make_float2(y0, y1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (t4 + u >= tn) break;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                a0 = fmaf(w0[k], xw[5 * u + k], a0);
+                a1 = fmaf(w1[k], xw[5 * u + k], a1);
+            }
+            TO* p = o + (long long)(t0 + t4 + u) * 512 + c;
+            if (sizeof(TO) == 2) {
+                const float y0 = gelu_fast(fmaf(a0, A0, B0));
+                const float y1 = gelu_fast(fmaf(a1, A1, B1));
+                *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(y0, y1);
+            } else {
+                const float y0 = gelu_erf((a0 - g0.x) * g0.y * ga0 + be0);
+                const float y1 = gelu_erf((a1 - g1.x) * g1.y * ga1 + be1);
+                *reinterpret_cast<float2*>(p) = make_float2(y0, y1);
+            }
+        }
     }
 }
 

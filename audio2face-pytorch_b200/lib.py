@@ -33,7 +33,7 @@ class GemmArgs(C.Structure):
         ("bias", c_void_p), ("act", c_int),
         ("resid", c_void_p), ("resid_dtype", c_int), ("ldr", c_ll),
         ("tmpl", c_void_p), ("rows_per_tmpl", c_int),
-        ("C", c_void_p), ("c_dtype", c_int), ("ldc", c_ll),
+        ("C", c_void_p), ("c_dtype", c_int), ("ldc", c_ll), ("c_batch_stride", c_ll),
     ]
 
 
@@ -82,6 +82,8 @@ _SIGNATURES = {
     "a2f_pack_feedback": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "a2f_voca_trunk": (c_int, [C.POINTER(VocaWeights), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p]),
+    "a2f_a2m_assemble": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "a2f_channel_affine": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_ll, c_ll, c_ll, c_void_p]),
     "a2f_voca_loss_workspace_bytes": (c_size_t, []),
     "a2f_voca_loss_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_void_p, c_void_p, c_size_t,
                                   c_void_p]),

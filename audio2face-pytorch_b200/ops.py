@@ -40,7 +40,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
          act: int = L.ACT_NONE, resid: Optional[torch.Tensor] = None, tmpl: Optional[torch.Tensor] = None,
          rows_per_tmpl: int = 1, backend: int = L.SIMT_F32, M: Optional[int] = None, K: Optional[int] = None,
          a_row_stride: Optional[int] = None, a_batch_stride: int = 0, rows_per_batch: Optional[int] = None,
-         N: Optional[int] = None, ldw: Optional[int] = None, ldc: Optional[int] = None) -> torch.Tensor:
+         N: Optional[int] = None, ldw: Optional[int] = None, ldc: Optional[int] = None, c_batch_stride: int = 0,
+         c_offset: int = 0) -> torch.Tensor:
     """out[m,n] = act(sum_k a[m,k] w[n,k] + bias[n]) + resid[m,n] + tmpl[m // rows_per_tmpl, n]  (a2f_gemm)."""
     _dev(a, w, out, bias, resid, tmpl)
     lib = L.load()
@@ -59,8 +60,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         g.resid, g.resid_dtype, g.ldr = resid.data_ptr(), _dt(resid), int(resid.stride(0))
     if tmpl is not None:
         g.tmpl, g.rows_per_tmpl = tmpl.data_ptr(), int(rows_per_tmpl)
-    g.C, g.c_dtype = out.data_ptr(), _dt(out)
+    g.C, g.c_dtype = out.data_ptr() + int(c_offset) * out.element_size(), _dt(out)
     g.ldc = int(ldc if ldc is not None else out.stride(0))
+    g.c_batch_stride = int(c_batch_stride)
     if bias is not None and bias.dtype != torch.float32:
         raise L.A2FError("bias must be fp32")
     if tmpl is not None and tmpl.dtype != torch.float32:
@@ -207,6 +209,24 @@ def mha(qkv: torch.Tensor, out: torch.Tensor, B: int, T: int, H: int = 12, D: in
     _dev(qkv, out)
     L.check(L.load().a2f_mha_fwd(qkv.data_ptr(), out.data_ptr(), _dt(qkv), B, T, H, D, scale, _stream()), "a2f_mha_fwd")
     return out
+
+
+def a2m_assemble(x: torch.Tensor, one_hot: torch.Tensor) -> torch.Tensor:
+    """x [B,52,32], one_hot [B,n] -> zero-left-padded single-channel input [B,64,33] (a2f_a2m_assemble)."""
+    _dev(x, one_hot)
+    B = x.shape[0]
+    out = torch.empty((B, 64, 33), dtype=torch.float32, device=x.device)
+    L.check(L.load().a2f_a2m_assemble(x.data_ptr(), one_hot.data_ptr(), one_hot.shape[1], out.data_ptr(), B, _stream()),
+            "a2f_a2m_assemble")
+    return out
+
+
+def channel_affine(buf: torch.Tensor, offset: int, scale: torch.Tensor, shift: torch.Tensor, C_: int, rows_per_batch: int,
+                   ld: int, batch_stride: int, batches: int) -> None:
+    _dev(buf, scale, shift)
+    L.check(L.load().a2f_channel_affine(buf.data_ptr() + offset * buf.element_size(), _dt(buf), scale.data_ptr(),
+                                        shift.data_ptr(), C_, rows_per_batch, ld, batch_stride, batches, _stream()),
+            "a2f_channel_affine")
 
 
 def pack_feedback(vm_w, vm_b, vmr_w, vmr_b):

@@ -82,6 +82,9 @@ typedef struct a2f_gemm_args {
     void* C;
     int c_dtype;
     long long ldc;
+    long long c_batch_stride; /* elements between the output blocks of consecutive batches; 0 = dense
+                                 (rows_per_batch*ldc).  Lets a conv layer write straight into the zero-padded
+                                 layout its successor reads (Audio2Mesh). */
 } a2f_gemm_args;
 
 int a2f_gemm(const a2f_gemm_args* args, int backend, void* stream);
@@ -197,6 +200,19 @@ typedef struct a2f_voca_weights {
 } a2f_voca_weights;
 int a2f_voca_trunk(const a2f_voca_weights* w, const float* x, const float* one_hot, int n_onehot, void* z, int z_dtype,
                    int ldz, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Audio2Mesh (ref:src/model/audio2face.py:5-69).  The ten convolutions are a2f_gemm calls over channels-last
+ * activations with one zero row/column of left padding ([B,64,W+1,C] for the analysis net, [B,H+1,256] for the
+ * articulation net); these two helpers build the first padded activation and apply the BatchNorms that precede a conv.
+ *  a2f_a2m_assemble: x [B,52,32] + tiled one_hot (emb[r][c] = one_hot[(32r+c) % n_onehot], ref audio2face.py:59)
+ *                    -> out [B,64,33] fp32, column 0 zero.
+ *  a2f_channel_affine: in place x[b, r, c] = x*scale[c] + shift[c] for r < rows_per_batch (element (b,r,c) at
+ *                    x + b*batch_stride + r*ld + c).
+ * ---------------------------------------------------------------------------------------------------------- */
+int a2f_a2m_assemble(const float* x, const float* one_hot, int n_onehot, float* out, int B, void* stream);
+int a2f_channel_affine(void* x, int dtype, const float* scale, const float* shift, int C, long long rows_per_batch,
+                       long long ld, long long batch_stride, long long batches, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Losses (ref:src/loss/loss.py:24-55; FaceFormerLoss :4-17 is the same with bs = T after dropping an odd last
