@@ -106,6 +106,21 @@ static int fill_params(const a2f_gemm_args* a, GemmParams* p) {
     p->tmpl = a->tmpl; p->rows_per_tmpl = a->rows_per_tmpl > 0 ? a->rows_per_tmpl : 1;
     p->C = a->C; p->ldc = a->ldc;
     p->c_batch_stride = a->c_batch_stride > 0 ? a->c_batch_stride : (long long)a->rows_per_batch * a->ldc;
+    p->a_rows = a->a_rows > 0 ? a->a_rows : a->rows_per_batch;
+    A2F_REQUIRE(a->n_seg >= 0 && a->n_seg <= 4, "a2f_gemm: n_seg must be 0..4");
+    p->n_seg = a->n_seg <= 1 ? 0 : a->n_seg;
+    A2F_REQUIRE(p->n_seg == 0 || a->K % p->n_seg == 0, "a2f_gemm: K must be a multiple of n_seg");
+    for (int i = 0; i < 4; ++i) {
+        p->seg_row_off[i] = a->seg_row_off[i];
+        p->seg_col_off[i] = a->seg_col_off[i];
+    }
+    if (a->n_seg == 1) {   // one explicit segment: still honours its row / column offset
+        p->n_seg = 1;
+    }
+    p->r_batch_stride = a->r_batch_stride > 0 ? a->r_batch_stride : (long long)a->rows_per_batch * a->ldr;
+    p->resid_mode = a->resid_mode;
+    A2F_REQUIRE(a->resid_mode == A2F_RESID_ADD || (a->resid_mode == A2F_RESID_DACT && a->resid != nullptr),
+                "a2f_gemm: bad resid_mode");
     return A2F_OK;
 }
 
@@ -130,6 +145,36 @@ int a2f_gemm(const a2f_gemm_args* args, int backend, void* stream) {
     return set_error(A2F_EINVAL, "a2f_gemm: unknown backend");
 }
 
+int a2f_gemm_wgrad(const a2f_wgrad_args* a, int backend, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(a != nullptr, "a2f_gemm_wgrad: args is NULL");
+    A2F_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "a2f_gemm_wgrad: bad M/N/K");
+    A2F_REQUIRE(a->dY && a->X && a->dW, "a2f_gemm_wgrad: dY, X and dW must be non-NULL");
+    A2F_REQUIRE(a->rows_per_batch > 0 && a->M % a->rows_per_batch == 0, "a2f_gemm_wgrad: M must be a multiple of rows_per_batch");
+    A2F_REQUIRE(a->n_seg >= 0 && a->n_seg <= 4, "a2f_gemm_wgrad: n_seg must be 0..4");
+    A2F_REQUIRE(a->dtype == A2F_F32 || a->dtype == A2F_BF16, "a2f_gemm_wgrad: bad dtype");
+    if (a->M == 0) return A2F_OK;
+    WgradParams p;
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.dY = a->dY; p.dy_row_stride = a->dy_row_stride; p.dy_batch_stride = a->dy_batch_stride;
+    p.X = a->X; p.x_row_stride = a->x_row_stride; p.x_batch_stride = a->x_batch_stride;
+    p.rows_per_batch = a->rows_per_batch;
+    p.x_rows = a->x_rows > 0 ? a->x_rows : a->rows_per_batch;
+    p.n_seg = a->n_seg < 1 ? 1 : a->n_seg;
+    for (int i = 0; i < 4; ++i) {
+        p.x_row_off[i] = a->n_seg < 1 ? 0 : a->x_row_off[i];
+        p.x_col_off[i] = a->n_seg < 1 ? 0 : a->x_col_off[i];
+    }
+    p.dW = a->dW; p.ldw = a->ldw;
+    if (backend == A2F_BACKEND_SIMT_F32) return wgrad_simt(p, a->dtype == A2F_BF16, as_stream(stream));
+    if (backend == A2F_BACKEND_TCGEN05) {
+        A2F_REQUIRE(a->dtype == A2F_BF16, "a2f_gemm_wgrad: the tcgen05 backend takes bf16 operands");
+        return wgrad_tc(p, as_stream(stream));
+    }
+    return set_error(A2F_EINVAL, "a2f_gemm_wgrad: unknown backend");
+}
+
 int a2f_posconv(const void* h, int h_dtype, const void* Wp, const float* bias, void* out, int out_dtype, int B, int T,
                 int backend, void* stream) {
     int rc = require_sm100();
@@ -143,6 +188,8 @@ int a2f_posconv(const void* h, int h_dtype, const void* Wp, const float* bias, v
     p.resid = h; p.resid_bf16 = (h_dtype == A2F_BF16); p.ldr = 768;
     p.tmpl = nullptr; p.rows_per_tmpl = 1;
     p.C = out; p.ldc = 768; p.c_batch_stride = (long long)T * 768;
+    p.a_rows = T; p.n_seg = 0; p.r_batch_stride = (long long)T * 768; p.resid_mode = A2F_RESID_ADD;
+    for (int i = 0; i < 4; ++i) p.seg_row_off[i] = p.seg_col_off[i] = 0;
     if (backend == A2F_BACKEND_SIMT_F32) {
         p.K = 128 * 48; p.ldw = 128 * 48;
         return posconv_simt(p, h_dtype == A2F_BF16, out_dtype == A2F_BF16, as_stream(stream));

@@ -21,11 +21,56 @@ struct GemmParams {
     void* C;
     long long ldc;
     long long c_batch_stride;   // elements between the output blocks of consecutive batches (rows_per_batch*ldc when dense)
+    // backward-pass extensions (a2f.h): explicit K segments with row / column offsets, zero rows outside [0,a_rows),
+    // batch stride of resid, resid_mode 1 = multiply by act'(resid)
+    int a_rows = 0;               // 0 = rows_per_batch (normalised by normalize_gemm)
+    int n_seg = 0;
+    int seg_row_off[4] = {0, 0, 0, 0};
+    int seg_col_off[4] = {0, 0, 0, 0};
+    long long r_batch_stride = 0; // 0 = rows_per_batch * ldr
+    int resid_mode = 0;
+};
+
+inline void normalize_gemm(GemmParams& p) {
+    if (p.a_rows <= 0) p.a_rows = p.rows_per_batch;
+    if (p.r_batch_stride <= 0) p.r_batch_stride = (long long)p.rows_per_batch * p.ldr;
+}
+
+struct WgradParams {
+    int M, N, K;
+    const void* dY;
+    long long dy_row_stride, dy_batch_stride;
+    const void* X;
+    long long x_row_stride, x_batch_stride;
+    int rows_per_batch, x_rows;
+    int n_seg;
+    int x_row_off[4];
+    int x_col_off[4];
+    float* dW;
+    long long ldw;
 };
 
 int gemm_simt(const GemmParams& p, int a_bf16, int c_bf16, cudaStream_t s);
 int posconv_simt(const GemmParams& p, int a_bf16, int c_bf16, cudaStream_t s);
 // tcgen05 back end (bf16 operands).  mode 0: plain / strided-row implicit GEMM, mode 2: positional conv.
 int gemm_tc(const GemmParams& p, int c_bf16, int mode, cudaStream_t s);
+int wgrad_simt(const WgradParams& p, int bf16_in, cudaStream_t s);
+int wgrad_tc(const WgradParams& p, cudaStream_t s);
+
+// derivative of the forward activation at pre-activation z (resid_mode A2F_RESID_DACT)
+A2F_D float act_grad(float z, int act) {
+    switch (act) {
+        case A2F_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+        case A2F_ACT_GELU: {
+            const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
+            return cdf + z * 0.39894228040143267794f * __expf(-0.5f * z * z);
+        }
+        case A2F_ACT_TANH: {
+            const float t = tanhf(z);
+            return 1.f - t * t;
+        }
+        default: return 1.f;
+    }
+}
 
 }  // namespace a2f

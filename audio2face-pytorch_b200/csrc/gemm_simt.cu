@@ -34,14 +34,19 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
     // per-thread A row base (row index fixed across the k loop)
     const int am = m0 + lrow;
     const bool a_row_ok = am < p.M;
-    long long a_base = 0;
+    long long a_base = 0, a_bbase = 0;
     int a_t = 0;
+    bool a_in_range = a_row_ok;
+    const int kseg = p.n_seg > 0 ? p.K / p.n_seg : p.K;
     if (a_row_ok) {
         int b = am / p.rows_per_batch, r = am % p.rows_per_batch;
-        if (MODE == 0) a_base = (long long)b * p.a_batch_stride + (long long)r * p.a_row_stride;
-        else {
+        a_t = r;
+        if (MODE == 0) {
+            a_bbase = (long long)b * p.a_batch_stride;
+            a_base = a_bbase + (long long)r * p.a_row_stride;
+            a_in_range = r < p.a_rows;
+        } else {
             a_base = (long long)b * p.rows_per_batch * p.a_row_stride;
-            a_t = r;
         }
     }
     const int wn = n0 + lrow;
@@ -61,8 +66,16 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
             float av = 0.f, wv = 0.f;
             if (k < p.K) {
                 if (a_row_ok) {
-                    if (MODE == 0) av = ld_as_float(A + a_base + k);
-                    else {
+                    if (MODE == 0) {
+                        if (p.n_seg > 0) {
+                            const int sg = k / kseg, kk = k - sg * kseg;
+                            const int row = a_t + p.seg_row_off[sg];
+                            if (row >= 0 && row < p.a_rows)
+                                av = ld_as_float(A + a_bbase + (long long)row * p.a_row_stride + p.seg_col_off[sg] + kk);
+                        } else if (a_in_range) {
+                            av = ld_as_float(A + a_base + k);
+                        }
+                    } else {
                         int tap = k / 48, c = k - tap * 48;
                         int t = a_t + tap - 64;
                         if (t >= 0 && t < p.rows_per_batch)
@@ -100,12 +113,21 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
             if (n >= p.N) continue;
             int nc = n + col_off;
             float v = acc[i][j];
-            if (bias) v += bias[nc];
-            v = apply_act_rt(v, p.act);
-            if (p.resid) {
-                long long ri = (long long)m * p.ldr + nc;
-                v += p.resid_bf16 ? __bfloat162float(static_cast<const bf16*>(p.resid)[ri])
-                                  : static_cast<const float*>(p.resid)[ri];
+            if (p.resid_mode == A2F_RESID_DACT) {
+                const long long ri = (long long)(m / p.rows_per_batch) * p.r_batch_stride +
+                                     (long long)(m % p.rows_per_batch) * p.ldr + nc;
+                const float z = p.resid_bf16 ? __bfloat162float(static_cast<const bf16*>(p.resid)[ri])
+                                             : static_cast<const float*>(p.resid)[ri];
+                v *= act_grad(z, p.act);
+            } else {
+                if (bias) v += bias[nc];
+                v = apply_act_rt(v, p.act);
+                if (p.resid) {
+                    const long long ri = (long long)(m / p.rows_per_batch) * p.r_batch_stride +
+                                         (long long)(m % p.rows_per_batch) * p.ldr + nc;
+                    v += p.resid_bf16 ? __bfloat162float(static_cast<const bf16*>(p.resid)[ri])
+                                      : static_cast<const float*>(p.resid)[ri];
+                }
             }
             if (p.tmpl) v += p.tmpl[(long long)(m / p.rows_per_tmpl) * p.N + n];
             const long long crow = (long long)(m / p.rows_per_batch) * p.c_batch_stride + (long long)(m % p.rows_per_batch) * p.ldc;
@@ -125,12 +147,100 @@ template <int MODE> static int launch_simt(const GemmParams& p, int a_bf16, int 
     return A2F_OK;
 }
 
-int gemm_simt(const GemmParams& p, int a_bf16, int c_bf16, cudaStream_t s) {
-    if (p.M <= 0 || p.N <= 0) return A2F_OK;
+int gemm_simt(const GemmParams& p_in, int a_bf16, int c_bf16, cudaStream_t s) {
+    if (p_in.M <= 0 || p_in.N <= 0) return A2F_OK;
+    GemmParams p = p_in;
+    normalize_gemm(p);
     return launch_simt<0>(p, a_bf16, c_bf16, 1, s);
 }
-int posconv_simt(const GemmParams& p, int a_bf16, int c_bf16, cudaStream_t s) {
+int posconv_simt(const GemmParams& p_in, int a_bf16, int c_bf16, cudaStream_t s) {
+    GemmParams p = p_in;
+    normalize_gemm(p);
     return launch_simt<2>(p, a_bf16, c_bf16, 16, s);
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[n, s*K + k] += sum_m dY[m, n] * X[(b, r + roff[s]), coff[s] + k].  64x64 output tiles, the M reduction split over
+// blockIdx.z, fp32 atomics into dW (the fp32 parity path; ordering noise ~1e-7 relative).
+constexpr int WG_ROWS = 512;   // reduction rows per CTA
+
+template <typename TI>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradParams p) {
+    __shared__ float As[SBK][SBM + 4];   // [m][n]
+    __shared__ float Bs[SBK][SBN + 4];   // [m][kcol]
+    const TI* __restrict__ dY = static_cast<const TI*>(p.dY);
+    const TI* __restrict__ X = static_cast<const TI*>(p.X);
+    const int n0 = blockIdx.y * SBM, c0 = blockIdx.x * SBN;
+    const int ktot = p.K * p.n_seg;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int lcol = tid % 64, lm = tid / 64;      // 4 m-rows per pass, 64 columns
+    // column of this thread's X loads: segment / offset are fixed across the reduction
+    const int xc = c0 + lcol;
+    const bool xc_ok = xc < ktot;
+    const int sg = xc_ok ? xc / p.K : 0;
+    const int xk = xc_ok ? xc - sg * p.K : 0;
+    const int roff = p.x_row_off[sg], coff = p.x_col_off[sg];
+    const int yn = n0 + lcol;
+    const bool yn_ok = yn < p.N;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const long long m_begin = (long long)blockIdx.z * WG_ROWS;
+    const long long m_end = m_begin + WG_ROWS < p.M ? m_begin + WG_ROWS : p.M;
+    for (long long mb = m_begin; mb < m_end; mb += SBK) {
+#pragma unroll
+        for (int q = 0; q < SBK / 4; ++q) {
+            const int kk = q * 4 + lm;
+            const long long m = mb + kk;
+            float yv = 0.f, xv = 0.f;
+            if (m < m_end) {
+                const int b = (int)(m / p.rows_per_batch), r = (int)(m % p.rows_per_batch);
+                if (yn_ok) yv = ld_as_float(dY + (long long)b * p.dy_batch_stride + (long long)r * p.dy_row_stride + yn);
+                const int xr = r + roff;
+                if (xc_ok && xr >= 0 && xr < p.x_rows)
+                    xv = ld_as_float(X + (long long)b * p.x_batch_stride + (long long)xr * p.x_row_stride + coff + xk);
+            }
+            As[kk][lcol] = yv;
+            Bs[kk][lcol] = xv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SBK; ++kk) {
+            float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + tx * 4 + j;
+            if (c < ktot) atomicAdd(p.dW + (long long)n * p.ldw + c, acc[i][j]);
+        }
+    }
+}
+
+int wgrad_simt(const WgradParams& p, int bf16_in, cudaStream_t s) {
+    const int ktot = p.K * p.n_seg;
+    dim3 grid((ktot + SBN - 1) / SBN, (p.N + SBM - 1) / SBM, (p.M + WG_ROWS - 1) / WG_ROWS);
+    if (bf16_in) wgrad_simt_kernel<bf16><<<grid, 256, 0, s>>>(p);
+    else wgrad_simt_kernel<float><<<grid, 256, 0, s>>>(p);
+    A2F_CHECK_LAUNCH("wgrad_simt_kernel");
+    count_launch();
+    return A2F_OK;
 }
 
 }  // namespace a2f

@@ -202,6 +202,13 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     if (p.mode == 2) {
                         tma_load_3d(dstA, &maps.a[0], &full_bar[stage], nb * 48, lt * TBM + kb - 64, b);
                         tma_load_2d(dstB, &maps.b, &full_bar[stage], kb * TBK, nb * 48);
+                    } else if (p.g.n_seg > 0) {
+                        // explicit K segments (data gradient of the strided convs): one map, per-segment row / column
+                        // offsets; rows outside [0, a_rows) are zero-filled by the TMA unit
+                        const int seg = kb / p.kb_per_seg, kin = (kb - seg * p.kb_per_seg) * TBK;
+                        tma_load_3d(dstA, &maps.a[0], &full_bar[stage], p.g.seg_col_off[seg] + kin,
+                                    lt * TBM + p.g.seg_row_off[seg], b);
+                        tma_load_2d(dstB, &maps.b, &full_bar[stage], kb * TBK, nb * BN);
                     } else {
                         const int seg = kb / p.kb_per_seg, kin = (kb - seg * p.kb_per_seg) * TBK;
                         tma_load_3d(dstA, &maps.a[seg], &full_bar[stage], kin, lt * TBM, b);
@@ -261,6 +268,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         const float* __restrict__ e_bias = g.bias;
         const void* __restrict__ e_resid = g.resid;
         const int e_act = g.act;
+        const bool e_dact = g.resid_mode == A2F_RESID_DACT;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
             const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
@@ -295,9 +303,22 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                         else tmem_ld_32x16(t_row + col0 + cc * CH, v + cc * CH);
                     }
                     tmem_ld_wait();
-                    epi_bias_act<SBW>(v, e_bias, p.bias_vec_ok, ncol0, n_end, e_act, p.fast_gelu);
-                    if (e_resid != nullptr && row_ok)
-                        epi_resid<SBW>(v, e_resid, g.resid_bf16, m * g.ldr + ncol0, ncol0, n_end, p.resid_vec_ok);
+                    const long long r_off = (long long)b * g.r_batch_stride + (long long)r_in_batch * g.ldr + ncol0;
+                    if (e_dact) {
+                        // activation backward fused into the data gradient: v *= act'(z), z = saved pre-activation
+                        if (row_ok) {
+                            float z[SBW];
+#pragma unroll
+                            for (int j = 0; j < SBW; ++j) z[j] = 0.f;
+                            epi_resid<SBW>(z, e_resid, g.resid_bf16, r_off, ncol0, n_end, p.resid_vec_ok);
+#pragma unroll
+                            for (int j = 0; j < SBW; ++j) v[j] *= act_grad(z[j], e_act);
+                        }
+                    } else {
+                        epi_bias_act<SBW>(v, e_bias, p.bias_vec_ok, ncol0, n_end, e_act, p.fast_gelu);
+                        if (e_resid != nullptr && row_ok)
+                            epi_resid<SBW>(v, e_resid, g.resid_bf16, r_off, ncol0, n_end, p.resid_vec_ok);
+                    }
                     // the previous TMA store of this half must have finished reading the staging block
                     if (leader) tma_store_wait_read();
                     named_bar_sync(bar_id, 128);
@@ -407,7 +428,8 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
 #pragma unroll
                         for (int r = 0; r < 32; ++r) {
                             if (col_ok && r < rows_left) {
-                                const long long ri = (m0w + r) * g.ldr + ncol;
+                                const long long ri = (long long)b * g.r_batch_stride +
+                                                     (long long)(lt * TBM + q * 32 + r) * g.ldr + ncol;
                                 add[r] += g.resid_bf16 ? __bfloat162float(static_cast<const bf16*>(g.resid)[ri])
                                                        : static_cast<const float*>(g.resid)[ri];
                             }
@@ -475,8 +497,10 @@ template <int BN> static int dispatch_out(TmapSet& maps, const TcParams& p, int 
 
 static int g_force_bn = 0;   // debug: force a tile width (tests exercise every instantiation)
 
-int gemm_tc(const GemmParams& g, int c_bf16, int mode, cudaStream_t s) {
-    if (g.M <= 0 || g.N <= 0) return A2F_OK;
+int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
+    if (g_in.M <= 0 || g_in.N <= 0) return A2F_OK;
+    GemmParams g = g_in;
+    normalize_gemm(g);
     TcParams p;
     p.g = g;
     p.mode = mode;
@@ -519,16 +543,35 @@ int gemm_tc(const GemmParams& g, int c_bf16, int mode, cudaStream_t s) {
         else BN = 64;
         p.tiles_n = (g.N + BN - 1) / BN;
         p.num_k_blocks = (g.K + TBK - 1) / TBK;
+        if (g.n_seg > 0) {
+            // explicit segments: one map over [a_rows x row_len], row_len = furthest column any segment touches
+            const int kseg = g.K / g.n_seg;
+            A2F_REQUIRE(kseg % TBK == 0, "gemm_tc: explicit K segments must be multiples of 64");
+            int row_len = 0;
+            for (int i = 0; i < g.n_seg; ++i) {
+                A2F_REQUIRE(g.seg_col_off[i] >= 0 && g.seg_col_off[i] % 8 == 0, "gemm_tc: seg_col_off must be a multiple of 8");
+                if (g.seg_col_off[i] + kseg > row_len) row_len = g.seg_col_off[i] + kseg;
+            }
+            A2F_REQUIRE(row_len <= g.a_row_stride, "gemm_tc: explicit segments must stay inside one A row");
+            p.kb_per_seg = kseg / TBK;
+            uint64_t dims[3] = {(uint64_t)row_len, (uint64_t)g.a_rows, (uint64_t)p.num_batches};
+            uint64_t strides[2] = {(uint64_t)g.a_row_stride * 2,
+                                   (uint64_t)(p.num_batches > 1 ? g.a_batch_stride : g.a_row_stride * g.a_rows) * 2};
+            uint32_t box[3] = {TBK, TBM, 1};
+            int rc = encode_tmap_bf16(&maps.a[0], g.A, 3, dims, strides, box, 1);
+            if (rc != A2F_OK) return rc;
+        }
         // K segments: every tensor map must have non-overlapping rows (segment length <= row stride)
         int nseg = 1;
-        if (g.a_row_stride < g.K) nseg = (int)((g.K + g.a_row_stride - 1) / g.a_row_stride);
+        if (g.n_seg > 0) nseg = 0;
+        else if (g.a_row_stride < g.K) nseg = (int)((g.K + g.a_row_stride - 1) / g.a_row_stride);
         A2F_REQUIRE(nseg <= MAX_SEGS, "gemm_tc: A rows overlap too much (more than 4 K segments)");
-        A2F_REQUIRE(g.K % nseg == 0 && (nseg == 1 || (g.K / nseg) % TBK == 0),
+        A2F_REQUIRE(nseg == 0 || (g.K % nseg == 0 && (nseg == 1 || (g.K / nseg) % TBK == 0)),
                     "gemm_tc: K segment length must be a multiple of 64");
-        const int kseg = g.K / nseg;
-        p.kb_per_seg = (nseg == 1) ? p.num_k_blocks : kseg / TBK;
+        const int kseg = nseg > 0 ? g.K / nseg : 0;
+        if (nseg > 0) p.kb_per_seg = (nseg == 1) ? p.num_k_blocks : kseg / TBK;
         for (int sgi = 0; sgi < nseg; ++sgi) {
-            uint64_t dims[3] = {(uint64_t)kseg, (uint64_t)g.rows_per_batch, (uint64_t)p.num_batches};
+            uint64_t dims[3] = {(uint64_t)kseg, (uint64_t)g.a_rows, (uint64_t)p.num_batches};
             uint64_t strides[2] = {(uint64_t)g.a_row_stride * 2,
                                    (uint64_t)(p.num_batches > 1 ? g.a_batch_stride : g.a_row_stride * g.rows_per_batch) * 2};
             uint32_t box[3] = {TBK, TBM, 1};
@@ -550,12 +593,14 @@ int gemm_tc(const GemmParams& g, int c_bf16, int mode, cudaStream_t s) {
     p.bias_vec_ok = (g.bias != nullptr) && (reinterpret_cast<uintptr_t>(g.bias) % 16 == 0);
     if (g.resid) {
         const size_t rsz = g.resid_bf16 ? 2 : 4;
-        p.resid_vec_ok = (reinterpret_cast<uintptr_t>(g.resid) % 16 == 0) && ((g.ldr * (long long)rsz) % 16 == 0);
+        p.resid_vec_ok = (reinterpret_cast<uintptr_t>(g.resid) % 16 == 0) && ((g.ldr * (long long)rsz) % 16 == 0) &&
+                         ((g.r_batch_stride * (long long)rsz) % 16 == 0);
     }
     // scalar (transposing) epilogue: outputs whose rows are not 16-byte aligned (the 15069-wide vertex head) and the
     // template-add epilogue.  fp32 output only.
     const bool scalar = (g.tmpl != nullptr) || !c_tma_ok;
     if (scalar) {
+        A2F_REQUIRE(g.resid_mode == A2F_RESID_ADD, "gemm_tc: the activation-backward epilogue needs 16-byte aligned outputs");
         A2F_REQUIRE(!c_bf16, "gemm_tc: template-add / unaligned outputs are fp32 only");
         A2F_REQUIRE(g.ldc < (1LL << 25) && g.N < (1 << 25), "gemm_tc: scalar epilogue needs ldc, N < 2^25");
         A2F_REQUIRE(mode != 2, "gemm_tc: posconv output must be 16-byte aligned");

@@ -16,6 +16,7 @@ A2F_OK, A2F_EINVAL, A2F_EARCH, A2F_ECUDA = 0, -1, -2, -3
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 SIMT_F32, TCGEN05 = 0, 1
+RESID_ADD, RESID_DACT = 0, 1
 
 c_void_p, c_int, c_ll, c_float, c_size_t = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 
@@ -34,6 +35,19 @@ class GemmArgs(C.Structure):
         ("resid", c_void_p), ("resid_dtype", c_int), ("ldr", c_ll),
         ("tmpl", c_void_p), ("rows_per_tmpl", c_int),
         ("C", c_void_p), ("c_dtype", c_int), ("ldc", c_ll), ("c_batch_stride", c_ll),
+        ("a_rows", c_int), ("n_seg", c_int), ("seg_row_off", c_int * 4), ("seg_col_off", c_int * 4),
+        ("r_batch_stride", c_ll), ("resid_mode", c_int),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("M", c_int), ("N", c_int), ("K", c_int), ("dtype", c_int),
+        ("dY", c_void_p), ("dy_row_stride", c_ll), ("dy_batch_stride", c_ll),
+        ("X", c_void_p), ("x_row_stride", c_ll), ("x_batch_stride", c_ll),
+        ("rows_per_batch", c_int), ("x_rows", c_int), ("n_seg", c_int),
+        ("x_row_off", c_int * 4), ("x_col_off", c_int * 4),
+        ("dW", c_void_p), ("ldw", c_ll),
     ]
 
 
@@ -61,6 +75,7 @@ _SIGNATURES = {
     "a2f_device_check": (c_int, []),
     "a2f_launch_count": (c_ll, []),
     "a2f_gemm": (c_int, [C.POINTER(GemmArgs), c_int, c_void_p]),
+    "a2f_gemm_wgrad": (c_int, [C.POINTER(WgradArgs), c_int, c_void_p]),
     "a2f_posconv": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "a2f_pack_posconv_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "a2f_pack_conv1d_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

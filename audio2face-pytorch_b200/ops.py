@@ -41,7 +41,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
          rows_per_tmpl: int = 1, backend: int = L.SIMT_F32, M: Optional[int] = None, K: Optional[int] = None,
          a_row_stride: Optional[int] = None, a_batch_stride: int = 0, rows_per_batch: Optional[int] = None,
          N: Optional[int] = None, ldw: Optional[int] = None, ldc: Optional[int] = None, c_batch_stride: int = 0,
-         c_offset: int = 0) -> torch.Tensor:
+         c_offset: int = 0, a_rows: int = 0, segs=None, resid_mode: int = 0, ldr: Optional[int] = None,
+         r_batch_stride: int = 0, r_offset: int = 0) -> torch.Tensor:
     """out[m,n] = act(sum_k a[m,k] w[n,k] + bias[n]) + resid[m,n] + tmpl[m // rows_per_tmpl, n]  (a2f_gemm)."""
     _dev(a, w, out, bias, resid, tmpl)
     lib = L.load()
@@ -57,7 +58,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     g.bias = L.ptr(bias)
     g.act = act
     if resid is not None:
-        g.resid, g.resid_dtype, g.ldr = resid.data_ptr(), _dt(resid), int(resid.stride(0))
+        g.resid, g.resid_dtype = resid.data_ptr() + int(r_offset) * resid.element_size(), _dt(resid)
+        g.ldr = int(ldr if ldr is not None else resid.stride(0))
+        g.r_batch_stride = int(r_batch_stride)
+        g.resid_mode = int(resid_mode)
+    g.a_rows = int(a_rows)
+    if segs is not None:                       # [(row_off, col_off), ...]: explicit K segments (a2f.h)
+        g.n_seg = len(segs)
+        for i, (ro, co) in enumerate(segs):
+            g.seg_row_off[i], g.seg_col_off[i] = int(ro), int(co)
     if tmpl is not None:
         g.tmpl, g.rows_per_tmpl = tmpl.data_ptr(), int(rows_per_tmpl)
     g.C, g.c_dtype = out.data_ptr() + int(c_offset) * out.element_size(), _dt(out)
@@ -78,6 +87,47 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         return out
     L.check(lib.a2f_gemm(C.byref(g), backend, _stream()), "a2f_gemm")
     return out
+
+
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, *, backend: int, M: Optional[int] = None,
+               N: Optional[int] = None, K: Optional[int] = None, dy_row_stride: Optional[int] = None,
+               dy_batch_stride: int = 0, x_row_stride: Optional[int] = None, x_batch_stride: int = 0,
+               rows_per_batch: Optional[int] = None, x_rows: int = 0, segs=None, ldw: Optional[int] = None,
+               x_offset: int = 0, dy_offset: int = 0) -> torch.Tensor:
+    """dw[n, s*K+k] += sum_m dy[m,n] * x[(b, r+roff_s), coff_s+k]   (a2f_gemm_wgrad; dw fp32, accumulated into)."""
+    _dev(dy, x, dw)
+    if dw.dtype != torch.float32:
+        raise L.A2FError("dW must be fp32")
+    if dy.dtype != x.dtype:
+        raise L.A2FError("dY and X must share a dtype")
+    g = L.WgradArgs()
+    g.M = int(M if M is not None else dy.shape[0])
+    g.N = int(N if N is not None else dy.shape[-1])
+    g.K = int(K if K is not None else x.shape[-1])
+    g.dtype = _dt(dy)
+    g.dY = dy.data_ptr() + int(dy_offset) * dy.element_size()
+    g.dy_row_stride = int(dy_row_stride if dy_row_stride is not None else dy.stride(-2))
+    g.dy_batch_stride = int(dy_batch_stride)
+    g.X = x.data_ptr() + int(x_offset) * x.element_size()
+    g.x_row_stride = int(x_row_stride if x_row_stride is not None else x.stride(-2))
+    g.x_batch_stride = int(x_batch_stride)
+    g.rows_per_batch = int(rows_per_batch if rows_per_batch is not None else g.M)
+    g.x_rows = int(x_rows)
+    if segs is not None:
+        g.n_seg = len(segs)
+        for i, (ro, co) in enumerate(segs):
+            g.x_row_off[i], g.x_col_off[i] = int(ro), int(co)
+    g.dW, g.ldw = dw.data_ptr(), int(ldw if ldw is not None else dw.stride(0))
+    lib = L.load()
+    if PROFILE is not None and backend == L.TCGEN05:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        L.check(lib.a2f_gemm_wgrad(C.byref(g), backend, _stream()), "a2f_gemm_wgrad")
+        e.record()
+        PROFILE.append(("wgrad_tc", 2.0 * g.M * g.N * g.K * max(1, g.n_seg), s, e))
+        return dw
+    L.check(lib.a2f_gemm_wgrad(C.byref(g), backend, _stream()), "a2f_gemm_wgrad")
+    return dw
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:

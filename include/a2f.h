@@ -85,9 +85,47 @@ typedef struct a2f_gemm_args {
     long long c_batch_stride; /* elements between the output blocks of consecutive batches; 0 = dense
                                  (rows_per_batch*ldc).  Lets a conv layer write straight into the zero-padded
                                  layout its successor reads (Audio2Mesh). */
+    /* ---- backward-pass extensions (all zero = forward behaviour) ---- */
+    int a_rows;               /* rows that exist in A per batch (0 = rows_per_batch); a logical row that maps outside
+                                 [0, a_rows) reads as zeros */
+    int n_seg;                /* 0/1: K is one run per row.  2..4: K = n_seg runs of K/n_seg elements; run s of logical
+                                 row r is A[b, r + seg_row_off[s], seg_col_off[s] .. +K/n_seg).  The data gradient of a
+                                 stride-2 Conv1d gathers its taps this way (no col2im scatter). */
+    int seg_row_off[4];
+    int seg_col_off[4];
+    long long r_batch_stride; /* elements between the resid blocks of consecutive batches (0 = rows_per_batch*ldr) */
+    int resid_mode;           /* A2F_RESID_ADD (default), or A2F_RESID_DACT: resid holds the forward PRE-activation z and
+                                 the result is multiplied by act'(z) (act = the forward activation; bias is ignored):
+                                 fuses the activation backward into the data-gradient GEMM */
 } a2f_gemm_args;
 
+#define A2F_RESID_ADD 0
+#define A2F_RESID_DACT 1
+
 int a2f_gemm(const a2f_gemm_args* args, int backend, void* stream);
+
+/* Weight gradient:  dW[n, s*K + k] += sum_m dY[m, n] * X[m -> (b, r + x_row_off[s]), x_col_off[s] + k],  s < n_seg
+ * (the transposed-operand GEMM of every nn.Linear / Conv1d backward on the path; rows of X outside [0, x_rows) read as
+ * zero).  dY: [M, N] rows addressed like A above; X likewise; dW: fp32 [N, n_seg*K] with row stride ldw, ACCUMULATED
+ * into (callers zero it once per step: it is the .grad buffer).  tcgen05 backend: bf16 dY / X read in place through
+ * MN-major UMMA descriptors (no transposed copies), split-K over the CTAs, fp32 TMA reduce-add into dW.
+ * SIMT backend: fp32 or bf16 operands, fp32 atomics. */
+typedef struct a2f_wgrad_args {
+    int M, N, K;
+    int dtype; /* of dY and X */
+    const void* dY;
+    long long dy_row_stride, dy_batch_stride;
+    const void* X;
+    long long x_row_stride, x_batch_stride;
+    int rows_per_batch; /* logical rows (of dY) per batch */
+    int x_rows;         /* rows of X that exist per batch (0 = rows_per_batch) */
+    int n_seg;          /* 0/1 = one segment */
+    int x_row_off[4];
+    int x_col_off[4];
+    float* dW;
+    long long ldw;
+} a2f_wgrad_args;
+int a2f_gemm_wgrad(const a2f_wgrad_args* args, int backend, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * wav2vec2 positional conv embedding (HF modeling_wav2vec2.py:326-379,690-693 via ref:src/model/wav2vec.py:174):
