@@ -152,7 +152,7 @@ int a2f_gemm_wgrad(const a2f_wgrad_args* a, int backend, void* stream) {
     A2F_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "a2f_gemm_wgrad: bad M/N/K");
     A2F_REQUIRE(a->dY && a->X && a->dW, "a2f_gemm_wgrad: dY, X and dW must be non-NULL");
     A2F_REQUIRE(a->rows_per_batch > 0 && a->M % a->rows_per_batch == 0, "a2f_gemm_wgrad: M must be a multiple of rows_per_batch");
-    A2F_REQUIRE(a->n_seg >= 0 && a->n_seg <= 4, "a2f_gemm_wgrad: n_seg must be 0..4");
+    A2F_REQUIRE(a->n_seg >= 0 && (a->n_seg <= 4 || a->x_row_step != 0), "a2f_gemm_wgrad: n_seg > 4 needs x_row_step");
     A2F_REQUIRE(a->dtype == A2F_F32 || a->dtype == A2F_BF16, "a2f_gemm_wgrad: bad dtype");
     if (a->M == 0) return A2F_OK;
     WgradParams p;
@@ -167,6 +167,7 @@ int a2f_gemm_wgrad(const a2f_wgrad_args* a, int backend, void* stream) {
         p.x_col_off[i] = a->n_seg < 1 ? 0 : a->x_col_off[i];
     }
     p.dW = a->dW; p.ldw = a->ldw;
+    p.x_row_step = a->n_seg > 1 ? a->x_row_step : 0;
     if (backend == A2F_BACKEND_SIMT_F32) return wgrad_simt(p, a->dtype == A2F_BF16, as_stream(stream));
     if (backend == A2F_BACKEND_TCGEN05) {
         A2F_REQUIRE(a->dtype == A2F_BF16, "a2f_gemm_wgrad: the tcgen05 backend takes bf16 operands");
@@ -199,6 +200,72 @@ int a2f_posconv(const void* h, int h_dtype, const void* Wp, const float* bias, v
         return gemm_tc(p, out_dtype == A2F_BF16, 2, as_stream(stream));
     }
     return set_error(A2F_EINVAL, "a2f_posconv: unknown backend");
+}
+
+static int posconv_common(GemmParams& p, const void* a, int dtype, const void* W, void* out, int B, int T, int backend,
+                          cudaStream_t s) {
+    p.M = B * T; p.N = 48;
+    p.A = a; p.a_row_stride = 768; p.a_batch_stride = (long long)T * 768; p.rows_per_batch = T;
+    p.W = W;
+    p.tmpl = nullptr; p.rows_per_tmpl = 1;
+    p.C = out; p.ldc = 768; p.c_batch_stride = (long long)T * 768;
+    p.ldr = 768;
+    if (backend == A2F_BACKEND_SIMT_F32) {
+        p.K = 128 * 48; p.ldw = 128 * 48;
+        return posconv_simt(p, dtype == A2F_BF16, dtype == A2F_BF16, s);
+    } else if (backend == A2F_BACKEND_TCGEN05) {
+        A2F_REQUIRE(dtype == A2F_BF16, "posconv: the tcgen05 backend takes bf16 activations");
+        p.K = 128 * 64; p.ldw = 128 * 64;
+        return gemm_tc(p, 1, 2, s);
+    }
+    return set_error(A2F_EINVAL, "posconv: unknown backend");
+}
+
+int a2f_posconv_pre(const void* h, int h_dtype, const void* Wp, const float* bias, void* pc, int B, int T, int backend,
+                    void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(h && Wp && pc && B > 0 && T > 0, "a2f_posconv_pre: bad arguments");
+    GemmParams p;
+    p.bias = bias; p.act = A2F_ACT_NONE; p.resid = nullptr; p.resid_bf16 = 0;
+    return posconv_common(p, h, h_dtype, Wp, pc, B, T, backend, as_stream(stream));
+}
+
+int a2f_posconv_dgrad(const void* dpc, int dtype, const void* Wd, const void* dout, void* dh, int B, int T, int backend,
+                      void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(dpc && Wd && dh && B > 0 && T > 0, "a2f_posconv_dgrad: bad arguments");
+    GemmParams p;
+    p.bias = nullptr; p.act = A2F_ACT_NONE;
+    p.resid = dout; p.resid_bf16 = (dtype == A2F_BF16);
+    p.seg_row_off[0] = 1;     // flipped taps: dh[s] = sum_tap' Wd[tap'] dpc[s + tap' - 63]
+    return posconv_common(p, dpc, dtype, Wd, dh, B, T, backend, as_stream(stream));
+}
+
+int a2f_posconv_wgrad(const void* dpc, const void* h, int dtype, float* dWp, int B, int T, int backend, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(dpc && h && dWp && B > 0 && T > 0, "a2f_posconv_wgrad: bad arguments");
+    const size_t esz = dtype == A2F_BF16 ? 2 : 4;
+    for (int g = 0; g < 16; ++g) {
+        WgradParams p;
+        p.M = B * T; p.N = 48; p.K = 48;
+        p.dY = static_cast<const char*>(dpc) + (size_t)g * 48 * esz; p.dy_row_stride = 768; p.dy_batch_stride = (long long)T * 768;
+        p.X = static_cast<const char*>(h) + (size_t)g * 48 * esz; p.x_row_stride = 768; p.x_batch_stride = (long long)T * 768;
+        p.rows_per_batch = T; p.x_rows = T;
+        p.n_seg = 128; p.x_row_step = 1;
+        for (int i = 0; i < 4; ++i) p.x_row_off[i] = p.x_col_off[i] = 0;
+        p.x_row_off[0] = -64;
+        p.dW = dWp + (size_t)g * 48 * 6144; p.ldw = 6144;
+        if (backend == A2F_BACKEND_SIMT_F32) rc = wgrad_simt(p, dtype == A2F_BF16, as_stream(stream));
+        else if (backend == A2F_BACKEND_TCGEN05) {
+            A2F_REQUIRE(dtype == A2F_BF16, "a2f_posconv_wgrad: the tcgen05 backend takes bf16 operands");
+            rc = wgrad_tc(p, as_stream(stream));
+        } else return set_error(A2F_EINVAL, "a2f_posconv_wgrad: unknown backend");
+        if (rc != A2F_OK) return rc;
+    }
+    return A2F_OK;
 }
 
 int a2f_pack_posconv_weight(const float* g, const float* v, void* out, int out_dtype, int kpad, float* norm_scratch,

@@ -14,8 +14,8 @@ namespace a2f {
 
 // ------------------------------------------------------------------------------------------------ fp32 SIMT
 // qkv: [B,T,3*H*64] fp32.  One warp per (b,h,query).  Lane l scores keys j = j0+l; output dims (2l, 2l+1).
-__global__ void __launch_bounds__(256) mha_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int B,
-                                                      int T, int H, float scale) {
+__global__ void __launch_bounds__(256) mha_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                      float* __restrict__ lse, int B, int T, int H, float scale) {
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int total = B * H * T;
@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) mha_f32_kernel(const float* __restrict__ 
     const float inv = 1.f / l;
     float* op = out + ((long long)b * T + t) * (H * 64) + h * 64 + 2 * lane;
     *reinterpret_cast<float2*>(op) = make_float2(o0 * inv, o1 * inv);
+    if (lse != nullptr && lane == 0) lse[((long long)b * H + h) * T + t] = m + logf(l);
 }
 
 // ------------------------------------------------------------------------------------------------ bf16 tensor-core
@@ -99,8 +100,8 @@ A2F_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory
 template <int N> A2F_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // grid: (ceil(T/64), H, B); 128 threads.
-__global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T,
-                                                       int H, float scale_log2) {
+__global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                       float* __restrict__ lse, int T, int H, float scale_log2) {
     __shared__ __align__(16) bf16 sQ[FA_BM * FA_LD];
     __shared__ __align__(16) bf16 sK[2][FA_BN * FA_LD];
     __shared__ __align__(16) bf16 sV[2][FA_BN * FA_LD];
@@ -251,6 +252,12 @@ __global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ 
     }
     const int row0 = q0 + warp * 16 + (lane >> 2);
     const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+    if (lse != nullptr && (lane & 3) == 0) {
+        // natural-log LSE of the scaled scores: m*scale + ln(l)
+        float* lp = lse + ((long long)b * H + h) * T;
+        if (row0 < T) lp[row0] = m_run[0] * scale_log2 * 0.69314718055994531f + logf(l_run[0]);
+        if (row0 + 8 < T) lp[row0 + 8] = m_run[1] * scale_log2 * 0.69314718055994531f + logf(l_run[1]);
+    }
     bf16* ob = out + (long long)b * T * (H * FA_D) + h * FA_D;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -262,12 +269,412 @@ __global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ 
     }
 }
 
+
+// ================================================================================================ backward
+// delta[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one warp per (b,t,h))
+template <typename T>
+__global__ void __launch_bounds__(256) mha_delta_kernel(const T* __restrict__ o, const T* __restrict__ dout,
+                                                        float* __restrict__ delta, int B, int Tn, int H) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (long long)B * Tn * H) return;
+    const int h = (int)(w % H);
+    const long long bt = w / H;
+    const int t = (int)(bt % Tn), b = (int)(bt / Tn);
+    const T* op = o + bt * (H * 64) + h * 64 + 2 * lane;
+    const T* dp = dout + bt * (H * 64) + h * 64 + 2 * lane;
+    float s = ld_as_float(op) * ld_as_float(dp) + ld_as_float(op + 1) * ld_as_float(dp + 1);
+    s = warp_sum(s);
+    if (lane == 0) delta[((long long)b * H + h) * Tn + t] = s;
+}
+
+// fp32 parity path: one warp per (b,h,query); lanes own keys; dK / dV through fp32 atomics (dqkv must be zeroed).
+__global__ void __launch_bounds__(128) mha_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
+                                                          const float* __restrict__ lse, const float* __restrict__ delta,
+                                                          float* __restrict__ dqkv, int B, int T, int H, float scale) {
+    __shared__ float qs[4][64], dos[4][64];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wg = blockIdx.x * 4 + wl;
+    if (wg >= B * H * T) return;
+    const int t = wg % T, h = (wg / T) % H, b = wg / (T * H);
+    const int ld = 3 * H * 64;
+    const float* base = qkv + (long long)b * T * ld;
+    float* dbase = dqkv + (long long)b * T * ld;
+    qs[wl][lane] = base[(long long)t * ld + h * 64 + lane];
+    qs[wl][lane + 32] = base[(long long)t * ld + h * 64 + lane + 32];
+    dos[wl][lane] = dout[((long long)b * T + t) * (H * 64) + h * 64 + lane];
+    dos[wl][lane + 32] = dout[((long long)b * T + t) * (H * 64) + h * 64 + lane + 32];
+    __syncwarp();
+    const float L = lse[((long long)b * H + h) * T + t], dl = delta[((long long)b * H + h) * T + t];
+    float dq[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) dq[d] = 0.f;
+    for (int j = lane; j < T; j += 32) {
+        const float* kp = base + (long long)j * ld + H * 64 + h * 64;
+        const float* vp = base + (long long)j * ld + 2 * H * 64 + h * 64;
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int d = 0; d < 64; d += 4) {
+            const float4 kf = *reinterpret_cast<const float4*>(kp + d);
+            const float4 vf = *reinterpret_cast<const float4*>(vp + d);
+            s = fmaf(qs[wl][d], kf.x, s); s = fmaf(qs[wl][d + 1], kf.y, s);
+            s = fmaf(qs[wl][d + 2], kf.z, s); s = fmaf(qs[wl][d + 3], kf.w, s);
+            dp = fmaf(dos[wl][d], vf.x, dp); dp = fmaf(dos[wl][d + 1], vf.y, dp);
+            dp = fmaf(dos[wl][d + 2], vf.z, dp); dp = fmaf(dos[wl][d + 3], vf.w, dp);
+        }
+        const float p = __expf(s * scale - L);
+        const float ds = p * (dp - dl) * scale;
+        float* dkp = dbase + (long long)j * ld + H * 64 + h * 64;
+        float* dvp = dbase + (long long)j * ld + 2 * H * 64 + h * 64;
+#pragma unroll
+        for (int d = 0; d < 64; ++d) {
+            dq[d] = fmaf(ds, kp[d], dq[d]);
+            atomicAdd(dkp + d, ds * qs[wl][d]);
+            atomicAdd(dvp + d, p * dos[wl][d]);
+        }
+    }
+    float* dqp = dbase + (long long)t * ld + h * 64;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) {
+        const float v = warp_sum(dq[d]);
+        if (lane == (d & 31)) dqp[d] = v;
+    }
+}
+
+constexpr int FAB_TILE = FA_BM * FA_LD;     // bf16 elements of one 64 x 64 (padded) tile
+
+// bf16 tensor-core backward, query-major pass: dQ = (P o (dO V^T - delta)) K * scale.   grid (ceil(T/64), H, B), 128 thr.
+__global__ void __launch_bounds__(128) mha_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                         const float* __restrict__ lse, const float* __restrict__ delta,
+                                                         bf16* __restrict__ dqkv, int T, int H, float scale) {
+    extern __shared__ __align__(16) bf16 fab_smem[];
+    bf16* sQ = fab_smem;
+    bf16* sdO = sQ + FAB_TILE;
+    bf16* sK = sdO + FAB_TILE;           // [2]
+    bf16* sV = sK + 2 * FAB_TILE;        // [2]
+    const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ld = 3 * H * FA_D, ldo = H * FA_D;
+    const bf16* base = qkv + (long long)b * T * ld;
+    const bf16* gQ = base + h * FA_D;
+    const bf16* gK = base + H * FA_D + h * FA_D;
+    const bf16* gV = base + 2 * H * FA_D + h * FA_D;
+    const bf16* gdO = dout + (long long)b * T * ldo + h * FA_D;
+    auto load_tile = [&](bf16* dst, const bf16* src, int row0, int lds) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = threadIdx.x + i * 128;
+            const int r = idx >> 3, c = (idx & 7) * 8;
+            const bool ok = (row0 + r) < T;
+            cp_async_16(dst + r * FA_LD + c, src + (long long)(ok ? row0 + r : 0) * lds + c, ok);
+        }
+    };
+    load_tile(sQ, gQ, q0, ld);
+    load_tile(sdO, gdO, q0, ldo);
+    load_tile(sK, gK, 0, ld);
+    load_tile(sV, gV, 0, ld);
+    cp_async_commit();
+    const float scale_log2 = scale * 1.4426950408889634f;
+    const int r0 = q0 + warp * 16 + (lane >> 2);
+    const float* lp = lse + ((long long)b * H + h) * T;
+    const float* dp_ = delta + ((long long)b * H + h) * T;
+    float lse2[2], dl[2];
+    lse2[0] = r0 < T ? lp[r0] * 1.4426950408889634f : 0.f;
+    lse2[1] = r0 + 8 < T ? lp[r0 + 8] * 1.4426950408889634f : 0.f;
+    dl[0] = r0 < T ? dp_[r0] : 0.f;
+    dl[1] = r0 + 8 < T ? dp_[r0 + 8] : 0.f;
+    uint32_t qf[4][4], dof[4][4];
+    float dq[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+    const int ntiles = (T + FA_BN - 1) / FA_BN;
+    for (int it = 0; it < ntiles; ++it) {
+        const int cur = it & 1;
+        if (it + 1 < ntiles) {
+            load_tile(sK + (cur ^ 1) * FAB_TILE, gK, (it + 1) * FA_BN, ld);
+            load_tile(sV + (cur ^ 1) * FAB_TILE, gV, (it + 1) * FA_BN, ld);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (it == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = ks * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sQ + r * FA_LD + c);
+                ldmatrix_x4(dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3], sdO + r * FA_LD + c);
+            }
+        }
+        const bf16* cK = sK + cur * FAB_TILE;
+        const bf16* cV = sV + cur * FAB_TILE;
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; dp[i][j] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                const int r = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+                ldmatrix_x4(b0, b1, b2, b3, cK + r * FA_LD + c);
+                mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+                ldmatrix_x4(b0, b1, b2, b3, cV + r * FA_LD + c);
+                mma_bf16_16816(dp[2 * np], dof[ks], b0, b1);
+                mma_bf16_16816(dp[2 * np + 1], dof[ks], b2, b3);
+            }
+        }
+        const int key0 = it * FA_BN;
+        uint32_t dsf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int kc = key0 + nt * 8 + (lane & 3) * 2;
+            float d4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int rr = e >> 1;
+                const bool ok = (kc + (e & 1)) < T;
+                const float p = ok ? exp2f(fmaf(s[nt][e], scale_log2, -lse2[rr])) : 0.f;
+                d4[e] = p * (dp[nt][e] - dl[rr]) * scale;
+            }
+            const int ks = nt >> 1, hi = nt & 1;
+            dsf[ks][hi * 2 + 0] = pack_bf16x2(d4[0], d4[1]);
+            dsf[ks][hi * 2 + 1] = pack_bf16x2(d4[2], d4[3]);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int dpp = 0; dpp < 4; ++dpp) {
+                uint32_t b0, b1, b2, b3;
+                const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = dpp * 16 + (lane >> 4) * 8;
+                ldmatrix_x4_trans(b0, b1, b2, b3, cK + r * FA_LD + c);
+                mma_bf16_16816(dq[2 * dpp], dsf[ks], b0, b1);
+                mma_bf16_16816(dq[2 * dpp + 1], dsf[ks], b2, b3);
+            }
+        }
+        __syncthreads();
+    }
+    bf16* ob = dqkv + (long long)b * T * ld + h * FA_D;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + (lane & 3) * 2;
+        if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * ld + c) = pack_bf16x2(dq[nt][0], dq[nt][1]);
+        if (r0 + 8 < T) *reinterpret_cast<uint32_t*>(ob + (long long)(r0 + 8) * ld + c) = pack_bf16x2(dq[nt][2], dq[nt][3]);
+    }
+}
+
+// key-major pass: dV = P^T dO, dK = (P o (dO V^T - delta))^T Q * scale.   grid (ceil(T/64), H, B), 128 threads.
+__global__ void __launch_bounds__(128) mha_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                          const float* __restrict__ lse, const float* __restrict__ delta,
+                                                          bf16* __restrict__ dqkv, int T, int H, float scale) {
+    extern __shared__ __align__(16) bf16 fab_smem[];
+    bf16* sK = fab_smem;
+    bf16* sV = sK + FAB_TILE;
+    bf16* sQ = sV + FAB_TILE;            // [2]
+    bf16* sdO = sQ + 2 * FAB_TILE;       // [2]
+    float* sL = reinterpret_cast<float*>(sdO + 2 * FAB_TILE);   // [2][64] lse * log2e
+    float* sD = sL + 128;                                       // [2][64] delta
+    const int k0 = blockIdx.x * FA_BN, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ld = 3 * H * FA_D, ldo = H * FA_D;
+    const bf16* base = qkv + (long long)b * T * ld;
+    const bf16* gQ = base + h * FA_D;
+    const bf16* gK = base + H * FA_D + h * FA_D;
+    const bf16* gV = base + 2 * H * FA_D + h * FA_D;
+    const bf16* gdO = dout + (long long)b * T * ldo + h * FA_D;
+    const float* lp = lse + ((long long)b * H + h) * T;
+    const float* dlp = delta + ((long long)b * H + h) * T;
+    auto load_tile = [&](bf16* dst, const bf16* src, int row0, int lds) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = threadIdx.x + i * 128;
+            const int r = idx >> 3, c = (idx & 7) * 8;
+            const bool ok = (row0 + r) < T;
+            cp_async_16(dst + r * FA_LD + c, src + (long long)(ok ? row0 + r : 0) * lds + c, ok);
+        }
+    };
+    auto load_stats = [&](int buf, int row0) {
+        if (threadIdx.x < 64) {
+            const int r = row0 + threadIdx.x;
+            sL[buf * 64 + threadIdx.x] = r < T ? lp[r] * 1.4426950408889634f : 0.f;
+            sD[buf * 64 + threadIdx.x] = r < T ? dlp[r] : 0.f;
+        }
+    };
+    load_tile(sK, gK, k0, ld);
+    load_tile(sV, gV, k0, ld);
+    load_tile(sQ, gQ, 0, ld);
+    load_tile(sdO, gdO, 0, ldo);
+    load_stats(0, 0);
+    cp_async_commit();
+    const float scale_log2 = scale * 1.4426950408889634f;
+    uint32_t kf[4][4], vf[4][4];
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dk[i][j] = 0.f; dv[i][j] = 0.f; }
+    const int ntiles = (T + FA_BM - 1) / FA_BM;
+    for (int it = 0; it < ntiles; ++it) {
+        const int cur = it & 1;
+        if (it + 1 < ntiles) {
+            load_tile(sQ + (cur ^ 1) * FAB_TILE, gQ, (it + 1) * FA_BM, ld);
+            load_tile(sdO + (cur ^ 1) * FAB_TILE, gdO, (it + 1) * FA_BM, ldo);
+            load_stats(cur ^ 1, (it + 1) * FA_BM);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (it == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = ks * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(kf[ks][0], kf[ks][1], kf[ks][2], kf[ks][3], sK + r * FA_LD + c);
+                ldmatrix_x4(vf[ks][0], vf[ks][1], vf[ks][2], vf[ks][3], sV + r * FA_LD + c);
+            }
+        }
+        const bf16* cQ = sQ + cur * FAB_TILE;
+        const bf16* cdO = sdO + cur * FAB_TILE;
+        // S^T = K Q^T and dP^T = V dO^T : [16 keys x 64 queries] per warp
+        float st[8][4], dpt[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { st[i][j] = 0.f; dpt[i][j] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                const int r = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+                ldmatrix_x4(b0, b1, b2, b3, cQ + r * FA_LD + c);
+                mma_bf16_16816(st[2 * np], kf[ks], b0, b1);
+                mma_bf16_16816(st[2 * np + 1], kf[ks], b2, b3);
+                ldmatrix_x4(b0, b1, b2, b3, cdO + r * FA_LD + c);
+                mma_bf16_16816(dpt[2 * np], vf[ks], b0, b1);
+                mma_bf16_16816(dpt[2 * np + 1], vf[ks], b2, b3);
+            }
+        }
+        const int qbase = it * FA_BM;
+        uint32_t pf[4][4], dsf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int qc = nt * 8 + (lane & 3) * 2;         // query column within the tile
+            float p4[4], d4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int qq = qc + (e & 1);
+                const bool ok = (qbase + qq) < T;
+                const float p = ok ? exp2f(fmaf(st[nt][e], scale_log2, -sL[cur * 64 + qq])) : 0.f;
+                p4[e] = p;
+                d4[e] = p * (dpt[nt][e] - sD[cur * 64 + qq]) * scale;
+            }
+            const int ks = nt >> 1, hi = nt & 1;
+            pf[ks][hi * 2 + 0] = pack_bf16x2(p4[0], p4[1]);
+            pf[ks][hi * 2 + 1] = pack_bf16x2(p4[2], p4[3]);
+            dsf[ks][hi * 2 + 0] = pack_bf16x2(d4[0], d4[1]);
+            dsf[ks][hi * 2 + 1] = pack_bf16x2(d4[2], d4[3]);
+        }
+        // dV += P^T dO ; dK += dS^T Q   (reduction over the 64 queries of the tile)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int dpp = 0; dpp < 4; ++dpp) {
+                uint32_t b0, b1, b2, b3;
+                const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = dpp * 16 + (lane >> 4) * 8;
+                ldmatrix_x4_trans(b0, b1, b2, b3, cdO + r * FA_LD + c);
+                mma_bf16_16816(dv[2 * dpp], pf[ks], b0, b1);
+                mma_bf16_16816(dv[2 * dpp + 1], pf[ks], b2, b3);
+                ldmatrix_x4_trans(b0, b1, b2, b3, cQ + r * FA_LD + c);
+                mma_bf16_16816(dk[2 * dpp], dsf[ks], b0, b1);
+                mma_bf16_16816(dk[2 * dpp + 1], dsf[ks], b2, b3);
+            }
+        }
+        __syncthreads();
+    }
+    const int r0 = k0 + warp * 16 + (lane >> 2);
+    bf16* okp = dqkv + (long long)b * T * ld + H * FA_D + h * FA_D;
+    bf16* ovp = dqkv + (long long)b * T * ld + 2 * H * FA_D + h * FA_D;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + (lane & 3) * 2;
+        if (r0 < T) {
+            *reinterpret_cast<uint32_t*>(okp + (long long)r0 * ld + c) = pack_bf16x2(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<uint32_t*>(ovp + (long long)r0 * ld + c) = pack_bf16x2(dv[nt][0], dv[nt][1]);
+        }
+        if (r0 + 8 < T) {
+            *reinterpret_cast<uint32_t*>(okp + (long long)(r0 + 8) * ld + c) = pack_bf16x2(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<uint32_t*>(ovp + (long long)(r0 + 8) * ld + c) = pack_bf16x2(dv[nt][2], dv[nt][3]);
+        }
+    }
+}
+
 }  // namespace a2f
 
 using namespace a2f;
 
 extern "C" int a2f_mha_fwd(const void* qkv, void* out, int dtype, int B, int T, int H, int D, float scale,
                            void* stream) {
+    return a2f_mha_fwd_lse(qkv, out, nullptr, dtype, B, T, H, D, scale, stream);
+}
+
+extern "C" int a2f_mha_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int dtype,
+                           int B, int T, int H, int D, float scale, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(qkv && out && dout && lse && dqkv && workspace && B > 0 && T > 0 && H > 0, "a2f_mha_bwd: bad arguments");
+    A2F_REQUIRE(D == 64, "a2f_mha_bwd: head_dim must be 64");
+    A2F_REQUIRE(workspace_bytes >= (size_t)B * H * T * sizeof(float), "a2f_mha_bwd: workspace too small (B*H*T floats)");
+    cudaStream_t s = as_stream(stream);
+    float* delta = static_cast<float*>(workspace);
+    const long long warps = (long long)B * T * H;
+    const int dgrid = (int)((warps * 32 + 255) / 256);
+    if (dtype == A2F_F32) {
+        mha_delta_kernel<float><<<dgrid, 256, 0, s>>>((const float*)out, (const float*)dout, delta, B, T, H);
+        A2F_CHECK_LAUNCH("mha_delta_kernel");
+        A2F_CHECK_CUDA(cudaMemsetAsync(dqkv, 0, (size_t)B * T * 3 * H * 64 * sizeof(float), s));
+        mha_bwd_f32_kernel<<<(int)((warps + 3) / 4), 128, 0, s>>>((const float*)qkv, (const float*)dout, lse, delta,
+                                                                  (float*)dqkv, B, T, H, scale);
+        A2F_CHECK_LAUNCH("mha_bwd_f32_kernel");
+        count_launch(2);
+    } else if (dtype == A2F_BF16) {
+        mha_delta_kernel<bf16><<<dgrid, 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
+        A2F_CHECK_LAUNCH("mha_delta_kernel");
+        const size_t smem = (size_t)6 * FAB_TILE * sizeof(bf16) + 256 * sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done) {
+            A2F_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            A2F_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        const dim3 grid((T + 63) / 64, H, B);
+        mha_bwd_dq_kernel<<<grid, 128, smem, s>>>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, T, H, scale);
+        A2F_CHECK_LAUNCH("mha_bwd_dq_kernel");
+        mha_bwd_dkv_kernel<<<grid, 128, smem, s>>>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, T, H, scale);
+        A2F_CHECK_LAUNCH("mha_bwd_dkv_kernel");
+        count_launch(3);
+    } else {
+        return set_error(A2F_EINVAL, "a2f_mha_bwd: bad dtype");
+    }
+    return A2F_OK;
+}
+
+extern "C" int a2f_mha_fwd_lse(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H, int D, float scale,
+                               void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, "a2f_mha_fwd: bad arguments");
@@ -276,12 +683,12 @@ extern "C" int a2f_mha_fwd(const void* qkv, void* out, int dtype, int B, int T, 
     if (dtype == A2F_F32) {
         const long long warps = (long long)B * H * T;
         const int grid = (int)((warps * 32 + 255) / 256);
-        mha_f32_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(qkv), static_cast<float*>(out), B, T, H, scale);
+        mha_f32_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(qkv), static_cast<float*>(out), lse, B, T, H, scale);
         A2F_CHECK_LAUNCH("mha_f32_kernel");
     } else if (dtype == A2F_BF16) {
         A2F_REQUIRE(reinterpret_cast<uintptr_t>(qkv) % 16 == 0, "a2f_mha_fwd: qkv must be 16-byte aligned");
         const dim3 grid((T + FA_BM - 1) / FA_BM, H, B);
-        mha_bf16_kernel<<<grid, 128, 0, s>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), T, H,
+        mha_bf16_kernel<<<grid, 128, 0, s>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, T, H,
                                               scale * 1.4426950408889634f);
         A2F_CHECK_LAUNCH("mha_bf16_kernel");
     } else {

@@ -48,6 +48,9 @@ struct WgradParams {
     int x_col_off[4];
     float* dW;
     long long ldw;
+    int x_row_step;
+    A2F_HD int row_off(int s) const { return x_row_step != 0 ? x_row_off[0] + s * x_row_step : x_row_off[s & 3]; }
+    A2F_HD int col_off(int s) const { return x_row_step != 0 ? x_col_off[0] : x_col_off[s & 3]; }
 };
 
 int gemm_simt(const GemmParams& p, int a_bf16, int c_bf16, cudaStream_t s);

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
                         }
                     } else {
                         int tap = k / 48, c = k - tap * 48;
-                        int t = a_t + tap - 64;
+                        int t = a_t + tap - 64 + p.seg_row_off[0];
                         if (t >= 0 && t < p.rows_per_batch)
                             av = ld_as_float(A + a_base + (long long)t * p.a_row_stride + g * 48 + c);
                     }
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradParams p) {
     const bool xc_ok = xc < ktot;
     const int sg = xc_ok ? xc / p.K : 0;
     const int xk = xc_ok ? xc - sg * p.K : 0;
-    const int roff = p.x_row_off[sg], coff = p.x_col_off[sg];
+    const int roff = p.row_off(sg), coff = p.col_off(sg);
     const int yn = n0 + lcol;
     const bool yn_ok = yn < p.N;
 

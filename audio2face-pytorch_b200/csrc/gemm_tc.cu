@@ -200,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     uint8_t* dstA = sA + (size_t)stage * A_STAGE_BYTES;
                     uint8_t* dstB = sB + (size_t)stage * Cfg::B_STAGE_BYTES;
                     if (p.mode == 2) {
-                        tma_load_3d(dstA, &maps.a[0], &full_bar[stage], nb * 48, lt * TBM + kb - 64, b);
+                        tma_load_3d(dstA, &maps.a[0], &full_bar[stage], nb * 48, lt * TBM + kb - 64 + p.g.seg_row_off[0], b);
                         tma_load_2d(dstB, &maps.b, &full_bar[stage], kb * TBK, nb * 48);
                     } else if (p.g.n_seg > 0) {
                         // explicit K segments (data gradient of the strided convs): one map, per-segment row / column

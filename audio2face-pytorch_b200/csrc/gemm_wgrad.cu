@@ -32,6 +32,7 @@ struct WgradMaps {
 struct WgradTc {
     WgradParams g;
     int tiles_n, tiles_c, n_tiles;      // dW row tiles, column tiles
+    int tiles_per_seg;                  // column tiles per segment (a tile never straddles two segments)
     int num_batches, kb_per_batch;      // 64-row reduction blocks per batch
     int chunks_per_batch, kb_per_chunk; // split of the reduction
     int total_items;
@@ -119,10 +120,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad_tc_kernel(const __grid_con
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 int tn, tc, b, kb0, kb1;
                 decode(item, tn, tc, b, kb0, kb1);
-                const int col0 = tc * BNW;                     // first dW column of the tile
-                const int sg = col0 / g.K;                      // segment (tap) of the tile
-                const int xcol = g.x_col_off[sg] + (col0 - sg * g.K);
-                const int xrow_off = g.x_row_off[sg];
+                const int sg = tc / p.tiles_per_seg;            // segment (tap) of the tile
+                const int xcol = g.col_off(sg) + (tc - sg * p.tiles_per_seg) * BNW;
+                const int xrow_off = g.row_off(sg);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE);
@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad_tc_kernel(const __grid_con
             const int r_tile = q * 32 + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
             uint8_t* rowp = stage_buf + r_tile * 128;
-            const int n_lim = min(BNW, ktot - tc * BNW);
+            const int sg = tc / p.tiles_per_seg, within = tc - sg * p.tiles_per_seg;
+            const int ocol = sg * g.K + within * BNW;         // first dW column of the tile
+            const int n_lim = min(BNW, ktot - ocol);
 #pragma unroll 1
             for (int blk = half; blk < BNW / 32; blk += 2) {
                 const int col0 = blk * 32;
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) wgrad_tc_kernel(const __grid_con
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
                 if (leader) {
-                    tma_reduce_add_2d(&maps.dw, stage_buf, tc * BNW + col0, tn * WBM);
+                    tma_reduce_add_2d(&maps.dw, stage_buf, ocol + col0, tn * WBM);
                     tma_store_commit();
                 }
             }
@@ -259,15 +261,17 @@ int wgrad_tc(const WgradParams& g, cudaStream_t s) {
     A2F_REQUIRE(g.dy_row_stride % 8 == 0 && g.dy_batch_stride % 8 == 0 && g.x_row_stride % 8 == 0 && g.x_batch_stride % 8 == 0,
                 "wgrad_tc: operand strides must be multiples of 8 elements (16 bytes)");
     A2F_REQUIRE(g.ldw % 4 == 0 && reinterpret_cast<uintptr_t>(g.dW) % 16 == 0, "wgrad_tc: dW must be 16-byte aligned with ldw % 4 == 0");
-    int BNW = ktot > 128 ? 256 : (ktot > 64 ? 128 : 64);
+    int BNW = g.K > 128 ? 256 : (g.K > 64 ? 128 : 64);
     if (g.n_seg > 1) {
-        // a column tile must not straddle two segments
+        // a column tile must not straddle two segments: K is a multiple of the tile width, or one tile per segment
+        // (columns K..BNW-1 of such a tile read zeros because the X map ends at x_col_off + K)
         while (BNW > 64 && g.K % BNW != 0) BNW >>= 1;
-        A2F_REQUIRE(g.K % BNW == 0, "wgrad_tc: with several segments K must be a multiple of 64");
+        A2F_REQUIRE(g.K % BNW == 0 || g.K < BNW, "wgrad_tc: with several segments K must be < 64 or a multiple of 64");
     }
     p.num_batches = g.M / g.rows_per_batch;
     p.tiles_n = (g.N + WBM - 1) / WBM;
-    p.tiles_c = (ktot + BNW - 1) / BNW;
+    p.tiles_per_seg = (g.K + BNW - 1) / BNW;
+    p.tiles_c = p.tiles_per_seg * g.n_seg;
     p.n_tiles = p.tiles_n * p.tiles_c;
     p.kb_per_batch = (g.rows_per_batch + WBK - 1) / WBK;
     // split the reduction until every SM has work (at least ~2 items per SM when the reduction is long enough)
@@ -295,8 +299,8 @@ int wgrad_tc(const WgradParams& g, cudaStream_t s) {
     {
         int row_len = 0;
         for (int i = 0; i < g.n_seg; ++i) {
-            A2F_REQUIRE(g.x_col_off[i] >= 0 && g.x_col_off[i] % 8 == 0, "wgrad_tc: x_col_off must be a multiple of 8");
-            if (g.x_col_off[i] + g.K > row_len) row_len = g.x_col_off[i] + g.K;
+            A2F_REQUIRE(g.col_off(i) >= 0 && g.col_off(i) % 8 == 0, "wgrad_tc: x_col_off must be a multiple of 8");
+            if (g.col_off(i) + g.K > row_len) row_len = g.col_off(i) + g.K;
         }
         A2F_REQUIRE(row_len <= g.x_row_stride, "wgrad_tc: segments must stay inside one X row");
         uint64_t dims[3] = {(uint64_t)row_len, (uint64_t)g.x_rows, (uint64_t)p.num_batches};

@@ -1,0 +1,697 @@
+// Backward-pass kernels of the audio->mesh path that are not GEMMs (those are gemm_tc.cu / gemm_wgrad.cu):
+//   a2f_act_fwd / a2f_act_bwd        y = act(z) ; dz = dy * act'(z)                       (HBM-bound elementwise)
+//   a2f_colsum                       bias gradients: out[n] += sum_m x[m,n]
+//   a2f_layernorm_bwd                LayerNorm backward (+ dgamma, dbeta, optional column sum of dx = bias gradient)
+//   a2f_interp_ln_bwd                backward of linear_interpolation + projection LayerNorm (ref:src/model/wav2vec.py:76-84)
+//   a2f_conv0_bwd                    backward of normalise+Conv1d(1->512,k10,s5)+GroupNorm+GELU without ever storing the
+//                                    512 x L0 pre-activation: the conv is recomputed from the audio (10 FMAs)
+//   a2f_weight_norm_bwd              g*v/||v|| backward of the positional conv (HF weight_norm(dim=2))
+//   a2f_transpose_cast, a2f_pack_posconv_dgrad_weight, a2f_cast_rows       operand packers of the backward GEMMs
+//   a2f_adam_step                    fused Adam with L2 weight decay (ref:src/model/lightning_model.py:209-213)
+#include "a2f_common.cuh"
+#include "gemm_params.cuh"
+
+namespace a2f {
+
+template <typename T> A2F_D T* ptr_as(void* p) { return static_cast<T*>(p); }
+
+// ------------------------------------------------------------------------------------------------ elementwise
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const TI* __restrict__ z, const TO* __restrict__ resid,
+                                                      TO* __restrict__ y, long long n, int act, int fast) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) {
+        if (i + 4 <= n) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = ld_as_float(z + i + j);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (act == A2F_ACT_GELU && fast) ? gelu_fast(v[j]) : apply_act_rt(v[j], act);
+            if (resid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] += ld_as_float(resid + i + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st_from_float(y + i + j, v[j]);
+        } else {
+            for (long long k = i; k < n; ++k) {
+                float v = ld_as_float(z + k);
+                v = (act == A2F_ACT_GELU && fast) ? gelu_fast(v) : apply_act_rt(v, act);
+                if (resid) v += ld_as_float(resid + k);
+                st_from_float(y + k, v);
+            }
+        }
+    }
+}
+
+template <typename TD, typename TZ, typename TO>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ dy, const TZ* __restrict__ z,
+                                                      TO* __restrict__ dz, long long n, int act) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) st_from_float(dz + i, ld_as_float(dy + i) * act_grad(ld_as_float(z + i), act));
+}
+
+// rows x cols (row stride ld_in) -> out rows x ld_out (columns >= cols zero filled)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_rows_kernel(const TI* __restrict__ in, long long ld_in, TO* __restrict__ out,
+                                                        long long ld_out, long long rows, int cols) {
+    const long long n = rows * ld_out;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const long long r = i / ld_out;
+        const int c = (int)(i - r * ld_out);
+        st_from_float(out + i, c < cols ? ld_as_float(in + r * ld_in + c) : 0.f);
+    }
+}
+
+// out[c*ldo + r] = in[r*ld_r + c*ld_c]   (32x32 smem tiles, coalesced on the output side)
+template <typename TO>
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ in, long long ld_r, long long ld_c,
+                                                             int R, int Cc, TO* __restrict__ out, long long ldo) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // read: fastest-varying index follows the smaller input stride
+    if (ld_c <= ld_r) {
+#pragma unroll
+        for (int j = ty; j < 32; j += 8) {
+            const int r = r0 + j, c = c0 + tx;
+            if (r < R && c < Cc) tile[j][tx] = in[(long long)r * ld_r + (long long)c * ld_c];
+        }
+    } else {
+#pragma unroll
+        for (int j = ty; j < 32; j += 8) {
+            const int r = r0 + tx, c = c0 + j;
+            if (r < R && c < Cc) tile[tx][j] = in[(long long)r * ld_r + (long long)c * ld_c];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + tx;
+        if (r < R && c < Cc) st_from_float(out + (long long)c * ldo + r, tile[tx][j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// out[n] += sum_m x[m*ld + n].  CTA = 64 columns x 256-row slab.
+template <typename TI>
+__global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ x, long long ld, long long rows, int cols,
+                                                     float* __restrict__ out) {
+    __shared__ float sh[4][64];
+    const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
+    const int c = blockIdx.x * 64 + cx;
+    const long long r0 = (long long)blockIdx.y * 256;
+    const long long r1 = r0 + 256 < rows ? r0 + 256 : rows;
+    float s = 0.f;
+    if (c < cols)
+        for (long long r = r0 + ry; r < r1; r += 4) s += ld_as_float(x + r * ld + c);
+    sh[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && c < cols) atomicAdd(out + c, (sh[0][cx] + sh[1][cx]) + (sh[2][cx] + sh[3][cx]));
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+template <typename TI> A2F_D float4 ldv4(const TI* p);
+template <> A2F_D float4 ldv4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> A2F_D float4 ldv4<bf16>(const bf16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+A2F_D void stv4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+A2F_D void stv4(bf16* p, float4 v) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+// One warp per row, rows strided over the grid; per-warp dgamma / dbeta / dbias partials live in registers and are
+// combined through shared memory once per CTA, then added atomically (<= 2*148 CTAs).
+template <typename TD, typename TX, typename TO, int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TD* __restrict__ dy, const TX* __restrict__ x,
+                                                            const float* __restrict__ gamma, float eps,
+                                                            TO* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                            long long rows) {
+    constexpr int C = NV * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 gm[NV], ag[NV], ab[NV], as[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        gm[j] = *reinterpret_cast<const float4*>(gamma + j * 128 + lane * 4);
+        ag[j] = ab[j] = as[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+        float4 xv[NV], dv[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            xv[j] = ldv4<TX>(x + row * C + j * 128 + lane * 4);
+            dv[j] = ldv4<TD>(dy + row * C + j * 128 + lane * 4);
+            s += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w);
+        }
+        const float mean = warp_sum(s) * (1.f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            xv[j].x -= mean; xv[j].y -= mean; xv[j].z -= mean; xv[j].w -= mean;
+            q += (xv[j].x * xv[j].x + xv[j].y * xv[j].y) + (xv[j].z * xv[j].z + xv[j].w * xv[j].w);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+        float s1 = 0.f, s2 = 0.f;      // sum g, sum g*xhat  with g = dy*gamma
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            xv[j].x *= rstd; xv[j].y *= rstd; xv[j].z *= rstd; xv[j].w *= rstd;      // xhat
+            ab[j].x += dv[j].x; ab[j].y += dv[j].y; ab[j].z += dv[j].z; ab[j].w += dv[j].w;
+            ag[j].x += dv[j].x * xv[j].x; ag[j].y += dv[j].y * xv[j].y; ag[j].z += dv[j].z * xv[j].z; ag[j].w += dv[j].w * xv[j].w;
+            dv[j].x *= gm[j].x; dv[j].y *= gm[j].y; dv[j].z *= gm[j].z; dv[j].w *= gm[j].w;      // g
+            s1 += (dv[j].x + dv[j].y) + (dv[j].z + dv[j].w);
+            s2 += (dv[j].x * xv[j].x + dv[j].y * xv[j].y) + (dv[j].z * xv[j].z + dv[j].w * xv[j].w);
+        }
+        s1 = warp_sum(s1) * (1.f / C);
+        s2 = warp_sum(s2) * (1.f / C);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            float4 o;
+            o.x = rstd * (dv[j].x - s1 - xv[j].x * s2);
+            o.y = rstd * (dv[j].y - s1 - xv[j].y * s2);
+            o.z = rstd * (dv[j].z - s1 - xv[j].z * s2);
+            o.w = rstd * (dv[j].w - s1 - xv[j].w * s2);
+            as[j].x += o.x; as[j].y += o.y; as[j].z += o.z; as[j].w += o.w;
+            stv4(dx + row * C + j * 128 + lane * 4, o);
+        }
+    }
+    __shared__ float sh[8][C + 4];
+    auto reduce_out = [&](float4* acc, float* dst) {
+        if (dst == nullptr) return;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NV; ++j) *reinterpret_cast<float4*>(&sh[warp][j * 128 + lane * 4]) = acc[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += sh[w][c];
+            atomicAdd(dst + c, t);
+        }
+    };
+    reduce_out(ag, dgamma);
+    reduce_out(ab, dbeta);
+    reduce_out(as, dbias);
+}
+
+// ------------------------------------------------------------------------------------------------ interp + LN backward
+// Forward (w2v_frontend.cu interp_ln_kernel): v = l0*x[i0] + l1*x[i1]; y = LN(v)*gamma + beta.  One warp per frame:
+// recompute v and its statistics, LayerNorm backward, scatter l0*dv / l1*dv into the fp32 gradient of the conv-stack
+// output with atomics (each source row receives <= ~3 frames), accumulate dgamma / dbeta.
+template <typename TI, typename TD, int C>
+__global__ void __launch_bounds__(256) interp_ln_bwd_kernel(const TI* __restrict__ in, const TD* __restrict__ dy,
+                                                            const float* __restrict__ gamma, float eps,
+                                                            float* __restrict__ din, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int B, int S, int T) {
+    constexpr int PER = C / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float ag[PER], ab[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) ag[j] = ab[j] = 0.f;
+    const float scale = T > 1 ? (float)(S - 1) / (float)(T - 1) : 0.f;
+    for (int f = blockIdx.x * 8 + warp; f < B * T; f += gridDim.x * 8) {
+        const int b = f / T, t = f % T;
+        const float src = scale * (float)t;
+        int i0 = (int)src;
+        if (i0 > S - 1) i0 = S - 1;
+        const int i1 = i0 + (i0 < S - 1 ? 1 : 0);
+        float l1 = src - (float)i0;
+        l1 = fminf(fmaxf(l1, 0.f), 1.f);
+        const float l0 = 1.f - l1;
+        const TI* r0 = in + ((long long)b * S + i0) * C;
+        const TI* r1 = in + ((long long)b * S + i1) * C;
+        float v[PER], g[PER];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int cc = j * 32 + lane;
+            v[j] = l0 * ld_as_float(r0 + cc) + l1 * ld_as_float(r1 + cc);
+            s += v[j];
+        }
+        const float mean = warp_sum(s) * (1.f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            v[j] -= mean;
+            q = fmaf(v[j], v[j], q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int cc = j * 32 + lane;
+            v[j] *= rstd;
+            const float d = ld_as_float(dy + (long long)f * C + cc);
+            ab[j] += d;
+            ag[j] += d * v[j];
+            g[j] = d * gamma[cc];
+            s1 += g[j];
+            s2 += g[j] * v[j];
+        }
+        s1 = warp_sum(s1) * (1.f / C);
+        s2 = warp_sum(s2) * (1.f / C);
+        float* d0 = din + ((long long)b * S + i0) * C;
+        float* d1 = din + ((long long)b * S + i1) * C;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int cc = j * 32 + lane;
+            const float dv = rstd * (g[j] - s1 - v[j] * s2);
+            atomicAdd(d0 + cc, l0 * dv);
+            if (l1 != 0.f) atomicAdd(d1 + cc, l1 * dv);
+        }
+    }
+    __shared__ float sh[8][C];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) sh[warp][j * 32 + lane] = ag[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w][c];
+        atomicAdd(dgamma + c, t);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) sh[warp][j * 32 + lane] = ab[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w][c];
+        atomicAdd(dbeta + c, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ conv0 backward
+// y = conv(xhat, w)  (k10, s5), zhat = (y - mu)*rstd, z = zhat*gamma + beta, a = gelu(z)   per (utterance, channel).
+// pass A:  S1 = sum_t dz, S2 = sum_t dz*zhat   with dz = da * gelu'(z)        -> atomics into S[b][c][2]
+// pass B:  dy = gamma*rstd*(dz - S1/L - zhat*S2/L);  dw[c][k] += sum_t dy*xhat[5t+k];  (chunk 0: dgamma += S2, dbeta += S1)
+constexpr int C0B_TCH = 256;
+
+template <typename TD, int PASS>
+__global__ void __launch_bounds__(256) conv0_bwd_kernel(const float* __restrict__ audio, const float* __restrict__ stats,
+                                                        const float* __restrict__ w, const float2* __restrict__ gn,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const TD* __restrict__ da, long long N, int L0,
+                                                        float* __restrict__ S, float* __restrict__ dw,
+                                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int b = blockIdx.y, t0 = blockIdx.x * C0B_TCH;
+    __shared__ float xs[5 * C0B_TCH + 8];
+    const float* x = audio + (long long)b * N;
+    const float mean = stats[2 * b], rstd_a = stats[2 * b + 1];
+    for (int i = threadIdx.x; i < 5 * C0B_TCH + 8; i += blockDim.x) {
+        const long long gi = 5LL * t0 + i;
+        xs[i] = (gi < N) ? (x[gi] - mean) * rstd_a : 0.f;
+    }
+    const int c = threadIdx.x * 2;
+    float w0[10], w1[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        w0[k] = w[c * 10 + k];
+        w1[k] = w[(c + 1) * 10 + k];
+    }
+    const float2 g0 = gn[b * 512 + c], g1 = gn[b * 512 + c + 1];
+    const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
+    float m1a = 0.f, m2a = 0.f, m1b = 0.f, m2b = 0.f;
+    float S1a = 0.f, S2a = 0.f, S1b = 0.f, S2b = 0.f;
+    const float invL = 1.f / (float)L0;
+    if (PASS == 1) {
+        S1a = S[(b * 512 + c) * 2] * invL; S2a = S[(b * 512 + c) * 2 + 1] * invL;
+        S1b = S[(b * 512 + c + 1) * 2] * invL; S2b = S[(b * 512 + c + 1) * 2 + 1] * invL;
+    }
+    float dwa[10], dwb[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) dwa[k] = dwb[k] = 0.f;
+    __syncthreads();
+    const TD* dab = da + (long long)b * L0 * 512;
+    const int tn = min(C0B_TCH, L0 - t0);
+    for (int t = 0; t < tn; ++t) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            a0 = fmaf(w0[k], xs[5 * t + k], a0);
+            a1 = fmaf(w1[k], xs[5 * t + k], a1);
+        }
+        const float zh0 = (a0 - g0.x) * g0.y, zh1 = (a1 - g1.x) * g1.y;
+        const float z0 = zh0 * ga0 + be0, z1 = zh1 * ga1 + be1;
+        const TD* dp = dab + (long long)(t0 + t) * 512 + c;
+        const float dz0 = ld_as_float(dp) * act_grad(z0, A2F_ACT_GELU);
+        const float dz1 = ld_as_float(dp + 1) * act_grad(z1, A2F_ACT_GELU);
+        if (PASS == 0) {
+            m1a += dz0; m2a = fmaf(dz0, zh0, m2a);
+            m1b += dz1; m2b = fmaf(dz1, zh1, m2b);
+        } else {
+            const float dy0 = ga0 * g0.y * (dz0 - S1a - zh0 * S2a);
+            const float dy1 = ga1 * g1.y * (dz1 - S1b - zh1 * S2b);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                dwa[k] = fmaf(dy0, xs[5 * t + k], dwa[k]);
+                dwb[k] = fmaf(dy1, xs[5 * t + k], dwb[k]);
+            }
+        }
+    }
+    if (PASS == 0) {
+        atomicAdd(S + (b * 512 + c) * 2, m1a);
+        atomicAdd(S + (b * 512 + c) * 2 + 1, m2a);
+        atomicAdd(S + (b * 512 + c + 1) * 2, m1b);
+        atomicAdd(S + (b * 512 + c + 1) * 2 + 1, m2b);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            atomicAdd(dw + c * 10 + k, dwa[k]);
+            atomicAdd(dw + (c + 1) * 10 + k, dwb[k]);
+        }
+        if (blockIdx.x == 0) {
+            atomicAdd(dbeta + c, S1a * (float)L0);
+            atomicAdd(dgamma + c, S2a * (float)L0);
+            atomicAdd(dbeta + c + 1, S1b * (float)L0);
+            atomicAdd(dgamma + c + 1, S2b * (float)L0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight norm backward
+// w[o,c,tap] = v[o,c,tap] * g[tap] / n[tap],  n[tap] = ||v[:,:,tap]||.   dWp is in the packed layout
+// [16 groups][48 out][128 taps][48 in] (the layout a2f_gemm_wgrad writes).
+//   dot[tap] = sum_{o,c} dW*v ;  dg[tap] += dot/n ;  dv += (g/n) * (dW - v*dot/n^2)
+__global__ void __launch_bounds__(256) wn_dot_kernel(const float* __restrict__ dWp, const float* __restrict__ v,
+                                                     double* __restrict__ dot, double* __restrict__ nrm2) {
+    const int tap = blockIdx.x;
+    double s = 0.0, n2 = 0.0;
+    for (int i = threadIdx.x; i < 768 * 48; i += blockDim.x) {
+        const int o = i / 48, c = i - o * 48;
+        const double vv = v[(long long)i * 128 + tap];
+        const double dw = dWp[((long long)o * 128 + tap) * 48 + c];
+        s += dw * vv;
+        n2 += vv * vv;
+    }
+    __shared__ double sh[2][8];
+    s = warp_sum_d(s);
+    n2 = warp_sum_d(n2);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = n2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, bq = 0.0;
+        for (int i = 0; i < 8; ++i) { a += sh[0][i]; bq += sh[1][i]; }
+        dot[tap] = a;
+        nrm2[tap] = bq;
+    }
+}
+__global__ void __launch_bounds__(256) wn_apply_kernel(const float* __restrict__ dWp, const float* __restrict__ v,
+                                                       const float* __restrict__ g, const double* __restrict__ dot,
+                                                       const double* __restrict__ nrm2, float* __restrict__ dv,
+                                                       float* __restrict__ dg) {
+    const long long n = (long long)768 * 48 * 128;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (i < 128) dg[i] += (float)(dot[i] / sqrt(nrm2[i]));
+    for (; i < n; i += stride) {
+        const int tap = (int)(i % 128);
+        const long long oc = i / 128;
+        const int c = (int)(oc % 48);
+        const long long o = oc / 48;
+        const double nn = sqrt(nrm2[tap]);
+        const double dw = dWp[(o * 128 + tap) * 48 + c];
+        dv[i] += (float)(((double)g[tap] / nn) * (dw - (double)v[i] * dot[tap] / nrm2[tap]));
+    }
+}
+
+// Data-gradient weight of the positional conv: Wd[g][ci(48)][tap'(128)][co (kpad)] = w_eff[g*48+co, ci, 127-tap']
+// so that the forward grouped-conv kernel run on the output gradient with a time shift of 63 gives the input gradient.
+template <typename TO>
+__global__ void posconv_pack_dgrad_kernel(const float* __restrict__ gw, const float* __restrict__ v,
+                                          const float* __restrict__ norm, TO* __restrict__ out, int kpad) {
+    const long long n = (long long)768 * 128 * kpad;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int co = (int)(i % kpad);
+        long long r = i / kpad;
+        const int tapp = (int)(r % 128);
+        r /= 128;                    // g*48 + ci
+        const int ci = (int)(r % 48), grp = (int)(r / 48);
+        float val = 0.f;
+        if (co < 48) {
+            const int tap = 127 - tapp;
+            val = v[((long long)(grp * 48 + co) * 48 + ci) * 128 + tap] * (gw[tap] / norm[tap]);
+        }
+        st_from_float(out + i, val);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam(lr, weight_decay) semantics (L2 added to the gradient), bias-corrected; grad pre-scaled by gscale.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2,
+                                                   float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float step = lr / bc1;
+    for (; i < n; i += stride) {
+        const float pi = p[i];
+        const float gi = fmaf(wd, pi, g[i] * gscale);
+        const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+}
+
+static int ew_grid(long long n, int per_thread = 1) {
+    long long blocks = (n / per_thread + 255) / 256;
+    const long long cap = 16LL * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace a2f
+
+using namespace a2f;
+
+extern "C" {
+
+int a2f_act_fwd(const void* z, int z_dtype, const void* resid, void* y, int y_dtype, long long n, int act, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(z && y && n >= 0, "a2f_act_fwd: bad arguments");
+    if (n == 0) return A2F_OK;
+    cudaStream_t s = as_stream(stream);
+    const int grid = ew_grid(n, 4);
+    const bool zi = z_dtype == A2F_BF16, yi = y_dtype == A2F_BF16;
+    // bf16 path: same MUFU.TANH GELU as the inference epilogues; fp32 path: exact erf
+    if (!zi && !yi) act_fwd_kernel<float, float><<<grid, 256, 0, s>>>((const float*)z, (const float*)resid, (float*)y, n, act, 0);
+    else if (zi && yi) act_fwd_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)z, (const bf16*)resid, (bf16*)y, n, act, 1);
+    else if (!zi && yi) act_fwd_kernel<float, bf16><<<grid, 256, 0, s>>>((const float*)z, (const bf16*)resid, (bf16*)y, n, act, 1);
+    else act_fwd_kernel<bf16, float><<<grid, 256, 0, s>>>((const bf16*)z, (const float*)resid, (float*)y, n, act, 0);
+    A2F_CHECK_LAUNCH("act_fwd_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_act_bwd(const void* dy, int dy_dtype, const void* z, int z_dtype, void* dz, int dz_dtype, long long n, int act,
+                void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(dy && z && dz && n >= 0, "a2f_act_bwd: bad arguments");
+    if (n == 0) return A2F_OK;
+    cudaStream_t s = as_stream(stream);
+    const int grid = ew_grid(n);
+    const int key = (dy_dtype == A2F_BF16 ? 4 : 0) | (z_dtype == A2F_BF16 ? 2 : 0) | (dz_dtype == A2F_BF16 ? 1 : 0);
+    switch (key) {
+        case 0: act_bwd_kernel<float, float, float><<<grid, 256, 0, s>>>((const float*)dy, (const float*)z, (float*)dz, n, act); break;
+        case 3: act_bwd_kernel<float, bf16, bf16><<<grid, 256, 0, s>>>((const float*)dy, (const bf16*)z, (bf16*)dz, n, act); break;
+        case 7: act_bwd_kernel<bf16, bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)dy, (const bf16*)z, (bf16*)dz, n, act); break;
+        case 1: act_bwd_kernel<float, float, bf16><<<grid, 256, 0, s>>>((const float*)dy, (const float*)z, (bf16*)dz, n, act); break;
+        default: return set_error(A2F_EINVAL, "a2f_act_bwd: unsupported dtype combination");
+    }
+    A2F_CHECK_LAUNCH("act_bwd_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_cast_rows(const void* in, int in_dtype, long long ld_in, void* out, int out_dtype, long long ld_out, long long rows,
+                  int cols, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(in && out && rows >= 0 && cols > 0 && ld_in >= cols && ld_out >= cols, "a2f_cast_rows: bad arguments");
+    if (rows == 0) return A2F_OK;
+    cudaStream_t s = as_stream(stream);
+    const int grid = ew_grid(rows * ld_out);
+    const bool ii = in_dtype == A2F_BF16, oi = out_dtype == A2F_BF16;
+    if (!ii && oi) cast_rows_kernel<float, bf16><<<grid, 256, 0, s>>>((const float*)in, ld_in, (bf16*)out, ld_out, rows, cols);
+    else if (ii && !oi) cast_rows_kernel<bf16, float><<<grid, 256, 0, s>>>((const bf16*)in, ld_in, (float*)out, ld_out, rows, cols);
+    else if (!ii && !oi) cast_rows_kernel<float, float><<<grid, 256, 0, s>>>((const float*)in, ld_in, (float*)out, ld_out, rows, cols);
+    else cast_rows_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)in, ld_in, (bf16*)out, ld_out, rows, cols);
+    A2F_CHECK_LAUNCH("cast_rows_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_transpose_cast(const float* in, long long ld_r, long long ld_c, int R, int Cc, void* out, int out_dtype,
+                       long long ldo, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(in && out && R > 0 && Cc > 0 && ldo >= R, "a2f_transpose_cast: bad arguments");
+    const dim3 grid((Cc + 31) / 32, (R + 31) / 32);
+    cudaStream_t s = as_stream(stream);
+    if (out_dtype == A2F_BF16) transpose_cast_kernel<bf16><<<grid, 256, 0, s>>>(in, ld_r, ld_c, R, Cc, (bf16*)out, ldo);
+    else transpose_cast_kernel<float><<<grid, 256, 0, s>>>(in, ld_r, ld_c, R, Cc, (float*)out, ldo);
+    A2F_CHECK_LAUNCH("transpose_cast_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_colsum(const void* x, int dtype, long long ld, long long rows, int cols, float* out, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(x && out && rows >= 0 && cols > 0 && ld >= cols, "a2f_colsum: bad arguments");
+    if (rows == 0) return A2F_OK;
+    const dim3 grid((cols + 63) / 64, (unsigned)((rows + 255) / 256));
+    cudaStream_t s = as_stream(stream);
+    if (dtype == A2F_BF16) colsum_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, ld, rows, cols, out);
+    else colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, ld, rows, cols, out);
+    A2F_CHECK_LAUNCH("colsum_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, float eps, void* dx,
+                      int dx_dtype, float* dgamma, float* dbeta, float* dbias, long long rows, int C, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(dy && x && gamma && dx && rows >= 0, "a2f_layernorm_bwd: bad arguments");
+    A2F_REQUIRE(C == 512 || C == 768, "a2f_layernorm_bwd: C must be 512 or 768");
+    A2F_REQUIRE(dy_dtype == x_dtype && x_dtype == dx_dtype, "a2f_layernorm_bwd: dy, x and dx must share a dtype");
+    if (rows == 0) return A2F_OK;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 2LL * sm_count()) blocks = 2LL * sm_count();
+    cudaStream_t s = as_stream(stream);
+    const int grid = (int)blocks;
+#define A2F_LNB(T, NV)                                                                                                  \
+    layernorm_bwd_kernel<T, T, T, NV><<<grid, 256, 0, s>>>((const T*)dy, (const T*)x, gamma, eps, (T*)dx, dgamma, dbeta, \
+                                                            dbias, rows)
+    if (x_dtype == A2F_BF16) {
+        if (C == 512) A2F_LNB(bf16, 4); else A2F_LNB(bf16, 6);
+    } else {
+        if (C == 512) A2F_LNB(float, 4); else A2F_LNB(float, 6);
+    }
+#undef A2F_LNB
+    A2F_CHECK_LAUNCH("layernorm_bwd_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_interp_ln_bwd(const void* in, int in_dtype, const void* dy, int dy_dtype, const float* gamma, float eps,
+                      float* din, float* dgamma, float* dbeta, int B, int S, int T, int C, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(in && dy && gamma && din && dgamma && dbeta && B > 0 && S > 0 && T > 0, "a2f_interp_ln_bwd: bad arguments");
+    A2F_REQUIRE(C == 512, "a2f_interp_ln_bwd: C must be 512");
+    A2F_REQUIRE(in_dtype == dy_dtype, "a2f_interp_ln_bwd: in and dy must share a dtype");
+    long long blocks = ((long long)B * T + 7) / 8;
+    if (blocks > 2LL * sm_count()) blocks = 2LL * sm_count();
+    cudaStream_t s = as_stream(stream);
+    if (in_dtype == A2F_BF16)
+        interp_ln_bwd_kernel<bf16, bf16, 512><<<(int)blocks, 256, 0, s>>>((const bf16*)in, (const bf16*)dy, gamma, eps, din,
+                                                                          dgamma, dbeta, B, S, T);
+    else
+        interp_ln_bwd_kernel<float, float, 512><<<(int)blocks, 256, 0, s>>>((const float*)in, (const float*)dy, gamma, eps,
+                                                                            din, dgamma, dbeta, B, S, T);
+    A2F_CHECK_LAUNCH("interp_ln_bwd_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+size_t a2f_conv0_bwd_workspace_bytes(int B) { return B > 0 ? (size_t)B * 512 * 2 * sizeof(float) : 0; }
+
+int a2f_conv0_bwd(const float* audio, const float* stats, const float* w, const float* gamma, const float* beta,
+                  const void* gn_stats, const void* da, int da_dtype, int B, long long N, float* dw, float* dgamma,
+                  float* dbeta, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(audio && stats && w && gamma && beta && gn_stats && da && dw && dgamma && dbeta && workspace,
+                "a2f_conv0_bwd: NULL argument");
+    A2F_REQUIRE(B > 0 && N >= 10, "a2f_conv0_bwd: bad sizes");
+    A2F_REQUIRE(workspace_bytes >= a2f_conv0_bwd_workspace_bytes(B), "a2f_conv0_bwd: workspace too small");
+    const int L0 = (int)((N - 10) / 5 + 1);
+    cudaStream_t s = as_stream(stream);
+    float* S = static_cast<float*>(workspace);
+    A2F_CHECK_CUDA(cudaMemsetAsync(S, 0, a2f_conv0_bwd_workspace_bytes(B), s));
+    const dim3 grid((L0 + C0B_TCH - 1) / C0B_TCH, B);
+    const float2* gn = static_cast<const float2*>(gn_stats);
+    if (da_dtype == A2F_BF16) {
+        conv0_bwd_kernel<bf16, 0><<<grid, 256, 0, s>>>(audio, stats, w, gn, gamma, beta, (const bf16*)da, N, L0, S, dw, dgamma, dbeta);
+        conv0_bwd_kernel<bf16, 1><<<grid, 256, 0, s>>>(audio, stats, w, gn, gamma, beta, (const bf16*)da, N, L0, S, dw, dgamma, dbeta);
+    } else {
+        conv0_bwd_kernel<float, 0><<<grid, 256, 0, s>>>(audio, stats, w, gn, gamma, beta, (const float*)da, N, L0, S, dw, dgamma, dbeta);
+        conv0_bwd_kernel<float, 1><<<grid, 256, 0, s>>>(audio, stats, w, gn, gamma, beta, (const float*)da, N, L0, S, dw, dgamma, dbeta);
+    }
+    A2F_CHECK_LAUNCH("conv0_bwd_kernel");
+    count_launch(2);
+    return A2F_OK;
+}
+
+int a2f_weight_norm_bwd(const float* dWp, const float* v, const float* g, float* dv, float* dg, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(dWp && v && g && dv && dg && workspace, "a2f_weight_norm_bwd: NULL argument");
+    A2F_REQUIRE(workspace_bytes >= 256 * sizeof(double) && reinterpret_cast<uintptr_t>(workspace) % 8 == 0,
+                "a2f_weight_norm_bwd: workspace must hold 256 doubles");
+    double* dot = static_cast<double*>(workspace);
+    double* nrm2 = dot + 128;
+    cudaStream_t s = as_stream(stream);
+    wn_dot_kernel<<<128, 256, 0, s>>>(dWp, v, dot, nrm2);
+    A2F_CHECK_LAUNCH("wn_dot_kernel");
+    wn_apply_kernel<<<ew_grid(768LL * 48 * 128), 256, 0, s>>>(dWp, v, g, dot, nrm2, dv, dg);
+    A2F_CHECK_LAUNCH("wn_apply_kernel");
+    count_launch(2);
+    return A2F_OK;
+}
+
+int a2f_pack_posconv_dgrad_weight(const float* g, const float* v, void* out, int out_dtype, int kpad, float* norm,
+                                  void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(g && v && out && norm && (kpad == 48 || kpad == 64), "a2f_pack_posconv_dgrad_weight: bad arguments");
+    // norm[128] must already hold ||v[:,:,tap]|| (a2f_pack_posconv_weight fills it)
+    cudaStream_t s = as_stream(stream);
+    const int grid = ew_grid(768LL * 128 * kpad);
+    if (out_dtype == A2F_BF16) posconv_pack_dgrad_kernel<bf16><<<grid, 256, 0, s>>>(g, v, norm, (bf16*)out, kpad);
+    else posconv_pack_dgrad_kernel<float><<<grid, 256, 0, s>>>(g, v, norm, (float*)out, kpad);
+    A2F_CHECK_LAUNCH("posconv_pack_dgrad_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, float grad_scale, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "a2f_adam_step: bad arguments");
+    if (n == 0) return A2F_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    adam_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
+                                                           grad_scale);
+    A2F_CHECK_LAUNCH("adam_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+}  // extern "C"

@@ -345,6 +345,11 @@ size_t a2f_conv0_workspace_bytes(int B, long long N) {
     return partial + gn + 64;
 }
 
+size_t a2f_conv0_gn_offset(int B, long long N) {
+    if (B <= 0 || N < 10) return 0;
+    return (size_t)B * conv0_nchunk(N) * MOM_N * sizeof(double);
+}
+
 int a2f_conv0_gn_gelu(const float* audio, const float* stats, const float* w, const float* gamma, const float* beta,
                       void* out, int out_dtype, int B, long long N, void* workspace, size_t workspace_bytes,
                       void* stream) {

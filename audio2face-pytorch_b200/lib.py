@@ -47,7 +47,7 @@ class WgradArgs(C.Structure):
         ("X", c_void_p), ("x_row_stride", c_ll), ("x_batch_stride", c_ll),
         ("rows_per_batch", c_int), ("x_rows", c_int), ("n_seg", c_int),
         ("x_row_off", c_int * 4), ("x_col_off", c_int * 4),
-        ("dW", c_void_p), ("ldw", c_ll),
+        ("dW", c_void_p), ("ldw", c_ll), ("x_row_step", c_int),
     ]
 
 
@@ -91,6 +91,9 @@ _SIGNATURES = {
     "a2f_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int, c_ll,
                               c_int, c_void_p]),
     "a2f_mha_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "a2f_mha_fwd_lse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "a2f_mha_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                            c_void_p, c_size_t, c_void_p]),
     "a2f_decoder_workspace_bytes": (c_size_t, [c_int, c_int]),
     "a2f_decoder_rollout": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                     c_int, c_void_p, c_size_t, c_void_p]),
@@ -104,6 +107,26 @@ _SIGNATURES = {
                                   c_void_p]),
     "a2f_voca_loss_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "a2f_debug_set_umma_field": (c_int, [c_int, C.c_uint]),
+    "a2f_act_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
+    "a2f_act_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p]),
+    "a2f_cast_rows": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_ll, c_int, c_void_p]),
+    "a2f_transpose_cast": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_void_p, c_int, c_ll, c_void_p]),
+    "a2f_colsum": (c_int, [c_void_p, c_int, c_ll, c_ll, c_int, c_void_p, c_void_p]),
+    "a2f_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "a2f_interp_ln_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_int, c_int, c_void_p]),
+    "a2f_conv0_gn_offset": (c_size_t, [c_int, c_ll]),
+    "a2f_conv0_bwd_workspace_bytes": (c_size_t, [c_int]),
+    "a2f_conv0_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "a2f_weight_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "a2f_pack_posconv_dgrad_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "a2f_posconv_dgrad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "a2f_posconv_pre": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "a2f_posconv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "a2f_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
+                              c_int, c_float, c_void_p]),
 }
 
 _lib = None

@@ -298,3 +298,186 @@ def decoder_rollout(wstruct: "L.DecoderWeights", memory: torch.Tensor, one_hot: 
     L.check(lib.a2f_decoder_rollout(C.byref(wstruct), memory.data_ptr(), one_hot.data_ptr(), one_hot.shape[1], period,
                                     D.data_ptr(), B, T, ws.data_ptr(), ws.numel() * 4, _stream()), "a2f_decoder_rollout")
     return D
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training step (backward-pass kernels, csrc/train.cu / attention.cu / decoder_bwd.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def act_fwd(z: torch.Tensor, act: int, out_dtype: Optional[torch.dtype] = None, resid: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _dev(z, resid, out)
+    if out is None:
+        out = torch.empty(z.shape, dtype=out_dtype or z.dtype, device=z.device)
+    if resid is not None and resid.dtype != out.dtype:
+        raise L.A2FError("act_fwd: resid must have the output dtype")
+    L.check(L.load().a2f_act_fwd(z.data_ptr(), _dt(z), L.ptr(resid), out.data_ptr(), _dt(out), z.numel(), act, _stream()),
+            "a2f_act_fwd")
+    return out
+
+
+def act_bwd(dy: torch.Tensor, z: torch.Tensor, act: int, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    _dev(dy, z)
+    out = torch.empty(z.shape, dtype=out_dtype or z.dtype, device=z.device)
+    L.check(L.load().a2f_act_bwd(dy.data_ptr(), _dt(dy), z.data_ptr(), _dt(z), out.data_ptr(), _dt(out), z.numel(), act,
+                                 _stream()), "a2f_act_bwd")
+    return out
+
+
+def cast_rows(x: torch.Tensor, out_dtype: torch.dtype, ld_out: int) -> torch.Tensor:
+    """[rows, cols] -> [rows, ld_out] converted, zero padded on the right."""
+    _dev(x)
+    rows, cols = x.shape
+    out = torch.empty((rows, ld_out), dtype=out_dtype, device=x.device)
+    L.check(L.load().a2f_cast_rows(x.data_ptr(), _dt(x), x.stride(0), out.data_ptr(), _dt(out), ld_out, rows, cols, _stream()),
+            "a2f_cast_rows")
+    return out
+
+
+def transpose_cast(w: torch.Tensor, out_dtype: torch.dtype, R: Optional[int] = None, Cc: Optional[int] = None,
+                   ld_r: Optional[int] = None, ld_c: int = 1, offset: int = 0, out: Optional[torch.Tensor] = None,
+                   ldo: Optional[int] = None, out_offset: int = 0) -> torch.Tensor:
+    """out[c, r] = w.flat[offset + r*ld_r + c*ld_c]  (fp32 in, fp32/bf16 out)."""
+    _dev(w)
+    if w.dtype != torch.float32:
+        raise L.A2FError("transpose_cast takes fp32 input")
+    R = int(R if R is not None else w.shape[0])
+    Cc = int(Cc if Cc is not None else w.shape[1])
+    ld_r = int(ld_r if ld_r is not None else w.stride(0))
+    if out is None:
+        out = torch.empty((Cc, R), dtype=out_dtype, device=w.device)
+    ldo = int(ldo if ldo is not None else out.stride(0))
+    L.check(L.load().a2f_transpose_cast(w.data_ptr() + 4 * offset, ld_r, ld_c, R, Cc,
+                                        out.data_ptr() + out_offset * out.element_size(), _dt(out), ldo, _stream()),
+            "a2f_transpose_cast")
+    return out
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, rows: Optional[int] = None, cols: Optional[int] = None,
+           ld: Optional[int] = None) -> torch.Tensor:
+    """out[n] += sum_m x[m, n]"""
+    _dev(x, out)
+    rows = int(rows if rows is not None else x.shape[0])
+    cols = int(cols if cols is not None else x.shape[1])
+    L.check(L.load().a2f_colsum(x.data_ptr(), _dt(x), int(ld if ld is not None else x.stride(0)), rows, cols, out.data_ptr(),
+                                _stream()), "a2f_colsum")
+    return out
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                  dbias: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+    _dev(dy, x, gamma, dgamma, dbeta, dbias)
+    rows, Cc = x.shape
+    dx = torch.empty_like(x)
+    L.check(L.load().a2f_layernorm_bwd(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), gamma.data_ptr(), eps, dx.data_ptr(),
+                                       _dt(dx), dgamma.data_ptr(), dbeta.data_ptr(), L.ptr(dbias), rows, Cc, _stream()),
+            "a2f_layernorm_bwd")
+    return dx
+
+
+def interp_ln_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                  eps: float = 1e-5) -> torch.Tensor:
+    """x [B,S,512] saved input, dy [B,T,512] -> fp32 gradient wrt x."""
+    _dev(x, dy, gamma, dgamma, dbeta)
+    B, S, Cc = x.shape
+    T = dy.shape[1]
+    din = torch.zeros((B, S, Cc), dtype=torch.float32, device=x.device)
+    L.check(L.load().a2f_interp_ln_bwd(x.data_ptr(), _dt(x), dy.data_ptr(), _dt(dy), gamma.data_ptr(), eps, din.data_ptr(),
+                                       dgamma.data_ptr(), dbeta.data_ptr(), B, S, T, Cc, _stream()), "a2f_interp_ln_bwd")
+    return din
+
+
+def conv0_gn_gelu_train(audio, stats, w, gamma, beta, dtype):
+    """conv0_gn_gelu that also returns the workspace (it holds the GroupNorm statistics the backward needs)."""
+    _dev(audio, stats, w, gamma, beta)
+    B, N = audio.shape
+    L0 = (N - 10) // 5 + 1
+    lib = L.load()
+    nbytes = lib.a2f_conv0_workspace_bytes(B, N)
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=audio.device)
+    out = torch.empty((B, L0, 512), dtype=dtype, device=audio.device)
+    L.check(lib.a2f_conv0_gn_gelu(audio.data_ptr(), stats.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                  out.data_ptr(), _dt(out), B, N, ws.data_ptr(), ws.numel() * 8, _stream()),
+            "a2f_conv0_gn_gelu")
+    return out, ws
+
+
+def conv0_bwd(audio, stats, w, gamma, beta, ws, da, dw, dgamma, dbeta):
+    _dev(audio, stats, w, gamma, beta, ws, da, dw, dgamma, dbeta)
+    B, N = audio.shape
+    lib = L.load()
+    off = lib.a2f_conv0_gn_offset(B, N)
+    nb = lib.a2f_conv0_bwd_workspace_bytes(B)
+    scratch = torch.empty((nb + 3) // 4, dtype=torch.float32, device=audio.device)
+    L.check(lib.a2f_conv0_bwd(audio.data_ptr(), stats.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                              ws.data_ptr() + off, da.data_ptr(), _dt(da), B, N, dw.data_ptr(), dgamma.data_ptr(),
+                              dbeta.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, _stream()), "a2f_conv0_bwd")
+
+
+def pack_posconv_weights_train(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype):
+    """-> (forward packed weight, data-gradient packed weight)"""
+    _dev(g, v)
+    kpad = 64 if dtype == torch.bfloat16 else 48
+    lib = L.load()
+    fwd = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+    bwd = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+    norm = torch.empty(128, dtype=torch.float32, device=v.device)
+    gc, vc = g.contiguous(), v.contiguous()
+    L.check(lib.a2f_pack_posconv_weight(gc.data_ptr(), vc.data_ptr(), fwd.data_ptr(), _dt(fwd), kpad, norm.data_ptr(), _stream()),
+            "a2f_pack_posconv_weight")
+    L.check(lib.a2f_pack_posconv_dgrad_weight(gc.data_ptr(), vc.data_ptr(), bwd.data_ptr(), _dt(bwd), kpad, norm.data_ptr(),
+                                              _stream()), "a2f_pack_posconv_dgrad_weight")
+    return fwd, bwd
+
+
+def posconv_pre(h, wp, bias, B, T, backend):
+    _dev(h, wp, bias)
+    pc = torch.empty_like(h)
+    L.check(L.load().a2f_posconv_pre(h.data_ptr(), _dt(h), wp.data_ptr(), bias.data_ptr(), pc.data_ptr(), B, T, backend,
+                                     _stream()), "a2f_posconv_pre")
+    return pc
+
+
+def posconv_dgrad(dpc, wd, dout, B, T, backend):
+    _dev(dpc, wd, dout)
+    dh = torch.empty_like(dpc)
+    L.check(L.load().a2f_posconv_dgrad(dpc.data_ptr(), _dt(dpc), wd.data_ptr(), L.ptr(dout), dh.data_ptr(), B, T, backend,
+                                       _stream()), "a2f_posconv_dgrad")
+    return dh
+
+
+def posconv_wgrad(dpc, h, B, T, backend):
+    """-> fp32 gradient wrt the effective conv weight in the packed layout [16][48][128][48]"""
+    _dev(dpc, h)
+    dwp = torch.zeros((16, 48, 128, 48), dtype=torch.float32, device=h.device)
+    L.check(L.load().a2f_posconv_wgrad(dpc.data_ptr(), h.data_ptr(), _dt(h), dwp.data_ptr(), B, T, backend, _stream()),
+            "a2f_posconv_wgrad")
+    return dwp
+
+
+def weight_norm_bwd(dwp, v, g, dv, dg):
+    _dev(dwp, v, g, dv, dg)
+    ws = torch.empty(256, dtype=torch.float64, device=v.device)
+    L.check(L.load().a2f_weight_norm_bwd(dwp.data_ptr(), v.data_ptr(), g.data_ptr(), dv.data_ptr(), dg.data_ptr(),
+                                         ws.data_ptr(), 256 * 8, _stream()), "a2f_weight_norm_bwd")
+
+
+def mha_lse(qkv, out, lse, B, T, H=12, D=64, scale=0.125):
+    _dev(qkv, out, lse)
+    L.check(L.load().a2f_mha_fwd_lse(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), _dt(qkv), B, T, H, D, scale, _stream()),
+            "a2f_mha_fwd_lse")
+    return out
+
+
+def mha_bwd(qkv, out, dout, lse, B, T, H=12, D=64, scale=0.125):
+    _dev(qkv, out, dout, lse)
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(B * H * T, dtype=torch.float32, device=qkv.device)
+    L.check(L.load().a2f_mha_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), _dt(qkv),
+                                 B, T, H, D, scale, ws.data_ptr(), ws.numel() * 4, _stream()), "a2f_mha_bwd")
+    return dqkv
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    _dev(p, g, m, v)
+    L.check(L.load().a2f_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                                   weight_decay, int(step), grad_scale, _stream()), "a2f_adam_step")

@@ -119,11 +119,13 @@ typedef struct a2f_wgrad_args {
     long long x_row_stride, x_batch_stride;
     int rows_per_batch; /* logical rows (of dY) per batch */
     int x_rows;         /* rows of X that exist per batch (0 = rows_per_batch) */
-    int n_seg;          /* 0/1 = one segment */
+    int n_seg;          /* 0/1 = one segment; 2..4 = table below; > 4 needs x_row_step (linear table) */
     int x_row_off[4];
     int x_col_off[4];
     float* dW;
     long long ldw;
+    int x_row_step;     /* != 0: segment s reads rows r + x_row_off[0] + s*x_row_step, columns x_col_off[0].. (the 128
+                           taps of the positional conv); the table entries 1..3 are ignored */
 } a2f_wgrad_args;
 int a2f_gemm_wgrad(const a2f_wgrad_args* args, int backend, void* stream);
 
@@ -179,6 +181,13 @@ int a2f_layernorm(const void* x, int x_dtype, const float* gamma, const float* b
  * D must be 64.  fp32 in/out -> SIMT fp32 kernel; bf16 in/out -> tensor-core kernel.
  * ---------------------------------------------------------------------------------------------------------- */
 int a2f_mha_fwd(const void* qkv, void* out, int dtype, int B, int T, int H, int D, float scale, void* stream);
+/* same, also writing the row log-sum-exp of the scaled scores, lse [B,H,T] fp32 (needed by the backward) */
+int a2f_mha_fwd_lse(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H, int D, float scale,
+                    void* stream);
+/* backward: dqkv [B,T,3*H*D] (dq | dk | dv) from dout [B,T,H*D]; the probabilities are recomputed from q, k and lse,
+ * never stored.  workspace: B*H*T floats.  bf16: two mma.sync passes (query-major dQ, key-major dK/dV), no atomics. */
+int a2f_mha_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int dtype, int B, int T,
+                int H, int D, float scale, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * FaceFormer autoregressive decoder (ref:src/model/faceformer.py:154-185; torch nn.TransformerDecoderLayer
@@ -264,6 +273,62 @@ int a2f_voca_loss_fwd(const float* pred, const float* gt, long long rows, int V3
 int a2f_voca_loss_bwd(const float* pred, const float* gt, long long rows, int V3, float k_rec, float k_vel,
                       const float* gscale /* device scalar d(out)/d(loss), or NULL = 1 */, float* dpred,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step (BASELINE.json configs[3]): the backward pass of the path above.  The reference gets it from
+ * torch.autograd over ref:src/model/faceformer.py:139-188 + HF Wav2Vec2Model inside Lightning's training_step
+ * (ref:src/model/lightning_model.py:150-161); here every backward op is an explicit kernel.  Gradient outputs that are
+ * parameter gradients (dgamma, dbeta, dbias, dw, dW, dv, dg ...) are ACCUMULATED into (+=), like autograd's .grad.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* y = act(z) + resid (resid optional, dtype of y) / dz = dy * act'(z), n elements (GELU / ReLU / tanh of the forward
+ * epilogues, kept as separate passes in training because the backward needs the pre-activation z). */
+int a2f_act_fwd(const void* z, int z_dtype, const void* resid, void* y, int y_dtype, long long n, int act, void* stream);
+int a2f_act_bwd(const void* dy, int dy_dtype, const void* z, int z_dtype, void* dz, int dz_dtype, long long n, int act,
+                void* stream);
+/* out[r, 0:cols] = in[r, 0:cols] converted, out[r, cols:ld_out] = 0 (bf16 operand of a backward GEMM from fp32 rows
+ * whose length is not a multiple of 8, e.g. the 15069-wide vertex gradient). */
+int a2f_cast_rows(const void* in, int in_dtype, long long ld_in, void* out, int out_dtype, long long ld_out, long long rows,
+                  int cols, void* stream);
+/* out[c*ldo + r] = in[r*ld_r + c*ld_c], r < R, c < C: W^T operands of the data-gradient GEMMs (Linear: ld_c = 1;
+ * one tap of a Conv1d weight [co,ci,taps]: ld_r = ci*taps, ld_c = taps). */
+int a2f_transpose_cast(const float* in, long long ld_r, long long ld_c, int R, int C, void* out, int out_dtype,
+                       long long ldo, void* stream);
+/* bias gradient: out[n] += sum_m x[m*ld + n] */
+int a2f_colsum(const void* x, int dtype, long long ld, long long rows, int cols, float* out, void* stream);
+/* LayerNorm backward over the last dim (C = 512 or 768): x is the saved LayerNorm INPUT.  dgamma / dbeta accumulate;
+ * dbias (optional) accumulates the column sums of dx = the bias gradient of the Linear that produced x. */
+int a2f_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, float eps, void* dx,
+                      int dx_dtype, float* dgamma, float* dbeta, float* dbias, long long rows, int C, void* stream);
+/* backward of a2f_interp_ln: `in` [B,S,C] is the saved input, dy [B,T,C]; din [B,S,C] fp32 is ACCUMULATED into. */
+int a2f_interp_ln_bwd(const void* in, int in_dtype, const void* dy, int dy_dtype, const float* gamma, float eps,
+                      float* din, float* dgamma, float* dbeta, int B, int S, int T, int C, void* stream);
+/* backward of a2f_conv0_gn_gelu given da = dL/d(output) [B,L0,512]; gn_stats = the [B,512] (mean, rstd) float2 block
+ * the forward left in its workspace (offset a2f_conv0_gn_offset(B,N) bytes).  dw [512,10], dgamma, dbeta accumulate. */
+size_t a2f_conv0_gn_offset(int B, long long N);
+size_t a2f_conv0_bwd_workspace_bytes(int B);
+int a2f_conv0_bwd(const float* audio, const float* stats, const float* w, const float* gamma, const float* beta,
+                  const void* gn_stats, const void* da, int da_dtype, int B, long long N, float* dw, float* dgamma,
+                  float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+/* weight_norm backward of the positional conv: dWp = gradient wrt the effective weight in the packed fp32 layout
+ * [16][48][128][48] (what a2f_posconv_wgrad writes); dv [768,48,128] and dg [128] accumulate. workspace: 256 doubles. */
+int a2f_weight_norm_bwd(const float* dWp, const float* v, const float* g, float* dv, float* dg, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* data-gradient weight of the positional conv (taps flipped, in/out swapped inside each group); norm[128] as filled by
+ * a2f_pack_posconv_weight. */
+int a2f_pack_posconv_dgrad_weight(const float* g, const float* v, void* out, int out_dtype, int kpad, float* norm,
+                                  void* stream);
+/* dh = dout + grouped_conv_transpose(dpc): input gradient of a2f_posconv (dpc = dout * gelu'(conv pre-activation)). */
+int a2f_posconv_dgrad(const void* dpc, int dtype, const void* Wd, const void* dout, void* dh, int B, int T, int backend,
+                      void* stream);
+/* conv pre-activation only (training forward): pc = grouped_conv(h) + bias, no GELU / residual. */
+int a2f_posconv_pre(const void* h, int h_dtype, const void* Wp, const float* bias, void* pc, int B, int T, int backend,
+                    void* stream);
+/* dWp[g][co][tap][ci] += sum_{b,t} dpc[b,t,g*48+co] * h[b,t+tap-64,g*48+ci]   (fp32 [16][48][128][48]) */
+int a2f_posconv_wgrad(const void* dpc, const void* h, int dtype, float* dWp, int B, int T, int backend, void* stream);
+/* fused Adam step with L2 weight decay on flat fp32 buffers (torch.optim.Adam semantics as configured at
+ * ref:src/model/lightning_model.py:209-213); the gradient is multiplied by grad_scale first (1/world_size). */
+int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; also bench.py's e2e leg): pinned or pageable HOST
