@@ -59,10 +59,16 @@ A2F_D void warp_ln64(float& a, float& b, float g0, float g1, float b0, float b1)
     b = (b - mean) * rstd * g1 + b1;
 }
 
+// Activations the backward pass (decoder_bwd.cu) needs, all [B,T,width] fp32; written only by the TRAIN instantiation.
+struct DecSaves {
+    float *X, *Q, *K, *V, *CTX, *Y1PRE, *Y2PRE, *Y2, *HID, *Y3PRE, *LSE;
+};
+
+template <bool TRAIN>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-attn vectors*/,
                        const float* __restrict__ one_hot, int n_onehot, int period, float* __restrict__ D, int T,
-                       float* __restrict__ kv_global /* [B][2][T][KV_LD] or NULL */) {
+                       float* __restrict__ kv_global /* [B][2][T][KV_LD] or NULL */, DecSaves sv) {
     extern __shared__ __align__(16) float dsm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x;
@@ -150,6 +156,12 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             if (tid < 64) qs[tid] = acc * 0.25f;                  // 1/sqrt(head_dim 16), exact power of two
             else if (tid < 128) Kc[(long long)i * KV_LD + (tid - 64)] = acc;
             else Vc[(long long)i * KV_LD + (tid - 128)] = acc;
+            if (TRAIN) {
+                const long long o = ((long long)b * T + i) * 64 + (tid & 63);
+                if (tid < 64) { sv.Q[o] = acc * 0.25f; sv.X[o] = xs[tid]; }
+                else if (tid < 128) sv.K[o] = acc;
+                else sv.V[o] = acc;
+            }
         }
         __syncthreads();
 
@@ -203,7 +215,12 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             named_bar_sync(1 + h, 128);
             if (u < 16) {
                 const float* pp = pvp + h * 64 + u;
-                os[h * 16 + u] = ((pp[0] + pp[16]) + (pp[32] + pp[48])) / l;
+                const float cv = ((pp[0] + pp[16]) + (pp[32] + pp[48])) / l;
+                os[h * 16 + u] = cv;
+                if (TRAIN) {
+                    sv.CTX[((long long)b * T + i) * 64 + h * 16 + u] = cv;
+                    if (u == 0) sv.LSE[((long long)b * T + i) * 4 + h] = m + logf(l);
+                }
             }
         }
         __syncthreads();
@@ -211,7 +228,9 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
         // ---------- phase 3: self-attn out_proj + residual ----------
         if (tid >= 192 && tid < 256) {
             const int r = tid - 192;
-            ys[r] = xs[r] + (bias_r + dot64_smem(wr, os));
+            const float yv = xs[r] + (bias_r + dot64_smem(wr, os));
+            ys[r] = yv;
+            if (TRAIN) sv.Y1PRE[((long long)b * T + i) * 64 + r] = yv;
         }
         __syncthreads();
 
@@ -222,12 +241,22 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             warp_ln64(a, c, lnA[0], lnA[1], lnA[2], lnA[3]);
             a += pre0;
             c += pre1;
+            if (TRAIN && wl == 0) {
+                sv.Y2PRE[((long long)b * T + i) * 64 + lane] = a;
+                sv.Y2PRE[((long long)b * T + i) * 64 + lane + 32] = c;
+            }
             warp_ln64(a, c, lnB[0], lnB[1], lnB[2], lnB[3]);
             float* xc = x2 + wl * 64;
             xc[lane] = a;
             xc[lane + 32] = c;
+            if (TRAIN && wl == 0) {
+                sv.Y2[((long long)b * T + i) * 64 + lane] = a;
+                sv.Y2[((long long)b * T + i) * 64 + lane + 32] = c;
+            }
             __syncwarp();
-            f1[tid - 256] = relu(bias_r + dot64_smem(wr, xc));
+            const float hv = relu(bias_r + dot64_smem(wr, xc));
+            f1[tid - 256] = hv;
+            if (TRAIN) sv.HID[((long long)b * T + i) * 128 + (tid - 256)] = hv;
         }
         __syncthreads();
 
@@ -236,7 +265,11 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             const int u = tid - 384, row = u >> 1, half = u & 1;
             float part = bias_r + dot64_smem(wr, f1 + half * 64);
             part += __shfl_xor_sync(0xffffffffu, part, 1);
-            if (half == 0) y3[row] = x2[row] + part;
+            if (half == 0) {
+                const float yv = x2[row] + part;
+                y3[row] = yv;
+                if (TRAIN) sv.Y3PRE[((long long)b * T + i) * 64 + row] = yv;
+            }
         }
         __syncthreads();
 
@@ -311,8 +344,18 @@ size_t a2f_decoder_workspace_bytes(int B, int T) {
     return n * sizeof(float);
 }
 
-int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
-                        int period, float* D, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+int a2f_decoder_save_offset(int field) {
+    // floats per (utterance, frame) before `field` in the saves buffer of a2f_decoder_rollout_train
+    static const int width[A2F_DEC_NFIELDS] = {64, 64, 64, 64, 64, 64, 64, 64, 128, 64, 4};
+    if (field < 0 || field > A2F_DEC_NFIELDS) return -1;
+    int o = 0;
+    for (int i = 0; i < field; ++i) o += width[i];
+    return o;
+}
+
+int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
+                              int period, float* D, int B, int T, void* workspace, size_t workspace_bytes, float* saves,
+                              void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(w && memory && one_hot && D && workspace, "a2f_decoder_rollout: NULL argument");
@@ -348,11 +391,32 @@ int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory, const
     dw.n1_w = w->n1_w; dw.n1_b = w->n1_b; dw.n2_w = w->n2_w; dw.n2_b = w->n2_b; dw.n3_w = w->n3_w; dw.n3_b = w->n3_b;
     dw.fb_w = w->fb_w; dw.fb_b = w->fb_b; dw.obj_w = w->obj_w; dw.pe = w->pe;
     const size_t smem = dec_smem_bytes(T, kv == nullptr);
-    A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    decoder_rollout_kernel<<<B, DEC_THREADS, smem, s>>>(dw, ca, one_hot, n_onehot, period, D, T, kv);
+    if (saves == nullptr) {
+        DecSaves none = {};
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        decoder_rollout_kernel<false><<<B, DEC_THREADS, smem, s>>>(dw, ca, one_hot, n_onehot, period, D, T, kv, none);
+    } else {
+        DecSaves sv;
+        const size_t bt = (size_t)B * T;
+        float* f = saves;
+        sv.X = f + bt * a2f_decoder_save_offset(A2F_DEC_X); sv.Q = f + bt * a2f_decoder_save_offset(A2F_DEC_Q);
+        sv.K = f + bt * a2f_decoder_save_offset(A2F_DEC_K); sv.V = f + bt * a2f_decoder_save_offset(A2F_DEC_V);
+        sv.CTX = f + bt * a2f_decoder_save_offset(A2F_DEC_CTX); sv.Y1PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y1PRE);
+        sv.Y2PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y2PRE); sv.Y2 = f + bt * a2f_decoder_save_offset(A2F_DEC_Y2);
+        sv.HID = f + bt * a2f_decoder_save_offset(A2F_DEC_HID); sv.Y3PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y3PRE);
+        sv.LSE = f + bt * a2f_decoder_save_offset(A2F_DEC_LSE);
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        decoder_rollout_kernel<true><<<B, DEC_THREADS, smem, s>>>(dw, ca, one_hot, n_onehot, period, D, T, kv, sv);
+    }
     A2F_CHECK_LAUNCH("decoder_rollout_kernel");
     count_launch();
     return A2F_OK;
+}
+
+int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
+                        int period, float* D, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+    return a2f_decoder_rollout_train(w, memory, one_hot, n_onehot, period, D, B, T, workspace, workspace_bytes, nullptr,
+                                     stream);
 }
 
 int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, const float* vmr_b, int V3, float* Wc,

@@ -96,6 +96,21 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
     }
 }
 
+// out[i0*so0 + i1*so1 + i2*so2] += in[i0*si0 + i1*si1 + i2*si2]   (un-permutes a packed weight gradient into .grad)
+__global__ void __launch_bounds__(256) add_strided3_kernel(const float* __restrict__ in, float* __restrict__ out, int n1,
+                                                           int n2, long long n, long long si0, long long si1,
+                                                           long long si2, long long so0, long long so1, long long so2) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int i2 = (int)(i % n2);
+        const long long r = i / n2;
+        const int i1 = (int)(r % n1);
+        const long long i0 = r / n1;
+        out[i0 * so0 + i1 * so1 + i2 * so2] += in[i0 * si0 + i1 * si1 + i2 * si2];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // out[n] += sum_m x[m*ld + n].  CTA = 64 columns x 256-row slab.
 template <typename TI>
@@ -552,6 +567,18 @@ int a2f_transpose_cast(const float* in, long long ld_r, long long ld_c, int R, i
     if (out_dtype == A2F_BF16) transpose_cast_kernel<bf16><<<grid, 256, 0, s>>>(in, ld_r, ld_c, R, Cc, (bf16*)out, ldo);
     else transpose_cast_kernel<float><<<grid, 256, 0, s>>>(in, ld_r, ld_c, R, Cc, (float*)out, ldo);
     A2F_CHECK_LAUNCH("transpose_cast_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_add_strided3(const float* in, float* out, int n0, int n1, int n2, long long si0, long long si1, long long si2,
+                     long long so0, long long so1, long long so2, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(in && out && n0 > 0 && n1 > 0 && n2 > 0, "a2f_add_strided3: bad arguments");
+    const long long n = (long long)n0 * n1 * n2;
+    add_strided3_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(in, out, n1, n2, n, si0, si1, si2, so0, so1, so2);
+    A2F_CHECK_LAUNCH("add_strided3_kernel");
     count_launch();
     return A2F_OK;
 }

@@ -97,6 +97,14 @@ _SIGNATURES = {
     "a2f_decoder_workspace_bytes": (c_size_t, [c_int, c_int]),
     "a2f_decoder_rollout": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                     c_int, c_void_p, c_size_t, c_void_p]),
+    "a2f_decoder_save_offset": (c_int, [c_int]),
+    "a2f_decoder_rollout_train": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                          c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "a2f_decoder_grad_offset": (c_int, [c_int]),
+    "a2f_decoder_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "a2f_decoder_rollout_bwd": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                        c_void_p, c_size_t, c_void_p]),
+    "a2f_ln64_param_grad": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
     "a2f_pack_feedback": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "a2f_voca_trunk": (c_int, [C.POINTER(VocaWeights), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p]),
@@ -111,6 +119,7 @@ _SIGNATURES = {
     "a2f_act_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "a2f_cast_rows": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_ll, c_int, c_void_p]),
     "a2f_transpose_cast": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_void_p, c_int, c_ll, c_void_p]),
+    "a2f_add_strided3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_void_p]),
     "a2f_colsum": (c_int, [c_void_p, c_int, c_ll, c_ll, c_int, c_void_p, c_void_p]),
     "a2f_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p,
                                   c_void_p, c_void_p, c_ll, c_int, c_void_p]),
@@ -128,6 +137,9 @@ _SIGNATURES = {
     "a2f_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                               c_int, c_float, c_void_p]),
 }
+
+DEC_SAVE_FIELDS = ("X", "Q", "K", "V", "CTX", "Y1PRE", "Y2PRE", "Y2", "HID", "Y3PRE", "LSE")      # a2f.h A2F_DEC_*
+DEC_GRAD_FIELDS = ("GD", "G3", "GHID", "GY2", "G2", "G1", "GQKV", "DEFB")                        # a2f.h A2F_DECG_*
 
 _lib = None
 

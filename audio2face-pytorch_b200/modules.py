@@ -479,8 +479,20 @@ class Faceformer(_A2FModule):
 
     def forward(self, audio, one_hot, template, **kwargs):
         self._need_cuda(audio, one_hot, template)
-        self._no_grad_guard(audio, template, *self.parameters())
         fps = int(kwargs.get("fps", self.fps))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step: forward that keeps a tape + explicit backward kernels (training.py); gradients are
+            # accumulated into every parameter's .grad by loss.backward()
+            from . import training
+            audio = audio.contiguous().float()
+            if audio.dim() != 2:
+                raise L.A2FError("audio must be [B, N] raw 16 kHz samples")
+            B = audio.shape[0]
+            if audio.shape[1] * fps // 16000 < 1:
+                raise L.A2FError("audio too short for one output frame")
+            anchor = next(p for p in self.parameters() if p.requires_grad)
+            return training.FaceformerTrainFn.apply(anchor, self, audio, one_hot.reshape(B, -1).contiguous().float(),
+                                                    template.reshape(B, -1).contiguous().float(), fps)
         audio = audio.contiguous().float()
         if audio.dim() != 2:
             raise L.A2FError("audio must be [B, N] raw 16 kHz samples")
@@ -552,6 +564,14 @@ class FaceFormerLoss:
         self.loss = VocaLoss()
 
     def __call__(self, pred, gt):
+        if pred.dim() == 4 and pred.shape[0] > 1:
+            # batch extension (the reference is batch-1): mean of the per-utterance losses.  With an
+            # even number of frames per utterance the velocity pairs (2k, 2k+1) never straddle two utterances, so this
+            # is VocaLoss over the [B*T, V3] rows.
+            if gt.shape[1] % 2 != 0:
+                gt = gt[:, :-1]
+                pred = pred[:, :-1]
+            return self.loss(pred.reshape(-1, pred.shape[2], pred.shape[3]), gt.reshape(-1, gt.shape[2], gt.shape[3]))
         gt = gt.squeeze(0)
         pred = pred.squeeze(0)
         if gt.shape[0] % 2 != 0:      # drop the last frame of an odd-length clip

@@ -481,3 +481,67 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
     _dev(p, g, m, v)
     L.check(L.load().a2f_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
                                    weight_decay, int(step), grad_scale, _stream()), "a2f_adam_step")
+
+
+class DecoderTape:
+    """Saved activations of one training rollout (a2f_decoder_rollout_train): named [B,T,w] views into one buffer."""
+
+    def __init__(self, B: int, T: int, device):
+        lib = L.load()
+        self.B, self.T = B, T
+        n = len(L.DEC_SAVE_FIELDS)
+        offs = [lib.a2f_decoder_save_offset(i) for i in range(n + 1)]
+        self.buf = torch.empty(B * T * offs[n], dtype=torch.float32, device=device)
+        for i, name in enumerate(L.DEC_SAVE_FIELDS):
+            w = offs[i + 1] - offs[i]
+            setattr(self, name, self.buf[B * T * offs[i]: B * T * offs[i + 1]].view(B * T, w))
+        nbytes = lib.a2f_decoder_workspace_bytes(B, T)
+        self.ws = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.float32, device=device)
+        self.TMP = self.ws[: B * T * 64].view(B * T, 64)            # v_proj(memory)
+        self.CA = self.ws[B * T * 64: 2 * B * T * 64].view(B * T, 64)
+
+
+def decoder_rollout_train(wstruct, memory, one_hot, period, B, T):
+    """-> (D [B,T,64], DecoderTape)"""
+    _dev(memory, one_hot)
+    tape = DecoderTape(B, T, memory.device)
+    D = torch.empty((B, T, 64), dtype=torch.float32, device=memory.device)
+    L.check(L.load().a2f_decoder_rollout_train(C.byref(wstruct), memory.data_ptr(), one_hot.data_ptr(), one_hot.shape[1],
+                                               period, D.data_ptr(), B, T, tape.ws.data_ptr(), tape.ws.numel() * 4,
+                                               tape.buf.data_ptr(), _stream()), "a2f_decoder_rollout_train")
+    return D, tape
+
+
+def decoder_rollout_bwd(wstruct, tape: DecoderTape, gD: torch.Tensor, period: int):
+    """-> dict of per-step gradient vectors ([B*T,w] views) + "DSTYLE" [B,64]  (a2f_decoder_rollout_bwd)."""
+    _dev(gD)
+    lib = L.load()
+    B, T = tape.B, tape.T
+    n = len(L.DEC_GRAD_FIELDS)
+    offs = [lib.a2f_decoder_grad_offset(i) for i in range(n + 1)]
+    buf = torch.empty(B * T * offs[n] + B * 64, dtype=torch.float32, device=gD.device)
+    nbytes = lib.a2f_decoder_bwd_workspace_bytes(B, T)
+    ws = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.float32, device=gD.device)
+    L.check(lib.a2f_decoder_rollout_bwd(C.byref(wstruct), tape.buf.data_ptr(), gD.data_ptr(), period, buf.data_ptr(), B, T,
+                                        ws.data_ptr(), ws.numel() * 4, _stream()), "a2f_decoder_rollout_bwd")
+    out = {"_buf": buf}
+    for i, name in enumerate(L.DEC_GRAD_FIELDS):
+        w = offs[i + 1] - offs[i]
+        out[name] = buf[B * T * offs[i]: B * T * offs[i + 1]].view(B * T, w)
+    out["DSTYLE"] = buf[B * T * offs[n]:].view(B, 64)
+    return out
+
+
+def ln64_param_grad(dy, x, dgamma, dbeta):
+    _dev(dy, x, dgamma, dbeta)
+    L.check(L.load().a2f_ln64_param_grad(dy.data_ptr(), x.data_ptr(), dy.shape[0], dgamma.data_ptr(), dbeta.data_ptr(),
+                                         _stream()), "a2f_ln64_param_grad")
+
+
+def add_strided3(src: torch.Tensor, dst: torch.Tensor, dims, src_strides, dst_strides) -> None:
+    """dst[i . dst_strides] += src[i . src_strides] over the 3-D index space `dims` (fp32)."""
+    _dev(src, dst)
+    if src.dtype != torch.float32 or dst.dtype != torch.float32:
+        raise L.A2FError("add_strided3 takes fp32 tensors")
+    L.check(L.load().a2f_add_strided3(src.data_ptr(), dst.data_ptr(), *[int(d) for d in dims], *[int(v) for v in src_strides],
+                                      *[int(v) for v in dst_strides], _stream()), "a2f_add_strided3")

@@ -1,0 +1,348 @@
+"""FaceFormer training step on the sm_100a kernels: the forward that keeps what the backward needs, and the explicit
+backward pass (ref: torch.autograd over ref:src/model/faceformer.py:139-188 + HF Wav2Vec2Model inside Lightning's
+training_step, ref:src/model/lightning_model.py:150-161).
+
+Semantics: eval-mode arithmetic (dropout, LayerDrop and SpecAugment are inactive -- stated in DESIGN.md; the
+reference's stochastic ops make bit-level train-mode parity meaningless), every parameter of the reference receives a
+gradient except `audio_encoder.masked_spec_embed` (unused without SpecAugment; same in the reference's eval-mode
+autograd).  Parameter gradients are ACCUMULATED into `param.grad` (allocated as zeros when
+missing), exactly where torch.optim / a flat-buffer trainer expects them.
+
+precision "fp32": true-fp32 SIMT GEMMs everywhere (the tight-tolerance parity path);
+precision "bf16": tcgen05 GEMMs for forward, data gradients (W^T operands) and weight gradients (MN-major operands
+read in place), bf16 activations / activation gradients, fp32 LayerNorm / softmax statistics, fp32 decoder, fp32
+parameter gradients.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import lib as L
+from . import ops
+
+GELU = L.ACT_GELU
+V3PAD = 15072          # 15069 rounded up to a multiple of 8 (16-byte bf16 rows for TMA)
+
+
+def _grad(p: torch.nn.Parameter) -> torch.Tensor:
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+def conv_lengths(n_samples: int) -> List[int]:
+    Ls = [(n_samples - 10) // 5 + 1]
+    for k in (3, 3, 3, 3, 2, 2):
+        Ls.append((Ls[-1] - k) // 2 + 1)
+    return Ls
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# derived weights of the backward pass (W^T operands); rebuilt when a parameter changes, never saved
+# ---------------------------------------------------------------------------------------------------------------
+def packed_backward_weights(model) -> Dict:
+    bf = model.precision == "bf16"
+    dt = torch.bfloat16 if bf else torch.float32
+    ae = model.audio_encoder
+
+    def build():
+        T_ = lambda w: ops.transpose_cast(w.detach(), dt)            # noqa: E731   [N,K] -> [K,N]
+        P = {}
+        convs = []
+        cl = ae.feature_extractor.conv_layers
+        for i, k in zip(range(1, 7), (3, 3, 3, 3, 2, 2)):
+            w = cl[i].conv.weight.detach()                           # [co, ci, k]
+            if k == 3:
+                even = torch.empty((512, 1024), dtype=dt, device=w.device)      # [ci, (tap2 co | tap0 co)]
+                ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1536, ld_c=3, offset=2, out=even, ldo=1024, out_offset=0)
+                ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1536, ld_c=3, offset=0, out=even, ldo=1024, out_offset=512)
+                odd = ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1536, ld_c=3, offset=1)
+                convs.append((even, odd))
+            else:
+                both = torch.empty((1024, 512), dtype=dt, device=w.device)      # [(tap, ci), co]
+                ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1024, ld_c=2, offset=0, out=both, ldo=512, out_offset=0)
+                ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1024, ld_c=2, offset=1, out=both, ldo=512,
+                                   out_offset=512 * 512)
+                convs.append((both,))
+        P["convs"] = convs
+        P["proj_t"] = T_(ae.feature_projection.projection.weight)             # [512,768]
+        pz = ae.encoder.pos_conv_embed.conv.parametrizations.weight
+        P["pos_fwd"], P["pos_bwd"] = ops.pack_posconv_weights_train(pz.original0.detach().reshape(-1),
+                                                                    pz.original1.detach(), dt)
+        lay = []
+        for blk in ae.encoder.layers:
+            a = blk.attention
+            qkv_t = torch.empty((768, 2304), dtype=dt, device=a.q_proj.weight.device)
+            for j, lin in enumerate((a.q_proj, a.k_proj, a.v_proj)):
+                ops.transpose_cast(lin.weight.detach(), dt, out=qkv_t, ldo=2304, out_offset=768 * j)
+            lay.append({"qkv_t": qkv_t, "o_t": T_(a.out_proj.weight),
+                        "f1_t": T_(blk.feed_forward.intermediate_dense.weight),     # [768,3072]
+                        "f2_t": T_(blk.feed_forward.output_dense.weight)})          # [3072,768]
+        P["layers"] = lay
+        P["afm_t"] = T_(model.audio_feature_map.weight)                              # [768,64]
+        wr = model.vertice_map_r.weight.detach()                                     # [15069,64]
+        if bf:
+            wr_t = torch.zeros((64, V3PAD), dtype=dt, device=wr.device)
+            ops.transpose_cast(wr, dt, out=wr_t, ldo=V3PAD)
+        else:
+            wr_t = ops.transpose_cast(wr, dt)                                        # [64,15069]
+        P["head_t"] = wr_t
+        d = model.transformer_decoder.layers[0]
+        P["ca_out_t"] = ops.transpose_cast(d.multihead_attn.out_proj.weight.detach(), torch.float32)
+        P["ca_v_t"] = ops.transpose_cast(d.multihead_attn.in_proj_weight.detach()[128:192].contiguous(), torch.float32)
+        return P
+
+    srcs = list(model.parameters())
+    return model._cache.get("ffbwd_" + model.precision, srcs, build)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# forward with tape
+# ---------------------------------------------------------------------------------------------------------------
+def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch.Tensor, fps: int):
+    """Same arithmetic as Faceformer.forward; returns (out [B,T,5023,3] fp32, tape)."""
+    P = model._packed()
+    bf = model.precision == "bf16"
+    dt = torch.bfloat16 if bf else torch.float32
+    be = model._backend()
+    ae = model.audio_encoder
+    B, N = audio.shape
+    T = N * fps // 16000
+    dev = audio.device
+    tp: Dict = {"B": B, "N": N, "T": T, "audio": audio, "one_hot": one_hot}
+
+    stats = ops.audio_stats(audio)
+    gn = ae.feature_extractor.conv_layers[0].layer_norm
+    a0, ws0 = ops.conv0_gn_gelu_train(audio, stats, P["conv0_w"], gn.weight.detach(), gn.bias.detach(), dt)
+    tp["stats"], tp["ws0"] = stats, ws0
+    A, Z = [a0], [None]
+    x, L_in = a0, a0.shape[1]
+    for i, k in enumerate((3, 3, 3, 3, 2, 2)):
+        L_out = (L_in - k) // 2 + 1
+        z = torch.empty((B, L_out, 512), dtype=dt, device=dev)
+        ops.gemm(x, P["convs"][i], z, backend=be, M=B * L_out, K=k * 512, a_row_stride=1024, a_batch_stride=L_in * 512,
+                 rows_per_batch=L_out, ldc=512)
+        y = ops.act_fwd(z, GELU)
+        Z.append(z)
+        A.append(y)
+        x, L_in = y, L_out
+    tp["A"], tp["Z"] = A, Z
+    fp = ae.feature_projection
+    xi = ops.interp_ln(x, fp.layer_norm.weight.detach(), fp.layer_norm.bias.detach(), T, dt)       # [B,T,512]
+    M = B * T
+    h0 = torch.empty((M, 768), dtype=dt, device=dev)
+    ops.gemm(xi.view(M, 512), P["proj_w"], h0, bias=fp.projection.bias.detach(), backend=be)
+    PB = packed_backward_weights(model)
+    pc = ops.posconv_pre(h0, PB["pos_fwd"], ae.encoder.pos_conv_embed.conv.bias.detach(), B, T, be)
+    pre = ops.act_fwd(pc, GELU, resid=h0)
+    h = torch.empty((M, 768), dtype=dt, device=dev)
+    ops.layernorm(pre, ae.encoder.layer_norm.weight.detach(), ae.encoder.layer_norm.bias.detach(), h)
+    tp.update(xi=xi, h0=h0, pc=pc, pre=pre)
+    layers = []
+    for blk, W in zip(ae.encoder.layers, P["layers"]):
+        s = {"h_in": h}
+        qkv = torch.empty((M, 2304), dtype=dt, device=dev)
+        ops.gemm(h, W["qkv_w"], qkv, bias=W["qkv_b"], backend=be)
+        att = torch.empty((M, 768), dtype=dt, device=dev)
+        lse = torch.empty((B, 12, T), dtype=torch.float32, device=dev)
+        ops.mha_lse(qkv, att, lse, B, T)
+        pre1 = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.gemm(att, W["o_w"], pre1, bias=blk.attention.out_proj.bias.detach(), resid=h, backend=be)
+        h1 = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.layernorm(pre1, blk.layer_norm.weight.detach(), blk.layer_norm.bias.detach(), h1)
+        fpre = torch.empty((M, 3072), dtype=dt, device=dev)
+        ops.gemm(h1, W["f1_w"], fpre, bias=blk.feed_forward.intermediate_dense.bias.detach(), backend=be)
+        f = ops.act_fwd(fpre, GELU)
+        pre2 = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.gemm(f, W["f2_w"], pre2, bias=blk.feed_forward.output_dense.bias.detach(), resid=h1, backend=be)
+        h = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.layernorm(pre2, blk.final_layer_norm.weight.detach(), blk.final_layer_norm.bias.detach(), h)
+        s.update(qkv=qkv, att=att, lse=lse, pre1=pre1, h1=h1, fpre=fpre, f=f, pre2=pre2)
+        layers.append(s)
+    tp["layers"], tp["hs"] = layers, h
+    memory = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    ops.gemm(h, P["afm_w"], memory, bias=model.audio_feature_map.bias.detach(), backend=be)
+    D, dtape = ops.decoder_rollout_train(P["dec"][0], memory, one_hot, model.period, B, T)
+    tp["memory"], tp["D"], tp["dtape"] = memory, D, dtape
+    out = model._vertex_head(D.view(M, 64), model.vertice_map_r.weight, model.vertice_map_r.bias, tmpl, T, 64)
+    return out.view(B, T, -1, 3), tp
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------------------------
+def backward(model, tp: Dict, dout: torch.Tensor) -> None:
+    """dout: dL/d(out) [B,T,5023,3] fp32.  Accumulates dL/d(parameter) into every parameter's .grad."""
+    P = model._packed()
+    PB = packed_backward_weights(model)
+    bf = model.precision == "bf16"
+    dt = torch.bfloat16 if bf else torch.float32
+    be = model._backend()
+    S = L.SIMT_F32
+    ae = model.audio_encoder
+    B, N, T = tp["B"], tp["N"], tp["T"]
+    M = B * T
+    dev = dout.device
+    V3 = model.vertice_dim
+    dY32 = dout.reshape(M, V3)
+    if not dY32.is_contiguous():
+        dY32 = dY32.contiguous()
+    D = tp["D"].view(M, 64)
+    dtape = tp["dtape"]
+    wr, br = model.vertice_map_r.weight, model.vertice_map_r.bias
+    wm, bm = model.vertice_map.weight, model.vertice_map.bias
+
+    # ---- vertex head: Y = D Wr^T + br + template ----
+    ops.colsum(dY32, _grad(br))
+    gD = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    if bf:
+        dYb = ops.cast_rows(dY32, torch.bfloat16, V3PAD)
+        Db = ops.cast_rows(D, torch.bfloat16, 64)
+        ops.gemm_wgrad(dYb, Db, _grad(wr), backend=be, N=V3)
+        ops.gemm(dYb, PB["head_t"], gD, backend=be)
+        del dYb
+    else:
+        ops.gemm_wgrad(dY32, D, _grad(wr), backend=S)
+        ops.gemm(dY32, PB["head_t"], gD, backend=S)
+
+    # ---- decoder rollout (BPTT) ----
+    G = ops.decoder_rollout_bwd(P["dec"][0], dtape, gD, model.period)
+    d = model.transformer_decoder.layers[0]
+    sa, ca = d.self_attn, d.multihead_attn
+    ops.gemm_wgrad(G["GQKV"], dtape.X, _grad(sa.in_proj_weight), backend=S)
+    ops.colsum(G["GQKV"], _grad(sa.in_proj_bias))
+    ops.gemm_wgrad(G["G1"], dtape.CTX, _grad(sa.out_proj.weight), backend=S)
+    ops.colsum(G["G1"], _grad(sa.out_proj.bias))
+    ops.gemm_wgrad(G["G3"], dtape.HID, _grad(d.linear2.weight), backend=S)
+    ops.colsum(G["G3"], _grad(d.linear2.bias))
+    ops.gemm_wgrad(G["GHID"], dtape.Y2, _grad(d.linear1.weight), backend=S)
+    ops.colsum(G["GHID"], _grad(d.linear1.bias))
+    ops.ln64_param_grad(G["GD"], dtape.Y3PRE, _grad(d.norm3.weight), _grad(d.norm3.bias))
+    ops.ln64_param_grad(G["GY2"], dtape.Y2PRE, _grad(d.norm2.weight), _grad(d.norm2.bias))
+    ops.ln64_param_grad(G["G2"], dtape.Y1PRE, _grad(d.norm1.weight), _grad(d.norm1.bias))
+    # cross-attention under the diagonal memory mask: ca = out_proj(v_proj(mem)) (q/k rows get exact zeros)
+    ops.gemm_wgrad(G["G2"], dtape.TMP, _grad(ca.out_proj.weight), backend=S)
+    ops.colsum(G["G2"], _grad(ca.out_proj.bias))
+    dTMP = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    ops.gemm(G["G2"], PB["ca_out_t"], dTMP, backend=S)
+    gw, gb = _grad(ca.in_proj_weight), _grad(ca.in_proj_bias)
+    ops.gemm_wgrad(dTMP, tp["memory"], gw[128:192], backend=S)
+    ops.colsum(dTMP, gb[128:192])
+    dMEM = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    ops.gemm(dTMP, PB["ca_v_t"], dMEM, backend=S)
+    # feedback e_{i+1} = Wc d_i + bc + style,  Wc = Wm Wr,  bc = Wm br + bm
+    dWc = torch.zeros((64, 64), dtype=torch.float32, device=dev)
+    dbc = torch.zeros((64,), dtype=torch.float32, device=dev)
+    ops.gemm_wgrad(G["DEFB"], D, dWc, backend=S, M=M, rows_per_batch=T, dy_batch_stride=T * 64, x_batch_stride=T * 64,
+                   x_rows=T, segs=[(-1, 0)])
+    ops.colsum(G["DEFB"], dbc)
+    gwm = _grad(wm)
+    ops.gemm(dWc, wr.detach(), gwm, resid=gwm, backend=S)                             # += dWc Wr^T
+    ops.gemm(dbc.view(64, 1), br.detach().view(V3, 1), gwm, resid=gwm, backend=S)     # += dbc br^T
+    ops.colsum(G["DEFB"], _grad(bm))
+    ops.gemm_wgrad(wm.detach(), dWc, _grad(wr), backend=S)                            # += Wm^T dWc
+    ops.gemm_wgrad(wm.detach(), dbc.view(64, 1), _grad(br).view(V3, 1), backend=S)    # += Wm^T dbc
+    ops.gemm_wgrad(G["DSTYLE"], tp["one_hot"], _grad(model.obj_vector.weight), backend=S)
+
+    # ---- audio_feature_map ----
+    afm = model.audio_feature_map
+    ops.colsum(dMEM, _grad(afm.bias))
+    dMEMc = ops.cast_rows(dMEM, dt, 64) if bf else dMEM
+    ops.gemm_wgrad(dMEMc, tp["hs"], _grad(afm.weight), backend=be)
+    dh = torch.empty((M, 768), dtype=dt, device=dev)
+    ops.gemm(dMEMc, PB["afm_t"], dh, backend=be)
+
+    # ---- encoder layers ----
+    for blk, W, s in zip(reversed(list(ae.encoder.layers)), reversed(PB["layers"]), reversed(tp["layers"])):
+        a, ff = blk.attention, blk.feed_forward
+        dpre2 = ops.layernorm_bwd(dh, s["pre2"], blk.final_layer_norm.weight.detach(), _grad(blk.final_layer_norm.weight),
+                                  _grad(blk.final_layer_norm.bias), _grad(ff.output_dense.bias))
+        ops.gemm_wgrad(dpre2, s["f"], _grad(ff.output_dense.weight), backend=be)
+        dfpre = torch.empty((M, 3072), dtype=dt, device=dev)
+        ops.gemm(dpre2, W["f2_t"], dfpre, act=GELU, resid=s["fpre"], resid_mode=L.RESID_DACT, backend=be)
+        ops.gemm_wgrad(dfpre, s["h1"], _grad(ff.intermediate_dense.weight), backend=be)
+        ops.colsum(dfpre, _grad(ff.intermediate_dense.bias))
+        dh1 = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.gemm(dfpre, W["f1_t"], dh1, resid=dpre2, backend=be)
+        dpre1 = ops.layernorm_bwd(dh1, s["pre1"], blk.layer_norm.weight.detach(), _grad(blk.layer_norm.weight),
+                                  _grad(blk.layer_norm.bias), _grad(a.out_proj.bias))
+        ops.gemm_wgrad(dpre1, s["att"], _grad(a.out_proj.weight), backend=be)
+        datt = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.gemm(dpre1, W["o_t"], datt, backend=be)
+        dqkv = ops.mha_bwd(s["qkv"], s["att"], datt, s["lse"], B, T)
+        for j, lin in enumerate((a.q_proj, a.k_proj, a.v_proj)):
+            ops.gemm_wgrad(dqkv, s["h_in"], _grad(lin.weight), backend=be, N=768, dy_offset=768 * j)
+            ops.colsum(dqkv[:, 768 * j: 768 * (j + 1)], _grad(lin.bias), ld=2304)
+        dh = torch.empty((M, 768), dtype=dt, device=dev)
+        ops.gemm(dqkv, W["qkv_t"], dh, resid=dpre1, backend=be)
+
+    # ---- encoder.layer_norm, positional conv, feature projection ----
+    dpre = ops.layernorm_bwd(dh, tp["pre"], ae.encoder.layer_norm.weight.detach(), _grad(ae.encoder.layer_norm.weight),
+                             _grad(ae.encoder.layer_norm.bias))
+    pcv = ae.encoder.pos_conv_embed.conv
+    dpc = ops.act_bwd(dpre, tp["pc"], GELU)
+    ops.colsum(dpc, _grad(pcv.bias))
+    dwp = ops.posconv_wgrad(dpc, tp["h0"], B, T, be)
+    pz = pcv.parametrizations.weight
+    ops.weight_norm_bwd(dwp, pz.original1.detach(), pz.original0.detach().reshape(-1), _grad(pz.original1),
+                        _grad(pz.original0).view(-1))
+    dh0 = ops.posconv_dgrad(dpc, PB["pos_bwd"], dpre, B, T, be)
+    fp = ae.feature_projection
+    ops.gemm_wgrad(dh0, tp["xi"].view(M, 512), _grad(fp.projection.weight), backend=be)
+    ops.colsum(dh0, _grad(fp.projection.bias))
+    dxi = torch.empty((M, 512), dtype=dt, device=dev)
+    ops.gemm(dh0, PB["proj_t"], dxi, backend=be)
+    A, Z = tp["A"], tp["Z"]
+    da6 = ops.interp_ln_bwd(A[6], dxi.view(B, T, 512), fp.layer_norm.weight.detach(), _grad(fp.layer_norm.weight),
+                            _grad(fp.layer_norm.bias))
+    dz = ops.act_bwd(da6, Z[6], GELU, out_dtype=dt)                       # [B,L6,512]
+
+    # ---- conv stack 6..1 (weight gradient in place on the strided view, data gradient as gather GEMMs) ----
+    cl = ae.feature_extractor.conv_layers
+    for i, k in zip(range(6, 0, -1), (2, 2, 3, 3, 3, 3)):
+        x = A[i - 1]
+        L_in, L_out = x.shape[1], dz.shape[1]
+        dwp = torch.zeros((512, k * 512), dtype=torch.float32, device=dev)
+        ops.gemm_wgrad(dz, x, dwp, backend=be, M=B * L_out, N=512, K=512, dy_row_stride=512, dy_batch_stride=L_out * 512,
+                       x_row_stride=1024, x_batch_stride=L_in * 512, rows_per_batch=L_out, x_rows=(L_in + 1) // 2,
+                       segs=[(0, 0), (0, 512), (1, 0)][:k])
+        ops.add_strided3(dwp, _grad(cl[i].conv.weight), (512, k, 512), (k * 512, 512, 1), (512 * k, 1, k))
+        dx = torch.zeros((B, L_in, 512), dtype=dt, device=dev)
+        last = i == 1                      # conv0's GELU backward lives in a2f_conv0_bwd (its pre-activation is never stored)
+        kw = {} if last else dict(act=GELU, resid=Z[i - 1], resid_mode=L.RESID_DACT, ldr=1024, r_batch_stride=L_in * 512)
+        Wd = PB["convs"][i - 1]
+        if k == 3:
+            U = min(L_out + 1, (L_in + 1) // 2)
+            ops.gemm(dz, Wd[0], dx, backend=be, M=B * U, K=1024, N=512, a_row_stride=512, a_batch_stride=L_out * 512,
+                     rows_per_batch=U, a_rows=L_out, segs=[(-1, 0), (0, 0)], ldc=1024, c_batch_stride=L_in * 512, **kw)
+            kw2 = dict(kw)
+            if not last:
+                kw2["r_offset"] = 512
+            ops.gemm(dz, Wd[1], dx, backend=be, M=B * L_out, K=512, N=512, a_row_stride=512, a_batch_stride=L_out * 512,
+                     rows_per_batch=L_out, ldc=1024, c_batch_stride=L_in * 512, c_offset=512, **kw2)
+        else:
+            ops.gemm(dz, Wd[0], dx, backend=be, M=B * L_out, K=512, N=1024, a_row_stride=512, a_batch_stride=L_out * 512,
+                     rows_per_batch=L_out, ldc=1024, c_batch_stride=L_in * 512, **kw)
+        dz = dx
+    gn = cl[0].layer_norm
+    ops.conv0_bwd(tp["audio"], tp["stats"], P["conv0_w"], gn.weight.detach(), gn.bias.detach(), tp["ws0"], dz,
+                  _grad(cl[0].conv.weight).view(512, 10), _grad(gn.weight), _grad(gn.bias))
+
+
+class FaceformerTrainFn(torch.autograd.Function):
+    """Glue to torch.autograd: `anchor` is one parameter of the model (so the output requires grad); the backward
+    writes ALL parameter gradients straight into their .grad buffers and returns nothing for the anchor."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, audio, one_hot, tmpl, fps):
+        out, tape = forward_train(model, audio, one_hot, tmpl, fps)
+        ctx.model, ctx.tape = model, tape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        backward(ctx.model, ctx.tape, dout.contiguous().float())
+        ctx.tape = None
+        return None, None, None, None, None, None

@@ -228,6 +228,48 @@ size_t a2f_decoder_workspace_bytes(int B, int T);
 int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory /*[B,T,64]*/, const float* one_hot
                         /*[B,n_onehot]*/, int n_onehot, int period, float* D /*[B,T,64]*/, int B, int T,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Training variant: identical result, additionally stores the per-step activations the backward pass needs into
+ * `saves` (fp32; field f is a dense [B,T,width_f] block starting at float offset B*T*a2f_decoder_save_offset(f);
+ * total size B*T*a2f_decoder_save_offset(A2F_DEC_NFIELDS) floats).  The first 2*B*T*64 floats of `workspace` hold
+ * v_proj(memory) and the cross-attention vectors afterwards (read by a2f_decoder_rollout_bwd's caller). */
+#define A2F_DEC_X 0      /* decoder input e_i + pe          64 */
+#define A2F_DEC_Q 1      /* scaled query                    64 */
+#define A2F_DEC_K 2      /*                                 64 */
+#define A2F_DEC_V 3      /*                                 64 */
+#define A2F_DEC_CTX 4    /* attention output (heads concat) 64 */
+#define A2F_DEC_Y1PRE 5  /* x + self_attn (LN1 input)       64 */
+#define A2F_DEC_Y2PRE 6  /* LN1 out + cross-attn (LN2 in)   64 */
+#define A2F_DEC_Y2 7     /* LN2 output                      64 */
+#define A2F_DEC_HID 8    /* relu(linear1)                  128 */
+#define A2F_DEC_Y3PRE 9  /* LN3 input                       64 */
+#define A2F_DEC_LSE 10   /* self-attn log-sum-exp per head   4 */
+#define A2F_DEC_NFIELDS 11
+int a2f_decoder_save_offset(int field);
+int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
+                              int period, float* D, int B, int T, void* workspace, size_t workspace_bytes, float* saves,
+                              void* stream);
+/* Backward through the rollout (BPTT; the reference trains by free rollout, ref:src/model/faceformer.py:154-185, so
+ * gradients flow through the fed-back embeddings).  One persistent CTA per utterance walks the frames in reverse.
+ * gD: [B,T,64] dL/dd_i from the vertex head.  grads (fp32): field f is a dense [B,T,width_f] block at float offset
+ * B*T*a2f_decoder_grad_offset(f); after the [B,T,*] blocks follow DSTYLE [B,64].  The per-step vectors are turned into
+ * weight gradients by batched a2f_gemm_wgrad / a2f_colsum calls (the sequential kernel carries no outer products).
+ * workspace: a2f_decoder_bwd_workspace_bytes(B,T), zero-filled by the call. */
+#define A2F_DECG_GD 0    /* dL/dd_i total (LN3 output grad)        64 */
+#define A2F_DECG_G3 1    /* dL/d(LN3 input)                        64 */
+#define A2F_DECG_GHID 2  /* dL/d(linear1 pre-activation)          128 */
+#define A2F_DECG_GY2 3   /* dL/d(LN2 output)                       64 */
+#define A2F_DECG_G2 4    /* dL/d(LN2 input) = dL/d(cross-attn)     64 */
+#define A2F_DECG_G1 5    /* dL/d(LN1 input) = dL/d(self-attn out)  64 */
+#define A2F_DECG_GQKV 6  /* dL/d(in_proj output) (raw q | k | v)  192 */
+#define A2F_DECG_DEFB 7  /* dL/de_i for i >= 1 (row 0 zero)        64 */
+#define A2F_DECG_NFIELDS 8
+int a2f_decoder_grad_offset(int field);
+size_t a2f_decoder_bwd_workspace_bytes(int B, int T);
+int a2f_decoder_rollout_bwd(const a2f_decoder_weights* w, const float* saves, const float* gD, int period, float* grads,
+                            int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+/* dgamma[64] += sum_rows dy * xhat(x), dbeta[64] += sum_rows dy  for a LayerNorm(64) with saved input x */
+int a2f_ln64_param_grad(const float* dy, const float* x, long long rows, float* dgamma, float* dbeta, void* stream);
+
 /* Wc[64,64], bc[64] from vertice_map {weight [64,V3], bias [64]} and vertice_map_r {weight [V3,64], bias [V3]};
  * accumulation in fp64. */
 int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, const float* vmr_b, int V3, float* Wc,
@@ -293,6 +335,10 @@ int a2f_cast_rows(const void* in, int in_dtype, long long ld_in, void* out, int 
  * one tap of a Conv1d weight [co,ci,taps]: ld_r = ci*taps, ld_c = taps). */
 int a2f_transpose_cast(const float* in, long long ld_r, long long ld_c, int R, int C, void* out, int out_dtype,
                        long long ldo, void* stream);
+/* out[i0*so0+i1*so1+i2*so2] += in[i0*si0+i1*si1+i2*si2] over an n0 x n1 x n2 index space (fp32): adds a weight gradient
+ * computed in the implicit-GEMM layout [co][tap][ci] into the parameter's own [co][ci][tap] .grad buffer. */
+int a2f_add_strided3(const float* in, float* out, int n0, int n1, int n2, long long si0, long long si1, long long si2,
+                     long long so0, long long so1, long long so2, void* stream);
 /* bias gradient: out[n] += sum_m x[m*ld + n] */
 int a2f_colsum(const void* x, int dtype, long long ld, long long rows, int cols, float* out, void* stream);
 /* LayerNorm backward over the last dim (C = 512 or 768): x is the saved LayerNorm INPUT.  dgamma / dbeta accumulate;
