@@ -101,7 +101,8 @@ template <int N> A2F_D void cp_async_wait() { asm volatile("cp.async.wait_group 
 
 // grid: (ceil(T/64), H, B); 128 threads.
 __global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                       float* __restrict__ lse, int T, int H, float scale_log2) {
+                                                       float* __restrict__ lse, float* __restrict__ out32, int T, int H,
+                                                       float scale_log2) {
     __shared__ __align__(16) bf16 sQ[FA_BM * FA_LD];
     __shared__ __align__(16) bf16 sK[2][FA_BN * FA_LD];
     __shared__ __align__(16) bf16 sV[2][FA_BN * FA_LD];
@@ -267,13 +268,24 @@ __global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ 
         if (row0 + 8 < T)
             *reinterpret_cast<uint32_t*>(ob + (long long)(row0 + 8) * (H * FA_D) + c) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
     }
+    if (out32 != nullptr) {      // training: un-rounded output for the backward's delta = rowsum(dO o O) term
+        float* o32 = out32 + (long long)b * T * (H * FA_D) + h * FA_D;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + (lane & 3) * 2;
+            if (row0 < T)
+                *reinterpret_cast<float2*>(o32 + (long long)row0 * (H * FA_D) + c) = make_float2(o[nt][0] * inv0, o[nt][1] * inv0);
+            if (row0 + 8 < T)
+                *reinterpret_cast<float2*>(o32 + (long long)(row0 + 8) * (H * FA_D) + c) = make_float2(o[nt][2] * inv1, o[nt][3] * inv1);
+        }
+    }
 }
 
 
 // ================================================================================================ backward
 // delta[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one warp per (b,t,h))
-template <typename T>
-__global__ void __launch_bounds__(256) mha_delta_kernel(const T* __restrict__ o, const T* __restrict__ dout,
+template <typename TO, typename T>
+__global__ void __launch_bounds__(256) mha_delta_kernel(const TO* __restrict__ o, const T* __restrict__ dout,
                                                         float* __restrict__ delta, int B, int Tn, int H) {
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -281,7 +293,7 @@ __global__ void __launch_bounds__(256) mha_delta_kernel(const T* __restrict__ o,
     const int h = (int)(w % H);
     const long long bt = w / H;
     const int t = (int)(bt % Tn), b = (int)(bt / Tn);
-    const T* op = o + bt * (H * 64) + h * 64 + 2 * lane;
+    const TO* op = o + bt * (H * 64) + h * 64 + 2 * lane;
     const T* dp = dout + bt * (H * 64) + h * 64 + 2 * lane;
     float s = ld_as_float(op) * ld_as_float(dp) + ld_as_float(op + 1) * ld_as_float(dp + 1);
     s = warp_sum(s);
@@ -628,12 +640,23 @@ using namespace a2f;
 
 extern "C" int a2f_mha_fwd(const void* qkv, void* out, int dtype, int B, int T, int H, int D, float scale,
                            void* stream) {
-    return a2f_mha_fwd_lse(qkv, out, nullptr, dtype, B, T, H, D, scale, stream);
+    return a2f_mha_fwd_train(qkv, out, nullptr, nullptr, dtype, B, T, H, D, scale, stream);
+}
+
+extern "C" int a2f_mha_fwd_lse(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H, int D, float scale,
+                               void* stream) {
+    return a2f_mha_fwd_train(qkv, out, lse, nullptr, dtype, B, T, H, D, scale, stream);
 }
 
 extern "C" int a2f_mha_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int dtype,
                            int B, int T, int H, int D, float scale, void* workspace, size_t workspace_bytes,
                            void* stream) {
+    return a2f_mha_bwd_train(qkv, out, nullptr, dout, lse, dqkv, dtype, B, T, H, D, scale, workspace, workspace_bytes, stream);
+}
+
+extern "C" int a2f_mha_bwd_train(const void* qkv, const void* out, const float* out_f32, const void* dout, const float* lse,
+                                 void* dqkv, int dtype, int B, int T, int H, int D, float scale, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(qkv && out && dout && lse && dqkv && workspace && B > 0 && T > 0 && H > 0, "a2f_mha_bwd: bad arguments");
@@ -644,7 +667,7 @@ extern "C" int a2f_mha_bwd(const void* qkv, const void* out, const void* dout, c
     const long long warps = (long long)B * T * H;
     const int dgrid = (int)((warps * 32 + 255) / 256);
     if (dtype == A2F_F32) {
-        mha_delta_kernel<float><<<dgrid, 256, 0, s>>>((const float*)out, (const float*)dout, delta, B, T, H);
+        mha_delta_kernel<float, float><<<dgrid, 256, 0, s>>>((const float*)out, (const float*)dout, delta, B, T, H);
         A2F_CHECK_LAUNCH("mha_delta_kernel");
         A2F_CHECK_CUDA(cudaMemsetAsync(dqkv, 0, (size_t)B * T * 3 * H * 64 * sizeof(float), s));
         mha_bwd_f32_kernel<<<(int)((warps + 3) / 4), 128, 0, s>>>((const float*)qkv, (const float*)dout, lse, delta,
@@ -652,7 +675,10 @@ extern "C" int a2f_mha_bwd(const void* qkv, const void* out, const void* dout, c
         A2F_CHECK_LAUNCH("mha_bwd_f32_kernel");
         count_launch(2);
     } else if (dtype == A2F_BF16) {
-        mha_delta_kernel<bf16><<<dgrid, 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
+        if (out_f32 != nullptr)
+            mha_delta_kernel<float, bf16><<<dgrid, 256, 0, s>>>(out_f32, (const bf16*)dout, delta, B, T, H);
+        else
+            mha_delta_kernel<bf16, bf16><<<dgrid, 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, B, T, H);
         A2F_CHECK_LAUNCH("mha_delta_kernel");
         const size_t smem = (size_t)6 * FAB_TILE * sizeof(bf16) + 256 * sizeof(float);
         static bool attr_done = false;
@@ -673,8 +699,8 @@ extern "C" int a2f_mha_bwd(const void* qkv, const void* out, const void* dout, c
     return A2F_OK;
 }
 
-extern "C" int a2f_mha_fwd_lse(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H, int D, float scale,
-                               void* stream) {
+extern "C" int a2f_mha_fwd_train(const void* qkv, void* out, float* lse, float* out_f32, int dtype, int B, int T, int H,
+                                 int D, float scale, void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, "a2f_mha_fwd: bad arguments");
@@ -688,7 +714,7 @@ extern "C" int a2f_mha_fwd_lse(const void* qkv, void* out, float* lse, int dtype
     } else if (dtype == A2F_BF16) {
         A2F_REQUIRE(reinterpret_cast<uintptr_t>(qkv) % 16 == 0, "a2f_mha_fwd: qkv must be 16-byte aligned");
         const dim3 grid((T + FA_BM - 1) / FA_BM, H, B);
-        mha_bf16_kernel<<<grid, 128, 0, s>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, T, H,
+        mha_bf16_kernel<<<grid, 128, 0, s>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, out_f32, T, H,
                                               scale * 1.4426950408889634f);
         A2F_CHECK_LAUNCH("mha_bf16_kernel");
     } else {

@@ -386,6 +386,16 @@ def interp_ln_bwd(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, dgamma
     return din
 
 
+def padded_rows(B: int, rows: int, C_: int, dtype: torch.dtype, device) -> torch.Tensor:
+    """[B, rows, C] activation followed by one zeroed spare row.  The weight-gradient GEMM of a stride-2 Conv1d reads
+    its input as rows of 2*C elements (a2f_gemm_wgrad, x_row_stride = 2*C): when `rows` is odd the last such row of
+    the LAST utterance extends C elements past the tensor; they are multiplied by zero-filled dY rows, so they must be
+    finite (0 * NaN = NaN inside the MMA)."""
+    flat = torch.empty(B * rows * C_ + C_, dtype=dtype, device=device)
+    flat[B * rows * C_:].zero_()
+    return flat[: B * rows * C_].view(B, rows, C_)
+
+
 def conv0_gn_gelu_train(audio, stats, w, gamma, beta, dtype):
     """conv0_gn_gelu that also returns the workspace (it holds the GroupNorm statistics the backward needs)."""
     _dev(audio, stats, w, gamma, beta)
@@ -394,7 +404,7 @@ def conv0_gn_gelu_train(audio, stats, w, gamma, beta, dtype):
     lib = L.load()
     nbytes = lib.a2f_conv0_workspace_bytes(B, N)
     ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=audio.device)
-    out = torch.empty((B, L0, 512), dtype=dtype, device=audio.device)
+    out = padded_rows(B, L0, 512, dtype, audio.device)
     L.check(lib.a2f_conv0_gn_gelu(audio.data_ptr(), stats.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                   out.data_ptr(), _dt(out), B, N, ws.data_ptr(), ws.numel() * 8, _stream()),
             "a2f_conv0_gn_gelu")
@@ -461,19 +471,23 @@ def weight_norm_bwd(dwp, v, g, dv, dg):
                                          ws.data_ptr(), 256 * 8, _stream()), "a2f_weight_norm_bwd")
 
 
-def mha_lse(qkv, out, lse, B, T, H=12, D=64, scale=0.125):
-    _dev(qkv, out, lse)
-    L.check(L.load().a2f_mha_fwd_lse(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), _dt(qkv), B, T, H, D, scale, _stream()),
-            "a2f_mha_fwd_lse")
+def mha_lse(qkv, out, lse, B, T, H=12, D=64, scale=0.125, out_f32: Optional[torch.Tensor] = None):
+    """training forward: also the row log-sum-exp and (bf16 path, optional) the un-rounded fp32 output."""
+    _dev(qkv, out, lse, out_f32)
+    if out_f32 is not None and (out_f32.dtype != torch.float32 or qkv.dtype != torch.bfloat16):
+        raise L.A2FError("out_f32 is the fp32 side output of the bf16 attention kernel")
+    L.check(L.load().a2f_mha_fwd_train(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), L.ptr(out_f32), _dt(qkv), B, T, H, D,
+                                       scale, _stream()), "a2f_mha_fwd_train")
     return out
 
 
-def mha_bwd(qkv, out, dout, lse, B, T, H=12, D=64, scale=0.125):
-    _dev(qkv, out, dout, lse)
+def mha_bwd(qkv, out, dout, lse, B, T, H=12, D=64, scale=0.125, out_f32: Optional[torch.Tensor] = None):
+    _dev(qkv, out, dout, lse, out_f32)
     dqkv = torch.empty_like(qkv)
     ws = torch.empty(B * H * T, dtype=torch.float32, device=qkv.device)
-    L.check(L.load().a2f_mha_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), _dt(qkv),
-                                 B, T, H, D, scale, ws.data_ptr(), ws.numel() * 4, _stream()), "a2f_mha_bwd")
+    L.check(L.load().a2f_mha_bwd_train(qkv.data_ptr(), out.data_ptr(), L.ptr(out_f32), dout.data_ptr(), lse.data_ptr(),
+                                       dqkv.data_ptr(), _dt(qkv), B, T, H, D, scale, ws.data_ptr(), ws.numel() * 4, _stream()),
+            "a2f_mha_bwd_train")
     return dqkv
 
 

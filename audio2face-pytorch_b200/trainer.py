@@ -1,0 +1,198 @@
+"""Data-parallel FaceFormer training step on the sm_100a kernels (BASELINE.json configs[3]).
+
+Mirrors what Lightning does around the reference model (ref:src/model/lightning_model.py:145-161 training_step,
+:209-213 configure_optimizers = Adam(lr, weight_decay=lr/10); ref:train.py:48-60 Trainer -> implicit DDP, SURVEY.md
+2.1): one process per GPU, every rank holds a replica and a shard of the utterances, and exactly ONE exchange per
+step -- the gradient all-reduce (NCCL over NVLink/NVSwitch).
+
+B200-first layout: parameters, gradients and the two Adam moments live in four FLAT fp32 buffers (the nn.Parameters
+are re-pointed at views of them, state_dict keys unchanged).  The flat order is the order in which the explicit
+backward pass (training.backward) finishes gradients, cut into 14 contiguous stages: as soon as a stage is final its
+slice is handed to ncclAllReduce, which runs on NCCL's stream underneath the remaining backward kernels.  The
+optimizer is one fused kernel over the flat buffers (a2f_adam_step) with the 1/world average folded in.
+
+FlatBuffers is device-agnostic host logic (it is covered by world_size-2 gloo tests on CPU); the compute path is
+CUDA only -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+
+ALIGN = 64          # every parameter starts on a 256-byte boundary of the flat buffers (TMA reduce-add / float4 access)
+
+
+def _world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class FlatBuffers:
+    """Flat parameter / gradient storage cut into all-reduce stages.
+
+    named_params: iterable of (name, nn.Parameter); stage_of(name) -> int in [0, n_stages).  Parameters are laid out
+    stage by stage (original order inside a stage); `p.data` and `p.grad` become views into `params` / `grads`."""
+
+    def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], stage_of: Callable[[str], int],
+                 n_stages: int, skip: Iterable[str] = ()):
+        skip = set(skip)
+        items = [(n, p) for n, p in named_params if n not in skip and p.requires_grad]
+        if not items:
+            raise ValueError("no trainable parameters")
+        dev = items[0][1].device
+        for n, p in items:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError(f"{n}: flat buffers hold fp32 parameters of one device")
+        order = sorted(range(len(items)), key=lambda i: (stage_of(items[i][0]), i))
+        self.entries: List[Tuple[str, torch.nn.Parameter, int, int, int]] = []
+        self.stage_ranges: List[Tuple[int, int]] = []
+        off = 0
+        cur = 0
+        lo = 0
+        for i in order:
+            name, p = items[i]
+            st = stage_of(name)
+            if not 0 <= st < n_stages:
+                raise ValueError(f"{name}: stage {st} out of range")
+            while cur < st:
+                self.stage_ranges.append((lo, off))
+                lo, cur = off, cur + 1
+            self.entries.append((name, p, off, p.numel(), st))
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        while cur < n_stages:
+            self.stage_ranges.append((lo, off))
+            lo, cur = off, cur + 1
+        self.total = off
+        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for name, p, o, n, _ in self.entries:
+                self.params[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.params[o:o + n].view(p.shape)
+                p.grad = self.grads[o:o + n].view(p.shape)
+        self._pending: List = []
+        self._reduced = [False] * n_stages
+
+    # -- gradient exchange ---------------------------------------------------------------------------------------
+    def zero_grads(self) -> None:
+        self.grads.zero_()
+        self._reduced = [False] * len(self.stage_ranges)
+
+    def all_reduce_stage(self, stage: int, group=None) -> None:
+        """Start the (asynchronous) sum all-reduce of one stage's gradient slice.  With NCCL the collective is
+        ordered after everything already enqueued on the current stream and runs on NCCL's own stream, i.e. under
+        the backward kernels launched afterwards."""
+        lo, hi = self.stage_ranges[stage]
+        self._reduced[stage] = True
+        if hi > lo and _world() > 1:
+            self._pending.append(dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+
+    def finish_all_reduce(self, group=None) -> None:
+        """Reduce any stage that was not started during the backward, then make the current stream wait for all."""
+        for st, done in enumerate(self._reduced):
+            if not done:
+                self.all_reduce_stage(st, group)
+        for h in self._pending:
+            h.wait()
+        self._pending = []
+
+    def broadcast_params(self, src: int = 0, group=None) -> None:
+        if _world() > 1:
+            dist.broadcast(self.params, src=src, group=group)
+
+    def bump_versions(self) -> None:
+        """The fused optimizer writes through raw pointers; tell torch (and the modules' derived-weight caches, which
+        key on the version counters) that the parameters changed."""
+        for _, p, _, _, _ in self.entries:
+            torch.autograd.graph.increment_version(p)
+
+    def named_grads(self) -> Dict[str, torch.Tensor]:
+        return {name: self.grads[o:o + n].view(p.shape) for name, p, o, n, _ in self.entries}
+
+
+class FaceformerTrainer:
+    """One process per GPU.  `step(audio, one_hot, template, gt)` = forward + FaceFormerLoss + backward + gradient
+    all-reduce + Adam, in the units it is given; `training_step(batch)` applies the reference's x100 scaling first
+    (ref:src/model/lightning_model.py:145-148).  Eval-mode arithmetic (dropout / LayerDrop / SpecAugment off).
+
+    Batch semantics (extension; the reference is batch-1): loss = mean over the utterances of the per-utterance
+    FaceFormerLoss; across ranks the gradient is the average of the per-rank gradients (DDP semantics)."""
+
+    def __init__(self, model, lr: float = 1e-4, weight_decay: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8,
+                 fps: int = 60, overlap: bool = True, group=None):
+        from . import training
+        if not next(model.parameters()).is_cuda:
+            raise L.A2FError("FaceformerTrainer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.model = model
+        self.lr = float(lr)
+        self.weight_decay = float(lr / 10 if weight_decay is None else weight_decay)    # ref lightning_model.py:99
+        self.betas, self.eps = betas, float(eps)
+        self.fps = int(fps)
+        self.overlap = overlap
+        self.group = group
+        self.flat = FlatBuffers(model.named_parameters(), training.grad_stage_of, training.N_GRAD_STAGES,
+                                skip=training.NO_GRAD_PARAMS)
+        self.exp_avg = torch.zeros_like(self.flat.params)
+        self.exp_avg_sq = torch.zeros_like(self.flat.params)
+        self.steps = 0
+        self.flat.broadcast_params(0, group)
+        self.flat.bump_versions()
+        self._ws = None
+
+    # -- one optimisation step -------------------------------------------------------------------------------------
+    def forward_backward(self, audio, one_hot, template, gt) -> torch.Tensor:
+        """Gradients of the local shard into the flat buffer (all-reduce started, not yet waited).  Returns the
+        device tensor {loss, rec_loss, vel_loss} [3] of the local shard."""
+        from . import ops, training
+        m = self.model
+        audio = audio.contiguous().float()
+        B = audio.shape[0]
+        one_hot = one_hot.reshape(B, -1).contiguous().float()
+        tmpl = template.reshape(B, -1).contiguous().float()
+        self.flat.zero_grads()
+        with torch.no_grad():
+            out, tape = training.forward_train(m, audio, one_hot, tmpl, self.fps)
+            T, V3 = out.shape[1], m.vertice_dim
+            Te = T - (T % 2)                                  # ref loss.py:12-15: an odd last frame is dropped
+            if Te < 2:
+                raise L.A2FError("FaceFormerLoss needs at least two frames")
+            pred = out.view(B, T, V3)
+            g = gt.reshape(B, -1, V3)
+            if Te != T:
+                pred_l, g_l = pred[:, :Te].contiguous(), g[:, :Te].contiguous().float()
+            else:
+                pred_l, g_l = pred, g.contiguous().float()
+            rows = B * Te
+            if self._ws is None:
+                self._ws = ops.loss_workspace(audio.device)
+            out3 = ops.voca_loss_fwd(pred_l.view(rows, V3), g_l.view(rows, V3), rows, V3, 1.0, 10.0, self._ws)
+            dpred = torch.empty((B, Te, V3), dtype=torch.float32, device=audio.device)
+            ops.voca_loss_bwd(pred_l.view(rows, V3), g_l.view(rows, V3), rows, V3, 1.0, 10.0, None, dpred.view(rows, V3))
+            if Te != T:
+                dfull = torch.zeros((B, T, V3), dtype=torch.float32, device=audio.device)
+                dfull[:, :Te] = dpred
+                dpred = dfull
+            hook = (lambda st: self.flat.all_reduce_stage(st, self.group)) if (self.overlap and _world() > 1) else None
+            training.backward(m, tape, dpred, on_ready=hook)
+        return out3
+
+    def optimizer_step(self) -> None:
+        from . import ops
+        self.flat.finish_all_reduce(self.group)
+        self.steps += 1
+        ops.adam_step(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
+                      self.betas[1], self.eps, self.weight_decay, self.steps, grad_scale=1.0 / _world())
+        self.flat.bump_versions()
+
+    def step(self, audio, one_hot, template, gt) -> Dict[str, torch.Tensor]:
+        out3 = self.forward_backward(audio, one_hot, template, gt)
+        self.optimizer_step()
+        return {"loss": out3[0], "rec_loss": out3[1], "vel_loss": out3[2]}
+
+    def training_step(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """batch keys as produced by the reference's dataset (ref:src/dataset/vocaset.py:72-77)."""
+        verts, tmpl = batch["verts"] * 100, batch["template_vert"] * 100        # ref lightning_model.py:145-148
+        return self.step(batch["audio"], batch["one_hot"], tmpl, verts)

@@ -124,7 +124,7 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
         z = torch.empty((B, L_out, 512), dtype=dt, device=dev)
         ops.gemm(x, P["convs"][i], z, backend=be, M=B * L_out, K=k * 512, a_row_stride=1024, a_batch_stride=L_in * 512,
                  rows_per_batch=L_out, ldc=512)
-        y = ops.act_fwd(z, GELU)
+        y = ops.act_fwd(z, GELU, out=ops.padded_rows(B, L_out, 512, dt, dev))     # read by the next layer's wgrad
         Z.append(z)
         A.append(y)
         x, L_in = y, L_out
@@ -147,7 +147,8 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
         ops.gemm(h, W["qkv_w"], qkv, bias=W["qkv_b"], backend=be)
         att = torch.empty((M, 768), dtype=dt, device=dev)
         lse = torch.empty((B, 12, T), dtype=torch.float32, device=dev)
-        ops.mha_lse(qkv, att, lse, B, T)
+        att32 = torch.empty((M, 768), dtype=torch.float32, device=dev) if bf else None
+        ops.mha_lse(qkv, att, lse, B, T, out_f32=att32)
         pre1 = torch.empty((M, 768), dtype=dt, device=dev)
         ops.gemm(att, W["o_w"], pre1, bias=blk.attention.out_proj.bias.detach(), resid=h, backend=be)
         h1 = torch.empty((M, 768), dtype=dt, device=dev)
@@ -159,7 +160,7 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
         ops.gemm(f, W["f2_w"], pre2, bias=blk.feed_forward.output_dense.bias.detach(), resid=h1, backend=be)
         h = torch.empty((M, 768), dtype=dt, device=dev)
         ops.layernorm(pre2, blk.final_layer_norm.weight.detach(), blk.final_layer_norm.bias.detach(), h)
-        s.update(qkv=qkv, att=att, lse=lse, pre1=pre1, h1=h1, fpre=fpre, f=f, pre2=pre2)
+        s.update(qkv=qkv, att=att, att32=att32, lse=lse, pre1=pre1, h1=h1, fpre=fpre, f=f, pre2=pre2)
         layers.append(s)
     tp["layers"], tp["hs"] = layers, h
     memory = torch.empty((M, 64), dtype=torch.float32, device=dev)
@@ -173,8 +174,12 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
 # ---------------------------------------------------------------------------------------------------------------
 # backward
 # ---------------------------------------------------------------------------------------------------------------
-def backward(model, tp: Dict, dout: torch.Tensor) -> None:
-    """dout: dL/d(out) [B,T,5023,3] fp32.  Accumulates dL/d(parameter) into every parameter's .grad."""
+def backward(model, tp: Dict, dout: torch.Tensor, on_ready=None) -> None:
+    """dout: dL/d(out) [B,T,5023,3] fp32.  Accumulates dL/d(parameter) into every parameter's .grad.
+
+    on_ready(stage): called (host side, after the stage's kernels are enqueued) when every gradient of a stage is
+    final -- stage 0 = vertex head + decoder + audio_feature_map, 1..12 = encoder layers 11..0, 13 = the rest (the
+    front end).  The data-parallel trainer starts that stage's gradient all-reduce from it (see grad_stage_of)."""
     P = model._packed()
     PB = packed_backward_weights(model)
     bf = model.precision == "bf16"
@@ -253,8 +258,11 @@ def backward(model, tp: Dict, dout: torch.Tensor) -> None:
     ops.gemm_wgrad(dMEMc, tp["hs"], _grad(afm.weight), backend=be)
     dh = torch.empty((M, 768), dtype=dt, device=dev)
     ops.gemm(dMEMc, PB["afm_t"], dh, backend=be)
+    if on_ready is not None:
+        on_ready(0)
 
     # ---- encoder layers ----
+    stage = 0
     for blk, W, s in zip(reversed(list(ae.encoder.layers)), reversed(PB["layers"]), reversed(tp["layers"])):
         a, ff = blk.attention, blk.feed_forward
         dpre2 = ops.layernorm_bwd(dh, s["pre2"], blk.final_layer_norm.weight.detach(), _grad(blk.final_layer_norm.weight),
@@ -271,12 +279,15 @@ def backward(model, tp: Dict, dout: torch.Tensor) -> None:
         ops.gemm_wgrad(dpre1, s["att"], _grad(a.out_proj.weight), backend=be)
         datt = torch.empty((M, 768), dtype=dt, device=dev)
         ops.gemm(dpre1, W["o_t"], datt, backend=be)
-        dqkv = ops.mha_bwd(s["qkv"], s["att"], datt, s["lse"], B, T)
+        dqkv = ops.mha_bwd(s["qkv"], s["att"], datt, s["lse"], B, T, out_f32=s["att32"])
         for j, lin in enumerate((a.q_proj, a.k_proj, a.v_proj)):
             ops.gemm_wgrad(dqkv, s["h_in"], _grad(lin.weight), backend=be, N=768, dy_offset=768 * j)
             ops.colsum(dqkv[:, 768 * j: 768 * (j + 1)], _grad(lin.bias), ld=2304)
         dh = torch.empty((M, 768), dtype=dt, device=dev)
         ops.gemm(dqkv, W["qkv_t"], dh, resid=dpre1, backend=be)
+        stage += 1
+        if on_ready is not None:
+            on_ready(stage)
 
     # ---- encoder.layer_norm, positional conv, feature projection ----
     dpre = ops.layernorm_bwd(dh, tp["pre"], ae.encoder.layer_norm.weight.detach(), _grad(ae.encoder.layer_norm.weight),
@@ -329,6 +340,21 @@ def backward(model, tp: Dict, dout: torch.Tensor) -> None:
     gn = cl[0].layer_norm
     ops.conv0_bwd(tp["audio"], tp["stats"], P["conv0_w"], gn.weight.detach(), gn.bias.detach(), tp["ws0"], dz,
                   _grad(cl[0].conv.weight).view(512, 10), _grad(gn.weight), _grad(gn.bias))
+    if on_ready is not None:
+        on_ready(N_GRAD_STAGES - 1)
+
+
+N_GRAD_STAGES = 14
+NO_GRAD_PARAMS = ("audio_encoder.masked_spec_embed",)     # unused without SpecAugment: grad is None in the reference too
+
+
+def grad_stage_of(name: str) -> int:
+    """Backward stage (see backward()) in which the gradient of Faceformer parameter `name` becomes final."""
+    if name.startswith("audio_encoder.encoder.layers."):
+        return 12 - int(name.split(".")[3])
+    if name.startswith("audio_encoder."):
+        return N_GRAD_STAGES - 1
+    return 0
 
 
 class FaceformerTrainFn(torch.autograd.Function):

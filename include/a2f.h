@@ -118,7 +118,10 @@ typedef struct a2f_wgrad_args {
     const void* X;
     long long x_row_stride, x_batch_stride;
     int rows_per_batch; /* logical rows (of dY) per batch */
-    int x_rows;         /* rows of X that exist per batch (0 = rows_per_batch) */
+    int x_rows;         /* rows of X that exist per batch (0 = rows_per_batch).  All x_rows rows must be READABLE and
+                           FINITE over the columns the segments touch: rows past rows_per_batch meet zero-filled dY rows
+                           inside the MMA, and 0 * NaN = NaN.  (Stride-2 conv over an odd-length input: the last
+                           2*C-wide row of the last batch runs C elements past the tensor -- keep one zeroed spare row.) */
     int n_seg;          /* 0/1 = one segment; 2..4 = table below; > 4 needs x_row_step (linear table) */
     int x_row_off[4];
     int x_col_off[4];
@@ -184,10 +187,19 @@ int a2f_mha_fwd(const void* qkv, void* out, int dtype, int B, int T, int H, int 
 /* same, also writing the row log-sum-exp of the scaled scores, lse [B,H,T] fp32 (needed by the backward) */
 int a2f_mha_fwd_lse(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H, int D, float scale,
                     void* stream);
+/* training forward: additionally out_f32 [B,T,H*D] (optional, bf16 path only) = the output BEFORE rounding to bf16.
+ * The backward's delta_i = sum_d dO_id O_id term cancels against dO V^T to within the spread of the value rows; when
+ * the tokens are nearly alike (random init, late layers) the bf16 rounding of O would dominate dQ / dK. */
+int a2f_mha_fwd_train(const void* qkv, void* out, float* lse, float* out_f32, int dtype, int B, int T, int H, int D,
+                      float scale, void* stream);
 /* backward: dqkv [B,T,3*H*D] (dq | dk | dv) from dout [B,T,H*D]; the probabilities are recomputed from q, k and lse,
  * never stored.  workspace: B*H*T floats.  bf16: two mma.sync passes (query-major dQ, key-major dK/dV), no atomics. */
 int a2f_mha_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int dtype, int B, int T,
                 int H, int D, float scale, void* workspace, size_t workspace_bytes, void* stream);
+/* same; out_f32 (optional) = a2f_mha_fwd_train's un-rounded output, used for delta instead of `out` */
+int a2f_mha_bwd_train(const void* qkv, const void* out, const float* out_f32, const void* dout, const float* lse,
+                      void* dqkv, int dtype, int B, int T, int H, int D, float scale, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * FaceFormer autoregressive decoder (ref:src/model/faceformer.py:154-185; torch nn.TransformerDecoderLayer

@@ -63,6 +63,22 @@ def main():
     names = sorted(ref_grads.keys())
     fx["names"] = np.array(names)
     fx["norms"] = np.array([float(ref_grads[k].norm()) for k in names], dtype=np.float64)
+    # bf16 noise floor: the LIVE reference under torch.autocast(bf16) -- what Lightning's mixed precision
+    # (ref:train.py:49 precision="16-mixed") does to these gradients -- against its own fp32 gradients.  Stored per
+    # parameter as a relative L2 error; tests scale the bf16 tolerance of the CUDA path by it.
+    model.zero_grad(set_to_none=True)
+    with torch.enable_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        pred16 = model(audio, oh, tp)
+        loss16 = FaceFormerLoss()(pred16.float(), gt)
+        loss16["loss"].backward()
+    noise = []
+    for k in names:
+        g16 = dict(model.named_parameters())[k].grad
+        g16 = g16 if g16 is not None else torch.zeros_like(ref_grads[k])
+        noise.append(float((g16.double() - ref_grads[k].double()).norm()) / max(float(ref_grads[k].norm()), 1e-30))
+    fx["bf16_noise"] = np.array(noise, dtype=np.float64)
+    fx["bf16_loss"] = np.array([float(loss16["loss"])], dtype=np.float64)
+    print("autocast-bf16 reference: loss", float(loss16["loss"]), " median per-tensor rel grad noise", float(np.median(noise)))
     for i, k in enumerate(names):
         fx[f"g{i}"] = subsample(ref_grads[k])
     np.savez_compressed(os.path.join(OUT, "faceformer_train.npz"), **fx)

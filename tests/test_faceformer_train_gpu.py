@@ -85,12 +85,35 @@ def test_train_step_fp32_vs_oracle_and_golden(a2f_lib, dev, ff_sd):
 
 
 def test_train_step_bf16_vs_oracle(a2f_lib, dev, ff_sd):
-    audio, oh, tp, gt = _train_inputs(8000, 41)
+    """bf16 tensor-core training step.  At random init this 12-layer post-LN encoder amplifies bf16 rounding strongly:
+    the LIVE reference under torch.autocast(bf16) (Lightning "16-mixed", ref:train.py:49) is itself 8 % (median) to
+    > 400 % (late-layer q/k projections, whose gradients are tiny differences) away from its own fp32 gradients.
+    The fixture stores that per-parameter noise floor; the CUDA path must stay within 3x of it (or 8e-2), its loss
+    within the north star's 1e-4, and the whole gradient within 0.97 cosine of the fp32 gradient."""
+    z = np.load(os.path.join(G, "faceformer_train.npz"))
+    audio, oh, tp, gt = _train_inputs(int(z["n_samples"]), int(z["seed_in"]))
     loss, grads = _run_gpu(dev, ff_sd, "bf16", audio, oh, tp, gt)
     tot, want = ort.faceformer_loss_and_grads(ff_sd, audio, oh, tp, gt)
-    assert abs(loss["loss"] - tot["loss"]) < 5e-3 * abs(tot["loss"])
-    worst, k = _compare(grads, want, 8e-2, zero_slack=300.0)     # "zero" gradients carry bf16 rounding noise
-    print(f"bf16 train step: loss {loss['loss']:.6f} (oracle {tot['loss']:.6f}); worst per-tensor rel grad err {worst:.2e} ({k})")
+    assert abs(loss["loss"] - tot["loss"]) < 1e-4 * abs(tot["loss"])
+    noise = {str(n): float(v) for n, v in zip(z["names"], z["bf16_noise"])}
+    gmax = max(float(g.norm()) for g in want.values())
+    worst, worst_k, dot, n1, n2 = 0.0, None, 0.0, 0.0, 0.0
+    for k, g in want.items():
+        a, b = grads[k].double().reshape(-1), g.double().reshape(-1)
+        dot, n1, n2 = dot + float(a @ b), n1 + float(a @ a), n2 + float(b @ b)
+        n = float(g.norm())
+        if n < 1e-6 * gmax:                           # mathematically-zero gradients (k_proj.bias)
+            assert float(grads[k].norm()) < 3e-4 * gmax, k
+            continue
+        rel = float((a - b).norm()) / n
+        ratio = rel / max(8e-2, 3.0 * noise[k])
+        if ratio > worst:
+            worst, worst_k = ratio, (k, rel, noise[k])
+    cos = dot / (n1 * n2) ** 0.5
+    print(f"bf16 train step: loss {loss['loss']:.6f} (oracle {tot['loss']:.6f}); gradient cosine {cos:.4f}; "
+          f"worst (err / allowed) {worst:.2f} at {worst_k}")
+    assert worst < 1.0, worst_k
+    assert cos > 0.97, cos
 
 
 def test_train_step_batch_fp32(a2f_lib, dev, ff_sd):
