@@ -106,7 +106,7 @@ def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: i
     from oracle import inputs as oin, ref_models as orm, weights as ow
 
     torch.set_num_threads(threads)
-    with torch.no_grad():
+    with torch.set_grad_enabled(workload == "faceformer_train"):
         if workload == "faceformer":
             sd = _SD_CACHE.get("faceformer") or _SD_CACHE.setdefault("faceformer", ow.make_state_dict("faceformer", 13))
             n = int(16000 * seconds)
@@ -119,6 +119,18 @@ def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: i
                 frames += y.shape[1]
             dt = time.perf_counter() - t0
             return frames / dt, f"{n_utt} utterance(s) x {seconds:g} s @ {fps} fps, fp32, reference O(T^2) decode loop"
+        if workload == "faceformer_train":
+            from oracle import ref_train as ort
+            sd = _SD_CACHE.get("faceformer") or _SD_CACHE.setdefault("faceformer", ow.make_state_dict("faceformer", 13))
+            n = int(16000 * seconds)
+            T = n * fps // 16000
+            audio, oh, tp = oin.audio(1, n, 1), oin.one_hot(1, 12, 1), oin.batch_templates(1, 1, scale=100.0)
+            gt = oin.gt_like((1, T, 5023, 3), tp[:, None], 2, scale=100.0)
+            t0 = time.perf_counter()
+            ort.faceformer_loss_and_grads(sd, audio, oh, tp, gt, fps)
+            dt = time.perf_counter() - t0
+            return T / dt, (f"1 utterance x {seconds:g} s @ {fps} fps: forward + FaceFormerLoss + autograd backward, fp32, "
+                            "reference O(T^2) decode loop (no optimizer step)")
         sd = ow.make_state_dict("voca", 11)
         B = 4096
         x, oh, tp = oin.voca_features(B, 1), oin.one_hot(B, 12, 1), oin.batch_templates(B, 1)
@@ -150,7 +162,7 @@ def run_reference(args):
     T = int(16000 * args.seconds) * args.fps // 16000
     line = {
         "impl": "reference", "metric": "mesh frames/sec (5023-vert FLAME)", "value": value, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (T / value if args.workload == "faceformer" else 4096 / value),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (T / value if args.workload.startswith("faceformer") else 4096 / value),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
@@ -168,6 +180,17 @@ def workload_config(args):
                 "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
                 "template_units": "centimetres (x100, ref lightning_model.py:145-148)",
                 "launch": "eager" if args.no_graph else "one CUDA graph per forward (modules.GraphedForward)"}
+    if args.workload == "faceformer_train":
+        T = int(16000 * args.seconds) * args.fps // 16000
+        return {"workload": f"faceformer_train_step_b{args.batch}_per_gpu_x{args.seconds:g}s_{args.fps}fps (BASELINE.json configs[3])",
+                "batch_per_gpu": args.batch, "audio_seconds": args.seconds, "sample_rate": 16000, "fps": args.fps,
+                "frames_per_utterance": T, "vertices": 5023, "precision": "bf16 tensor-core GEMMs, fp32 master weights/grads/Adam",
+                "step": "forward + FaceFormerLoss (rec + 10 vel) + backward (BPTT through the free rollout) + gradient "
+                        "all-reduce (NCCL, overlapped with the backward) + fused Adam(lr 1e-4, wd 1e-5)",
+                "stochastic_ops": "off (dropout / LayerDrop / SpecAugment; eval-mode arithmetic, DESIGN.md)",
+                "weights": "random-init (oracle.weights seed 13, heads de-zeroed)",
+                "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
+                "template_units": "centimetres (x100, ref lightning_model.py:145-148)", "launch": "eager"}
     return {"workload": f"voca_inference_b{args.batch} (BASELINE.json configs[0] shape)", "batch_per_gpu": args.batch,
             "vertices": 5023, "weights": "random-init (oracle.weights seed 11)",
             "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)"}
@@ -348,31 +371,156 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE.json configs[3]: FaceFormer bf16 training step, data-parallel, batch 8 per GPU."""
+    import torch
+    import torch.distributed as dist
+
+    from a2f_b200 import modules, ops, trainer as tr, lib as L
+    from oracle import inputs as oin, weights as ow       # input / weight generators only (not the timed path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    L.check(lib.a2f_device_check(), "a2f_device_check")
+    B, n = args.batch, int(16000 * args.seconds)
+    T = n * args.fps // 16000
+    model = modules.Faceformer(15069, 12)
+    model.load_state_dict(ow.make_state_dict("faceformer", 13), strict=True)
+    model = model.to(dev).eval().set_precision("bf16")
+    trainer = tr.FaceformerTrainer(model, lr=1e-4, fps=args.fps)
+    tp = oin.batch_templates(B, 100 + rank, scale=100.0)
+    h_in = [oin.audio(B, n, 100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(), tp.pin_memory(),
+            oin.gt_like((B, T, 5023, 3), tp[:, None], 200 + rank, scale=100.0).pin_memory()]
+    d_in = [t.to(dev) for t in h_in]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    units = B * T
+    flops_step = 3.0 * B * ff_flops_per_utt(n, T)        # fwd + dgrad + wgrad (SURVEY.md 8d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n0 = lib.a2f_launch_count()
+    loss0 = trainer.step(*d_in)["loss"]
+    launches_per_step = int(lib.a2f_launch_count() - n0)
+    for _ in range(max(3, args.warmup) - 1):
+        trainer.step(*d_in)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev:
+        flush.zero_()
+        s.record()
+        out = trainer.step(*d_in)
+        e.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_s = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
+    loss_last = float(out["loss"])
+    # end to end: every step uploads its batch (audio, one-hot, template, ground-truth vertices) from pinned host
+    # memory and reads the loss back
+    h_loss = torch.empty(3, dtype=torch.float32).pin_memory()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        di = [t.to(dev, non_blocking=True) for t in h_in]
+        o = trainer.step(*di)
+        h_loss.copy_(torch.stack([o["loss"], o["rec_loss"], o["vel_loss"]]), non_blocking=True)
+    t1.record()
+    barrier()
+    e2e_s = t0.elapsed_time(t1) * 1e-3
+    # per-kernel roofline pass (instrumented, untimed)
+    ops.PROFILE = []
+    for _ in range(2):
+        trainer.step(*d_in)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+
+    if world > 1:
+        t = torch.tensor([dev_s, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    total_units = units * world
+    gem = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind in ("gemm_tc", "wgrad_tc")]
+    g_flops, g_time = sum(f for f, _ in gem), sum(t for _, t in gem)
+    achieved = g_flops / g_time / 1e12
+    roofline = {"bound": "tensor", "kernel": "a2f::gemm_tc_kernel + a2f::wgrad_tc_kernel (tcgen05 forward / data-gradient / "
+                                             "weight-gradient GEMMs, all launches of a step)",
+                "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                "traffic": None, "peak_source": pk["source"] + ", sustained bf16", "launches_per_step": len(gem) // 2,
+                "kernel_share_of_step": (g_time / 2) / (dev_s / args.steps),
+                "whole_step_tflops": flops_step * world * args.steps / dev_s / 1e12,
+                "whole_step_frac": flops_step * args.steps / dev_s / 1e12 / pk["bf16_sustained"]}
+    threads = os.cpu_count() or 1
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample = cpu_reference_frames_per_s("faceformer_train", args.fps, min(args.seconds, 2.0), 1, threads)
+        cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}
+    line = {
+        "metric": "mesh frames/sec (5023-vert FLAME)", "value": total_units * args.steps / dev_s, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dev_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": total_units * args.steps / e2e_s, "unit": "frames/s",
+                "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in h_in), "d2h_bytes_per_step": 12,
+                "note": "pinned host batch (audio, one-hot, template, ground-truth vertices) in, loss scalars out"},
+        "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "loss_first_step": float(loss0), "loss_last_timed_step": loss_last,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca"])
+    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "faceformer_train"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--seconds", type=float, default=5.0)
-    ap.add_argument("--fps", type=int, default=30)
+    ap.add_argument("--fps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph fast path")
     args = ap.parse_args()
+    args.fps_default = args.fps is None
+    if args.fps is None:
+        args.fps = 60 if args.workload == "faceformer_train" else 30
     if args.batch is None:
-        args.batch = 32 if args.workload == "faceformer" else 16384
+        args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384}[args.workload]
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.workload == "faceformer_train" and args.fps_default:
+        args.fps = 60
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_ours(args)
+    if args.workload == "faceformer_train":
+        run_train(args)
+    else:
+        run_ours(args)
 
 
 if __name__ == "__main__":
