@@ -42,7 +42,16 @@ struct TcParams {
     int bias_vec_ok;                // 16-byte vector bias loads are legal
     int fast_gelu;                  // bf16 output: A-S erf approximation instead of erff
     uint32_t lbo_enc, sbo_enc, desc_version, desc_layout;
+    unsigned long long* timeline;   // debug (a2f_debug_set_timeline): 8 globaltimer stamps per CTA, else NULL
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_STAMP(slot) do { if (p.timeline) { p.timeline[blockIdx.x * 8 + (slot)] = gtimer(); \
+                                               p.timeline[(gridDim.x + blockIdx.x) * 8 + (slot)] = (unsigned long long)clock64(); } } while (0)
 
 // debug knobs (a2f_debug_set_umma_field): defaults are the CUTLASS-documented K-major SWIZZLE_128B values
 static uint32_t g_umma_fields[4] = {1u, 64u, 1u, 2u};
@@ -159,6 +168,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GemmParams& g = p.g;
+    if (threadIdx.x == 0) TL_STAMP(0);                                  // kernel entry
 
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B needs 1024-byte alignment
     if (warp == 0 && lane == 0) {
@@ -182,6 +192,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL_STAMP(1);                                  // setup done (barriers, TMEM)
 
     const int tiles_m = p.tiles_m_per_batch * p.num_batches;
     const int total_tiles = tiles_m * p.tiles_n;
@@ -235,6 +246,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (tile == (int)blockIdx.x && kb == 0) TL_STAMP(2);   // first operands landed
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)stage * A_STAGE_BYTES), p);
                     const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * Cfg::B_STAGE_BYTES), p);
@@ -248,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+                if (tile == (int)blockIdx.x) TL_STAMP(3);                  // first tile's MMAs all issued
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -278,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+            if (threadIdx.x == 64 && tile == (int)blockIdx.x) TL_STAMP(4);  // first accumulator complete
 
             const int r_tile = q * 32 + lane;
             const int r_in_batch = lt * TBM + r_tile;
@@ -445,10 +459,13 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (threadIdx.x == 64 && tile == (int)blockIdx.x) TL_STAMP(5);  // first tile's epilogue issued
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (threadIdx.x == 64) TL_STAMP(6);                                 // all tiles' epilogues issued
         if (!SCALAR && leader) tma_store_wait_all();
+        if (threadIdx.x == 64) TL_STAMP(7);                                 // stores drained
     }
 
     tc_fence_before();
@@ -457,6 +474,276 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
+}
+
+// ====================================================================================================================
+// CTA-pair variant (cta_group::2): the two SMs of a TPC run ONE 256 x BN UMMA tile.  Each CTA stages its own 128 A rows
+// and only HALF of the B tile, so a k-block costs (128 + BN/2) x 128 B of L2->SM traffic per SM instead of
+// (128 + BN) x 128 B -- the 1-CTA mainloop above is bound by exactly that traffic (measured: ~750 cycles per k-block
+// against 512 of MMA time, profiles/r1_gemm_timeline.txt).  The leader CTA (even rank) issues every MMA and owns the
+// full / accumulator-empty barriers; smem-empty and accumulator-full arrive in both CTAs through multicast commits.
+// TMA-store epilogue only (16-byte aligned outputs), mode 0.
+template <int BN, typename TC> struct Tc2Cfg {
+    static constexpr int ACC_COLS = 256;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int B_HALF_BYTES = (BN / 2) * TBK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;        // per CTA
+    static constexpr int STAGES = (BN >= 256) ? 6 : 8;
+    static constexpr int SBW = (int)(128 / sizeof(TC));
+    static constexpr int NBLK = BN / SBW;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 2 * EPI_STAGE_BYTES + 256;
+};
+
+template <int BN, typename TC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
+    using Cfg = Tc2Cfg<BN, TC>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int PBM = 2 * TBM;              // rows of a pair tile
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)STAGES * A_STAGE_BYTES;
+    uint8_t* sEpi = smem + (size_t)STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 2 * EPI_STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]  used in the leader only
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]  both CTAs (multicast commit)
+    uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       both CTAs (multicast commit)
+    uint64_t* tempty_bar = tfull_bar + 2;      // [2]       leader only: 8 epilogue warps x 2 CTAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GemmParams& g = p.g;
+    const int rank = (int)cluster_ctarank();
+    const bool is_leader = rank == 0;
+    const int pair = (int)cluster_id_x(), n_pairs = (int)cluster_count_x();
+    if (threadIdx.x == 0) TL_STAMP(0);
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.b);
+        tma_prefetch_desc(&maps.c);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 16);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();                        // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL_STAMP(1);
+
+    const int tiles_m = p.tiles_m_per_batch * p.num_batches;     // pair tiles (256 rows)
+    const int total_tiles = tiles_m * p.tiles_n;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
+                const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
+                const int row0 = lt * PBM + rank * TBM;           // this CTA's 128 A rows
+                const int wrow0 = nb * BN + rank * (BN / 2);      // this CTA's half of the B tile
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    uint8_t* dstA = sA + (size_t)stage * A_STAGE_BYTES;
+                    uint8_t* dstB = sB + (size_t)stage * Cfg::B_HALF_BYTES;
+                    const int seg = kb / p.kb_per_seg, kin = (kb - seg * p.kb_per_seg) * TBK;
+                    if (p.g.n_seg > 0)
+                        tma_load_3d_2sm(dstA, &maps.a[0], &full_bar[stage], p.g.seg_col_off[seg] + kin,
+                                        row0 + p.g.seg_row_off[seg], b);
+                    else
+                        tma_load_3d_2sm(dstA, &maps.a[seg], &full_bar[stage], kin, row0, b);
+                    tma_load_2d_2sm(dstB, &maps.b, &full_bar[stage], kb * TBK, wrow0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (is_leader && lane == 0) {
+            // D=f32, A=B=bf16, K-major, N=BN, M=256 (128 rows per CTA)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(PBM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    if (tile == pair && kb == 0) TL_STAMP(2);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)stage * A_STAGE_BYTES), p);
+                    const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * Cfg::B_HALF_BYTES), p);
+#pragma unroll
+                    for (int k = 0; k < TBK / UMMA_K; ++k)
+                        umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_2sm(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tfull_bar[acc]);
+                if (tile == pair) TL_STAMP(3);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: 8 warps per CTA, each CTA drains its own 128 accumulator rows ===============
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const bool leader = ((ew & 3) == 0) && lane == 0;
+        const int bar_id = 1 + half;
+        uint8_t* stage_buf = sEpi + half * EPI_STAGE_BYTES;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const float* __restrict__ e_bias = g.bias;
+        const void* __restrict__ e_resid = g.resid;
+        const int e_act = g.act;
+        const bool e_dact = g.resid_mode == A2F_RESID_DACT;
+        constexpr int SBW = Cfg::SBW;
+        constexpr int EPC = 16 / (int)sizeof(TC);
+        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+            const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
+            const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
+            const int n_tile0 = nb * BN;
+            const int n_lim = min(BN, g.N - n_tile0);
+            const int n_end = n_tile0 + n_lim;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            if (threadIdx.x == 64 && tile == pair) TL_STAMP(4);
+
+            const int r_tile = q * 32 + lane;
+            const int row_base = lt * PBM + rank * TBM;
+            const int r_in_batch = row_base + r_tile;
+            const bool row_ok = r_in_batch < g.rows_per_batch;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
+            uint8_t* rowp = stage_buf + r_tile * 128;
+#pragma unroll 1
+            for (int blk = half; blk < Cfg::NBLK; blk += 2) {
+                const int col0 = blk * SBW;
+                if (col0 >= n_lim) break;
+                const int ncol0 = n_tile0 + col0;
+                float v[SBW];
+#pragma unroll
+                for (int cc = 0; cc < SBW / 32; ++cc) tmem_ld_32x32(t_row + col0 + cc * 32, v + cc * 32);
+                tmem_ld_wait();
+                const long long r_off = (long long)b * g.r_batch_stride + (long long)r_in_batch * g.ldr + ncol0;
+                if (e_dact) {
+                    if (row_ok) {
+                        float z[SBW];
+#pragma unroll
+                        for (int j = 0; j < SBW; ++j) z[j] = 0.f;
+                        epi_resid<SBW>(z, e_resid, g.resid_bf16, r_off, ncol0, n_end, p.resid_vec_ok);
+#pragma unroll
+                        for (int j = 0; j < SBW; ++j) v[j] *= act_grad(z[j], e_act);
+                    }
+                } else {
+                    epi_bias_act<SBW>(v, e_bias, p.bias_vec_ok, ncol0, n_end, e_act, p.fast_gelu);
+                    if (e_resid != nullptr && row_ok)
+                        epi_resid<SBW>(v, e_resid, g.resid_bf16, r_off, ncol0, n_end, p.resid_vec_ok);
+                }
+                if (leader) tma_store_wait_read();
+                named_bar_sync(bar_id, 128);
+#pragma unroll
+                for (int ch = 0; ch < SBW / EPC; ++ch) {
+                    const int pch = ch ^ (r_tile & 7);
+                    uint4 u;
+                    if (sizeof(TC) == 2) {
+                        u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+                        u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+                        u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+                        u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+                    } else {
+                        u.x = __float_as_uint(v[ch * EPC + 0]);
+                        u.y = __float_as_uint(v[ch * EPC + 1]);
+                        u.z = __float_as_uint(v[ch * EPC + 2]);
+                        u.w = __float_as_uint(v[ch * EPC + 3]);
+                    }
+                    *reinterpret_cast<uint4*>(rowp + pch * 16) = u;
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (leader) {
+                    tma_store_3d(&maps.c, stage_buf, ncol0, row_base, b);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+            if (threadIdx.x == 64 && tile == pair) TL_STAMP(5);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (threadIdx.x == 64) TL_STAMP(6);
+        if (leader) tma_store_wait_all();
+        if (threadIdx.x == 64) TL_STAMP(7);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                        // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BN, typename TC>
+static int launch_tc2(TmapSet& maps, const TcParams& p, cudaStream_t s) {
+    using Cfg = Tc2Cfg<BN, TC>;
+    const GemmParams& g = p.g;
+    uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)g.rows_per_batch, (uint64_t)p.num_batches};
+    uint64_t strides[2] = {(uint64_t)g.ldc * sizeof(TC), (uint64_t)g.c_batch_stride * sizeof(TC)};
+    uint32_t box[3] = {(uint32_t)Cfg::SBW, TBM, 1};
+    int rc = encode_tmap(&maps.c, g.C, (int)sizeof(TC), 3, dims, strides, box, 1);
+    if (rc != A2F_OK) return rc;
+    auto kern = gemm_tc2_kernel<BN, TC>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int total = p.tiles_m_per_batch * p.num_batches * p.tiles_n;
+    const int max_pairs = sm_count() / 2;
+    const int pairs = total < max_pairs ? total : max_pairs;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
+    count_launch();
+    return A2F_OK;
 }
 
 template <int BN, typename TC, bool SCALAR>
@@ -496,6 +783,8 @@ template <int BN> static int dispatch_out(TmapSet& maps, const TcParams& p, int 
 }
 
 static int g_force_bn = 0;   // debug: force a tile width (tests exercise every instantiation)
+static int g_pair_mode = 1;  // debug: 0 = never use the CTA-pair kernel
+static unsigned long long* g_timeline = nullptr;
 
 int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
     if (g_in.M <= 0 || g_in.N <= 0) return A2F_OK;
@@ -509,6 +798,7 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
     p.desc_version = g_umma_fields[2];
     p.desc_layout = g_umma_fields[3];
     p.fast_gelu = c_bf16 ? 1 : 0;
+    p.timeline = g_timeline;
     TmapSet maps;
     memset(&maps, 0, sizeof(maps));
 
@@ -517,6 +807,7 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
     p.tiles_m_per_batch = (g.rows_per_batch + TBM - 1) / TBM;
 
     int BN;
+    bool use_pair = false;
     if (mode == 2) {
         // positional conv: g.N = 48 per group, 16 groups, K = 128 taps x 64 (48 live + 16 zero-weight) channels
         BN = 48;
@@ -541,6 +832,14 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
         else if (g.N > 128) BN = 256;
         else if (g.N > 64) BN = 128;
         else BN = 64;
+        {
+            // CTA-pair kernel: 256-row tiles, TMA-store epilogue only
+            const size_t csz0 = c_bf16 ? 2 : 4;
+            const bool c_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((g.ldc * (long long)csz0) % 16 == 0) &&
+                              ((g.c_batch_stride * (long long)csz0) % 16 == 0);
+            use_pair = g_pair_mode && BN == 256 && g.tmpl == nullptr && c_ok && g.rows_per_batch > TBM && sm_count() >= 2;
+            if (use_pair) p.tiles_m_per_batch = (g.rows_per_batch + 2 * TBM - 1) / (2 * TBM);
+        }
         p.tiles_n = (g.N + BN - 1) / BN;
         p.num_k_blocks = (g.K + TBK - 1) / TBK;
         if (g.n_seg > 0) {
@@ -581,7 +880,7 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
         }
         uint64_t bdims[2] = {(uint64_t)g.K, (uint64_t)g.N};
         uint64_t bstr[1] = {(uint64_t)g.ldw * 2};
-        uint32_t bbox[2] = {TBK, (uint32_t)BN};
+        uint32_t bbox[2] = {TBK, (uint32_t)(use_pair ? BN / 2 : BN)};
         int rc = encode_tmap_bf16(&maps.b, g.W, 2, bdims, bstr, bbox, 1);
         if (rc != A2F_OK) return rc;
     }
@@ -606,6 +905,10 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
         A2F_REQUIRE(mode != 2, "gemm_tc: posconv output must be 16-byte aligned");
     }
 
+    if (use_pair) {
+        if (c_bf16) return launch_tc2<256, bf16>(maps, p, s);
+        return launch_tc2<256, float>(maps, p, s);
+    }
     switch (BN) {
         case 256: return dispatch_out<256>(maps, p, c_bf16, scalar, s);
         case 128: return dispatch_out<128>(maps, p, c_bf16, scalar, s);
@@ -617,9 +920,18 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
 
 }  // namespace a2f
 
+extern "C" int a2f_debug_set_timeline(void* dev_ptr) {
+    a2f::g_timeline = static_cast<unsigned long long*>(dev_ptr);
+    return A2F_OK;
+}
+
 extern "C" int a2f_debug_set_umma_field(int field, unsigned value) {
     if (field >= 0 && field < 4) {
         a2f::g_umma_fields[field] = value;
+        return A2F_OK;
+    }
+    if (field == 5) {   // 0 = never use the CTA-pair (cta_group::2) kernel, 1 = automatic
+        a2f::g_pair_mode = value ? 1 : 0;
         return A2F_OK;
     }
     if (field == 4) {   // force tile width (0 = automatic)

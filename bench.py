@@ -300,6 +300,10 @@ def run_ours(args):
         barrier()
         e2e_s = t_e2e0.elapsed_time(t_e2e1) * 1e-3
         # ------------------------------ per-kernel roofline pass (instrumented, untimed) -------------
+        # The GPU is parked on a spin kernel first so that the host has enqueued every launch and event of the pass
+        # before the device starts: the event pairs then bracket kernels that run back to back (no host-side gaps).
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(0.08 * 1.9e9))
         ops.PROFILE = []
         for _ in range(2):
             call(*d_in)
@@ -441,6 +445,8 @@ def run_train(args):
     barrier()
     e2e_s = t0.elapsed_time(t1) * 1e-3
     # per-kernel roofline pass (instrumented, untimed)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.3 * 1.9e9))      # park the GPU while the host enqueues the instrumented steps (see run_ours)
     ops.PROFILE = []
     for _ in range(2):
         trainer.step(*d_in)

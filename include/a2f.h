@@ -395,6 +395,10 @@ int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
  * ---------------------------------------------------------------------------------------------------------- */
 /* debug/bring-up knobs of the tcgen05 path (tests only). field: 0=LBO enc, 1=SBO enc, 2=version, 3=layout type */
 int a2f_debug_set_umma_field(int field, unsigned value);
+/* debug: when non-NULL, every tcgen05 GEMM CTA writes 8 %globaltimer stamps (entry, setup done, first operands landed,
+ * first tile issued, first accumulator complete, first epilogue issued, all epilogues issued, stores drained) to
+ * dev_ptr[blockIdx.x*8 ..]; NULL switches it off. */
+int a2f_debug_set_timeline(void* dev_ptr);
 
 #ifdef __cplusplus
 }
