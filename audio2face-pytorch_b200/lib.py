@@ -138,6 +138,13 @@ _SIGNATURES = {
     "a2f_posconv_dgrad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "a2f_posconv_pre": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "a2f_posconv_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "a2f_voca_assemble": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "a2f_bn_train_stats": (c_int, [c_void_p, c_int, c_ll, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "a2f_affine_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll,
+                               c_void_p]),
+    "a2f_bn_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_ll, c_ll, c_ll, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "a2f_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                               c_int, c_float, c_void_p]),
 }

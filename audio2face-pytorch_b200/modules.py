@@ -161,11 +161,15 @@ class Voca(_A2FModule):
 
     def forward(self, x, one_hot, template, **kwargs):
         self._need_cuda(x, one_hot, template)
-        self._no_grad_guard(x, template, *self.parameters())
         bs = x.size(0)
         x = x.contiguous().float()
         one_hot = one_hot.contiguous().float()
         tmpl = template.reshape(bs, -1).contiguous().float()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step: taped forward + explicit backward kernels (conv_training.py), true-fp32 path
+            from . import conv_training
+            anchor = next(p for p in self.parameters() if p.requires_grad)
+            return conv_training.ConvModelTrainFn.apply(anchor, self, "voca", x, one_hot, tmpl)
         z = torch.empty((bs, 64), dtype=torch.float32, device=x.device)
         ops.voca_trunk(self._weights_struct(), x, one_hot, z)
         out = self._vertex_head(z, self.decoder[4].weight, self.decoder[4].bias, tmpl, 1, 50)
@@ -232,14 +236,22 @@ class Audio2Mesh(_A2FModule):
 
     def forward(self, x, one_hot, template, **kwargs):
         self._need_cuda(x, one_hot, template)
-        self._no_grad_guard(x, template, *self.parameters())
-        if self.training:
-            raise L.A2FError("Audio2Mesh: train-mode BatchNorm (batch statistics) is not built yet; call .eval()")
         bs = x.size(0)
         dev = x.device
         x = x.contiguous().float()
         one_hot = one_hot.contiguous().float()
         tmpl = template.reshape(bs, -1).contiguous().float()
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if self.training:
+            # model.train(): BatchNorm uses batch statistics and updates its running stats (conv_training.py)
+            from . import conv_training
+            if grad:
+                anchor = next(p for p in self.parameters() if p.requires_grad)
+                return conv_training.ConvModelTrainFn.apply(anchor, self, "audio2mesh", x, one_hot, tmpl)
+            return conv_training.a2m_forward_train(self, x, one_hot, tmpl)[0]
+        if grad:
+            raise L.A2FError("Audio2Mesh: gradients with eval-mode (frozen) BatchNorm are not built; call .train() or "
+                             "run under torch.no_grad()")
         P = self._packed()
         S = L.SIMT_F32
         cur = ops.a2m_assemble(x, one_hot)                                   # [B,64,33] (C=1)

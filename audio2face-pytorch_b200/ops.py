@@ -559,3 +559,60 @@ def add_strided3(src: torch.Tensor, dst: torch.Tensor, dims, src_strides, dst_st
         raise L.A2FError("add_strided3 takes fp32 tensors")
     L.check(L.load().a2f_add_strided3(src.data_ptr(), dst.data_ptr(), *[int(d) for d in dims], *[int(v) for v in src_strides],
                                       *[int(v) for v in dst_strides], _stream()), "a2f_add_strided3")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training step of the convolutional models (csrc/conv_train.cu)
+# ---------------------------------------------------------------------------------------------------------------
+class View:
+    """A strided [batches, rows_per_batch, C] window into a padded channels-last fp32 buffer (a2f.h layout convention)."""
+
+    def __init__(self, buf: torch.Tensor, offset: int, C_: int, rows_per_batch: int, ld: int, batch_stride: int, batches: int):
+        self.buf, self.offset, self.C, self.rows, self.ld, self.bs, self.batches = buf, offset, C_, rows_per_batch, ld, batch_stride, batches
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + 4 * self.offset
+
+    def like(self, buf: torch.Tensor) -> "View":
+        return View(buf, self.offset, self.C, self.rows, self.ld, self.bs, self.batches)
+
+
+def voca_assemble(x: torch.Tensor, one_hot: torch.Tensor) -> torch.Tensor:
+    _dev(x, one_hot)
+    B = x.shape[0]
+    out = torch.empty((B, 17, 37), dtype=torch.float32, device=x.device)
+    L.check(L.load().a2f_voca_assemble(x.data_ptr(), one_hot.data_ptr(), one_hot.shape[1], out.data_ptr(), B, _stream()),
+            "a2f_voca_assemble")
+    return out
+
+
+def bn_train_stats(v: View, gamma, beta, eps, momentum, running_mean, running_var):
+    """-> (mean_rstd [2C], scale_shift [2C]); updates the running statistics in place."""
+    _dev(v.buf, gamma, beta, running_mean, running_var)
+    mr = torch.empty(2 * v.C, dtype=torch.float32, device=v.buf.device)
+    ss = torch.empty(2 * v.C, dtype=torch.float32, device=v.buf.device)
+    ws = torch.empty(2 * v.C, dtype=torch.float64, device=v.buf.device)
+    L.check(L.load().a2f_bn_train_stats(v.ptr, v.C, v.rows, v.ld, v.bs, v.batches, gamma.data_ptr(), beta.data_ptr(), eps,
+                                        momentum, L.ptr(running_mean), L.ptr(running_var), mr.data_ptr(), ss.data_ptr(),
+                                        ws.data_ptr(), ws.numel() * 8, _stream()), "a2f_bn_train_stats")
+    return mr, ss
+
+
+def affine_act(src: View, dst: View, scale_shift: Optional[torch.Tensor], act: int) -> None:
+    _dev(src.buf, dst.buf, scale_shift)
+    sc = scale_shift.data_ptr() if scale_shift is not None else None
+    sh = scale_shift.data_ptr() + 4 * src.C if scale_shift is not None else None
+    L.check(L.load().a2f_affine_act(src.ptr, dst.ptr, sc, sh, act, src.C, src.rows, src.ld, src.bs, dst.ld, dst.bs,
+                                    src.batches, _stream()), "a2f_affine_act")
+
+
+def bn_train_bwd(dy: View, y_relu: Optional[View], z: View, mean_rstd, gamma, dz: View, dgamma, dbeta) -> None:
+    _dev(dy.buf, z.buf, dz.buf, mean_rstd, gamma, dgamma, dbeta)
+    for o in (y_relu, z, dz):
+        if o is not None and (o.ld, o.bs, o.rows, o.batches, o.C) != (dy.ld, dy.bs, dy.rows, dy.batches, dy.C):
+            raise L.A2FError("bn_train_bwd: all views must share one layout")
+    ws = torch.empty(2 * dy.C, dtype=torch.float64, device=dy.buf.device)
+    L.check(L.load().a2f_bn_train_bwd(dy.ptr, y_relu.ptr if y_relu is not None else None, z.ptr, mean_rstd.data_ptr(),
+                                      gamma.data_ptr(), dy.C, dy.rows, dy.ld, dy.bs, dy.batches, dz.ptr, dgamma.data_ptr(),
+                                      dbeta.data_ptr(), ws.data_ptr(), ws.numel() * 8, _stream()), "a2f_bn_train_bwd")

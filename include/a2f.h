@@ -315,6 +315,28 @@ int a2f_a2m_assemble(const float* x, const float* one_hot, int n_onehot, float* 
 int a2f_channel_affine(void* x, int dtype, const float* scale, const float* shift, int C, long long rows_per_batch,
                        long long ld, long long batch_stride, long long batches, void* stream);
 
+/* Training step of the convolutional models (train-mode BatchNorm2d = batch statistics, ref audio2face.py:13-47 under
+ * Lightning's training_step).  Layout of every tensor below: element (b, r, c) at base + b*batch_stride + r*ld + c,
+ * b < batches, r < rows_per_batch, c < C; callers pass `base` advanced past the left zero padding.
+ *  a2f_voca_assemble: x [B,29,16] + tiled one-hot (ref voca.py:40-45) -> out [B,17,37] channels-last, row 0 zero.
+ *  a2f_bn_train_stats: per-channel batch mean / rstd (biased variance, fp64 sums) -> mean_rstd [2C]; the fused
+ *      scale = gamma*rstd, shift = beta - mean*scale -> scale_shift [2C]; running_mean / running_var (optional)
+ *      updated with `momentum` and the unbiased variance, as torch.nn.BatchNorm2d does.  workspace: 2*C doubles.
+ *  a2f_affine_act: out = act(in*scale[c] + shift[c]) (scale/shift NULL = identity); in and out may alias.
+ *  a2f_bn_train_bwd: dz = d/dz of y = gamma*(z-mean)*rstd + beta given dy (masked by y_relu > 0 when a ReLU followed,
+ *      y_relu NULL otherwise); dgamma / dbeta accumulate.  workspace: 2*C doubles. */
+int a2f_voca_assemble(const float* x, const float* one_hot, int n_onehot, float* out, int B, void* stream);
+int a2f_bn_train_stats(const float* x, int C, long long rows_per_batch, long long ld, long long batch_stride,
+                       long long batches, const float* gamma, const float* beta, float eps, float momentum,
+                       float* running_mean, float* running_var, float* mean_rstd, float* scale_shift, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int a2f_affine_act(const float* in, float* out, const float* scale, const float* shift, int act, int C,
+                   long long rows_per_batch, long long ld_in, long long bs_in, long long ld_out, long long bs_out,
+                   long long batches, void* stream);
+int a2f_bn_train_bwd(const float* dy, const float* y_relu, const float* z, const float* mean_rstd, const float* gamma, int C,
+                     long long rows_per_batch, long long ld, long long batch_stride, long long batches, float* dz,
+                     float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Losses (ref:src/loss/loss.py:24-55; FaceFormerLoss :4-17 is the same with bs = T after dropping an odd last
  * frame -- done by the caller through `rows`).  pred, gt: [rows, V3] fp32, rows even.

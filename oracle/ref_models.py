@@ -48,27 +48,34 @@ def voca_forward(sd: SD, x: torch.Tensor, one_hot: torch.Tensor, template: torch
 # ------------------------------------------------------------------------------------------------------------
 # Audio2Mesh  (ref:src/model/audio2face.py:57-66)
 # ------------------------------------------------------------------------------------------------------------
-def _bn(sd: SD, prefix: str, h: torch.Tensor, train: bool) -> torch.Tensor:
-    # nn.BatchNorm2d defaults eps=1e-5; eval: running stats; train: biased batch stats (running update not modelled)
+def _bn(sd: SD, prefix: str, h: torch.Tensor, train: bool, running: Optional[SD] = None) -> torch.Tensor:
+    # nn.BatchNorm2d defaults eps=1e-5, momentum=0.1; eval: running stats; train: biased batch stats.  When `running`
+    # is given (train mode) its <prefix>.running_mean / running_var tensors are updated IN PLACE exactly as
+    # nn.BatchNorm2d does (momentum 0.1, unbiased variance) and <prefix>.num_batches_tracked is incremented.
+    if train and running is not None:
+        out = F.batch_norm(h, running[prefix + ".running_mean"], running[prefix + ".running_var"], sd[prefix + ".weight"],
+                           sd[prefix + ".bias"], training=True, momentum=0.1, eps=1e-5)
+        running[prefix + ".num_batches_tracked"] += 1
+        return out
     return F.batch_norm(h, None if train else sd[prefix + ".running_mean"], None if train else sd[prefix + ".running_var"],
                         sd[prefix + ".weight"], sd[prefix + ".bias"], training=train, momentum=0.0, eps=1e-5)
 
 
 def audio2mesh_forward(sd: SD, x: torch.Tensor, one_hot: torch.Tensor, template: torch.Tensor,
-                       train_bn: bool = False) -> torch.Tensor:
+                       train_bn: bool = False, running: Optional[SD] = None) -> torch.Tensor:
     bs = x.size(0)
     emb = one_hot.repeat(1, 32).view(bs, 1, -1, 32)                     # audio2face.py:59
     h = torch.cat((x.unsqueeze(1), emb), 2)                             # audio2face.py:60-62 -> [bs,1,64,32]
     for i in range(5):                                                  # audio2face.py:13-29 conv -> BN -> ReLU
         h = F.conv2d(h, sd[f"analysis_net.{3 * i}.weight"], sd[f"analysis_net.{3 * i}.bias"], stride=(1, 2), padding=(0, 1))
-        h = F.relu(_bn(sd, f"analysis_net.{3 * i + 1}", h, train_bn))
+        h = F.relu(_bn(sd, f"analysis_net.{3 * i + 1}", h, train_bn, running))
     for conv_idx, bn_idx in ((0, 1), (3, 4), (6, 7)):                   # audio2face.py:31-40 conv -> BN -> ReLU
         h = F.conv2d(h, sd[f"articulation_net.{conv_idx}.weight"], sd[f"articulation_net.{conv_idx}.bias"],
                      stride=(2, 1), padding=(1, 0))
-        h = F.relu(_bn(sd, f"articulation_net.{bn_idx}", h, train_bn))
-    h = _bn(sd, "articulation_net.9", h, train_bn)                      # audio2face.py:41-43 BN -> conv -> ReLU
+        h = F.relu(_bn(sd, f"articulation_net.{bn_idx}", h, train_bn, running))
+    h = _bn(sd, "articulation_net.9", h, train_bn, running)                      # audio2face.py:41-43 BN -> conv -> ReLU
     h = F.relu(F.conv2d(h, sd["articulation_net.10.weight"], sd["articulation_net.10.bias"], stride=(2, 1), padding=(1, 0)))
-    h = _bn(sd, "articulation_net.12", h, train_bn)                     # audio2face.py:44-46
+    h = _bn(sd, "articulation_net.12", h, train_bn, running)                     # audio2face.py:44-46
     h = F.relu(F.conv2d(h, sd["articulation_net.13.weight"], sd["articulation_net.13.bias"], stride=(4, 1)))
     h = h.view(bs, -1)                                                  # audio2face.py:64
     h = torch.cat((h, one_hot), 1)                                      # audio2face.py:65

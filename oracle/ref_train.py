@@ -49,6 +49,27 @@ def faceformer_loss_and_grads(sd: Dict[str, torch.Tensor], audio: torch.Tensor, 
     return tot, grads
 
 
+def conv_loss_and_grads(kind: str, sd: Dict[str, torch.Tensor], x: torch.Tensor, one_hot: torch.Tensor,
+                        template: torch.Tensor, gt: torch.Tensor):
+    """Training step of Voca / Audio2Mesh (ref:src/model/lightning_model.py:150-161 with VocaLoss, ref:src/loss/loss.py:24-55):
+    `pred = model(x, one_hot, template)` in TRAIN mode (Audio2Mesh: batch-statistics BatchNorm), `VocaLoss()(pred, gt)`,
+    autograd.  -> (losses, {param: grad}, running-stat dict after the step (Audio2Mesh) or None)."""
+    params = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
+              for k, v in sd.items()}
+    running = None
+    with torch.enable_grad():
+        if kind == "voca":
+            out = orm.voca_forward(params, x, one_hot, template)
+        else:
+            running = {k: v for k, v in params.items() if "running_" in k or "num_batches" in k}
+            out = orm.audio2mesh_forward(params, x, one_hot, template, train_bn=True, running=running)
+        l = orm.voca_loss(out, gt)
+        l["loss"].backward()
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()
+             if isinstance(p, torch.Tensor) and p.requires_grad}
+    return {k: float(v) for k, v in l.items()}, grads, running
+
+
 def adam_reference(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], lr: float, steps_state=None):
     """One torch.optim.Adam(lr, weight_decay=lr/10) step (ref:src/model/lightning_model.py:99,209-213) on copies."""
     ps = {k: torch.nn.Parameter(v.detach().clone()) for k, v in params.items() if k in grads}

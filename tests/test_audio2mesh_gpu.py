@@ -42,10 +42,11 @@ def test_a2m_fp32_and_bf16_match_oracle(a2f_lib, dev, B):
     assert float((got16 - want).abs().max()) < 5e-5      # fp32 trunk + error-compensated tensor-core head
 
 
-def test_a2m_train_mode_is_refused_loudly(a2f_lib, dev):
+def test_a2m_eval_mode_autograd_is_refused_loudly(a2f_lib, dev):
+    """Gradients with frozen (eval-mode) BatchNorm are not built: the module must say so instead of silently
+    returning a tensor without a graph.  (Train-mode forward/backward: tests/test_conv_train_gpu.py.)"""
     import a2f_b200
     m, _ = _model(dev, 12)
-    m.train()
+    m.eval()
     with pytest.raises(a2f_b200.A2FError):
-        with torch.no_grad():
-            m(oin.a2m_features(2, 3).to(dev), oin.one_hot(2, 12, 3).to(dev), oin.batch_templates(2, 3).to(dev))
+        m(oin.a2m_features(2, 3).to(dev), oin.one_hot(2, 12, 3).to(dev), oin.batch_templates(2, 3).to(dev))

@@ -1,0 +1,105 @@
+"""Training step of the convolutional models (Voca, Audio2Mesh with train-mode BatchNorm) on the GPU against torch
+autograd over the oracle restatement (oracle/ref_train.conv_loss_and_grads; ref:src/model/lightning_model.py:150-161
+with VocaLoss), and the train-mode forward against the live-reference fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs as oin, ref_train as ort, weights as ow
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _inputs(kind, B, seed):
+    x = oin.voca_features(B, seed) if kind == "voca" else oin.a2m_features(B, seed)
+    oh, tp = oin.one_hot(B, 12, seed), oin.batch_templates(B, seed)
+    gt = oin.gt_like((B, 5023, 3), tp, seed + 1)
+    return x, oh, tp, gt
+
+
+def _compare(grads, want, tol):
+    gmax = max(float(g.norm()) for g in want.values())
+    worst, worst_k = 0.0, None
+    for k, g in want.items():
+        n = float(g.norm())
+        if n < 1e-5 * gmax:          # conv biases in front of a train-mode BatchNorm: mathematically zero gradient
+            assert float(grads[k].norm()) < 1e-4 * gmax, (k, float(grads[k].norm()), gmax)
+            continue
+        rel = float((grads[k].double() - g.double()).norm()) / n
+        if rel > worst:
+            worst, worst_k = rel, k
+    assert worst < tol, (worst_k, worst)
+    return worst, worst_k
+
+
+@pytest.mark.parametrize("kind,B,seed", [("voca", 6, 7), ("voca", 64, 7), ("audio2mesh", 4, 7), ("audio2mesh", 64, 17)])
+def test_conv_model_train_step_vs_oracle(a2f_lib, dev, kind, B, seed):
+    """NB ReLU'(0) is discontinuous: a BatchNorm output that rounds to +1e-9 in one implementation and to 0 in the other
+    flips one mask element and moves that channel's gradient by one whole term (seen with B=64, input seed 7: channel 8
+    of articulation_net.7, every other element equal to 1e-6).  The input seeds below avoid such ties."""
+    from a2f_b200 import modules
+    sd = ow.make_state_dict(kind, seed=11)
+    x, oh, tp, gt = _inputs(kind, B, seed)
+    want_loss, want, running = ort.conv_loss_and_grads(kind, sd, x, oh, tp, gt)
+    m = (modules.Voca if kind == "voca" else modules.Audio2Mesh)(15069, 12).to(dev)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    loss = modules.VocaLoss()(m(x.to(dev), oh.to(dev), tp.to(dev)), gt.to(dev))
+    loss["loss"].backward()
+    torch.cuda.synchronize()
+    for k in ("loss", "rec_loss", "vel_loss"):
+        assert abs(float(loss[k]) - want_loss[k]) < 1e-4 * abs(want_loss[k]), k       # north star: losses to 1e-4
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
+    worst, k = _compare(grads, want, 2e-3)
+    print(f"{kind} B={B}: loss {float(loss['loss']):.6f} (oracle {want_loss['loss']:.6f}); worst per-tensor rel grad err {worst:.2e} ({k})")
+    if running is not None:        # BatchNorm running statistics after one training step
+        got = m.state_dict()
+        for name, v in running.items():
+            if v.dtype == torch.int64:
+                assert int(got[name]) == int(v), name
+            else:
+                assert float((got[name].cpu() - v).abs().max()) < 1e-5 * (1 + float(v.abs().max())), name
+
+
+def test_audio2mesh_train_mode_forward_matches_reference_fixture(a2f_lib, dev):
+    from a2f_b200 import modules
+    z = np.load(os.path.join(G, "audio2mesh.npz"))
+    sd = ow.make_state_dict("audio2mesh", seed=int(z["seed_w"]))
+    B, s = int(z["batch"]), int(z["seed_in"])
+    x, oh, tp = oin.a2m_features(B, s), oin.one_hot(B, 12, s), oin.batch_templates(B, s)
+    m = modules.Audio2Mesh(15069, 12).to(dev)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    with torch.no_grad():
+        y = m(x.to(dev), oh.to(dev), tp.to(dev)).cpu()
+    np.testing.assert_allclose(y.reshape(-1)[::int(z["step"])].numpy(), z["out_train"], rtol=0, atol=1e-5)
+    # the running statistics moved; the eval-mode path must pick the new values up (derived-weight cache invalidated)
+    m.eval()
+    with torch.no_grad():
+        y_eval = m(x.to(dev), oh.to(dev), tp.to(dev)).cpu()
+    from oracle import ref_models as orm
+    want = orm.audio2mesh_forward({k: v.cpu() for k, v in m.state_dict().items()}, x, oh, tp)
+    assert float((y_eval - want).abs().max()) < 1e-5
+
+
+def test_torch_optimizer_drives_the_drop_in_module(a2f_lib, dev):
+    """The reference trains through torch.optim.Adam (ref:src/model/lightning_model.py:209-213): a few steps on the
+    drop-in VOCA must reduce the loss."""
+    from a2f_b200 import modules
+    sd = ow.make_state_dict("voca", seed=11)
+    x, oh, tp, gt = _inputs("voca", 32, 9)
+    m = modules.Voca(15069, 12).to(dev)
+    m.load_state_dict(sd, strict=True)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-4)
+    lf = modules.VocaLoss()
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        l = lf(m(x.to(dev), oh.to(dev), tp.to(dev)), gt.to(dev))
+        l["loss"].backward()
+        opt.step()
+        losses.append(float(l["loss"]))
+    assert losses[-1] < losses[0], losses

@@ -98,7 +98,7 @@ def test_layernorm(a2f_lib, dev, C):
     assert _maxerr(out16, want) < 4e-2
 
 
-@pytest.mark.parametrize("B,T", [(1, 60), (2, 150), (1, 333)])
+@pytest.mark.parametrize("B,T", [(1, 60), (2, 150), (1, 333), (2, 1), (3, 17), (1, 256), (1, 257)])
 def test_mha(a2f_lib, dev, B, T):
     from a2f_b200 import ops
     g = torch.Generator().manual_seed(9)
