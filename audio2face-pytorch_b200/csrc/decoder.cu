@@ -17,6 +17,7 @@
 // periodic positional encoding row (i mod period) (ref:faceformer.py:70-88) are generated from indices.
 #include "a2f_common.cuh"
 #include "gemm_params.cuh"
+#include <cooperative_groups.h>
 
 namespace a2f {
 
@@ -303,25 +304,52 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
     }
 }
 
-// Wc = Wm @ Wr ([64,V3] @ [V3,64]) and bc = Wm @ br + bm, fp64 accumulation.  One CTA per output row of Wc.
-__global__ void __launch_bounds__(256) pack_feedback_kernel(const float* __restrict__ vm_w, const float* __restrict__ vm_b,
-                                                            const float* __restrict__ vmr_w,
-                                                            const float* __restrict__ vmr_b, int V3,
-                                                            float* __restrict__ Wc, float* __restrict__ bc) {
-    const int r = blockIdx.x;                  // row of Wc
+// Wc = Wm @ Wr ([64,V3] @ [V3,64]) and bc = Wm @ br + bm, fp64 accumulation.  One 8-CTA cluster per output row of Wc:
+// CTA `cx` of the cluster covers the cx-th eighth of the 15069-long contraction with 4 interleaved partial sums per
+// column, and the leader CTA adds the eight per-CTA sums through distributed shared memory in a fixed order
+// (deterministic; this runs once per weight version in inference but once per STEP in training).
+constexpr int FB_SPLIT = 8;
+
+__global__ void __cluster_dims__(FB_SPLIT, 1, 1) __launch_bounds__(256)
+pack_feedback_kernel(const float* __restrict__ vm_w, const float* __restrict__ vm_b, const float* __restrict__ vmr_w,
+                     const float* __restrict__ vmr_b, int V3, float* __restrict__ Wc, float* __restrict__ bc) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = blockIdx.y;                  // row of Wc
+    const int cx = blockIdx.x;                 // slice of the contraction (== rank in the cluster)
     const int c = threadIdx.x & 63, part = threadIdx.x >> 6;   // 4 partial sums per column
+    const int chunk = (V3 + FB_SPLIT - 1) / FB_SPLIT;
+    const int v0 = cx * chunk, v1 = min(V3, v0 + chunk);
     __shared__ double sh[4][65];
-    double acc = 0.0, accb = 0.0;
-    for (int v = part; v < V3; v += 4) {
-        const double a = (double)vm_w[(long long)r * V3 + v];
-        acc += a * (double)vmr_w[(long long)v * 64 + c];
-        if (c == 0) accb += a * (double)vmr_b[v];
+    __shared__ double tot[65];
+    const float* a_row = vm_w + (long long)r * V3;
+    double acc0 = 0.0, acc1 = 0.0, accb = 0.0;
+    int v = v0 + part;
+    for (; v + 4 < v1; v += 8) {               // two independent chains, loads issued together
+        const float a0 = __ldg(a_row + v), a1 = __ldg(a_row + v + 4);
+        const float w0 = __ldg(vmr_w + (long long)v * 64 + c), w1 = __ldg(vmr_w + (long long)(v + 4) * 64 + c);
+        acc0 = fma((double)a0, (double)w0, acc0);
+        acc1 = fma((double)a1, (double)w1, acc1);
+        if (c == 0) accb += (double)a0 * (double)__ldg(vmr_b + v) + (double)a1 * (double)__ldg(vmr_b + v + 4);
     }
-    sh[part][c] = acc;
+    for (; v < v1; v += 4) {
+        const float a0 = __ldg(a_row + v);
+        acc0 = fma((double)a0, (double)__ldg(vmr_w + (long long)v * 64 + c), acc0);
+        if (c == 0) accb += (double)a0 * (double)__ldg(vmr_b + v);
+    }
+    sh[part][c] = acc0 + acc1;
     if (c == 0) sh[part][64] = accb;
     __syncthreads();
-    if (threadIdx.x < 64) Wc[r * 64 + c] = (float)((sh[0][c] + sh[1][c]) + (sh[2][c] + sh[3][c]));
-    if (threadIdx.x == 64) bc[r] = (float)(((sh[0][64] + sh[1][64]) + (sh[2][64] + sh[3][64])) + (double)vm_b[r]);
+    if (threadIdx.x < 65) tot[threadIdx.x] = (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+    cluster.sync();                            // every CTA's `tot` is complete and visible cluster-wide
+    if (cx == 0 && threadIdx.x < 65) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < FB_SPLIT; ++k) s += *cluster.map_shared_rank(&tot[threadIdx.x], k);
+        if (threadIdx.x < 64) Wc[r * 64 + threadIdx.x] = (float)s;
+        else bc[r] = (float)(s + (double)vm_b[r]);
+    }
+    cluster.sync();                            // peers keep their shared memory alive until the leader has read it
 }
 
 static size_t dec_smem_bytes(int T, bool kv_in_smem) {
@@ -424,7 +452,7 @@ int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, 
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(vm_w && vm_b && vmr_w && vmr_b && Wc && bc && V3 > 0, "a2f_pack_feedback: bad arguments");
-    pack_feedback_kernel<<<64, 256, 0, as_stream(stream)>>>(vm_w, vm_b, vmr_w, vmr_b, V3, Wc, bc);
+    pack_feedback_kernel<<<dim3(FB_SPLIT, 64), 256, 0, as_stream(stream)>>>(vm_w, vm_b, vmr_w, vmr_b, V3, Wc, bc);
     A2F_CHECK_LAUNCH("pack_feedback_kernel");
     count_launch();
     return A2F_OK;

@@ -162,10 +162,10 @@ int posconv_simt(const GemmParams& p_in, int a_bf16, int c_bf16, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[n, s*K + k] += sum_m dY[m, n] * X[(b, r + roff[s]), coff[s] + k].  64x64 output tiles, the M reduction split over
 // blockIdx.z, fp32 atomics into dW (the fp32 parity path; ordering noise ~1e-7 relative).
-constexpr int WG_ROWS = 512;   // reduction rows per CTA
-
+// Reduction rows per CTA are chosen by the launcher so that small outputs (the decoder's 64x64 matrices over a few
+// thousand rows) still fill the machine: a fixed 512-row slice left them on 5 CTAs (95 us for 20 MFLOP).
 template <typename TI>
-__global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradParams p) {
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradParams p, int WG_ROWS) {
     __shared__ float As[SBK][SBM + 4];   // [m][n]
     __shared__ float Bs[SBK][SBN + 4];   // [m][kcol]
     const TI* __restrict__ dY = static_cast<const TI*>(p.dY);
@@ -235,9 +235,15 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradParams p) {
 
 int wgrad_simt(const WgradParams& p, int bf16_in, cudaStream_t s) {
     const int ktot = p.K * p.n_seg;
-    dim3 grid((ktot + SBN - 1) / SBN, (p.N + SBM - 1) / SBM, (p.M + WG_ROWS - 1) / WG_ROWS);
-    if (bf16_in) wgrad_simt_kernel<bf16><<<grid, 256, 0, s>>>(p);
-    else wgrad_simt_kernel<float><<<grid, 256, 0, s>>>(p);
+    const int gx = (ktot + SBN - 1) / SBN, gy = (p.N + SBM - 1) / SBM;
+    const int want_z = (2 * sm_count() + gx * gy - 1) / (gx * gy);            // ~2 CTAs per SM overall
+    long long rows = (p.M + want_z - 1) / want_z;
+    rows = (rows + SBK - 1) / SBK * SBK;
+    if (rows < 2 * SBK) rows = 2 * SBK;
+    if (rows > 512) rows = 512;
+    dim3 grid(gx, gy, (unsigned)((p.M + rows - 1) / rows));
+    if (bf16_in) wgrad_simt_kernel<bf16><<<grid, 256, 0, s>>>(p, (int)rows);
+    else wgrad_simt_kernel<float><<<grid, 256, 0, s>>>(p, (int)rows);
     A2F_CHECK_LAUNCH("wgrad_simt_kernel");
     count_launch();
     return A2F_OK;

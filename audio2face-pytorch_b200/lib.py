@@ -51,6 +51,14 @@ class WgradArgs(C.Structure):
     ]
 
 
+class CopyJob(C.Structure):
+    """a2f_copy_job of include/a2f.h (one strided 2-D copy of an a2f_strided_copy_jobs launch)."""
+    _fields_ = [
+        ("src", c_void_p), ("dst", c_void_p), ("ld_r", c_ll), ("ld_c", c_ll), ("ldo_r", c_ll), ("ldo_c", c_ll),
+        ("R", c_int), ("C", c_int), ("dst_dtype", c_int), ("tile0", c_int),
+    ]
+
+
 class DecoderWeights(C.Structure):
     _names = [
         "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b", "ca_in_w", "ca_in_b", "ca_out_w", "ca_out_b",
@@ -122,6 +130,7 @@ _SIGNATURES = {
     "a2f_act_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "a2f_act_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "a2f_cast_rows": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_ll, c_int, c_void_p]),
+    "a2f_strided_copy_jobs": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "a2f_transpose_cast": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_void_p, c_int, c_ll, c_void_p]),
     "a2f_add_strided3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_void_p]),
     "a2f_colsum": (c_int, [c_void_p, c_int, c_ll, c_ll, c_int, c_void_p, c_void_p]),

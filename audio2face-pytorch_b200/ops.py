@@ -188,10 +188,11 @@ def pack_conv1d_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def pack_posconv_weight(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+def pack_posconv_weight(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _dev(g, v)
     kpad = 64 if dtype == torch.bfloat16 else 48
-    out = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+    if out is None:
+        out = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
     norm = torch.empty(128, dtype=torch.float32, device=v.device)
     L.check(L.load().a2f_pack_posconv_weight(g.contiguous().data_ptr(), v.contiguous().data_ptr(), out.data_ptr(), _dt(out),
                                              kpad, norm.data_ptr(), _stream()), "a2f_pack_posconv_weight")
@@ -279,10 +280,13 @@ def channel_affine(buf: torch.Tensor, offset: int, scale: torch.Tensor, shift: t
             "a2f_channel_affine")
 
 
-def pack_feedback(vm_w, vm_b, vmr_w, vmr_b):
+def pack_feedback(vm_w, vm_b, vmr_w, vmr_b, out=None):
     _dev(vm_w, vm_b, vmr_w, vmr_b)
-    wc = torch.empty((64, 64), dtype=torch.float32, device=vm_w.device)
-    bc = torch.empty((64,), dtype=torch.float32, device=vm_w.device)
+    if out is None:
+        wc = torch.empty((64, 64), dtype=torch.float32, device=vm_w.device)
+        bc = torch.empty((64,), dtype=torch.float32, device=vm_w.device)
+    else:
+        wc, bc = out
     L.check(L.load().a2f_pack_feedback(vm_w.data_ptr(), vm_b.data_ptr(), vmr_w.data_ptr(), vmr_b.data_ptr(),
                                        vmr_w.shape[0], wc.data_ptr(), bc.data_ptr(), _stream()), "a2f_pack_feedback")
     return wc, bc
@@ -350,6 +354,70 @@ def transpose_cast(w: torch.Tensor, out_dtype: torch.dtype, R: Optional[int] = N
                                         out.data_ptr() + out_offset * out.element_size(), _dt(out), ldo, _stream()),
             "a2f_transpose_cast")
     return out
+
+
+class PackPlan:
+    """A recorded list of strided fp32 -> fp32/bf16 copies executed by ONE kernel launch (a2f_strided_copy_jobs).
+
+    The drop-in modules derive every packed GEMM operand (bf16 casts, W^T data-gradient operands, implicit-GEMM conv
+    layouts, the fused QKV weight) from the fp32 master parameters.  Source and destination pointers are stable across
+    optimizer steps (parameters are updated in place, destinations are owned by the plan's user), so the job table is
+    uploaded once and `run()` re-derives all operands after every step."""
+
+    def __init__(self, device):
+        self.device = device
+        self.jobs = []
+        self.keep = []          # tensors the jobs point into (kept alive with the plan)
+        self.table = None
+        self.total_tiles = 0
+
+    def add(self, src: torch.Tensor, dst: torch.Tensor, R: int, Cc: int, ld_r: int, ld_c: int, ldo_r: int, ldo_c: int,
+            src_off: int = 0, dst_off: int = 0) -> None:
+        """dst.flat[dst_off + r*ldo_r + c*ldo_c] = src.flat[src_off + r*ld_r + c*ld_c], r < R, c < Cc."""
+        _dev(src, dst)
+        if src.dtype != torch.float32 or dst.dtype not in (torch.float32, torch.bfloat16):
+            raise L.A2FError("PackPlan copies fp32 sources into fp32 / bf16 destinations")
+        if self.table is not None:
+            raise L.A2FError("PackPlan is already finalised")
+        j = L.CopyJob()
+        j.src = src.data_ptr() + 4 * src_off
+        j.dst = dst.data_ptr() + dst.element_size() * dst_off
+        j.ld_r, j.ld_c, j.ldo_r, j.ldo_c = int(ld_r), int(ld_c), int(ldo_r), int(ldo_c)
+        j.R, j.C, j.dst_dtype = int(R), int(Cc), _dt(dst)
+        j.tile0 = self.total_tiles
+        self.total_tiles += ((int(R) + 31) // 32) * ((int(Cc) + 31) // 32)
+        self.jobs.append(j)
+        self.keep += [src, dst]
+
+    def cast(self, src: torch.Tensor, dst: torch.Tensor, dst_off: int = 0) -> None:
+        """dst.flat[dst_off:dst_off + src.numel()] = src (row-major, contiguous)."""
+        cols = src.shape[-1]
+        rows = src.numel() // cols
+        self.add(src, dst, rows, cols, cols, 1, cols, 1, dst_off=dst_off)
+
+    def transpose(self, src: torch.Tensor, dst: torch.Tensor, ldo: Optional[int] = None, dst_off: int = 0, R=None, Cc=None,
+                  ld_r=None, ld_c: int = 1, src_off: int = 0) -> None:
+        """dst[c, r] = src.flat[src_off + r*ld_r + c*ld_c]   (same contract as transpose_cast)."""
+        R = int(R if R is not None else src.shape[0])
+        Cc = int(Cc if Cc is not None else src.shape[1])
+        ld_r = int(ld_r if ld_r is not None else src.stride(0))
+        ldo = int(ldo if ldo is not None else dst.stride(0))
+        self.add(src, dst, R, Cc, ld_r, ld_c, 1, ldo, src_off=src_off, dst_off=dst_off)
+
+    def finalize(self) -> "PackPlan":
+        if not self.jobs:
+            raise L.A2FError("empty PackPlan")
+        arr = (L.CopyJob * len(self.jobs))(*self.jobs)
+        raw = bytes(arr)
+        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        self.table = host.to(self.device)
+        return self
+
+    def run(self) -> None:
+        if self.table is None:
+            self.finalize()
+        L.check(L.load().a2f_strided_copy_jobs(self.table.data_ptr(), len(self.jobs), self.total_tiles, _stream()),
+                "a2f_strided_copy_jobs")
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor, rows: Optional[int] = None, cols: Optional[int] = None,
@@ -423,13 +491,16 @@ def conv0_bwd(audio, stats, w, gamma, beta, ws, da, dw, dgamma, dbeta):
                               dbeta.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, _stream()), "a2f_conv0_bwd")
 
 
-def pack_posconv_weights_train(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype):
+def pack_posconv_weights_train(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype, out=None):
     """-> (forward packed weight, data-gradient packed weight)"""
     _dev(g, v)
     kpad = 64 if dtype == torch.bfloat16 else 48
     lib = L.load()
-    fwd = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
-    bwd = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+    if out is None:
+        fwd = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+        bwd = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+    else:
+        fwd, bwd = out
     norm = torch.empty(128, dtype=torch.float32, device=v.device)
     gc, vc = g.contiguous(), v.contiguous()
     L.check(lib.a2f_pack_posconv_weight(gc.data_ptr(), vc.data_ptr(), fwd.data_ptr(), _dt(fwd), kpad, norm.data_ptr(), _stream()),

@@ -48,35 +48,44 @@ def packed_backward_weights(model) -> Dict:
     ae = model.audio_encoder
 
     def build():
-        T_ = lambda w: ops.transpose_cast(w.detach(), dt)            # noqa: E731   [N,K] -> [K,N]
+        dev = model.audio_feature_map.weight.device
+        plan = ops.PackPlan(dev)
+        new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)                # noqa: E731
+
+        def T_(w, dtype=None):                                                       # [N,K] -> [K,N]
+            w = w.detach()
+            o = torch.empty((w.shape[1], w.shape[0]), dtype=dtype or dt, device=dev)
+            plan.transpose(w, o)
+            return o
+
         P = {}
         convs = []
         cl = ae.feature_extractor.conv_layers
         for i, k in zip(range(1, 7), (3, 3, 3, 3, 2, 2)):
             w = cl[i].conv.weight.detach()                           # [co, ci, k]
             if k == 3:
-                even = torch.empty((512, 1024), dtype=dt, device=w.device)      # [ci, (tap2 co | tap0 co)]
-                ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1536, ld_c=3, offset=2, out=even, ldo=1024, out_offset=0)
-                ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1536, ld_c=3, offset=0, out=even, ldo=1024, out_offset=512)
-                odd = ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1536, ld_c=3, offset=1)
+                even = new(512, 1024)                                # [ci, (tap2 co | tap0 co)]
+                plan.transpose(w, even, ldo=1024, dst_off=0, R=512, Cc=512, ld_r=1536, ld_c=3, src_off=2)
+                plan.transpose(w, even, ldo=1024, dst_off=512, R=512, Cc=512, ld_r=1536, ld_c=3, src_off=0)
+                odd = new(512, 512)
+                plan.transpose(w, odd, R=512, Cc=512, ld_r=1536, ld_c=3, src_off=1)
                 convs.append((even, odd))
             else:
-                both = torch.empty((1024, 512), dtype=dt, device=w.device)      # [(tap, ci), co]
-                ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1024, ld_c=2, offset=0, out=both, ldo=512, out_offset=0)
-                ops.transpose_cast(w, dt, R=512, Cc=512, ld_r=1024, ld_c=2, offset=1, out=both, ldo=512,
-                                   out_offset=512 * 512)
+                both = new(1024, 512)                                # [(tap, ci), co]
+                plan.transpose(w, both, ldo=512, dst_off=0, R=512, Cc=512, ld_r=1024, ld_c=2, src_off=0)
+                plan.transpose(w, both, ldo=512, dst_off=512 * 512, R=512, Cc=512, ld_r=1024, ld_c=2, src_off=1)
                 convs.append((both,))
         P["convs"] = convs
         P["proj_t"] = T_(ae.feature_projection.projection.weight)             # [512,768]
         pz = ae.encoder.pos_conv_embed.conv.parametrizations.weight
-        P["pos_fwd"], P["pos_bwd"] = ops.pack_posconv_weights_train(pz.original0.detach().reshape(-1),
-                                                                    pz.original1.detach(), dt)
+        kpad = 64 if bf else 48
+        P["pos_fwd"], P["pos_bwd"] = new(16, 48, 128, kpad), new(16, 48, 128, kpad)
         lay = []
         for blk in ae.encoder.layers:
             a = blk.attention
-            qkv_t = torch.empty((768, 2304), dtype=dt, device=a.q_proj.weight.device)
+            qkv_t = new(768, 2304)
             for j, lin in enumerate((a.q_proj, a.k_proj, a.v_proj)):
-                ops.transpose_cast(lin.weight.detach(), dt, out=qkv_t, ldo=2304, out_offset=768 * j)
+                plan.transpose(lin.weight.detach(), qkv_t, ldo=2304, dst_off=768 * j)
             lay.append({"qkv_t": qkv_t, "o_t": T_(a.out_proj.weight),
                         "f1_t": T_(blk.feed_forward.intermediate_dense.weight),     # [768,3072]
                         "f2_t": T_(blk.feed_forward.output_dense.weight)})          # [3072,768]
@@ -84,14 +93,26 @@ def packed_backward_weights(model) -> Dict:
         P["afm_t"] = T_(model.audio_feature_map.weight)                              # [768,64]
         wr = model.vertice_map_r.weight.detach()                                     # [15069,64]
         if bf:
-            wr_t = torch.zeros((64, V3PAD), dtype=dt, device=wr.device)
-            ops.transpose_cast(wr, dt, out=wr_t, ldo=V3PAD)
+            wr_t = torch.zeros((64, V3PAD), dtype=dt, device=dev)
+            plan.transpose(wr, wr_t, ldo=V3PAD)
         else:
-            wr_t = ops.transpose_cast(wr, dt)                                        # [64,15069]
+            wr_t = new(64, wr.shape[0])                                              # [64,15069]
+            plan.transpose(wr, wr_t)
         P["head_t"] = wr_t
         d = model.transformer_decoder.layers[0]
-        P["ca_out_t"] = ops.transpose_cast(d.multihead_attn.out_proj.weight.detach(), torch.float32)
-        P["ca_v_t"] = ops.transpose_cast(d.multihead_attn.in_proj_weight.detach()[128:192].contiguous(), torch.float32)
+        P["ca_out_t"] = T_(d.multihead_attn.out_proj.weight, torch.float32)
+        P["ca_v_t"] = torch.empty((64, 64), dtype=torch.float32, device=dev)
+        plan.transpose(d.multihead_attn.in_proj_weight.detach(), P["ca_v_t"], R=64, Cc=64, ld_r=64, src_off=128 * 64)
+        plan.finalize()
+        P["_plan"] = plan
+
+        def refresh():
+            plan.run()
+            ops.pack_posconv_weights_train(pz.original0.detach().reshape(-1), pz.original1.detach(), dt,
+                                           out=(P["pos_fwd"], P["pos_bwd"]))
+
+        P["_refresh"] = refresh
+        refresh()
         return P
 
     srcs = list(model.parameters())

@@ -369,6 +369,21 @@ int a2f_cast_rows(const void* in, int in_dtype, long long ld_in, void* out, int 
  * one tap of a Conv1d weight [co,ci,taps]: ld_r = ci*taps, ld_c = taps). */
 int a2f_transpose_cast(const float* in, long long ld_r, long long ld_c, int R, int C, void* out, int out_dtype,
                        long long ldo, void* stream);
+/* Many strided 2-D fp32 -> fp32/bf16 copies in one launch: for every job, dst[r*ldo_r + c*ldo_c] = src[r*ld_r + c*ld_c],
+ * r < R, c < C.  `jobs_dev` is a DEVICE array of n_jobs entries whose `tile0` fields hold the exclusive prefix sum of
+ * ceil(R/32)*ceil(C/32) (total_tiles = the full sum).  Re-derives every packed operand of a training step (bf16 casts,
+ * transposed data-gradient operands, implicit-GEMM conv layouts, fused QKV) after the optimizer touched the fp32 masters
+ * (the reference has no counterpart: torch.autocast re-casts weights op by op). */
+typedef struct a2f_copy_job {
+    const float* src;
+    void* dst;
+    long long ld_r, ld_c;      /* source strides of the logical [R, C] matrix, in elements */
+    long long ldo_r, ldo_c;    /* destination strides, in elements */
+    int R, C;
+    int dst_dtype;             /* A2F_F32 or A2F_BF16 */
+    int tile0;                 /* first 32x32 tile of this job within the launch */
+} a2f_copy_job;
+int a2f_strided_copy_jobs(const a2f_copy_job* jobs_dev, int n_jobs, int total_tiles, void* stream);
 /* out[i0*so0+i1*so1+i2*so2] += in[i0*si0+i1*si1+i2*si2] over an n0 x n1 x n2 index space (fp32): adds a weight gradient
  * computed in the implicit-GEMM layout [co][tap][ci] into the parameter's own [co][ci][tap] .grad buffer. */
 int a2f_add_strided3(const float* in, float* out, int n0, int n1, int n2, long long si0, long long si1, long long si2,
