@@ -166,8 +166,12 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
         }
         __syncthreads();
 
-        // ---------- phase 2: biased causal attention over keys 0..i (threads 0..511, 128 per head) ----------
-        if (tid < 512) {
+        // ---------- phase 2: biased causal attention over keys 0..i (threads 0..511, 4 warps per head) ----------
+        // Flash-style split: warp wq of head h owns the keys {128m + 32wq + lane} and runs its own softmax
+        // (max by one REDUX on order-preserving integers, probabilities and P.V warp-synchronously); the four
+        // (max, sum, P.V) partials of a head are merged after ONE named barrier.  (The first version shared max and
+        // sum through shared memory with three barriers per step: 40 % of the step, profiles/r1_decoder_lines.txt.)
+        {
             const int h = tid >> 7, u = tid & 127, wq = (tid >> 5) & 3;
             const float slope = (h == 0) ? 0.25f : (h == 1) ? 0.0625f : (h == 2) ? 0.015625f : 0.00390625f;
             float qh[16];
@@ -180,43 +184,67 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             float lmax = -INFINITY;
             for (int j = u; j <= i; j += 128) {
                 const float* kp = Kc + (long long)j * KV_LD + h * 16;
-                float acc = 0.f;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
                 for (int d = 0; d < 16; d += 4) {
                     const float4 f = *reinterpret_cast<const float4*>(kp + d);
-                    acc = fmaf(qh[d], f.x, acc);
-                    acc = fmaf(qh[d + 1], f.y, acc);
-                    acc = fmaf(qh[d + 2], f.z, acc);
-                    acc = fmaf(qh[d + 3], f.w, acc);
+                    a0 = fmaf(qh[d], f.x, a0);
+                    a1 = fmaf(qh[d + 1], f.y, a1);
+                    a2 = fmaf(qh[d + 2], f.z, a2);
+                    a3 = fmaf(qh[d + 3], f.w, a3);
                 }
-                const float s = acc - slope * (float)((i - j) / period);
+                const float s = ((a0 + a1) + (a2 + a3)) - slope * (float)((i - j) / period);
                 sch[j] = s;
                 lmax = fmaxf(lmax, s);
             }
-            lmax = warp_max(lmax);
-            if (lane == 0) red[h * 8 + wq] = lmax;
-            named_bar_sync(1 + h, 128);
-            const float m = fmaxf(fmaxf(red[h * 8], red[h * 8 + 1]), fmaxf(red[h * 8 + 2], red[h * 8 + 3]));
+            const float wmax = warp_max_redux(lmax);                  // -inf when this warp owns no key yet
             float lsum = 0.f;
             for (int j = u; j <= i; j += 128) {
-                const float pj = expf(sch[j] - m);
+                const float pj = expf(sch[j] - wmax);
                 sch[j] = pj;
                 lsum += pj;
             }
+            __syncwarp();
+            // P.V over this warp's keys: lane = (key slot kg, 4-wide column group dg); conflict-free float4 reads
+            const int kg = lane & 7, dg = lane >> 3;
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+            for (int base = 32 * wq; base <= i; base += 128) {
+                const int nvalid = min(32, i - base + 1);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int jj = kg + 8 * t;
+                    if (jj < nvalid) {
+                        const int j = base + jj;
+                        const float pj = sch[j];
+                        const float4 v = *reinterpret_cast<const float4*>(Vc + (long long)j * KV_LD + h * 16 + dg * 4);
+                        o0 = fmaf(pj, v.x, o0);
+                        o1 = fmaf(pj, v.y, o1);
+                        o2 = fmaf(pj, v.z, o2);
+                        o3 = fmaf(pj, v.w, o3);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                o0 += __shfl_xor_sync(0xffffffffu, o0, o);
+                o1 += __shfl_xor_sync(0xffffffffu, o1, o);
+                o2 += __shfl_xor_sync(0xffffffffu, o2, o);
+                o3 += __shfl_xor_sync(0xffffffffu, o3, o);
+            }
             lsum = warp_sum(lsum);
-            if (lane == 0) red[h * 8 + 4 + wq] = lsum;
-            named_bar_sync(1 + h, 128);
-            const float l = (red[h * 8 + 4] + red[h * 8 + 5]) + (red[h * 8 + 6] + red[h * 8 + 7]);
-            // P V: thread (jg, d) accumulates keys j = jg (mod 8)
-            const int d = u & 15, jg = u >> 4;
-            float acc = 0.f;
-            for (int j = jg; j <= i; j += 8) acc = fmaf(sch[j], Vc[(long long)j * KV_LD + h * 16 + d], acc);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-            if (lane < 16) pvp[(h * 4 + wq) * 16 + lane] = acc;
+            if (kg == 0) *reinterpret_cast<float4*>(pvp + (h * 4 + wq) * 16 + dg * 4) = make_float4(o0, o1, o2, o3);
+            if (lane == 0) {
+                red[h * 8 + wq] = wmax;
+                red[h * 8 + 4 + wq] = lsum;
+            }
             named_bar_sync(1 + h, 128);
             if (u < 16) {
+                const float m0 = red[h * 8], m1 = red[h * 8 + 1], m2 = red[h * 8 + 2], m3 = red[h * 8 + 3];
+                const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                const float e0 = expf(m0 - m), e1 = expf(m1 - m), e2 = expf(m2 - m), e3 = expf(m3 - m);
+                const float l = (e0 * red[h * 8 + 4] + e1 * red[h * 8 + 5]) + (e2 * red[h * 8 + 6] + e3 * red[h * 8 + 7]);
                 const float* pp = pvp + h * 64 + u;
-                const float cv = ((pp[0] + pp[16]) + (pp[32] + pp[48])) / l;
+                const float cv = ((e0 * pp[0] + e1 * pp[16]) + (e2 * pp[32] + e3 * pp[48])) / l;
                 os[h * 16 + u] = cv;
                 if (TRAIN) {
                     sv.CTX[((long long)b * T + i) * 64 + h * 16 + u] = cv;

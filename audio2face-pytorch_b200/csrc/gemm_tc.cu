@@ -32,6 +32,7 @@ struct TmapSet {
     CUtensorMap a[MAX_SEGS];
     CUtensorMap b;
     CUtensorMap c;
+    CUtensorMap r;                  // residual / saved pre-activation (pair kernel, bf16, 16-byte aligned rows)
 };
 
 struct TcParams {
@@ -41,6 +42,7 @@ struct TcParams {
     int resid_vec_ok;               // 16-byte vector residual loads are legal
     int bias_vec_ok;                // 16-byte vector bias loads are legal
     int fast_gelu;                  // bf16 output: A-S erf approximation instead of erff
+    int resid_tma;                  // pair kernel: the residual tile arrives by TMA in the store-staging layout
     uint32_t lbo_enc, sbo_enc, desc_version, desc_layout;
     unsigned long long* timeline;   // debug (a2f_debug_set_timeline): 8 globaltimer stamps per CTA, else NULL
 };
@@ -96,7 +98,11 @@ __device__ __forceinline__ void epi_bias_act(float* v, const float* __restrict__
     if (act == A2F_ACT_GELU) {
         if (fast_gelu) {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j]);
+            for (int j = 0; j < CH; j += 2) {       // packed fp32 (FFMA2 / FMUL2): half the issue slots of the scalar form
+                const float2 r = gelu_fast2(make_float2(v[j], v[j + 1]));
+                v[j] = r.x;
+                v[j + 1] = r.y;
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
@@ -488,10 +494,12 @@ template <int BN, typename TC> struct Tc2Cfg {
     static constexpr int TMEM_COLS = 512;
     static constexpr int B_HALF_BYTES = (BN / 2) * TBK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;        // per CTA
-    static constexpr int STAGES = (BN >= 256) ? 6 : 8;
+    static constexpr int STAGES = (BN >= 256) ? 5 : 8;
     static constexpr int SBW = (int)(128 / sizeof(TC));
     static constexpr int NBLK = BN / SBW;
-    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 2 * EPI_STAGE_BYTES + 256;
+    static constexpr int N_EPI_BUF = 4;                                     // two column halves x double buffering
+    static constexpr int BIAS_BYTES = 2 * BN * 4;                           // bias of the tile, double-buffered by accumulator
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + N_EPI_BUF * EPI_STAGE_BYTES + BIAS_BYTES + 256;
 };
 
 template <int BN, typename TC>
@@ -505,12 +513,14 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)STAGES * A_STAGE_BYTES;
     uint8_t* sEpi = smem + (size_t)STAGES * Cfg::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 2 * EPI_STAGE_BYTES);
+    float* sbias = reinterpret_cast<float*>(sEpi + Cfg::N_EPI_BUF * EPI_STAGE_BYTES);      // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + Cfg::N_EPI_BUF * EPI_STAGE_BYTES + Cfg::BIAS_BYTES);
     uint64_t* full_bar = bars;                 // [STAGES]  used in the leader only
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]  both CTAs (multicast commit)
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       both CTAs (multicast commit)
     uint64_t* tempty_bar = tfull_bar + 2;      // [2]       leader only: 8 epilogue warps x 2 CTAs
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* rbar = tempty_bar + 2;           // [2]       residual tile landed (one per column half), CTA-local
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GemmParams& g = p.g;
@@ -524,6 +534,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b);
         tma_prefetch_desc(&maps.c);
+        if (p.resid_tma) tma_prefetch_desc(&maps.r);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -533,6 +544,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 16);
+            mbar_init(&rbar[i], 1);
         }
         fence_mbar_init();
     }
@@ -609,18 +621,25 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         __syncwarp();
     } else {
         // ===================== epilogue: 8 warps per CTA, each CTA drains its own 128 accumulator rows ===============
+        // Latency plan (per-CTA timeline, profiles/r1_gemm_timeline.txt: 2.9 us per tile, 6.2 us with a residual, against
+        // 4.3 us of mainloop at K=768): the tile's bias sits in shared memory before the accumulator is complete; the
+        // residual / saved pre-activation tile is fetched by TMA straight into the (128B-swizzled) store-staging buffer,
+        // so each thread reads its own row with conflict-free 16-byte loads instead of 32 uncoalesced global rows per
+        // warp instruction; staging is double-buffered so that a block never waits for the previous block's store.
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
         const bool leader = ((ew & 3) == 0) && lane == 0;
         const int bar_id = 1 + half;
-        uint8_t* stage_buf = sEpi + half * EPI_STAGE_BYTES;
+        uint8_t* stage_base = sEpi + half * 2 * EPI_STAGE_BYTES;       // two staging buffers per column half
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t sb = 0;                                               // blocks this half has processed
         const float* __restrict__ e_bias = g.bias;
         const void* __restrict__ e_resid = g.resid;
         const int e_act = g.act;
         const bool e_dact = g.resid_mode == A2F_RESID_DACT;
+        const bool rtma = p.resid_tma != 0;
         constexpr int SBW = Cfg::SBW;
         constexpr int EPC = 16 / (int)sizeof(TC);
         for (int tile = pair; tile < total_tiles; tile += n_pairs) {
@@ -629,43 +648,88 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
             const int n_tile0 = nb * BN;
             const int n_lim = min(BN, g.N - n_tile0);
             const int n_end = n_tile0 + n_lim;
+            const int row_base = lt * PBM + rank * TBM;
+
+            // while the mainloop runs: bias of this tile -> smem, first residual block -> staging buffer
+            float* tb = sbias + acc * BN;
+            if (e_bias != nullptr) {
+                const int c = ew * 32 + lane;                          // 256 epilogue threads, BN == 256 columns
+                tb[c] = (n_tile0 + c < g.N) ? __ldg(e_bias + n_tile0 + c) : 0.f;
+            }
+            if (rtma && leader && half * SBW < n_lim) {
+                tma_store_wait_read1();                                // the store that used this buffer two blocks ago
+                mbar_expect_tx(&rbar[half], EPI_STAGE_BYTES);
+                tma_load_3d(stage_base + (sb & 1) * EPI_STAGE_BYTES, &maps.r, &rbar[half], n_tile0 + half * SBW, row_base, b);
+            }
+            named_bar_sync(3, 256);                                    // bias visible to all epilogue warps
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             if (threadIdx.x == 64 && tile == pair) TL_STAMP(4);
 
             const int r_tile = q * 32 + lane;
-            const int row_base = lt * PBM + rank * TBM;
             const int r_in_batch = row_base + r_tile;
             const bool row_ok = r_in_batch < g.rows_per_batch;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
-            uint8_t* rowp = stage_buf + r_tile * 128;
 #pragma unroll 1
             for (int blk = half; blk < Cfg::NBLK; blk += 2) {
                 const int col0 = blk * SBW;
                 if (col0 >= n_lim) break;
                 const int ncol0 = n_tile0 + col0;
+                uint8_t* stage_buf = stage_base + (sb & 1) * EPI_STAGE_BYTES;
+                uint8_t* rowp = stage_buf + r_tile * 128;
                 float v[SBW];
 #pragma unroll
                 for (int cc = 0; cc < SBW / 32; ++cc) tmem_ld_32x32(t_row + col0 + cc * 32, v + cc * 32);
                 tmem_ld_wait();
-                const long long r_off = (long long)b * g.r_batch_stride + (long long)r_in_batch * g.ldr + ncol0;
-                if (e_dact) {
-                    if (row_ok) {
-                        float z[SBW];
+                if (!e_dact) {
+                    if (e_bias != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < SBW; ++j) z[j] = 0.f;
-                        epi_resid<SBW>(z, e_resid, g.resid_bf16, r_off, ncol0, n_end, p.resid_vec_ok);
+                        for (int j = 0; j < SBW; j += 4) {
+                            const float4 f = *reinterpret_cast<const float4*>(tb + col0 + j);
+                            v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+                        }
+                    }
+                    epi_bias_act<SBW>(v, nullptr, 0, ncol0, n_end, e_act, p.fast_gelu);
+                }
+                if (rtma) {
+                    mbar_wait(&rbar[half], sb & 1);                    // residual block landed (and the buffer is ours)
+                    if (sizeof(TC) == 2) {
 #pragma unroll
-                        for (int j = 0; j < SBW; ++j) v[j] *= act_grad(z[j], e_act);
+                        for (int ch = 0; ch < SBW / 8; ++ch) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16));
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __bfloat1622float2(h2[e]);
+                                if (e_dact) {
+                                    v[ch * 8 + 2 * e] *= act_grad(f.x, e_act);
+                                    v[ch * 8 + 2 * e + 1] *= act_grad(f.y, e_act);
+                                } else {
+                                    v[ch * 8 + 2 * e] += f.x;
+                                    v[ch * 8 + 2 * e + 1] += f.y;
+                                }
+                            }
+                        }
                     }
                 } else {
-                    epi_bias_act<SBW>(v, e_bias, p.bias_vec_ok, ncol0, n_end, e_act, p.fast_gelu);
-                    if (e_resid != nullptr && row_ok)
+                    const long long r_off = (long long)b * g.r_batch_stride + (long long)r_in_batch * g.ldr + ncol0;
+                    if (e_dact) {
+                        if (row_ok) {
+                            float z[SBW];
+#pragma unroll
+                            for (int j = 0; j < SBW; ++j) z[j] = 0.f;
+                            epi_resid<SBW>(z, e_resid, g.resid_bf16, r_off, ncol0, n_end, p.resid_vec_ok);
+#pragma unroll
+                            for (int j = 0; j < SBW; ++j) v[j] *= act_grad(z[j], e_act);
+                        }
+                    } else if (e_resid != nullptr && row_ok) {
                         epi_resid<SBW>(v, e_resid, g.resid_bf16, r_off, ncol0, n_end, p.resid_vec_ok);
+                    }
+                    // the store that used this staging buffer two blocks ago must have finished reading it
+                    if (leader) tma_store_wait_read1();
+                    named_bar_sync(bar_id, 128);
                 }
-                if (leader) tma_store_wait_read();
-                named_bar_sync(bar_id, 128);
 #pragma unroll
                 for (int ch = 0; ch < SBW / EPC; ++ch) {
                     const int pch = ch ^ (r_tile & 7);
@@ -685,9 +749,15 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
+                ++sb;
                 if (leader) {
                     tma_store_3d(&maps.c, stage_buf, ncol0, row_base, b);
                     tma_store_commit();
+                    if (rtma && col0 + 2 * SBW < n_lim) {              // next block of this tile: fetch its residual now
+                        tma_store_wait_read1();
+                        mbar_expect_tx(&rbar[half], EPI_STAGE_BYTES);
+                        tma_load_3d(stage_base + (sb & 1) * EPI_STAGE_BYTES, &maps.r, &rbar[half], ncol0 + 2 * SBW, row_base, b);
+                    }
                 }
             }
             tc_fence_before();
@@ -711,14 +781,25 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
 }
 
 template <int BN, typename TC>
-static int launch_tc2(TmapSet& maps, const TcParams& p, cudaStream_t s) {
+static int launch_tc2(TmapSet& maps, const TcParams& p_in, cudaStream_t s) {
     using Cfg = Tc2Cfg<BN, TC>;
-    const GemmParams& g = p.g;
-    uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)g.rows_per_batch, (uint64_t)p.num_batches};
+    const GemmParams& g = p_in.g;
+    uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)g.rows_per_batch, (uint64_t)p_in.num_batches};
     uint64_t strides[2] = {(uint64_t)g.ldc * sizeof(TC), (uint64_t)g.c_batch_stride * sizeof(TC)};
     uint32_t box[3] = {(uint32_t)Cfg::SBW, TBM, 1};
     int rc = encode_tmap(&maps.c, g.C, (int)sizeof(TC), 3, dims, strides, box, 1);
     if (rc != A2F_OK) return rc;
+    TcParams p = p_in;
+    p.resid_tma = 0;
+    if (g.resid != nullptr && g.resid_bf16 && sizeof(TC) == 2 && reinterpret_cast<uintptr_t>(g.resid) % 16 == 0 &&
+        (g.ldr * 2) % 16 == 0 && (g.r_batch_stride * 2) % 16 == 0) {
+        uint64_t rdims[3] = {(uint64_t)g.N, (uint64_t)g.rows_per_batch, (uint64_t)p.num_batches};
+        uint64_t rstr[2] = {(uint64_t)g.ldr * 2, (uint64_t)g.r_batch_stride * 2};
+        uint32_t rbox[3] = {64, TBM, 1};
+        rc = encode_tmap(&maps.r, g.resid, 2, 3, rdims, rstr, rbox, 1);
+        if (rc != A2F_OK) return rc;
+        p.resid_tma = 1;
+    }
     auto kern = gemm_tc2_kernel<BN, TC>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -798,6 +879,7 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
     p.desc_version = g_umma_fields[2];
     p.desc_layout = g_umma_fields[3];
     p.fast_gelu = c_bf16 ? 1 : 0;
+    p.resid_tma = 0;
     p.timeline = g_timeline;
     TmapSet maps;
     memset(&maps, 0, sizeof(maps));

@@ -26,8 +26,13 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const TI* __restrict__ z, 
             float v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = ld_as_float(z + i + j);
+            if (act == A2F_ACT_GELU && fast) {
+                const float2 r0 = gelu_fast2(make_float2(v[0], v[1])), r1 = gelu_fast2(make_float2(v[2], v[3]));
+                v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (act == A2F_ACT_GELU && fast) ? gelu_fast(v[j]) : apply_act_rt(v[j], act);
+                for (int j = 0; j < 4; ++j) v[j] = apply_act_rt(v[j], act);
+            }
             if (resid) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] += ld_as_float(resid + i + j);

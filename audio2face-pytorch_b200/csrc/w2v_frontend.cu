@@ -151,17 +151,14 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
     }
     // each thread owns two adjacent channels (one packed 4-byte store in bf16, coalesced either way)
     const int c = threadIdx.x * 2;
-    float w0[10], w1[10];
+    float2 wp[10];                        // (w[c][k], w[c+1][k]): one FFMA2 per tap for the channel pair
 #pragma unroll
-    for (int k = 0; k < 10; ++k) {
-        w0[k] = w[c * 10 + k];
-        w1[k] = w[(c + 1) * 10 + k];
-    }
+    for (int k = 0; k < 10; ++k) wp[k] = make_float2(w[c * 10 + k], w[(c + 1) * 10 + k]);
     const float2 g0 = gn[b * 512 + c], g1 = gn[b * 512 + c + 1];
     const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
     // bf16 path: GroupNorm affine folded to one FMA (y = conv*A + Bc) and the MUFU.TANH GELU; fp32 path: literal form
-    const float A0 = g0.y * ga0, A1 = g1.y * ga1;
-    const float B0 = be0 - g0.x * A0, B1 = be1 - g1.x * A1;
+    const float2 Aff = make_float2(g0.y * ga0, g1.y * ga1);
+    const float2 Bff = make_float2(be0 - g0.x * Aff.x, be1 - g1.x * Aff.y);
     __syncthreads();
     TO* o = out + (long long)b * out_batch_stride;
     const int tn = min(C0_TCH, L0 - t0);
@@ -176,20 +173,16 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (t4 + u >= tn) break;
-            float a0 = 0.f, a1 = 0.f;
+            float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < 10; ++k) {
-                a0 = fmaf(w0[k], xw[5 * u + k], a0);
-                a1 = fmaf(w1[k], xw[5 * u + k], a1);
-            }
+            for (int k = 0; k < 10; ++k) a = ffma2(wp[k], make_float2(xw[5 * u + k], xw[5 * u + k]), a);
             TO* p = o + (long long)(t0 + t4 + u) * 512 + c;
             if (sizeof(TO) == 2) {
-                const float y0 = gelu_fast(fmaf(a0, A0, B0));
-                const float y1 = gelu_fast(fmaf(a1, A1, B1));
-                *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(y0, y1);
+                const float2 y = gelu_fast2(ffma2(a, Aff, Bff));
+                *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(y.x, y.y);
             } else {
-                const float y0 = gelu_erf((a0 - g0.x) * g0.y * ga0 + be0);
-                const float y1 = gelu_erf((a1 - g1.x) * g1.y * ga1 + be1);
+                const float y0 = gelu_erf((a.x - g0.x) * g0.y * ga0 + be0);
+                const float y1 = gelu_erf((a.y - g1.x) * g1.y * ga1 + be1);
                 *reinterpret_cast<float2*>(p) = make_float2(y0, y1);
             }
         }
