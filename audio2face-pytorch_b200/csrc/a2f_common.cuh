@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <math.h>
+#include <string.h>
 #include "../../include/a2f.h"
 
 #define A2F_HD __host__ __device__ __forceinline__
@@ -38,6 +39,37 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 int sm_count();   // cached multiprocessor count of the current device
 void count_launch(int n = 1);   // feeds a2f_launch_count()
 int require_sm100();           // A2F_OK or A2F_EARCH (cached per device)
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// Every kernel of the inference chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (launch_pdl below) and runs `pdl_sync()` after its private prologue (barrier init, TMEM allocation, descriptor
+// prefetch) and BEFORE its first access to global memory.  griddepcontrol.wait blocks until the previous kernel of the
+// stream has completed and flushed; griddepcontrol.launch_dependents lets the NEXT kernel's CTAs become resident (and
+// run their own prologue up to their wait) as soon as SM resources free up -- so launch latency and prologues overlap
+// the tail of the running kernel instead of adding ~2 us per launch to a ~100-launch step.  Without the launch
+// attribute both instructions are no-ops, so the same kernels work when launched the ordinary way.
+int pdl_enabled();             // 1 unless A2F_PDL=0 in the environment (debug switch)
+#ifdef __CUDACC__
+A2F_D void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 
 // ---- scalar math -----------------------------------------------------------------------------
 A2F_D float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

@@ -73,6 +73,7 @@ __global__ void posconv_pack_kernel(const float* __restrict__ gw, const float* _
 // a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  (everything but the lo*lo term) with fp32 accumulation.
 __global__ void split_bf16x3_kernel(const float* __restrict__ in, long long ld_in, bf16* __restrict__ out, long long rows,
                                     int K, int is_weight) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     const long long n = rows * K;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -319,7 +320,7 @@ int a2f_split_bf16x3(const float* in, long long ld_in, void* out, long long rows
     if (rows == 0) return A2F_OK;
     const long long n = rows * K;
     const int grid = (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256);
-    split_bf16x3_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, ld_in, static_cast<bf16*>(out), rows, K, is_weight);
+    A2F_CHECK_CUDA(launch_pdl(split_bf16x3_kernel, dim3(grid), dim3(256), 0, as_stream(stream), in, ld_in, static_cast<bf16*>(out), rows, K, is_weight));
     A2F_CHECK_LAUNCH("split_bf16x3_kernel");
     count_launch();
     return A2F_OK;

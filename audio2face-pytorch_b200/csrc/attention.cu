@@ -103,6 +103,7 @@ template <int N> A2F_D void cp_async_wait() { asm volatile("cp.async.wait_group 
 __global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                        float* __restrict__ lse, float* __restrict__ out32, int T, int H,
                                                        float scale_log2) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     __shared__ __align__(16) bf16 sQ[FA_BM * FA_LD];
     __shared__ __align__(16) bf16 sK[2][FA_BN * FA_LD];
     __shared__ __align__(16) bf16 sV[2][FA_BN * FA_LD];
@@ -636,6 +637,16 @@ __global__ void __launch_bounds__(128) mha_bwd_dkv_kernel(const bf16* __restrict
 
 }  // namespace a2f
 
+namespace a2f {
+int mha_tc_fwd(const void* qkv, void* out, int B, int T, int H, float scale, cudaStream_t s);   // attention_tc.cu
+static int g_mha_impl = 0;          // 0 = automatic, 1 = always mma.sync, 2 = always tcgen05 (a2f_debug_set_umma_field 6)
+static int g_mha_tc_min_t = 300;    // automatic: tcgen05 from this sequence length on (field 7)
+int mha_impl() { return g_mha_impl; }
+int mha_tc_min_t() { return g_mha_tc_min_t; }
+void set_mha_impl(int v) { g_mha_impl = v; }
+void set_mha_tc_min_t(int v) { g_mha_tc_min_t = v; }
+}  // namespace a2f
+
 using namespace a2f;
 
 extern "C" int a2f_mha_fwd(const void* qkv, void* out, int dtype, int B, int T, int H, int D, float scale,
@@ -713,9 +724,19 @@ extern "C" int a2f_mha_fwd_train(const void* qkv, void* out, float* lse, float* 
         A2F_CHECK_LAUNCH("mha_f32_kernel");
     } else if (dtype == A2F_BF16) {
         A2F_REQUIRE(reinterpret_cast<uintptr_t>(qkv) % 16 == 0, "a2f_mha_fwd: qkv must be 16-byte aligned");
+        // inference forward (no log-sum-exp / fp32 side output): the tcgen05 kernel of attention_tc.cu for sequences
+        // long enough to fill its 128x128 tiles; the mma.sync kernel below for short ones and for training
+        const int impl = mha_impl();
+        if (lse == nullptr && out_f32 == nullptr && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+            (impl == 2 || (impl == 0 && T >= mha_tc_min_t()))) {
+            rc = mha_tc_fwd(qkv, out, B, T, H, scale, s);
+            if (rc != A2F_OK) return rc;
+            count_launch();
+            return A2F_OK;
+        }
         const dim3 grid((T + FA_BM - 1) / FA_BM, H, B);
-        mha_bf16_kernel<<<grid, 128, 0, s>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, out_f32, T, H,
-                                              scale * 1.4426950408889634f);
+        A2F_CHECK_CUDA(launch_pdl(mha_bf16_kernel, dim3(grid), dim3(128), 0, s, static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, out_f32, T, H,
+                                              scale * 1.4426950408889634f));
         A2F_CHECK_LAUNCH("mha_bf16_kernel");
     } else {
         return set_error(A2F_EINVAL, "a2f_mha_fwd: bad dtype");

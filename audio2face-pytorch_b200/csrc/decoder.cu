@@ -71,6 +71,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                        const float* __restrict__ one_hot, int n_onehot, int period, float* __restrict__ D, int T,
                        float* __restrict__ kv_global /* [B][2][T][KV_LD] or NULL */, DecSaves sv) {
     extern __shared__ __align__(16) float dsm[];
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x;
     const int Tpad = (T + 3) & ~3;
@@ -450,7 +451,7 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
     if (saves == nullptr) {
         DecSaves none = {};
         A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        decoder_rollout_kernel<false><<<B, DEC_THREADS, smem, s>>>(dw, ca, one_hot, n_onehot, period, D, T, kv, none);
+        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca, one_hot, n_onehot, period, D, T, kv, none));
     } else {
         DecSaves sv;
         const size_t bt = (size_t)B * T;
@@ -462,7 +463,7 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
         sv.HID = f + bt * a2f_decoder_save_offset(A2F_DEC_HID); sv.Y3PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y3PRE);
         sv.LSE = f + bt * a2f_decoder_save_offset(A2F_DEC_LSE);
         A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        decoder_rollout_kernel<true><<<B, DEC_THREADS, smem, s>>>(dw, ca, one_hot, n_onehot, period, D, T, kv, sv);
+        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<true>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca, one_hot, n_onehot, period, D, T, kv, sv));
     }
     A2F_CHECK_LAUNCH("decoder_rollout_kernel");
     count_launch();

@@ -13,6 +13,7 @@ constexpr int SBM = 64, SBN = 64, SBK = 16;
 // MODE 2: positional conv: k = tap*48 + c -> h[b, t + tap - 64, g*48 + c], zero outside [0,T).
 template <typename TA, typename TC, int MODE>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     __shared__ float As[SBK][SBM + 4];
     __shared__ float Bs[SBK][SBN + 4];
 
@@ -138,10 +139,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
 
 template <int MODE> static int launch_simt(const GemmParams& p, int a_bf16, int c_bf16, int groups, cudaStream_t s) {
     dim3 grid((p.N + SBN - 1) / SBN, (p.M + SBM - 1) / SBM, groups);
-    if (!a_bf16 && !c_bf16) gemm_simt_kernel<float, float, MODE><<<grid, 256, 0, s>>>(p);
-    else if (!a_bf16 && c_bf16) gemm_simt_kernel<float, bf16, MODE><<<grid, 256, 0, s>>>(p);
-    else if (a_bf16 && !c_bf16) gemm_simt_kernel<bf16, float, MODE><<<grid, 256, 0, s>>>(p);
-    else gemm_simt_kernel<bf16, bf16, MODE><<<grid, 256, 0, s>>>(p);
+    if (!a_bf16 && !c_bf16) A2F_CHECK_CUDA(launch_pdl((gemm_simt_kernel<float, float, MODE>), dim3(grid), dim3(256), 0, s, p));
+    else if (!a_bf16 && c_bf16) A2F_CHECK_CUDA(launch_pdl((gemm_simt_kernel<float, bf16, MODE>), dim3(grid), dim3(256), 0, s, p));
+    else if (a_bf16 && !c_bf16) A2F_CHECK_CUDA(launch_pdl((gemm_simt_kernel<bf16, float, MODE>), dim3(grid), dim3(256), 0, s, p));
+    else A2F_CHECK_CUDA(launch_pdl((gemm_simt_kernel<bf16, bf16, MODE>), dim3(grid), dim3(256), 0, s, p));
     A2F_CHECK_LAUNCH("gemm_simt_kernel");
     count_launch();
     return A2F_OK;

@@ -198,6 +198,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();     // PDL: everything above overlapped the previous kernel's tail; global memory is touched below
     if (threadIdx.x == 0) TL_STAMP(1);                                  // setup done (barriers, TMEM)
 
     const int tiles_m = p.tiles_m_per_batch * p.num_batches;
@@ -553,6 +554,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     cluster_sync_all();                        // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
     if (threadIdx.x == 0) TL_STAMP(1);
 
     const int tiles_m = p.tiles_m_per_batch * p.num_batches;     // pair tiles (256 rows)
@@ -815,13 +817,15 @@ static int launch_tc2(TmapSet& maps, const TcParams& p_in, cudaStream_t s) {
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
     count_launch();
     return A2F_OK;
@@ -838,8 +842,7 @@ static int launch_tc(const TmapSet& maps, const TcParams& p, cudaStream_t s) {
     }
     const int total = p.tiles_m_per_batch * p.num_batches * p.tiles_n;
     const int grid = total < sm_count() ? total : sm_count();
-    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(maps, p);
-    A2F_CHECK_LAUNCH("gemm_tc_kernel");
+    A2F_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, maps, p));
     count_launch();
     return A2F_OK;
 }
@@ -1002,6 +1005,10 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
 
 }  // namespace a2f
 
+namespace a2f {
+void set_mha_impl(int v);
+void set_mha_tc_min_t(int v);
+}
 extern "C" int a2f_debug_set_timeline(void* dev_ptr) {
     a2f::g_timeline = static_cast<unsigned long long*>(dev_ptr);
     return A2F_OK;
@@ -1014,6 +1021,15 @@ extern "C" int a2f_debug_set_umma_field(int field, unsigned value) {
     }
     if (field == 5) {   // 0 = never use the CTA-pair (cta_group::2) kernel, 1 = automatic
         a2f::g_pair_mode = value ? 1 : 0;
+        return A2F_OK;
+    }
+    if (field == 6) {   // encoder attention kernel: 0 = automatic, 1 = mma.sync, 2 = tcgen05
+        if (value > 2) return a2f::set_error(A2F_EINVAL, "bad attention impl");
+        a2f::set_mha_impl((int)value);
+        return A2F_OK;
+    }
+    if (field == 7) {   // automatic mode: shortest sequence that takes the tcgen05 attention kernel
+        a2f::set_mha_tc_min_t((int)value);
         return A2F_OK;
     }
     if (field == 4) {   // force tile width (0 = automatic)

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace a2f {
@@ -29,6 +30,15 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+int pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("A2F_PDL");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

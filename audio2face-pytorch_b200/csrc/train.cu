@@ -603,6 +603,35 @@ static int ew_grid(long long n, int per_thread = 1) {
     return (int)blocks;
 }
 
+
+// ------------------------------------------------------------------------------------------------ SpecAugment
+// ref:src/model/wav2vec.py:149-162: hidden_states[mask_time_indices] = masked_spec_embed (training only).
+// mask: one byte per row of the [rows, cols] activation, non-zero = replaced.  One warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256) spec_mask_fwd_kernel(T* __restrict__ h, const unsigned char* __restrict__ mask,
+                                                            const float* __restrict__ embed, long long rows, int cols) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows || mask[row] == 0) return;
+    T* dst = h + row * cols;
+    for (int c = threadIdx.x & 31; c < cols; c += 32) st_from_float(dst + c, embed[c]);
+}
+// backward: dembed[c] += sum over masked rows of dh[row, c]; the masked rows of dh become zero (the projection below
+// them received no signal).  One thread per column walks the rows in order: deterministic, and the walk only touches
+// the ~5-10 % masked rows.
+template <typename T>
+__global__ void __launch_bounds__(128) spec_mask_bwd_kernel(T* __restrict__ dh, const unsigned char* __restrict__ mask,
+                                                            float* __restrict__ dembed, long long rows, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float acc = 0.f;
+    for (long long r = 0; r < rows; ++r) {
+        if (mask[r] == 0) continue;
+        acc += ld_as_float(dh + r * cols + c);
+        st_from_float(dh + r * cols + c, 0.f);
+    }
+    dembed[c] += acc;
+}
+
 }  // namespace a2f
 
 using namespace a2f;
@@ -845,6 +874,36 @@ int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
     adam_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
                                                            grad_scale);
     A2F_CHECK_LAUNCH("adam_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_spec_mask_fwd(void* h, int dtype, const unsigned char* mask, const float* embed, long long rows, int cols,
+                      void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(h && mask && embed && rows >= 0 && cols > 0, "a2f_spec_mask_fwd: bad arguments");
+    A2F_REQUIRE(dtype == A2F_F32 || dtype == A2F_BF16, "a2f_spec_mask_fwd: bad dtype");
+    if (rows == 0) return A2F_OK;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (dtype == A2F_BF16) spec_mask_fwd_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>((bf16*)h, mask, embed, rows, cols);
+    else spec_mask_fwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)h, mask, embed, rows, cols);
+    A2F_CHECK_LAUNCH("spec_mask_fwd_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_spec_mask_bwd(void* dh, int dtype, const unsigned char* mask, float* dembed, long long rows, int cols,
+                      void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(dh && mask && dembed && rows >= 0 && cols > 0, "a2f_spec_mask_bwd: bad arguments");
+    A2F_REQUIRE(dtype == A2F_F32 || dtype == A2F_BF16, "a2f_spec_mask_bwd: bad dtype");
+    if (rows == 0) return A2F_OK;
+    const unsigned grid = (unsigned)((cols + 127) / 128);
+    if (dtype == A2F_BF16) spec_mask_bwd_kernel<bf16><<<grid, 128, 0, as_stream(stream)>>>((bf16*)dh, mask, dembed, rows, cols);
+    else spec_mask_bwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>((float*)dh, mask, dembed, rows, cols);
+    A2F_CHECK_LAUNCH("spec_mask_bwd_kernel");
     count_launch();
     return A2F_OK;
 }

@@ -17,6 +17,7 @@ namespace a2f {
 // ------------------------------------------------------------------------------------------------ audio stats
 __global__ void __launch_bounds__(1024) audio_stats_kernel(const float* __restrict__ audio, long long N,
                                                            float* __restrict__ stats) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     const float* x = audio + (long long)blockIdx.x * N;
     __shared__ double sh[32];
     __shared__ double s_mean;
@@ -60,6 +61,7 @@ constexpr int MOM_N = 65;       // 10 sums + 55 upper-triangular products
 __global__ void __launch_bounds__(256) conv0_moments_kernel(const float* __restrict__ audio,
                                                             const float* __restrict__ stats, long long N, int L0,
                                                             int nchunk, double* __restrict__ partial) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     const int b = blockIdx.y, chunk = blockIdx.x;
     const float* x = audio + (long long)b * N;
     const float mean = stats[2 * b], rstd = stats[2 * b + 1];
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) conv0_moments_kernel(const float* __restr
 __global__ void __launch_bounds__(512) conv0_gn_stats_kernel(const double* __restrict__ partial, int nchunk,
                                                              const float* __restrict__ w, int L0,
                                                              float2* __restrict__ gn) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     const int b = blockIdx.x, c = threadIdx.x;
     __shared__ double mom[MOM_N];
     for (int i = threadIdx.x; i < MOM_N; i += blockDim.x) {
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, TO* __restrict__ out,
                                                           long long N, int L0, long long out_batch_stride) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     const int b = blockIdx.y, t0 = blockIdx.x * C0_TCH;
     __shared__ __align__(16) float xs[5 * C0_TCH + 8];
     const float* x = audio + (long long)b * N;
@@ -196,6 +200,7 @@ template <typename TI, typename TO, int C>
 __global__ void __launch_bounds__(256) interp_ln_kernel(const TI* __restrict__ in, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         TO* __restrict__ out, int B, int S, int T) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     constexpr int PER = C / 32;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * T) return;
@@ -256,6 +261,7 @@ template <typename TI, typename TO, typename TO2, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         TO* __restrict__ out, TO2* __restrict__ out2, long long rows) {
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     constexpr int C = NV * 128;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -297,8 +303,9 @@ static int launch_ln(const void* x, const float* g, const float* b, float eps, v
     const int grid = (int)((rows * 32 + 255) / 256);
 #define A2F_LN_CASE(NV)                                                                                              \
     case NV:                                                                                                         \
-        layernorm_kernel<TI, TO, TO2, NV><<<grid, 256, 0, s>>>(static_cast<const TI*>(x), g, b, eps,                \
-                                                                static_cast<TO*>(out), static_cast<TO2*>(out2), rows); \
+        A2F_CHECK_CUDA(launch_pdl((layernorm_kernel<TI, TO, TO2, NV>), dim3(grid), dim3(256), 0, s,                  \
+                                  static_cast<const TI*>(x), g, b, eps, static_cast<TO*>(out),                      \
+                                  static_cast<TO2*>(out2), rows));                                                   \
         break;
     switch (C / 128) {
         A2F_LN_CASE(1) A2F_LN_CASE(2) A2F_LN_CASE(3) A2F_LN_CASE(4) A2F_LN_CASE(5) A2F_LN_CASE(6) A2F_LN_CASE(7) A2F_LN_CASE(8)
@@ -325,7 +332,7 @@ int a2f_audio_stats(const float* audio, int B, long long N, float* stats, void* 
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(audio && stats && B > 0 && N > 0, "a2f_audio_stats: bad arguments");
-    audio_stats_kernel<<<B, 1024, 0, as_stream(stream)>>>(audio, N, stats);
+    A2F_CHECK_CUDA(launch_pdl(audio_stats_kernel, dim3(B), dim3(1024), 0, as_stream(stream), audio, N, stats));
     A2F_CHECK_LAUNCH("audio_stats_kernel");
     count_launch();
     return A2F_OK;
@@ -359,18 +366,18 @@ int a2f_conv0_gn_gelu(const float* audio, const float* stats, const float* w, co
     double* partial = static_cast<double*>(workspace);
     float2* gn = reinterpret_cast<float2*>(partial + (size_t)B * nchunk * MOM_N);
     cudaStream_t s = as_stream(stream);
-    conv0_moments_kernel<<<dim3(nchunk, B), 256, 0, s>>>(audio, stats, N, L0, nchunk, partial);
+    A2F_CHECK_CUDA(launch_pdl(conv0_moments_kernel, dim3(dim3(nchunk, B)), dim3(256), 0, s, audio, stats, N, L0, nchunk, partial));
     A2F_CHECK_LAUNCH("conv0_moments_kernel");
-    conv0_gn_stats_kernel<<<B, 512, 0, s>>>(partial, nchunk, w, L0, gn);
+    A2F_CHECK_CUDA(launch_pdl(conv0_gn_stats_kernel, dim3(B), dim3(512), 0, s, partial, nchunk, w, L0, gn));
     A2F_CHECK_LAUNCH("conv0_gn_stats_kernel");
     const dim3 grid((L0 + C0_TCH - 1) / C0_TCH, B);
     const long long L0_pad = L0;   // dense [B,L0,512]
     if (out_dtype == A2F_BF16)
-        conv0_apply_kernel<bf16><<<grid, 256, 0, s>>>(audio, stats, w, gn, gamma, beta, static_cast<bf16*>(out), N, L0,
-                                                      L0_pad * 512);
+        A2F_CHECK_CUDA(launch_pdl(conv0_apply_kernel<bf16>, dim3(grid), dim3(256), 0, s, audio, stats, w, gn, gamma, beta, static_cast<bf16*>(out), N, L0,
+                                                      L0_pad * 512));
     else
-        conv0_apply_kernel<float><<<grid, 256, 0, s>>>(audio, stats, w, gn, gamma, beta, static_cast<float*>(out), N, L0,
-                                                       L0_pad * 512);
+        A2F_CHECK_CUDA(launch_pdl(conv0_apply_kernel<float>, dim3(grid), dim3(256), 0, s, audio, stats, w, gn, gamma, beta, static_cast<float*>(out), N, L0,
+                                                       L0_pad * 512));
     A2F_CHECK_LAUNCH("conv0_apply_kernel");
     count_launch(3);
     return A2F_OK;
@@ -385,14 +392,14 @@ int a2f_interp_ln(const void* in, int in_dtype, const float* gamma, const float*
     const int grid = (int)(((long long)B * T * 32 + 255) / 256);
     cudaStream_t s = as_stream(stream);
     if (in_dtype == A2F_F32 && out_dtype == A2F_F32)
-        interp_ln_kernel<float, float, 512><<<grid, 256, 0, s>>>(static_cast<const float*>(in), gamma, beta, eps,
-                                                                  static_cast<float*>(out), B, S, T);
+        A2F_CHECK_CUDA(launch_pdl((interp_ln_kernel<float, float, 512>), dim3(grid), dim3(256), 0, s, static_cast<const float*>(in), gamma, beta, eps,
+                                                                  static_cast<float*>(out), B, S, T));
     else if (in_dtype == A2F_BF16 && out_dtype == A2F_BF16)
-        interp_ln_kernel<bf16, bf16, 512><<<grid, 256, 0, s>>>(static_cast<const bf16*>(in), gamma, beta, eps,
-                                                                static_cast<bf16*>(out), B, S, T);
+        A2F_CHECK_CUDA(launch_pdl((interp_ln_kernel<bf16, bf16, 512>), dim3(grid), dim3(256), 0, s, static_cast<const bf16*>(in), gamma, beta, eps,
+                                                                static_cast<bf16*>(out), B, S, T));
     else if (in_dtype == A2F_F32 && out_dtype == A2F_BF16)
-        interp_ln_kernel<float, bf16, 512><<<grid, 256, 0, s>>>(static_cast<const float*>(in), gamma, beta, eps,
-                                                                 static_cast<bf16*>(out), B, S, T);
+        A2F_CHECK_CUDA(launch_pdl((interp_ln_kernel<float, bf16, 512>), dim3(grid), dim3(256), 0, s, static_cast<const float*>(in), gamma, beta, eps,
+                                                                 static_cast<bf16*>(out), B, S, T));
     else
         return set_error(A2F_EINVAL, "a2f_interp_ln: unsupported dtype combination");
     A2F_CHECK_LAUNCH("interp_ln_kernel");

@@ -383,6 +383,9 @@ class Faceformer(_A2FModule):
         super().__init__()
         self.feature_dim = 64
         self.n_onehot = n_onehot
+        # training forward only: apply wav2vec2's SpecAugment time masking (ref:src/model/wav2vec.py:149-162) with the
+        # reference's host-side numpy draws (spec_augment.py).  Off by default = eval-mode arithmetic.
+        self.spec_augment = False
         self.dataset = "vocaset"
         self.period = 60
         self.fps = 60
@@ -559,6 +562,15 @@ class Faceformer(_A2FModule):
             raise L.A2FError("audio too short for one output frame")
         one_hot = one_hot.reshape(B, -1).contiguous().float()
         tmpl = template.reshape(B, -1).contiguous().float()            # ref:faceformer.py:147
+        # utterances are independent: a batch holding more than `max_chunk_seconds` of audio runs in utterance chunks
+        # (bounds the conv0 activation, 16.4 MB bf16 per second of audio, and keeps element offsets inside int32)
+        per = max(1, int(min(float(kwargs.get("max_chunk_seconds", 480.0)) * 16000.0 / N, float(B))))
+        if B > per:
+            out = torch.empty((B, frame_num, self.vertice_dim // 3, 3), dtype=torch.float32, device=audio.device)
+            kw = dict(kwargs, max_chunk_seconds=float("inf"))
+            for b0 in range(0, B, per):
+                out[b0:b0 + per] = self.forward(audio[b0:b0 + per], one_hot[b0:b0 + per], tmpl[b0:b0 + per], **kw)
+            return out
         P = self._packed()
         h = self.encode(audio, frame_num)
         M = B * frame_num

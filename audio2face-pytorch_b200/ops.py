@@ -431,6 +431,24 @@ def colsum(x: torch.Tensor, out: torch.Tensor, rows: Optional[int] = None, cols:
     return out
 
 
+def spec_mask_fwd(h: torch.Tensor, mask_u8: torch.Tensor, embed: torch.Tensor) -> torch.Tensor:
+    """h[mask] = embed, in place (ref:src/model/wav2vec.py:159-161).  h [rows, cols], mask_u8 uint8 [rows]."""
+    _dev(h, mask_u8, embed)
+    rows, cols = h.shape
+    L.check(L.load().a2f_spec_mask_fwd(h.data_ptr(), _dt(h), mask_u8.data_ptr(), embed.data_ptr(), rows, cols, _stream()),
+            "a2f_spec_mask_fwd")
+    return h
+
+
+def spec_mask_bwd(dh: torch.Tensor, mask_u8: torch.Tensor, dembed: torch.Tensor) -> torch.Tensor:
+    """dembed += sum of the masked rows of dh; those rows of dh are zeroed in place."""
+    _dev(dh, mask_u8, dembed)
+    rows, cols = dh.shape
+    L.check(L.load().a2f_spec_mask_bwd(dh.data_ptr(), _dt(dh), mask_u8.data_ptr(), dembed.data_ptr(), rows, cols, _stream()),
+            "a2f_spec_mask_bwd")
+    return dh
+
+
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
                   dbias: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
     _dev(dy, x, gamma, dgamma, dbeta, dbias)

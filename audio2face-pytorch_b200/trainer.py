@@ -134,7 +134,7 @@ class FaceformerTrainer:
         self.overlap = overlap
         self.group = group
         self.flat = FlatBuffers(model.named_parameters(), training.grad_stage_of, training.N_GRAD_STAGES,
-                                skip=training.NO_GRAD_PARAMS)
+                                skip=training.no_grad_params(model))
         self.exp_avg = torch.zeros_like(self.flat.params)
         self.exp_avg_sq = torch.zeros_like(self.flat.params)
         self.steps = 0

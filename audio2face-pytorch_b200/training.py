@@ -2,10 +2,11 @@
 backward pass (ref: torch.autograd over ref:src/model/faceformer.py:139-188 + HF Wav2Vec2Model inside Lightning's
 training_step, ref:src/model/lightning_model.py:150-161).
 
-Semantics: eval-mode arithmetic (dropout, LayerDrop and SpecAugment are inactive -- stated in DESIGN.md; the
-reference's stochastic ops make bit-level train-mode parity meaningless), every parameter of the reference receives a
-gradient except `audio_encoder.masked_spec_embed` (unused without SpecAugment; same in the reference's eval-mode
-autograd).  Parameter gradients are ACCUMULATED into `param.grad` (allocated as zeros when
+Semantics: eval-mode arithmetic by default (dropout and LayerDrop are inactive -- stated in DESIGN.md; torch's
+device-side RNG makes bit-level parity of those ops meaningless).  SpecAugment, whose randomness is host-side numpy in
+the reference, is available with `model.spec_augment = True` and reproduces the reference's masks draw for draw
+(spec_augment.py).  Every parameter of the reference receives a gradient; `audio_encoder.masked_spec_embed` only with
+SpecAugment on (same in the reference: unused otherwise).  Parameter gradients are ACCUMULATED into `param.grad` (allocated as zeros when
 missing), exactly where torch.optim / a flat-buffer trainer expects them.
 
 precision "fp32": true-fp32 SIMT GEMMs everywhere (the tight-tolerance parity path);
@@ -17,10 +18,12 @@ from __future__ import annotations
 
 from typing import Dict, List
 
+import numpy as np
 import torch
 
 from . import lib as L
 from . import ops
+from . import spec_augment
 
 GELU = L.ACT_GELU
 V3PAD = 15072          # 15069 rounded up to a multiple of 8 (16-byte bf16 rows for TMA)
@@ -155,6 +158,12 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
     M = B * T
     h0 = torch.empty((M, 768), dtype=dt, device=dev)
     ops.gemm(xi.view(M, 512), P["proj_w"], h0, bias=fp.projection.bias.detach(), backend=be)
+    if getattr(model, "spec_augment", False):
+        # SpecAugment (ref:src/model/wav2vec.py:149-162): the mask is drawn on the host with the reference's numpy
+        # sequence (spec_augment.py), applied and back-propagated by the a2f_spec_mask_* kernels
+        mask = spec_augment.time_mask(B, T)
+        tp["spec_mask"] = torch.from_numpy(mask.reshape(-1).astype(np.uint8)).to(dev)
+        ops.spec_mask_fwd(h0, tp["spec_mask"], ae.masked_spec_embed.detach())
     PB = packed_backward_weights(model)
     pc = ops.posconv_pre(h0, PB["pos_fwd"], ae.encoder.pos_conv_embed.conv.bias.detach(), B, T, be)
     pre = ops.act_fwd(pc, GELU, resid=h0)
@@ -321,6 +330,8 @@ def backward(model, tp: Dict, dout: torch.Tensor, on_ready=None) -> None:
     ops.weight_norm_bwd(dwp, pz.original1.detach(), pz.original0.detach().reshape(-1), _grad(pz.original1),
                         _grad(pz.original0).view(-1))
     dh0 = ops.posconv_dgrad(dpc, PB["pos_bwd"], dpre, B, T, be)
+    if tp.get("spec_mask") is not None:
+        ops.spec_mask_bwd(dh0, tp["spec_mask"], _grad(ae.masked_spec_embed))
     fp = ae.feature_projection
     ops.gemm_wgrad(dh0, tp["xi"].view(M, 512), _grad(fp.projection.weight), backend=be)
     ops.colsum(dh0, _grad(fp.projection.bias))
@@ -367,6 +378,11 @@ def backward(model, tp: Dict, dout: torch.Tensor, on_ready=None) -> None:
 
 N_GRAD_STAGES = 14
 NO_GRAD_PARAMS = ("audio_encoder.masked_spec_embed",)     # unused without SpecAugment: grad is None in the reference too
+
+
+def no_grad_params(model) -> tuple:
+    """Parameters that receive no gradient from backward() for this model configuration."""
+    return () if getattr(model, "spec_augment", False) else NO_GRAD_PARAMS
 
 
 def grad_stage_of(name: str) -> int:

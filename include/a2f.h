@@ -390,6 +390,14 @@ int a2f_add_strided3(const float* in, float* out, int n0, int n1, int n2, long l
                      long long so0, long long so1, long long so2, void* stream);
 /* bias gradient: out[n] += sum_m x[m*ld + n] */
 int a2f_colsum(const void* x, int dtype, long long ld, long long rows, int cols, float* out, void* stream);
+/* SpecAugment time masking (training only), replaces `hidden_states[mask_time_indices] = masked_spec_embed` of
+ * ref:src/model/wav2vec.py:149-162.  h / dh: [rows, cols] activations (fp32 or bf16) modified in place; mask: one byte
+ * per row, non-zero = masked (the host draws it with the reference's numpy sequence, spec_augment.py); embed /
+ * dembed: fp32 [cols].  bwd: dembed[c] += sum_{masked r} dh[r,c], then dh[masked rows] = 0. */
+int a2f_spec_mask_fwd(void* h, int dtype, const unsigned char* mask, const float* embed, long long rows, int cols,
+                      void* stream);
+int a2f_spec_mask_bwd(void* dh, int dtype, const unsigned char* mask, float* dembed, long long rows, int cols,
+                      void* stream);
 /* LayerNorm backward over the last dim (C = 512 or 768): x is the saved LayerNorm INPUT.  dgamma / dbeta accumulate;
  * dbias (optional) accumulates the column sums of dx = the bias gradient of the Linear that produced x. */
 int a2f_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, float eps, void* dx,

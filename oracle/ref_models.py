@@ -20,6 +20,7 @@ from __future__ import annotations
 import math
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -207,11 +208,39 @@ def encoder(sd: SD, h: torch.Tensor) -> torch.Tensor:
     return h
 
 
-def audio_encoder(sd: SD, audio_norm: torch.Tensor, frame_num: int) -> torch.Tensor:
-    """ref:src/model/wav2vec.py:91-187 for dataset == "vocaset", eval mode (no SpecAugment)."""
+def spec_augment_time_mask(batch: int, frames: int, mask_prob: float = 0.05, mask_length: int = 10,
+                           min_masks: int = 2, rng=np.random) -> np.ndarray:
+    """`_compute_mask_indices((B,T), mask_time_prob, mask_time_length, None, min_masks=2)` of
+    ref:src/model/wav2vec.py:25-72 as called at :153-159 (HF Wav2Vec2Config defaults 0.05 / 10), for
+    attention_mask=None.  Draws from `rng` (numpy's global generator by default) in the reference's order:
+    rand() once (:37), choice(sz-min_len, n) per row (:59), choice(idc, min_len) per over-long row (:70-71)."""
+    num = max(min_masks, int(mask_prob * frames / float(mask_length) + rng.rand()))      # :37-38
+    rows = []
+    for _ in range(batch):
+        min_len = mask_length                                                            # :51-55 (all spans equal)
+        if frames - min_len <= num:
+            min_len = frames - num - 1                                                   # :56-57
+        start = rng.choice(frames - min_len, num, replace=False)                         # :59
+        idc = np.asarray([start[j] + o for j in range(num) for o in range(mask_length)]) # :60-66
+        rows.append(np.unique(idc[idc < frames]))                                        # :67
+    shortest = min(len(r) for r in rows)                                                 # :69
+    mask = np.full((batch, frames), False)
+    for i, r in enumerate(rows):
+        if len(r) > shortest:
+            r = rng.choice(r, shortest, replace=False)                                   # :71-72
+        mask[i, r] = True
+    return mask
+
+
+def audio_encoder(sd: SD, audio_norm: torch.Tensor, frame_num: int, spec_mask=None) -> torch.Tensor:
+    """ref:src/model/wav2vec.py:91-187 for dataset == "vocaset"; eval mode when spec_mask is None, otherwise the
+    training branch :149-162 with the given bool [B,T] time mask (dropout / LayerDrop stay off)."""
     h = feature_extractor(sd, audio_norm).transpose(1, 2)               # wav2vec.py:116-117
     h = linear_interpolation(h, frame_num)                              # wav2vec.py:125-128
     h = feature_projection(sd, h)                                       # wav2vec.py:147
+    if spec_mask is not None:
+        m = torch.as_tensor(np.asarray(spec_mask), dtype=torch.bool)[..., None]
+        h = torch.where(m, sd["audio_encoder.masked_spec_embed"].to(h.dtype), h)        # wav2vec.py:159-161
     return encoder(sd, h)                                               # wav2vec.py:174-180
 
 
@@ -281,14 +310,14 @@ def faceformer_decode(sd: SD, hidden_states: torch.Tensor, one_hot: torch.Tensor
 
 
 def faceformer_forward(sd: SD, audio: torch.Tensor, one_hot: torch.Tensor, template: torch.Tensor,
-                       fps: int = 60, return_parts: bool = False):
+                       fps: int = 60, return_parts: bool = False, spec_mask=None):
     """ref:src/model/faceformer.py:139-188 for one utterance: audio [1,N] raw 16 kHz, one_hot [1,n], template
     [1,5023,3] -> [1,T,5023,3].  fps=60 is the reference's hard-coded rate (faceformer.py:141); other values are the
     documented extension: only frame_num changes."""
     frame_num = audio.shape[1] * fps // 16000                           # faceformer.py:141
     audio_n = processor_normalize(audio.squeeze(0))[None]               # faceformer.py:142-144
     template = template.reshape(1, 1, -1)                               # faceformer.py:147
-    hs = audio_encoder(sd, audio_n, frame_num)                          # faceformer.py:149-151
+    hs = audio_encoder(sd, audio_n, frame_num, spec_mask)               # faceformer.py:149-151
     memory = F.linear(hs, sd["audio_feature_map.weight"], sd["audio_feature_map.bias"])   # faceformer.py:152
     vertice_out = faceformer_decode(sd, memory, one_hot, frame_num)
     out = (vertice_out + template).view(1, frame_num, -1, 3)            # faceformer.py:187-188

@@ -23,7 +23,7 @@ from . import ref_models as orm
 
 
 def faceformer_loss_and_grads(sd: Dict[str, torch.Tensor], audio: torch.Tensor, one_hot: torch.Tensor,
-                              template: torch.Tensor, gt: torch.Tensor, fps: int = 60
+                              template: torch.Tensor, gt: torch.Tensor, fps: int = 60, spec_mask=None
                               ) -> Tuple[Dict[str, float], Dict[str, torch.Tensor]]:
     """audio [B,N], one_hot [B,12], template [B,5023,3], gt [B,T,5023,3] (already in training units) ->
     ({"loss","rec_loss","vel_loss"} batch means, {param name: grad})."""
@@ -38,7 +38,8 @@ def faceformer_loss_and_grads(sd: Dict[str, torch.Tensor], audio: torch.Tensor, 
     loss_sum = None
     with torch.enable_grad():
         for b in range(B):
-            out = orm.faceformer_forward(params, audio[b:b + 1], one_hot[b:b + 1], template[b:b + 1], fps)
+            out = orm.faceformer_forward(params, audio[b:b + 1], one_hot[b:b + 1], template[b:b + 1], fps,
+                                         spec_mask=None if spec_mask is None else spec_mask[b:b + 1])
             l = orm.faceformer_loss(out, gt[b:b + 1])
             for k in tot:
                 tot[k] += float(l[k]) / B

@@ -116,6 +116,54 @@ def test_mha(a2f_lib, dev, B, T):
     assert _maxerr(out16, want16) < 3e-2
 
 
+@pytest.mark.parametrize("B,T", [(2, 1), (3, 17), (1, 128), (2, 129), (2, 150), (1, 257), (2, 600), (1, 1000), (1, 1801)])
+def test_mha_tcgen05(a2f_lib, dev, B, T):
+    """attention_tc.cu (tcgen05 / TMEM flash attention, the long-sequence kernel) forced on for every length: ragged
+    query and key tiles, one tile, many tiles; against fp64 softmax attention on the bf16-rounded inputs, and against
+    the mma.sync kernel (same tolerance as test_mha)."""
+    from a2f_b200 import ops, lib as L
+    g = torch.Generator().manual_seed(11)
+    qkv = torch.randn(B, T, 2304, generator=g)
+    qkv[:, :, :768] *= 2.0                                   # sharper softmax than unit logits
+    q16 = qkv.to(dev).bfloat16()
+    qb, kb, vb = [t.view(B, T, 12, 64).transpose(1, 2).double().cpu() for t in q16.float().split(768, dim=-1)]
+    want16 = (torch.softmax(qb @ kb.transpose(2, 3) * 0.125, -1) @ vb).transpose(1, 2).reshape(B, T, 768)
+    out_tc = torch.full((B, T, 768), float("nan"), device=dev, dtype=torch.bfloat16)
+    out_mma = torch.empty((B, T, 768), device=dev, dtype=torch.bfloat16)
+    try:
+        L.check(a2f_lib.a2f_debug_set_umma_field(6, 2))
+        ops.mha(q16, out_tc, B, T)
+        L.check(a2f_lib.a2f_debug_set_umma_field(6, 1))
+        ops.mha(q16, out_mma, B, T)
+    finally:
+        a2f_lib.a2f_debug_set_umma_field(6, 0)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out_tc.float()).all())
+    assert _maxerr(out_tc, want16) < 3e-2
+    assert _maxerr(out_tc, out_mma) < 3e-2
+    # mean error stays at bf16 output rounding level (catches a mis-scaled row sum that a max-error bound can hide)
+    assert float((out_tc.double().cpu() - want16).abs().mean()) < 2e-3
+
+
+def test_faceformer_long_clip_takes_tcgen05_attention(ff_model, ff_sd, dev, a2f_lib):
+    """12 s at 60 fps (T = 720 > the automatic switch-over length): the bf16 module output with the tcgen05 attention
+    kernel against the same module forced onto the mma.sync kernel, and both inside the 5e-4 m bf16 budget of each
+    other (units: cm, x100 templates)."""
+    from a2f_b200 import lib as L
+    n = 16000 * 12
+    audio, oh, tp = oin.audio(1, n, 3).to(dev), oin.one_hot(1, 12, 3).to(dev), oin.batch_templates(1, 3, scale=100.0).to(dev)
+    ff_model.set_precision("bf16")
+    with torch.no_grad():
+        y_auto = ff_model(audio, oh, tp).clone()
+        try:
+            L.check(a2f_lib.a2f_debug_set_umma_field(6, 1))
+            y_mma = ff_model(audio, oh, tp).clone()
+        finally:
+            a2f_lib.a2f_debug_set_umma_field(6, 0)
+    assert y_auto.shape == (1, 720, 5023, 3)
+    assert _maxerr(y_auto, y_mma) / 100.0 < 5e-4
+
+
 @pytest.mark.parametrize("T", [1, 7, 61, 130])
 def test_decoder_rollout_vs_oracle_loop(a2f_lib, dev, ff_sd, ff_model, T):
     """KV-cached persistent decode + collapsed feedback == the reference's prefix-recompute loop."""
