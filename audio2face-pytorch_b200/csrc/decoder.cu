@@ -12,18 +12,25 @@
 //   tid 256..383  linear1 rows (ffn 64->128, ReLU)            tid 384..511  linear2 rows, two 64-wide halves per row
 // The 64x64 feedback matrix Wc = vertice_map.weight @ vertice_map_r.weight (a2f_pack_feedback) sits transposed in
 // shared memory and is applied by threads 192..255.
-// K/V cache rows live in shared memory (padded to 68 floats: conflict-free float4 reads) when T <= 384, otherwise in
-// the L2-resident workspace.  The temporal bias -2^{-2(h+1)} * floor((i-j)/period) (ref:faceformer.py:22-54) and the
+// K/V cache rows live in shared memory (padded to 68 floats: conflict-free float4 reads) when T <= 360, otherwise in
+// the L2-resident workspace.
+// Long clips (T > 360, inference): one CTA reading a 1.8 MB K/V prefix per step is bound by a single SM's L2 read
+// bandwidth (15 us per step at T = 3600, profiles/r1_sweep_long.txt).  The CLUSTER instantiation spreads the keys of an
+// utterance over a thread-block cluster of C CTAs (key j belongs to rank j mod C): rank 0 runs the step as above,
+// broadcasts the scaled query into every CTA's shared memory (DSMEM), all ranks attend over their own keys straight
+// from L2 and hand (max, sum, P.V) partials back through rank 0's shared memory; two cluster barriers per step.  The temporal bias -2^{-2(h+1)} * floor((i-j)/period) (ref:faceformer.py:22-54) and the
 // periodic positional encoding row (i mod period) (ref:faceformer.py:70-88) are generated from indices.
 #include "a2f_common.cuh"
 #include "gemm_params.cuh"
 #include <cooperative_groups.h>
 
 namespace a2f {
+namespace cg = cooperative_groups;
 
 constexpr int DEC_THREADS = 512;
 constexpr int KV_LD = 68;
 constexpr int DEC_SMEM_T = 360;     // longest clip whose K/V cache fits in shared memory
+constexpr int DEC_CLUSTER_T = 900;  // automatic mode: clips from this length on spread their keys over a CTA cluster
 
 struct DecW {
     const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b;
@@ -65,7 +72,12 @@ struct DecSaves {
     float *X, *Q, *K, *V, *CTX, *Y1PRE, *Y2PRE, *Y2, *HID, *Y3PRE, *LSE;
 };
 
-template <bool TRAIN>
+// K/V rows written by another SM of the cluster: read through L2 (L1 is not coherent across SMs)
+template <bool CL> A2F_D float4 ld_kv4(const float* p) {
+    return CL ? __ldcg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
+}
+
+template <bool TRAIN, bool CL>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-attn vectors*/,
                        const float* __restrict__ one_hot, int n_onehot, int period, float* __restrict__ D, int T,
@@ -73,8 +85,12 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
     extern __shared__ __align__(16) float dsm[];
     pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x;
-    const int Tpad = (T + 3) & ~3;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = CL ? (int)cluster.num_blocks() : 1;          // CTAs per utterance
+    const int rank = CL ? (int)cluster.block_rank() : 0;        // this CTA owns the keys j with j % CS == rank
+    const int b = CL ? (int)blockIdx.x / CS : (int)blockIdx.x;
+    const bool lead = rank == 0;
+    const int Tpad = CL ? ((((T + CS - 1) / CS) + 3) & ~3) : ((T + 3) & ~3);    // score slots per head in this CTA
 
     // ---- shared memory carve-up ----
     float* xs = dsm;                 // [64]  decoder input of the current step (e_i + pe)
@@ -89,7 +105,8 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
     float* red = style + 64;         // [4][8] group reductions (max, sum) ; [4][4][16] PV partials after it
     float* pvp = red + 32;           // [4][4][16]
     float* wct = pvp + 256;          // [64][64] feedback matrix transposed: wct[k*64+r] = Wc[r][k]
-    float* sc = wct + 4096;          // [4][Tpad] scores / probabilities
+    float* cpart = wct + 4096;       // [8][4][20] cluster partials (max, sum, P.V[16]) per rank and head (rank 0's copy is read)
+    float* sc = cpart + 640;         // [4][Tpad] scores / probabilities
     float* Kc;
     float* Vc;
     if (kv_global) {
@@ -103,7 +120,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
     // ---- weights into registers ----
     float wr[64];
     float bias_r = 0.f;
-    {
+    if (lead) {
         const float* src;
         if (tid < 192) { src = w.sa_in_w + tid * 64; bias_r = w.sa_in_b[tid]; }
         else if (tid < 256) { src = w.sa_out_w + (tid - 192) * 64; bias_r = w.sa_out_b[tid - 192]; }
@@ -120,7 +137,8 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
         }
     }
     // feedback matrix (a2f_pack_feedback) transposed into shared memory; its rows are applied by threads 192..255
-    for (int idx = tid; idx < 4096; idx += DEC_THREADS) wct[(idx & 63) * 64 + (idx >> 6)] = w.fb_w[idx];
+    if (lead)
+        for (int idx = tid; idx < 4096; idx += DEC_THREADS) wct[(idx & 63) * 64 + (idx >> 6)] = w.fb_w[idx];
     const float fb_bias = (tid >= 192 && tid < 256) ? w.fb_b[tid - 192] : 0.f;
     // style embedding: obj_vector(one_hot), no bias (ref:faceformer.py:131,148); token 0 = style
     if (tid < 64) {
@@ -146,16 +164,21 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
     for (int i = 0; i < T; ++i) {
         // prefetch this step's global operands so that their latency hides behind phases 1-3
         float pre0 = 0.f, pre1 = 0.f;
-        if (tid >= 256 && tid < 384) {
+        if (!lead) {
+        } else if (tid >= 256 && tid < 384) {
             pre0 = __ldg(ca_b + (long long)i * 64 + lane);
             pre1 = __ldg(ca_b + (long long)i * 64 + lane + 32);
         } else if (tid >= 192 && tid < 256) {
             pre0 = __ldg(w.pe + ((i + 1) % period) * 64 + (tid - 192));
         }
         // ---------- phase 1: q, k, v of the new token ----------
-        if (tid < 192) {
+        if (lead && tid < 192) {
             const float acc = bias_r + dot64_smem(wr, xs);
-            if (tid < 64) qs[tid] = acc * 0.25f;                  // 1/sqrt(head_dim 16), exact power of two
+            if (tid < 64) {
+                qs[tid] = acc * 0.25f;                            // 1/sqrt(head_dim 16), exact power of two
+                if (CL)
+                    for (int rr = 1; rr < CS; ++rr) cluster.map_shared_rank(qs, rr)[tid] = acc * 0.25f;
+            }
             else if (tid < 128) Kc[(long long)i * KV_LD + (tid - 64)] = acc;
             else Vc[(long long)i * KV_LD + (tid - 128)] = acc;
             if (TRAIN) {
@@ -165,7 +188,8 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 else sv.V[o] = acc;
             }
         }
-        __syncthreads();
+        if (CL) cluster.sync();      // q has landed in every rank's shared memory, K/V row i is visible cluster-wide
+        else __syncthreads();
 
         // ---------- phase 2: biased causal attention over keys 0..i (threads 0..511, 4 warps per head) ----------
         // Flash-style split: warp wq of head h owns the keys {128m + 32wq + lane} and runs its own softmax
@@ -182,42 +206,46 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 qh[d] = f.x; qh[d + 1] = f.y; qh[d + 2] = f.z; qh[d + 3] = f.w;
             }
             float* sch = sc + h * Tpad;
+            // local key slot n <-> key j = rank + CS * n (one CTA: j = n); n_max = last slot that is <= i
+            const int n_max = (i >= rank) ? (i - rank) / CS : -1;
             float lmax = -INFINITY;
-            for (int j = u; j <= i; j += 128) {
+            for (int n = u; n <= n_max; n += 128) {
+                const int j = rank + CS * n;
                 const float* kp = Kc + (long long)j * KV_LD + h * 16;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
                 for (int d = 0; d < 16; d += 4) {
-                    const float4 f = *reinterpret_cast<const float4*>(kp + d);
+                    const float4 f = ld_kv4<CL>(kp + d);
                     a0 = fmaf(qh[d], f.x, a0);
                     a1 = fmaf(qh[d + 1], f.y, a1);
                     a2 = fmaf(qh[d + 2], f.z, a2);
                     a3 = fmaf(qh[d + 3], f.w, a3);
                 }
                 const float s = ((a0 + a1) + (a2 + a3)) - slope * (float)((i - j) / period);
-                sch[j] = s;
+                sch[n] = s;
                 lmax = fmaxf(lmax, s);
             }
             const float wmax = warp_max_redux(lmax);                  // -inf when this warp owns no key yet
             float lsum = 0.f;
-            for (int j = u; j <= i; j += 128) {
-                const float pj = expf(sch[j] - wmax);
-                sch[j] = pj;
+            for (int n = u; n <= n_max; n += 128) {
+                const float pj = expf(sch[n] - wmax);
+                sch[n] = pj;
                 lsum += pj;
             }
             __syncwarp();
             // P.V over this warp's keys: lane = (key slot kg, 4-wide column group dg); conflict-free float4 reads
             const int kg = lane & 7, dg = lane >> 3;
             float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-            for (int base = 32 * wq; base <= i; base += 128) {
-                const int nvalid = min(32, i - base + 1);
+            for (int base = 32 * wq; base <= n_max; base += 128) {
+                const int nvalid = min(32, n_max - base + 1);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int jj = kg + 8 * t;
                     if (jj < nvalid) {
-                        const int j = base + jj;
-                        const float pj = sch[j];
-                        const float4 v = *reinterpret_cast<const float4*>(Vc + (long long)j * KV_LD + h * 16 + dg * 4);
+                        const int n = base + jj;
+                        const int j = rank + CS * n;
+                        const float pj = sch[n];
+                        const float4 v = ld_kv4<CL>(Vc + (long long)j * KV_LD + h * 16 + dg * 4);
                         o0 = fmaf(pj, v.x, o0);
                         o1 = fmaf(pj, v.y, o1);
                         o2 = fmaf(pj, v.z, o2);
@@ -239,7 +267,34 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 red[h * 8 + 4 + wq] = lsum;
             }
             named_bar_sync(1 + h, 128);
-            if (u < 16) {
+            if (CL) {
+                // this rank's (max, sum, unnormalised P.V) of head h -> rank 0's shared memory
+                if (u < 16) {
+                    const float m0 = red[h * 8], m1 = red[h * 8 + 1], m2 = red[h * 8 + 2], m3 = red[h * 8 + 3];
+                    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    const float e0 = m0 == -INFINITY ? 0.f : expf(m0 - m), e1 = m1 == -INFINITY ? 0.f : expf(m1 - m);
+                    const float e2 = m2 == -INFINITY ? 0.f : expf(m2 - m), e3 = m3 == -INFINITY ? 0.f : expf(m3 - m);
+                    const float l = (e0 * red[h * 8 + 4] + e1 * red[h * 8 + 5]) + (e2 * red[h * 8 + 6] + e3 * red[h * 8 + 7]);
+                    const float* pp = pvp + h * 64 + u;
+                    float* dst = cluster.map_shared_rank(cpart, 0) + (rank * 4 + h) * 20;
+                    dst[2 + u] = (e0 * pp[0] + e1 * pp[16]) + (e2 * pp[32] + e3 * pp[48]);
+                    if (u == 0) { dst[0] = m; dst[1] = l; }
+                }
+                cluster.sync();
+                if (!lead) continue;         // ranks > 0 only attend; they meet rank 0 again at the next step's barrier
+                if (u < 16) {
+                    float m = -INFINITY;
+                    for (int rr = 0; rr < CS; ++rr) m = fmaxf(m, cpart[(rr * 4 + h) * 20]);
+                    float l = 0.f, cv = 0.f;
+                    for (int rr = 0; rr < CS; ++rr) {
+                        const float* cp = cpart + (rr * 4 + h) * 20;
+                        const float e = cp[0] == -INFINITY ? 0.f : expf(cp[0] - m);
+                        l = fmaf(e, cp[1], l);
+                        cv = fmaf(e, cp[2 + u], cv);
+                    }
+                    os[h * 16 + u] = cv / l;
+                }
+            } else if (u < 16) {
                 const float m0 = red[h * 8], m1 = red[h * 8 + 1], m2 = red[h * 8 + 2], m3 = red[h * 8 + 3];
                 const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 const float e0 = expf(m0 - m), e1 = expf(m1 - m), e2 = expf(m2 - m), e3 = expf(m3 - m);
@@ -381,9 +436,12 @@ pack_feedback_kernel(const float* __restrict__ vm_w, const float* __restrict__ v
     cluster.sync();                            // peers keep their shared memory alive until the leader has read it
 }
 
-static size_t dec_smem_bytes(int T, bool kv_in_smem) {
-    const int Tpad = (T + 3) & ~3;
-    size_t fl = 64 * 4 + 256 + 128 + 64 + 128 + 64 + 32 + 256 + 4096 + (size_t)4 * Tpad;
+static int g_dec_cluster = 0;      // debug (a2f_debug_set_umma_field 8): 0 = automatic, 1 = never, 2/4/8 = forced cluster size
+void set_dec_cluster(int v) { g_dec_cluster = v; }
+
+static size_t dec_smem_bytes(int T, bool kv_in_smem, int cluster = 1) {
+    const int Tpad = (((T + cluster - 1) / cluster) + 3) & ~3;
+    size_t fl = 64 * 4 + 256 + 128 + 64 + 128 + 64 + 32 + 256 + 4096 + 640 + (size_t)4 * Tpad;
     if (kv_in_smem) fl += (size_t)2 * T * KV_LD;
     return fl * sizeof(float);
 }
@@ -448,10 +506,41 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
     dw.n1_w = w->n1_w; dw.n1_b = w->n1_b; dw.n2_w = w->n2_w; dw.n2_b = w->n2_b; dw.n3_w = w->n3_w; dw.n3_b = w->n3_b;
     dw.fb_w = w->fb_w; dw.fb_b = w->fb_b; dw.obj_w = w->obj_w; dw.pe = w->pe;
     const size_t smem = dec_smem_bytes(T, kv == nullptr);
-    if (saves == nullptr) {
+    // long clips, inference: keys of one utterance spread over a cluster of CS CTAs (largest power of two that still
+    // gives every utterance its own cluster in one wave, at most 8 = the portable cluster size)
+    // Measured (profiles/r1_sweep_long.txt): the two cluster barriers cost ~0.8 us per step, the single CTA's L2-bound
+    // attention ~0.5 us per 100 keys: the cluster wins from T ~ 800 on.
+    int CS = 1;
+    if (saves == nullptr && kv != nullptr && g_dec_cluster != 1) {
+        if (g_dec_cluster > 1) CS = g_dec_cluster;
+        else if (T >= DEC_CLUSTER_T)
+            while (CS < 8 && 2 * CS * B <= sm_count()) CS *= 2;
+    }
+    if (CS > 1) {
         DecSaves none = {};
-        A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca, one_hot, n_onehot, period, D, T, kv, none));
+        auto kern = decoder_rollout_kernel<false, true>;
+        const size_t csmem = dec_smem_bytes(T, false, CS);
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(B * CS, 1, 1);
+        cfg.blockDim = dim3(DEC_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = csmem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, dw, (const float*)ca, one_hot, n_onehot, period, D, T, kv, none));
+    } else if (saves == nullptr) {
+        DecSaves none = {};
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca, one_hot, n_onehot, period, D, T, kv, none));
     } else {
         DecSaves sv;
         const size_t bt = (size_t)B * T;
@@ -462,8 +551,8 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
         sv.Y2PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y2PRE); sv.Y2 = f + bt * a2f_decoder_save_offset(A2F_DEC_Y2);
         sv.HID = f + bt * a2f_decoder_save_offset(A2F_DEC_HID); sv.Y3PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y3PRE);
         sv.LSE = f + bt * a2f_decoder_save_offset(A2F_DEC_LSE);
-        A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<true>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca, one_hot, n_onehot, period, D, T, kv, sv));
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<true, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca, one_hot, n_onehot, period, D, T, kv, sv));
     }
     A2F_CHECK_LAUNCH("decoder_rollout_kernel");
     count_launch();

@@ -1008,6 +1008,7 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
 namespace a2f {
 void set_mha_impl(int v);
 void set_mha_tc_min_t(int v);
+void set_dec_cluster(int v);
 }
 extern "C" int a2f_debug_set_timeline(void* dev_ptr) {
     a2f::g_timeline = static_cast<unsigned long long*>(dev_ptr);
@@ -1026,6 +1027,11 @@ extern "C" int a2f_debug_set_umma_field(int field, unsigned value) {
     if (field == 6) {   // encoder attention kernel: 0 = automatic, 1 = mma.sync, 2 = tcgen05
         if (value > 2) return a2f::set_error(A2F_EINVAL, "bad attention impl");
         a2f::set_mha_impl((int)value);
+        return A2F_OK;
+    }
+    if (field == 8) {   // decoder rollout on long clips: 0 = automatic cluster size, 1 = single CTA, 2/4/8 = forced
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return a2f::set_error(A2F_EINVAL, "bad cluster size");
+        a2f::set_dec_cluster((int)value);
         return A2F_OK;
     }
     if (field == 7) {   // automatic mode: shortest sequence that takes the tcgen05 attention kernel

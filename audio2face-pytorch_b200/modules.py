@@ -112,13 +112,14 @@ class _A2FModule(nn.Module):
             raise L.A2FError("autograd through this module is not available; call it under torch.no_grad()")
 
     def _vertex_head(self, z: torch.Tensor, weight: nn.Parameter, bias: nn.Parameter, template2d: torch.Tensor,
-                     rows_per_tmpl: int, k_live: int) -> torch.Tensor:
+                     rows_per_tmpl: int, k_live: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Shared K11 head: out = z @ W^T + b + template, out [M, V3] fp32.  z: fp32 [M, 64] (columns >= k_live zero).
 
         bf16 precision runs the tcgen05 GEMM on an error-compensated bf16 split (K' = 192: hi*hi + lo*hi + hi*lo), so
         the HBM-bound head keeps ~2^-16 relative accuracy while using the tensor cores."""
         M, v3 = z.shape[0], weight.shape[0]
-        out = torch.empty((M, v3), dtype=torch.float32, device=z.device)
+        if out is None:
+            out = torch.empty((M, v3), dtype=torch.float32, device=z.device)
         if self.precision == "bf16":
             def build():
                 w = torch.zeros((v3, 64), dtype=torch.float32, device=weight.device)
@@ -562,22 +563,26 @@ class Faceformer(_A2FModule):
             raise L.A2FError("audio too short for one output frame")
         one_hot = one_hot.reshape(B, -1).contiguous().float()
         tmpl = template.reshape(B, -1).contiguous().float()            # ref:faceformer.py:147
-        # utterances are independent: a batch holding more than `max_chunk_seconds` of audio runs in utterance chunks
-        # (bounds the conv0 activation, 16.4 MB bf16 per second of audio, and keeps element offsets inside int32)
+        # utterances are independent: a batch holding more than `max_chunk_seconds` of audio is ENCODED in utterance
+        # chunks (bounds the conv0 activation, 16.4 MB bf16 per second of audio, and keeps element offsets inside
+        # int32); the latency-bound decoder rollout then runs once for the whole batch (one CTA / cluster per utterance)
         per = max(1, int(min(float(kwargs.get("max_chunk_seconds", 480.0)) * 16000.0 / N, float(B))))
-        if B > per:
-            out = torch.empty((B, frame_num, self.vertice_dim // 3, 3), dtype=torch.float32, device=audio.device)
-            kw = dict(kwargs, max_chunk_seconds=float("inf"))
-            for b0 in range(0, B, per):
-                out[b0:b0 + per] = self.forward(audio[b0:b0 + per], one_hot[b0:b0 + per], tmpl[b0:b0 + per], **kw)
-            return out
         P = self._packed()
-        h = self.encode(audio, frame_num)
         M = B * frame_num
         memory = torch.empty((M, 64), dtype=torch.float32, device=audio.device)
-        ops.gemm(h, P["afm_w"], memory, bias=self.audio_feature_map.bias.detach(), backend=self._backend())
+        for b0 in range(0, B, per):
+            b1 = min(B, b0 + per)
+            h = self.encode(audio[b0:b1], frame_num)
+            ops.gemm(h, P["afm_w"], memory[b0 * frame_num:b1 * frame_num], bias=self.audio_feature_map.bias.detach(),
+                     backend=self._backend())
+            del h
         D = ops.decoder_rollout(P["dec"][0], memory, one_hot, self.period, B, frame_num)
-        out = self._vertex_head(D.view(M, 64), self.vertice_map_r.weight, self.vertice_map_r.bias, tmpl, frame_num, 64)
+        out = torch.empty((M, self.vertice_dim), dtype=torch.float32, device=audio.device)
+        hp = max(1, (1 << 17) // frame_num)                            # utterances per vertex-head launch (int32 offsets)
+        for b0 in range(0, B, hp):
+            b1 = min(B, b0 + hp)
+            self._vertex_head(D.view(M, 64)[b0 * frame_num:b1 * frame_num], self.vertice_map_r.weight, self.vertice_map_r.bias,
+                              tmpl[b0:b1], frame_num, 64, out=out[b0 * frame_num:b1 * frame_num])
         return out.view(B, frame_num, -1, 3)                           # ref:faceformer.py:187-188
 
     def predict(self, audio, one_hot, template, **kwargs):

@@ -181,6 +181,33 @@ def test_decoder_rollout_vs_oracle_loop(a2f_lib, dev, ff_sd, ff_model, T):
         assert _maxerr(got, want) < 2e-5, (b, T)
 
 
+@pytest.mark.parametrize("T", [361, 777])
+def test_decoder_rollout_cluster_vs_single_cta_and_oracle(a2f_lib, dev, ff_sd, ff_model, T):
+    """Long clips (K/V cache in L2): keys spread over a thread-block cluster of 2 / 4 / 8 CTAs (DSMEM query broadcast,
+    partial-softmax merge in rank 0) against the single-CTA rollout, and the single-CTA rollout against the oracle's
+    prefix-recompute loop with the biased mask / PPE rebuilt at the needed length."""
+    from a2f_b200 import ops, lib as L
+    B = 3
+    g = torch.Generator().manual_seed(12)
+    mem = torch.randn(B, T, 64, generator=g)
+    oh = oin.one_hot(B, 12, 12)
+    ff_model.set_precision("fp32")
+    P = ff_model._packed()
+    outs = {}
+    try:
+        for cs in (1, 2, 4, 8, 0):
+            L.check(a2f_lib.a2f_debug_set_umma_field(8, cs))
+            outs[cs] = ops.decoder_rollout(P["dec"][0], mem.to(dev).contiguous(), oh.to(dev), 60, B, T).cpu()
+    finally:
+        a2f_lib.a2f_debug_set_umma_field(8, 0)
+    for cs in (2, 4, 8, 0):
+        assert bool(torch.isfinite(outs[cs]).all())
+        assert _maxerr(outs[cs], outs[1]) < 2e-5, cs              # LayerNorm-ed states are O(1): fp32 summation order only
+    want = orm.faceformer_decode(ff_sd, mem[:1], oh[:1], T)[0]
+    got = outs[8][0] @ ff_sd["vertice_map_r.weight"].T + ff_sd["vertice_map_r.bias"]
+    assert _maxerr(got, want) < 5e-5
+
+
 # ------------------------------------------------------------------------------------------------- module
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_faceformer_fp32_matches_golden_and_oracle(ff_model, ff_sd, dev, tag):
