@@ -13,10 +13,11 @@
 //     warp 1       MMA issuer (one lane): S = Q K^T  -> TMEM columns   0..127 (M=128, N=128, K=64: 4 tcgen05.mma)
 //                                         O_j = P V  -> TMEM columns 128..191 (M=128, N=64, K=128: 8 tcgen05.mma),
 //                  V is consumed IN PLACE as an MN-major operand (keys are the reduction rows), P from shared memory.
-//     warps 2..5   softmax: thread = query row = TMEM lane.  Pass 1 over S finds the row maximum, pass 2 exponentiates
-//                  (ex2.approx on pre-scaled logits), accumulates the row sum and writes bf16 P into the K-major
-//                  128B-swizzled layout the P V MMA reads.  O_j comes back from TMEM once per key tile and is folded into
-//                  a register accumulator with the usual online-softmax rescale (no TMEM read-modify-write).
+//     warps 2..5   softmax: thread = query row = TMEM lane.  The S row comes into registers with one TMEM round trip
+//                  (S is released at once, so Q K^T of the next tile overlaps the exponentials), ex2.approx on
+//                  pre-scaled logits, row sum, bf16 P into the K-major 128B-swizzled layout the P V MMA reads.
+//                  O stays in TMEM across key tiles (accumulating MMAs); it is rescaled only when the running row
+//                  maximum has grown by more than 2^8 (lazy online softmax), one tcgen05.ld / st round trip.
 //   Probabilities never leave the SM (the reference materialises and returns [B,12,T,T] for 12 layers,
 //   ref:src/model/wav2vec.py:101).
 //
@@ -151,7 +152,7 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, bf16* __restrict__ ou
                 for (int kk = 0; kk < FT_BN / 16; ++kk) {
                     const uint64_t pd = (kk < 4 ? pdesc0 : pdesc1) + (uint64_t)(2 * (kk & 3));
                     // 16 keys = 2 groups of 8 rows x 128 B = 2048 B: +128 in the >>4 address field
-                    umma_f16(t_o, pd, vdesc + (uint64_t)(128 * kk), idesc_pv, kk != 0 ? 1u : 0u);
+                    umma_f16(t_o, pd, vdesc + (uint64_t)(128 * kk), idesc_pv, (j | kk) != 0 ? 1u : 0u);
                 }
                 umma_commit(&v_empty[s]);
                 umma_commit(o_full);
@@ -165,107 +166,110 @@ mha_tc_kernel(const __grid_constant__ CUtensorMap qkv_map, bf16* __restrict__ ou
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
         uint8_t* prow = sP + r * 128;
         const int sw = r & 7;
-        float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-        float o[FT_D];
-#pragma unroll
-        for (int i = 0; i < FT_D; ++i) o[i] = 0.f;
-
-        auto fold_o = [&](float a) {                       // o = o * a + O_j (TMEM columns 128..191)
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                float v[32];
-                tmem_ld_32x32(t_row + 128 + cc * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[cc * 32 + i] = fmaf(o[cc * 32 + i], a, v[i]);
-            }
-        };
+        // O accumulates in TMEM across key tiles (the P V MMAs run with accumulate = 1).  `m_used` is the row maximum
+        // that O and the row sum l are currently expressed against; it only moves (and O is only rescaled, a
+        // tcgen05.ld / st round trip) when the running maximum has grown by more than 2^8 -- probabilities stay
+        // below 256, far inside bf16 / fp32 range, and after the first tiles the rescale almost never triggers.
+        float m_used = 0.f, l = 0.f;
 
         for (int j = 0; j < n_kv; ++j) {
             const int valid = min(FT_BN, T - j * FT_BN);   // live keys of this tile (uniform)
             mbar_wait(s_full, (uint32_t)j & 1u);
             tc_fence_after();
-            // ---- pass 1: row maximum of the raw logits ----
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                if (cc * 32 >= valid) break;
-                float v[32];
-                tmem_ld_32x32(t_row + cc * 32, v);
-                tmem_ld_wait();
-                if (cc * 32 + 32 <= valid) {
+            // ---- the whole S row into registers with one TMEM round trip, then release S for Q K^T_{j+1} ----
+            float v[FT_BN];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
-                } else {
+            for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32(t_row + cc * 32, v + cc * 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
+            if (valid < FT_BN) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (cc * 32 + i < valid) mx = fmaxf(mx, v[i]);
-                }
+                for (int i = 0; i < FT_BN; ++i)
+                    if (i >= valid) v[i] = -INFINITY;     // keys past T (zero-filled by TMA): exp2(-inf) = 0
             }
-            const float m_new = fmaxf(m, mx);
-            const float alpha = ex2_approx((m - m_new) * c);        // first tile: exp2(-inf) = 0
-            const float mc = m_new * c;
-            // ---- O_{j-1} back from TMEM (also proves P V_{j-1} is done with the P buffer) ----
+            float mx0 = v[0], mx1 = v[1], mx2 = v[2], mx3 = v[3];
+#pragma unroll
+            for (int i = 4; i < FT_BN; i += 4) {
+                mx0 = fmaxf(mx0, v[i]);
+                mx1 = fmaxf(mx1, v[i + 1]);
+                mx2 = fmaxf(mx2, v[i + 2]);
+                mx3 = fmaxf(mx3, v[i + 3]);
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            float alpha = 1.f;
+            bool rescale = false;
+            if (j == 0) {
+                m_used = mx;
+            } else if ((mx - m_used) * c > 8.0f) {
+                alpha = ex2_approx((m_used - mx) * c);
+                m_used = mx;
+                rescale = true;
+            }
+            const float mc = m_used * c;
+            // ---- p = 2^(s*c - m*c), row sum, packed to bf16 ----
+            uint32_t pk[FT_BN / 2];
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < FT_BN; i += 2) {
+                const float p0 = ex2_approx(fmaf(v[i], c, -mc));
+                const float p1 = ex2_approx(fmaf(v[i + 1], c, -mc));
+                s0 += p0;
+                s1 += p1;
+                pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+            l = fmaf(l, alpha, s0 + s1);
+            // ---- P V_{j-1} must have retired before P is overwritten / O is rescaled ----
             if (j > 0) {
                 mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
                 tc_fence_after();
-                fold_o(alpha_prev);
-            }
-            // ---- pass 2: p = 2^(s*c - m*c), row sum, bf16 P into the swizzled K-major layout ----
-            float sum = 0.f;
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                uint32_t pk[16];
-                if (cc * 32 < valid) {
-                    float v[32];
-                    tmem_ld_32x32(t_row + cc * 32, v);
-                    tmem_ld_wait();
-                    if (cc * 32 + 32 <= valid) {
+                if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = ex2_approx(fmaf(v[i], c, -mc));
-                    } else {
+                    for (int cc = 0; cc < 2; ++cc) {
+                        float o[32];
+                        tmem_ld_32x32(t_row + 128 + cc * 32, o);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = (cc * 32 + i < valid) ? ex2_approx(fmaf(v[i], c, -mc)) : 0.f;
+                        for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                        tmem_st_32x32(t_row + 128 + cc * 32, o);
                     }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        sum += v[i] + v[i + 1];
-                        pk[i >> 1] = pack_bf16x2(v[i], v[i + 1]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                    tmem_st_wait();
                 }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
                 uint8_t* blk = prow + (cc >> 1) * FT_TILE_BYTES;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                     const int pch = ((cc & 1) * 4 + ch) ^ sw;
-                    *reinterpret_cast<uint4*>(blk + pch * 16) = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+                    *reinterpret_cast<uint4*>(blk + pch * 16) =
+                        make_uint4(pk[cc * 16 + ch * 4], pk[cc * 16 + ch * 4 + 1], pk[cc * 16 + ch * 4 + 2], pk[cc * 16 + ch * 4 + 3]);
                 }
             }
-            l = fmaf(l, alpha, sum);
-            m = m_new;
-            alpha_prev = alpha;
             fence_proxy_async_smem();          // P (generic-proxy stores) visible to the tensor core's async proxy
             tc_fence_before();
-            mbar_arrive(s_free);
             mbar_arrive(p_full);
         }
         mbar_wait(o_full, (uint32_t)(n_kv - 1) & 1u);
         tc_fence_after();
-        fold_o(alpha_prev);
         const int row = q0 + r;
-        if (row < T) {
-            const float inv = 1.0f / l;
-            bf16* dst = out + ((long long)b * T + row) * (H * FT_D) + h * FT_D;
+        const float inv = 1.0f / l;
+        bf16* dst = out + ((long long)b * T + row) * (H * FT_D) + h * FT_D;
 #pragma unroll
-            for (int i = 0; i < FT_D; i += 8) {
-                uint4 u;
-                u.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
-                u.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
-                u.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
-                u.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
-                *reinterpret_cast<uint4*>(dst + i) = u;
+        for (int cc = 0; cc < 2; ++cc) {
+            float o[32];
+            tmem_ld_32x32(t_row + 128 + cc * 32, o);
+            tmem_ld_wait();
+            if (row < T) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 u;
+                    u.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
+                    u.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
+                    u.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
+                    u.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+                    *reinterpret_cast<uint4*>(dst + cc * 32 + i) = u;
+                }
             }
         }
     }

@@ -78,12 +78,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         raise L.A2FError("tmpl must be fp32")
     if a.dtype != w.dtype:
         raise L.A2FError("A and W must share a dtype")
-    if PROFILE is not None and backend == L.TCGEN05:
+    if PROFILE is not None:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         L.check(lib.a2f_gemm(C.byref(g), backend, _stream()), "a2f_gemm")
         e.record()
-        PROFILE.append(("gemm_tc", 2.0 * g.M * g.N * g.K, s, e))
+        PROFILE.append(("gemm_tc" if backend == L.TCGEN05 else "gemm_simt", 2.0 * g.M * g.N * g.K, s, e))
         return out
     L.check(lib.a2f_gemm(C.byref(g), backend, _stream()), "a2f_gemm")
     return out

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 audio->mesh hot path (contract in the task prompt / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload faceformer|voca]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload faceformer|faceformer_train|audio2mesh|voca]      (configs[2] | [3] | [1] | [0]-shaped)
+    (configs[4], the long-sequence sweep: tools/sweep_long.py)
 
 Workload (BASELINE.json configs[2], the largest single-GPU inference configuration): FaceFormer inference,
 random-init wav2vec2-base encoder + 1-layer biased causal decoder, batch 32 x 5 s synthetic 16 kHz audio at 30 fps,
@@ -131,6 +133,18 @@ def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: i
             dt = time.perf_counter() - t0
             return T / dt, (f"1 utterance x {seconds:g} s @ {fps} fps: forward + FaceFormerLoss + autograd backward, fp32, "
                             "reference O(T^2) decode loop (no optimizer step)")
+        if workload == "audio2mesh":
+            sd = ow.make_state_dict("audio2mesh", 12)
+            B = 64
+            x, oh, tp = oin.a2m_features(B, 1), oin.one_hot(B, 12, 1), oin.batch_templates(B, 1)
+            orm.audio2mesh_forward(sd, x, oh, tp)
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 5.0:
+                orm.audio2mesh_forward(sd, x, oh, tp)
+                reps += 1
+            dt = time.perf_counter() - t0
+            return reps * B / dt, f"{reps} x {B} windows, fp32, eval-mode BatchNorm"
         sd = ow.make_state_dict("voca", 11)
         B = 4096
         x, oh, tp = oin.voca_features(B, 1), oin.one_hot(B, 12, 1), oin.batch_templates(B, 1)
@@ -191,6 +205,11 @@ def workload_config(args):
                 "weights": "random-init (oracle.weights seed 13, heads de-zeroed)",
                 "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
                 "template_units": "centimetres (x100, ref lightning_model.py:145-148)", "launch": "eager"}
+    if args.workload == "audio2mesh":
+        return {"workload": f"audio2mesh_inference_b{args.batch}_windows (BASELINE.json configs[1])", "batch_per_gpu": args.batch,
+                "window": "52 x 32 MFCC", "vertices": 5023, "weights": "random-init (oracle.weights seed 12, randomised BatchNorm stats)",
+                "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
+                "launch": "eager" if args.no_graph else "one CUDA graph per forward (modules.GraphedForward)"}
     return {"workload": f"voca_inference_b{args.batch} (BASELINE.json configs[0] shape)", "batch_per_gpu": args.batch,
             "vertices": 5023, "weights": "random-init (oracle.weights seed 11)",
             "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)"}
@@ -228,6 +247,16 @@ def run_ours(args):
         flops_step = B * ff_flops_per_utt(n, T)
         call = lambda a, o, t: model(a, o, t, fps=args.fps)      # noqa: E731
         out_shape = (B, T, 5023, 3)
+    elif args.workload == "audio2mesh":
+        model = modules.Audio2Mesh(15069, 12)
+        model.load_state_dict(ow.make_state_dict("audio2mesh", 12), strict=True)
+        model = model.to(dev).eval().set_precision("bf16")
+        h_in = [oin.a2m_features(B, 100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(),
+                oin.batch_templates(B, 100 + rank).pin_memory()]
+        units = B
+        flops_step = B * 131.0e6                                 # 131.0 MFLOP per window
+        call = lambda a, o, t: model(a, o, t)                    # noqa: E731
+        out_shape = (B, 5023, 3)
     else:
         model = modules.Voca(15069, 12)
         model.load_state_dict(ow.make_state_dict("voca", 11), strict=True)
@@ -336,12 +365,32 @@ def run_ours(args):
         g_flops = sum(f for f, _ in gem)
         g_time = sum(t for _, t in gem)
         achieved = g_flops / g_time / 1e12
-        roofline = {"bound": "tensor", "kernel": "a2f::gemm_tc_kernel (tcgen05/TMEM/TMA GEMM, all launches of a step)",
+        # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's tcgen05 GEMM launches)
+        # from the committed ncu pass of this same shape; null for any other shape
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic_infer.json")
+        if os.path.exists(tpath) and B == 32 and args.fps == 30 and args.seconds == 5.0:
+            tj = json.load(open(tpath))
+            traffic = tj["gemm_tc_all"]["dram_bytes_per_launch"]
+            traffic_src = "profiles/r1_traffic_infer.json (bytes per launch, mean over %d launches)" % tj["gemm_tc_all"]["launches"]
+        roofline = {"bound": "tensor", "kernel": "a2f::gemm_tc2_kernel / gemm_tc_kernel (tcgen05/TMEM/TMA GEMMs, all launches of a step)",
                     "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                    "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"] + ", sustained bf16",
                     "launches_per_step": len(gem) // 2, "kernel_share_of_step": (g_time / 2) / (dev_s / args.steps),
                     "whole_step_tflops": flops_step * world * args.steps / dev_s / 1e12,
                     "whole_step_frac": flops_step * world * args.steps / dev_s / 1e12 / (pk["bf16_sustained"] * world)}
+    elif args.workload == "audio2mesh":
+        # the ten convolutions + FC layers run as fp32 implicit GEMMs (a2f::gemm_simt_kernel); roofline = fp32 FMA
+        gem = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind in ("gemm_simt", "gemm_tc")]
+        g_flops, g_time = sum(f for f, _ in gem), sum(t for _, t in gem)
+        achieved = g_flops / g_time / 1e12
+        fp32_peak = 148 * 128 * 2 * 1.965e-3                     # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz = 74.4 TFLOP/s
+        roofline = {"bound": "tensor", "kernel": "a2f::gemm_simt_kernel (fp32 implicit-GEMM convolutions + FC layers, all launches of a step)",
+                    "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                    "peak_source": "fp32 FMA peak of the SIMT path (148 SMs x 128 lanes x 2 x 1.965 GHz); the bf16 tensor peak "
+                                   f"would be {pk['bf16_sustained']} TFLOP/s", "launches_per_step": len(gem) // 2,
+                    "kernel_share_of_step": (g_time / 2) / (dev_s / args.steps),
+                    "whole_step_tflops": flops_step * world * args.steps / dev_s / 1e12}
     else:
         head = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind == "gemm_tc"]
         byts = 2 * (B * 15069 * 4) * len(head)            # template read + vertex write per launch
@@ -500,7 +549,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "faceformer_train"])
+    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "audio2mesh", "faceformer_train"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--fps", type=int, default=None)
@@ -511,7 +560,7 @@ def main():
     if args.fps is None:
         args.fps = 60 if args.workload == "faceformer_train" else 30
     if args.batch is None:
-        args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384}[args.workload]
+        args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384, "audio2mesh": 64}[args.workload]
     if args.impl == "reference":
         run_reference(args)
         return
