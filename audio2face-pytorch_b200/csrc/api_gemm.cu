@@ -49,21 +49,23 @@ __global__ void posconv_norm_kernel(const float* __restrict__ v, float* __restri
     }
 }
 // out[g][n][tap][c (kpad)] = g[tap] * v[g*48+n, c, tap] / norm[tap]   (c >= 48 -> 0)
+// kpad == 8: the chunked layout of posconv_tc.cu, out[g][tap][c/8][n][c%8] (shared-memory image of one tap's B operand).
 // torch's _weight_norm computes v * (g / norm): same association here.
 template <typename TO>
 __global__ void posconv_pack_kernel(const float* __restrict__ gw, const float* __restrict__ v,
                                     const float* __restrict__ norm, TO* __restrict__ out, int kpad) {
-    const long long n = (long long)768 * 128 * kpad;
+    const int kp = kpad == 8 ? 48 : kpad;
+    const long long n = (long long)768 * 128 * kp;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        int c = (int)(i % kpad);
-        long long r = i / kpad;
+        int c = (int)(i % kp);
+        long long r = i / kp;
         int tap = (int)(r % 128);
         int o = (int)(r / 128);   // g*48 + n
         float val = 0.f;
         if (c < 48) val = v[((long long)o * 48 + c) * 128 + tap] * (gw[tap] / norm[tap]);
-        st_from_float(out + i, val);
+        st_from_float(out + (kpad == 8 ? posconv_chunked_index(o / 48, o % 48, tap, c) : i), val);
     }
 }
 
@@ -89,6 +91,12 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ in, long long ld_i
         o[2 * K + k] = is_weight ? lo : hi;
     }
 }
+
+// positional-conv implementation of the tcgen05 backend: 0 = posconv_tc.cu (chunked weight layout, kpad 8),
+// 1 = legacy gemm_tc mode 2 (kpad 64).  a2f_debug_set_umma_field(9, v); the packers must be called with the matching kpad.
+static int g_posconv_impl = 0;
+int posconv_impl() { return g_posconv_impl; }
+void set_posconv_impl(int v) { g_posconv_impl = v; }
 
 static int fill_params(const a2f_gemm_args* a, GemmParams* p) {
     A2F_REQUIRE(a != nullptr, "a2f_gemm: args is NULL");
@@ -197,6 +205,10 @@ int a2f_posconv(const void* h, int h_dtype, const void* Wp, const float* bias, v
         return posconv_simt(p, h_dtype == A2F_BF16, out_dtype == A2F_BF16, as_stream(stream));
     } else if (backend == A2F_BACKEND_TCGEN05) {
         A2F_REQUIRE(h_dtype == A2F_BF16, "a2f_posconv: the tcgen05 backend takes bf16 activations");
+        if (posconv_impl() == 0) {
+            A2F_REQUIRE(out_dtype == A2F_BF16, "a2f_posconv: the tcgen05 backend writes bf16");
+            return posconv_tc(h, Wp, bias, nullptr, 1, out, B, T, -64, A2F_ACT_GELU, as_stream(stream));
+        }
         p.K = 128 * 64; p.ldw = 128 * 64;
         return gemm_tc(p, out_dtype == A2F_BF16, 2, as_stream(stream));
     }
@@ -216,6 +228,8 @@ static int posconv_common(GemmParams& p, const void* a, int dtype, const void* W
         return posconv_simt(p, dtype == A2F_BF16, dtype == A2F_BF16, s);
     } else if (backend == A2F_BACKEND_TCGEN05) {
         A2F_REQUIRE(dtype == A2F_BF16, "posconv: the tcgen05 backend takes bf16 activations");
+        if (posconv_impl() == 0)
+            return posconv_tc(a, W, p.bias, p.resid, p.resid ? 2 : 0, out, B, T, -64 + p.seg_row_off[0], p.act, s);
         p.K = 128 * 64; p.ldw = 128 * 64;
         return gemm_tc(p, 1, 2, s);
     }
@@ -273,11 +287,11 @@ int a2f_pack_posconv_weight(const float* g, const float* v, void* out, int out_d
                             void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
-    A2F_REQUIRE(g && v && out && norm_scratch && (kpad == 48 || kpad == 64), "a2f_pack_posconv_weight: bad arguments");
+    A2F_REQUIRE(g && v && out && norm_scratch && (kpad == 48 || kpad == 64 || kpad == 8), "a2f_pack_posconv_weight: bad arguments");
     float* norm = norm_scratch;
     posconv_norm_kernel<<<128, 256, 0, as_stream(stream)>>>(v, norm);
     A2F_CHECK_LAUNCH("posconv_norm_kernel");
-    const long long n = (long long)768 * 128 * kpad;
+    const long long n = (long long)768 * 128 * (kpad == 8 ? 48 : kpad);
     const int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
     if (out_dtype == A2F_BF16)
         posconv_pack_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(g, v, norm, static_cast<bf16*>(out), kpad);

@@ -57,6 +57,13 @@ int gemm_simt(const GemmParams& p, int a_bf16, int c_bf16, cudaStream_t s);
 int posconv_simt(const GemmParams& p, int a_bf16, int c_bf16, cudaStream_t s);
 // tcgen05 back end (bf16 operands).  mode 0: plain / strided-row implicit GEMM, mode 2: positional conv.
 int gemm_tc(const GemmParams& p, int c_bf16, int mode, cudaStream_t s);
+// dedicated positional-conv kernel (posconv_tc.cu): bf16 channels-last [B,T,768] in / out, chunked weight layout
+int posconv_tc(const void* A, const void* W, const float* bias, const void* resid, int resid_mode, void* C, int B, int T,
+               int row_off, int act, cudaStream_t s);
+// element index of (group, n, tap, c) in the chunked layout [16][128 taps][6 chunks][48 n][8]
+A2F_HD long long posconv_chunked_index(int grp, int n, int tap, int c) {
+    return ((((long long)grp * 128 + tap) * 6 + (c >> 3)) * 48 + n) * 8 + (c & 7);
+}
 int wgrad_simt(const WgradParams& p, int bf16_in, cudaStream_t s);
 int wgrad_tc(const WgradParams& p, cudaStream_t s);
 

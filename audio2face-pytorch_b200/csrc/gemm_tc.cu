@@ -1009,6 +1009,8 @@ namespace a2f {
 void set_mha_impl(int v);
 void set_mha_tc_min_t(int v);
 void set_dec_cluster(int v);
+void set_posconv_impl(int v);
+void set_posconv_swap(int v);
 }
 extern "C" int a2f_debug_set_timeline(void* dev_ptr) {
     a2f::g_timeline = static_cast<unsigned long long*>(dev_ptr);
@@ -1036,6 +1038,14 @@ extern "C" int a2f_debug_set_umma_field(int field, unsigned value) {
     }
     if (field == 7) {   // automatic mode: shortest sequence that takes the tcgen05 attention kernel
         a2f::set_mha_tc_min_t((int)value);
+        return A2F_OK;
+    }
+    if (field == 9) {   // positional conv of the tcgen05 backend: 0 = posconv_tc.cu (kpad 8 weights), 1 = legacy mode 2 (kpad 64)
+        a2f::set_posconv_impl(value ? 1 : 0);
+        return A2F_OK;
+    }
+    if (field == 10) {  // posconv_tc.cu: exchange the LBO / SBO descriptor fields (bring-up experiment)
+        a2f::set_posconv_swap(value ? 1 : 0);
         return A2F_OK;
     }
     if (field == 4) {   // force tile width (0 = automatic)

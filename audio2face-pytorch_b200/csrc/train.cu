@@ -558,12 +558,13 @@ __global__ void __launch_bounds__(256) wn_apply_kernel(const float* __restrict__
 template <typename TO>
 __global__ void posconv_pack_dgrad_kernel(const float* __restrict__ gw, const float* __restrict__ v,
                                           const float* __restrict__ norm, TO* __restrict__ out, int kpad) {
-    const long long n = (long long)768 * 128 * kpad;
+    const int kp = kpad == 8 ? 48 : kpad;      // kpad 8: chunked layout of posconv_tc.cu
+    const long long n = (long long)768 * 128 * kp;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const int co = (int)(i % kpad);
-        long long r = i / kpad;
+        const int co = (int)(i % kp);
+        long long r = i / kp;
         const int tapp = (int)(r % 128);
         r /= 128;                    // g*48 + ci
         const int ci = (int)(r % 48), grp = (int)(r / 48);
@@ -572,7 +573,7 @@ __global__ void posconv_pack_dgrad_kernel(const float* __restrict__ gw, const fl
             const int tap = 127 - tapp;
             val = v[((long long)(grp * 48 + co) * 48 + ci) * 128 + tap] * (gw[tap] / norm[tap]);
         }
-        st_from_float(out + i, val);
+        st_from_float(out + (kpad == 8 ? posconv_chunked_index(grp, ci, tapp, co) : i), val);
     }
 }
 
@@ -852,7 +853,7 @@ int a2f_pack_posconv_dgrad_weight(const float* g, const float* v, void* out, int
                                   void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
-    A2F_REQUIRE(g && v && out && norm && (kpad == 48 || kpad == 64), "a2f_pack_posconv_dgrad_weight: bad arguments");
+    A2F_REQUIRE(g && v && out && norm && (kpad == 48 || kpad == 64 || kpad == 8), "a2f_pack_posconv_dgrad_weight: bad arguments");
     // norm[128] must already hold ||v[:,:,tap]|| (a2f_pack_posconv_weight fills it)
     cudaStream_t s = as_stream(stream);
     const int grid = ew_grid(768LL * 128 * kpad);

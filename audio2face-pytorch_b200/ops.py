@@ -188,11 +188,19 @@ def pack_conv1d_weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
+def posconv_weight_shape(dtype: torch.dtype):
+    """(kpad code, packed shape): fp32 SIMT layout [16][48 out][128 taps][48 in]; bf16 tcgen05 layout of posconv_tc.cu
+    [16][128 taps][6 chunks][48 out][8 in] (kpad code 8)."""
+    if dtype == torch.bfloat16:
+        return 8, (16, 128, 6, 48, 8)
+    return 48, (16, 48, 128, 48)
+
+
 def pack_posconv_weight(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _dev(g, v)
-    kpad = 64 if dtype == torch.bfloat16 else 48
+    kpad, shape = posconv_weight_shape(dtype)
     if out is None:
-        out = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+        out = torch.empty(shape, dtype=dtype, device=v.device)
     norm = torch.empty(128, dtype=torch.float32, device=v.device)
     L.check(L.load().a2f_pack_posconv_weight(g.contiguous().data_ptr(), v.contiguous().data_ptr(), out.data_ptr(), _dt(out),
                                              kpad, norm.data_ptr(), _stream()), "a2f_pack_posconv_weight")
@@ -512,11 +520,11 @@ def conv0_bwd(audio, stats, w, gamma, beta, ws, da, dw, dgamma, dbeta):
 def pack_posconv_weights_train(g: torch.Tensor, v: torch.Tensor, dtype: torch.dtype, out=None):
     """-> (forward packed weight, data-gradient packed weight)"""
     _dev(g, v)
-    kpad = 64 if dtype == torch.bfloat16 else 48
+    kpad, shape = posconv_weight_shape(dtype)
     lib = L.load()
     if out is None:
-        fwd = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
-        bwd = torch.empty((16, 48, 128, kpad), dtype=dtype, device=v.device)
+        fwd = torch.empty(shape, dtype=dtype, device=v.device)
+        bwd = torch.empty(shape, dtype=dtype, device=v.device)
     else:
         fwd, bwd = out
     norm = torch.empty(128, dtype=torch.float32, device=v.device)

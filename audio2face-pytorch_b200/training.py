@@ -81,8 +81,8 @@ def packed_backward_weights(model) -> Dict:
         P["convs"] = convs
         P["proj_t"] = T_(ae.feature_projection.projection.weight)             # [512,768]
         pz = ae.encoder.pos_conv_embed.conv.parametrizations.weight
-        kpad = 64 if bf else 48
-        P["pos_fwd"], P["pos_bwd"] = new(16, 48, 128, kpad), new(16, 48, 128, kpad)
+        _, pshape = ops.posconv_weight_shape(dt)
+        P["pos_fwd"], P["pos_bwd"] = new(*pshape), new(*pshape)
         lay = []
         for blk in ae.encoder.layers:
             a = blk.attention

@@ -135,13 +135,16 @@ int a2f_gemm_wgrad(const a2f_wgrad_args* args, int backend, void* stream);
 /* ------------------------------------------------------------------------------------------------------------
  * wav2vec2 positional conv embedding (HF modeling_wav2vec2.py:326-379,690-693 via ref:src/model/wav2vec.py:174):
  *   out[b,t,:] = h[b,t,:] + gelu( grouped_conv1d_k128_pad64_g16(h)[b,t,:] + bias )      (last conv step dropped)
- * h, out: channels-last [B,T,768].  Wp: packed weight [16 groups][48 out][128 taps][kpad in] produced by
- * a2f_pack_posconv_weight (kpad = 48 for the SIMT backend, 64 zero-padded for the tcgen05 backend).
+ * h, out: channels-last [B,T,768].  Wp: packed weight produced by a2f_pack_posconv_weight:
+ *   SIMT backend     kpad = 48: fp32 [16 groups][48 out][128 taps][48 in]
+ *   tcgen05 backend  kpad = 8:  bf16 [16 groups][128 taps][6 chunks][48 out][8 in] -- per tap the shared-memory image of
+ *                    the UMMA B operand (K-major, no swizzle), streamed by 1-D bulk copies (csrc/posconv_tc.cu); bf16 in/out
+ *   (kpad = 64, bf16 [16][48][128][64 zero-padded]: the generic-GEMM path kept behind a2f_debug_set_umma_field(9, 1))
  * ---------------------------------------------------------------------------------------------------------- */
 int a2f_posconv(const void* h, int h_dtype, const void* Wp, const float* bias, void* out, int out_dtype, int B, int T,
                 int backend, void* stream);
 /* weight_norm fold g*v/||v|| (norm over dims (0,1) per tap; HF weight_norm(dim=2)) + regroup.
- * g: [128] (original0), v: [768,48,128] (original1) fp32.  out dtype fp32 (kpad=48) or bf16 (kpad=64). */
+ * g: [128] (original0), v: [768,48,128] (original1) fp32.  out dtype fp32 (kpad=48) or bf16 (kpad=8 / 64). */
 int a2f_pack_posconv_weight(const float* g, const float* v, void* out, int out_dtype, int kpad,
                             float* norm_scratch /* [128] device floats */, void* stream);
 /* Conv1d weight [Cout,Cin,taps] fp32 -> implicit-GEMM W [Cout, taps*Cin] (k = tap*Cin + cin), fp32 or bf16 */

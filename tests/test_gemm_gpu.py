@@ -125,7 +125,7 @@ def test_conv1d_implicit_gemm(a2f_lib, dev, taps, L_in, B):
         assert err < tol, (backend, err)
 
 
-@pytest.mark.parametrize("B,T", [(1, 60), (2, 150), (1, 300)])
+@pytest.mark.parametrize("B,T", [(1, 60), (2, 150), (1, 300), (3, 129), (1, 777)])
 def test_posconv(a2f_lib, dev, B, T):
     """h + gelu(weight-normed grouped conv k=128 pad 64 groups 16, last step dropped) vs torch."""
     from a2f_b200 import lib as L
@@ -136,8 +136,11 @@ def test_posconv(a2f_lib, dev, B, T):
     bias = _rand((768,), dev, 44, scale=0.05)
     wfull = torch._weight_norm(v.cpu(), g.cpu(), 2)
     norm = torch.empty(128, device=dev)
-    for backend, dt, kpad, tol in ((L.SIMT_F32, torch.float32, 48, 3e-5), (L.TCGEN05, torch.bfloat16, 64, 5e-2)):
-        wp = torch.empty((16, 48, 128, kpad), device=dev, dtype=dt)
+    # kpad 8 = chunked layout [16][128 taps][6][48 out][8 in] of posconv_tc.cu; kpad 64 = legacy gemm_tc mode 2 (debug field 9)
+    for backend, dt, kpad, tol in ((L.SIMT_F32, torch.float32, 48, 3e-5), (L.TCGEN05, torch.bfloat16, 8, 5e-2),
+                                   (L.TCGEN05, torch.bfloat16, 64, 5e-2)):
+        a2f_lib.a2f_debug_set_umma_field(9, 1 if kpad == 64 else 0)
+        wp = torch.empty((16, 128, 6, 48, 8) if kpad == 8 else (16, 48, 128, kpad), device=dev, dtype=dt)
         L.check(a2f_lib.a2f_pack_posconv_weight(g.data_ptr(), v.data_ptr(), wp.data_ptr(), 1 if dt == torch.bfloat16 else 0,
                                                  kpad, norm.data_ptr(), st))
         ha = h.to(dt).contiguous()
@@ -146,7 +149,10 @@ def test_posconv(a2f_lib, dev, B, T):
                                      out.data_ptr(), 1 if dt == torch.bfloat16 else 0, B, T, backend, st), "a2f_posconv")
         torch.cuda.synchronize()
         hh = ha.double().cpu()
-        if dt == torch.bfloat16:   # reference on the bf16-rounded packed weights
+        a2f_lib.a2f_debug_set_umma_field(9, 0)
+        if kpad == 8:              # reference on the bf16-rounded packed weights: [g][tap][chunk][n][8] -> [g*48+n][c][tap]
+            wq = wp.double().cpu().permute(0, 3, 2, 4, 1).reshape(768, 48, 128)
+        elif dt == torch.bfloat16:
             wq = wp[..., :48].double().cpu().permute(0, 1, 3, 2).reshape(768, 48, 128)
         else:
             wq = wfull.double()
