@@ -283,6 +283,182 @@ __global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ 
 }
 
 
+// ------------------------------------------------------------------------------------------------ short sequences
+// Clips of at most 160 frames (5 s at 30 fps is T = 150): every key of a (batch, head) fits in shared memory and a warp's
+// whole score row block (16 x NKT*16) fits in registers, so the softmax is single-pass (no running max / rescale) and
+// nothing is re-synchronised per key block.  One CTA = 80 queries (5 warps x 16 rows) of one (b, h) against all keys:
+// at T = 150 that is 768 CTAs of 160x160 useful work instead of the flash kernel's 1152 CTAs over 192x192 padded work
+// with three barrier-separated key steps each (22 us -> see profiles/).  K is waited for separately from V, so QK^T and the
+// softmax overlap the V load.
+constexpr int FS_NW = 5;                 // warps per CTA
+constexpr int FS_BM = 16 * FS_NW;        // queries per CTA
+template <int NKT> struct FsCfg {
+    static constexpr int KEYS = NKT * 16;
+    static constexpr size_t SMEM_BYTES = (size_t)(FS_BM + 2 * KEYS) * FA_LD * sizeof(bf16);
+};
+
+// grid: (ceil(T/80), H, B); 160 threads; T <= NKT*16.
+template <int NKT>
+__global__ void __launch_bounds__(32 * FS_NW, 3) mha_short_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                                   float* __restrict__ lse, float* __restrict__ out32, int T,
+                                                                   int H, float scale_log2) {
+    constexpr int KEYS = NKT * 16;
+    extern __shared__ __align__(16) uint8_t fs_smem[];
+    bf16* sQ = reinterpret_cast<bf16*>(fs_smem);
+    bf16* sK = sQ + FS_BM * FA_LD;
+    bf16* sV = sK + KEYS * FA_LD;
+    pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
+
+    const int q0 = blockIdx.x * FS_BM, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ld = 3 * H * FA_D;
+    const bf16* base = qkv + (long long)b * T * ld;
+    const bf16* gQ = base + h * FA_D;
+    const bf16* gK = base + H * FA_D + h * FA_D;
+    const bf16* gV = base + 2 * H * FA_D + h * FA_D;
+
+    // rows x 8 chunks of 16 B; rows beyond T are zero-filled (V must be finite: its rows meet zero probabilities)
+    auto load_rows = [&](bf16* dst, const bf16* src, int row0, int rows) {
+        for (int idx = threadIdx.x; idx < rows * 8; idx += 32 * FS_NW) {
+            const int r = idx >> 3, c = (idx & 7) * 8;
+            const bool ok = (row0 + r) < T;
+            cp_async_16(dst + r * FA_LD + c, src + (long long)(ok ? row0 + r : 0) * ld + c, ok);
+        }
+    };
+    load_rows(sQ, gQ, q0, FS_BM);
+    load_rows(sK, gK, 0, KEYS);
+    cp_async_commit();
+    load_rows(sV, gV, 0, KEYS);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    const bool active = q0 + warp * 16 < T;          // warp-uniform
+    uint32_t pf[NKT][4];                             // P as A fragments: NKT k-steps of 16 keys
+    float rs[2] = {0.f, 0.f}, mx[2] = {-INFINITY, -INFINITY};
+    if (active) {
+        uint32_t qf[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int c = ks * 16 + (lane >> 4) * 8;
+            ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sQ + r * FA_LD + c);
+        }
+        float s[2 * NKT][4];
+#pragma unroll
+        for (int i = 0; i < 2 * NKT; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int np = 0; np < NKT; ++np) {
+                uint32_t b0, b1, b2, b3;
+                const int r = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+                ldmatrix_x4(b0, b1, b2, b3, sK + r * FA_LD + c);
+                mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+            }
+        }
+        // mask keys beyond T, row max (rows g = lane/4 and g+8), probabilities, row sums
+#pragma unroll
+        for (int nt = 0; nt < 2 * NKT; ++nt) {
+            const int kc = nt * 8 + (lane & 3) * 2;
+            if (kc >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+            if (kc + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+            mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        }
+        const float msc0 = mx[0] * scale_log2, msc1 = mx[1] * scale_log2;
+#pragma unroll
+        for (int nt = 0; nt < 2 * NKT; ++nt) {
+            const float p0 = exp2f(fmaf(s[nt][0], scale_log2, -msc0));
+            const float p1 = exp2f(fmaf(s[nt][1], scale_log2, -msc0));
+            const float p2 = exp2f(fmaf(s[nt][2], scale_log2, -msc1));
+            const float p3 = exp2f(fmaf(s[nt][3], scale_log2, -msc1));
+            rs[0] += p0 + p1;
+            rs[1] += p2 + p3;
+            const int ks = nt >> 1, hi = nt & 1;
+            pf[ks][hi * 2 + 0] = pack_bf16x2(p0, p1);
+            pf[ks][hi * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                                 // V has landed
+    if (!active) return;
+
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < NKT; ++ks) {
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+            uint32_t b0, b1, b2, b3;
+            const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int c = dp * 16 + (lane >> 4) * 8;
+            ldmatrix_x4_trans(b0, b1, b2, b3, sV + r * FA_LD + c);
+            mma_bf16_16816(o[2 * dp], pf[ks], b0, b1);
+            mma_bf16_16816(o[2 * dp + 1], pf[ks], b2, b3);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+        rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+    }
+    const int row0 = q0 + warp * 16 + (lane >> 2);
+    const float inv0 = 1.f / rs[0], inv1 = 1.f / rs[1];
+    if (lse != nullptr && (lane & 3) == 0) {
+        float* lp = lse + ((long long)b * H + h) * T;
+        if (row0 < T) lp[row0] = mx[0] * scale_log2 * 0.69314718055994531f + logf(rs[0]);
+        if (row0 + 8 < T) lp[row0 + 8] = mx[1] * scale_log2 * 0.69314718055994531f + logf(rs[1]);
+    }
+    bf16* ob = out + (long long)b * T * (H * FA_D) + h * FA_D;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + (lane & 3) * 2;
+        if (row0 < T)
+            *reinterpret_cast<uint32_t*>(ob + (long long)row0 * (H * FA_D) + c) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+        if (row0 + 8 < T)
+            *reinterpret_cast<uint32_t*>(ob + (long long)(row0 + 8) * (H * FA_D) + c) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+    if (out32 != nullptr) {
+        float* o32 = out32 + (long long)b * T * (H * FA_D) + h * FA_D;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + (lane & 3) * 2;
+            if (row0 < T)
+                *reinterpret_cast<float2*>(o32 + (long long)row0 * (H * FA_D) + c) = make_float2(o[nt][0] * inv0, o[nt][1] * inv0);
+            if (row0 + 8 < T)
+                *reinterpret_cast<float2*>(o32 + (long long)(row0 + 8) * (H * FA_D) + c) = make_float2(o[nt][2] * inv1, o[nt][3] * inv1);
+        }
+    }
+}
+
+template <int NKT>
+static int launch_mha_short(const bf16* qkv, bf16* out, float* lse, float* out32, int B, int T, int H, float scale_log2,
+                            cudaStream_t s) {
+    auto kern = mha_short_kernel<NKT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FsCfg<NKT>::SMEM_BYTES));
+        attr_done = true;
+    }
+    const dim3 grid((T + FS_BM - 1) / FS_BM, H, B);
+    A2F_CHECK_CUDA(launch_pdl(kern, grid, dim3(32 * FS_NW), FsCfg<NKT>::SMEM_BYTES, s, qkv, out, lse, out32, T, H, scale_log2));
+    return A2F_OK;
+}
+
+
 // ================================================================================================ backward
 // delta[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one warp per (b,t,h))
 template <typename TO, typename T>
@@ -730,6 +906,15 @@ extern "C" int a2f_mha_fwd_train(const void* qkv, void* out, float* lse, float* 
         if (lse == nullptr && out_f32 == nullptr && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
             (impl == 2 || (impl == 0 && T >= mha_tc_min_t()))) {
             rc = mha_tc_fwd(qkv, out, B, T, H, scale, s);
+            if (rc != A2F_OK) return rc;
+            count_launch();
+            return A2F_OK;
+        }
+        if (impl != 1 && T <= 160) {
+            // short clips: single-pass kernel with every key of a (batch, head) resident in shared memory
+            const float sl2 = scale * 1.4426950408889634f;
+            rc = T <= 80 ? launch_mha_short<5>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, out_f32, B, T, H, sl2, s)
+                         : launch_mha_short<10>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, out_f32, B, T, H, sl2, s);
             if (rc != A2F_OK) return rc;
             count_launch();
             return A2F_OK;

@@ -98,8 +98,10 @@ def test_layernorm(a2f_lib, dev, C):
     assert _maxerr(out16, want) < 4e-2
 
 
-@pytest.mark.parametrize("B,T", [(1, 60), (2, 150), (1, 333), (2, 1), (3, 17), (1, 256), (1, 257)])
+@pytest.mark.parametrize("B,T", [(1, 60), (2, 150), (1, 333), (2, 1), (3, 17), (1, 256), (1, 257), (1, 80), (2, 81), (1, 160),
+                                 (1, 161)])
 def test_mha(a2f_lib, dev, B, T):
+    # bf16, automatic dispatch: T <= 80 / <= 160 take the single-pass short-clip kernels, longer ones the flash kernel
     from a2f_b200 import ops
     g = torch.Generator().manual_seed(9)
     qkv = torch.randn(B, T, 2304, generator=g)

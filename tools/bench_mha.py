@@ -18,12 +18,12 @@ def main():
                                                                               (8, 1800), (8, 3600), (1, 3600)]
     lib = L.load()
     dev = torch.device("cuda:0")
-    print(f"{'B':>4} {'T':>6} {'mma.sync us':>12} {'TFLOP/s':>9} {'tcgen05 us':>12} {'TFLOP/s':>9} {'speedup':>8}")
+    print(f"{'B':>4} {'T':>6} {'mma.sync us':>12} {'TFLOP/s':>9} {'tcgen05 us':>12} {'TFLOP/s':>9} {'speedup':>8} {'auto us':>9}  (auto: short-clip kernel for T <= 160)")
     for B, T in shapes:
         qkv = torch.randn(B, T, 2304, device=dev).bfloat16()
         out = torch.empty(B, T, 768, device=dev, dtype=torch.bfloat16)
         res = []
-        for impl in (1, 2):
+        for impl in (1, 2, 0):
             L.check(lib.a2f_debug_set_umma_field(6, impl))
             for _ in range(5):
                 ops.mha(qkv, out, B, T)
@@ -37,7 +37,7 @@ def main():
             res.append(s.elapsed_time(e) / 20 * 1e3)
         lib.a2f_debug_set_umma_field(6, 0)
         fl = 4.0 * T * T * 768 * B
-        print(f"{B:4d} {T:6d} {res[0]:12.1f} {fl / res[0] / 1e6:9.1f} {res[1]:12.1f} {fl / res[1] / 1e6:9.1f} {res[0] / res[1]:8.2f}")
+        print(f"{B:4d} {T:6d} {res[0]:12.1f} {fl / res[0] / 1e6:9.1f} {res[1]:12.1f} {fl / res[1] / 1e6:9.1f} {res[0] / res[1]:8.2f} {res[2]:9.1f}")
 
 
 if __name__ == "__main__":

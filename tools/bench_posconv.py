@@ -28,7 +28,7 @@ for B, T in shapes:
         hh = h.double().cpu()
         pos = F.conv1d(hh.transpose(1, 2), wfull, bias.double().cpu(), padding=64, groups=16)[:, :, :-1]
         want = hh + F.gelu(pos).transpose(1, 2)
-    for name, kpad, impl, swap in (("posconv_tc", 8, 0, 0), ("posconv_tc/swapped-strides", 8, 0, 1), ("gemm_tc mode 2", 64, 1, 0)):
+    for name, kpad, impl, swap in (("posconv_tc", 8, 0, 0), ("gemm_tc mode 2", 64, 1, 0)):
         lib.a2f_debug_set_umma_field(9, impl)
         lib.a2f_debug_set_umma_field(10, swap)
         wp = torch.zeros((16, 128, 6, 48, 8) if kpad == 8 else (16, 48, 128, 64), device=dev, dtype=torch.bfloat16)
