@@ -24,3 +24,13 @@ def get_loss_fn(modelname: str):
     """Mirror of ref:src/model/lightning_model.py:70-73."""
     from . import modules
     return modules.FaceFormerLoss() if modelname == "faceformer" else modules.VocaLoss()
+
+
+def get_extractor(extractor):
+    """Mirror of ref:src/model/lightning_model.py:61-67 for the extractor on the B200 path ("mfcc"; None -> no extractor)."""
+    from . import features
+    if extractor is None:
+        return lambda *args, **kwargs: None
+    if extractor != "mfcc":
+        raise KeyError(f"extractor {extractor!r} is outside the B200 hot path (SURVEY.md section 8(f))")
+    return features.MFCCExtractor

@@ -1,0 +1,147 @@
+"""Feature extractors in front of the conv models: drop-in for the reference's MFCCExtractor.
+
+ref:src/model/extractor.py:10-60 wraps torchaudio.transforms.MFCC (MelSpectrogram -> AmplitudeToDB(top_db=80) -> ortho
+DCT-II), transposes to [B, frames, n_mfcc] and bilinearly resizes the time axis to out_dim.  Here the same arithmetic
+runs as four launches of liba2f_sm100.so: frame gather, DFT as a GEMM against a window-folded (cos | sin) basis on the
+a2f_gemm back ends (fp32 SIMT, or tcgen05 on an error-compensated bf16x3 split), mel + dB + batch-global maximum, and
+clamp + DCT + resize.  Constructor arguments, output shape and the persistent buffers (`T.dct_mat`,
+`T.MelSpectrogram.spectrogram.window`, `T.MelSpectrogram.mel_scale.fb`) match the reference module, so a Lightning
+checkpoint's `feature_extractor.*` entries load strictly.  CUDA (sm_100a) only -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import lib as L
+from . import ops
+from .modules import _PackCache
+
+N_MELS = 128        # torchaudio.transforms.MFCC default melkwargs["n_mels"]
+TOP_DB = 80.0       # torchaudio.transforms.MFCC: AmplitudeToDB("power", 80.0)
+
+
+def hann_periodic(win_length: int) -> torch.Tensor:
+    """The buffer torchaudio's Spectrogram registers: torch.hann_window(win_length, periodic=True), fp32 arithmetic
+    (an fp64 evaluation differs from it by up to 2e-7, and checkpoints carry the fp32 one)."""
+    return torch.hann_window(win_length, periodic=True)
+
+
+def htk_mel_filterbank(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """torchaudio.functional.melscale_fbanks(norm=None, mel_scale="htk") -> [n_freqs, n_mels] fp32 (same fp32 op order)."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + f_min / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + f_max / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))
+
+
+def dct2_ortho(n_mfcc: int, n_mels: int) -> torch.Tensor:
+    """torchaudio.functional.create_dct(n_mfcc, n_mels, norm="ortho") -> [n_mels, n_mfcc]."""
+    n = torch.arange(float(n_mels))
+    k = torch.arange(float(n_mfcc)).unsqueeze(1)
+    dct = torch.cos(math.pi / float(n_mels) * (n + 0.5) * k)
+    dct[0] *= 1.0 / math.sqrt(2.0)
+    dct *= math.sqrt(2.0 / float(n_mels))
+    return dct.t()
+
+
+class _Buffers(nn.Module):
+    """Empty container used to reproduce torchaudio's buffer names."""
+
+
+class MFCCExtractor(nn.Module):
+    """
+    Input shape: (batch, time)
+    Output shape: (batch, out_dim, n_mfcc)
+    """
+
+    def __init__(self, sample_rate: int, n_feature: int, out_dim: int, win_length: int, hop_length: int = None,
+                 n_fft: int = None):
+        super().__init__()
+        self.sample_rate = sample_rate
+        self.n_mfcc = n_feature
+        self.out_dim = out_dim
+        self.win_length = win_length
+        self.hop_length = hop_length if hop_length else win_length // 2
+        self.n_fft = n_fft if n_fft else win_length
+        if self.win_length > self.n_fft:
+            raise ValueError("win_length must not exceed n_fft")
+        self.n_freq = self.n_fft // 2 + 1
+        # torchaudio's module tree: MFCC.dct_mat, MFCC.MelSpectrogram.spectrogram.window, MFCC.MelSpectrogram.mel_scale.fb
+        self.T = _Buffers()
+        self.T.register_buffer("dct_mat", dct2_ortho(self.n_mfcc, N_MELS))
+        self.T.MelSpectrogram = _Buffers()
+        self.T.MelSpectrogram.spectrogram = _Buffers()
+        self.T.MelSpectrogram.spectrogram.register_buffer("window", hann_periodic(self.win_length))
+        self.T.MelSpectrogram.mel_scale = _Buffers()
+        self.T.MelSpectrogram.mel_scale.register_buffer(
+            "fb", htk_mel_filterbank(self.n_freq, 0.0, float(sample_rate // 2), N_MELS, sample_rate))
+        self.precision = "fp32"
+        self._cache = _PackCache()
+
+    def set_precision(self, precision: str):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        return self
+
+    # ---- derived operands (rebuilt when a buffer changes, e.g. after load_state_dict) -------------------------------
+    def _basis(self):
+        window = self.T.MelSpectrogram.spectrogram.window
+        bf = self.precision == "bf16"
+
+        def build():
+            win, n_fft, nf = self.win_length, self.n_fft, self.n_freq
+            kpad = (win + 63) // 64 * 64
+            lo = (n_fft - win) // 2
+            j = torch.arange(win, dtype=torch.float64) + lo
+            ang = 2.0 * math.pi * torch.outer(torch.arange(nf, dtype=torch.float64), j) / n_fft
+            w = window.detach().double().cpu()
+            npad = (2 * nf + 7) // 8 * 8
+            basis = torch.zeros((npad, kpad), dtype=torch.float64)
+            basis[:nf, :win] = torch.cos(ang) * w
+            basis[nf:2 * nf, :win] = torch.sin(ang) * w
+            basis = basis.float().to(window.device)
+            return {"kpad": kpad, "npad": npad, "w": ops.split_bf16x3(basis, True) if bf else basis}
+        return self._cache.get("basis_bf16" if bf else "basis_f32", (window,), build)
+
+    def _bands(self):
+        fb = self.T.MelSpectrogram.mel_scale.fb
+
+        def build():
+            nz = (fb.detach().cpu() != 0)
+            band = torch.zeros((fb.shape[1], 2), dtype=torch.int32)
+            for m in range(fb.shape[1]):
+                idx = torch.nonzero(nz[:, m]).flatten()
+                if idx.numel():
+                    band[m, 0], band[m, 1] = int(idx[0]), int(idx[-1]) + 1
+            return band.to(fb.device)
+        return self._cache.get("bands", (fb,), build)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise L.A2FError("the a2f_b200 modules run on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dim() != 2:
+            raise L.A2FError("MFCCExtractor expects (batch, time) audio")
+        if not self.T.dct_mat.is_cuda:
+            raise L.A2FError("move the extractor to the GPU first (.to(device))")
+        x = x.contiguous().float()
+        B = x.shape[0]
+        bs = self._basis()
+        bf = self.precision == "bf16"
+        gmax = torch.empty(1, dtype=torch.float32, device=x.device)
+        frames, F_ = ops.mfcc_frames(x, self.win_length, self.hop_length, self.n_fft, bs["kpad"],
+                                     torch.bfloat16 if bf else torch.float32, gmax)
+        spec = torch.empty((B * F_, bs["npad"]), dtype=torch.float32, device=x.device)
+        ops.gemm(frames, bs["w"], spec, backend=L.TCGEN05 if bf else L.SIMT_F32)
+        fb = self.T.MelSpectrogram.mel_scale.fb
+        db = ops.mfcc_mel_db(spec, self.n_freq, fb.detach().contiguous(), self._bands(), gmax)
+        return ops.mfcc_dct_resize(db, gmax, TOP_DB, self.T.dct_mat.detach().contiguous(), B, F_, self.out_dim)

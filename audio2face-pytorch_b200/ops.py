@@ -713,3 +713,34 @@ def bn_train_bwd(dy: View, y_relu: Optional[View], z: View, mean_rstd, gamma, dz
     L.check(L.load().a2f_bn_train_bwd(dy.ptr, y_relu.ptr if y_relu is not None else None, z.ptr, mean_rstd.data_ptr(),
                                       gamma.data_ptr(), dy.C, dy.rows, dy.ld, dy.bs, dy.batches, dz.ptr, dgamma.data_ptr(),
                                       dbeta.data_ptr(), ws.data_ptr(), ws.numel() * 8, _stream()), "a2f_bn_train_bwd")
+
+
+# ---------------------------------------------------------------------------------------------------- MFCC extractor
+def mfcc_frames(audio: torch.Tensor, win: int, hop: int, n_fft: int, kpad: int, dtype: torch.dtype, gmax: torch.Tensor):
+    """audio [B,N] fp32 -> frame matrix [B*F, kpad] fp32 or [B*F, 3*kpad] bf16 split (a2f_mfcc_frames)."""
+    _dev(audio, gmax)
+    B, N = audio.shape
+    F_ = 1 + N // hop
+    out = torch.empty((B * F_, kpad if dtype == torch.float32 else 3 * kpad), dtype=dtype, device=audio.device)
+    L.check(L.load().a2f_mfcc_frames(audio.data_ptr(), B, N, win, hop, n_fft, kpad, out.data_ptr(), _dt(out), gmax.data_ptr(),
+                                     _stream()), "a2f_mfcc_frames")
+    return out, F_
+
+
+def mfcc_mel_db(spec: torch.Tensor, n_freq: int, fb: torch.Tensor, band: torch.Tensor, gmax: torch.Tensor) -> torch.Tensor:
+    _dev(spec, fb, band, gmax)
+    M, n_mels = spec.shape[0], fb.shape[1]
+    db = torch.empty((M, n_mels), dtype=torch.float32, device=spec.device)
+    L.check(L.load().a2f_mfcc_mel_db(spec.data_ptr(), spec.stride(0), M, n_freq, fb.data_ptr(), band.data_ptr(), n_mels,
+                                     db.data_ptr(), gmax.data_ptr(), _stream()), "a2f_mfcc_mel_db")
+    return db
+
+
+def mfcc_dct_resize(db: torch.Tensor, gmax: torch.Tensor, top_db: float, dct: torch.Tensor, B: int, F_: int,
+                    out_dim: int) -> torch.Tensor:
+    _dev(db, gmax, dct)
+    n_mels, n_mfcc = dct.shape
+    out = torch.empty((B, out_dim, n_mfcc), dtype=torch.float32, device=db.device)
+    L.check(L.load().a2f_mfcc_dct_resize(db.data_ptr(), gmax.data_ptr(), float(top_db), dct.data_ptr(), B, F_, n_mels, n_mfcc,
+                                         out_dim, out.data_ptr(), _stream()), "a2f_mfcc_dct_resize")
+    return out

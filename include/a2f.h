@@ -437,6 +437,27 @@ int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
                   float weight_decay, int step, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * MFCC feature extractor (replaces ref:src/model/extractor.py:10-60 = torchaudio.transforms.MFCC
+ * + transpose + bilinear resize, which runs as ~8 library kernels in the reference).  The DFT itself is a2f_gemm of the
+ * frame matrix with a window-folded (cos | sin) basis [2*n_freq (+pad), K]; these three entry points are the rest.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* audio [B,N] fp32 -> frame matrix, F = 1 + N/hop rows per clip (centre=True, reflect padding n_fft/2):
+ *   A[b*F+t, k] = audio_reflect[b, t*hop + (n_fft-win)/2 - n_fft/2 + k], k < win; zero for win <= k < kpad.
+ * a_dtype A2F_F32: [B*F, kpad] fp32; A2F_BF16: [B*F, 3*kpad] error-compensated split [hi | lo | hi] (pair it with the
+ * basis split [hi | hi | lo] of a2f_split_bf16x3).  Also resets *gmax_slot (the batch-global dB maximum) to -inf. */
+int a2f_mfcc_frames(const float* audio, int B, int N, int win, int hop, int n_fft, int kpad, void* A, int a_dtype,
+                    float* gmax_slot, void* stream);
+/* spec [M, ld_spec] fp32 rows (Re[0..n_freq) | Im[0..n_freq)) -> db [M, n_mels] = 10*log10(max(|X|^2 @ fb, 1e-10));
+ * fb [n_freq, n_mels] (torchaudio MelScale.fb), band [n_mels][2] = [first, last+1) frequency bin of each band's support;
+ * *gmax_slot accumulates the maximum over everything written (torchaudio amplitude_to_DB on a 3-D batch: one cut-off). */
+int a2f_mfcc_mel_db(const float* spec, int ld_spec, int M, int n_freq, const float* fb, const int* band, int n_mels,
+                    float* db, float* gmax_slot, void* stream);
+/* out [B, out_dim, n_mfcc] = bilinear_resize_time( max(db, gmax - top_db) @ dct ), dct [n_mels, n_mfcc] (ortho DCT-II);
+ * resize = torch.nn.functional.interpolate(mode="bilinear", align_corners=False) from F to out_dim rows. */
+int a2f_mfcc_dct_resize(const float* db, const float* gmax_slot, float top_db, const float* dct, int B, int F, int n_mels,
+                        int n_mfcc, int out_dim, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; also bench.py's e2e leg): pinned or pageable HOST
  * pointers in, HOST pointers out; H2D, compute and D2H are all enqueued on `stream`, then the stream is synchronised.
  * `dev_scratch` is a caller-owned DEVICE buffer of at least *_scratch_bytes.

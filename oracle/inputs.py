@@ -64,3 +64,27 @@ def gt_like(pred_shape, template: torch.Tensor, seed: int = 0, scale: float = 1.
     r = _rng(seed, 107)
     noise = (0.002 * scale) * r.standard_normal(tuple(pred_shape)).astype(np.float32)
     return template + torch.from_numpy(noise)
+
+
+def speech_like_windows(batch: int, n_samples: int = 11440, sample_rate: int = 22000, seed: int = 0) -> torch.Tensor:
+    """[B, N] audio windows for the MFCC extractor (ref:src/dataset/vocaset.py:408-430: 0.52 s at 22 kHz = 11 440
+    samples): harmonics of a per-window pitch with a formant-like envelope, broadband noise, one window with a silent
+    stretch (exercises the 1e-10 clamp / top_db floor) and one quiet window (exercises the batch-global cut-off)."""
+    r = _rng(seed, 108)
+    t = np.arange(n_samples, dtype=np.float64) / sample_rate
+    out = np.zeros((batch, n_samples), dtype=np.float64)
+    for b in range(batch):
+        f0 = r.uniform(90.0, 260.0)
+        amp = r.uniform(0.05, 0.4)
+        for h in range(1, 30):
+            fh = f0 * h
+            if fh > sample_rate / 2:
+                break
+            env = 1.0 / (1.0 + ((fh - 700.0) / 900.0) ** 2) + 0.5 / (1.0 + ((fh - 2400.0) / 1200.0) ** 2)
+            out[b] += amp * env / h ** 0.5 * np.sin(2 * np.pi * fh * t + r.uniform(0, 2 * np.pi))
+        out[b] += 0.01 * r.standard_normal(n_samples)
+    if batch > 1:
+        out[1, : n_samples // 3] = 0.0
+    if batch > 2:
+        out[2] *= 1e-3
+    return torch.from_numpy(out.astype(np.float32))
