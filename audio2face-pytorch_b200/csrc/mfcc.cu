@@ -100,38 +100,62 @@ __global__ void __launch_bounds__(32 * MEL_WARPS) mfcc_mel_db_kernel(const float
     if (lane == 0 && lmax > -INFINITY) atomicMax(gmax_slot, float_to_ordered(lmax));
 }
 
-// one warp per output row (b, o): two source frames, each clamped and DCT-transformed, then blended
-__global__ void __launch_bounds__(256) mfcc_dct_resize_kernel(const float* __restrict__ db, const int* __restrict__ gmax_slot,
-                                                              float top_db, const float* __restrict__ dct, int B, int F,
-                                                              int n_mels, int n_mfcc, int out_dim, float* __restrict__ out) {
+// one warp per output row (b, o): the two source frames are clamped and blended FIRST (the DCT is linear and the blend
+// weights sum to one, so this equals blending the two DCT rows up to fp32 rounding), staged in shared memory, and the
+// 128 x n_mfcc DCT runs with the 32 lanes split as (coefficient k, slice of the mel axis) -- all lanes busy for
+// n_mfcc = 16 or 32, DCT matrix in shared memory, one shuffle round to add the slices.
+constexpr int DCT_WARPS = 8;
+__global__ void __launch_bounds__(32 * DCT_WARPS) mfcc_dct_resize_kernel(const float* __restrict__ db, const int* __restrict__ gmax_slot,
+                                                                         float top_db, const float* __restrict__ dct, int B, int F,
+                                                                         int n_mels, int n_mfcc, int out_dim, float* __restrict__ out) {
+    extern __shared__ float dct_sm[];                  // [n_mels * n_mfcc] DCT matrix, then [DCT_WARPS][n_mels] blended rows
+    float* sdct = dct_sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* srow = dct_sm + n_mels * n_mfcc + warp * n_mels;
+    for (int i = threadIdx.x; i < n_mels * n_mfcc; i += blockDim.x) sdct[i] = __ldg(dct + i);   // module constant
     pdl_sync();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B * out_dim) return;
-    const int b = warp / out_dim, o = warp % out_dim;
+    __syncthreads();
     const float floor_db = ordered_to_float(*gmax_slot) - top_db;
-    int h0 = o, h1 = o;
-    float l0 = 1.f, l1 = 0.f;
-    if (out_dim != F) {
-        // ATen area_pixel_compute_source_index (align_corners=False): src = scale*(dst+0.5)-0.5, clamped at 0
-        const float scale = (float)F / (float)out_dim;
-        float src = scale * ((float)o + 0.5f) - 0.5f;
-        if (src < 0.f) src = 0.f;
-        h0 = (int)src;
-        if (h0 > F - 1) h0 = F - 1;
-        h1 = h0 + (h0 < F - 1 ? 1 : 0);
-        l1 = src - (float)h0;
-        l0 = 1.f - l1;
-    }
-    const float* r0 = db + ((long long)b * F + h0) * n_mels;
-    const float* r1 = db + ((long long)b * F + h1) * n_mels;
-    for (int k = lane; k < n_mfcc; k += 32) {
-        float a0 = 0.f, a1 = 0.f;
-        for (int m = 0; m < n_mels; ++m) {
-            const float w = __ldg(dct + (long long)m * n_mfcc + k);
-            a0 = fmaf(fmaxf(r0[m], floor_db), w, a0);
-            a1 = fmaf(fmaxf(r1[m], floor_db), w, a1);
+    // lanes = (k, slice): KP coefficients in flight, 32/KP slices of the mel axis
+    const int KP = n_mfcc >= 32 ? 32 : n_mfcc >= 16 ? 16 : n_mfcc >= 8 ? 8 : 4;
+    const int NS = 32 / KP;
+    const int kl = lane % KP, sl = lane / KP;
+    const int mper = (n_mels + NS - 1) / NS;
+    for (int row = blockIdx.x * DCT_WARPS + warp; row < B * out_dim; row += gridDim.x * DCT_WARPS) {
+        const int b = row / out_dim, o = row % out_dim;
+        int h0 = o, h1 = o;
+        float l0 = 1.f, l1 = 0.f;
+        if (out_dim != F) {
+            // ATen area_pixel_compute_source_index (align_corners=False): src = scale*(dst+0.5)-0.5, clamped at 0
+            const float scale = (float)F / (float)out_dim;
+            float src = scale * ((float)o + 0.5f) - 0.5f;
+            if (src < 0.f) src = 0.f;
+            h0 = (int)src;
+            if (h0 > F - 1) h0 = F - 1;
+            h1 = h0 + (h0 < F - 1 ? 1 : 0);
+            l1 = src - (float)h0;
+            l0 = 1.f - l1;
         }
-        out[((long long)b * out_dim + o) * n_mfcc + k] = (out_dim != F) ? (l0 * a0 + l1 * a1) : a0;
+        const float* r0 = db + ((long long)b * F + h0) * n_mels;
+        const float* r1 = db + ((long long)b * F + h1) * n_mels;
+        for (int m = lane; m < n_mels; m += 32) {
+            const float a = fmaxf(r0[m], floor_db);
+            srow[m] = (out_dim != F) ? l0 * a + l1 * fmaxf(r1[m], floor_db) : a;
+        }
+        __syncwarp();
+        for (int k0 = 0; k0 < n_mfcc; k0 += KP) {
+            const int k = k0 + kl;
+            // fp64 accumulation: c0 sums 128 dB values of the same sign (|c0| ~ 500), where fp32 summation-order noise
+            // alone reaches 1e-3; 2048 fp64 FMAs per row are free next to the DFT
+            double acc = 0.0;
+            if (k < n_mfcc) {
+                const int m1 = min(n_mels, (sl + 1) * mper);
+                for (int m = sl * mper; m < m1; ++m) acc = fma((double)srow[m], (double)sdct[m * n_mfcc + k], acc);
+            }
+            for (int off = KP; off < 32; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (sl == 0 && k < n_mfcc) out[(long long)row * n_mfcc + k] = (float)acc;
+        }
+        __syncwarp();
     }
 }
 
@@ -188,10 +212,11 @@ int a2f_mfcc_dct_resize(const float* db, const float* gmax_slot, float top_db, c
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(db && gmax_slot && dct && out && B > 0 && F > 0 && n_mels > 0 && n_mfcc > 0 && out_dim > 0,
                 "a2f_mfcc_dct_resize: bad arguments");
-    const long long warps = (long long)B * out_dim;
-    const long long blocks = (warps * 32 + 255) / 256;
-    A2F_REQUIRE(blocks < (1LL << 31), "a2f_mfcc_dct_resize: batch too large");
-    A2F_CHECK_CUDA(launch_pdl(mfcc_dct_resize_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), db,
+    const size_t smem = ((size_t)n_mels * n_mfcc + (size_t)DCT_WARPS * n_mels) * sizeof(float);
+    A2F_REQUIRE(smem <= 48 * 1024, "a2f_mfcc_dct_resize: n_mels * n_mfcc too large");
+    long long blocks = ((long long)B * out_dim + DCT_WARPS - 1) / DCT_WARPS;
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    A2F_CHECK_CUDA(launch_pdl(mfcc_dct_resize_kernel, dim3((unsigned)blocks), dim3(32 * DCT_WARPS), smem, as_stream(stream), db,
                               reinterpret_cast<const int*>(gmax_slot), top_db, dct, B, F, n_mels, n_mfcc, out_dim, out));
     count_launch();
     return A2F_OK;

@@ -145,3 +145,28 @@ class MFCCExtractor(nn.Module):
         fb = self.T.MelSpectrogram.mel_scale.fb
         db = ops.mfcc_mel_db(spec, self.n_freq, fb.detach().contiguous(), self._bands(), gmax)
         return ops.mfcc_dct_resize(db, gmax, TOP_DB, self.T.dct_mat.detach().contiguous(), B, F_, self.out_dim)
+
+
+class ExtractAndPredict(nn.Module):
+    """extractor -> model, the composition ref:src/model/lightning_model.py:111-117 (Audio2FaceModel.forward) performs:
+    `feature = self.feature_extractor(x).detach(); return self.model(feature, one_hot, template)`."""
+
+    def __init__(self, feature_extractor: nn.Module, model: nn.Module):
+        super().__init__()
+        self.feature_extractor = feature_extractor
+        self.model = model
+
+    def set_precision(self, precision: str):
+        self.feature_extractor.set_precision(precision)
+        self.model.set_precision(precision)
+        return self
+
+    def forward(self, x, one_hot, template, **kwargs):
+        if self.feature_extractor is None:
+            return self.model(x, one_hot, template, **kwargs)
+        feature = self.feature_extractor(x).detach()
+        return self.model(feature, one_hot, template, **kwargs)
+
+    def graphed(self, x, one_hot, template, **kwargs):
+        from .modules import GraphedForward
+        return GraphedForward(self, x, one_hot, template, **kwargs)

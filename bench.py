@@ -2,7 +2,8 @@
 """bench.py -- headline benchmark of the B200 audio->mesh hot path (contract in the task prompt / DESIGN.md).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload faceformer|faceformer_train|audio2mesh|voca]      (configs[2] | [3] | [1] | [0]-shaped)
+                    [--workload faceformer|faceformer_train|audio2mesh|voca|voca_audio]   (configs[2] | [3] | [1] | [0]-shaped |
+                                                                              raw audio windows -> MFCC -> VOCA)
     (configs[4], the long-sequence sweep: tools/sweep_long.py)
 
 Workload (BASELINE.json configs[2], the largest single-GPU inference configuration): FaceFormer inference,
@@ -133,6 +134,21 @@ def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: i
             dt = time.perf_counter() - t0
             return T / dt, (f"1 utterance x {seconds:g} s @ {fps} fps: forward + FaceFormerLoss + autograd backward, fp32, "
                             "reference O(T^2) decode loop (no optimizer step)")
+        if workload == "voca_audio":
+            from oracle import ref_mfcc as omf
+            cfg = omf.CONFIGS["voca"]
+            sd, bufs = ow.make_state_dict("voca", 11), omf.make_buffers(cfg[0], cfg[1], cfg[3], cfg[5])
+            B = 512
+            x, oh, tp = oin.speech_like_windows(B, seed=1), oin.one_hot(B, 12, 1), oin.batch_templates(B, 1)
+            run = lambda: orm.voca_forward(sd, omf.mfcc_forward(bufs, x, cfg[2], cfg[3], cfg[4], cfg[5]), oh, tp)  # noqa: E731
+            run()
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 5.0:
+                run()
+                reps += 1
+            dt = time.perf_counter() - t0
+            return reps * B / dt, f"{reps} x {B} windows of 11440 samples: MFCC (torch stft path) + VOCA, fp32"
         if workload == "audio2mesh":
             sd = ow.make_state_dict("audio2mesh", 12)
             B = 64
@@ -210,6 +226,13 @@ def workload_config(args):
                 "window": "52 x 32 MFCC", "vertices": 5023, "weights": "random-init (oracle.weights seed 12, randomised BatchNorm stats)",
                 "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
                 "launch": "eager" if args.no_graph else "one CUDA graph per forward (modules.GraphedForward)"}
+    if args.workload == "voca_audio":
+        return {"workload": f"mfcc_plus_voca_b{args.batch}_windows (BASELINE.json configs[0] from raw audio: SURVEY.md 8(f) rank 1 + a18)",
+                "batch_per_gpu": args.batch, "window_samples": 11440, "sample_rate": 22000,
+                "mfcc": "n_mfcc 16, win 790, hop 395, n_fft 1024, 128 mels, top_db 80 (ref config.yaml)", "vertices": 5023,
+                "weights": "random-init (oracle.weights seed 11)",
+                "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
+                "launch": "eager" if args.no_graph else "one CUDA graph per forward (modules.GraphedForward)"}
     return {"workload": f"voca_inference_b{args.batch} (BASELINE.json configs[0] shape)", "batch_per_gpu": args.batch,
             "vertices": 5023, "weights": "random-init (oracle.weights seed 11)",
             "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)"}
@@ -255,6 +278,18 @@ def run_ours(args):
                 oin.batch_templates(B, 100 + rank).pin_memory()]
         units = B
         flops_step = B * 131.0e6                                 # 131.0 MFLOP per window
+        call = lambda a, o, t: model(a, o, t)                    # noqa: E731
+        out_shape = (B, 5023, 3)
+    elif args.workload == "voca_audio":
+        from a2f_b200 import features
+        voca = modules.Voca(15069, 12)
+        voca.load_state_dict(ow.make_state_dict("voca", 11), strict=True)
+        model = features.ExtractAndPredict(features.MFCCExtractor(22000, 16, 29, 790, None, 1024), voca).to(dev).eval()
+        model.set_precision("bf16")
+        h_in = [oin.speech_like_windows(B, seed=100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(),
+                oin.batch_templates(B, 100 + rank).pin_memory()]
+        units = B
+        flops_step = B * (2.0 * 29 * 1026 * 790 + 1.679e6)       # DFT as a GEMM over the window support + VOCA
         call = lambda a, o, t: model(a, o, t)                    # noqa: E731
         out_shape = (B, 5023, 3)
     else:
@@ -391,6 +426,20 @@ def run_ours(args):
                                    f"would be {pk['bf16_sustained']} TFLOP/s", "launches_per_step": len(gem) // 2,
                     "kernel_share_of_step": (g_time / 2) / (dev_s / args.steps),
                     "whole_step_tflops": flops_step * world * args.steps / dev_s / 1e12}
+    elif args.workload == "voca_audio":
+        # dominant kernel: the DFT GEMM (frames x window-folded cos|sin basis) on the bf16x3 split -- the first tcgen05
+        # launch of a forward; algorithmic FLOPs = 2 * rows * 1026 * 790 (un-padded, un-split), so the 3-term split and
+        # the K padding to 832 cap frac at 0.32
+        gem = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind == "gemm_tc"]
+        dft = gem[0::2]
+        g_time = sum(t for _, t in dft)
+        alg = 2.0 * B * 29 * 1026 * 790 * len(dft)
+        achieved = alg / g_time / 1e12
+        roofline = {"bound": "tensor", "kernel": "a2f::gemm_tc2_kernel (DFT of the MFCC extractor as a bf16x3-split GEMM)",
+                    "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                    "traffic": None, "peak_source": pk["source"] + ", sustained bf16", "launches_per_step": 1,
+                    "executed_tflops": sum(f for f, _ in dft) / g_time / 1e12,
+                    "kernel_share_of_step": (g_time / len(dft)) / (dev_s / args.steps)}
     else:
         head = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind == "gemm_tc"]
         byts = 2 * (B * 15069 * 4) * len(head)            # template read + vertex write per launch
@@ -571,7 +620,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "audio2mesh", "faceformer_train"])
+    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "voca_audio", "audio2mesh", "faceformer_train"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--fps", type=int, default=None)
@@ -582,7 +631,7 @@ def main():
     if args.fps is None:
         args.fps = 60 if args.workload == "faceformer_train" else 30
     if args.batch is None:
-        args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384, "audio2mesh": 64}[args.workload]
+        args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384, "voca_audio": 4096, "audio2mesh": 64}[args.workload]
     if args.impl == "reference":
         run_reference(args)
         return

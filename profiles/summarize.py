@@ -2,6 +2,7 @@
 
     python profiles/summarize.py launches gpurun_out/launches_r1.csv  > profiles/r1_launches.txt
     python profiles/summarize.py kernel   gpurun_out/prof_x.ncu-rep   > profiles/r1_x.txt
+    python profiles/summarize.py traffic  gpurun_out/traffic.csv "note" > profiles/r1_traffic_infer.json
 """
 import csv
 import io
@@ -44,6 +45,39 @@ def launches(path):
     print(f"{'TOTAL':80s} {sum(a[0] for a in agg.values()):8d} {total:10.1f}")
 
 
+def traffic(path, note=""):
+    """launch list with dram__bytes_read/write -> JSON (per kernel: launches, us, bytes) incl. the `gemm_tc_all` entry
+    bench.py reads for roofline.traffic (mean DRAM bytes per tcgen05 GEMM launch of one forward)."""
+    import json
+    rows = [r for r in csv.reader(open(path)) if r and not r[0].startswith("==")]
+    hdr = rows[0]
+    ix = {h: i for i, h in enumerate(hdr)}
+    per = OrderedDict()
+    seen = {}
+    for r in rows[1:]:
+        if len(r) < len(hdr):
+            continue
+        name = r[ix["Kernel Name"]].split("(")[0]
+        k = per.setdefault(name, {"launches": 0, "us": 0.0, "read": 0.0, "write": 0.0})
+        metric, unit = r[ix["Metric Name"]], r[ix["Metric Unit"]]
+        v = float(r[ix["Metric Value"]].replace(",", ""))
+        if metric == "gpu__time_duration.sum":
+            k["us"] += v / 1000.0 if unit in ("ns", "nsecond") else v if unit in ("us", "usecond") else v * 1000.0
+            if seen.get(r[ix["ID"]]) is None:
+                seen[r[ix["ID"]]] = 1
+                k["launches"] += 1
+        elif metric in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+            k["read" if "read" in metric else "write"] += v * scale
+    gem = [v for n, v in per.items() if "gemm_tc" in n or "posconv_tc" in n]
+    tot = sum(v["read"] + v["write"] for v in gem)
+    n = sum(v["launches"] for v in gem)
+    out = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; "
+                     + note, "kernels": per,
+           "gemm_tc_all": {"launches": n, "dram_bytes": tot, "dram_bytes_per_launch": tot / max(n, 1)}}
+    print(json.dumps(out, indent=1))
+
+
 def kernel(path):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -74,4 +108,4 @@ def kernel(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
