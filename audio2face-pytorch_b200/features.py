@@ -170,3 +170,68 @@ class ExtractAndPredict(nn.Module):
     def graphed(self, x, one_hot, template, **kwargs):
         from .modules import GraphedForward
         return GraphedForward(self, x, one_hot, template, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------ audio preparation
+def audio_fragments(audio: torch.Tensor, n_frames: int, *, fps: int = 60, sample_rate: int = 22000, length: float = 0.52,
+                    shift: int = 0, first_frame: int = 0) -> torch.Tensor:
+    """All per-frame windows of one clip in one launch: row f = ref:src/dataset/vocaset.py:408-430
+    get_audio_fragment(audio, first_frame + f, fps=..., sample_rate=..., length=..., shift=...), int16 clips scaled by
+    1/32768 (ref:vocaset.py:64-69).  audio: 1-D CUDA tensor (float32 or int16) -> [n_frames, 2*int(sample_rate*length/2)]."""
+    if not audio.is_cuda:
+        raise L.A2FError("the a2f_b200 modules run on CUDA (sm_100a) only; there is no CPU fallback")
+    if audio.dim() != 1 or audio.dtype not in (torch.float32, torch.int16):
+        raise L.A2FError("audio_fragments expects a 1-D float32 or int16 clip")
+    audio = audio.contiguous()
+    n_pad = int(sample_rate * length / 2)
+    out = torch.empty((n_frames, 2 * n_pad), dtype=torch.float32, device=audio.device)
+    L.check(L.load().a2f_audio_fragments(audio.data_ptr(), L.I16 if audio.dtype == torch.int16 else L.F32, audio.numel(),
+                                         int(first_frame), int(n_frames), int(sample_rate), int(fps), n_pad, int(shift),
+                                         out.data_ptr(), torch.cuda.current_stream().cuda_stream), "a2f_audio_fragments")
+    return out
+
+
+_RESAMPLE_KERNELS = {}
+
+
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """torchaudio.functional.functional._get_sinc_resample_kernel for a float32 waveform ("sinc_interp_hann"): the same
+    float32 operation sequence, so the filter bank is the one torchaudio applies.  -> (kernel [new, 2*width+orig], width,
+    orig, new) with the frequencies already divided by their gcd."""
+    gcd = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // gcd, int(new_freq) // gcd
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx = torch.arange(-width, width + orig, dtype=torch.float32)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=torch.float32)[:, None, None] / new + idx
+    t *= base_freq
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    scale = base_freq / orig
+    kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
+    kernels *= window * scale
+    return kernels.reshape(new, -1).contiguous(), width, orig, new
+
+
+def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
+    """torchaudio.functional.resample(waveform, orig_freq, new_freq) with its default parameters, on (..., time) CUDA fp32."""
+    if not waveform.is_cuda:
+        raise L.A2FError("the a2f_b200 modules run on CUDA (sm_100a) only; there is no CPU fallback")
+    if orig_freq <= 0 or new_freq <= 0:
+        raise ValueError("Original frequency and desired frequecy should be positive")
+    if orig_freq == new_freq:
+        return waveform
+    key = (int(orig_freq), int(new_freq), waveform.device)
+    if key not in _RESAMPLE_KERNELS:
+        k, width, orig, new = sinc_resample_kernel(orig_freq, new_freq)
+        _RESAMPLE_KERNELS[key] = (k.to(waveform.device), width, orig, new)
+    k, width, orig, new = _RESAMPLE_KERNELS[key]
+    shape = waveform.shape
+    x = waveform.reshape(-1, shape[-1]).contiguous().float()
+    B, N = x.shape
+    target = int(math.ceil(new * N / orig))
+    out = torch.empty((B, target), dtype=torch.float32, device=x.device)
+    L.check(L.load().a2f_resample_sinc(x.data_ptr(), B, N, orig, new, k.data_ptr(), k.shape[1], width, out.data_ptr(), target,
+                                       torch.cuda.current_stream().cuda_stream), "a2f_resample_sinc")
+    return out.view(shape[:-1] + (target,))

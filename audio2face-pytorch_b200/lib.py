@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liba2f_sm100.so")
 
 A2F_OK, A2F_EINVAL, A2F_EARCH, A2F_ECUDA = 0, -1, -2, -3
-F32, BF16 = 0, 1
+F32, BF16, I16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 SIMT_F32, TCGEN05 = 0, 1
 RESID_ADD, RESID_DACT = 0, 1
@@ -160,6 +160,8 @@ _SIGNATURES = {
     "a2f_mfcc_mel_db": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "a2f_mfcc_dct_resize": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p]),
+    "a2f_audio_fragments": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "a2f_resample_sinc": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "a2f_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                               c_int, c_float, c_void_p]),
 }

@@ -35,6 +35,7 @@ extern "C" {
 
 #define A2F_F32 0
 #define A2F_BF16 1
+#define A2F_I16 2   /* int16 PCM: a2f_audio_fragments input only */
 
 #define A2F_ACT_NONE 0
 #define A2F_ACT_RELU 1
@@ -456,6 +457,23 @@ int a2f_mfcc_mel_db(const float* spec, int ld_spec, int M, int n_freq, const flo
  * resize = torch.nn.functional.interpolate(mode="bilinear", align_corners=False) from F to out_dim rows. */
 int a2f_mfcc_dct_resize(const float* db, const float* gmax_slot, float top_db, const float* dct, int B, int F, int n_mels,
                         int n_mfcc, int out_dim, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Audio preparation: what the reference's CPU DataLoader does before the extractor / model.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* ref:src/dataset/vocaset.py:408-430 get_audio_fragment for frames first_frame .. first_frame+n_frames-1 of one clip:
+ *   out[f, k] = pad_audio[(first_frame+f)*sample_rate/fps + k], k < 2*n_pad,
+ *   pad_audio = [zeros(n_pad + shift), audio, zeros(2*n_pad)], n_pad = int(sample_rate*length/2).
+ * audio_dtype A2F_F32, or A2F_I16 (scaled by 1/32768 = ref:vocaset.py:64-69 normalize_audio).  A2F_EINVAL when the last
+ * fragment would end past the padded clip (the reference returns None there). */
+int a2f_audio_fragments(const void* audio, int audio_dtype, long long n_samples, int first_frame, int n_frames, int sample_rate,
+                        int fps, int n_pad, int shift, float* out, void* stream);
+/* torchaudio.functional.resample as used at ref:src/dataset/vocaset.py:279-283 and ref:src/model/extractor.py:88:
+ *   out[b, i*nnew + p] = sum_{k<kw} kernel[p][k] * xpad[b, i*orig + k],  xpad = x zero-padded by (width, width+orig),
+ * orig/nnew = the two rates divided by their gcd, kernel [nnew][kw = 2*width + orig] the windowed-sinc filter bank,
+ * target_len = ceil(nnew*N/orig) outputs per waveform. */
+int a2f_resample_sinc(const float* x, int B, long long N, int orig, int nnew, const float* kernel, int kw, int width, float* out,
+                      long long target_len, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; also bench.py's e2e leg): pinned or pageable HOST

@@ -88,3 +88,19 @@ def speech_like_windows(batch: int, n_samples: int = 11440, sample_rate: int = 2
     if batch > 2:
         out[2] *= 1e-3
     return torch.from_numpy(out.astype(np.float32))
+
+
+def pcm16_clip(n_samples: int = 127600, sample_rate: int = 22000, seed: int = 0) -> np.ndarray:
+    """int16 mono clip shaped like ref:assets/audio_sample.npy (22 kHz, 127 600 samples = 5.8 s; the asset itself is not
+    redistributed): speech-like harmonics with a slow amplitude envelope plus noise, scaled to ~60 % of full scale."""
+    r = _rng(seed, 109)
+    t = np.arange(n_samples, dtype=np.float64) / sample_rate
+    f0 = 120.0 + 30.0 * np.sin(2 * np.pi * 0.7 * t)
+    phase = 2 * np.pi * np.cumsum(f0) / sample_rate
+    x = np.zeros(n_samples)
+    for h in range(1, 25):
+        x += np.sin(h * phase + r.uniform(0, 2 * np.pi)) / h
+    x *= 0.5 * (1.0 + np.sin(2 * np.pi * 2.3 * t)) * (t > 0.2)
+    x += 0.02 * r.standard_normal(n_samples)
+    x *= 0.6 / np.abs(x).max()
+    return np.round(x * 32767.0).astype(np.int16)

@@ -5,9 +5,11 @@ CPU: the oracle restatement (oracle/ref_mfcc.py) against the fixture produced by
 GPU (-m gpu): the CUDA path (frame gather -> DFT GEMM -> mel/dB/global max -> clamp/DCT/resize) through the C-ABI against
 the oracle on the same inputs and against the fixture.
 
-Tolerances (absolute, on coefficients of magnitude up to ~570): oracle vs live reference 1e-4 (fp32 FFT rounding);
-fp32 path 1e-3 (the DFT is an fp32 GEMM: measured 6e-5 in a CPU emulation); tensor-core path 1e-2 (bf16x3 split:
-measured 8e-4).  A plain bf16 DFT would be off by 0.3 -- that is why the split is used.
+Tolerances (absolute, on coefficients of magnitude up to ~570, plus 2e-6 relative to the largest coefficient -- c0 sums
+128 same-sign dB values, so the reference's own fp32 matmul carries that much summation-order noise; the kernel
+accumulates the DCT in fp64): oracle vs live reference 1e-4 (fp32 FFT rounding); fp32 path 1e-3 (the DFT is an fp32
+GEMM: measured 2e-4 on B200); tensor-core path 1e-2 (bf16x3 split: measured 2e-3).  A plain bf16 DFT would be off by
+0.3 -- that is why the split is used.
 """
 import os
 
@@ -76,6 +78,11 @@ def test_cpu_tensors_are_refused():
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU
+def _close(got, want, tol):
+    err = float((got - want).abs().max())
+    assert err < tol + 2e-6 * float(want.abs().max()), err
+
+
 def _run(dev, name, x, precision, cfg=None):
     from a2f_b200 import features
     sr, nf, od, win, hop, nfft = cfg or omf.CONFIGS[name]
@@ -95,8 +102,8 @@ def test_mfcc_gpu_matches_oracle_and_fixture(a2f_lib, dev, name, precision, tol)
     want = omf.mfcc_forward(omf.make_buffers(sr, nf, win, nfft), x, od, win, hop, nfft)
     got = _run(dev, name, x, precision)
     assert tuple(got.shape) == tuple(want.shape)
-    assert float((got - want).abs().max()) < tol
-    assert float((got.numpy() - z[f"{name}_out"]).__abs__().max()) < tol
+    _close(got, want, tol)
+    _close(got, torch.from_numpy(z[f"{name}_out"]), tol)
 
 
 @pytest.mark.gpu
@@ -114,7 +121,7 @@ def test_mfcc_gpu_geometries(a2f_lib, dev, B, N, cfg):
     for precision, tol in (("fp32", 1e-3), ("bf16", 1e-2)):
         got = _run(dev, None, x, precision, cfg)
         assert tuple(got.shape) == (B, od, nf)
-        assert float((got - want).abs().max()) < tol, (precision, float((got - want).abs().max()))
+        _close(got, want, tol)
 
 
 @pytest.mark.gpu
@@ -126,12 +133,12 @@ def test_mfcc_gpu_silence_and_global_cutoff(a2f_lib, dev):
     x = torch.zeros(3, 11440)
     got = _run(dev, "voca", x, "fp32")
     want = omf.mfcc_forward(sd, x, cfg[2], cfg[3], cfg[4], cfg[5])
-    assert float((got - want).abs().max()) < 1e-3
+    _close(got, want, 1e-3)
     x = 1e-4 * oin.speech_like_windows(4, seed=9)
     x[0] *= 1e4
     got = _run(dev, "voca", x, "fp32")
     want = omf.mfcc_forward(sd, x, cfg[2], cfg[3], cfg[4], cfg[5])
-    assert float((got - want).abs().max()) < 1e-3
+    _close(got, want, 1e-3)
     alone = omf.mfcc_forward(sd, x[1:2], cfg[2], cfg[3], cfg[4], cfg[5])
     assert float((want[1:2] - alone).abs().max()) > 1.0          # the cut-off really is batch-global in the reference
 
