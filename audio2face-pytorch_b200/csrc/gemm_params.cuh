@@ -83,4 +83,16 @@ A2F_D float act_grad(float z, int act) {
     }
 }
 
+// GELU'(z) = Phi(z) + z phi(z) for the bf16 tensor-core path: Phi through the tanh form on MUFU.TANH (|error| <= 5e-4,
+// the same approximation the forward epilogues use), phi through MUFU.EX2 -- ~12 instructions instead of erff + expf
+// (~45), in an epilogue that is instruction-issue bound (the data-gradient GEMM of FFN2 evaluates it 7.4 M times).
+A2F_D float gelu_grad_fast(float z) {
+    const float z2 = z * z;
+    const float u = z * fmaf(0.0356774081f, z2, 0.7978845608f);
+    float t, e;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044f * z2));     // exp(-z^2/2)
+    return fmaf(z * 0.39894228040f, e, fmaf(0.5f, t, 0.5f));
+}
+
 }  // namespace a2f

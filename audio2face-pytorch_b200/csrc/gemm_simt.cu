@@ -60,11 +60,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < p.K; k0 += SBK) {
+    // operands of one k-block for this thread (4 consecutive k of one A row and one W row)
+    auto fetch = [&](int k0, float* av, float* wv) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int k = k0 + lk + j;
-            float av = 0.f, wv = 0.f;
+            const int k = k0 + lk + j;
+            av[j] = 0.f;
+            wv[j] = 0.f;
             if (k < p.K) {
                 if (a_row_ok) {
                     if (MODE == 0) {
@@ -72,23 +74,34 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
                             const int sg = k / kseg, kk = k - sg * kseg;
                             const int row = a_t + p.seg_row_off[sg];
                             if (row >= 0 && row < p.a_rows)
-                                av = ld_as_float(A + a_bbase + (long long)row * p.a_row_stride + p.seg_col_off[sg] + kk);
+                                av[j] = ld_as_float(A + a_bbase + (long long)row * p.a_row_stride + p.seg_col_off[sg] + kk);
                         } else if (a_in_range) {
-                            av = ld_as_float(A + a_base + k);
+                            av[j] = ld_as_float(A + a_base + k);
                         }
                     } else {
                         int tap = k / 48, c = k - tap * 48;
                         int t = a_t + tap - 64 + p.seg_row_off[0];
                         if (t >= 0 && t < p.rows_per_batch)
-                            av = ld_as_float(A + a_base + (long long)t * p.a_row_stride + g * 48 + c);
+                            av[j] = ld_as_float(A + a_base + (long long)t * p.a_row_stride + g * 48 + c);
                     }
                 }
-                if (w_row_ok) wv = ld_as_float(W + w_base + k);
+                if (w_row_ok) wv[j] = ld_as_float(W + w_base + k);
             }
-            As[lk + j][lrow] = av;
-            Bs[lk + j][lrow] = wv;
+        }
+    };
+
+    // software pipeline: the global loads of k-block i+1 are in flight while k-block i is multiplied (small grids run
+    // one CTA per SM, where nothing else hides the load latency -- Audio2Mesh at 64 windows, the 64-wide decoder GEMMs)
+    float av[4], wv[4];
+    fetch(0, av, wv);
+    for (int k0 = 0; k0 < p.K; k0 += SBK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            As[lk + j][lrow] = av[j];
+            Bs[lk + j][lrow] = wv[j];
         }
         __syncthreads();
+        if (k0 + SBK < p.K) fetch(k0 + SBK, av, wv);
 #pragma unroll
         for (int kk = 0; kk < SBK; ++kk) {
             float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);

@@ -642,6 +642,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         const int e_act = g.act;
         const bool e_dact = g.resid_mode == A2F_RESID_DACT;
         const bool rtma = p.resid_tma != 0;
+        const bool fast_dgelu = e_dact && p.fast_gelu && e_act == A2F_ACT_GELU;    // bf16 output: MUFU-based GELU'
         constexpr int SBW = Cfg::SBW;
         constexpr int EPC = 16 / (int)sizeof(TC);
         for (int tile = pair; tile < total_tiles; tile += n_pairs) {
@@ -705,8 +706,13 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                             for (int e = 0; e < 4; ++e) {
                                 const float2 f = __bfloat1622float2(h2[e]);
                                 if (e_dact) {
-                                    v[ch * 8 + 2 * e] *= act_grad(f.x, e_act);
-                                    v[ch * 8 + 2 * e + 1] *= act_grad(f.y, e_act);
+                                    if (fast_dgelu) {
+                                        v[ch * 8 + 2 * e] *= gelu_grad_fast(f.x);
+                                        v[ch * 8 + 2 * e + 1] *= gelu_grad_fast(f.y);
+                                    } else {
+                                        v[ch * 8 + 2 * e] *= act_grad(f.x, e_act);
+                                        v[ch * 8 + 2 * e + 1] *= act_grad(f.y, e_act);
+                                    }
                                 } else {
                                     v[ch * 8 + 2 * e] += f.x;
                                     v[ch * 8 + 2 * e + 1] += f.y;

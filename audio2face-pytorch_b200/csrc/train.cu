@@ -106,57 +106,91 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
 // (bf16 casts, W^T operands of the data-gradient GEMMs, implicit-GEMM conv layouts, fused QKV); as separate launches
 // they cost 1.4 ms of a 15.9 ms step, as one launch they cost the HBM traffic.  32x32 smem tiles: the read side
 // follows the smaller source stride, the write side the smaller destination stride.
-__global__ void __launch_bounds__(256) strided_copy_jobs_kernel(const a2f_copy_job* __restrict__ jobs, int n_jobs) {
-    __shared__ float tile[32][33];
-    __shared__ a2f_copy_job jb;
+// One CTA walks CJ_TILES consecutive tiles, CJ_BATCH at a time: the job lookup (a binary search over the device-resident
+// table) is paid once per CTA, and the loads of CJ_BATCH tiles are in flight together before the first barrier -- with one
+// tile per CTA every 1024 elements cost a full load -> barrier -> store round trip (186 k tiles of a FaceFormer re-pack:
+// 330 us per launch against ~90 us of HBM traffic).
+constexpr int CJ_TILES = 8;
+constexpr int CJ_BATCH = 4;
+__global__ void __launch_bounds__(256) strided_copy_jobs_kernel(const a2f_copy_job* __restrict__ jobs, int n_jobs,
+                                                                int total_tiles) {
+    __shared__ float tile[CJ_BATCH][32][33];
+    __shared__ int job0;
+    const int t_first = (int)blockIdx.x * CJ_TILES;
     if (threadIdx.x == 0) {
-        int lo = 0, hi = n_jobs - 1;                   // last job whose first tile is <= blockIdx.x
+        int lo = 0, hi = n_jobs - 1;                   // last job whose first tile is <= t_first
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (jobs[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+            if (jobs[mid].tile0 <= t_first) lo = mid; else hi = mid - 1;
         }
-        jb = jobs[lo];
+        job0 = lo;
     }
     __syncthreads();
-    const int tiles_c = (jb.C + 31) >> 5;
-    const int t = (int)blockIdx.x - jb.tile0;
-    const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    int ji = job0;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float* __restrict__ in = jb.src;
-    if (jb.ld_c <= jb.ld_r) {
+    const int t_end = min(t_first + CJ_TILES, total_tiles);
+    for (int tb = t_first; tb < t_end; tb += CJ_BATCH) {
+        int jidx[CJ_BATCH];
 #pragma unroll
-        for (int j = ty; j < 32; j += 8) {
-            const int r = r0 + j, c = c0 + tx;
-            if (r < jb.R && c < jb.C) tile[j][tx] = in[(long long)r * jb.ld_r + (long long)c * jb.ld_c];
-        }
-    } else {
+        for (int i = 0; i < CJ_BATCH; ++i) {
+            const int tt = tb + i;
+            if (tt < t_end) {
+                while (ji + 1 < n_jobs && jobs[ji + 1].tile0 <= tt) ++ji;      // uniform across the CTA
+                jidx[i] = ji;
+                const a2f_copy_job jb = jobs[ji];
+                const int tiles_c = (jb.C + 31) >> 5;
+                const int t = tt - jb.tile0;
+                const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+                const float* __restrict__ in = jb.src;
+                if (jb.ld_c <= jb.ld_r) {
 #pragma unroll
-        for (int j = ty; j < 32; j += 8) {
-            const int r = r0 + tx, c = c0 + j;
-            if (r < jb.R && c < jb.C) tile[tx][j] = in[(long long)r * jb.ld_r + (long long)c * jb.ld_c];
-        }
-    }
-    __syncthreads();
-    if (jb.ldo_c <= jb.ldo_r) {
+                    for (int j = ty; j < 32; j += 8) {
+                        const int r = r0 + j, c = c0 + tx;
+                        if (r < jb.R && c < jb.C) tile[i][j][tx] = in[(long long)r * jb.ld_r + (long long)c * jb.ld_c];
+                    }
+                } else {
 #pragma unroll
-        for (int j = ty; j < 32; j += 8) {
-            const int r = r0 + j, c = c0 + tx;
-            if (r < jb.R && c < jb.C) {
-                const long long o = (long long)r * jb.ldo_r + (long long)c * jb.ldo_c;
-                if (jb.dst_dtype == A2F_BF16) static_cast<bf16*>(jb.dst)[o] = __float2bfloat16(tile[j][tx]);
-                else static_cast<float*>(jb.dst)[o] = tile[j][tx];
+                    for (int j = ty; j < 32; j += 8) {
+                        const int r = r0 + tx, c = c0 + j;
+                        if (r < jb.R && c < jb.C) tile[i][tx][j] = in[(long long)r * jb.ld_r + (long long)c * jb.ld_c];
+                    }
+                }
+            } else {
+                jidx[i] = -1;
             }
         }
-    } else {
+        __syncthreads();
 #pragma unroll
-        for (int j = ty; j < 32; j += 8) {
-            const int r = r0 + tx, c = c0 + j;
-            if (r < jb.R && c < jb.C) {
-                const long long o = (long long)r * jb.ldo_r + (long long)c * jb.ldo_c;
-                if (jb.dst_dtype == A2F_BF16) static_cast<bf16*>(jb.dst)[o] = __float2bfloat16(tile[tx][j]);
-                else static_cast<float*>(jb.dst)[o] = tile[tx][j];
+        for (int i = 0; i < CJ_BATCH; ++i) {
+            if (jidx[i] < 0) continue;
+            const int tt = tb + i;
+            const a2f_copy_job jb = jobs[jidx[i]];
+            const int tiles_c = (jb.C + 31) >> 5;
+            const int t = tt - jb.tile0;
+            const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+            if (jb.ldo_c <= jb.ldo_r) {
+#pragma unroll
+                for (int j = ty; j < 32; j += 8) {
+                    const int r = r0 + j, c = c0 + tx;
+                    if (r < jb.R && c < jb.C) {
+                        const long long o = (long long)r * jb.ldo_r + (long long)c * jb.ldo_c;
+                        if (jb.dst_dtype == A2F_BF16) static_cast<bf16*>(jb.dst)[o] = __float2bfloat16(tile[i][j][tx]);
+                        else static_cast<float*>(jb.dst)[o] = tile[i][j][tx];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = ty; j < 32; j += 8) {
+                    const int r = r0 + tx, c = c0 + j;
+                    if (r < jb.R && c < jb.C) {
+                        const long long o = (long long)r * jb.ldo_r + (long long)c * jb.ldo_c;
+                        if (jb.dst_dtype == A2F_BF16) static_cast<bf16*>(jb.dst)[o] = __float2bfloat16(tile[i][tx][j]);
+                        else static_cast<float*>(jb.dst)[o] = tile[i][tx][j];
+                    }
+                }
             }
         }
+        __syncthreads();                               // the tile buffers are reused by the next batch
     }
 }
 
@@ -194,9 +228,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TI* __restrict__ x, l
 }
 
 // 16-byte loads (8 bf16 / 4 fp32 columns per thread): CTA = 32 column groups x 8 row lanes over a 64-row slab.
+struct ColsumOuts {
+    float* p[3];
+    int seg_cols;        // columns per output segment (cols when there is one output)
+};
 template <typename TI>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const TI* __restrict__ x, long long ld, long long rows, int cols,
-                                                         float* __restrict__ out) {
+                                                         ColsumOuts outs) {
     constexpr int VEC = 16 / (int)sizeof(TI);
     __shared__ float sh[8][32 * VEC + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -233,7 +271,8 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const TI* __restrict__ 
             float t = 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) t += sh[k][i];
-            atomicAdd(out + cc, t);
+            const int sg = cc / outs.seg_cols;
+            atomicAdd(outs.p[sg] + (cc - sg * outs.seg_cols), t);
         }
     }
 }
@@ -714,7 +753,7 @@ int a2f_strided_copy_jobs(const a2f_copy_job* jobs_dev, int n_jobs, int total_ti
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(jobs_dev && n_jobs > 0 && total_tiles > 0, "a2f_strided_copy_jobs: bad arguments");
-    strided_copy_jobs_kernel<<<total_tiles, 256, 0, as_stream(stream)>>>(jobs_dev, n_jobs);
+    strided_copy_jobs_kernel<<<(total_tiles + CJ_TILES - 1) / CJ_TILES, 256, 0, as_stream(stream)>>>(jobs_dev, n_jobs, total_tiles);
     A2F_CHECK_LAUNCH("strided_copy_jobs_kernel");
     count_launch();
     return A2F_OK;
@@ -741,8 +780,10 @@ int a2f_colsum(const void* x, int dtype, long long ld, long long rows, int cols,
     const int vec = dtype == A2F_BF16 ? 8 : 4;
     if (cols % vec == 0 && ld % vec == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && rows >= 64) {
         const dim3 vgrid((cols / vec + 31) / 32, (unsigned)((rows + 63) / 64));
-        if (dtype == A2F_BF16) colsum_vec_kernel<bf16><<<vgrid, 256, 0, s>>>((const bf16*)x, ld, rows, cols, out);
-        else colsum_vec_kernel<float><<<vgrid, 256, 0, s>>>((const float*)x, ld, rows, cols, out);
+        ColsumOuts outs;
+        outs.p[0] = out; outs.p[1] = outs.p[2] = nullptr; outs.seg_cols = cols;
+        if (dtype == A2F_BF16) colsum_vec_kernel<bf16><<<vgrid, 256, 0, s>>>((const bf16*)x, ld, rows, cols, outs);
+        else colsum_vec_kernel<float><<<vgrid, 256, 0, s>>>((const float*)x, ld, rows, cols, outs);
         A2F_CHECK_LAUNCH("colsum_vec_kernel");
         count_launch();
         return A2F_OK;
@@ -751,6 +792,35 @@ int a2f_colsum(const void* x, int dtype, long long ld, long long rows, int cols,
     if (dtype == A2F_BF16) colsum_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, ld, rows, cols, out);
     else colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, ld, rows, cols, out);
     A2F_CHECK_LAUNCH("colsum_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_colsum3(const void* x, int dtype, long long ld, long long rows, int seg_cols, float* out0, float* out1, float* out2,
+                void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(x && out0 && out1 && out2 && rows >= 0 && seg_cols > 0 && ld >= 3 * seg_cols, "a2f_colsum3: bad arguments");
+    if (rows == 0) return A2F_OK;
+    const int vec = dtype == A2F_BF16 ? 8 : 4;
+    if (!(seg_cols % vec == 0 && ld % vec == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && rows >= 64)) {
+        // small or unaligned: three ordinary launches
+        const size_t esz = dtype == A2F_BF16 ? 2 : 4;
+        float* outs[3] = {out0, out1, out2};
+        for (int i = 0; i < 3; ++i) {
+            rc = a2f_colsum(static_cast<const char*>(x) + (size_t)i * seg_cols * esz, dtype, ld, rows, seg_cols, outs[i], stream);
+            if (rc != A2F_OK) return rc;
+        }
+        return A2F_OK;
+    }
+    const int cols = 3 * seg_cols;
+    const dim3 vgrid((cols / vec + 31) / 32, (unsigned)((rows + 63) / 64));
+    ColsumOuts outs;
+    outs.p[0] = out0; outs.p[1] = out1; outs.p[2] = out2; outs.seg_cols = seg_cols;
+    cudaStream_t s = as_stream(stream);
+    if (dtype == A2F_BF16) colsum_vec_kernel<bf16><<<vgrid, 256, 0, s>>>((const bf16*)x, ld, rows, cols, outs);
+    else colsum_vec_kernel<float><<<vgrid, 256, 0, s>>>((const float*)x, ld, rows, cols, outs);
+    A2F_CHECK_LAUNCH("colsum_vec_kernel");
     count_launch();
     return A2F_OK;
 }

@@ -439,6 +439,14 @@ def colsum(x: torch.Tensor, out: torch.Tensor, rows: Optional[int] = None, cols:
     return out
 
 
+def colsum3(x: torch.Tensor, outs) -> None:
+    """outs[i][n] += sum_m x[m, i*seg + n] for the three column segments of a fused [M, 3*seg] gradient, one launch."""
+    _dev(x, *outs)
+    seg = x.shape[1] // 3
+    L.check(L.load().a2f_colsum3(x.data_ptr(), _dt(x), x.stride(0), x.shape[0], seg, outs[0].data_ptr(), outs[1].data_ptr(),
+                                 outs[2].data_ptr(), _stream()), "a2f_colsum3")
+
+
 def spec_mask_fwd(h: torch.Tensor, mask_u8: torch.Tensor, embed: torch.Tensor) -> torch.Tensor:
     """h[mask] = embed, in place (ref:src/model/wav2vec.py:159-161).  h [rows, cols], mask_u8 uint8 [rows]."""
     _dev(h, mask_u8, embed)

@@ -37,7 +37,7 @@ class FlatBuffers:
     stage by stage (original order inside a stage); `p.data` and `p.grad` become views into `params` / `grads`."""
 
     def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], stage_of: Callable[[str], int],
-                 n_stages: int, skip: Iterable[str] = ()):
+                 n_stages: int, skip: Iterable[str] = (), order_in_stage: Optional[Callable[[str], int]] = None):
         skip = set(skip)
         items = [(n, p) for n, p in named_params if n not in skip and p.requires_grad]
         if not items:
@@ -46,7 +46,10 @@ class FlatBuffers:
         for n, p in items:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError(f"{n}: flat buffers hold fp32 parameters of one device")
-        order = sorted(range(len(items)), key=lambda i: (stage_of(items[i][0]), i))
+        # order_in_stage(name): optional rank inside a stage (ties keep the original order); used to make q/k/v weight
+        # (and bias) gradients adjacent so that one fused weight-gradient GEMM / column sum writes all three
+        rank = order_in_stage if order_in_stage is not None else (lambda n: 0)
+        order = sorted(range(len(items)), key=lambda i: (stage_of(items[i][0]), rank(items[i][0]), i))
         self.entries: List[Tuple[str, torch.nn.Parameter, int, int, int]] = []
         self.stage_ranges: List[Tuple[int, int]] = []
         off = 0
@@ -134,7 +137,7 @@ class FaceformerTrainer:
         self.overlap = overlap
         self.group = group
         self.flat = FlatBuffers(model.named_parameters(), training.grad_stage_of, training.N_GRAD_STAGES,
-                                skip=training.no_grad_params(model))
+                                skip=training.no_grad_params(model), order_in_stage=training.grad_order_in_stage)
         self.exp_avg = torch.zeros_like(self.flat.params)
         self.exp_avg_sq = torch.zeros_like(self.flat.params)
         self.steps = 0

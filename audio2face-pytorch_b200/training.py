@@ -310,9 +310,18 @@ def backward(model, tp: Dict, dout: torch.Tensor, on_ready=None) -> None:
         datt = torch.empty((M, 768), dtype=dt, device=dev)
         ops.gemm(dpre1, W["o_t"], datt, backend=be)
         dqkv = ops.mha_bwd(s["qkv"], s["att"], datt, s["lse"], B, T, out_f32=s["att32"])
-        for j, lin in enumerate((a.q_proj, a.k_proj, a.v_proj)):
-            ops.gemm_wgrad(dqkv, s["h_in"], _grad(lin.weight), backend=be, N=768, dy_offset=768 * j)
-            ops.colsum(dqkv[:, 768 * j: 768 * (j + 1)], _grad(lin.bias), ld=2304)
+        gw = [_grad(lin.weight) for lin in (a.q_proj, a.k_proj, a.v_proj)]
+        gb = [_grad(lin.bias) for lin in (a.q_proj, a.k_proj, a.v_proj)]
+        if _adjacent(gw):
+            # flat gradient buffer (trainer.FlatBuffers orders q | k | v back to back): one fused [2304, 768] GEMM
+            ops.gemm_wgrad(dqkv, s["h_in"], gw[0].as_strided((2304, 768), (768, 1)), backend=be)
+        else:
+            for j in range(3):
+                ops.gemm_wgrad(dqkv, s["h_in"], gw[j], backend=be, N=768, dy_offset=768 * j)
+        if _adjacent(gb):
+            ops.colsum(dqkv, gb[0].as_strided((2304,), (1,)))
+        else:
+            ops.colsum3(dqkv, gb)
         dh = torch.empty((M, 768), dtype=dt, device=dev)
         ops.gemm(dqkv, W["qkv_t"], dh, resid=dpre1, backend=be)
         stage += 1
@@ -392,6 +401,28 @@ def grad_stage_of(name: str) -> int:
     if name.startswith("audio_encoder."):
         return N_GRAD_STAGES - 1
     return 0
+
+
+_QKV_RANK = {"attention.q_proj.weight": 0, "attention.k_proj.weight": 1, "attention.v_proj.weight": 2,
+             "attention.q_proj.bias": 3, "attention.k_proj.bias": 4, "attention.v_proj.bias": 5}
+
+
+def grad_order_in_stage(name: str) -> int:
+    """Rank of a parameter inside its stage of the flat gradient buffer: q, k, v projection weights first and adjacent
+    (then their biases), so that backward() can write all three gradients with ONE [2304, 768] weight-gradient GEMM."""
+    for suffix, r in _QKV_RANK.items():
+        if name.endswith(suffix):
+            return r
+    return 6
+
+
+def _adjacent(ts) -> bool:
+    """True when the tensors are contiguous and laid out back to back in one storage (the flat gradient buffer)."""
+    for a, b in zip(ts[:-1], ts[1:]):
+        if not (a.is_contiguous() and b.is_contiguous()) or a.untyped_storage().data_ptr() != b.untyped_storage().data_ptr() \
+                or b.data_ptr() != a.data_ptr() + a.numel() * a.element_size():
+            return False
+    return True
 
 
 class FaceformerTrainFn(torch.autograd.Function):

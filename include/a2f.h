@@ -394,6 +394,9 @@ int a2f_add_strided3(const float* in, float* out, int n0, int n1, int n2, long l
                      long long so0, long long so1, long long so2, void* stream);
 /* bias gradient: out[n] += sum_m x[m*ld + n] */
 int a2f_colsum(const void* x, int dtype, long long ld, long long rows, int cols, float* out, void* stream);
+/* three bias gradients from one pass over a fused [rows, 3*seg_cols] gradient (q | k | v): out_i[n] += sum_m x[m*ld + i*seg_cols + n] */
+int a2f_colsum3(const void* x, int dtype, long long ld, long long rows, int seg_cols, float* out0, float* out1, float* out2,
+                void* stream);
 /* SpecAugment time masking (training only), replaces `hidden_states[mask_time_indices] = masked_spec_embed` of
  * ref:src/model/wav2vec.py:149-162.  h / dh: [rows, cols] activations (fp32 or bf16) modified in place; mask: one byte
  * per row, non-zero = masked (the host draws it with the reference's numpy sequence, spec_augment.py); embed /
