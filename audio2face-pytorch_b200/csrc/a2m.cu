@@ -48,6 +48,58 @@ __global__ void channel_affine_kernel(T* __restrict__ x, const float* __restrict
     }
 }
 
+// Tensor-core path of the conv stack (precision "bf16"): explicit im2col of a 1-D convolution over the middle axis of a
+// channels-last fp32 activation [outer, L, C] into the error-compensated bf16 split [hi | lo | hi] (three Kpad-wide
+// blocks per row, Kpad = taps*C rounded up to 64), which a2f_gemm multiplies with the weight split [hi | hi | lo] on
+// tcgen05 -- hi*hi + lo*hi + hi*lo keeps ~2^-16 relative accuracy, so ten chained layers stay inside the 5e-4 m budget
+// that a plain bf16 trunk misses (1 % of the offset scale).  An eval-mode BatchNorm that PRECEDES the conv is applied here
+// (per-channel affine on in-range taps only: the zero padding comes after the BatchNorm in the reference).
+// One thread per 8 consecutive k of one output row.
+__global__ void __launch_bounds__(256) im2col1d_split_kernel(const float* __restrict__ x, long long outer_stride, int ld, int C,
+                                                             int L, int L_out, int taps, int stride, int pad,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             long long rows, int kpad, bf16* __restrict__ out) {
+    pdl_sync();
+    const int chunks = kpad >> 3;
+    const int K = taps * C;
+    const long long total = rows * chunks;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long long row = i / chunks;
+        const int lo = (int)(row % L_out);
+        const long long o = row / L_out;
+        const float* xo = x + o * outer_stride;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = ch * 8 + e;
+            float a = 0.f;
+            if (k < K) {
+                const int tap = k / C, c = k - tap * C;
+                const int l = lo * stride - pad + tap;
+                if (l >= 0 && l < L) {
+                    a = __ldg(xo + (long long)l * ld + c);
+                    if (scale != nullptr) a = fmaf(a, __ldg(scale + c), __ldg(shift + c));
+                }
+            }
+            v[e] = a;
+        }
+        uint32_t hi[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bf16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+            __nv_bfloat162 hh(h0, h1);
+            hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+            lw[e] = pack_bf16x2(v[2 * e] - __bfloat162float(h0), v[2 * e + 1] - __bfloat162float(h1));
+        }
+        bf16* op = out + row * 3 * kpad + ch * 8;
+        const uint4 uh = make_uint4(hi[0], hi[1], hi[2], hi[3]), ul = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *reinterpret_cast<uint4*>(op) = uh;
+        *reinterpret_cast<uint4*>(op + kpad) = ul;
+        *reinterpret_cast<uint4*>(op + 2 * kpad) = uh;
+    }
+}
+
 }  // namespace a2f
 
 using namespace a2f;
@@ -63,6 +115,27 @@ int a2f_a2m_assemble(const float* x, const float* one_hot, int n_onehot, float* 
     const int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
     a2m_assemble_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, one_hot, n_onehot, out, B);
     A2F_CHECK_LAUNCH("a2m_assemble_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_im2col1d_split(const float* x, long long outer, long long outer_stride, int ld, int C, int L, int taps, int stride,
+                        int pad, const float* scale, const float* shift, int kpad, void* out, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(x && out && outer > 0 && C > 0 && L > 0 && taps > 0 && stride > 0 && pad >= 0 && ld >= C,
+                "a2f_im2col1d_split: bad arguments");
+    A2F_REQUIRE((scale == nullptr) == (shift == nullptr), "a2f_im2col1d_split: scale and shift come together");
+    A2F_REQUIRE(kpad >= taps * C && kpad % 8 == 0, "a2f_im2col1d_split: kpad must cover taps*C and be a multiple of 8");
+    A2F_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, "a2f_im2col1d_split: out must be 16-byte aligned");
+    const int L_out = (L + 2 * pad - taps) / stride + 1;
+    A2F_REQUIRE(L_out > 0, "a2f_im2col1d_split: empty output");
+    const long long rows = outer * L_out;
+    const long long total = rows * (kpad / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    A2F_CHECK_CUDA(launch_pdl(im2col1d_split_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), x, outer_stride, ld, C,
+                              L, L_out, taps, stride, pad, scale, shift, rows, kpad, static_cast<bf16*>(out)));
     count_launch();
     return A2F_OK;
 }

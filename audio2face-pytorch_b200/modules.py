@@ -242,6 +242,56 @@ class Audio2Mesh(_A2FModule):
         srcs = list(self.parameters()) + [b for b in self.buffers()]
         return self._cache.get("a2m", srcs, build)
 
+    def _packed_tc(self):
+        """Tensor-core operands of the conv stack: BN-folded weights [Cout, taps*Cin] zero-padded to Kpad (multiple of
+        64) and split hi|hi|lo into bf16 (ops.split_bf16x3) -- the partner of ops.im2col1d_split's hi|lo|hi rows."""
+        def build():
+            P = self._packed()
+            out = {"ana": [], "art": []}
+
+            def split(w):
+                kpad = (w.shape[1] + 63) // 64 * 64
+                wp = torch.zeros((w.shape[0], kpad), dtype=torch.float32, device=w.device)
+                wp[:, :w.shape[1]] = w
+                return ops.split_bf16x3(wp, True), kpad
+            for w, b in P["ana"]:
+                out["ana"].append(split(w) + (b,))
+            for ent in P["art"]:
+                out["art"].append(split(ent[0]) + tuple(ent[1:]))
+            return out
+        srcs = list(self.parameters()) + [b for b in self.buffers()]
+        return self._cache.get("a2m_tc", srcs, build)
+
+    def _trunk_tc(self, x, one_hot, bs):
+        """conv stack on tcgen05 (precision "bf16"): per layer one im2col (fp32 -> bf16 hi|lo|hi split, padding and a
+        preceding BatchNorm applied on the fly) and one GEMM with the bias + ReLU epilogue; activations stay fp32."""
+        P = self._packed_tc()
+        dev = x.device
+        T = L.TCGEN05
+        cur = ops.a2m_assemble(x, one_hot)                                   # [B,64,33], column 0 is a zero pad (unused here)
+        outer, ostride, ld, Ci, Li, xoff = bs * 64, 33, 1, 1, 32, 1
+        for i in range(5):                                                   # formant analysis net: conv along W
+            w3, kpad, b = P["ana"][i]
+            Co = self._CH[i + 1]
+            a3 = ops.im2col1d_split(cur, outer, ostride, ld, Ci, Li, 3, 2, 1, kpad, x_offset=xoff)
+            Lo = Li // 2
+            ldc = (Co + 3) // 4 * 4
+            out = torch.empty((outer * Lo, ldc), dtype=torch.float32, device=dev)
+            ops.gemm(a3, w3, out, bias=b, act=L.ACT_RELU, backend=T, N=Co, ldc=ldc)
+            cur, ostride, ld, Ci, Li, xoff = out, Lo * ldc, ldc, Co, Lo, 0
+        outer, ostride, Li = bs, 64 * 256, 64                                # [B*64, 1, 256] is [B, 64, 256]
+        for j in range(5):                                                   # articulation net: conv along H
+            ent = P["art"][j]
+            w3, kpad, b = ent[0], ent[1], ent[2]
+            sc, sh = (ent[3], ent[4]) if len(ent) > 3 else (None, None)
+            taps, stride, pad = (3, 2, 1) if j < 4 else (4, 4, 0)
+            a3 = ops.im2col1d_split(cur, outer, ostride, 256, 256, Li, taps, stride, pad, kpad, scale=sc, shift=sh)
+            Lo = (Li + 2 * pad - taps) // stride + 1
+            out = torch.empty((outer * Lo, 256), dtype=torch.float32, device=dev)
+            ops.gemm(a3, w3, out, bias=b, act=L.ACT_RELU, backend=T)
+            cur, ostride, Li = out, Lo * 256, Lo
+        return cur                                                           # [B, 256]
+
     def forward(self, x, one_hot, template, **kwargs):
         self._need_cuda(x, one_hot, template)
         bs = x.size(0)
@@ -262,6 +312,9 @@ class Audio2Mesh(_A2FModule):
                              "run under torch.no_grad()")
         P = self._packed()
         S = L.SIMT_F32
+        if self.precision == "bf16":
+            feat = self._trunk_tc(x, one_hot, bs)
+            return self._output_net(feat, one_hot, tmpl, bs)
         cur = ops.a2m_assemble(x, one_hot)                                   # [B,64,33] (C=1)
         Wi, Ci = 32, 1
         for i in range(5):                                                   # formant analysis net, conv along W
@@ -293,6 +346,11 @@ class Audio2Mesh(_A2FModule):
         feat = torch.empty((bs, 256), dtype=torch.float32, device=dev)
         ops.gemm(cur.view(-1)[256:], w, feat, bias=b, act=L.ACT_RELU, backend=S, M=bs, K=1024, a_row_stride=5 * 256,
                  rows_per_batch=bs)
+        return self._output_net(feat, one_hot, tmpl, bs)
+
+    def _output_net(self, feat, one_hot, tmpl, bs):
+        S = L.SIMT_F32
+        dev = feat.device
         fc = self.output_net
         w0 = fc[0].weight.detach()
         part = torch.empty((bs, 72), dtype=torch.float32, device=dev)        # cat((feat, one_hot)) @ W0^T as two GEMMs

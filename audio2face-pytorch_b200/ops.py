@@ -288,6 +288,18 @@ def channel_affine(buf: torch.Tensor, offset: int, scale: torch.Tensor, shift: t
             "a2f_channel_affine")
 
 
+def im2col1d_split(x: torch.Tensor, outer: int, outer_stride: int, ld: int, C_: int, L_: int, taps: int, stride: int, pad: int,
+                   kpad: int, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+                   x_offset: int = 0) -> torch.Tensor:
+    """fp32 channels-last [outer, L, C] -> bf16 [outer*L_out, 3*kpad] im2col rows in the hi|lo|hi split (a2f_im2col1d_split)."""
+    _dev(x, scale, shift)
+    L_out = (L_ + 2 * pad - taps) // stride + 1
+    out = torch.empty((outer * L_out, 3 * kpad), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().a2f_im2col1d_split(x.data_ptr() + x_offset * 4, outer, outer_stride, ld, C_, L_, taps, stride, pad,
+                                        L.ptr(scale), L.ptr(shift), kpad, out.data_ptr(), _stream()), "a2f_im2col1d_split")
+    return out
+
+
 def pack_feedback(vm_w, vm_b, vmr_w, vmr_b, out=None):
     _dev(vm_w, vm_b, vmr_w, vmr_b)
     if out is None:

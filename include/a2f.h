@@ -306,6 +306,13 @@ typedef struct a2f_voca_weights {
 int a2f_voca_trunk(const a2f_voca_weights* w, const float* x, const float* one_hot, int n_onehot, void* z, int z_dtype,
                    int ldz, int B, void* stream);
 
+/* explicit im2col of a 1-D convolution over the middle axis of a channels-last fp32 activation x[o*outer_stride + l*ld + c]
+ * (o < outer, l < L, c < C) into the error-compensated bf16 split consumed by the tcgen05 GEMM:
+ *   out[(o*L_out + lo), s*kpad + tap*C + c], s = 0,1,2 = hi | lo | hi of  affine(x[o, lo*stride - pad + tap, c])  (0 outside
+ *   [0,L) and for k >= taps*C), L_out = (L + 2*pad - taps)/stride + 1; affine = x*scale[c] + shift[c] when scale != NULL
+ *   (an eval-mode BatchNorm that precedes the conv, ref:src/model/audio2face.py:41-46).  Audio2Mesh trunk, precision "bf16". */
+int a2f_im2col1d_split(const float* x, long long outer, long long outer_stride, int ld, int C, int L, int taps, int stride,
+                        int pad, const float* scale, const float* shift, int kpad, void* out, void* stream);
 /* ------------------------------------------------------------------------------------------------------------
  * Audio2Mesh (ref:src/model/audio2face.py:5-69).  The ten convolutions are a2f_gemm calls over channels-last
  * activations with one zero row/column of left padding ([B,64,W+1,C] for the analysis net, [B,H+1,256] for the

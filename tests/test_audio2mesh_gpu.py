@@ -39,7 +39,10 @@ def test_a2m_fp32_and_bf16_match_oracle(a2f_lib, dev, B):
         got16 = m.set_precision("bf16")(x.to(dev), oh.to(dev), tp.to(dev)).cpu()
     assert got.shape == (B, 5023, 3)
     assert float((got - want).abs().max()) < 1e-5
-    assert float((got16 - want).abs().max()) < 5e-5      # fp32 trunk + error-compensated tensor-core head
+    # precision "bf16": conv stack AND head on tcgen05 with the error-compensated bf16x3 split (im2col hi|lo|hi x weights
+    # hi|hi|lo); the oracle's random-init offsets are O(4 m), so 2e-4 is 5e-5 relative (north-star budget 5e-4 m; a plain
+    # bf16 trunk would be off by 4e-2 here)
+    assert float((got16 - want).abs().max()) < 2e-4
 
 
 def test_a2m_eval_mode_autograd_is_refused_loudly(a2f_lib, dev):
