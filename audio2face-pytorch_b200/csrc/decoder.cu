@@ -513,8 +513,34 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
     int CS = 1;
     if (saves == nullptr && kv != nullptr && g_dec_cluster != 1) {
         if (g_dec_cluster > 1) CS = g_dec_cluster;
-        else if (T >= DEC_CLUSTER_T)
-            while (CS < 8 && 2 * CS * B <= sm_count()) CS *= 2;
+        else if (T >= DEC_CLUSTER_T) {
+            // largest cluster size whose B clusters are all co-resident: a cluster needs CS free SMs inside ONE GPC, so
+            // B*CS <= #SMs is not enough (16 clusters of 8 do not fit the 148 SMs of a B200: the B=16 points of the long
+            // sweep ran in two waves, 2x the B=8 time) -- ask the occupancy calculator for the real limit
+            auto kern = decoder_rollout_kernel<false, true>;
+            A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            for (int cs = 8; cs >= 2; cs >>= 1) {
+                if ((long long)cs * B > sm_count()) continue;
+                cudaLaunchConfig_t q;
+                memset(&q, 0, sizeof(q));
+                q.gridDim = dim3(B * cs, 1, 1);
+                q.blockDim = dim3(DEC_THREADS, 1, 1);
+                q.dynamicSmemBytes = dec_smem_bytes(T, false, cs);
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = cs;
+                qa[0].val.clusterDim.y = 1;
+                qa[0].val.clusterDim.z = 1;
+                q.attrs = qa;
+                q.numAttrs = 1;
+                int n_clusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                if (n_clusters >= B) { CS = cs; break; }
+            }
+        }
     }
     if (CS > 1) {
         DecSaves none = {};
