@@ -199,3 +199,49 @@ class FaceformerTrainer:
         """batch keys as produced by the reference's dataset (ref:src/dataset/vocaset.py:72-77)."""
         verts, tmpl = batch["verts"] * 100, batch["template_vert"] * 100        # ref lightning_model.py:145-148
         return self.step(batch["audio"], batch["one_hot"], tmpl, verts)
+
+
+class ConvModelTrainer:
+    """Training step of the convolutional models (Voca / Audio2Mesh) with an optional feature extractor in front:
+    the reference's default configuration (ref:config.yaml: modelname audio2mesh, feature_extractor mfcc, batch 128)
+    as Lightning runs it (ref:src/model/lightning_model.py:111-117 forward, :145-161 training_step, :209-213 Adam).
+
+    One process per GPU; parameters / gradients / Adam moments in flat fp32 buffers, one all-reduce of the whole
+    gradient (2.2 M floats for Audio2Mesh) and the fused Adam kernel.  BatchNorm statistics stay per replica (the
+    reference has no SyncBN)."""
+
+    def __init__(self, model, feature_extractor=None, lr: float = 1e-4, weight_decay: Optional[float] = None,
+                 betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+        from . import modules
+        if not next(model.parameters()).is_cuda:
+            raise L.A2FError("ConvModelTrainer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.model, self.feature_extractor = model.train(), feature_extractor
+        self.loss = modules.VocaLoss()
+        self.lr = float(lr)
+        self.weight_decay = float(lr / 10 if weight_decay is None else weight_decay)
+        self.betas, self.eps, self.group = betas, float(eps), group
+        self.flat = FlatBuffers(model.named_parameters(), lambda name: 0, 1)
+        self.exp_avg = torch.zeros_like(self.flat.params)
+        self.exp_avg_sq = torch.zeros_like(self.flat.params)
+        self.steps = 0
+        self.flat.broadcast_params(0, group)
+        self.flat.bump_versions()
+
+    def step(self, x, one_hot, template, gt) -> Dict[str, torch.Tensor]:
+        from . import ops
+        self.flat.zero_grads()
+        with torch.no_grad():
+            feat = self.feature_extractor(x).detach() if self.feature_extractor is not None else x
+        with torch.enable_grad():
+            out = self.loss(self.model(feat, one_hot, template), gt)
+            out["loss"].backward()
+        self.flat.finish_all_reduce(self.group)
+        self.steps += 1
+        ops.adam_step(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                      self.eps, self.weight_decay, self.steps, grad_scale=1.0 / _world())
+        self.flat.bump_versions()
+        return {k: v.detach() for k, v in out.items()}
+
+    def training_step(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        verts, tmpl = batch["verts"] * 100, batch["template_vert"] * 100        # ref lightning_model.py:145-148
+        return self.step(batch["audio"], batch["one_hot"], tmpl, verts)

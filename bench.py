@@ -109,7 +109,7 @@ def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: i
     from oracle import inputs as oin, ref_models as orm, weights as ow
 
     torch.set_num_threads(threads)
-    with torch.set_grad_enabled(workload == "faceformer_train"):
+    with torch.set_grad_enabled(workload in ("faceformer_train", "audio2mesh_train")):
         if workload == "faceformer":
             sd = _SD_CACHE.get("faceformer") or _SD_CACHE.setdefault("faceformer", ow.make_state_dict("faceformer", 13))
             n = int(16000 * seconds)
@@ -134,6 +134,27 @@ def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: i
             dt = time.perf_counter() - t0
             return T / dt, (f"1 utterance x {seconds:g} s @ {fps} fps: forward + FaceFormerLoss + autograd backward, fp32, "
                             "reference O(T^2) decode loop (no optimizer step)")
+        if workload == "audio2mesh_train":
+            from oracle import ref_mfcc as omf, ref_train as ort
+            cfg = omf.CONFIGS["audio2mesh"]
+            sd, bufs = ow.make_state_dict("audio2mesh", 12), omf.make_buffers(cfg[0], cfg[1], cfg[3], cfg[5])
+            B = 128
+            x, oh, tp = oin.speech_like_windows(B, seed=1), oin.one_hot(B, 12, 1), oin.batch_templates(B, 1)
+            gt = oin.gt_like((B, 5023, 3), tp, 2)
+
+            def run():
+                with torch.no_grad():
+                    feat = omf.mfcc_forward(bufs, x, cfg[2], cfg[3], cfg[4], cfg[5])
+                ort.conv_loss_and_grads("audio2mesh", sd, feat, oh, tp, gt)
+            run()
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 8.0:
+                run()
+                reps += 1
+            dt = time.perf_counter() - t0
+            return reps * B / dt, (f"{reps} x {B} windows: MFCC + Audio2Mesh train-mode forward + VocaLoss + autograd backward, fp32 "
+                                   "(no optimizer step)")
         if workload == "voca_audio":
             from oracle import ref_mfcc as omf
             cfg = omf.CONFIGS["voca"]
@@ -226,6 +247,16 @@ def workload_config(args):
                 "window": "52 x 32 MFCC", "vertices": 5023, "weights": "random-init (oracle.weights seed 12, randomised BatchNorm stats)",
                 "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
                 "launch": "eager" if args.no_graph else "one CUDA graph per forward (modules.GraphedForward)"}
+    if args.workload == "audio2mesh_train":
+        return {"workload": f"audio2mesh_train_step_b{args.batch}_windows (the reference's own config.yaml: modelname audio2mesh, "
+                            "feature_extractor mfcc, batch 128; BASELINE.json configs[1] shape, training)",
+                "batch_per_gpu": args.batch, "window_samples": 11440, "sample_rate": 22000,
+                "mfcc": "n_mfcc 32, out_dim 52, win 440, hop 220, n_fft 1024 (ref config.yaml)", "vertices": 5023,
+                "step": "MFCC extractor (tcgen05 bf16x3 DFT) + train-mode forward (batch-statistics BatchNorm) + VocaLoss + "
+                        "backward + gradient all-reduce + fused Adam(lr 1e-4, wd 1e-5)",
+                "precision": "fp32 SIMT GEMMs for the model's forward / backward (the 1e-5 parity path)",
+                "weights": "random-init (oracle.weights seed 12)",
+                "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)", "launch": "eager"}
     if args.workload == "voca_audio":
         return {"workload": f"mfcc_plus_voca_b{args.batch}_windows (BASELINE.json configs[0] from raw audio: SURVEY.md 8(f) rank 1 + a18)",
                 "batch_per_gpu": args.batch, "window_samples": 11440, "sample_rate": 22000,
@@ -617,13 +648,125 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_conv_train(args):
+    """The reference's default configuration (ref:config.yaml): Audio2Mesh + MFCC extractor, batch 128, one training step."""
+    import torch
+    import torch.distributed as dist
+
+    from a2f_b200 import features, modules, ops, trainer as tr, lib as L
+    from oracle import inputs as oin, weights as ow       # input / weight generators only (not the timed path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    L.check(lib.a2f_device_check(), "a2f_device_check")
+    B = args.batch
+    model = modules.Audio2Mesh(15069, 12)
+    model.load_state_dict(ow.make_state_dict("audio2mesh", 12), strict=True)
+    model = model.to(dev)
+    ext = features.MFCCExtractor(22000, 32, 52, 440, None, 1024).to(dev).set_precision("bf16")
+    trainer = tr.ConvModelTrainer(model, ext, lr=1e-4)
+    tp = oin.batch_templates(B, 100 + rank)
+    h_in = [oin.speech_like_windows(B, seed=100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(), tp.pin_memory(),
+            oin.gt_like((B, 5023, 3), tp, 200 + rank).pin_memory()]
+    d_in = [t.to(dev) for t in h_in]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flops_step = 3.0 * B * 131.0e6 + B * 2.0 * 53 * 1026 * 440      # fwd + dgrad + wgrad of the model, DFT of the extractor
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n0 = lib.a2f_launch_count()
+    loss0 = float(trainer.step(*d_in)["loss"])
+    launches_per_step = int(lib.a2f_launch_count() - n0)
+    for _ in range(max(3, args.warmup) - 1):
+        trainer.step(*d_in)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev:
+        flush.zero_()
+        s.record()
+        out = trainer.step(*d_in)
+        e.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_s = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
+    loss_last = float(out["loss"])
+    h_loss = torch.empty(3, dtype=torch.float32).pin_memory()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        di = [t.to(dev, non_blocking=True) for t in h_in]
+        o = trainer.step(*di)
+        h_loss.copy_(torch.stack([o["loss"], o["rec_loss"], o["vel_loss"]]), non_blocking=True)
+    t1.record()
+    barrier()
+    e2e_s = t0.elapsed_time(t1) * 1e-3
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.3 * 1.9e9))
+    ops.PROFILE = []
+    for _ in range(2):
+        trainer.step(*d_in)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    if world > 1:
+        t = torch.tensor([dev_s, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    gem = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind == "gemm_simt"]
+    g_flops, g_time = sum(f for f, _ in gem), sum(t for _, t in gem)
+    fp32_peak = 148 * 128 * 2 * 1.965e-3
+    roofline = {"bound": "tensor", "kernel": "a2f::gemm_simt_kernel (fp32 forward / data-gradient GEMMs of the conv stack; weight "
+                                             "gradients run in the SIMT wgrad kernel)",
+                "achieved": g_flops / g_time / 1e12, "peak": fp32_peak, "unit": "TFLOP/s", "frac": g_flops / g_time / 1e12 / fp32_peak,
+                "traffic": None, "peak_source": "fp32 FMA peak of the SIMT path (148 SMs x 128 lanes x 2 x 1.965 GHz)",
+                "launches_per_step": len(gem) // 2, "kernel_share_of_step": (g_time / 2) / (dev_s / args.steps),
+                "whole_step_tflops": flops_step * world * args.steps / dev_s / 1e12}
+    threads = os.cpu_count() or 1
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample = cpu_reference_frames_per_s("audio2mesh_train", args.fps, args.seconds, 1, threads)
+        cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample}
+    line = {
+        "metric": "mesh frames/sec (5023-vert FLAME)", "value": B * world * args.steps / dev_s, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dev_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": B * world * args.steps / e2e_s, "unit": "frames/s",
+                "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in h_in), "d2h_bytes_per_step": 12,
+                "note": "pinned host batch (audio windows, one-hot, template, ground-truth vertices) in, loss scalars out"},
+        "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "loss_first_step": loss0, "loss_last_timed_step": loss_last,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "voca_audio", "audio2mesh", "faceformer_train"])
+    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "voca_audio", "audio2mesh", "faceformer_train",
+                                                                    "audio2mesh_train"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--fps", type=int, default=None)
@@ -634,7 +777,8 @@ def main():
     if args.fps is None:
         args.fps = 60 if args.workload == "faceformer_train" else 30
     if args.batch is None:
-        args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384, "voca_audio": 4096, "audio2mesh": 64}[args.workload]
+        args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384, "voca_audio": 4096, "audio2mesh": 64,
+                      "audio2mesh_train": 128}[args.workload]
     if args.impl == "reference":
         run_reference(args)
         return
@@ -648,6 +792,8 @@ def main():
         sys.exit(subprocess.call(cmd))
     if args.workload == "faceformer_train":
         run_train(args)
+    elif args.workload == "audio2mesh_train":
+        run_conv_train(args)
     else:
         run_ours(args)
 

@@ -103,3 +103,28 @@ def test_torch_optimizer_drives_the_drop_in_module(a2f_lib, dev):
         opt.step()
         losses.append(float(l["loss"]))
     assert losses[-1] < losses[0], losses
+
+
+def test_conv_model_trainer_with_mfcc_extractor_reduces_the_loss(a2f_lib, dev):
+    """trainer.ConvModelTrainer = the reference's default configuration (ref:config.yaml: audio2mesh + mfcc): raw audio
+    windows -> MFCCExtractor -> train-mode Audio2Mesh -> VocaLoss -> backward -> fused Adam on the flat buffers.  The
+    first step's losses must equal the oracle's on the same features, and a few steps must reduce the loss."""
+    from a2f_b200 import features, modules, trainer as tr
+    from oracle import ref_mfcc as omf, ref_train as ort
+    cfg = omf.CONFIGS["audio2mesh"]
+    B = 16
+    sd = ow.make_state_dict("audio2mesh", seed=12)
+    x, oh, tp = oin.speech_like_windows(B, seed=7), oin.one_hot(B, 12, 7), oin.batch_templates(B, 7)
+    gt = oin.gt_like((B, 5023, 3), tp, 8)
+    with torch.no_grad():
+        feat = omf.mfcc_forward(omf.make_buffers(cfg[0], cfg[1], cfg[3], cfg[5]), x, cfg[2], cfg[3], cfg[4], cfg[5])
+    want, _, _ = ort.conv_loss_and_grads("audio2mesh", sd, feat, oh, tp, gt)
+    m = modules.Audio2Mesh(15069, 12).to(dev)
+    m.load_state_dict(sd, strict=True)
+    t = tr.ConvModelTrainer(m, features.MFCCExtractor(*cfg).to(dev), lr=1e-3)
+    losses = [t.step(x.to(dev), oh.to(dev), tp.to(dev), gt.to(dev)) for _ in range(4)]
+    first = {k: float(v) for k, v in losses[0].items()}
+    for k in ("loss", "rec_loss", "vel_loss"):
+        assert abs(first[k] - want[k]) <= 2e-4 * abs(want[k]), (k, first[k], want[k])
+    assert float(losses[-1]["loss"]) < float(losses[0]["loss"])
+    assert set(m.state_dict().keys()) == set(sd.keys())
