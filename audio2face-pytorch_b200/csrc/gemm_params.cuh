@@ -29,6 +29,9 @@ struct GemmParams {
     int seg_col_off[4] = {0, 0, 0, 0};
     long long r_batch_stride = 0; // 0 = rows_per_batch * ldr
     int resid_mode = 0;
+    // SIMT back end only: K range split over gridDim.z (fp32 atomicAdd into a zeroed C), set by gemm_simt itself
+    int split_k = 1;
+    int k_per_split = 0;
 };
 
 inline void normalize_gemm(GemmParams& p) {

@@ -61,13 +61,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
     // operands of one k-block for this thread (4 consecutive k of one A row and one W row)
+    const int k_lim = (MODE == 0 && p.split_k > 1) ? min(p.K, ((int)blockIdx.z + 1) * p.k_per_split) : p.K;
     auto fetch = [&](int k0, float* av, float* wv) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = k0 + lk + j;
             av[j] = 0.f;
             wv[j] = 0.f;
-            if (k < p.K) {
+            if (k < k_lim) {
                 if (a_row_ok) {
                     if (MODE == 0) {
                         if (p.n_seg > 0) {
@@ -92,16 +93,19 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
 
     // software pipeline: the global loads of k-block i+1 are in flight while k-block i is multiplied (small grids run
     // one CTA per SM, where nothing else hides the load latency -- Audio2Mesh at 64 windows, the 64-wide decoder GEMMs)
+    // split-K (MODE 0 only): this CTA's slice of the contraction
+    const int k_begin = (MODE == 0 && p.split_k > 1) ? (int)blockIdx.z * p.k_per_split : 0;
+    const int k_end = (MODE == 0 && p.split_k > 1) ? min(p.K, k_begin + p.k_per_split) : p.K;
     float av[4], wv[4];
-    fetch(0, av, wv);
-    for (int k0 = 0; k0 < p.K; k0 += SBK) {
+    fetch(k_begin, av, wv);
+    for (int k0 = k_begin; k0 < k_end; k0 += SBK) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             As[lk + j][lrow] = av[j];
             Bs[lk + j][lrow] = wv[j];
         }
         __syncthreads();
-        if (k0 + SBK < p.K) fetch(k0 + SBK, av, wv);
+        if (k0 + SBK < k_end) fetch(k0 + SBK, av, wv);
 #pragma unroll
         for (int kk = 0; kk < SBK; ++kk) {
             float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -127,6 +131,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
             if (n >= p.N) continue;
             int nc = n + col_off;
             float v = acc[i][j];
+            if (MODE == 0 && p.split_k > 1) {
+                // partial sum of one K slice: accumulate into the zeroed output (bias once, from slice 0)
+                if (bias && blockIdx.z == 0) v += bias[nc];
+                const long long crow_s = (long long)(m / p.rows_per_batch) * p.c_batch_stride + (long long)(m % p.rows_per_batch) * p.ldc;
+                atomicAdd(reinterpret_cast<float*>(C) + crow_s + nc, v);
+                continue;
+            }
             if (p.resid_mode == A2F_RESID_DACT) {
                 const long long ri = (long long)(m / p.rows_per_batch) * p.r_batch_stride +
                                      (long long)(m % p.rows_per_batch) * p.ldr + nc;
@@ -165,6 +176,21 @@ int gemm_simt(const GemmParams& p_in, int a_bf16, int c_bf16, cudaStream_t s) {
     if (p_in.M <= 0 || p_in.N <= 0) return A2F_OK;
     GemmParams p = p_in;
     normalize_gemm(p);
+    // split-K: a long contraction behind a handful of output tiles (the vertex-head data gradient of the conv models is
+    // M=128, N=50, K=15069 -- two CTAs walking 942 k-blocks, 0.77 ms) is spread over gridDim.z; plain linear epilogues only
+    const long long tiles = (long long)((p.N + SBN - 1) / SBN) * ((p.M + SBM - 1) / SBM);
+    if (!c_bf16 && p.K >= 2048 && tiles * 4 <= sm_count() && p.act == A2F_ACT_NONE && p.resid == nullptr && p.tmpl == nullptr &&
+        p.n_seg == 0 && p.rows_per_batch == p.M) {
+        int splits = (int)(2LL * sm_count() / tiles);
+        const int max_splits = p.K / 256;
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 1) {
+            p.k_per_split = ((p.K + splits - 1) / splits + SBK - 1) / SBK * SBK;
+            p.split_k = (p.K + p.k_per_split - 1) / p.k_per_split;
+            A2F_CHECK_CUDA(cudaMemset2DAsync(p.C, (size_t)p.ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), (size_t)p.M, s));
+            return launch_simt<0>(p, a_bf16, c_bf16, p.split_k, s);
+        }
+    }
     return launch_simt<0>(p, a_bf16, c_bf16, 1, s);
 }
 int posconv_simt(const GemmParams& p_in, int a_bf16, int c_bf16, cudaStream_t s) {

@@ -1,6 +1,6 @@
 """Per-call device timeline of one step of the hot path, measured with CUDA events around EVERY C-ABI call.
 
-    python tools/step_timeline.py [infer|train] [B] [fps]
+    python tools/step_timeline.py [infer|train|a2m_train|a2m] [B] [fps]
 
 The GPU is first parked on a long spin kernel so that the host has enqueued the whole step (calls + events) before
 the device starts: the event pairs then measure the kernels back to back, warm L2, real clocks -- without the
@@ -55,6 +55,27 @@ def main():
     fps = int(sys.argv[3]) if len(sys.argv) > 3 else (30 if mode == "infer" else 60)
     rec = Recorder()
     dev = torch.device("cuda:0")
+    if mode in ("a2m_train", "a2m"):
+        from a2f_b200 import features
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else (128 if mode == "a2m_train" else 64)
+        am = modules.Audio2Mesh(15069, 12)
+        am.load_state_dict(ow.make_state_dict("audio2mesh", 12), strict=True)
+        am = am.to(dev)
+        ext = features.MFCCExtractor(22000, 32, 52, 440, None, 1024).to(dev).set_precision("bf16")
+        tp = oin.batch_templates(B, 1)
+        x, oh, tpl = oin.speech_like_windows(B, seed=1).to(dev), oin.one_hot(B, 12, 1).to(dev), tp.to(dev)
+        if mode == "a2m_train":
+            t = tr.ConvModelTrainer(am, ext, lr=1e-4)
+            gt = oin.gt_like((B, 5023, 3), tp, 2).to(dev)
+            step = lambda: t.step(x, oh, tpl, gt)                        # noqa: E731
+        else:
+            am = am.eval().set_precision("bf16")
+
+            def step():
+                with torch.no_grad():
+                    return am(ext(x), oh, tpl)
+        fps, T = 0, 1
+        return run(rec, step, mode, B, fps, T)
     m = modules.Faceformer(15069, 12)
     m.load_state_dict(ow.make_state_dict("faceformer", 13), strict=True)
     m = m.to(dev).eval().set_precision("bf16")
@@ -70,10 +91,14 @@ def main():
         def step():
             with torch.no_grad():
                 return m(audio, oh, tpl, fps=fps)
+    return run(rec, step, mode, B, fps, T)
+
+
+def run(rec, step, mode, B, fps, T):
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    torch.cuda._sleep(int(1.9e9 * (0.06 if mode == "infer" else 0.25)))     # park the GPU while the host enqueues
+    torch.cuda._sleep(int(1.9e9 * (0.06 if mode in ("infer", "a2m") else 0.25)))     # park the GPU while the host enqueues
     rec.on = True
     s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
