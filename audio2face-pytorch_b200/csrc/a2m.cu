@@ -100,6 +100,61 @@ __global__ void __launch_bounds__(256) im2col1d_split_kernel(const float* __rest
     }
 }
 
+// Fused output MLP of Audio2Mesh (ref:src/model/audio2face.py:49-55,64-66 without the last Linear, which is the shared
+// vertex head): z = W2 tanh(W1 (W0 [feat ; one_hot] + b0) + b1) + b2, zero-padded to ldz columns.  Four SIMT GEMM launches
+// of 17-29 us each at 64 windows (profiles/r1_timeline_a2m_infer_b64.txt) become one; MLP_WPB rows per CTA, one thread
+// per output neuron, activations in shared memory.
+constexpr int MLP_WPB = 4;
+constexpr int MLP_MAXW = 512;
+__device__ __forceinline__ void mlp_layer(const float* __restrict__ in, int K, float* __restrict__ out, int N,
+                                          const float* __restrict__ w, const float* __restrict__ b, bool tanh_act) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float acc[MLP_WPB];
+        const float bv = __ldg(b + n);
+#pragma unroll
+        for (int i = 0; i < MLP_WPB; ++i) acc[i] = bv;
+        const float* wr = w + (long long)n * K;
+        for (int k = 0; k < K; ++k) {
+            const float wv = __ldg(wr + k);
+#pragma unroll
+            for (int i = 0; i < MLP_WPB; ++i) acc[i] = fmaf(wv, in[i * MLP_MAXW + k], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < MLP_WPB; ++i) out[i * MLP_MAXW + n] = tanh_act ? tanhf(acc[i]) : acc[i];
+    }
+}
+
+__global__ void __launch_bounds__(128) a2m_mlp_kernel(const float* __restrict__ feat, int ld_feat, int K0a,
+                                                      const float* __restrict__ extra, int K0b, const float* __restrict__ w0,
+                                                      const float* __restrict__ b0, int N0, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1, int N1, const float* __restrict__ w2,
+                                                      const float* __restrict__ b2, int N2, float* __restrict__ z, int ldz, int B) {
+    __shared__ float bufA[MLP_WPB * MLP_MAXW];
+    __shared__ float bufB[MLP_WPB * MLP_MAXW];
+    pdl_sync();
+    const int K0 = K0a + K0b;
+    for (int r0 = blockIdx.x * MLP_WPB; r0 < B; r0 += gridDim.x * MLP_WPB) {
+        for (int i = threadIdx.x; i < MLP_WPB * K0; i += blockDim.x) {
+            const int wi = i / K0, k = i - wi * K0, r = r0 + wi;
+            float v = 0.f;
+            if (r < B) v = k < K0a ? feat[(long long)r * ld_feat + k] : extra[(long long)r * K0b + (k - K0a)];
+            bufA[wi * MLP_MAXW + k] = v;
+        }
+        __syncthreads();
+        mlp_layer(bufA, K0, bufB, N0, w0, b0, false);
+        __syncthreads();
+        mlp_layer(bufB, N0, bufA, N1, w1, b1, true);
+        __syncthreads();
+        mlp_layer(bufA, N1, bufB, N2, w2, b2, false);
+        __syncthreads();
+        for (int i = threadIdx.x; i < MLP_WPB * ldz; i += blockDim.x) {
+            const int wi = i / ldz, j = i - wi * ldz, r = r0 + wi;
+            if (r < B) z[(long long)r * ldz + j] = j < N2 ? bufB[wi * MLP_MAXW + j] : 0.f;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace a2f
 
 using namespace a2f;
@@ -136,6 +191,23 @@ int a2f_im2col1d_split(const float* x, long long outer, long long outer_stride, 
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
     A2F_CHECK_CUDA(launch_pdl(im2col1d_split_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), x, outer_stride, ld, C,
                               L, L_out, taps, stride, pad, scale, shift, rows, kpad, static_cast<bf16*>(out)));
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_a2m_mlp(const float* feat, int ld_feat, int k_feat, const float* extra, int k_extra, const float* w0, const float* b0,
+                int n0, const float* w1, const float* b1, int n1, const float* w2, const float* b2, int n2, float* z, int ldz,
+                int B, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(feat && extra && w0 && b0 && w1 && b1 && w2 && b2 && z, "a2f_a2m_mlp: NULL argument");
+    A2F_REQUIRE(k_feat > 0 && k_extra >= 0 && k_feat + k_extra <= MLP_MAXW && n0 > 0 && n0 <= MLP_MAXW && n1 > 0 && n1 <= MLP_MAXW &&
+                n2 > 0 && n2 <= ldz && ldz <= MLP_MAXW && ld_feat >= k_feat, "a2f_a2m_mlp: layer widths must be <= 512");
+    if (B <= 0) return A2F_OK;
+    int grid = (B + MLP_WPB - 1) / MLP_WPB;
+    if (grid > 8 * sm_count()) grid = 8 * sm_count();
+    A2F_CHECK_CUDA(launch_pdl(a2m_mlp_kernel, dim3(grid), dim3(128), 0, as_stream(stream), feat, ld_feat, k_feat, extra, k_extra, w0,
+                              b0, n0, w1, b1, n1, w2, b2, n2, z, ldz, B));
     count_launch();
     return A2F_OK;
 }

@@ -165,6 +165,8 @@ _SIGNATURES = {
     "a2f_colsum3": (c_int, [c_void_p, c_int, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "a2f_im2col1d_split": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                    c_void_p, c_void_p]),
+    "a2f_a2m_mlp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                            c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "a2f_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                               c_int, c_float, c_void_p]),
 }

@@ -349,18 +349,9 @@ class Audio2Mesh(_A2FModule):
         return self._output_net(feat, one_hot, tmpl, bs)
 
     def _output_net(self, feat, one_hot, tmpl, bs):
-        S = L.SIMT_F32
-        dev = feat.device
         fc = self.output_net
-        w0 = fc[0].weight.detach()
-        part = torch.empty((bs, 72), dtype=torch.float32, device=dev)        # cat((feat, one_hot)) @ W0^T as two GEMMs
-        ops.gemm(one_hot, w0[:, 256:], part, bias=fc[0].bias.detach(), backend=S, K=self.n_onehot)
-        f0 = torch.empty((bs, 72), dtype=torch.float32, device=dev)
-        ops.gemm(feat, w0, f0, resid=part, backend=S, K=256)
-        f1 = torch.empty((bs, 128), dtype=torch.float32, device=dev)
-        ops.gemm(f0, fc[1].weight.detach(), f1, bias=fc[1].bias.detach(), act=L.ACT_TANH, backend=S)
-        z = torch.zeros((bs, 64), dtype=torch.float32, device=dev)
-        ops.gemm(f1, fc[3].weight.detach(), z, bias=fc[3].bias.detach(), backend=S, ldc=64)
+        # cat((feat, one_hot)) -> Linear -> Linear -> Tanh -> Linear in one launch (a2f_a2m_mlp), then the shared vertex head
+        z = ops.a2m_mlp(feat, one_hot, fc[0], fc[1], fc[3], ldz=64)
         out = self._vertex_head(z, fc[4].weight, fc[4].bias, tmpl, 1, 50)
         return out.view(bs, -1, 3)
 

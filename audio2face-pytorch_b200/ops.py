@@ -300,6 +300,18 @@ def im2col1d_split(x: torch.Tensor, outer: int, outer_stride: int, ld: int, C_: 
     return out
 
 
+def a2m_mlp(feat: torch.Tensor, extra: torch.Tensor, fc0, fc1, fc2, ldz: int = 64) -> torch.Tensor:
+    """z = fc2(tanh(fc1(fc0(cat(feat, extra))))) zero-padded to ldz columns (a2f_a2m_mlp); fc* are nn.Linear modules."""
+    _dev(feat, extra)
+    B = feat.shape[0]
+    z = torch.empty((B, ldz), dtype=torch.float32, device=feat.device)
+    w = [t.detach().contiguous() for fc in (fc0, fc1, fc2) for t in (fc.weight, fc.bias)]
+    L.check(L.load().a2f_a2m_mlp(feat.data_ptr(), feat.stride(0), feat.shape[1], extra.data_ptr(), extra.shape[1],
+                                 w[0].data_ptr(), w[1].data_ptr(), w[0].shape[0], w[2].data_ptr(), w[3].data_ptr(), w[2].shape[0],
+                                 w[4].data_ptr(), w[5].data_ptr(), w[4].shape[0], z.data_ptr(), ldz, B, _stream()), "a2f_a2m_mlp")
+    return z
+
+
 def pack_feedback(vm_w, vm_b, vmr_w, vmr_b, out=None):
     _dev(vm_w, vm_b, vmr_w, vmr_b)
     if out is None:

@@ -306,6 +306,12 @@ typedef struct a2f_voca_weights {
 int a2f_voca_trunk(const a2f_voca_weights* w, const float* x, const float* one_hot, int n_onehot, void* z, int z_dtype,
                    int ldz, int B, void* stream);
 
+/* fused output MLP of Audio2Mesh (ref:src/model/audio2face.py:49-55 minus the vertex head):
+ *   z[r, :n2] = W2 tanh(W1 (W0 [feat[r, :k_feat] ; extra[r, :k_extra]] + b0) + b1) + b2,  z[r, n2:ldz] = 0
+ * all fp32, row-major weights [n_out, n_in]; every width <= 512. */
+int a2f_a2m_mlp(const float* feat, int ld_feat, int k_feat, const float* extra, int k_extra, const float* w0, const float* b0,
+                int n0, const float* w1, const float* b1, int n1, const float* w2, const float* b2, int n2, float* z, int ldz,
+                int B, void* stream);
 /* explicit im2col of a 1-D convolution over the middle axis of a channels-last fp32 activation x[o*outer_stride + l*ld + c]
  * (o < outer, l < L, c < C) into the error-compensated bf16 split consumed by the tcgen05 GEMM:
  *   out[(o*L_out + lo), s*kpad + tap*C + c], s = 0,1,2 = hi | lo | hi of  affine(x[o, lo*stride - pad + tap, c])  (0 outside
