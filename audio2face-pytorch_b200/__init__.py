@@ -27,10 +27,11 @@ def get_loss_fn(modelname: str):
 
 
 def get_extractor(extractor):
-    """Mirror of ref:src/model/lightning_model.py:61-67 for the extractor on the B200 path ("mfcc"; None -> no extractor)."""
+    """Mirror of ref:src/model/lightning_model.py:61-67 for the extractors on the B200 path ("mfcc", "wav2vec"; None -> no extractor)."""
     from . import features
     if extractor is None:
         return lambda *args, **kwargs: None
-    if extractor != "mfcc":
+    table = {"mfcc": features.MFCCExtractor, "wav2vec": features.Wav2VecExtractor}
+    if extractor not in table:
         raise KeyError(f"extractor {extractor!r} is outside the B200 hot path (SURVEY.md section 8(f))")
-    return features.MFCCExtractor
+    return table[extractor]

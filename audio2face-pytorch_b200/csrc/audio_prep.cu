@@ -60,6 +60,34 @@ __global__ void __launch_bounds__(256) resample_sinc_kernel(const float* __restr
     }
 }
 
+// Bilinear resize (align_corners = False, ATen's source-index formula) of the map M_b[c, t] = h[b, t, c] stored channels-last
+// ([B, T, C], what the encoder kernels write) to out[b, i, j], i < out_h along the channel axis, j < out_w along time:
+// the F.interpolate of ref:src/model/extractor.py:93-96 without materialising the transpose of :92.
+template <typename TI>
+__global__ void __launch_bounds__(256) bilinear_cl_kernel(const TI* __restrict__ h, int B, int T, int C, int out_h, int out_w,
+                                                          float* __restrict__ out) {
+    pdl_sync();
+    const long long total = (long long)B * out_h * out_w;
+    const float sh = (float)C / (float)out_h, sw = (float)T / (float)out_w;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % out_w);
+        const int i = (int)((idx / out_w) % out_h);
+        const long long b = idx / ((long long)out_w * out_h);
+        float fy = sh * ((float)i + 0.5f) - 0.5f, fx = sw * ((float)j + 0.5f) - 0.5f;
+        if (fy < 0.f) fy = 0.f;
+        if (fx < 0.f) fx = 0.f;
+        int y0 = (int)fy, x0 = (int)fx;
+        if (y0 > C - 1) y0 = C - 1;
+        if (x0 > T - 1) x0 = T - 1;
+        const int y1 = y0 + (y0 < C - 1 ? 1 : 0), x1 = x0 + (x0 < T - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const TI* hb = h + b * T * C;
+        const float v00 = ld_as_float(hb + (long long)x0 * C + y0), v01 = ld_as_float(hb + (long long)x1 * C + y0);
+        const float v10 = ld_as_float(hb + (long long)x0 * C + y1), v11 = ld_as_float(hb + (long long)x1 * C + y1);
+        out[idx] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    }
+}
+
 }  // namespace a2f
 
 using namespace a2f;
@@ -89,6 +117,25 @@ int a2f_audio_fragments(const void* audio, int audio_dtype, long long n_samples,
                                   static_cast<const short*>(audio), n_samples, first_frame, n_frames, sample_rate, fps, n_pad,
                                   shift, 1.0f / 32768.0f, out));
     else return set_error(A2F_EINVAL, "a2f_audio_fragments: audio must be fp32 or int16");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_bilinear_cl(const void* h, int h_dtype, int B, int T, int C, int out_h, int out_w, float* out, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(h && out && B > 0 && T > 0 && C > 0 && out_h > 0 && out_w > 0, "a2f_bilinear_cl: bad arguments");
+    const long long total = (long long)B * out_h * out_w;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    cudaStream_t s = as_stream(stream);
+    if (h_dtype == A2F_BF16)
+        A2F_CHECK_CUDA(launch_pdl(bilinear_cl_kernel<bf16>, dim3((unsigned)blocks), dim3(256), 0, s, static_cast<const bf16*>(h), B, T,
+                                  C, out_h, out_w, out));
+    else if (h_dtype == A2F_F32)
+        A2F_CHECK_CUDA(launch_pdl(bilinear_cl_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, s, static_cast<const float*>(h), B, T,
+                                  C, out_h, out_w, out));
+    else return set_error(A2F_EINVAL, "a2f_bilinear_cl: bad dtype");
     count_launch();
     return A2F_OK;
 }

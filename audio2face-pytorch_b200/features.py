@@ -235,3 +235,59 @@ def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Ten
     L.check(L.load().a2f_resample_sinc(x.data_ptr(), B, N, orig, new, k.data_ptr(), k.shape[1], width, out.data_ptr(), target,
                                        torch.cuda.current_stream().cuda_stream), "a2f_resample_sinc")
     return out.view(shape[:-1] + (target,))
+
+
+# ------------------------------------------------------------------------------------------------ wav2vec extractor
+class Wav2VecExtractor(nn.Module):
+    """Drop-in for ref:src/model/extractor.py:63-96: resample to 16 kHz, the HF processor's zero-mean / unit-variance
+    normalisation (computed JOINTLY over the whole [B, N] tensor: a torch tensor is not "batched" for the HF feature
+    extractor, so it is treated as one array -- ref:extractor.py:88-91, HF feature_extraction_wav2vec2.py), the
+    wav2vec2-base encoder (`model.*` parameters, HF Wav2Vec2Model names), transpose and bilinear resize of the
+    [768, frames] map to (out_dim, n_feature).  Output [B, out_dim, n_feature] fp32.
+
+    The encoder is the sm_100a path of modules.Faceformer (conv stack as implicit GEMMs, tcgen05 GEMMs, flash
+    attention); with frame_num = the conv stack's own length its interpolation is an identity, i.e. the plain HF model."""
+
+    def __init__(self, sample_rate: int, n_feature: int, out_dim: int, *args, **kwargs):
+        super().__init__()
+        from .modules import Faceformer
+        self.ori_sample_rate = sample_rate
+        self.sample_rate = 16000
+        self.out_dim = out_dim
+        self.n_feature = n_feature
+        ff = Faceformer(15069, 12)
+        object.__setattr__(self, "_ff", ff)          # compute engine; only its encoder is part of this module's state
+        self.model = ff.audio_encoder                # registered: state_dict keys model.* (HF Wav2Vec2Model layout)
+        self.precision = "fp32"
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        self._ff._apply(fn, *a, **k)                 # decoder / head tensors of the engine follow the device moves
+        return self
+
+    def set_precision(self, precision: str):
+        self._ff.set_precision(precision)
+        self.precision = precision
+        return self
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise L.A2FError("the a2f_b200 modules run on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dim() != 2:
+            raise L.A2FError("Wav2VecExtractor expects (batch, time) audio")
+        with torch.no_grad():
+            x = resample(x.contiguous().float(), self.ori_sample_rate, self.sample_rate).contiguous()
+            B, N = x.shape
+            joint = ops.audio_stats(x.view(1, -1))                    # one (mean, rstd) for the whole tensor
+            stats = joint.expand(B, 2).contiguous()
+            n = (N - 10) // 5 + 1
+            for k in (3, 3, 3, 3, 2, 2):
+                n = (n - k) // 2 + 1
+            if n < 1:
+                raise L.A2FError("audio too short for one wav2vec2 frame")
+            h = self._ff.encode(x, n, stats=stats)                    # [B*n, 768]
+            out = torch.empty((B, self.out_dim, self.n_feature), dtype=torch.float32, device=x.device)
+            L.check(L.load().a2f_bilinear_cl(h.data_ptr(), L.BF16 if h.dtype == torch.bfloat16 else L.F32, B, n, 768, self.out_dim,
+                                             self.n_feature, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                    "a2f_bilinear_cl")
+        return out

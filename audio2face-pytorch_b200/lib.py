@@ -167,6 +167,7 @@ _SIGNATURES = {
                                    c_void_p, c_void_p]),
     "a2f_a2m_mlp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                             c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "a2f_bilinear_cl": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "a2f_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                               c_int, c_float, c_void_p]),
 }

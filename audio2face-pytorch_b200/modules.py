@@ -543,9 +543,12 @@ class Faceformer(_A2FModule):
         return self._cache.get("ff_" + self.precision, srcs, build)
 
     # -- forward ----------------------------------------------------------------------------------------------
-    def encode(self, audio: torch.Tensor, frame_num: int) -> torch.Tensor:
+    def encode(self, audio: torch.Tensor, frame_num: int, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Wav2Vec2Model.forward of ref:src/model/wav2vec.py:91-187 (processor normalisation included):
-        raw audio [B,N] -> last_hidden_state [B*T,768] (bf16 or fp32 by precision)."""
+        raw audio [B,N] -> last_hidden_state [B*T,768] (bf16 or fp32 by precision).  `stats` [B,2] = (mean, rstd) of the
+        processor's normalisation when the caller computes them differently (features.Wav2VecExtractor: one joint
+        statistic for the whole batch); frame_num equal to the conv stack's output length makes the interpolation an
+        identity, i.e. the plain HF Wav2Vec2Model."""
         P = self._packed()
         bf = self.precision == "bf16"
         dt = torch.bfloat16 if bf else torch.float32
@@ -553,7 +556,8 @@ class Faceformer(_A2FModule):
         ae = self.audio_encoder
         B, N = audio.shape
         dev = audio.device
-        stats = ops.audio_stats(audio)
+        if stats is None:
+            stats = ops.audio_stats(audio)
         gn = ae.feature_extractor.conv_layers[0].layer_norm
         x = ops.conv0_gn_gelu(audio, stats, P["conv0_w"], gn.weight.detach(), gn.bias.detach(), dt)   # [B,L0,512]
         L_in = x.shape[1]

@@ -490,6 +490,10 @@ int a2f_audio_fragments(const void* audio, int audio_dtype, long long n_samples,
  * target_len = ceil(nnew*N/orig) outputs per waveform. */
 int a2f_resample_sinc(const float* x, int B, long long N, int orig, int nnew, const float* kernel, int kw, int width, float* out,
                       long long target_len, void* stream);
+/* out[b, i, j] = bilinear resize (align_corners = False) of the map M_b[c, t] = h[b, t, c] (h channels-last [B, T, C], fp32 or
+ * bf16) to out_h x out_w: ref:src/model/extractor.py:92-96 (Wav2VecExtractor: transpose(1,2) + F.interpolate(size=(out_dim,
+ * n_feature), mode="bilinear")) in one pass. */
+int a2f_bilinear_cl(const void* h, int h_dtype, int B, int T, int C, int out_h, int out_w, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Host-buffer entry points (what a non-PyTorch caller binds; also bench.py's e2e leg): pinned or pageable HOST

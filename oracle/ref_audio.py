@@ -43,6 +43,8 @@ def fragments(audio: np.ndarray, n_frames: int, fps: int = 60, sample_rate: int 
 
 
 def resample(x: torch.Tensor, orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99) -> torch.Tensor:
+    if orig_freq == new_freq:                    # torchaudio returns the waveform untouched (no 0.99-Nyquist low-pass)
+        return x
     gcd = math.gcd(int(orig_freq), int(new_freq))
     orig, new = int(orig_freq) // gcd, int(new_freq) // gcd
     base = min(orig, new) * rolloff
