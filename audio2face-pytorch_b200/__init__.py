@@ -12,9 +12,9 @@ def get_model(modelname: str):
     """Mirror of ref:src/model/lightning_model.py:50-58 for the models on the hot path."""
     from . import modules
     table = {"voca": modules.Voca}
-    for opt in ("Audio2Mesh", "Faceformer"):
+    for opt in ("Audio2Mesh", "Faceformer", "Song2Face"):
         if hasattr(modules, opt):
-            table[{"Audio2Mesh": "audio2mesh", "Faceformer": "faceformer"}[opt]] = getattr(modules, opt)
+            table[{"Audio2Mesh": "audio2mesh", "Faceformer": "faceformer", "Song2Face": "song2face"}[opt]] = getattr(modules, opt)
     if modelname not in table:
         raise KeyError(f"model {modelname!r} is outside the B200 hot path (SURVEY.md section 8)")
     return table[modelname]

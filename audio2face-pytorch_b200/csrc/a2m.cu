@@ -55,10 +55,11 @@ __global__ void channel_affine_kernel(T* __restrict__ x, const float* __restrict
 // that a plain bf16 trunk misses (1 % of the offset scale).  An eval-mode BatchNorm that PRECEDES the conv is applied here
 // (per-channel affine on in-range taps only: the zero padding comes after the BatchNorm in the reference).
 // One thread per 8 consecutive k of one output row.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) im2col1d_split_kernel(const float* __restrict__ x, long long outer_stride, int ld, int C,
                                                              int L, int L_out, int taps, int stride, int pad,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
-                                                             long long rows, int kpad, bf16* __restrict__ out) {
+                                                             long long rows, int kpad, void* __restrict__ out_v) {
     pdl_sync();
     const int chunks = kpad >> 3;
     const int K = taps * C;
@@ -84,6 +85,13 @@ __global__ void __launch_bounds__(256) im2col1d_split_kernel(const float* __rest
             }
             v[e] = a;
         }
+        if (!SPLIT) {                                   // fp32 rows [rows, kpad] for the SIMT parity path
+            float* of = static_cast<float*>(out_v) + row * kpad + ch * 8;
+            *reinterpret_cast<float4*>(of) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(of + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            continue;
+        }
+        bf16* out = static_cast<bf16*>(out_v);
         uint32_t hi[4], lw[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -189,8 +197,27 @@ int a2f_im2col1d_split(const float* x, long long outer, long long outer_stride, 
     const long long total = rows * (kpad / 8);
     long long blocks = (total + 255) / 256;
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
-    A2F_CHECK_CUDA(launch_pdl(im2col1d_split_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), x, outer_stride, ld, C,
-                              L, L_out, taps, stride, pad, scale, shift, rows, kpad, static_cast<bf16*>(out)));
+    A2F_CHECK_CUDA(launch_pdl(im2col1d_split_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), x, outer_stride,
+                              ld, C, L, L_out, taps, stride, pad, scale, shift, rows, kpad, out));
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_im2col1d(const float* x, long long outer, long long outer_stride, int ld, int C, int L, int taps, int stride, int pad,
+                 const float* scale, const float* shift, int kpad, float* out, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(x && out && outer > 0 && C > 0 && L > 0 && taps > 0 && stride > 0 && pad >= 0 && ld >= C, "a2f_im2col1d: bad arguments");
+    A2F_REQUIRE((scale == nullptr) == (shift == nullptr), "a2f_im2col1d: scale and shift come together");
+    A2F_REQUIRE(kpad >= taps * C && kpad % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "a2f_im2col1d: bad kpad / alignment");
+    const int L_out = (L + 2 * pad - taps) / stride + 1;
+    A2F_REQUIRE(L_out > 0, "a2f_im2col1d: empty output");
+    const long long rows = outer * L_out;
+    const long long total = rows * (kpad / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+    A2F_CHECK_CUDA(launch_pdl(im2col1d_split_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), x, outer_stride,
+                              ld, C, L, L_out, taps, stride, pad, scale, shift, rows, kpad, static_cast<void*>(out)));
     count_launch();
     return A2F_OK;
 }

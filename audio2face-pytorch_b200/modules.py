@@ -360,6 +360,126 @@ class Audio2Mesh(_A2FModule):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+class Song2Face(_A2FModule):
+    """Drop-in for ref:src/model/song2face.py:5-72 (registry entry "song2face", ref:src/model/lightning_model.py:50-58),
+    inference (eval-mode BatchNorm).  Same sub-module names, so the state_dict keys (and their order) are the reference's.
+
+    Every convolution is an explicit im2col (csrc/a2m.cu) + a2f_gemm with the folded BatchNorm / bias / ReLU epilogue; the
+    two LSTMs run over the CHANNEL axis like the reference (256 steps of 64 / 256 features): input projections of all steps
+    as one GEMM, the recurrence in a2f_lstm_recurrence (csrc/song2face.cu, fp32); the bilinear 256 -> 32 resize writes the
+    channels-last layout the regression convs read; the output MLP and vertex head are Audio2Mesh's.  precision "fp32":
+    SIMT GEMMs (1e-5 parity path); "bf16": tcgen05 GEMMs on the error-compensated bf16x3 split."""
+
+    _CH = (1, 72, 108, 162, 243, 256)
+
+    def __init__(self, n_verts: int, n_onehot: int):
+        super().__init__()
+        self.n_verts = n_verts
+        self.n_onehot = n_onehot
+
+        def conv_bn(ci, co, k, st, pad, bn=True):
+            mods = [nn.Conv2d(ci, co, k, st, pad)]
+            if bn:
+                mods.append(nn.BatchNorm2d(co))
+            mods.append(nn.ReLU())
+            return nn.Sequential(*mods)
+
+        self.vocal_encoder_nn = nn.Sequential(
+            conv_bn(1, 72, (1, 5), (1, 2), (0, 2)), conv_bn(72, 108, (1, 5), (1, 2), (0, 2)),
+            conv_bn(108, 162, (1, 3), (1, 2), (0, 1)), conv_bn(162, 243, (1, 3), (1, 2), (0, 1)),
+            conv_bn(243, 256, (1, 3), (1, 2), (0, 1)))
+        self.vocal_encoder_lstm1 = nn.LSTM(64, 256, 1, bidirectional=False, batch_first=True)
+        self.vocal_encoder_lstm2 = nn.LSTM(256, 256, 1, bidirectional=False, batch_first=True)
+        self.output_net = nn.Sequential(nn.Linear(256 + n_onehot, 72), nn.Linear(72, 128), nn.Tanh(), nn.Linear(128, 50),
+                                        nn.Linear(50, n_verts))
+        self.regression_net = nn.Sequential(
+            conv_bn(256, 256, (3, 1), (2, 1), (1, 0)), conv_bn(256, 256, (3, 1), (2, 1), (1, 0)),
+            conv_bn(256, 256, (3, 1), (2, 1), (1, 0)), conv_bn(256, 256, (3, 1), (2, 1), (0, 0), False))
+
+    def _packed(self):
+        bf = self.precision == "bf16"
+
+        def build():
+            def operand(w2d):                       # [N, K] fp32 -> K padded to 64, bf16x3 split on the tensor-core path
+                kpad = (w2d.shape[1] + 63) // 64 * 64
+                wp = torch.zeros((w2d.shape[0], kpad), dtype=torch.float32, device=w2d.device)
+                wp[:, :w2d.shape[1]] = w2d
+                return (ops.split_bf16x3(wp, True) if bf else wp), kpad
+
+            def conv_entry(seq, taps_dim):
+                conv = seq[0]
+                w = conv.weight.detach()
+                w = w[:, :, 0, :] if taps_dim == 3 else w[:, :, :, 0]
+                mat = w.permute(0, 2, 1).reshape(w.shape[0], -1)             # [Co, tap*Ci + ci]
+                b = conv.bias.detach()
+                if isinstance(seq[1], nn.BatchNorm2d):
+                    s_, t_ = Audio2Mesh._bn_affine(seq[1])
+                    mat, b = mat * s_[:, None], b * s_ + t_
+                return operand(mat.contiguous()) + (b.contiguous(),)
+
+            P = {"enc": [conv_entry(seq, 3) for seq in self.vocal_encoder_nn],
+                 "reg": [conv_entry(seq, 2) for seq in self.regression_net], "lstm": []}
+            for lstm in (self.vocal_encoder_lstm1, self.vocal_encoder_lstm2):
+                w_ih, kpad = operand(lstm.weight_ih_l0.detach())
+                P["lstm"].append((w_ih, kpad, (lstm.bias_ih_l0.detach() + lstm.bias_hh_l0.detach()).contiguous(),
+                                  lstm.weight_hh_l0.detach().t().contiguous()))
+            return P
+        srcs = list(self.parameters()) + [b for b in self.buffers()]
+        return self._cache.get("s2f_" + self.precision, srcs, build)
+
+    def _conv(self, cur, outer, ostride, ld, Ci, Li, taps, stride, pad, ent, Co, x_offset=0):
+        """one conv (+ folded BN) + ReLU over channels-last fp32 [outer, Li, Ci] -> ([outer*Lo, ldc] fp32, Lo, ldc)"""
+        bf = self.precision == "bf16"
+        w, kpad, b = ent
+        a = ops.im2col1d(cur, outer, ostride, ld, Ci, Li, taps, stride, pad, kpad, bf, x_offset=x_offset)
+        Lo = (Li + 2 * pad - taps) // stride + 1
+        ldc = (Co + 3) // 4 * 4
+        out = torch.empty((outer * Lo, ldc), dtype=torch.float32, device=cur.device)
+        ops.gemm(a, w, out, bias=b, act=L.ACT_RELU, backend=self._backend(), N=Co, ldc=ldc)
+        return out, Lo, ldc
+
+    def forward(self, x, one_hot, template, **kwargs):
+        self._need_cuda(x, one_hot, template)
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            raise L.A2FError("Song2Face: only the inference path (eval mode, torch.no_grad()) is built on the sm_100a kernels")
+        bs = x.size(0)
+        x = x.contiguous().float()
+        one_hot = one_hot.contiguous().float()
+        tmpl = template.reshape(bs, -1).contiguous().float()
+        P = self._packed()
+        bf = self.precision == "bf16"
+        cur = ops.a2m_assemble(x, one_hot)                                   # [B,64,33]; column 0 is an unused zero pad
+        outer, ostride, ld, Ci, Li, xoff = bs * 64, 33, 1, 1, 32, 1
+        for i, (taps, pad) in enumerate(((5, 2), (5, 2), (3, 1), (3, 1), (3, 1))):     # vocal encoder, conv along W
+            Co = self._CH[i + 1]
+            cur, Lo, ldc = self._conv(cur, outer, ostride, ld, Ci, Li, taps, 2, pad, P["enc"][i], Co, x_offset=xoff)
+            ostride, ld, Ci, Li, xoff = Lo * ldc, ldc, Co, Lo, 0
+        h = ops.transpose_batched(cur.view(bs, 64, 256))                     # [B, steps = 256 channels, features = 64]
+        for w_ih, kpad, bias, whh_t in P["lstm"]:
+            a2 = h.view(bs * 256, -1)
+            if a2.shape[1] != kpad:                                          # features padded to the packed K
+                ap = torch.zeros((a2.shape[0], kpad), dtype=torch.float32, device=a2.device)
+                ap[:, :a2.shape[1]] = a2
+                a2 = ap
+            a_op = ops.split_bf16x3(a2, False) if bf else a2
+            xp = torch.empty((bs * 256, 1024), dtype=torch.float32, device=x.device)
+            ops.gemm(a_op, w_ih, xp, bias=bias, backend=self._backend())
+            h = ops.lstm_recurrence(xp, whh_t, bs, 256, 256)                 # [B, 256, 256]
+        cur = ops.song2face_resize(h, 32)                                    # [B, 32, 256] channels-last (C = LSTM step)
+        outer, ostride, Li = bs, 32 * 256, 32
+        for i in range(4):                                                   # regression net, conv along the resized axis
+            cur, Lo, _ = self._conv(cur, outer, ostride, 256, 256, Li, 3, 2, 1 if i < 3 else 0, P["reg"][i], 256)
+            ostride, Li = Lo * 256, Lo
+        fc = self.output_net
+        z = ops.a2m_mlp(cur, one_hot, fc[0], fc[1], fc[3], ldz=64)
+        out = self._vertex_head(z, fc[4].weight, fc[4].bias, tmpl, 1, 50)
+        return out.view(bs, -1, 3)
+
+    def predict(self, x, one_hot, template, **kwargs):
+        return self(x, one_hot, template, **kwargs)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 class _Box(nn.Module):
     """Plain namespace module: owns parameters / sub-modules under reference-compatible names, never called."""
 

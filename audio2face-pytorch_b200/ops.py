@@ -300,6 +300,45 @@ def im2col1d_split(x: torch.Tensor, outer: int, outer_stride: int, ld: int, C_: 
     return out
 
 
+def im2col1d(x: torch.Tensor, outer: int, outer_stride: int, ld: int, C_: int, L_: int, taps: int, stride: int, pad: int,
+             kpad: int, split: bool, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+             x_offset: int = 0) -> torch.Tensor:
+    """im2col rows of a 1-D conv over channels-last fp32 [outer, L, C]: bf16 hi|lo|hi split (tcgen05 path) or plain fp32."""
+    if split:
+        return im2col1d_split(x, outer, outer_stride, ld, C_, L_, taps, stride, pad, kpad, scale, shift, x_offset)
+    _dev(x, scale, shift)
+    L_out = (L_ + 2 * pad - taps) // stride + 1
+    out = torch.empty((outer * L_out, kpad), dtype=torch.float32, device=x.device)
+    L.check(L.load().a2f_im2col1d(x.data_ptr() + x_offset * 4, outer, outer_stride, ld, C_, L_, taps, stride, pad, L.ptr(scale),
+                                  L.ptr(shift), kpad, out.data_ptr(), _stream()), "a2f_im2col1d")
+    return out
+
+
+def transpose_batched(x: torch.Tensor) -> torch.Tensor:
+    """[B, R, C] fp32 -> [B, C, R]"""
+    _dev(x)
+    B, R, C_ = x.shape
+    y = torch.empty((B, C_, R), dtype=torch.float32, device=x.device)
+    L.check(L.load().a2f_transpose_batched(x.data_ptr(), y.data_ptr(), B, R, C_, _stream()), "a2f_transpose_batched")
+    return y
+
+
+def lstm_recurrence(xp: torch.Tensor, whh_t: torch.Tensor, B: int, T: int, hidden: int) -> torch.Tensor:
+    _dev(xp, whh_t)
+    h = torch.empty((B, T, hidden), dtype=torch.float32, device=xp.device)
+    L.check(L.load().a2f_lstm_recurrence(xp.data_ptr(), whh_t.data_ptr(), h.data_ptr(), B, T, hidden, _stream()),
+            "a2f_lstm_recurrence")
+    return h
+
+
+def song2face_resize(h: torch.Tensor, out_h: int) -> torch.Tensor:
+    _dev(h)
+    B, T, hid = h.shape
+    out = torch.empty((B, out_h, T), dtype=torch.float32, device=h.device)
+    L.check(L.load().a2f_song2face_resize(h.data_ptr(), B, T, hid, out_h, out.data_ptr(), _stream()), "a2f_song2face_resize")
+    return out
+
+
 def a2m_mlp(feat: torch.Tensor, extra: torch.Tensor, fc0, fc1, fc2, ldz: int = 64) -> torch.Tensor:
     """z = fc2(tanh(fc1(fc0(cat(feat, extra))))) zero-padded to ldz columns (a2f_a2m_mlp); fc* are nn.Linear modules."""
     _dev(feat, extra)

@@ -306,6 +306,20 @@ typedef struct a2f_voca_weights {
 int a2f_voca_trunk(const a2f_voca_weights* w, const float* x, const float* one_hot, int n_onehot, void* z, int z_dtype,
                    int ldz, int B, void* stream);
 
+/* the same im2col with plain fp32 rows [rows, kpad] (SIMT parity path; Song2Face's k=5 / k=3 convolutions) */
+int a2f_im2col1d(const float* x, long long outer, long long outer_stride, int ld, int C, int L, int taps, int stride, int pad,
+                 const float* scale, const float* shift, int kpad, float* out, void* stream);
+/* ---- Song2Face (ref:src/model/song2face.py:5-72) specific pieces; its convolutions, projections, MLP and head reuse
+ * a2f_im2col1d(_split) + a2f_gemm, a2f_a2m_mlp and the vertex-head GEMM ---- */
+/* y[b, c, r] = x[b, r, c]  (fp32): conv output [B, H, C] -> the [B, steps = C, features = H] tensor the LSTM reads */
+int a2f_transpose_batched(const float* x, float* y, int B, int R, int C, void* stream);
+/* single-layer batch_first LSTM recurrence (torch.nn.LSTM gate order i, f, g, o; h0 = c0 = 0):
+ *   gates_t = xp[b, t, :] + W_hh h_{t-1},  xp = x W_ih^T + b_ih + b_hh precomputed for all steps ([B, T, 4*hidden]),
+ *   whh_t = W_hh transposed to [hidden, 4*hidden];  hout [B, T, hidden].  hidden must be 256. */
+int a2f_lstm_recurrence(const float* xp, const float* whh_t, float* hout, int B, int T, int hidden, void* stream);
+/* out[b, i, t] = bilinear resize (align_corners = False) of h[b, t, :] from `hidden` to out_h samples: ref song2face.py:65-66
+ * F.interpolate(x.unsqueeze(3), size=(32, 1)) written channels-last [B, out_h, T] for the regression convs */
+int a2f_song2face_resize(const float* h, int B, int T, int hidden, int out_h, float* out, void* stream);
 /* fused output MLP of Audio2Mesh (ref:src/model/audio2face.py:49-55 minus the vertex head):
  *   z[r, :n2] = W2 tanh(W1 (W0 [feat[r, :k_feat] ; extra[r, :k_extra]] + b0) + b1) + b2,  z[r, n2:ldz] = 0
  * all fp32, row-major weights [n_out, n_in]; every width <= 512. */

@@ -87,6 +87,53 @@ def audio2mesh_forward(sd: SD, x: torch.Tensor, one_hot: torch.Tensor, template:
     return h.view(bs, -1, 3) + template                                 # audio2face.py:66
 
 
+def lstm_forward(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
+    """torch.nn.LSTM(batch_first=True, num_layers=1, unidirectional) forward with zero initial state, written out
+    (gate order i, f, g, o; torch/nn/modules/rnn.py): x [B,T,I] -> [B,T,H]."""
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    h = x.new_zeros(B, H)
+    c = x.new_zeros(B, H)
+    out = []
+    xp = F.linear(x, w_ih, b_ih + b_hh)
+    for t in range(T):
+        g = xp[:, t] + F.linear(h, w_hh)
+        i, f, gg, o = g.chunk(4, 1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out.append(h)
+    return torch.stack(out, 1)
+
+
+def song2face_forward(sd: SD, x: torch.Tensor, one_hot: torch.Tensor, template: torch.Tensor) -> torch.Tensor:
+    """ref:src/model/song2face.py:63-76, eval mode (running-stat BatchNorm)."""
+    bs = x.size(0)
+    emb = one_hot.repeat(1, 32).view(bs, 1, -1, 32)                     # song2face.py:65
+    h = torch.cat((x.unsqueeze(1), emb), 2)                             # :66-67 -> [bs,1,64,32]
+    for i, (kw, pad) in enumerate(((5, 2), (5, 2), (3, 1), (3, 1), (3, 1))):        # :33-39 conv -> BN -> ReLU
+        p = f"vocal_encoder_nn.{i}."
+        h = F.conv2d(h, sd[p + "0.weight"], sd[p + "0.bias"], stride=(1, 2), padding=(0, pad))
+        h = F.relu(_bn(sd, p + "1", h, False))
+    h = h.squeeze(3)                                                    # :68 -> [bs, 256, 64]
+    for name in ("vocal_encoder_lstm1", "vocal_encoder_lstm2"):         # :69-70: 256 steps of 64 / 256 features
+        h = lstm_forward(h, sd[name + ".weight_ih_l0"], sd[name + ".weight_hh_l0"], sd[name + ".bias_ih_l0"],
+                         sd[name + ".bias_hh_l0"])
+    h = F.interpolate(h.unsqueeze(3), size=(32, 1), mode="bilinear")    # :71-72 -> [bs, 256, 32, 1]
+    for i in range(4):                                                  # :54-59
+        p = f"regression_net.{i}."
+        h = F.conv2d(h, sd[p + "0.weight"], sd[p + "0.bias"], stride=(2, 1), padding=(1 if i < 3 else 0, 0))
+        if i < 3:
+            h = _bn(sd, p + "1", h, False)
+        h = F.relu(h)
+    h = h.squeeze(3).squeeze(2)                                         # :74
+    h = torch.cat((h, one_hot), 1)                                      # :75
+    h = F.linear(h, sd["output_net.0.weight"], sd["output_net.0.bias"])
+    h = torch.tanh(F.linear(h, sd["output_net.1.weight"], sd["output_net.1.bias"]))
+    h = F.linear(h, sd["output_net.3.weight"], sd["output_net.3.bias"])
+    h = F.linear(h, sd["output_net.4.weight"], sd["output_net.4.bias"])
+    return h.view(bs, -1, 3) + template                                 # :76
+
+
 # ------------------------------------------------------------------------------------------------------------
 # Losses  (ref:src/loss/loss.py)
 # ------------------------------------------------------------------------------------------------------------

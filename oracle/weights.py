@@ -68,6 +68,34 @@ def audio2mesh_shapes(n_verts: int = V3, n_onehot: int = 12) -> "OrderedDict[str
     return d
 
 
+def song2face_shapes(n_verts: int = V3, n_onehot: int = 12) -> "OrderedDict[str, tuple]":
+    """ref:src/model/song2face.py:32-61"""
+    d = OrderedDict()
+
+    def conv_bn(prefix, ci, co, kh, kw, bn=True):
+        d[f"{prefix}.0.weight"] = (co, ci, kh, kw)
+        d[f"{prefix}.0.bias"] = (co,)
+        if bn:
+            for leaf, shp in (("weight", (co,)), ("bias", (co,)), ("running_mean", (co,)), ("running_var", (co,)),
+                              ("num_batches_tracked", ())):
+                d[f"{prefix}.1.{leaf}"] = shp
+
+    chans = [1, 72, 108, 162, 243, 256]
+    for i, kw in enumerate((5, 5, 3, 3, 3)):
+        conv_bn(f"vocal_encoder_nn.{i}", chans[i], chans[i + 1], 1, kw)
+    for name, insz in (("vocal_encoder_lstm1", 64), ("vocal_encoder_lstm2", 256)):
+        d[f"{name}.weight_ih_l0"] = (1024, insz)
+        d[f"{name}.weight_hh_l0"] = (1024, 256)
+        d[f"{name}.bias_ih_l0"] = (1024,)
+        d[f"{name}.bias_hh_l0"] = (1024,)
+    for idx, (n, k) in zip((0, 1, 3, 4), ((72, 256 + n_onehot), (128, 72), (50, 128), (n_verts, 50))):
+        d[f"output_net.{idx}.weight"] = (n, k)
+        d[f"output_net.{idx}.bias"] = (n,)
+    for i in range(4):
+        conv_bn(f"regression_net.{i}", 256, 256, 3, 1, bn=i < 3)
+    return d
+
+
 def faceformer_shapes(n_verts: int = V3, n_onehot: int = 12) -> "OrderedDict[str, tuple]":
     """ref:src/model/faceformer.py:91-135 + transformers Wav2Vec2Config() defaults (base architecture)."""
     d = OrderedDict()
@@ -170,7 +198,8 @@ def _fill(name: str, shape: tuple, seed: int) -> torch.Tensor:
             return torch.from_numpy((0.1 * r.standard_normal(shape)).astype(np.float32))
         return torch.from_numpy((0.05 * r.standard_normal(shape)).astype(np.float32))
     fan_in = int(np.prod(shape[1:]))
-    gain = 1.4 if ("conv_layers" in name or "time_conv" in name or "analysis_net" in name
+    gain = 1.4 if ("conv_layers" in name or "time_conv" in name or "analysis_net" in name or "vocal_encoder_nn" in name
+                   or "regression_net" in name
                    or "articulation_net" in name or "intermediate_dense" in name or "linear1" in name) else 1.0
     std = gain / math.sqrt(max(fan_in, 1))
     return torch.from_numpy((std * r.standard_normal(shape)).astype(np.float32))
@@ -182,11 +211,12 @@ def _is_bn_vector(name: str, shapes) -> bool:
 
 
 def make_state_dict(model: str, seed: int = 0, n_verts: int = V3, n_onehot: int = 12) -> "OrderedDict[str, torch.Tensor]":
-    shapes = {"voca": voca_shapes, "audio2mesh": audio2mesh_shapes, "faceformer": faceformer_shapes}[model]
+    shapes = {"voca": voca_shapes, "audio2mesh": audio2mesh_shapes, "faceformer": faceformer_shapes,
+              "song2face": song2face_shapes}[model]
     shp = shapes(n_verts) if model == "voca" else shapes(n_verts, n_onehot)
     sd = OrderedDict()
     for name, shape in shp.items():
-        if model == "audio2mesh" and _is_bn_vector(name, shp) and name.endswith((".weight", ".bias")):
+        if model in ("audio2mesh", "song2face") and _is_bn_vector(name, shp) and name.endswith((".weight", ".bias")):
             r = _rng(seed, name)
             if name.endswith(".weight"):
                 sd[name] = torch.from_numpy(r.uniform(0.5, 1.5, shape).astype(np.float32))
