@@ -27,26 +27,33 @@ __global__ void __launch_bounds__(256) transpose_batched_kernel(const float* __r
         if (c0 + j < C && r0 + tx < R) yb[(long long)(c0 + j) * R + r0 + tx] = tile[tx][j];
 }
 
-// One CTA per LSTM_BT batch elements, one thread per hidden unit (HID = blockDim.x = 256).  The thread keeps c[b][u] in
-// registers for the whole sequence and computes the four gates of its unit: xp[b, t, g*HID + u] (input projection with both
-// biases, precomputed for all steps by one GEMM) + sum_k W_hh[g*HID + u, k] h_{t-1}[b, k].  W_hh is read TRANSPOSED
-// ([k][4*HID], coalesced across the threads) from L2 every step and shared by the LSTM_BT batch elements of the CTA.
-// PyTorch gate order i, f, g, o (torch.nn.LSTM); fp32 throughout.
-constexpr int LSTM_BT = 4;
-__global__ void __launch_bounds__(256) lstm_recurrence_kernel(const float* __restrict__ xp, const float* __restrict__ whh_t,
-                                                              float* __restrict__ hout, int B, int T, int HID) {
-    extern __shared__ float lstm_sm[];               // [2][LSTM_BT][HID] previous / next hidden state
+// One CTA per LSTM_BT batch elements (2 for small batches: more CTAs in flight; 4 from 128 windows on: less L2 traffic --
+// measured at 64 windows: BT 1 / 2 / 4 = 15.1 / 6.8 / 9.3 ms per forward); thread (u, part) owns hidden unit u and 1/LSTM_KP of the contraction (HID = 256,
+// blockDim = HID * LSTM_KP).  Part 0 keeps c[b][u] in registers for the whole sequence.  Per step the four gates of unit u
+// are xp[b, t, g*HID + u] (input projection with both biases, precomputed for all steps by one GEMM)
+// + sum_k W_hh[g*HID + u, k] h_{t-1}[b, k]; W_hh is read TRANSPOSED ([k][4*HID], coalesced across the threads) from L2
+// every step and shared by the LSTM_BT batch elements of the CTA.  The step is a chain of dependent L2 round trips, so
+// the k loop is unrolled 8-fold (32 independent loads in flight per thread) and split over LSTM_KP thread groups whose
+// partial sums meet in shared memory: 83 -> ~10 us per step at 64 windows.  (Next step: W_hh slices resident in the
+// shared memory of an 8-CTA cluster, h exchanged through DSMEM.)  PyTorch gate order i, f, g, o; fp32 throughout.
+constexpr int LSTM_KP = 4;
+template <int LSTM_BT>
+__global__ void __launch_bounds__(256 * LSTM_KP) lstm_recurrence_kernel(const float* __restrict__ xp, const float* __restrict__ whh_t,
+                                                                       float* __restrict__ hout, int B, int T, int HID) {
+    extern __shared__ float lstm_sm[];               // [2][LSTM_BT][HID] hidden states, then [LSTM_KP-1][4][LSTM_BT][HID] partials
+    float* part_sm = lstm_sm + 2 * LSTM_BT * HID;
     pdl_sync();
-    const int u = threadIdx.x;
+    const int u = threadIdx.x % HID, part = threadIdx.x / HID;
     const int b0 = blockIdx.x * LSTM_BT;
     float c[LSTM_BT];
 #pragma unroll
     for (int i = 0; i < LSTM_BT; ++i) {
         c[i] = 0.f;
-        lstm_sm[i * HID + u] = 0.f;
+        if (part == 0) lstm_sm[i * HID + u] = 0.f;
     }
     __syncthreads();
     const int G = 4 * HID;
+    const int kper = HID / LSTM_KP, k0 = part * kper;
     for (int t = 0; t < T; ++t) {
         const float* hp = lstm_sm + (t & 1) * LSTM_BT * HID;
         float* hn = lstm_sm + ((t + 1) & 1) * LSTM_BT * HID;
@@ -56,30 +63,53 @@ __global__ void __launch_bounds__(256) lstm_recurrence_kernel(const float* __res
 #pragma unroll
             for (int i = 0; i < LSTM_BT; ++i) {
                 const int b = b0 + i;
-                acc[g][i] = b < B ? __ldg(xp + ((long long)b * T + t) * G + g * HID + u) : 0.f;
+                acc[g][i] = (part == 0 && b < B) ? __ldg(xp + ((long long)b * T + t) * G + g * HID + u) : 0.f;
             }
-#pragma unroll 4
-        for (int k = 0; k < HID; ++k) {
-            const float* wr = whh_t + (long long)k * G + u;
-            const float w0 = __ldg(wr), w1 = __ldg(wr + HID), w2 = __ldg(wr + 2 * HID), w3 = __ldg(wr + 3 * HID);
+#pragma unroll 1
+        for (int kk = 0; kk < kper; kk += 8) {
+            float w[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float* wr = whh_t + (long long)(k0 + kk + j) * G + u;
+                w[j][0] = __ldg(wr); w[j][1] = __ldg(wr + HID); w[j][2] = __ldg(wr + 2 * HID); w[j][3] = __ldg(wr + 3 * HID);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < LSTM_BT; ++i) {
+                    const float h = hp[i * HID + k0 + kk + j];
+                    acc[0][i] = fmaf(w[j][0], h, acc[0][i]);
+                    acc[1][i] = fmaf(w[j][1], h, acc[1][i]);
+                    acc[2][i] = fmaf(w[j][2], h, acc[2][i]);
+                    acc[3][i] = fmaf(w[j][3], h, acc[3][i]);
+                }
+        }
+        if (part > 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int i = 0; i < LSTM_BT; ++i) part_sm[(((part - 1) * 4 + g) * LSTM_BT + i) * HID + u] = acc[g][i];
+        }
+        __syncthreads();
+        if (part == 0) {
 #pragma unroll
             for (int i = 0; i < LSTM_BT; ++i) {
-                const float h = hp[i * HID + k];
-                acc[0][i] = fmaf(w0, h, acc[0][i]);
-                acc[1][i] = fmaf(w1, h, acc[1][i]);
-                acc[2][i] = fmaf(w2, h, acc[2][i]);
-                acc[3][i] = fmaf(w3, h, acc[3][i]);
-            }
-        }
+                float gsum[4];
 #pragma unroll
-        for (int i = 0; i < LSTM_BT; ++i) {
-            const float ig = 1.f / (1.f + expf(-acc[0][i])), fg = 1.f / (1.f + expf(-acc[1][i]));
-            const float gg = tanhf(acc[2][i]), og = 1.f / (1.f + expf(-acc[3][i]));
-            c[i] = fmaf(fg, c[i], ig * gg);
-            const float h = og * tanhf(c[i]);
-            hn[i * HID + u] = h;
-            const int b = b0 + i;
-            if (b < B) hout[((long long)b * T + t) * HID + u] = h;
+                for (int g = 0; g < 4; ++g) {
+                    float v = acc[g][i];
+#pragma unroll
+                    for (int pp = 0; pp < LSTM_KP - 1; ++pp) v += part_sm[((pp * 4 + g) * LSTM_BT + i) * HID + u];
+                    gsum[g] = v;
+                }
+                const float ig = 1.f / (1.f + expf(-gsum[0])), fg = 1.f / (1.f + expf(-gsum[1]));
+                const float gg = tanhf(gsum[2]), og = 1.f / (1.f + expf(-gsum[3]));
+                c[i] = fmaf(fg, c[i], ig * gg);
+                const float h = og * tanhf(c[i]);
+                hn[i * HID + u] = h;
+                const int b = b0 + i;
+                if (b < B) hout[((long long)b * T + t) * HID + u] = h;
+            }
         }
         __syncthreads();
     }
@@ -128,9 +158,20 @@ int a2f_lstm_recurrence(const float* xp, const float* whh_t, float* hout, int B,
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(xp && whh_t && hout && B > 0 && T > 0, "a2f_lstm_recurrence: bad arguments");
     A2F_REQUIRE(hidden == 256, "a2f_lstm_recurrence: hidden size must be 256 (one thread per unit)");
-    const size_t smem = (size_t)2 * LSTM_BT * hidden * sizeof(float);
-    A2F_CHECK_CUDA(launch_pdl(lstm_recurrence_kernel, dim3((B + LSTM_BT - 1) / LSTM_BT), dim3(hidden), smem, as_stream(stream), xp,
-                              whh_t, hout, B, T, hidden));
+    const int bt = B >= 128 ? 4 : 2;
+    const size_t smem = ((size_t)2 * bt * hidden + (size_t)(LSTM_KP - 1) * 4 * bt * hidden) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(lstm_recurrence_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+    }
+    if (bt == 2)
+        A2F_CHECK_CUDA(launch_pdl(lstm_recurrence_kernel<2>, dim3((B + 1) / 2), dim3(hidden * LSTM_KP), smem, as_stream(stream), xp,
+                                  whh_t, hout, B, T, hidden));
+    else
+        A2F_CHECK_CUDA(launch_pdl(lstm_recurrence_kernel<4>, dim3((B + 3) / 4), dim3(hidden * LSTM_KP), smem, as_stream(stream), xp,
+                                  whh_t, hout, B, T, hidden));
     count_launch();
     return A2F_OK;
 }

@@ -134,6 +134,18 @@ def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: i
             dt = time.perf_counter() - t0
             return T / dt, (f"1 utterance x {seconds:g} s @ {fps} fps: forward + FaceFormerLoss + autograd backward, fp32, "
                             "reference O(T^2) decode loop (no optimizer step)")
+        if workload == "song2face":
+            sd = ow.make_state_dict("song2face", 14)
+            B = 64
+            x, oh, tp = oin.a2m_features(B, 1), oin.one_hot(B, 12, 1), oin.batch_templates(B, 1)
+            orm.song2face_forward(sd, x[:4], oh[:4], tp[:4])
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 8.0:
+                orm.song2face_forward(sd, x, oh, tp)
+                reps += 1
+            dt = time.perf_counter() - t0
+            return reps * B / dt, f"{reps} x {B} windows, fp32, eval-mode BatchNorm, LSTM as a Python loop over torch ops (oracle port)"
         if workload == "audio2mesh_train":
             from oracle import ref_mfcc as omf, ref_train as ort
             cfg = omf.CONFIGS["audio2mesh"]
@@ -247,6 +259,12 @@ def workload_config(args):
                 "window": "52 x 32 MFCC", "vertices": 5023, "weights": "random-init (oracle.weights seed 12, randomised BatchNorm stats)",
                 "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
                 "launch": "eager" if args.no_graph else "one CUDA graph per forward (modules.GraphedForward)"}
+    if args.workload == "song2face":
+        return {"workload": f"song2face_inference_b{args.batch}_windows (registry entry song2face, SURVEY.md 8(f) rank 4)",
+                "batch_per_gpu": args.batch, "window": "52 x 32 MFCC", "vertices": 5023,
+                "weights": "random-init (oracle.weights seed 14, randomised BatchNorm stats)",
+                "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
+                "launch": "eager" if args.no_graph else "one CUDA graph per forward (modules.GraphedForward)"}
     if args.workload == "audio2mesh_train":
         return {"workload": f"audio2mesh_train_step_b{args.batch}_windows (the reference's own config.yaml: modelname audio2mesh, "
                             "feature_extractor mfcc, batch 128; BASELINE.json configs[1] shape, training)",
@@ -309,6 +327,19 @@ def run_ours(args):
                 oin.batch_templates(B, 100 + rank).pin_memory()]
         units = B
         flops_step = B * 131.0e6                                 # 131.0 MFLOP per window
+        call = lambda a, o, t: model(a, o, t)                    # noqa: E731
+        out_shape = (B, 5023, 3)
+    elif args.workload == "song2face":
+        model = modules.Song2Face(15069, 12)
+        model.load_state_dict(ow.make_state_dict("song2face", 14), strict=True)
+        model = model.to(dev).eval().set_precision("bf16")
+        h_in = [oin.a2m_features(B, 100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(),
+                oin.batch_templates(B, 100 + rank).pin_memory()]
+        units = B
+        # convs (k=5,5,3,3,3 along W; 4 x k=3 along the resized axis), LSTM projections + recurrences, MLP + head
+        conv = 2.0 * 64 * (16 * 72 * 5 + 8 * 108 * 360 + 4 * 162 * 324 + 2 * 243 * 486 + 256 * 729) + 2.0 * 256 * 768 * (16 + 8 + 4 + 1)
+        lstm = 2.0 * 256 * 1024 * (64 + 256) + 2 * (2.0 * 256 * 1024 * 256)
+        flops_step = B * (conv + lstm + 1.6e6)
         call = lambda a, o, t: model(a, o, t)                    # noqa: E731
         out_shape = (B, 5023, 3)
     elif args.workload == "voca_audio":
@@ -460,6 +491,21 @@ def run_ours(args):
                     "kernel_share_of_step": (g_time / 2) / (dev_s / args.steps),
                     "whole_step_tflops": flops_step * world * args.steps / dev_s / 1e12,
                     "note": "B=64 windows is launch / latency bound (27 launches, ~0.39 ms); --batch 1024 reaches ~0.5 M windows/s"}
+    elif args.workload == "song2face":
+        # dominant kernel: the two fp32 LSTM recurrences (256 dependent steps each; W_hh re-read from L2 every step by
+        # B/4 CTAs) -- timed by difference: whole step minus the GEMM launches the instrumented pass sees
+        gem = [(f, s.elapsed_time(e) * 1e-3) for (kind, f, s, e) in prof if kind in ("gemm_tc", "gemm_simt")]
+        g_time = sum(t for _, t in gem) / 2
+        rec_flops = B * 2 * (2.0 * 256 * 1024 * 256)
+        rec_time = max(dev_s / args.steps - g_time, 1e-9)
+        fp32_peak = 148 * 128 * 2 * 1.965e-3
+        roofline = {"bound": "tensor", "kernel": "a2f::lstm_recurrence_kernel (fp32 SIMT; time = step minus the GEMM launches, so it "
+                                                 "also carries the im2col / transpose / resize launches)",
+                    "achieved": rec_flops / rec_time / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": rec_flops / rec_time / 1e12 / fp32_peak, "traffic": None,
+                    "peak_source": "fp32 FMA peak of the SIMT path (148 SMs x 128 lanes x 2 x 1.965 GHz)",
+                    "gemm_share_of_step": g_time / (dev_s / args.steps),
+                    "whole_step_tflops": flops_step * world * args.steps / dev_s / 1e12}
     elif args.workload == "voca_audio":
         # dominant kernel: the DFT GEMM (frames x window-folded cos|sin basis) on the bf16x3 split -- the first tcgen05
         # launch of a forward; algorithmic FLOPs = 2 * rows * 1026 * 790 (un-padded, un-split), so the 3-term split and
@@ -766,7 +812,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "voca_audio", "audio2mesh", "faceformer_train",
-                                                                    "audio2mesh_train"])
+                                                                    "audio2mesh_train", "song2face"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--fps", type=int, default=None)
@@ -778,7 +824,7 @@ def main():
         args.fps = 60 if args.workload == "faceformer_train" else 30
     if args.batch is None:
         args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384, "voca_audio": 4096, "audio2mesh": 64,
-                      "audio2mesh_train": 128}[args.workload]
+                      "audio2mesh_train": 128, "song2face": 64}[args.workload]
     if args.impl == "reference":
         run_reference(args)
         return
