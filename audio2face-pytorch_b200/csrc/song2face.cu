@@ -9,8 +9,11 @@
 //                           (F.interpolate(size=(32,1)): source index 8 i + 3.5, the mean of two neighbours) written in
 //                           the channels-last layout the regression convs read
 #include "a2f_common.cuh"
+#include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace a2f {
+namespace cg = cooperative_groups;
 
 __global__ void __launch_bounds__(256) transpose_batched_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
     __shared__ float tile[32][33];
@@ -115,6 +118,80 @@ __global__ void __launch_bounds__(256 * LSTM_KP) lstm_recurrence_kernel(const fl
     }
 }
 
+// Cluster variant: W_hh never leaves the chip.  A thread-block cluster of LC_CTAS = 8 CTAs serves LC_BT = 8 windows; CTA r
+// owns hidden units [32 r, 32 r + 32) = 128 gate rows, whose W_hh rows (128 x 256 fp32, padded to a 257-float pitch:
+// conflict-free for a warp of consecutive rows) sit in its shared memory for the whole sequence.  Per step: thread
+// (gate row, half of the batch tile) accumulates 4 outputs over k = 0..255 (one weight LDS + one broadcast float4 LDS of
+// h_{t-1} per k); the 128 x 8 gate pre-activations meet in shared memory; thread (unit, window) applies the
+// nonlinearities (c stays in its registers), writes h_t to global memory and into the h buffer of ALL eight CTAs
+// through distributed shared memory; one cluster barrier per step (h is double-buffered).
+constexpr int LC_CTAS = 8;
+constexpr int LC_BT = 8;
+constexpr int LC_UNITS = 32;                  // hidden units per CTA (HID = 256)
+constexpr int LC_ROWS = 4 * LC_UNITS;         // gate rows per CTA
+constexpr int LC_WPITCH = 257;
+constexpr size_t LC_SMEM = ((size_t)LC_ROWS * LC_WPITCH + 2 * 256 * LC_BT + LC_ROWS * LC_BT) * sizeof(float);
+
+__global__ void __cluster_dims__(LC_CTAS, 1, 1) __launch_bounds__(256, 1)
+lstm_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ whh, float* __restrict__ hout, int B, int T) {
+    extern __shared__ __align__(16) float lc_sm[];
+    float* wsm = lc_sm;                                   // [LC_ROWS][LC_WPITCH]   local row g*32 + j = gate g of unit u0 + j
+    float* hsm = wsm + LC_ROWS * LC_WPITCH;               // [2][256 k][LC_BT]      hidden state, k-major, windows innermost
+    float* gsm = hsm + 2 * 256 * LC_BT;                   // [LC_ROWS][LC_BT]       gate pre-activations of this step
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = ((int)blockIdx.x / LC_CTAS) * LC_BT;
+    const int u0 = rank * LC_UNITS;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < LC_ROWS * 256; i += 256) {      // W_hh rows of this CTA (module weights: safe before the PDL wait)
+        const int lr = i >> 8, k = i & 255;
+        const int g = lr / LC_UNITS, j = lr - g * LC_UNITS;
+        wsm[lr * LC_WPITCH + k] = __ldg(whh + (long long)(g * 256 + u0 + j) * 256 + k);
+    }
+    for (int i = tid; i < 2 * 256 * LC_BT; i += 256) hsm[i] = 0.f;
+    pdl_sync();
+    cluster.sync();
+    const int row = tid & (LC_ROWS - 1), bh = tid >> 7;   // MAC phase: gate row, half of the batch tile (4 windows)
+    const int gu = tid & (LC_UNITS - 1), gb = tid >> 5;   // gate phase: unit, window
+    const int grow = (row / LC_UNITS) * 256 + u0 + (row % LC_UNITS);     // global gate row of `row`
+    float c = 0.f;
+    for (int t = 0; t < T; ++t) {
+        const float* hp = hsm + (t & 1) * 256 * LC_BT;
+        float acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = b0 + bh * 4 + i;
+            acc[i] = b < B ? __ldg(xp + ((long long)b * T + t) * 1024 + grow) : 0.f;
+        }
+        const float* wr = wsm + row * LC_WPITCH;
+#pragma unroll 8
+        for (int k = 0; k < 256; ++k) {
+            const float w = wr[k];
+            const float4 h4 = *reinterpret_cast<const float4*>(hp + k * LC_BT + bh * 4);
+            acc[0] = fmaf(w, h4.x, acc[0]);
+            acc[1] = fmaf(w, h4.y, acc[1]);
+            acc[2] = fmaf(w, h4.z, acc[2]);
+            acc[3] = fmaf(w, h4.w, acc[3]);
+        }
+        *reinterpret_cast<float4*>(gsm + row * LC_BT + bh * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        __syncthreads();
+        {
+            const float gi = gsm[(0 * LC_UNITS + gu) * LC_BT + gb], gf = gsm[(1 * LC_UNITS + gu) * LC_BT + gb];
+            const float gg = gsm[(2 * LC_UNITS + gu) * LC_BT + gb], go = gsm[(3 * LC_UNITS + gu) * LC_BT + gb];
+            const float ig = 1.f / (1.f + expf(-gi)), fg = 1.f / (1.f + expf(-gf));
+            const float og = 1.f / (1.f + expf(-go));
+            c = fmaf(fg, c, ig * tanhf(gg));
+            const float h = og * tanhf(c);
+            const int b = b0 + gb;
+            if (b < B) hout[((long long)b * T + t) * 256 + u0 + gu] = h;
+            const int dst = ((t + 1) & 1) * 256 * LC_BT + (u0 + gu) * LC_BT + gb;
+#pragma unroll
+            for (int r = 0; r < LC_CTAS; ++r) cluster.map_shared_rank(hsm, r)[dst] = h;
+        }
+        cluster.sync();                                   // h_t visible in every CTA; gsm free for the next step
+    }
+}
+
 // out[b, i, t] = 0.5 * (h[b, t, 8 i + 3] + h[b, t, 8 i + 4]) generalised: bilinear source index of F.interpolate
 // (align_corners = False) along the hidden axis, output channels-last [B, out_h, steps]
 __global__ void __launch_bounds__(256) song2face_resize_kernel(const float* __restrict__ h, int B, int T, int HID, int out_h,
@@ -153,11 +230,31 @@ int a2f_transpose_batched(const float* x, float* y, int B, int R, int C, void* s
     return A2F_OK;
 }
 
-int a2f_lstm_recurrence(const float* xp, const float* whh_t, float* hout, int B, int T, int hidden, void* stream) {
+static int g_lstm_impl = 0;      // debug: 1 = never use the cluster kernel
+int a2f_lstm_recurrence(const float* xp, const float* whh_t, const float* whh_n, float* hout, int B, int T, int hidden,
+                        void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(xp && whh_t && hout && B > 0 && T > 0, "a2f_lstm_recurrence: bad arguments");
+    {
+        const char* e = getenv("A2F_LSTM_IMPL");
+        g_lstm_impl = (e && e[0] == '1') ? 1 : 0;
+    }
     A2F_REQUIRE(hidden == 256, "a2f_lstm_recurrence: hidden size must be 256 (one thread per unit)");
+    if (B >= 4 && g_lstm_impl != 1) {
+        // cluster kernel: W_hh (un-transposed [4*hidden, hidden]) resident in shared memory; whh_n must be given
+        A2F_REQUIRE(whh_n != nullptr, "a2f_lstm_recurrence: the cluster kernel needs W_hh in its [4*hidden, hidden] layout");
+        static bool cattr = false;
+        if (!cattr) {
+            A2F_CHECK_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC_SMEM));
+            cattr = true;
+        }
+        const int groups = (B + LC_BT - 1) / LC_BT;
+        A2F_CHECK_CUDA(launch_pdl(lstm_cluster_kernel, dim3(groups * LC_CTAS), dim3(256), LC_SMEM, as_stream(stream), xp, whh_n, hout,
+                                  B, T));
+        count_launch();
+        return A2F_OK;
+    }
     const int bt = B >= 128 ? 4 : 2;
     const size_t smem = ((size_t)2 * bt * hidden + (size_t)(LSTM_KP - 1) * 4 * bt * hidden) * sizeof(float);
     static bool attr_done = false;

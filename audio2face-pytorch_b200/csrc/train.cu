@@ -142,7 +142,19 @@ __global__ void __launch_bounds__(256) strided_copy_jobs_kernel(const a2f_copy_j
                 const int t = tt - jb.tile0;
                 const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
                 const float* __restrict__ in = jb.src;
-                if (jb.ld_c <= jb.ld_r) {
+                if (jb.ld_c == 1 && jb.ldo_c == 1 && jb.dst_dtype == A2F_BF16 && (jb.ld_r & 3) == 0 && (jb.ldo_r & 3) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(jb.src) & 15) | (reinterpret_cast<uintptr_t>(jb.dst) & 7)) == 0 &&
+                    r0 + 32 <= jb.R && c0 + 32 <= jb.C) {
+                    // plain fp32 -> bf16 cast of a full tile (half of a re-pack's volume): 16-byte loads, 8-byte stores,
+                    // no trip through shared memory
+                    const int r = r0 + (threadIdx.x >> 3), c = c0 + (threadIdx.x & 7) * 4;
+                    const float4 f = *reinterpret_cast<const float4*>(in + (long long)r * jb.ld_r + c);
+                    uint2 o;
+                    o.x = pack_bf16x2(f.x, f.y);
+                    o.y = pack_bf16x2(f.z, f.w);
+                    *reinterpret_cast<uint2*>(static_cast<bf16*>(jb.dst) + (long long)r * jb.ldo_r + c) = o;
+                    jidx[i] = -1;                                              // done
+                } else if (jb.ld_c <= jb.ld_r) {
 #pragma unroll
                     for (int j = ty; j < 32; j += 8) {
                         const int r = r0 + j, c = c0 + tx;
@@ -168,7 +180,19 @@ __global__ void __launch_bounds__(256) strided_copy_jobs_kernel(const a2f_copy_j
             const int tiles_c = (jb.C + 31) >> 5;
             const int t = tt - jb.tile0;
             const int r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+            const bool full = r0 + 32 <= jb.R && c0 + 32 <= jb.C;
             if (jb.ldo_c <= jb.ldo_r) {
+                if (full && jb.dst_dtype == A2F_BF16 && jb.ldo_c == 1 && (jb.ldo_r & 1) == 0 &&
+                    (reinterpret_cast<uintptr_t>(jb.dst) & 3) == 0) {
+                    // bf16 rows: two columns per thread, 4-byte stores (128 B per warp instruction instead of 64)
+                    const int cp = (threadIdx.x & 15) * 2;
+#pragma unroll
+                    for (int j = threadIdx.x >> 4; j < 32; j += 16) {
+                        const long long o = (long long)(r0 + j) * jb.ldo_r + c0 + cp;
+                        *reinterpret_cast<uint32_t*>(static_cast<bf16*>(jb.dst) + o) = pack_bf16x2(tile[i][j][cp], tile[i][j][cp + 1]);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = ty; j < 32; j += 8) {
                     const int r = r0 + j, c = c0 + tx;
@@ -179,6 +203,17 @@ __global__ void __launch_bounds__(256) strided_copy_jobs_kernel(const a2f_copy_j
                     }
                 }
             } else {
+                if (full && jb.dst_dtype == A2F_BF16 && jb.ldo_r == 1 && (jb.ldo_c & 1) == 0 &&
+                    (reinterpret_cast<uintptr_t>(jb.dst) & 3) == 0) {
+                    // transposed bf16 output (rows of the destination run along r): two r per thread
+                    const int rp = (threadIdx.x & 15) * 2;
+#pragma unroll
+                    for (int j = threadIdx.x >> 4; j < 32; j += 16) {
+                        const long long o = (long long)(c0 + j) * jb.ldo_c + r0 + rp;
+                        *reinterpret_cast<uint32_t*>(static_cast<bf16*>(jb.dst) + o) = pack_bf16x2(tile[i][rp][j], tile[i][rp + 1][j]);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = ty; j < 32; j += 8) {
                     const int r = r0 + tx, c = c0 + j;

@@ -422,7 +422,7 @@ class Song2Face(_A2FModule):
             for lstm in (self.vocal_encoder_lstm1, self.vocal_encoder_lstm2):
                 w_ih, kpad = operand(lstm.weight_ih_l0.detach())
                 P["lstm"].append((w_ih, kpad, (lstm.bias_ih_l0.detach() + lstm.bias_hh_l0.detach()).contiguous(),
-                                  lstm.weight_hh_l0.detach().t().contiguous()))
+                                  lstm.weight_hh_l0.detach().t().contiguous(), lstm.weight_hh_l0.detach().contiguous()))
             return P
         srcs = list(self.parameters()) + [b for b in self.buffers()]
         return self._cache.get("s2f_" + self.precision, srcs, build)
@@ -455,7 +455,7 @@ class Song2Face(_A2FModule):
             cur, Lo, ldc = self._conv(cur, outer, ostride, ld, Ci, Li, taps, 2, pad, P["enc"][i], Co, x_offset=xoff)
             ostride, ld, Ci, Li, xoff = Lo * ldc, ldc, Co, Lo, 0
         h = ops.transpose_batched(cur.view(bs, 64, 256))                     # [B, steps = 256 channels, features = 64]
-        for w_ih, kpad, bias, whh_t in P["lstm"]:
+        for w_ih, kpad, bias, whh_t, whh in P["lstm"]:
             a2 = h.view(bs * 256, -1)
             if a2.shape[1] != kpad:                                          # features padded to the packed K
                 ap = torch.zeros((a2.shape[0], kpad), dtype=torch.float32, device=a2.device)
@@ -464,7 +464,7 @@ class Song2Face(_A2FModule):
             a_op = ops.split_bf16x3(a2, False) if bf else a2
             xp = torch.empty((bs * 256, 1024), dtype=torch.float32, device=x.device)
             ops.gemm(a_op, w_ih, xp, bias=bias, backend=self._backend())
-            h = ops.lstm_recurrence(xp, whh_t, bs, 256, 256)                 # [B, 256, 256]
+            h = ops.lstm_recurrence(xp, whh_t, bs, 256, 256, whh=whh)        # [B, 256, 256]
         cur = ops.song2face_resize(h, 32)                                    # [B, 32, 256] channels-last (C = LSTM step)
         outer, ostride, Li = bs, 32 * 256, 32
         for i in range(4):                                                   # regression net, conv along the resized axis

@@ -323,10 +323,14 @@ def transpose_batched(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def lstm_recurrence(xp: torch.Tensor, whh_t: torch.Tensor, B: int, T: int, hidden: int) -> torch.Tensor:
-    _dev(xp, whh_t)
+def lstm_recurrence(xp: torch.Tensor, whh_t: torch.Tensor, B: int, T: int, hidden: int,
+                    whh: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """xp [B,T,4H] input projections (+ both biases), whh_t = W_hh^T [H,4H], whh = W_hh [4H,H] (cluster kernel) -> h [B,T,H]"""
+    _dev(xp, whh_t, whh)
+    if whh is None:
+        whh = whh_t.t().contiguous()
     h = torch.empty((B, T, hidden), dtype=torch.float32, device=xp.device)
-    L.check(L.load().a2f_lstm_recurrence(xp.data_ptr(), whh_t.data_ptr(), h.data_ptr(), B, T, hidden, _stream()),
+    L.check(L.load().a2f_lstm_recurrence(xp.data_ptr(), whh_t.data_ptr(), whh.data_ptr(), h.data_ptr(), B, T, hidden, _stream()),
             "a2f_lstm_recurrence")
     return h
 

@@ -315,8 +315,11 @@ int a2f_im2col1d(const float* x, long long outer, long long outer_stride, int ld
 int a2f_transpose_batched(const float* x, float* y, int B, int R, int C, void* stream);
 /* single-layer batch_first LSTM recurrence (torch.nn.LSTM gate order i, f, g, o; h0 = c0 = 0):
  *   gates_t = xp[b, t, :] + W_hh h_{t-1},  xp = x W_ih^T + b_ih + b_hh precomputed for all steps ([B, T, 4*hidden]),
- *   whh_t = W_hh transposed to [hidden, 4*hidden];  hout [B, T, hidden].  hidden must be 256. */
-int a2f_lstm_recurrence(const float* xp, const float* whh_t, float* hout, int B, int T, int hidden, void* stream);
+ *   whh_t = W_hh transposed to [hidden, 4*hidden], whh_n = W_hh as stored [4*hidden, hidden];  hout [B, T, hidden];
+ *   hidden must be 256.  From 4 sequences on an 8-CTA thread-block cluster keeps W_hh (whh_n) in shared memory for the whole
+ *   sequence and exchanges h_t through distributed shared memory; smaller batches stream whh_t from L2 every step. */
+int a2f_lstm_recurrence(const float* xp, const float* whh_t, const float* whh_n, float* hout, int B, int T, int hidden,
+                        void* stream);
 /* out[b, i, t] = bilinear resize (align_corners = False) of h[b, t, :] from `hidden` to out_h samples: ref song2face.py:65-66
  * F.interpolate(x.unsqueeze(3), size=(32, 1)) written channels-last [B, out_h, T] for the regression convs */
 int a2f_song2face_resize(const float* h, int B, int T, int hidden, int out_h, float* out, void* stream);
