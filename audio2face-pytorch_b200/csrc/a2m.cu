@@ -71,12 +71,12 @@ __global__ void __launch_bounds__(256) im2col1d_split_kernel(const float* __rest
         const long long o = row / L_out;
         const float* xo = x + o * outer_stride;
         float v[8];
+        int tap = (ch * 8) / C, c = ch * 8 - tap * C;       // one division per 8 elements; (tap, c) then advance incrementally
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int k = ch * 8 + e;
             float a = 0.f;
             if (k < K) {
-                const int tap = k / C, c = k - tap * C;
                 const int l = lo * stride - pad + tap;
                 if (l >= 0 && l < L) {
                     a = __ldg(xo + (long long)l * ld + c);
@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) im2col1d_split_kernel(const float* __rest
                 }
             }
             v[e] = a;
+            if (++c == C) { c = 0; ++tap; }
         }
         if (!SPLIT) {                                   // fp32 rows [rows, kpad] for the SIMT parity path
             float* of = static_cast<float*>(out_v) + row * kpad + ch * 8;
@@ -122,7 +123,24 @@ __device__ __forceinline__ void mlp_layer(const float* __restrict__ in, int K, f
 #pragma unroll
         for (int i = 0; i < MLP_WPB; ++i) acc[i] = bv;
         const float* wr = w + (long long)n * K;
-        for (int k = 0; k < K; ++k) {
+        int k = 0;
+        if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(wr) & 15) == 0) {
+            // 16-byte weight / activation loads, 4 independent rows in flight: the scalar loop was one dependent L1 round
+            // trip per k (40 us per launch at 64 windows, profiles/r1_launches_conv_models.txt)
+#pragma unroll 4
+            for (; k < K; k += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+                for (int i = 0; i < MLP_WPB; ++i) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(in + i * MLP_MAXW + k);
+                    acc[i] = fmaf(w4.x, x4.x, acc[i]);
+                    acc[i] = fmaf(w4.y, x4.y, acc[i]);
+                    acc[i] = fmaf(w4.z, x4.z, acc[i]);
+                    acc[i] = fmaf(w4.w, x4.w, acc[i]);
+                }
+            }
+        }
+        for (; k < K; ++k) {
             const float wv = __ldg(wr + k);
 #pragma unroll
             for (int i = 0; i < MLP_WPB; ++i) acc[i] = fmaf(wv, in[i * MLP_MAXW + k], acc[i]);
@@ -137,8 +155,8 @@ __global__ void __launch_bounds__(128) a2m_mlp_kernel(const float* __restrict__ 
                                                       const float* __restrict__ b0, int N0, const float* __restrict__ w1,
                                                       const float* __restrict__ b1, int N1, const float* __restrict__ w2,
                                                       const float* __restrict__ b2, int N2, float* __restrict__ z, int ldz, int B) {
-    __shared__ float bufA[MLP_WPB * MLP_MAXW];
-    __shared__ float bufB[MLP_WPB * MLP_MAXW];
+    __shared__ __align__(16) float bufA[MLP_WPB * MLP_MAXW];
+    __shared__ __align__(16) float bufB[MLP_WPB * MLP_MAXW];
     pdl_sync();
     const int K0 = K0a + K0b;
     for (int r0 = blockIdx.x * MLP_WPB; r0 < B; r0 += gridDim.x * MLP_WPB) {
