@@ -155,13 +155,20 @@ lstm_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ whh,
     const int gu = tid & (LC_UNITS - 1), gb = tid >> 5;   // gate phase: unit, window
     const int grow = (row / LC_UNITS) * 256 + u0 + (row % LC_UNITS);     // global gate row of `row`
     float c = 0.f;
+    float nxt[4];                                          // input projections of the next step, requested one step ahead
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int b = b0 + bh * 4 + i;
+        nxt[i] = (b < B && T > 0) ? __ldg(xp + ((long long)b * T) * 1024 + grow) : 0.f;
+    }
     for (int t = 0; t < T; ++t) {
         const float* hp = hsm + (t & 1) * 256 * LC_BT;
         float acc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+            acc[i] = nxt[i];
             const int b = b0 + bh * 4 + i;
-            acc[i] = b < B ? __ldg(xp + ((long long)b * T + t) * 1024 + grow) : 0.f;
+            nxt[i] = (b < B && t + 1 < T) ? __ldg(xp + ((long long)b * T + t + 1) * 1024 + grow) : 0.f;
         }
         const float* wr = wsm + row * LC_WPITCH;
 #pragma unroll 8
