@@ -468,9 +468,24 @@ int a2f_decoder_save_offset(int field) {
     return o;
 }
 
+static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memory, int memory_is_ca, const float* one_hot,
+                                int n_onehot, int period, float* D, int B, int T, void* workspace, size_t workspace_bytes,
+                                float* saves, void* stream);
+
 int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
                               int period, float* D, int B, int T, void* workspace, size_t workspace_bytes, float* saves,
                               void* stream) {
+    return decoder_rollout_impl(w, memory, 0, one_hot, n_onehot, period, D, B, T, workspace, workspace_bytes, saves, stream);
+}
+
+int a2f_decoder_rollout_ca(const a2f_decoder_weights* w, const float* ca, const float* one_hot, int n_onehot, int period,
+                           float* D, int B, int T, void* workspace, size_t workspace_bytes, void* stream) {
+    return decoder_rollout_impl(w, ca, 1, one_hot, n_onehot, period, D, B, T, workspace, workspace_bytes, nullptr, stream);
+}
+
+static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memory, int memory_is_ca, const float* one_hot,
+                                int n_onehot, int period, float* D, int B, int T, void* workspace, size_t workspace_bytes,
+                                float* saves, void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(w && memory && one_hot && D && workspace, "a2f_decoder_rollout: NULL argument");
@@ -487,8 +502,12 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
     float* ca = tmp + (size_t)B * T * 64;
     float* kv = (T > DEC_SMEM_T) ? ca + (size_t)B * T * 64 : nullptr;
 
-    // cross-attention with the diagonal memory mask: ca_t = out_proj(v_proj(memory_t))   
+    // cross-attention with the diagonal memory mask: ca_t = out_proj(v_proj(memory_t))   (SURVEY.md fact 0.6);
+    // a2f_decoder_rollout_ca: the caller already folded both projections (and audio_feature_map) into the GEMM that
+    // produced `memory`, which then IS the cross-attention vector
+    const float* ca_in = memory_is_ca ? memory : nullptr;
     GemmParams g;
+    if (!memory_is_ca) {
     g.M = B * T; g.N = 64; g.K = 64;
     g.A = memory; g.a_row_stride = 64; g.a_batch_stride = 0; g.rows_per_batch = B * T;
     g.W = w->ca_in_w + 128 * 64; g.ldw = 64; g.bias = w->ca_in_b + 128; g.act = A2F_ACT_NONE;
@@ -499,6 +518,8 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
     g.A = tmp; g.W = w->ca_out_w; g.bias = w->ca_out_b; g.C = ca;
     rc = gemm_simt(g, 0, 0, s);
     if (rc != A2F_OK) return rc;
+    }
+    const float* ca_use = memory_is_ca ? ca_in : ca;
 
     DecW dw;
     dw.sa_in_w = w->sa_in_w; dw.sa_in_b = w->sa_in_b; dw.sa_out_w = w->sa_out_w; dw.sa_out_b = w->sa_out_b;
@@ -562,11 +583,11 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, dw, (const float*)ca, one_hot, n_onehot, period, D, T, kv, none));
+        A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, dw, ca_use, one_hot, n_onehot, period, D, T, kv, none));
     } else if (saves == nullptr) {
         DecSaves none = {};
         A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca, one_hot, n_onehot, period, D, T, kv, none));
+        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca_use, one_hot, n_onehot, period, D, T, kv, none));
     } else {
         DecSaves sv;
         const size_t bt = (size_t)B * T;
@@ -578,7 +599,7 @@ int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory,
         sv.HID = f + bt * a2f_decoder_save_offset(A2F_DEC_HID); sv.Y3PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y3PRE);
         sv.LSE = f + bt * a2f_decoder_save_offset(A2F_DEC_LSE);
         A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<true, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca, one_hot, n_onehot, period, D, T, kv, sv));
+        A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<true, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca_use, one_hot, n_onehot, period, D, T, kv, sv));
     }
     A2F_CHECK_LAUNCH("decoder_rollout_kernel");
     count_launch();

@@ -106,6 +106,8 @@ _SIGNATURES = {
     "a2f_mha_bwd_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_void_p, c_size_t, c_void_p]),
     "a2f_decoder_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "a2f_decoder_rollout_ca": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                    c_int, c_void_p, c_size_t, c_void_p]),
     "a2f_decoder_rollout": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                     c_int, c_void_p, c_size_t, c_void_p]),
     "a2f_decoder_save_offset": (c_int, [c_int]),

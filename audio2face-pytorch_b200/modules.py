@@ -621,6 +621,22 @@ class Faceformer(_A2FModule):
                 })
             P["layers"] = lay
             P["afm_w"] = cast(self.audio_feature_map.weight)
+            # cross-attention with the diagonal memory mask is out_proj(v_proj(audio_feature_map(h))): three Linear layers in a
+            # row, folded (fp64) into ONE [64, 768] operand so that the encoder states go straight to the vectors the decoder
+            # kernel adds (a2f_decoder_rollout_ca); re-derived by fold_ca() with the other packed operands
+            ca_w = torch.empty((64, 768), dtype=dt, device=dev)
+            ca_b = torch.empty((64,), dtype=torch.float32, device=dev)
+            P["ca_w"], P["ca_b"] = ca_w, ca_b
+
+            def fold_ca():
+                with torch.no_grad():
+                    ca_mod = self.transformer_decoder.layers[0].multihead_attn
+                    wv = ca_mod.in_proj_weight.detach()[128:192].double()
+                    bv = ca_mod.in_proj_bias.detach()[128:192].double()
+                    wo, bo = ca_mod.out_proj.weight.detach().double(), ca_mod.out_proj.bias.detach().double()
+                    wa, ba = self.audio_feature_map.weight.detach().double(), self.audio_feature_map.bias.detach().double()
+                    ca_w.copy_(wo @ (wv @ wa))
+                    ca_b.copy_(wo @ (wv @ ba + bv) + bo)
             wc = torch.empty((64, 64), dtype=torch.float32, device=dev)
             bc = torch.empty((64,), dtype=torch.float32, device=dev)
             P["fb"] = (wc, bc)
@@ -648,6 +664,7 @@ class Faceformer(_A2FModule):
 
             def refresh():
                 plan.run()
+                fold_ca()
                 ops.pack_posconv_weight(pz.original0.detach().reshape(-1), pz.original1.detach(), dt, out=P["pos_w"])
                 ops.pack_feedback(self.vertice_map.weight.detach(), self.vertice_map.bias.detach(),
                                   self.vertice_map_r.weight.detach(), self.vertice_map_r.bias.detach(), out=(wc, bc))
@@ -746,10 +763,9 @@ class Faceformer(_A2FModule):
         for b0 in range(0, B, per):
             b1 = min(B, b0 + per)
             h = self.encode(audio[b0:b1], frame_num)
-            ops.gemm(h, P["afm_w"], memory[b0 * frame_num:b1 * frame_num], bias=self.audio_feature_map.bias.detach(),
-                     backend=self._backend())
+            ops.gemm(h, P["ca_w"], memory[b0 * frame_num:b1 * frame_num], bias=P["ca_b"], backend=self._backend())
             del h
-        D = ops.decoder_rollout(P["dec"][0], memory, one_hot, self.period, B, frame_num)
+        D = ops.decoder_rollout(P["dec"][0], memory, one_hot, self.period, B, frame_num, memory_is_ca=True)
         out = torch.empty((M, self.vertice_dim), dtype=torch.float32, device=audio.device)
         hp = max(1, (1 << 17) // frame_num)                            # utterances per vertex-head launch (int32 offsets)
         for b0 in range(0, B, hp):

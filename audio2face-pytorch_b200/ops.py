@@ -367,15 +367,18 @@ def pack_feedback(vm_w, vm_b, vmr_w, vmr_b, out=None):
     return wc, bc
 
 
-def decoder_rollout(wstruct: "L.DecoderWeights", memory: torch.Tensor, one_hot: torch.Tensor, period: int, B: int, T: int):
-    """memory [B,T,64] fp32 -> decoder states D [B,T,64] fp32 (a2f_decoder_rollout)."""
+def decoder_rollout(wstruct: "L.DecoderWeights", memory: torch.Tensor, one_hot: torch.Tensor, period: int, B: int, T: int,
+                    memory_is_ca: bool = False):
+    """memory [B,T,64] fp32 -> decoder states D [B,T,64] fp32 (a2f_decoder_rollout); memory_is_ca: `memory` already holds
+    the cross-attention vectors out_proj(v_proj(audio_feature_map(h))) (a2f_decoder_rollout_ca)."""
     _dev(memory, one_hot)
     lib = L.load()
     nbytes = lib.a2f_decoder_workspace_bytes(B, T)
     ws = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.float32, device=memory.device)
     D = torch.empty((B, T, 64), dtype=torch.float32, device=memory.device)
-    L.check(lib.a2f_decoder_rollout(C.byref(wstruct), memory.data_ptr(), one_hot.data_ptr(), one_hot.shape[1], period,
-                                    D.data_ptr(), B, T, ws.data_ptr(), ws.numel() * 4, _stream()), "a2f_decoder_rollout")
+    fn = lib.a2f_decoder_rollout_ca if memory_is_ca else lib.a2f_decoder_rollout
+    L.check(fn(C.byref(wstruct), memory.data_ptr(), one_hot.data_ptr(), one_hot.shape[1], period,
+               D.data_ptr(), B, T, ws.data_ptr(), ws.numel() * 4, _stream()), "a2f_decoder_rollout")
     return D
 
 

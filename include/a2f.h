@@ -258,7 +258,13 @@ int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory /*[B,T
 #define A2F_DEC_Y2 7     /* LN2 output                      64 */
 #define A2F_DEC_HID 8    /* relu(linear1)                  128 */
 #define A2F_DEC_Y3PRE 9  /* LN3 input                       64 */
-#define A2F_DEC_LSE 10   /* self-attn log-sum-exp per head   4 */
+#define A2F_DEC_LSE 10   /* a2f_decoder_rollout with the cross-attention vectors already computed: ca [B,T,64] = out_proj(v_proj(memory)).  Because
+ * memory = audio_feature_map(h) is itself linear, a caller can fold the three Linear layers into ONE [64, 768] GEMM from the
+ * encoder states (modules.Faceformer does, for inference); the two 64x64 SIMT GEMM launches of a2f_decoder_rollout
+ * disappear.  Same workspace contract. */
+int a2f_decoder_rollout_ca(const a2f_decoder_weights* w, const float* ca, const float* one_hot, int n_onehot, int period,
+                           float* D, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+/* self-attn log-sum-exp per head   4 */
 #define A2F_DEC_NFIELDS 11
 int a2f_decoder_save_offset(int field);
 int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
