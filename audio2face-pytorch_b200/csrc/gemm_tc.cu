@@ -64,18 +64,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, const TcParam
            ((uint64_t)(p.desc_layout & 7u) << 61);
 }
 
-template <int BN, typename TC> struct TcCfg {
+// WIDE: the scalar epilogue of a 256-column fp32 tile stages 32 rows x 128 columns per epilogue warp (16 KB each) so
+// that every output / template row is touched in 512-byte runs; the smem comes out of the operand ring (2 stages: the
+// vertex heads have K <= 192 and are bound by the HBM traffic of the epilogue, not by the mainloop).
+template <int BN, typename TC, bool SCALAR> constexpr bool tc_wide_v = SCALAR && BN == 256 && sizeof(TC) == 4;
+constexpr int WIDE_WARP_FLOATS = 32 * 128;
+constexpr int WIDE_WR = 8;               // rows of the rolling template window (WIDE_WR x 4 loads per lane in flight)
+
+template <int BN, typename TC, bool WIDE = false> struct TcCfg {
     static constexpr int ACC_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static constexpr int B_STAGE_BYTES = BN * TBK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128) ? 6 : 8;
+    static constexpr int STAGES = WIDE ? 2 : (BN >= 256) ? 4 : (BN >= 128) ? 6 : 8;
+    static constexpr int EPI_BYTES = WIDE ? 8 * WIDE_WARP_FLOATS * 4 : 2 * EPI_STAGE_BYTES;
     // TMA-store block width (columns): 128 bytes of output per row, except for the 48-wide posconv tiles
     static constexpr int SBW = (BN % 32 != 0) ? ((sizeof(TC) == 2) ? BN : 16) : (int)(128 / sizeof(TC));
     static constexpr int NBLK = BN / SBW;
     static constexpr int ROW_PITCH = SBW * (int)sizeof(TC);
     static constexpr bool SWZ = (ROW_PITCH == 128);
-    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 2 * EPI_STAGE_BYTES + 256 /*barriers*/;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/;
 };
 
 // ---- epilogue helpers: every data-independent condition is tested once per chunk, never per element ----
@@ -155,17 +163,56 @@ __device__ __forceinline__ void epi_resid(float* v, const void* __restrict__ res
     }
 }
 
+// ---- wide scalar epilogue helpers (gemm_tc_kernel, WIDE) ----
+// Position the template refill stream on output row m0 (template row m0 / rows_per_tmpl), column ncol.
+A2F_D void wide_fill_start(const float* tmpl, long long m0, int ncol, int rpt, int N, const float*& tp, int& rem) {
+    if (tmpl == nullptr) return;
+    const unsigned tr = (unsigned)m0 / (unsigned)rpt;
+    rem = (int)((unsigned)m0 - tr * (unsigned)rpt);
+    tp = tmpl + (long long)tr * N + ncol;
+}
+// WIDE_WR output rows [row_base, row_base+WIDE_WR) of a warp's 32 x 128 slice: out = (acc + bias) + template, where the template
+// values come from the rolling window `tadd`; every consumed window slot is refilled at once from the refill stream
+// (WIDE_WR rows ahead).  PRED = false: slice and refill target are complete, no predicates.
+template <bool PRED>
+A2F_D void wide_rows(float (&tadd)[WIDE_WR * 4], const float* trw, const float (&bj)[4], float* cp, int ldc, int row_base, int rows,
+                     const bool (&cok)[4], const float*& tp, int& rem, int rpt, int N, bool has_t, int fill_rows,
+                     const bool (&fok)[4], int lane) {
+#pragma unroll
+    for (int r = 0; r < WIDE_WR; ++r) {
+        const int rr = row_base + r;
+        float sv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sv[c] = trw[c * 1024 + rr * 32 + ((lane + rr) & 31)];
+        float* cpr = cp + (long long)(rr * ldc);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float o = (sv[c] + bj[c]) + tadd[r * 4 + c];
+            if (!PRED || (rr < rows && cok[c])) cpr[c * 32] = o;
+        }
+        if (has_t) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (PRED) tadd[r * 4 + c] = (r < fill_rows && fok[c]) ? __ldg(tp + c * 32) : 0.f;
+                else tadd[r * 4 + c] = __ldg(tp + c * 32);
+            }
+            if (++rem == rpt) { rem = 0; tp += N; }
+        }
+    }
+}
+
 template <int BN, typename TC, bool SCALAR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
-    using Cfg = TcCfg<BN, TC>;
+    constexpr bool WIDE = tc_wide_v<BN, TC, SCALAR>;
+    using Cfg = TcCfg<BN, TC, WIDE>;
     constexpr int STAGES = Cfg::STAGES;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)STAGES * A_STAGE_BYTES;
     uint8_t* sEpi = smem + (size_t)STAGES * Cfg::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 2 * EPI_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + Cfg::EPI_BYTES);
     uint64_t* full_bar = bars;                 // [STAGES]
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -289,6 +336,25 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         const void* __restrict__ e_resid = g.resid;
         const int e_act = g.act;
         const bool e_dact = g.resid_mode == A2F_RESID_DACT;
+        // ---- wide scalar epilogue (vertex heads): this warp owns 32 rows x 128 columns of every tile ----
+        const bool wide = WIDE && g.resid == nullptr && g.act == A2F_ACT_NONE && p.mode != 2;
+        float tadd[WIDE_WR * 4];    // template values of the NEXT WIDE_WR rows x 4 chunks, always in flight
+        bool tadd_primed = false;
+        const float* fill_tp = nullptr;         // template row the refill stream reads next
+        int fill_rem = 0;                       // output rows already served by that template row
+        const float* __restrict__ e_tmpl = g.tmpl;
+        const int e_N = g.N;
+        // slice of tile `t_` owned by this warp: output pointer of (row 0, column lane), first global row, live rows
+        auto wslice = [&](int t_, float*& cp_, long long& m0_, int& rows_, int& ncol_) {
+            if (t_ >= total_tiles) { cp_ = nullptr; m0_ = 0; rows_ = 0; ncol_ = 0; return; }
+            const int nb_ = t_ % p.tiles_n, mb_ = t_ / p.tiles_n;
+            const int b_ = mb_ / p.tiles_m_per_batch, lt_ = mb_ % p.tiles_m_per_batch;
+            const int r0_ = lt_ * TBM + q * 32;
+            rows_ = min(32, max(0, g.rows_per_batch - r0_));
+            ncol_ = nb_ * BN + half * 128 + lane;
+            m0_ = (long long)b_ * g.rows_per_batch + r0_;
+            cp_ = reinterpret_cast<float*>(g.C) + (long long)b_ * g.c_batch_stride + (long long)r0_ * g.ldc + ncol_;
+        };
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
             const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
@@ -365,6 +431,74 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     if (leader) {
                         tma_store_3d(&maps.c, stage_buf, ncol0, lt * TBM, b);
                         tma_store_commit();
+                    }
+                }
+            } else if (WIDE && wide) {
+                // 512-byte runs per row: HBM pages are touched in 4x longer bursts than by the 32x32 chunks below, and
+                // 32 template loads per lane stay in flight through the whole tile (rolling WIDE_WR-row window that runs
+                // ahead into the next tile), profiles/r1_vertex_head_access_pattern.txt
+                float* cp; long long m0; int rows, ncol;
+                wslice(tile, cp, m0, rows, ncol);
+                bool cok[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cok[c] = ncol + c * 32 < e_N;
+                if (!tadd_primed) {
+                    wide_fill_start(e_tmpl, m0, ncol, g.rows_per_tmpl, e_N, fill_tp, fill_rem);
+#pragma unroll
+                    for (int r = 0; r < WIDE_WR; ++r) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            tadd[r * 4 + c] = (e_tmpl && r < rows && cok[c]) ? __ldg(fill_tp + c * 32) : 0.f;
+                        if (++fill_rem == g.rows_per_tmpl) { fill_rem = 0; fill_tp += e_N; }
+                    }
+                    tadd_primed = true;
+                }
+                float* trw = reinterpret_cast<float*>(sEpi) + ew * WIDE_WARP_FLOATS;
+                __syncwarp();
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (half * 128 + cc * 32 >= n_lim) break;
+                    float v[32];
+                    tmem_ld_32x32(t_row + half * 128 + cc * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) trw[cc * 1024 + lane * 32 + ((j + lane) & 31)] = v[j];
+                }
+                // the accumulator is in smem: hand the TMEM buffer back before the stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                float bj[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) bj[c] = (e_bias && cok[c]) ? __ldg(e_bias + ncol + c * 32) : 0.f;
+                const int ldc_i = (int)g.ldc;
+                float* cpn; long long m0n; int rowsn, ncoln;
+                wslice(tile + (int)gridDim.x, cpn, m0n, rowsn, ncoln);
+                bool cokn[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cokn[c] = ncoln + c * 32 < e_N;
+                // interior tiles (this slice and the next one complete): no predicates in the 128-store body
+                const bool interior = rows == 32 && rowsn == 32 && n_tile0 + half * 128 + 128 <= e_N &&
+                                      __all_sync(0xffffffffu, cokn[3]);
+                // each phase consumes the window (WIDE_WR rows) and refills it with the rows WIDE_WR further on: the
+                // last phase of a tile fetches the first rows of the next tile of this CTA
+                if (interior) {
+#pragma unroll
+                    for (int ph = 0; ph < 32 / WIDE_WR; ++ph) {
+                        if (ph == 32 / WIDE_WR - 1) wide_fill_start(e_tmpl, m0n, ncoln, g.rows_per_tmpl, e_N, fill_tp, fill_rem);
+                        wide_rows<false>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, 32, cok, fill_tp, fill_rem, g.rows_per_tmpl,
+                                         e_N, e_tmpl != nullptr, WIDE_WR, cok, lane);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int ph = 0; ph < 32 / WIDE_WR; ++ph) {
+                        const bool last = ph == 32 / WIDE_WR - 1;
+                        if (last) wide_fill_start(e_tmpl, m0n, ncoln, g.rows_per_tmpl, e_N, fill_tp, fill_rem);
+                        bool fok[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) fok[c] = last ? cokn[c] : cok[c];
+                        wide_rows<true>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, rows, cok, fill_tp, fill_rem, g.rows_per_tmpl,
+                                        e_N, e_tmpl != nullptr, last ? rowsn : rows - (ph + 1) * WIDE_WR, fok, lane);
                     }
                 }
             } else {
@@ -463,9 +597,11 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                                           apply_act_rt(tr[r * 32 + ((lane + r) & 31)] + bj, g.act) + add[r]);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (!(WIDE && wide)) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
             if (threadIdx.x == 64 && tile == (int)blockIdx.x) TL_STAMP(5);  // first tile's epilogue issued
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -839,7 +975,7 @@ static int launch_tc2(TmapSet& maps, const TcParams& p_in, cudaStream_t s) {
 
 template <int BN, typename TC, bool SCALAR>
 static int launch_tc(const TmapSet& maps, const TcParams& p, cudaStream_t s) {
-    using Cfg = TcCfg<BN, TC>;
+    using Cfg = TcCfg<BN, TC, tc_wide_v<BN, TC, SCALAR>>;
     auto kern = gemm_tc_kernel<BN, TC, SCALAR>;
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
