@@ -188,7 +188,7 @@ A2F_D void wide_rows(float (&tadd)[WIDE_WR * 4], const float* trw, const float (
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float o = (sv[c] + bj[c]) + tadd[r * 4 + c];
-            if (!PRED || (rr < rows && cok[c])) cpr[c * 32] = o;
+            if (!PRED || (rr < rows && cok[c])) __stcs(cpr + c * 32, o);     // written once, never re-read here
         }
         if (has_t) {
 #pragma unroll

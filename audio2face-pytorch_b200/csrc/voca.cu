@@ -2,13 +2,21 @@
 // concat(one_hot[:8]), Linear 72->72, Linear 72->128, tanh, Linear 128->50.  The last Linear 50->15069 + template add
 // is the shared vertex-head GEMM (a2f_gemm with tmpl), which is where VOCA's HBM bytes are.
 //
-// Each CTA keeps WPB windows in shared memory and walks the layers; a thread owns one output unit and reuses every
-// weight it loads for all WPB windows.  Accumulation order per output: bias first, then (ci, kh) ascending.
+// Each CTA keeps WPB windows in shared memory and walks the layers.  Activations are stored unit-major with the WPB
+// windows of a unit contiguous ([unit][WPB]), so a thread that owns one output unit reads the inputs of all its windows
+// as broadcast 16-byte loads; every layer's weights are transposed into shared memory first ([k][n], pitch n+1), so the
+// weight reads of a warp are consecutive.  Layers with fewer outputs than threads split the windows over 2 or 4 threads
+// per output.  Accumulation order per output: bias first, then (ci, kh) ascending (same as the oracle's loops).
 #include "a2f_common.cuh"
 
 namespace a2f {
 
-constexpr int WPB = 8;   // windows per CTA iteration
+constexpr int WPB = 16;              // windows per CTA iteration
+constexpr int VT = 256;              // threads per CTA
+constexpr int VOCA_W_FLOATS = 192 * 65;          // largest transposed weight block (conv 64->64: K = 192, N = 64)
+constexpr int VOCA_A_FLOATS = 37 * 16 * WPB;     // buffer A: input (592 units), later a2 / a4 / f2
+constexpr int VOCA_B_FLOATS = 32 * 8 * WPB;      // buffer B: a1 (256 units), later a3 / f1 / z
+constexpr size_t VOCA_SMEM = (size_t)(VOCA_W_FLOATS + VOCA_A_FLOATS + VOCA_B_FLOATS) * sizeof(float);
 
 struct VocaW {
     const float* cw[4];
@@ -17,97 +25,142 @@ struct VocaW {
     const float* fb[3];
 };
 
-template <int CIN, int HIN, int COUT>
-__device__ __forceinline__ void voca_conv(const float* __restrict__ in /*[WPB][CIN][HIN]*/,
-                                          float* __restrict__ out /*[WPB][out_stride]*/, int out_stride,
-                                          const float* __restrict__ w, const float* __restrict__ b) {
-    constexpr int HOUT = HIN / 2;
-    for (int o = threadIdx.x; o < COUT * HOUT; o += blockDim.x) {
-        const int co = o / HOUT, ho = o % HOUT;
-        float acc[WPB];
-        const float bv = __ldg(b + co);
-#pragma unroll
-        for (int i = 0; i < WPB; ++i) acc[i] = bv;
-        for (int ci = 0; ci < CIN; ++ci) {
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const int hi = 2 * ho + kh - 1;
-                if (hi < 0 || hi >= HIN) continue;
-                const float wv = __ldg(w + (co * CIN + ci) * 3 + kh);
-#pragma unroll
-                for (int i = 0; i < WPB; ++i) acc[i] = fmaf(wv, in[(i * CIN + ci) * HIN + hi], acc[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < WPB; ++i) out[i * out_stride + co * HOUT + ho] = relu(acc[i]);
+// w [N][K] (row-major, K = ci*3+kh for the convs) -> sw [K][N+1]
+template <int K, int N>
+__device__ __forceinline__ void voca_stage_w(const float* __restrict__ w, float* __restrict__ sw) {
+    for (int e = threadIdx.x; e < N * K; e += VT) {
+        const int n = e / K, k = e - n * K;
+        sw[k * (N + 1) + n] = __ldg(w + e);
     }
 }
 
-template <int K, int N, int ACT>
-__device__ __forceinline__ void voca_fc(const float* __restrict__ in, int in_stride, float* __restrict__ out,
-                                        int out_stride, const float* __restrict__ w, const float* __restrict__ b) {
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float acc[WPB];
-        const float bv = __ldg(b + n);
+// one output unit x WN windows: acc[i] = bias, then += w[k] * in[unit(k)][win0 + i] over the live taps
+template <int CIN, int HIN, int COUT, int SPLIT>
+__device__ __forceinline__ void voca_conv(const float* __restrict__ in /*[CIN*HIN][WPB]*/,
+                                          float* __restrict__ out /*[out_units][WPB]*/,
+                                          const float* __restrict__ sw /*[CIN*3][COUT+1]*/, const float* __restrict__ b) {
+    constexpr int HOUT = HIN / 2, O = COUT * HOUT, WN = WPB / SPLIT;
+    static_assert(O * SPLIT <= VT && WN % 4 == 0, "voca_conv: mapping");
+    const int t = threadIdx.x;
+    if (t >= O * SPLIT) return;
+    const int part = t / O, o = t - part * O;
+    const int ho = o / COUT, co = o - ho * COUT;        // consecutive threads: consecutive output channels
+    float acc[WN];
+    const float bv = __ldg(b + co);
 #pragma unroll
-        for (int i = 0; i < WPB; ++i) acc[i] = bv;
-        for (int k = 0; k < K; ++k) {
-            const float wv = __ldg(w + n * K + k);
+    for (int i = 0; i < WN; ++i) acc[i] = bv;
+    const float* inp = in + part * WN;
+#pragma unroll 2
+    for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
-            for (int i = 0; i < WPB; ++i) acc[i] = fmaf(wv, in[i * in_stride + k], acc[i]);
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hi = 2 * ho + kh - 1;
+            if (hi < 0 || hi >= HIN) continue;
+            const float wv = sw[(ci * 3 + kh) * (COUT + 1) + co];
+            const float4* ip = reinterpret_cast<const float4*>(inp + (ci * HIN + hi) * WPB);
+#pragma unroll
+            for (int i = 0; i < WN / 4; ++i) {
+                const float4 v = ip[i];
+                acc[4 * i + 0] = fmaf(wv, v.x, acc[4 * i + 0]);
+                acc[4 * i + 1] = fmaf(wv, v.y, acc[4 * i + 1]);
+                acc[4 * i + 2] = fmaf(wv, v.z, acc[4 * i + 2]);
+                acc[4 * i + 3] = fmaf(wv, v.w, acc[4 * i + 3]);
+            }
         }
-#pragma unroll
-        for (int i = 0; i < WPB; ++i) out[i * out_stride + n] = apply_act<ACT>(acc[i]);
     }
+    float4* op = reinterpret_cast<float4*>(out + (co * HOUT + ho) * WPB + part * WN);
+#pragma unroll
+    for (int i = 0; i < WN / 4; ++i)
+        op[i] = make_float4(relu(acc[4 * i]), relu(acc[4 * i + 1]), relu(acc[4 * i + 2]), relu(acc[4 * i + 3]));
+}
+
+template <int K, int N, int ACT, int SPLIT>
+__device__ __forceinline__ void voca_fc(const float* __restrict__ in /*[K][WPB]*/, float* __restrict__ out /*[N][WPB]*/,
+                                        const float* __restrict__ sw /*[K][N+1]*/, const float* __restrict__ b) {
+    constexpr int WN = WPB / SPLIT;
+    static_assert(N * SPLIT <= VT && WN % 4 == 0, "voca_fc: mapping");
+    const int t = threadIdx.x;
+    if (t >= N * SPLIT) return;
+    const int part = t / N, n = t - part * N;
+    float acc[WN];
+    const float bv = __ldg(b + n);
+#pragma unroll
+    for (int i = 0; i < WN; ++i) acc[i] = bv;
+    const float* inp = in + part * WN;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float wv = sw[k * (N + 1) + n];
+        const float4* ip = reinterpret_cast<const float4*>(inp + k * WPB);
+#pragma unroll
+        for (int i = 0; i < WN / 4; ++i) {
+            const float4 v = ip[i];
+            acc[4 * i + 0] = fmaf(wv, v.x, acc[4 * i + 0]);
+            acc[4 * i + 1] = fmaf(wv, v.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(wv, v.z, acc[4 * i + 2]);
+            acc[4 * i + 3] = fmaf(wv, v.w, acc[4 * i + 3]);
+        }
+    }
+    float4* op = reinterpret_cast<float4*>(out + n * WPB + part * WN);
+#pragma unroll
+    for (int i = 0; i < WN / 4; ++i)
+        op[i] = make_float4(apply_act<ACT>(acc[4 * i]), apply_act<ACT>(acc[4 * i + 1]), apply_act<ACT>(acc[4 * i + 2]),
+                            apply_act<ACT>(acc[4 * i + 3]));
 }
 
 template <typename TZ>
-__global__ void __launch_bounds__(256) voca_trunk_kernel(VocaW w, const float* __restrict__ x,
-                                                         const float* __restrict__ one_hot, int n_onehot,
-                                                         TZ* __restrict__ z, int ldz, int B) {
-    __shared__ float s_in[WPB * 37 * 16];
-    __shared__ float s_a1[WPB * 32 * 8];
-    __shared__ float s_a2[WPB * 32 * 4];
-    __shared__ float s_a3[WPB * 64 * 2];
-    __shared__ float s_a4[WPB * 72];
-    __shared__ float s_f1[WPB * 72];
-    __shared__ float s_f2[WPB * 128];
-    __shared__ float s_z[WPB * 50];
+__global__ void __launch_bounds__(VT, 2) voca_trunk_kernel(VocaW w, const float* __restrict__ x,
+                                                           const float* __restrict__ one_hot, int n_onehot,
+                                                           TZ* __restrict__ z, int ldz, int B) {
+    extern __shared__ __align__(16) float vsm[];
+    float* sw = vsm;
+    float* sA = vsm + VOCA_W_FLOATS;
+    float* sB = sA + VOCA_A_FLOATS;
 
     for (int w0 = blockIdx.x * WPB; w0 < B; w0 += gridDim.x * WPB) {
         // input assembly: channels 0..28 = features, 29..36 = tiled one-hot: emb[r][c] = oh8[(16 r + c) % 8]
-        for (int i = threadIdx.x; i < WPB * 37 * 16; i += blockDim.x) {
-            const int wi = i / (37 * 16), rem = i % (37 * 16), ch = rem / 16, h = rem % 16;
-            const int bw = w0 + wi;
-            float v = 0.f;
-            if (bw < B) {
-                if (ch < 29) v = x[((long long)bw * 29 + ch) * 16 + h];
-                else v = one_hot[(long long)bw * n_onehot + ((16 * (ch - 29) + h) % 8)];
-            }
-            s_in[i] = v;
+        for (int i = threadIdx.x; i < WPB * 29 * 16; i += VT) {
+            const int wi = i / (29 * 16), u = i - wi * (29 * 16), bw = w0 + wi;      // coalesced over a window's features
+            sA[u * WPB + wi] = (bw < B) ? x[(long long)bw * (29 * 16) + u] : 0.f;
         }
-        for (int i = threadIdx.x; i < WPB * 8; i += blockDim.x) {
-            const int wi = i / 8, j = i % 8, bw = w0 + wi;
-            s_a4[wi * 72 + 64 + j] = (bw < B) ? one_hot[(long long)bw * n_onehot + j] : 0.f;
+        for (int i = threadIdx.x; i < WPB * 8 * 16; i += VT) {
+            const int wi = i % WPB, u = i / WPB, ch = u / 16, h = u % 16, bw = w0 + wi;
+            sA[(29 * 16 + u) * WPB + wi] = (bw < B) ? one_hot[(long long)bw * n_onehot + ((16 * ch + h) % 8)] : 0.f;
+        }
+        voca_stage_w<37 * 3, 32>(w.cw[0], sw);
+        __syncthreads();
+        voca_conv<37, 16, 32, 1>(sA, sB, sw, w.cb[0]);            // in (A) -> a1 (B)
+        __syncthreads();
+        voca_stage_w<32 * 3, 32>(w.cw[1], sw);
+        __syncthreads();
+        voca_conv<32, 8, 32, 2>(sB, sA, sw, w.cb[1]);             // a1 (B) -> a2 (A)
+        __syncthreads();
+        voca_stage_w<32 * 3, 64>(w.cw[2], sw);
+        __syncthreads();
+        voca_conv<32, 4, 64, 2>(sA, sB, sw, w.cb[2]);             // a2 (A) -> a3 (B)
+        __syncthreads();
+        voca_stage_w<64 * 3, 64>(w.cw[3], sw);
+        for (int i = threadIdx.x; i < WPB * 8; i += VT) {         // one_hot[:8] behind the 64 conv features
+            const int wi = i % WPB, j = i / WPB, bw = w0 + wi;
+            sA[(64 + j) * WPB + wi] = (bw < B) ? one_hot[(long long)bw * n_onehot + j] : 0.f;
         }
         __syncthreads();
-        voca_conv<37, 16, 32>(s_in, s_a1, 32 * 8, w.cw[0], w.cb[0]);
+        voca_conv<64, 2, 64, 4>(sB, sA, sw, w.cb[3]);             // a3 (B) -> a4[0..63] (A)
         __syncthreads();
-        voca_conv<32, 8, 32>(s_a1, s_a2, 32 * 4, w.cw[1], w.cb[1]);
+        voca_stage_w<72, 72>(w.fw[0], sw);
         __syncthreads();
-        voca_conv<32, 4, 64>(s_a2, s_a3, 64 * 2, w.cw[2], w.cb[2]);
+        voca_fc<72, 72, A2F_ACT_NONE, 2>(sA, sB, sw, w.fb[0]);    // a4 (A) -> f1 (B)
         __syncthreads();
-        voca_conv<64, 2, 64>(s_a3, s_a4, 72, w.cw[3], w.cb[3]);   // -> first 64 of the 72-vector
+        voca_stage_w<72, 128>(w.fw[1], sw);
         __syncthreads();
-        voca_fc<72, 72, A2F_ACT_NONE>(s_a4, 72, s_f1, 72, w.fw[0], w.fb[0]);
+        voca_fc<72, 128, A2F_ACT_TANH, 2>(sB, sA, sw, w.fb[1]);   // f1 (B) -> f2 (A)
         __syncthreads();
-        voca_fc<72, 128, A2F_ACT_TANH>(s_f1, 72, s_f2, 128, w.fw[1], w.fb[1]);
+        voca_stage_w<128, 50>(w.fw[2], sw);
         __syncthreads();
-        voca_fc<128, 50, A2F_ACT_NONE>(s_f2, 128, s_z, 50, w.fw[2], w.fb[2]);
+        voca_fc<128, 50, A2F_ACT_NONE, 4>(sA, sB, sw, w.fb[2]);   // f2 (A) -> z (B)
         __syncthreads();
-        for (int i = threadIdx.x; i < WPB * ldz; i += blockDim.x) {
-            const int wi = i / ldz, j = i % ldz, bw = w0 + wi;
-            if (bw < B) st_from_float(z + (long long)bw * ldz + j, j < 50 ? s_z[wi * 50 + j] : 0.f);
+        for (int i = threadIdx.x; i < WPB * ldz; i += VT) {
+            const int wi = i / ldz, j = i - wi * ldz, bw = w0 + wi;
+            if (bw < B) st_from_float(z + (long long)bw * ldz + j, j < 50 ? sB[j * WPB + wi] : 0.f);
         }
         __syncthreads();
     }
@@ -136,12 +189,18 @@ extern "C" int a2f_voca_trunk(const a2f_voca_weights* w, const float* x, const f
         vw.fb[i] = w->fc_b[i];
     }
     int grid = (B + WPB - 1) / WPB;
-    const int cap = 4 * sm_count();
+    const int cap = 2 * sm_count();
     if (grid > cap) grid = cap;
+    static bool attr_done = false;
+    if (!attr_done) {
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(voca_trunk_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOCA_SMEM));
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(voca_trunk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOCA_SMEM));
+        attr_done = true;
+    }
     if (z_dtype == A2F_BF16)
-        voca_trunk_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(vw, x, one_hot, n_onehot, static_cast<bf16*>(z), ldz, B);
+        voca_trunk_kernel<bf16><<<grid, VT, VOCA_SMEM, as_stream(stream)>>>(vw, x, one_hot, n_onehot, static_cast<bf16*>(z), ldz, B);
     else
-        voca_trunk_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(vw, x, one_hot, n_onehot, static_cast<float*>(z), ldz, B);
+        voca_trunk_kernel<float><<<grid, VT, VOCA_SMEM, as_stream(stream)>>>(vw, x, one_hot, n_onehot, static_cast<float*>(z), ldz, B);
     A2F_CHECK_LAUNCH("voca_trunk_kernel");
     count_launch();
     return A2F_OK;

@@ -390,8 +390,12 @@ def run_ours(args):
         n0 = lib.a2f_launch_count()
         call(*d_in)
         launches_per_step = int(lib.a2f_launch_count() - n0)
+        # device-resident leg: the inputs live in the graph's captured input buffers (GraphedForward.static_in), so a
+        # replay reads them in place; passing other tensors would add a device-to-device copy of every input per step
+        # (1 GB of per-sample templates at the VOCA shape).  The e2e leg uploads straight into the same buffers.
+        d_run = d_in if args.no_graph else step.static_in
         for _ in range(max(3, args.warmup)):
-            out = step(*d_in)
+            out = step(*d_run)
         barrier()
         # ------------------------------ device-resident timing (value) ------------------------------
         sampler = ClockSampler(local)
@@ -402,7 +406,7 @@ def run_ours(args):
         for s, e in ev:
             flush.zero_()                       # L2 flush, outside the event pair
             s.record()
-            out = step(*d_in)
+            out = step(*d_run)
             e.record()
         barrier()
         launches = launches_per_step * args.steps   # kernels of liba2f_sm100.so executed in the timed region
@@ -424,7 +428,12 @@ def run_ours(args):
         for i in range(args.steps):
             slot = i & 1
             comp.wait_event(done[slot])                         # the slot's previous D2H has drained
-            di = [t.to(dev, non_blocking=True) for t in h_in]   # H2D of this step's inputs
+            if args.no_graph:
+                di = [t.to(dev, non_blocking=True) for t in h_in]   # H2D of this step's inputs
+            else:
+                di = step.static_in                                 # H2D straight into the captured input buffers
+                for dst, src in zip(di, h_in):
+                    dst.copy_(src, non_blocking=True)
             d_stage[slot].copy_(step(*di))                      # graph output buffer is reused by the next replay
             outs[slot] = d_stage[slot]
             ready = torch.cuda.Event()
