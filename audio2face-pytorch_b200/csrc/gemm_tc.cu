@@ -64,11 +64,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, const TcParam
            ((uint64_t)(p.desc_layout & 7u) << 61);
 }
 
-// WIDE: the scalar epilogue of a 256-column fp32 tile stages 32 rows x 128 columns per epilogue warp (16 KB each) so
-// that every output / template row is touched in 512-byte runs; the smem comes out of the operand ring (2 stages: the
-// vertex heads have K <= 192 and are bound by the HBM traffic of the epilogue, not by the mainloop).
+// WIDE: the scalar epilogue of a 256-column fp32 tile gives every epilogue warp 32 rows x 128 columns, staged 16 rows at
+// a time (8 KB per warp), so that every output / template row is touched in 512-byte runs.  The operand ring shrinks to
+// 2 stages (the vertex heads have K <= 192 and are bound by the HBM traffic of the epilogue, not by the mainloop): 160 KB
+// of shared memory in total, which leaves the L1 large enough for the template loads in flight.
 template <int BN, typename TC, bool SCALAR> constexpr bool tc_wide_v = SCALAR && BN == 256 && sizeof(TC) == 4;
-constexpr int WIDE_WARP_FLOATS = 32 * 128;
+constexpr int WIDE_WARP_FLOATS = 16 * 128;      // staging block of one epilogue warp: 16 rows x 128 columns
 constexpr int WIDE_WR = 8;               // rows of the rolling template window (WIDE_WR x 4 loads per lane in flight)
 
 template <int BN, typename TC, bool WIDE = false> struct TcCfg {
@@ -183,7 +184,7 @@ A2F_D void wide_rows(float (&tadd)[WIDE_WR * 4], const float* trw, const float (
         const int rr = row_base + r;
         float sv[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sv[c] = trw[c * 1024 + rr * 32 + ((lane + rr) & 31)];
+        for (int c = 0; c < 4; ++c) sv[c] = trw[c * 512 + (rr & 15) * 32 + ((lane + rr) & 31)];
         float* cpr = cp + (long long)(rr * ldc);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -454,20 +455,6 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     tadd_primed = true;
                 }
                 float* trw = reinterpret_cast<float*>(sEpi) + ew * WIDE_WARP_FLOATS;
-                __syncwarp();
-#pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
-                    if (half * 128 + cc * 32 >= n_lim) break;
-                    float v[32];
-                    tmem_ld_32x32(t_row + half * 128 + cc * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) trw[cc * 1024 + lane * 32 + ((j + lane) & 31)] = v[j];
-                }
-                // the accumulator is in smem: hand the TMEM buffer back before the stores
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 float bj[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) bj[c] = (e_bias && cok[c]) ? __ldg(e_bias + ncol + c * 32) : 0.f;
@@ -480,25 +467,51 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                 // interior tiles (this slice and the next one complete): no predicates in the 128-store body
                 const bool interior = rows == 32 && rowsn == 32 && n_tile0 + half * 128 + 128 <= e_N &&
                                       __all_sync(0xffffffffu, cokn[3]);
-                // each phase consumes the window (WIDE_WR rows) and refills it with the rows WIDE_WR further on: the
-                // last phase of a tile fetches the first rows of the next tile of this CTA
-                if (interior) {
+                // Two passes of 16 rows: the staging block holds 16 rows x 128 columns (8 KB per warp), so that the
+                // kernel's shared memory stays at 160 KB and the L1 keeps enough lines for the template loads in flight
+                // (with the 228 KB carve-out a pure streaming kernel of this pattern drops from 6.0 to 4.1 TB/s,
+                // profiles/r1_vertex_head_access_pattern.txt).  Each pass re-reads the accumulator chunks from TMEM and
+                // the lanes of its row half write them transposed.
 #pragma unroll
-                    for (int ph = 0; ph < 32 / WIDE_WR; ++ph) {
-                        if (ph == 32 / WIDE_WR - 1) wide_fill_start(e_tmpl, m0n, ncoln, g.rows_per_tmpl, e_N, fill_tp, fill_rem);
-                        wide_rows<false>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, 32, cok, fill_tp, fill_rem, g.rows_per_tmpl,
-                                         e_N, e_tmpl != nullptr, WIDE_WR, cok, lane);
-                    }
-                } else {
+                for (int hp = 0; hp < 2; ++hp) {
+                    __syncwarp();
 #pragma unroll 1
-                    for (int ph = 0; ph < 32 / WIDE_WR; ++ph) {
-                        const bool last = ph == 32 / WIDE_WR - 1;
-                        if (last) wide_fill_start(e_tmpl, m0n, ncoln, g.rows_per_tmpl, e_N, fill_tp, fill_rem);
-                        bool fok[4];
+                    for (int cc = 0; cc < 4; ++cc) {
+                        if (half * 128 + cc * 32 >= n_lim) break;
+                        float v[32];
+                        tmem_ld_32x32(t_row + half * 128 + cc * 32, v);
+                        tmem_ld_wait();
+                        if ((lane >> 4) == hp) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) fok[c] = last ? cokn[c] : cok[c];
-                        wide_rows<true>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, rows, cok, fill_tp, fill_rem, g.rows_per_tmpl,
-                                        e_N, e_tmpl != nullptr, last ? rowsn : rows - (ph + 1) * WIDE_WR, fok, lane);
+                            for (int j = 0; j < 32; ++j) trw[cc * 512 + (lane & 15) * 32 + ((j + lane) & 31)] = v[j];
+                        }
+                    }
+                    if (hp == 1) tc_fence_before();
+                    __syncwarp();
+                    // second pass read: hand the TMEM buffer back before the remaining stores
+                    if (hp == 1 && lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    // each phase consumes the window (WIDE_WR rows) and refills it with the rows WIDE_WR further on:
+                    // the last phase of a tile fetches the first rows of the next tile of this CTA
+                    if (interior) {
+#pragma unroll
+                        for (int ph = hp * (16 / WIDE_WR); ph < (hp + 1) * (16 / WIDE_WR); ++ph) {
+                            if (ph == 32 / WIDE_WR - 1)
+                                wide_fill_start(e_tmpl, m0n, ncoln, g.rows_per_tmpl, e_N, fill_tp, fill_rem);
+                            wide_rows<false>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, 32, cok, fill_tp, fill_rem,
+                                             g.rows_per_tmpl, e_N, e_tmpl != nullptr, WIDE_WR, cok, lane);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int ph = hp * (16 / WIDE_WR); ph < (hp + 1) * (16 / WIDE_WR); ++ph) {
+                            const bool last = ph == 32 / WIDE_WR - 1;
+                            if (last) wide_fill_start(e_tmpl, m0n, ncoln, g.rows_per_tmpl, e_N, fill_tp, fill_rem);
+                            bool fok[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) fok[c] = last ? cokn[c] : cok[c];
+                            wide_rows<true>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, rows, cok, fill_tp, fill_rem,
+                                            g.rows_per_tmpl, e_N, e_tmpl != nullptr,
+                                            last ? rowsn : rows - (ph + 1) * WIDE_WR, fok, lane);
+                        }
                     }
                 }
             } else {

@@ -37,6 +37,46 @@ __global__ void __launch_bounds__(256, 1) pat(const float* __restrict__ t, float
         }
     }
 }
+// rolling window like the WIDE epilogue: WR rows x 4 chunks per lane always in flight, every consumed slot refilled at once
+template <int WR>
+__global__ void __launch_bounds__(256, 1) roll(const float* __restrict__ t, float* __restrict__ o, int M) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = warp >> 2;
+    const int tiles_n = (N + BN - 1) / BN, tiles_m = M / TBM, total = tiles_n * tiles_m;
+    float v[WR * 4];
+    auto base = [&](int tile, long long& row0, int& col0) {
+        const int nb = tile % tiles_n, mb = tile / tiles_n;
+        row0 = (long long)mb * TBM + q * 32;
+        col0 = nb * BN + half * 128 + lane;
+    };
+    long long row0; int col0;
+    base(blockIdx.x, row0, col0);
+#pragma unroll
+    for (int r = 0; r < WR; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r * 4 + c] = (col0 + c * 32 < N) ? __ldg(t + (row0 + r) * N + col0 + c * 32) : 0.f;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        base(tile, row0, col0);
+        long long rown = 0; int coln = 0;
+        const bool hasn = tile + (int)gridDim.x < total;
+        if (hasn) base(tile + gridDim.x, rown, coln);
+#pragma unroll
+        for (int ph = 0; ph < 32 / WR; ++ph) {
+            const bool last = ph == 32 / WR - 1;
+#pragma unroll
+            for (int r = 0; r < WR; ++r) {
+                const int rr = ph * WR + r;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float x = v[r * 4 + c];
+                    if (!last) v[r * 4 + c] = (col0 + c * 32 < N) ? __ldg(t + (row0 + rr + WR) * N + col0 + c * 32) : 0.f;
+                    else v[r * 4 + c] = (hasn && coln + c * 32 < N) ? __ldg(t + (rown + r) * N + coln + c * 32) : 0.f;
+                    if (col0 + c * 32 < N) o[(row0 + rr) * N + col0 + c * 32] = x + 1.f;
+                }
+            }
+        }
+    }
+}
 __global__ void flat(const float* __restrict__ t, float* __restrict__ o, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = t[i] + 1.f;
 }
@@ -61,6 +101,16 @@ int main() {
     rep("rows8 x 512B, 2 CTAs/SM", timeit([&] { pat<4, 8, 0><<<296, 256>>>(t, o, M); }));
     rep("rows32 x 128B, 4 CTAs/SM", timeit([&] { pat<1, 32, 0><<<592, 256>>>(t, o, M); }));
     rep("rows8 x 512B, 4 CTAs/SM", timeit([&] { pat<4, 8, 0><<<592, 256>>>(t, o, M); }));
+    rep("rolling window 8 rows x 512B, 8 warps", timeit([&] { roll<8><<<148, 256>>>(t, o, M); }));
+    rep("rolling window 16 rows x 512B, 8 warps", timeit([&] { roll<16><<<148, 256>>>(t, o, M); }));
+    rep("rolling window 4 rows x 512B, 8 warps", timeit([&] { roll<4><<<148, 256>>>(t, o, M); }));
+    // the same kernel with the GEMM's shared-memory carve-out (224 KB dynamic smem -> ~28 KB of L1 left)
+    cudaFuncSetAttribute(roll<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    rep("rolling 8 rows x 512B, 224 KB smem", timeit([&] { roll<8><<<148, 256, 224 * 1024>>>(t, o, M); }));
+    cudaFuncSetAttribute(roll<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    rep("rolling 8 rows x 512B, 160 KB smem", timeit([&] { roll<8><<<148, 256, 160 * 1024>>>(t, o, M); }));
+    cudaFuncSetAttribute(roll<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    rep("rolling 4 rows x 512B, 224 KB smem", timeit([&] { roll<4><<<148, 256, 224 * 1024>>>(t, o, M); }));
     cudaError_t e = cudaDeviceSynchronize(); printf("%s\n", cudaGetErrorString(e));
     return 0;
 }
