@@ -410,7 +410,6 @@ def run_ours(args):
             e.record()
         barrier()
         launches = launches_per_step * args.steps   # kernels of liba2f_sm100.so executed in the timed region
-        clocks = sampler.stop() if rank == 0 else None
         dev_s = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
         # ------------------------------ end-to-end timing (host buffers) ----------------------------
         # every step: H2D of the step's inputs from pinned memory, forward, D2H of the step's result into pinned
@@ -446,6 +445,9 @@ def run_ours(args):
         t_e2e1.record()
         barrier()
         e2e_s = t_e2e0.elapsed_time(t_e2e1) * 1e-3
+        # clocks are sampled through both timed legs (device-resident and end-to-end): the first alone can be
+        # shorter than two nvidia-smi sampling periods
+        clocks = sampler.stop() if rank == 0 else None
         # ------------------------------ per-kernel roofline pass (instrumented, untimed) -------------
         # The GPU is parked on a spin kernel first so that the host has enqueued every launch and event of the pass
         # before the device starts: the event pairs then bracket kernels that run back to back (no host-side gaps).
@@ -546,9 +548,17 @@ def run_ours(args):
         byts = 2 * (B * 15069 * 4) * len(head)            # template read + vertex write per launch
         t_head = sum(t for _, t in head)
         achieved = byts / t_head / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic_voca.json")
+        if args.workload == "voca" and B == 16384 and os.path.exists(tpath):   # the committed ncu pass is of this shape
+            tj = json.load(open(tpath))
+            traffic = tj["gemm_tc_all"]["dram_bytes_per_launch"]
+            traffic_src = "profiles/r1_traffic_voca.json (dram bytes read + written per launch, mean over %d launches)" % tj["gemm_tc_all"]["launches"]
         roofline = {"bound": "hbm", "kernel": "a2f::gemm_tc_kernel<256,float,scalar> (vertex head + template add)",
                     "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                    "traffic": None, "peak_source": pk["source"]}
+                    "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": byts // max(len(head), 1),
+                    "kernel_share_of_step": (t_head / max(len(head), 1)) / (dev_s / args.steps),
+                    "peak_source": pk["source"]}
 
     threads = os.cpu_count() or 1
     if world == 1 and not args.no_cpu_baseline:
@@ -627,7 +637,6 @@ def run_train(args):
         out = trainer.step(*d_in)
         e.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     dev_s = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
     loss_last = float(out["loss"])
     # end to end: every step uploads its batch (audio, one-hot, template, ground-truth vertices) from pinned host
@@ -665,6 +674,9 @@ def run_train(args):
     t1.record()
     barrier()
     e2e_s = t0.elapsed_time(t1) * 1e-3
+    # clocks are sampled through both timed legs (device-resident and end-to-end): the first alone can be
+    # shorter than two nvidia-smi sampling periods
+    clocks = sampler.stop() if rank == 0 else None
     # per-kernel roofline pass (instrumented, untimed)
     torch.cuda.synchronize()
     torch.cuda._sleep(int(0.3 * 1.9e9))      # park the GPU while the host enqueues the instrumented steps (see run_ours)
@@ -767,7 +779,6 @@ def run_conv_train(args):
         out = trainer.step(*d_in)
         e.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     dev_s = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
     loss_last = float(out["loss"])
     h_loss = torch.empty(3, dtype=torch.float32).pin_memory()
@@ -781,6 +792,9 @@ def run_conv_train(args):
     t1.record()
     barrier()
     e2e_s = t0.elapsed_time(t1) * 1e-3
+    # clocks are sampled through both timed legs (device-resident and end-to-end): the first alone can be
+    # shorter than two nvidia-smi sampling periods
+    clocks = sampler.stop() if rank == 0 else None
     torch.cuda.synchronize()
     torch.cuda._sleep(int(0.3 * 1.9e9))
     ops.PROFILE = []
