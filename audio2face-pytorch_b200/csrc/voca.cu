@@ -28,9 +28,20 @@ struct VocaW {
 // w [N][K] (row-major, K = ci*3+kh for the convs) -> sw [K][N+1]
 template <int K, int N>
 __device__ __forceinline__ void voca_stage_w(const float* __restrict__ w, float* __restrict__ sw) {
-    for (int e = threadIdx.x; e < N * K; e += VT) {
-        const int n = e / K, k = e - n * K;
-        sw[k * (N + 1) + n] = __ldg(w + e);
+    constexpr int UB = 8;                      // loads in flight per thread (the staging is L2-latency bound)
+#pragma unroll 1
+    for (int e0 = threadIdx.x; e0 < N * K; e0 += VT * UB) {
+        float v[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) v[u] = (e0 + u * VT < N * K) ? __ldg(w + e0 + u * VT) : 0.f;
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int e = e0 + u * VT;
+            if (e < N * K) {
+                const int n = e / K, k = e - n * K;
+                sw[k * (N + 1) + n] = v[u];
+            }
+        }
     }
 }
 
