@@ -175,9 +175,12 @@ A2F_D void wide_fill_start(const float* tmpl, long long m0, int ncol, int rpt, i
 // WIDE_WR output rows [row_base, row_base+WIDE_WR) of a warp's 32 x 128 slice: out = (acc + bias) + template, where the template
 // values come from the rolling window `tadd`; every consumed window slot is refilled at once from the refill stream
 // (WIDE_WR rows ahead).  PRED = false: slice and refill target are complete, no predicates.
-template <bool PRED>
+// HAS_T is a template parameter on purpose: with a run-time flag the compiler loads into a temporary and moves it into
+// the window under a predicate, and that move waits for the load at once (profiles/r1_voca_head_wide.txt: the hottest
+// instructions were those moves), which serialises the window.
+template <bool PRED, bool HAS_T>
 A2F_D void wide_rows(float (&tadd)[WIDE_WR * 4], const float* trw, const float (&bj)[4], float* cp, int ldc, int row_base, int rows,
-                     const bool (&cok)[4], const float*& tp, int& rem, int rpt, int N, bool has_t, int fill_rows,
+                     const bool (&cok)[4], const float*& tp, int& rem, int rpt, int N, int fill_rows,
                      const bool (&fok)[4], int lane) {
 #pragma unroll
     for (int r = 0; r < WIDE_WR; ++r) {
@@ -191,7 +194,7 @@ A2F_D void wide_rows(float (&tadd)[WIDE_WR * 4], const float* trw, const float (
             const float o = (sv[c] + bj[c]) + tadd[r * 4 + c];
             if (!PRED || (rr < rows && cok[c])) __stcs(cpr + c * 32, o);     // written once, never re-read here
         }
-        if (has_t) {
+        if (HAS_T) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if (PRED) tadd[r * 4 + c] = (r < fill_rows && fok[c]) ? __ldg(tp + c * 32) : 0.f;
@@ -497,8 +500,12 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                         for (int ph = hp * (16 / WIDE_WR); ph < (hp + 1) * (16 / WIDE_WR); ++ph) {
                             if (ph == 32 / WIDE_WR - 1)
                                 wide_fill_start(e_tmpl, m0n, ncoln, g.rows_per_tmpl, e_N, fill_tp, fill_rem);
-                            wide_rows<false>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, 32, cok, fill_tp, fill_rem,
-                                             g.rows_per_tmpl, e_N, e_tmpl != nullptr, WIDE_WR, cok, lane);
+                            if (e_tmpl != nullptr)
+                                wide_rows<false, true>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, 32, cok, fill_tp, fill_rem,
+                                                       g.rows_per_tmpl, e_N, WIDE_WR, cok, lane);
+                            else
+                                wide_rows<false, false>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, 32, cok, fill_tp, fill_rem,
+                                                        g.rows_per_tmpl, e_N, WIDE_WR, cok, lane);
                         }
                     } else {
 #pragma unroll 1
@@ -508,9 +515,13 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                             bool fok[4];
 #pragma unroll
                             for (int c = 0; c < 4; ++c) fok[c] = last ? cokn[c] : cok[c];
-                            wide_rows<true>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, rows, cok, fill_tp, fill_rem,
-                                            g.rows_per_tmpl, e_N, e_tmpl != nullptr,
-                                            last ? rowsn : rows - (ph + 1) * WIDE_WR, fok, lane);
+                            const int fill_rows = last ? rowsn : rows - (ph + 1) * WIDE_WR;
+                            if (e_tmpl != nullptr)
+                                wide_rows<true, true>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, rows, cok, fill_tp, fill_rem,
+                                                      g.rows_per_tmpl, e_N, fill_rows, fok, lane);
+                            else
+                                wide_rows<true, false>(tadd, trw, bj, cp, ldc_i, ph * WIDE_WR, rows, cok, fill_tp, fill_rem,
+                                                       g.rows_per_tmpl, e_N, fill_rows, fok, lane);
                         }
                     }
                 }
