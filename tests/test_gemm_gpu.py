@@ -160,3 +160,38 @@ def test_posconv(a2f_lib, dev, B, T):
         want = hh + F.gelu(pos).transpose(1, 2)
         err = float((out.cpu().double() - want).abs().max())
         assert err < tol, (backend, err)
+
+
+# Wide scalar epilogue of the 256-column fp32 tile (gemm_tc.cu, WIDE): 32 rows x 128 columns per epilogue warp, rolling
+# template window that runs ahead into the CTA's next tile.  Cases: more tiles than SMs (the window crosses tiles), ragged
+# last row tile (quarters with 28 and 0 live rows), ragged last column tile (221 / 89 live columns: partial and empty
+# chunks), one template row per output row / shared by 150 rows (changes inside a tile) / none, with and without bias.
+WIDE_CASES = [
+    # M, N, K, rows_per_tmpl (0 = no template), use_bias
+    (700, 15069, 192, 1, True),
+    (700, 15069, 192, 150, True),
+    (700, 15069, 64, 0, False),
+    (1, 15069, 64, 1, True),
+    (33, 601, 64, 1, False),
+    (2500, 2137, 128, 7, True),
+]
+
+
+@pytest.mark.parametrize("M,N,K,rpt,use_bias", WIDE_CASES)
+def test_tcgen05_wide_scalar_epilogue(a2f_lib, dev, M, N, K, rpt, use_bias):
+    from a2f_b200 import ops, lib as L
+    a = _rand((M, K), dev, 31, torch.bfloat16)
+    w = _rand((N, K), dev, 32, torch.bfloat16, scale=K ** -0.5)
+    b = _rand((N,), dev, 33) if use_bias else None
+    t = _rand(((M + rpt - 1) // rpt, N), dev, 34) if rpt else None
+    out = torch.full((M + 1, N), 7.0, device=dev)            # one guard row behind the output
+    try:
+        L.check(a2f_lib.a2f_debug_set_umma_field(4, 256))
+        ops.gemm(a, w, out[:M], bias=b, tmpl=t, rows_per_tmpl=max(rpt, 1), backend=L.TCGEN05)
+        torch.cuda.synchronize()
+    finally:
+        a2f_lib.a2f_debug_set_umma_field(4, 0)
+    want = _ref(a, w, b, 0, None, t, max(rpt, 1))
+    err = float((out[:M].cpu().double() - want).abs().max())
+    assert err < 2e-4, err
+    assert bool((out[M] == 7.0).all()), "the epilogue wrote past the last row"
