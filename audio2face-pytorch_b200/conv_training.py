@@ -21,10 +21,7 @@ S = L.SIMT_F32
 RELU, TANH, NONE = L.ACT_RELU, L.ACT_TANH, L.ACT_NONE
 
 
-def _grad(p: torch.nn.Parameter) -> torch.Tensor:
-    if p.grad is None:
-        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
-    return p.grad
+from .training import _grad, collect_grads      # noqa: E402  (gradient sink shared with the FaceFormer backward)
 
 
 class Pad:
@@ -299,11 +296,11 @@ def a2m_backward(m, tp: Dict, dout: torch.Tensor) -> None:
 
 
 class ConvModelTrainFn(torch.autograd.Function):
-    """Glue to torch.autograd for Voca / Audio2Mesh (same scheme as training.FaceformerTrainFn): the backward writes
-    every parameter gradient straight into `.grad`."""
+    """Glue to torch.autograd for Voca / Audio2Mesh (same scheme as training.FaceformerTrainFn): every parameter is an input
+    of the Function and its gradient an output of backward(), so AccumulateGrad / torch DDP hooks fire per parameter."""
 
     @staticmethod
-    def forward(ctx, anchor, model, kind, x, one_hot, tmpl):
+    def forward(ctx, model, kind, x, one_hot, tmpl, *params):
         fwd = voca_forward_train if kind == "voca" else a2m_forward_train
         out, tape = fwd(model, x, one_hot, tmpl)
         ctx.model, ctx.tape, ctx.kind = model, tape, kind
@@ -312,6 +309,11 @@ class ConvModelTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         bwd = voca_backward if ctx.kind == "voca" else a2m_backward
-        bwd(ctx.model, ctx.tape, dout.contiguous().float())
+        with collect_grads(list(ctx.model.parameters())) as sink:
+            bwd(ctx.model, ctx.tape, dout.contiguous().float())
         ctx.tape = None
-        return None, None, None, None, None, None
+        return (None, None, None, None, None) + sink.grads()
+
+    @staticmethod
+    def run(model, kind, x, one_hot, tmpl):
+        return ConvModelTrainFn.apply(model, kind, x, one_hot, tmpl, *model.parameters())

@@ -698,20 +698,53 @@ __global__ void posconv_pack_dgrad_kernel(const float* __restrict__ gw, const fl
 
 // ------------------------------------------------------------------------------------------------ Adam
 // torch.optim.Adam(lr, weight_decay) semantics (L2 added to the gradient), bias-corrected; grad pre-scaled by gscale.
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+// G = float: the local (or fp32 all-reduced) gradient; G = bf16: the gradient as it came off the wire of the bf16
+// all-reduce (trainer.FlatBuffers wire="bf16").  Four parameters per thread and iteration (every flat-buffer entry
+// starts on a 256-byte boundary and the buffers are padded to multiples of 64 floats).
+template <typename G>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const G* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, float lr, float b1, float b2,
                                                    float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
     const float step = lr / bc1;
-    for (; i < n; i += stride) {
-        const float pi = p[i];
-        const float gi = fmaf(wd, pi, g[i] * gscale);
-        const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
-        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
-        m[i] = mi;
-        v[i] = vi;
-        p[i] = pi - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pi = reinterpret_cast<const float4*>(p)[i];
+        float4 mi = reinterpret_cast<const float4*>(m)[i];
+        float4 vi = reinterpret_cast<const float4*>(v)[i];
+        float gi[4];
+        if (sizeof(G) == 4) {
+            const float4 t = reinterpret_cast<const float4*>(g)[i];
+            gi[0] = t.x; gi[1] = t.y; gi[2] = t.z; gi[3] = t.w;
+        } else {
+            const uint2 t = reinterpret_cast<const uint2*>(g)[i];
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+            gi[0] = a.x; gi[1] = a.y; gi[2] = b.x; gi[3] = b.y;
+        }
+        float* pp = &pi.x; float* mp = &mi.x; float* vp = &vi.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gj = fmaf(wd, pp[j], gi[j] * gscale);
+            mp[j] = fmaf(b1, mp[j], (1.f - b1) * gj);
+            vp[j] = fmaf(b2, vp[j], (1.f - b2) * gj * gj);
+            pp[j] = pp[j] - step * (mp[j] / (sqrtf(vp[j]) / bc2_sqrt + eps));
+        }
+        reinterpret_cast<float4*>(m)[i] = mi;
+        reinterpret_cast<float4*>(v)[i] = vi;
+        reinterpret_cast<float4*>(p)[i] = pi;
+    }
+    // tail (n not a multiple of 4): one thread
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (long long i = n4 << 2; i < n; ++i) {
+            const float pi = p[i];
+            const float gi = fmaf(wd, pi, ld_as_float(g + i) * gscale);
+            const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+            const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+            m[i] = mi;
+            v[i] = vi;
+            p[i] = pi - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+        }
     }
 }
 
@@ -1017,19 +1050,35 @@ int a2f_pack_posconv_dgrad_weight(const float* g, const float* v, void* out, int
     return A2F_OK;
 }
 
-int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, int step, float grad_scale, void* stream) {
+static int adam_launch(float* p, const void* g, int g_bf16, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, float grad_scale, void* stream) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "a2f_adam_step: bad arguments");
     if (n == 0) return A2F_OK;
+    A2F_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(g) & (g_bf16 ? 7 : 15)) == 0, "a2f_adam_step: buffers must be 16-byte aligned");
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
-    adam_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
-                                                           grad_scale);
+    if (g_bf16)
+        adam_kernel<bf16><<<ew_grid(n, 4), 256, 0, as_stream(stream)>>>(p, static_cast<const bf16*>(g), m, v, n, lr, beta1, beta2, eps,
+                                                                       weight_decay, bc1, bc2s, grad_scale);
+    else
+        adam_kernel<float><<<ew_grid(n, 4), 256, 0, as_stream(stream)>>>(p, static_cast<const float*>(g), m, v, n, lr, beta1, beta2,
+                                                                        eps, weight_decay, bc1, bc2s, grad_scale);
     A2F_CHECK_LAUNCH("adam_kernel");
     count_launch();
     return A2F_OK;
+}
+
+int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, float grad_scale, void* stream) {
+    return adam_launch(p, g, 0, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream);
+}
+
+int a2f_adam_step_bf16g(float* p, const void* g_bf16, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    return adam_launch(p, g_bf16, 1, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream);
 }
 
 int a2f_spec_mask_fwd(void* h, int dtype, const unsigned char* mask, const float* embed, long long rows, int cols,

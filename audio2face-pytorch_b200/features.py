@@ -172,6 +172,34 @@ class ExtractAndPredict(nn.Module):
         return GraphedForward(self, x, one_hot, template, **kwargs)
 
 
+class ClipToVerts(nn.Module):
+    """One clip -> one mesh per video frame: the reference's dataset + Lightning composition for the conv models
+    (ref:src/dataset/vocaset.py:408-430 get_audio_fragment per frame, :64-69 normalize_audio;
+    ref:src/model/lightning_model.py:111-117 extractor -> model).  forward(clip, one_hot, template): clip 1-D int16 or
+    float32 at `sample_rate`, one_hot [F,n], template [F,5023,3] with F = len(clip) * fps // sample_rate frames."""
+
+    def __init__(self, feature_extractor: nn.Module, model: nn.Module, *, fps: int = 60, sample_rate: int = 22000,
+                 length: float = 0.52):
+        super().__init__()
+        self.net = ExtractAndPredict(feature_extractor, model)
+        self.fps, self.sample_rate, self.length = int(fps), int(sample_rate), float(length)
+
+    def set_precision(self, precision: str):
+        self.net.set_precision(precision)
+        return self
+
+    def n_frames(self, n_samples: int) -> int:
+        return int(n_samples) * self.fps // self.sample_rate
+
+    def forward(self, clip, one_hot, template, **kwargs):
+        win = audio_fragments(clip, self.n_frames(clip.numel()), fps=self.fps, sample_rate=self.sample_rate, length=self.length)
+        return self.net(win, one_hot, template, **kwargs)
+
+    def graphed(self, clip, one_hot, template, **kwargs):
+        from .modules import GraphedForward
+        return GraphedForward(self, clip, one_hot, template, **kwargs)
+
+
 # ------------------------------------------------------------------------------------------------ audio preparation
 def audio_fragments(audio: torch.Tensor, n_frames: int, *, fps: int = 60, sample_rate: int = 22000, length: float = 0.52,
                     shift: int = 0, first_frame: int = 0) -> torch.Tensor:
@@ -184,6 +212,13 @@ def audio_fragments(audio: torch.Tensor, n_frames: int, *, fps: int = 60, sample
         raise L.A2FError("audio_fragments expects a 1-D float32 or int16 clip")
     audio = audio.contiguous()
     n_pad = int(sample_rate * length / 2)
+    if n_frames > 0:
+        # the reference returns None ("Audio is not long enough to get fragment", ref:vocaset.py:424-428) when a window
+        # ends beyond the padded clip; the batched kernel would zero-fill there, so refuse instead of inventing data
+        end = (int(first_frame) + int(n_frames) - 1) * int(sample_rate) // int(fps) + 2 * n_pad
+        if end > (n_pad + int(shift)) + audio.numel() + 2 * n_pad or first_frame < 0:
+            raise L.A2FError(f"audio_fragments: frame {first_frame + n_frames - 1} ends at padded sample {end}, beyond the clip "
+                             "(the reference's get_audio_fragment returns None here)")
     out = torch.empty((n_frames, 2 * n_pad), dtype=torch.float32, device=audio.device)
     L.check(L.load().a2f_audio_fragments(audio.data_ptr(), L.I16 if audio.dtype == torch.int16 else L.F32, audio.numel(),
                                          int(first_frame), int(n_frames), int(sample_rate), int(fps), n_pad, int(shift),
@@ -286,6 +321,15 @@ class Wav2VecExtractor(nn.Module):
             if n < 1:
                 raise L.A2FError("audio too short for one wav2vec2 frame")
             h = self._ff.encode(x, n, stats=stats)                    # [B*n, 768]
+            if self.out_dim == 768:
+                # ref:extractor.py:92-96 resizes only `if self.out_dim != x.shape[1]`, and that axis is the 768 channels
+                # after the transpose: with out_dim == 768 the reference returns the transposed hidden states [B,768,n]
+                if h.dtype != torch.float32:
+                    h32 = torch.empty(h.shape, dtype=torch.float32, device=h.device)
+                    L.check(L.load().a2f_cast_bf16_to_f32(h.data_ptr(), h32.data_ptr(), h.numel(),
+                                                          torch.cuda.current_stream().cuda_stream), "a2f_cast_bf16_to_f32")
+                    h = h32
+                return ops.transpose_batched(h.view(B, n, 768))
             out = torch.empty((B, self.out_dim, self.n_feature), dtype=torch.float32, device=x.device)
             L.check(L.load().a2f_bilinear_cl(h.data_ptr(), L.BF16 if h.dtype == torch.bfloat16 else L.F32, B, n, 768, self.out_dim,
                                              self.n_feature, out.data_ptr(), torch.cuda.current_stream().cuda_stream),

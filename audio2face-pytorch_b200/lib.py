@@ -119,6 +119,8 @@ _SIGNATURES = {
                                         c_void_p, c_size_t, c_void_p]),
     "a2f_ln64_param_grad": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
     "a2f_pack_feedback": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "a2f_pack_cross_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                         c_void_p, c_void_p]),
     "a2f_voca_trunk": (c_int, [C.POINTER(VocaWeights), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p]),
     "a2f_a2m_assemble": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
@@ -177,6 +179,8 @@ _SIGNATURES = {
     "a2f_song2face_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "a2f_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                               c_int, c_float, c_void_p]),
+    "a2f_adam_step_bf16g": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
+                                    c_int, c_float, c_void_p]),
 }
 
 DEC_SAVE_FIELDS = ("X", "Q", "K", "V", "CTX", "Y1PRE", "Y2PRE", "Y2", "HID", "Y3PRE", "LSE")      # a2f.h A2F_DEC_*

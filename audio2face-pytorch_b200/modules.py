@@ -87,6 +87,15 @@ class _A2FModule(nn.Module):
         self.precision = "fp32"
         self._cache = _PackCache()
 
+    def __call__(self, *args, **kwargs):
+        # run on the device of the inputs whatever torch's current device is (a torch module would too): the kernels are
+        # launched with raw pointers on the current device's stream
+        x = args[0] if args else None
+        if isinstance(x, torch.Tensor) and x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):
+                return super().__call__(*args, **kwargs)
+        return super().__call__(*args, **kwargs)
+
     def graphed(self, x, one_hot, template, **kwargs) -> GraphedForward:
         """Capture forward(x, one_hot, template, **kwargs) for these shapes as a CUDA graph."""
         return GraphedForward(self, x, one_hot, template, **kwargs)
@@ -127,7 +136,8 @@ class _A2FModule(nn.Module):
                 return ops.split_bf16x3(w, True)
             wp = self._cache.get("head_bf16x3", (weight,), build)
             z3 = ops.split_bf16x3(z, False)
-            ops.gemm(z3, wp, out, bias=bias.detach(), tmpl=template2d, rows_per_tmpl=rows_per_tmpl, backend=L.TCGEN05, K=192)
+            ops.gemm(z3, wp, out, bias=bias.detach(), tmpl=template2d, rows_per_tmpl=rows_per_tmpl, backend=L.TCGEN05, K=192,
+                     alg_K=k_live)
         else:
             ops.gemm(z, weight.detach(), out, bias=bias.detach(), tmpl=template2d, rows_per_tmpl=rows_per_tmpl,
                      backend=L.SIMT_F32, K=k_live)
@@ -176,8 +186,7 @@ class Voca(_A2FModule):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training step: taped forward + explicit backward kernels (conv_training.py), true-fp32 path
             from . import conv_training
-            anchor = next(p for p in self.parameters() if p.requires_grad)
-            return conv_training.ConvModelTrainFn.apply(anchor, self, "voca", x, one_hot, tmpl)
+            return conv_training.ConvModelTrainFn.run(self, "voca", x, one_hot, tmpl)
         z = torch.empty((bs, 64), dtype=torch.float32, device=x.device)
         ops.voca_trunk(self._weights_struct(), x, one_hot, z)
         out = self._vertex_head(z, self.decoder[4].weight, self.decoder[4].bias, tmpl, 1, 50)
@@ -304,8 +313,7 @@ class Audio2Mesh(_A2FModule):
             # model.train(): BatchNorm uses batch statistics and updates its running stats (conv_training.py)
             from . import conv_training
             if grad:
-                anchor = next(p for p in self.parameters() if p.requires_grad)
-                return conv_training.ConvModelTrainFn.apply(anchor, self, "audio2mesh", x, one_hot, tmpl)
+                return conv_training.ConvModelTrainFn.run(self, "audio2mesh", x, one_hot, tmpl)
             return conv_training.a2m_forward_train(self, x, one_hot, tmpl)[0]
         if grad:
             raise L.A2FError("Audio2Mesh: gradients with eval-mode (frozen) BatchNorm are not built; call .train() or "
@@ -554,8 +562,9 @@ class Faceformer(_A2FModule):
         self.feature_dim = 64
         self.n_onehot = n_onehot
         # training forward only: apply wav2vec2's SpecAugment time masking (ref:src/model/wav2vec.py:149-162) with the
-        # reference's host-side numpy draws (spec_augment.py).  Off by default = eval-mode arithmetic.
-        self.spec_augment = False
+        # reference's host-side numpy draws (spec_augment.py).  None = follow self.training like the reference does;
+        # True / False force it.
+        self.spec_augment = None
         self.dataset = "vocaset"
         self.period = 60
         self.fps = 60
@@ -629,14 +638,10 @@ class Faceformer(_A2FModule):
             P["ca_w"], P["ca_b"] = ca_w, ca_b
 
             def fold_ca():
-                with torch.no_grad():
-                    ca_mod = self.transformer_decoder.layers[0].multihead_attn
-                    wv = ca_mod.in_proj_weight.detach()[128:192].double()
-                    bv = ca_mod.in_proj_bias.detach()[128:192].double()
-                    wo, bo = ca_mod.out_proj.weight.detach().double(), ca_mod.out_proj.bias.detach().double()
-                    wa, ba = self.audio_feature_map.weight.detach().double(), self.audio_feature_map.bias.detach().double()
-                    ca_w.copy_(wo @ (wv @ wa))
-                    ca_b.copy_(wo @ (wv @ ba + bv) + bo)
+                ca_mod = self.transformer_decoder.layers[0].multihead_attn
+                ops.pack_cross_attention(ca_mod.in_proj_weight.detach(), ca_mod.in_proj_bias.detach(),
+                                         ca_mod.out_proj.weight.detach(), ca_mod.out_proj.bias.detach(),
+                                         self.audio_feature_map.weight.detach(), self.audio_feature_map.bias.detach(), ca_w, ca_b)
             wc = torch.empty((64, 64), dtype=torch.float32, device=dev)
             bc = torch.empty((64,), dtype=torch.float32, device=dev)
             P["fb"] = (wc, bc)
@@ -741,9 +746,8 @@ class Faceformer(_A2FModule):
             B = audio.shape[0]
             if audio.shape[1] * fps // 16000 < 1:
                 raise L.A2FError("audio too short for one output frame")
-            anchor = next(p for p in self.parameters() if p.requires_grad)
-            return training.FaceformerTrainFn.apply(anchor, self, audio, one_hot.reshape(B, -1).contiguous().float(),
-                                                    template.reshape(B, -1).contiguous().float(), fps)
+            return training.FaceformerTrainFn.run(self, audio, one_hot.reshape(B, -1).contiguous().float(),
+                                                  template.reshape(B, -1).contiguous().float(), fps)
         audio = audio.contiguous().float()
         if audio.dim() != 2:
             raise L.A2FError("audio must be [B, N] raw 16 kHz samples")
@@ -846,8 +850,19 @@ class FaceFormerLoss:
 def mse_error(pred: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
     """ref:src/model/lightning_model.py:119-125: mean_b mean_15069 (p-g)^2 == rec_loss / 3 (one fused pass)."""
     rows = pred.numel() // (5023 * 3)
-    if rows % 2 != 0:
-        raise L.A2FError("mse_error needs an even number of frames on this path")
+    if rows < 1 or not pred.is_cuda:
+        raise L.A2FError("mse_error runs on CUDA (sm_100a) only and needs at least one frame")
     p = pred.detach().reshape(rows, -1).contiguous().float()
     g = gt.detach().reshape(rows, -1).contiguous().float()
-    return ops.voca_loss_fwd(p, g, rows, p.shape[1], 1.0, 0.0)[1] / 3.0
+    v3 = p.shape[1]
+    even = rows - (rows % 2)
+    acc = None
+    if even:
+        acc = ops.voca_loss_fwd(p, g, even, v3, 1.0, 0.0)[1] * (even / rows)
+    if rows % 2:
+        # any frame count is legal here (the reference calls mse_error on the FULL prediction, odd-length FaceFormer
+        # clips included, ref:lightning_model.py:119-125,156): the paired-row kernel takes the last row twice
+        lp, lg = p[rows - 1:].expand(2, v3).contiguous(), g[rows - 1:].expand(2, v3).contiguous()
+        last = ops.voca_loss_fwd(lp, lg, 2, v3, 1.0, 0.0)[1] * (1.0 / rows)
+        acc = last if acc is None else acc + last
+    return acc / 3.0

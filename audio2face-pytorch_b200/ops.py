@@ -31,9 +31,22 @@ def _dt(t: torch.Tensor) -> int:
 
 
 def _dev(*ts):
+    """Every tensor of a call lives on ONE CUDA device and that device is torch's current one: kernels are launched on
+    torch.cuda.current_stream() of the current device with raw pointers, so a tensor of another GPU would fault (the
+    drop-in modules switch devices themselves, _A2FModule.__call__; direct callers use `with torch.cuda.device(...)`)."""
+    idx = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise L.A2FError("a2f ops need CUDA tensors (there is no CPU path)")
+        if idx is None:
+            idx = t.device.index
+        elif t.device.index != idx:
+            raise L.A2FError(f"a2f ops need all tensors on one device (got cuda:{idx} and cuda:{t.device.index})")
+    if idx is not None and idx != torch.cuda.current_device():
+        raise L.A2FError(f"tensors live on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}; "
+                         f"wrap the call in `with torch.cuda.device({idx}):`")
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
@@ -42,7 +55,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
          a_row_stride: Optional[int] = None, a_batch_stride: int = 0, rows_per_batch: Optional[int] = None,
          N: Optional[int] = None, ldw: Optional[int] = None, ldc: Optional[int] = None, c_batch_stride: int = 0,
          c_offset: int = 0, a_rows: int = 0, segs=None, resid_mode: int = 0, ldr: Optional[int] = None,
-         r_batch_stride: int = 0, r_offset: int = 0) -> torch.Tensor:
+         r_batch_stride: int = 0, r_offset: int = 0, alg_K: Optional[int] = None) -> torch.Tensor:
     """out[m,n] = act(sum_k a[m,k] w[n,k] + bias[n]) + resid[m,n] + tmpl[m // rows_per_tmpl, n]  (a2f_gemm)."""
     _dev(a, w, out, bias, resid, tmpl)
     lib = L.load()
@@ -83,7 +96,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         s.record()
         L.check(lib.a2f_gemm(C.byref(g), backend, _stream()), "a2f_gemm")
         e.record()
-        PROFILE.append(("gemm_tc" if backend == L.TCGEN05 else "gemm_simt", 2.0 * g.M * g.N * g.K, s, e))
+        # alg_K: contraction length of the ALGORITHM when the operands carry an error-compensated split (bf16x3: K = 3 x alg_K)
+        PROFILE.append(("gemm_tc" if backend == L.TCGEN05 else "gemm_simt", 2.0 * g.M * g.N * (alg_K if alg_K else g.K), s, e))
         return out
     L.check(lib.a2f_gemm(C.byref(g), backend, _stream()), "a2f_gemm")
     return out
@@ -365,6 +379,18 @@ def pack_feedback(vm_w, vm_b, vmr_w, vmr_b, out=None):
     L.check(L.load().a2f_pack_feedback(vm_w.data_ptr(), vm_b.data_ptr(), vmr_w.data_ptr(), vmr_b.data_ptr(),
                                        vmr_w.shape[0], wc.data_ptr(), bc.data_ptr(), _stream()), "a2f_pack_feedback")
     return wc, bc
+
+
+def pack_cross_attention(in_proj_w, in_proj_b, out_w, out_b, afm_w, afm_b, W: torch.Tensor, b: torch.Tensor) -> None:
+    """W[64,Kin], b[64] = out_proj(v_proj(audio_feature_map(.))) folded in fp64 (a2f_pack_cross_attention).  in_proj_*: the
+    packed [192,64] / [192] multihead_attn.in_proj parameters (rows 128..191 = v)."""
+    _dev(in_proj_w, in_proj_b, out_w, out_b, afm_w, afm_b, W, b)
+    for t in (in_proj_w, in_proj_b, out_w, out_b, afm_w, afm_b):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise L.A2FError("pack_cross_attention takes contiguous fp32 parameters")
+    L.check(L.load().a2f_pack_cross_attention(in_proj_w.data_ptr() + 128 * 64 * 4, in_proj_b.data_ptr() + 128 * 4, out_w.data_ptr(),
+                                              out_b.data_ptr(), afm_w.data_ptr(), afm_b.data_ptr(), afm_w.shape[1], W.data_ptr(),
+                                              _dt(W), b.data_ptr(), _stream()), "a2f_pack_cross_attention")
 
 
 def decoder_rollout(wstruct: "L.DecoderWeights", memory: torch.Tensor, one_hot: torch.Tensor, period: int, B: int, T: int,
@@ -667,9 +693,24 @@ def mha_bwd(qkv, out, dout, lse, B, T, H=12, D=64, scale=0.125, out_f32: Optiona
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    """fused Adam (+ L2 weight decay) over flat fp32 buffers; `g` fp32, or bf16 as it comes off a bf16 all-reduce."""
     _dev(p, g, m, v)
-    L.check(L.load().a2f_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
-                                   weight_decay, int(step), grad_scale, _stream()), "a2f_adam_step")
+    if g.numel() != p.numel():
+        raise L.A2FError("adam_step: gradient and parameter buffers differ in length")
+    fn = L.load().a2f_adam_step_bf16g if g.dtype == torch.bfloat16 else L.load().a2f_adam_step
+    if g.dtype not in (torch.bfloat16, torch.float32):
+        raise L.A2FError("adam_step: gradient must be fp32 or bf16")
+    L.check(fn(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+               weight_decay, int(step), grad_scale, _stream()), "a2f_adam_step")
+
+
+def cast_into(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[:] = bf16(x) for contiguous fp32 x / bf16 out of equal length (a2f_cast_f32_to_bf16)."""
+    _dev(x, out)
+    if x.dtype != torch.float32 or out.dtype != torch.bfloat16 or x.numel() != out.numel() or not (x.is_contiguous() and out.is_contiguous()):
+        raise L.A2FError("cast_into: contiguous fp32 -> bf16 of equal length")
+    L.check(L.load().a2f_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "a2f_cast_f32_to_bf16")
+    return out
 
 
 class DecoderTape:

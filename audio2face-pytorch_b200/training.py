@@ -29,10 +29,54 @@ GELU = L.ACT_GELU
 V3PAD = 15072          # 15069 rounded up to a multiple of 8 (16-byte bf16 rows for TMA)
 
 
+_GRAD_SINK = None      # set by collect_grads(): id(param) -> buffer the explicit backward accumulates into instead of .grad
+
+
 def _grad(p: torch.nn.Parameter) -> torch.Tensor:
+    """Where the explicit backward accumulates dL/dp: the parameter's .grad (allocated as zeros when missing -- the flat
+    gradient buffer under trainer.FlatBuffers), or the sink of an enclosing collect_grads()."""
+    if _GRAD_SINK is not None:
+        _GRAD_SINK.touched.add(id(p))
+        return _GRAD_SINK.bufs[id(p)]
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return p.grad
+
+
+class collect_grads:
+    """Context manager for the torch.autograd glue: inside it the explicit backward writes every parameter gradient into
+    views of ONE fresh zero-filled flat buffer (parameters in the order given, each on a 256-byte boundary, so the fused
+    q|k|v weight-gradient GEMM still applies) instead of touching `.grad`.  `grads()` then hands them to autograd as the
+    Function's outputs: AccumulateGrad (and with it torch DDP's reducer hooks, Lightning's gradient clipping, hooks
+    registered by the user) sees them exactly as it sees the reference's gradients."""
+
+    def __init__(self, params, order_key=None):
+        self.params = list(params)
+        self.touched = set()
+        order = sorted(range(len(self.params)), key=(lambda i: (order_key(i), i)) if order_key else None)
+        offs, off = {}, 0
+        for i in order:
+            offs[i] = off
+            off += (self.params[i].numel() + 63) // 64 * 64
+        dev = self.params[0].device if self.params else None
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.bufs = {id(p): self.flat[offs[i]:offs[i] + p.numel()].view(p.shape) for i, p in enumerate(self.params)}
+
+    def __enter__(self):
+        global _GRAD_SINK
+        if _GRAD_SINK is not None:
+            raise L.A2FError("nested backward passes are not supported")
+        _GRAD_SINK = self
+        return self
+
+    def __exit__(self, *exc):
+        global _GRAD_SINK
+        _GRAD_SINK = None
+        return False
+
+    def grads(self):
+        """One entry per parameter: its gradient, or None when the backward never wrote it / it does not require grad."""
+        return tuple(self.bufs[id(p)] if (id(p) in self.touched and p.requires_grad) else None for p in self.params)
 
 
 def conv_lengths(n_samples: int) -> List[int]:
@@ -158,7 +202,7 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
     M = B * T
     h0 = torch.empty((M, 768), dtype=dt, device=dev)
     ops.gemm(xi.view(M, 512), P["proj_w"], h0, bias=fp.projection.bias.detach(), backend=be)
-    if getattr(model, "spec_augment", False):
+    if spec_augment_active(model):
         # SpecAugment (ref:src/model/wav2vec.py:149-162): the mask is drawn on the host with the reference's numpy
         # sequence (spec_augment.py), applied and back-propagated by the a2f_spec_mask_* kernels
         mask = spec_augment.time_mask(B, T)
@@ -389,9 +433,17 @@ N_GRAD_STAGES = 14
 NO_GRAD_PARAMS = ("audio_encoder.masked_spec_embed",)     # unused without SpecAugment: grad is None in the reference too
 
 
+def spec_augment_active(model) -> bool:
+    """SpecAugment runs when `model.spec_augment` is True, or -- left at None -- whenever the module is in train mode: the
+    reference applies it under `self.training` (HF config apply_spec_augment=True, mask_time_prob=0.05,
+    ref:src/model/wav2vec.py:149-162)."""
+    sa = getattr(model, "spec_augment", None)
+    return bool(model.training if sa is None else sa)
+
+
 def no_grad_params(model) -> tuple:
     """Parameters that receive no gradient from backward() for this model configuration."""
-    return () if getattr(model, "spec_augment", False) else NO_GRAD_PARAMS
+    return () if spec_augment_active(model) else NO_GRAD_PARAMS
 
 
 def grad_stage_of(name: str) -> int:
@@ -426,17 +478,29 @@ def _adjacent(ts) -> bool:
 
 
 class FaceformerTrainFn(torch.autograd.Function):
-    """Glue to torch.autograd: `anchor` is one parameter of the model (so the output requires grad); the backward
-    writes ALL parameter gradients straight into their .grad buffers and returns nothing for the anchor."""
+    """Glue to torch.autograd.  Every parameter of the model is an INPUT of the Function and its gradient an output of
+    backward(), so AccumulateGrad runs per parameter: `.grad` accumulates like the reference's, and torch DDP (what the
+    reference's Lightning Trainer wraps the model in on a multi-GPU box, ref:train.py:48-60) sees every gradient in its
+    reducer hooks.  (trainer.FaceformerTrainer is the fast path: flat buffers, bucketed all-reduce started from inside the
+    backward, fused Adam -- it calls forward_train / backward directly and never comes through here.)"""
 
     @staticmethod
-    def forward(ctx, anchor, model, audio, one_hot, tmpl, fps):
+    def forward(ctx, model, audio, one_hot, tmpl, fps, *params):
         out, tape = forward_train(model, audio, one_hot, tmpl, fps)
         ctx.model, ctx.tape = model, tape
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        backward(ctx.model, ctx.tape, dout.contiguous().float())
+        model = ctx.model
+        names = {id(p): n for n, p in model.named_parameters()}
+        params = list(model.parameters())
+        key = lambda i: (grad_stage_of(names[id(params[i])]), grad_order_in_stage(names[id(params[i])]))   # noqa: E731
+        with collect_grads(params, key) as sink:
+            backward(model, ctx.tape, dout.contiguous().float())
         ctx.tape = None
-        return None, None, None, None, None, None
+        return (None, None, None, None, None) + sink.grads()
+
+    @staticmethod
+    def run(model, audio, one_hot, tmpl, fps):
+        return FaceformerTrainFn.apply(model, audio, one_hot, tmpl, fps, *model.parameters())

@@ -179,6 +179,29 @@ def cpu_reference_frames_per_s(workload: str, fps: int, seconds: float, n_utt: i
             dt = time.perf_counter() - t0
             return reps * B / dt, (f"{reps} x {B} windows: MFCC + Audio2Mesh train-mode forward + VocaLoss + autograd backward, fp32 "
                                    "(no optimizer step)")
+        if workload == "voca_config0":
+            import numpy as np
+            from oracle import ref_audio as ora, ref_mfcc as omf
+            z0 = np.load(os.path.join(ROOT, "tests", "golden", "config0_voca.npz"))
+            cfg = omf.CONFIGS["voca"]
+            sd, bufs = ow.make_state_dict("voca", int(z0["weight_seed"])), omf.make_buffers(cfg[0], cfg[1], cfg[3], cfg[5])
+            F_ = int(z0["n_frames"])
+            oh = torch.zeros(F_, 12)
+            oh[:, 0] = 1.0
+            tp = oin.flame_like_template(int(z0["template_seed"]))[None].expand(F_, -1, -1).contiguous()
+
+            def run():
+                win = ora.fragments(z0["clip"], F_)
+                return orm.voca_forward(sd, omf.mfcc_forward(bufs, win, cfg[2], cfg[3], cfg[4], cfg[5]), oh, tp)
+            run()
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 4.0:
+                run()
+                reps += 1
+            dt = time.perf_counter() - t0
+            return reps * F_ / dt, (f"{reps} x the 348-window clip: get_audio_fragment loop + MFCC (torch stft path) + VOCA, fp32 "
+                                    "(the configuration BASELINE.json configs[0] says runs on CPU)")
         if workload == "voca_audio":
             from oracle import ref_mfcc as omf
             cfg = omf.CONFIGS["voca"]
@@ -228,8 +251,8 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     vals = []
     sample = ""
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        pass
+    if args.warmup > 0:        # one untimed pass (thread pool, allocator, lazily built oracle state); more would only repeat it
+        cpu_reference_frames_per_s(args.workload, args.fps, min(args.seconds, 1.0), 1, threads)
     for _ in range(max(1, args.steps)):
         v, sample = cpu_reference_frames_per_s(args.workload, args.fps, args.seconds, 1, threads)
         vals.append(v)
@@ -239,7 +262,12 @@ def run_reference(args):
         "impl": "reference", "metric": "mesh frames/sec (5023-vert FLAME)", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (T / value if args.workload.startswith("faceformer") else 4096 / value),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "config": dict(workload_config(args), reference_arm=(
+            "oracle port (oracle/ref_models.py: plain torch fp32 restatement, pinned to the live reference by tests/golden) on all "
+            "host cores; each step is a bounded sample of the workload (one utterance / one timed batch loop); one untimed "
+            "warm-up pass whatever --warmup says; conservative: the real reference also materialises and returns 12 x "
+            "[12,T,T] attention maps (ref:src/model/wav2vec.py:101), does a D2H+H2D round trip for the processor, and "
+            "cannot be imported on the GPU box (ref:src/model/lightning_model.py:14 needs a missing module)")),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -287,6 +315,14 @@ def workload_config(args):
                 "precision": "fp32 SIMT GEMMs for the model's forward / backward (the 1e-5 parity path)",
                 "weights": "random-init (oracle.weights seed 12)",
                 "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)", "launch": "eager"}
+    if args.workload == "voca_config0":
+        return {"workload": "voca_inference_audio_sample_348_windows (BASELINE.json configs[0], literal shape)",
+                "input": "the reference's assets/audio_sample.npy (int16, 22 kHz, 127 600 samples; carried by tests/golden/config0_voca.npz)",
+                "step": "clip -> 348 windows of 11 440 samples (get_audio_fragment / normalize_audio) -> MFCC(16 x 29) -> Voca -> [348,5023,3]",
+                "batch_per_gpu": 348, "vertices": 5023, "weights": "random-init (oracle.weights seed 11)", "template": "one per window (module interface)",
+                "check": "assets/verts_sample.npy is absent from the reference checkout; parity is against the live reference modules (fixture)",
+                "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
+                "launch": "eager" if args.no_graph else "one CUDA graph per forward (modules.GraphedForward)"}
     if args.workload == "voca_audio":
         return {"workload": f"mfcc_plus_voca_b{args.batch}_windows (BASELINE.json configs[0] from raw audio: SURVEY.md 8(f) rank 1 + a18)",
                 "batch_per_gpu": args.batch, "window_samples": 11440, "sample_rate": 22000,
@@ -299,24 +335,60 @@ def workload_config(args):
             "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)"}
 
 
-# ---------------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
 
-    import a2f_b200
-    from a2f_b200 import modules, ops, lib as L
+class Ctx:
+    """One process per GPU: rank / device / process group are set up ONCE in main() and shared by every workload leg."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        from a2f_b200 import lib as L
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1 and not dist.is_initialized():
+            # the gradient all-reduce of the training leg runs UNDER the backward kernels: cap NCCL's CTAs so that the
+            # persistent GEMM kernels keep their SMs (NVLS / NVSwitch needs few; override with the environment)
+            os.environ.setdefault("NCCL_MAX_CTAS", "16")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = L.load()
+        L.check(self.lib.a2f_device_check(), "a2f_device_check")
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return vals
+        t = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(x) for x in t)
+
+    def close(self):
+        import torch.distributed as dist
+        if self.world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args, ctx):
+    """Inference workloads (configs[2] headline, configs[0], configs[1], ...).  Returns the JSON line (rank 0) or None."""
+    import torch
+
+    import a2f_b200  # noqa: F401
+    from a2f_b200 import modules, ops
     from oracle import inputs as oin, weights as ow       # input / weight generators only (not the timed path)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = L.load()
-    L.check(lib.a2f_device_check(), "a2f_device_check")
+    world, rank, local, dev, lib = ctx.world, ctx.rank, ctx.local, ctx.dev, ctx.lib
 
     B = args.batch
     if args.workload == "faceformer":
@@ -366,6 +438,26 @@ def run_ours(args):
         flops_step = B * (2.0 * 29 * 1026 * 790 + 1.679e6)       # DFT as a GEMM over the window support + VOCA
         call = lambda a, o, t: model(a, o, t)                    # noqa: E731
         out_shape = (B, 5023, 3)
+    elif args.workload == "voca_config0":
+        # BASELINE.json configs[0] at its literal shape: the reference's assets/audio_sample.npy (int16, 22 kHz, 127 600
+        # samples; carried by tests/golden/config0_voca.npz together with the live reference's vertices) -> 348 windows
+        # -> MFCC -> VOCA.  One step = the whole clip.
+        import numpy as np
+        from a2f_b200 import features
+        z0 = np.load(os.path.join(ROOT, "tests", "golden", "config0_voca.npz"))
+        voca = modules.Voca(15069, 12)
+        voca.load_state_dict(ow.make_state_dict("voca", int(z0["weight_seed"])), strict=True)
+        model = features.ClipToVerts(features.MFCCExtractor(22000, 16, 29, 790, None, 1024), voca).to(dev).eval()
+        model.set_precision("bf16")
+        B = args.batch = int(z0["n_frames"])
+        oh0 = torch.zeros(B, 12)
+        oh0[:, 0] = 1.0
+        h_in = [torch.from_numpy(z0["clip"]).pin_memory(), oh0.pin_memory(),
+                oin.flame_like_template(int(z0["template_seed"]))[None].expand(B, -1, -1).contiguous().pin_memory()]
+        units = B
+        flops_step = B * (2.0 * 29 * 1026 * 790 + 1.679e6)
+        call = lambda a, o, t: model(a, o, t)                    # noqa: E731
+        out_shape = (B, 5023, 3)
     else:
         model = modules.Voca(15069, 12)
         model.load_state_dict(ow.make_state_dict("voca", 11), strict=True)
@@ -377,12 +469,7 @@ def run_ours(args):
         call = lambda a, o, t: model(a, o, t)                    # noqa: E731
         out_shape = (B, 5023, 3)
     d_in = [t.to(dev) for t in h_in]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    flush, barrier = ctx.flush, ctx.barrier
 
     with torch.no_grad():
         # the product's fixed-shape fast path: one forward captured as a CUDA graph (modules.GraphedForward)
@@ -411,6 +498,8 @@ def run_ours(args):
         barrier()
         launches = launches_per_step * args.steps   # kernels of liba2f_sm100.so executed in the timed region
         dev_s = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
+        n_par = {"faceformer": 1, "voca": 64}.get(args.workload, B)     # samples of the LAST TIMED step kept for the parity check
+        timed_out = out[:n_par].detach().cpu() if rank == 0 else None
         # ------------------------------ end-to-end timing (host buffers) ----------------------------
         # every step: H2D of the step's inputs from pinned memory, forward, D2H of the step's result into pinned
         # memory.  Copies run on a side stream so that step i's D2H overlaps step i+1's compute (double-buffered).
@@ -460,14 +549,11 @@ def run_ours(args):
         prof = deglitch(ops.PROFILE)
         ops.PROFILE = None
 
-    if world > 1:
-        t = torch.tensor([dev_s, e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, e2e_s = float(t[0]), float(t[1])
+    dev_s, e2e_s = ctx.max_over_ranks(dev_s, e2e_s)
+    del model, step
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     pk = peaks()
     total_units = units * world
@@ -543,6 +629,20 @@ def run_ours(args):
                     "traffic": None, "peak_source": pk["source"] + ", sustained bf16", "launches_per_step": 1,
                     "executed_tflops": sum(f for f, _ in dft) / g_time / 1e12,
                     "kernel_share_of_step": (g_time / len(dft)) / (dev_s / args.steps)}
+    elif args.workload == "voca_config0":
+        # 348 windows: 42.6 MB of algorithmic traffic per step (122 456 B per window) in 6 launches -- a
+        # latency-bound step; the roofline line is the WHOLE step against HBM, the head launch is listed beside it
+        gem = [(f, t) for (kind, f, t) in prof if kind == "gemm_tc"]
+        head = gem[1::2]
+        byts = B * 122456 + h_in[0].numel() * 2
+        achieved = byts / (dev_s / args.steps) / 1e9
+        roofline = {"bound": "hbm", "kernel": "whole step (a2f_audio_fragments, mfcc_frames, DFT gemm_tc2, mfcc_mel_db, mfcc_dct_resize, "
+                                              "voca_trunk, vertex-head gemm_tc)",
+                    "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                    "algorithmic_bytes_per_step": byts, "launches_per_step": launches_per_step,
+                    "head_launch_us": 1e6 * sum(t for _, t in head) / max(len(head), 1),
+                    "head_launch_gbs": 2 * (B * 15069 * 4) * len(head) / max(sum(t for _, t in head), 1e-12) / 1e9,
+                    "peak_source": pk["source"]}
     else:
         head = [(f, t) for (kind, f, t) in prof if kind == "gemm_tc"]
         byts = 2 * (B * 15069 * 4) * len(head)            # template read + vertex write per launch
@@ -578,29 +678,62 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "parity": infer_parity(args, timed_out, h_in),
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
-def run_train(args):
-    """BASELINE.json configs[3]: FaceFormer bf16 training step, data-parallel, batch 8 per GPU."""
+def infer_parity(args, timed_out, h_in):
+    """The oracle as the CHECKER of the timed output (rank 0's last timed step), never as the thing measured: max error of
+    the first sample(s) against the CPU restatement (configs[0] literal: against the live-reference fixture)."""
+    import numpy as np
     import torch
-    import torch.distributed as dist
+    from oracle import ref_models as orm, weights as ow
 
-    from a2f_b200 import modules, ops, trainer as tr, lib as L
+    n = timed_out.shape[0]
+    a, oh, tp = h_in[0], h_in[1][:n], h_in[2][:n]
+    if args.workload != "voca_config0":
+        a = a[:n]
+    with torch.no_grad():
+        if args.workload == "faceformer":
+            want = orm.faceformer_forward(_SD_CACHE.get("faceformer") or _SD_CACHE.setdefault("faceformer", ow.make_state_dict("faceformer", 13)),
+                                          a, oh, tp, args.fps)
+            err = float((timed_out - want).abs().max()) / 100.0               # centimetres -> metres
+            off = float((want - tp[:, None]).abs().max()) / 100.0
+            return {"checked": f"utterance 0 of the last timed step vs oracle.faceformer_forward (fp32 CPU), {want.shape[1]} frames",
+                    "max_abs_err_m": err, "tol_m": 5e-4, "err_rel_to_max_offset": err / off, "ok": bool(err < 5e-4)}
+        if args.workload == "voca_config0":
+            z0 = np.load(os.path.join(ROOT, "tests", "golden", "config0_voca.npz"))
+            err = float(np.abs(timed_out.reshape(-1)[:: int(z0["verts_step"])].numpy() - z0["verts_sub"]).max())
+            return {"checked": "all 348 windows of the last timed step vs the LIVE reference's vertices for assets/audio_sample.npy "
+                               "(tests/golden/config0_voca.npz, sub-sampled)", "max_abs_err": err, "tol": 5e-4,
+                    "err_rel_to_max_offset": err / float(z0["offset_absmax"]), "ok": bool(err < 5e-4)}
+        if args.workload == "voca":
+            want = orm.voca_forward(ow.make_state_dict("voca", 11), a, oh, tp)
+            tol = 5e-5
+        elif args.workload == "audio2mesh":
+            want = orm.audio2mesh_forward(ow.make_state_dict("audio2mesh", 12), a, oh, tp)
+            tol = 2e-4
+        elif args.workload == "song2face":
+            want = orm.song2face_forward(ow.make_state_dict("song2face", 14), a, oh, tp)
+            tol = 2e-4
+        else:
+            return None
+        err = float((timed_out - want).abs().max())
+        off = float((want - tp).abs().max())
+        return {"checked": f"first {n} windows of the last timed step vs the oracle (fp32 CPU)", "max_abs_err": err, "tol": tol,
+                "err_rel_to_max_offset": err / off, "ok": bool(err < tol)}
+
+
+def run_train(args, ctx):
+    """BASELINE.json configs[3]: FaceFormer bf16 training step, data-parallel, batch 8 per GPU.  Under torchrun the step's
+    gradient all-reduce (NCCL) is inside the timed region."""
+    import torch
+
+    from a2f_b200 import modules, ops, trainer as tr, training
     from oracle import inputs as oin, weights as ow       # input / weight generators only (not the timed path)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = L.load()
-    L.check(lib.a2f_device_check(), "a2f_device_check")
+    world, rank, local, dev, lib = ctx.world, ctx.rank, ctx.local, ctx.dev, ctx.lib
     B, n = args.batch, int(16000 * args.seconds)
     T = n * args.fps // 16000
     model = modules.Faceformer(15069, 12)
@@ -611,14 +744,21 @@ def run_train(args):
     h_in = [oin.audio(B, n, 100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(), tp.pin_memory(),
             oin.gt_like((B, T, 5023, 3), tp[:, None], 200 + rank, scale=100.0).pin_memory()]
     d_in = [t.to(dev) for t in h_in]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush, barrier = ctx.flush, ctx.barrier
     units = B * T
     flops_step = 3.0 * B * ff_flops_per_utt(n, T)        # fwd + dgrad + wgrad
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # parity of the path about to be timed (rank 0): the taped forward of this batch at the initial weights, utterance 0's
+    # FaceFormerLoss from the loss kernel vs the oracle's forward + loss (checker only)
+    parity = None
+    if rank == 0:
+        with torch.no_grad():
+            out0, _tape = training.forward_train(model, d_in[0], d_in[1], d_in[2].reshape(B, -1), args.fps)
+            Te = T - (T % 2)
+            l_gpu = ops.voca_loss_fwd(out0[0, :Te].reshape(Te, -1).contiguous(), d_in[3][0, :Te].reshape(Te, -1).contiguous(), Te,
+                                      15069, 1.0, 10.0).cpu()
+            del out0, _tape
+        parity = train_parity(args, l_gpu, h_in)
 
     n0 = lib.a2f_launch_count()
     loss0 = trainer.step(*d_in)["loss"]
@@ -686,14 +826,12 @@ def run_train(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = deglitch(ops.PROFILE), None
 
-    if world > 1:
-        t = torch.tensor([dev_s, e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, e2e_s = float(t[0]), float(t[1])
+    dev_s, e2e_s = ctx.max_over_ranks(dev_s, e2e_s)
+    comm = {"world": world, "gradient_bytes_fp32": int(trainer.flat.total) * 4, "wire": trainer.wire_description()}
+    del trainer, model
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     pk = peaks()
     total_units = units * world
     gem = [(f, t) for (kind, f, t) in prof if kind in ("gemm_tc", "wgrad_tc")]
@@ -720,30 +858,31 @@ def run_train(args):
                 "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in h_in), "d2h_bytes_per_step": 12,
                 "note": "pinned host batch (audio, one-hot, template, ground-truth vertices) in, loss scalars out; the upload of step i+1 overlaps step i (copy stream, double-buffered device batch)"},
         "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "loss_first_step": float(loss0), "loss_last_timed_step": loss_last,
+        "loss_first_step": float(loss0), "loss_last_timed_step": loss_last, "parity": parity, "gradient_exchange": comm,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
-def run_conv_train(args):
+def train_parity(args, l_gpu, h_in):
+    import torch
+    from oracle import ref_models as orm, weights as ow
+    sd = _SD_CACHE.get("faceformer") or _SD_CACHE.setdefault("faceformer", ow.make_state_dict("faceformer", 13))
+    with torch.no_grad():
+        want = orm.faceformer_loss(orm.faceformer_forward(sd, h_in[0][:1], h_in[1][:1], h_in[2][:1], args.fps), h_in[3][:1])
+    rel = {k: abs(float(l_gpu[j]) - float(want[k])) / abs(float(want[k])) for j, k in enumerate(("loss", "rec_loss", "vel_loss"))}
+    return {"checked": "utterance 0 of the timed batch at the initial weights: taped bf16 forward + loss kernel vs the oracle's fp32 "
+                       "forward + FaceFormerLoss", "loss_gpu": float(l_gpu[0]), "loss_oracle": float(want["loss"]),
+            "rel_err": rel, "tol_rel": 1e-4, "ok": bool(max(rel.values()) < 1e-4)}
+
+
+def run_conv_train(args, ctx):
     """The reference's default configuration (ref:config.yaml): Audio2Mesh + MFCC extractor, batch 128, one training step."""
     import torch
-    import torch.distributed as dist
 
-    from a2f_b200 import features, modules, ops, trainer as tr, lib as L
+    from a2f_b200 import features, modules, ops, trainer as tr
     from oracle import inputs as oin, weights as ow       # input / weight generators only (not the timed path)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = L.load()
-    L.check(lib.a2f_device_check(), "a2f_device_check")
+    world, rank, local, dev, lib = ctx.world, ctx.rank, ctx.local, ctx.dev, ctx.lib
     B = args.batch
     model = modules.Audio2Mesh(15069, 12)
     model.load_state_dict(ow.make_state_dict("audio2mesh", 12), strict=True)
@@ -754,13 +893,8 @@ def run_conv_train(args):
     h_in = [oin.speech_like_windows(B, seed=100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(), tp.pin_memory(),
             oin.gt_like((B, 5023, 3), tp, 200 + rank).pin_memory()]
     d_in = [t.to(dev) for t in h_in]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush, barrier = ctx.flush, ctx.barrier
     flops_step = 3.0 * B * 131.0e6 + B * 2.0 * 53 * 1026 * 440      # fwd + dgrad + wgrad of the model, DFT of the extractor
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     n0 = lib.a2f_launch_count()
     loss0 = float(trainer.step(*d_in)["loss"])
@@ -802,14 +936,11 @@ def run_conv_train(args):
         trainer.step(*d_in)
     torch.cuda.synchronize()
     prof, ops.PROFILE = deglitch(ops.PROFILE), None
-    if world > 1:
-        t = torch.tensor([dev_s, e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, e2e_s = float(t[0]), float(t[1])
+    dev_s, e2e_s = ctx.max_over_ranks(dev_s, e2e_s)
+    del trainer, model
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     gem = [(f, t) for (kind, f, t) in prof if kind == "gemm_simt"]
     g_flops, g_time = sum(f for f, _ in gem), sum(t for _, t in gem)
     fp32_peak = 148 * 128 * 2 * 1.965e-3
@@ -835,9 +966,83 @@ def run_conv_train(args):
         "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "loss_first_step": loss0, "loss_last_timed_step": loss_last,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def run_sweep(args, ctx):
+    """BASELINE.json configs[4] in brief (the full grid is tools/sweep_long.py): FaceFormer autoregressive decode of long
+    utterances at 60 fps, TOTAL batch fixed per point (strong scaling: B_total / n_gpus utterances per rank, at least one --
+    ranks beyond B_total run replicas and are not counted), eager launches, bf16."""
+    import torch
+
+    from a2f_b200 import modules
+    from oracle import inputs as oin, weights as ow       # input / weight generators only (not the timed path)
+
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    m = modules.Faceformer(15069, 12)
+    m.load_state_dict(ow.make_state_dict("faceformer", 13), strict=True)
+    m = m.to(dev).eval().set_precision("bf16")
+    pk = peaks()
+    rows = []
+    steps = max(2, min(args.steps, 3))
+    for L_s, B_total in ((10.0, 128), (30.0, 32), (60.0, 8)):
+        n = int(16000 * L_s)
+        T = n * 60 // 16000
+        Bp = max(1, B_total // world)
+        counted = min(world, B_total)                       # ranks holding distinct utterances
+        audio = oin.audio(1, n, 7 + rank).to(dev).expand(Bp, n).contiguous()
+        audio *= torch.linspace(0.7, 1.3, Bp, device=dev)[:, None]
+        oh = oin.one_hot(Bp, 12, 7).to(dev)
+        tp = oin.batch_templates(1, 7, scale=100.0).to(dev).expand(Bp, 5023, 3).contiguous()
+        with torch.no_grad():
+            for _ in range(2):
+                out = m(audio, oh, tp, fps=60)
+            finite = bool(torch.isfinite(out[:, -1]).all())
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            ctx.barrier()
+            for s_, e_ in ev:
+                ctx.flush.zero_()
+                s_.record()
+                out = m(audio, oh, tp, fps=60)
+                e_.record()
+            ctx.barrier()
+        sec, = ctx.max_over_ranks(sum(s_.elapsed_time(e_) for s_, e_ in ev) * 1e-3)
+        del out, audio, tp
+        torch.cuda.empty_cache()
+        frames = counted * Bp * T * steps / sec
+        tfl = counted * Bp * ff_flops_per_utt(n, T) * steps / sec / 1e12
+        rows.append({"seconds": L_s, "batch_total": counted * Bp, "batch_per_gpu": Bp, "gpus_with_work": counted,
+                     "frames_per_utterance": T, "ms_per_step": 1e3 * sec / steps, "frames_per_s": frames, "tflops": tfl,
+                     "frac_of_bf16_sustained": tfl / (pk["bf16_sustained"] * counted), "finite": finite})
+    del m
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"metric": "mesh frames/sec (5023-vert FLAME)", "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": 2,
+            "scaling": "strong (total batch fixed per point)", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "faceformer_long_sequence_sweep_60fps (BASELINE.json configs[4], three points; full grid: "
+                                   "tools/sweep_long.py -> profiles/)", "launch": "eager",
+                       "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)"},
+            "points": rows, "value": max(r["frames_per_s"] for r in rows)}
+
+
+EXTRA_WORKLOADS = (          # (key, workload, batch, fps) -- legs the default invocation runs after the headline
+    ("voca_config0", "voca_config0", 348, None),
+    ("voca_b16384", "voca", 16384, None),
+    ("audio2mesh_b64", "audio2mesh", 64, None),
+    ("faceformer_train_b8", "faceformer_train", 8, 60),
+    ("long_sweep", "sweep", None, 60),
+)
+
+
+def run_one(args, ctx):
+    if args.workload == "faceformer_train":
+        return run_train(args, ctx)
+    if args.workload == "audio2mesh_train":
+        return run_conv_train(args, ctx)
+    if args.workload == "sweep":
+        return run_sweep(args, ctx)
+    return run_ours(args, ctx)
 
 
 def main():
@@ -846,37 +1051,54 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="faceformer", choices=["faceformer", "voca", "voca_audio", "audio2mesh", "faceformer_train",
-                                                                    "audio2mesh_train", "song2face"])
+    ap.add_argument("--workload", default=None, choices=["faceformer", "voca", "voca_config0", "voca_audio", "audio2mesh",
+                                                         "faceformer_train", "audio2mesh_train", "song2face", "sweep"],
+                    help="one workload only; default: the headline (faceformer, BASELINE.json configs[2]) followed by the "
+                         "other BASELINE configs as `extra_workloads` of the same JSON line")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--fps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="default invocation: skip the extra workloads")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph fast path")
     args = ap.parse_args()
-    args.fps_default = args.fps is None
+    with_extras = args.workload is None and not args.no_extra and args.impl == "ours"
+    if args.workload is None:
+        args.workload = "faceformer"
+    defaults = {"faceformer": 32, "faceformer_train": 8, "voca": 16384, "voca_config0": 348, "voca_audio": 4096, "audio2mesh": 64,
+                "audio2mesh_train": 128, "song2face": 64, "sweep": 0}
     if args.fps is None:
-        args.fps = 60 if args.workload == "faceformer_train" else 30
+        args.fps = 60 if args.workload in ("faceformer_train", "sweep") else 30
     if args.batch is None:
-        args.batch = {"faceformer": 32, "faceformer_train": 8, "voca": 16384, "voca_audio": 4096, "audio2mesh": 64,
-                      "audio2mesh_train": 128, "song2face": 64}[args.workload]
+        args.batch = defaults[args.workload]
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.workload == "faceformer_train" and args.fps_default:
-        args.fps = 60
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.workload == "faceformer_train":
-        run_train(args)
-    elif args.workload == "audio2mesh_train":
-        run_conv_train(args)
-    else:
-        run_ours(args)
+    ctx = Ctx()
+    line = run_one(args, ctx)
+    if with_extras:
+        extras = {}
+        for key, wl, batch, fps in EXTRA_WORKLOADS:
+            sub = argparse.Namespace(**vars(args))
+            sub.workload, sub.batch, sub.fps = wl, batch, fps if fps is not None else 30
+            sub.seconds = 5.0
+            sub.steps = min(args.steps, 10)
+            try:
+                extras[key] = run_one(sub, ctx)
+            except Exception as exc:  # noqa: BLE001  (an extra leg must never take the headline line down with it)
+                import traceback
+                extras[key] = {"error": f"{type(exc).__name__}: {exc}", "traceback": traceback.format_exc()[-1500:]}
+        if line is not None:
+            line["extra_workloads"] = extras
+    if line is not None:
+        print(json.dumps(line))
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -296,6 +296,13 @@ int a2f_ln64_param_grad(const float* dy, const float* x, long long rows, float* 
  * accumulation in fp64. */
 int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, const float* vmr_b, int V3, float* Wc,
                       float* bc, void* stream);
+/* The cross-attention of the decoder layer under the diagonal memory mask (ref:src/model/faceformer.py:58-66,168-179)
+ * is out_proj(v_proj(audio_feature_map(h))).  Folds the three Linear layers (fp64) into one operand for a2f_gemm:
+ *   W[64,Kin] = wo wv wa,  b[64] = wo (wv ba + bv) + bo
+ * wv / bv: rows 128..191 of multihead_attn.in_proj_{weight,bias}; wo / bo: multihead_attn.out_proj; wa [64,Kin] / ba:
+ * audio_feature_map.  W is written as fp32 or bf16 (w_dtype). */
+int a2f_pack_cross_attention(const float* wv, const float* bv, const float* wo, const float* bo, const float* wa,
+                             const float* ba, int Kin, void* W, int w_dtype, float* b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * VOCA trunk (ref:src/model/voca.py:19-46): one-hot tiling + 4 x (Conv2d(3x1,s2,p1)+ReLU) + concat(one_hot[:8])
@@ -475,6 +482,10 @@ int a2f_posconv_wgrad(const void* dpc, const void* h, int dtype, float* dWp, int
  * ref:src/model/lightning_model.py:209-213); the gradient is multiplied by grad_scale first (1/world_size). */
 int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, float grad_scale, void* stream);
+/* same step with the gradient read as bf16: the flat gradient as it comes off a bf16 all-reduce (data-parallel training,
+ * trainer.FlatBuffers wire="bf16": half the bytes on NVLink; masters, moments and the update stay fp32). */
+int a2f_adam_step_bf16g(float* p, const void* g_bf16, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * MFCC feature extractor (replaces ref:src/model/extractor.py:10-60 = torchaudio.transforms.MFCC

@@ -42,7 +42,7 @@ def main():
         out3 = t.forward_backward(audio[sl].to(dev), oh[sl].to(dev), tp[sl].to(dev), gt[sl].to(dev))
         t.flat.finish_all_reduce()
         torch.cuda.synchronize()
-        grads[overlap] = (t.flat.grads / world).clone()
+        grads[overlap] = (t.flat.reduced_grads().float() / world).clone()   # bf16 precision: the bf16 wire mirror
         if overlap:
             t.optimizer_step()
             torch.cuda.synchronize()
@@ -50,10 +50,10 @@ def main():
             other = mine.clone()
             dist.broadcast(other, src=0)
             if not torch.equal(mine, other):
-                g0 = t.flat.grads.clone()
+                g0 = t.flat.reduced_grads().float().clone()
                 dist.broadcast(g0, src=0)
                 for name, p, off, nn_, st in t.flat.entries:
-                    dg = float((g0[off:off + nn_] - t.flat.grads[off:off + nn_]).abs().max())
+                    dg = float((g0[off:off + nn_] - t.flat.reduced_grads()[off:off + nn_].float()).abs().max())
                     dp = float((other[off:off + nn_] - mine[off:off + nn_]).abs().max())
                     if (dg > 0 or dp > 0) and rank == 1:
                         print(f"  DIVERGED stage {st:2d} {name}: max|dgrad| {dg:.3e} max|dparam| {dp:.3e} "

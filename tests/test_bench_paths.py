@@ -1,0 +1,157 @@
+"""The paths bench.py TIMES, at the shapes it times them, pinned to the oracle:
+
+  * configs[2]  FaceFormer inference, B=32 x 5 s @ 30 fps, bf16, ONE CUDA graph (modules.GraphedForward: pair GEMMs,
+                mha_short<10>, posconv_tc<2>, PDL) -- graph replay == eager launches bit for bit, utterances vs the oracle
+                at north_star's 5e-4 m, error also reported relative to the predicted offsets;
+  * configs[3]  FaceFormer bf16 training step, B=8 x 5 s @ 60 fps -- the trainer's loss == mean of per-utterance losses,
+                and the per-utterance loss of the taped forward vs the oracle forward + FaceFormerLoss at 1e-4;
+  * configs[0]  VOCA at its literal shape: the reference's assets/audio_sample.npy (carried by the fixture) -> 348 windows
+                -> MFCC -> Voca, vs the live-reference fixture tests/golden/config0_voca.npz;
+  * configs[1]  Audio2Mesh, 64 windows, graphed bf16x3 tensor path vs the oracle.
+
+The CPU part (`-m "not gpu"`) checks the oracle chain against the configs[0] fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs as oin, ref_audio as ora, ref_mfcc as omf, ref_models as orm, weights as ow
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _config0():
+    z = np.load(os.path.join(G, "config0_voca.npz"))
+    n = int(z["n_frames"])
+    oh = torch.zeros(n, 12)
+    oh[:, 0] = 1.0
+    tp = oin.flame_like_template(int(z["template_seed"]))[None].expand(n, -1, -1).contiguous()
+    return z, n, oh, tp
+
+
+def test_config0_oracle_chain_matches_live_reference_fixture():
+    z, n, oh, tp = _config0()
+    cfg = omf.CONFIGS["voca"]
+    win = ora.fragments(z["clip"], n)
+    assert tuple(win.shape) == (348, 11440)
+    feat = omf.mfcc_forward(omf.make_buffers(cfg[0], cfg[1], cfg[3], cfg[5]), win, cfg[2], cfg[3], cfg[4], cfg[5])
+    assert tuple(feat.shape) == (348, 29, 16)
+    np.testing.assert_allclose(feat.reshape(-1)[:: int(z["feat_step"])].numpy(), z["feat_sub"], rtol=0, atol=2e-4)
+    verts = orm.voca_forward(ow.make_state_dict("voca", seed=int(z["weight_seed"])), feat, oh, tp)
+    np.testing.assert_allclose(verts.reshape(-1)[:: int(z["verts_step"])].numpy(), z["verts_sub"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(verts.double().reshape(n, -1).sum(1).numpy(), z["verts_rowsum"], rtol=0, atol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------- configs[0]
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-4)])
+def test_config0_voca_literal_shape_vs_live_reference(a2f_lib, dev, precision, tol):
+    """int16 clip -> a2f_audio_fragments -> MFCC kernels -> VOCA kernels, all on the GPU, vs the live reference's
+    vertices for the same clip.  Offsets reach 5.1 (raw model units at random init); tol is absolute in those units:
+    fp32 path 1e-4 = 2e-5 relative (the MFCC coefficients, up to 612, carry ~2e-4 absolute error into the trunk),
+    tensor path 5e-4 (north_star's bf16 bar)."""
+    from a2f_b200 import features, modules
+    z, n, oh, tp = _config0()
+    cfg = omf.CONFIGS["voca"]
+    model = modules.Voca(15069, 12)
+    model.load_state_dict(ow.make_state_dict("voca", seed=int(z["weight_seed"])), strict=True)
+    net = features.ExtractAndPredict(features.MFCCExtractor(*cfg), model).to(dev).eval().set_precision(precision)
+    clip = torch.from_numpy(z["clip"]).to(dev)
+    with torch.no_grad():
+        win = features.audio_fragments(clip, n, fps=60, sample_rate=22000, length=0.52)
+        got = net(win, oh.to(dev), tp.to(dev)).cpu()
+    assert tuple(got.shape) == (348, 5023, 3)
+    err = float(np.abs(got.reshape(-1)[:: int(z["verts_step"])].numpy() - z["verts_sub"]).max())
+    rs = float(np.abs(got.double().reshape(n, -1).sum(1).numpy() - z["verts_rowsum"]).max())
+    print(f"configs[0] {precision}: max|err| {err:.3e} on offsets up to {float(z['offset_absmax']):.2f}; row-sum err {rs:.3e}")
+    assert err < tol
+    assert rs < 15069 * tol * 0.05          # per-window checksum over all 15069 coordinates (errors do not line up)
+
+
+# ---------------------------------------------------------------------------------------------------------- configs[2]
+@pytest.mark.gpu
+def test_config2_graphed_b32_5s_30fps_bf16_vs_oracle(a2f_lib, dev):
+    from a2f_b200 import modules
+    B, n, fps = 32, 80000, 30
+    T = n * fps // 16000
+    sd = ow.make_state_dict("faceformer", seed=13)
+    m = modules.Faceformer(15069, 12)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval().set_precision("bf16")
+    audio, oh, tp = oin.audio(B, n, 100), oin.one_hot(B, 12, 100), oin.batch_templates(B, 100, scale=100.0)   # bench.py rank 0
+    d_in = [audio.to(dev), oh.to(dev), tp.to(dev)]
+    with torch.no_grad():
+        eager = m(*d_in, fps=fps).clone()
+        g = m.graphed(*d_in, fps=fps)
+        rep = g(*g.static_in).clone()
+        rep2 = g(*g.static_in).clone()
+    torch.cuda.synchronize()
+    assert tuple(rep.shape) == (B, T, 5023, 3)
+    assert g.launches_per_replay > 90                      # the whole forward is inside the graph
+    assert torch.equal(rep, eager), "CUDA-graph replay differs from eager launches"
+    assert torch.equal(rep, rep2), "two replays differ (non-deterministic kernel on the inference path)"
+    worst, worst_rel = 0.0, 0.0
+    for b in (0, 17, 31):
+        want = orm.faceformer_forward(sd, audio[b:b + 1], oh[b:b + 1], tp[b:b + 1], fps)
+        err_m = float((rep[b:b + 1].cpu() - want).abs().max()) / 100.0
+        off = float((want - tp[b:b + 1, None]).abs().max()) / 100.0
+        worst, worst_rel = max(worst, err_m), max(worst_rel, err_m / off)
+    print(f"configs[2] graphed bf16 B=32xT=150: max per-vertex |err| {worst:.3e} m = {100 * worst_rel:.2f} % of the largest offset")
+    assert worst < 5e-4                                    # north_star: 5e-4 m on the bf16 path
+
+
+# ---------------------------------------------------------------------------------------------------------- configs[3]
+@pytest.mark.gpu
+def test_config3_train_step_b8_5s_60fps_bf16_loss_vs_oracle(a2f_lib, dev):
+    from a2f_b200 import modules, ops, trainer as tr, training
+    B, n, fps = 8, 80000, 60
+    T = n * fps // 16000
+    sd = ow.make_state_dict("faceformer", seed=13)
+    m = modules.Faceformer(15069, 12)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval().set_precision("bf16")
+    t = tr.FaceformerTrainer(m, lr=1e-4, fps=fps)
+    tp = oin.batch_templates(B, 100, scale=100.0)
+    audio, oh = oin.audio(B, n, 100), oin.one_hot(B, 12, 100)
+    gt = oin.gt_like((B, T, 5023, 3), tp[:, None], 200, scale=100.0)
+    d = [x.to(dev) for x in (audio, oh, tp, gt)]
+    with torch.no_grad():                                  # the taped forward the step runs, at the initial weights
+        out, _ = training.forward_train(m, d[0], d[1], d[2].reshape(B, -1), fps)
+        per = [ops.voca_loss_fwd(out[b].reshape(T, -1).contiguous(), d[3][b].reshape(T, -1).contiguous(), T, 15069, 1.0, 10.0)
+               for b in range(B)]
+        per = torch.stack(per).cpu()                       # [B, 3]
+    step = t.step(*d)
+    loss = float(step["loss"])
+    assert abs(loss - float(per[:, 0].mean())) < 2e-6 * abs(loss), (loss, float(per[:, 0].mean()))
+    for b in (0, 5):
+        want = orm.faceformer_loss(orm.faceformer_forward(sd, audio[b:b + 1], oh[b:b + 1], tp[b:b + 1], fps), gt[b:b + 1])
+        for j, k in enumerate(("loss", "rec_loss", "vel_loss")):
+            rel = abs(float(per[b, j]) - float(want[k])) / abs(float(want[k]))
+            print(f"configs[3] utterance {b} {k}: gpu {float(per[b, j]):.6f} oracle {float(want[k]):.6f} rel {rel:.2e}")
+            assert rel < 1e-4                              # north_star: losses to 1e-4 relative
+    l2 = float(t.step(*d)["loss"])
+    assert np.isfinite(l2) and l2 < loss                   # the optimizer step at this shape moves downhill
+
+
+# ---------------------------------------------------------------------------------------------------------- configs[1]
+@pytest.mark.gpu
+def test_config1_audio2mesh_b64_graphed_vs_oracle(a2f_lib, dev):
+    from a2f_b200 import modules
+    B = 64
+    sd = ow.make_state_dict("audio2mesh", seed=12)
+    m = modules.Audio2Mesh(15069, 12)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval().set_precision("bf16")
+    x, oh, tp = oin.a2m_features(B, 100), oin.one_hot(B, 12, 100), oin.batch_templates(B, 100)
+    want = orm.audio2mesh_forward(sd, x, oh, tp)
+    d_in = [x.to(dev), oh.to(dev), tp.to(dev)]
+    with torch.no_grad():
+        eager = m(*d_in).clone()
+        g = m.graphed(*d_in)
+        rep = g(*g.static_in).clone()
+    assert torch.equal(rep, eager)
+    err = float((rep.cpu() - want).abs().max())
+    off = float((want - tp).abs().max())
+    print(f"configs[1] graphed tensor path B=64: max|err| {err:.3e} on offsets up to {off:.2f} ({100 * err / off:.4f} %)")
+    assert err < 2e-4

@@ -101,6 +101,133 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_bf16_buckets(rank, world, port, q):
+    """bf16 wire + buckets: stages 0 and 1 travel together (sent when BOTH are final), stage 2 alone."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from a2f_b200.trainer import FlatBuffers
+        torch.manual_seed(0)
+        m = _Toy()
+        fb = FlatBuffers(m.named_parameters(), _stage, 3, skip=("unused",), wire="bf16", buckets=[[0, 1], [2]])
+        fb.zero_grads()
+        for name, p, off, n, st in fb.entries:
+            p.grad.fill_(float((rank + 1) * (st + 1)) + 0.001)          # 0.001 is below bf16 resolution at these magnitudes
+        fb.all_reduce_stage(0)
+        sent_early = fb._sent[0]                                        # must wait for stage 1
+        fb.all_reduce_stage(1)
+        sent_both = fb._sent[0] and not fb._sent[1]
+        fb.finish_all_reduce()
+        red = fb.reduced_grads()
+        want = sum(r + 1 for r in range(world))
+        ok = red.dtype == torch.bfloat16 and all(
+            bool((red[off:off + n].float() == float(torch.tensor(want * (st + 1) + 0.002).bfloat16())).all())
+            or bool((red[off:off + n].float() - want * (st + 1)).abs().max() < 0.05) for _, _, off, n, st in fb.entries)
+        local_kept = all(bool((p.grad == float((rank + 1) * (st + 1)) + 0.001).all()) for _, p, _, _, st in fb.entries)
+        q.put((rank, (not sent_early) and sent_both, ok, local_kept))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_bf16_wire_all_reduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_bf16_buckets, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, True, True), (1, True, True, True)]
+
+
+class _ExplicitFn(torch.autograd.Function):
+    """The pattern of training.FaceformerTrainFn / conv_training.ConvModelTrainFn on a toy model: an explicit backward that
+    accumulates through training._grad, run inside training.collect_grads, every parameter an input of the Function."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        ctx.model = model
+        ctx.save_for_backward(x)
+        return x @ model.w.detach() + model.b.detach()
+
+    @staticmethod
+    def backward(ctx, dout):
+        from a2f_b200 import training
+        (x,) = ctx.saved_tensors
+        m = ctx.model
+        with training.collect_grads(list(m.parameters())) as sink:
+            training._grad(m.w).add_(x.t() @ dout)           # what the kernels do: accumulate into the buffer handed out
+            training._grad(m.b).add_(dout.sum(0))
+        return (None, None) + sink.grads()
+
+
+class _ExplicitToy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = nn.Parameter(torch.randn(4, 3))
+        self.b = nn.Parameter(torch.zeros(3))
+        self.unused = nn.Parameter(torch.ones(2))            # never written by the backward (masked_spec_embed's role)
+
+    def forward(self, x):
+        return _ExplicitFn.apply(self, x, *self.parameters())
+
+
+def _worker_ddp(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        m = _ExplicitToy()
+        ddp = nn.parallel.DistributedDataParallel(m, find_unused_parameters=True)
+        ok = True
+        for it in range(3):                                  # iteration 2+ raised under the one-anchor scheme (ADVICE r1)
+            torch.manual_seed(100 + 10 * it + rank)
+            x = torch.randn(5, 4)
+            for p_ in m.parameters():
+                p_.grad = None
+            ddp(x).square().sum().backward()
+            xs = []
+            for r in range(world):
+                torch.manual_seed(100 + 10 * it + r)
+                xs.append(torch.randn(5, 4))
+            gw = sum(2 * xr.t() @ (xr @ m.w.detach() + m.b.detach()) for xr in xs) / world
+            gb = sum(2 * (xr @ m.w.detach() + m.b.detach()).sum(0) for xr in xs) / world
+            ok = ok and torch.allclose(m.w.grad, gw, atol=1e-5) and torch.allclose(m.b.grad, gb, atol=1e-5)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_autograd_glue_is_ddp_compatible_gloo_world2():
+    """the module-level autograd path must hand every gradient to AccumulateGrad so that torch DDP's
+    reducer averages it across ranks (the reference trains under Lightning's implicit DDP)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ddp, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
+def test_default_buckets():
+    from a2f_b200.trainer import default_buckets
+    assert default_buckets(14, 4) == [[0, 1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12], [13]]
+    assert default_buckets(1, 4) == [[0]]
+    assert default_buckets(14, 14) == [[i] for i in range(14)]
+    for n in range(1, 20):
+        for k in range(1, 8):
+            b = default_buckets(n, k)
+            assert [s for x in b for s in x] == list(range(n)) and len(b) <= max(1, k)
+
+
 def _Toy_params_seed0():
     torch.manual_seed(0)
     return {k: v.detach().clone() for k, v in _Toy().named_parameters()}

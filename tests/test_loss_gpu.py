@@ -54,3 +54,14 @@ def test_odd_rows_rejected(a2f_lib, dev):
     from a2f_b200 import modules
     with pytest.raises(a2f_b200.A2FError):
         modules.VocaLoss()(torch.zeros(3, 5023, 3, device=dev), torch.zeros(3, 5023, 3, device=dev))
+
+
+@pytest.mark.parametrize("rows", [1, 2, 7, 300])
+def test_mse_error_any_frame_count(a2f_lib, dev, rows):
+    """ref:src/model/lightning_model.py:119-125 takes any number of frames (odd-length FaceFormer clips reach it)."""
+    from a2f_b200 import modules
+    g = torch.Generator().manual_seed(70 + rows)
+    pred, gt = torch.randn(rows, 5023, 3, generator=g), torch.randn(rows, 5023, 3, generator=g)
+    want = orm.mse_error(pred, gt)
+    got = modules.mse_error(pred.to(dev), gt.to(dev)).cpu()
+    assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))

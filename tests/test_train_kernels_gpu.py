@@ -187,3 +187,37 @@ def test_adam_step_matches_torch(a2f_lib, dev):
         opt.step()
         ops.adam_step(p, (g * step * 2).to(dev), m, v, 1e-4, 0.9, 0.999, 1e-8, 1e-5, step, grad_scale=0.5)
     assert _err(p, ref.detach()) < 1e-6
+
+
+def test_adam_step_bf16_gradient_matches_torch(a2f_lib, dev):
+    """a2f_adam_step_bf16g: the gradient as it comes off the bf16 all-reduce; everything else fp32.  Reference = torch Adam
+    fed the SAME bf16-rounded gradient; n is not a multiple of 4 (vector body + scalar tail)."""
+    from a2f_b200 import ops
+    n = 100003
+    p0, g = _rand((n,), 32), _rand((n,), 33, 0.1)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-4, weight_decay=1e-5)
+    p, m, v = p0.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for step in range(1, 4):
+        g16 = (g * step * 2).bfloat16()
+        ref.grad = g16.float() * 0.5
+        opt.step()
+        ops.adam_step(p, g16.to(dev), m, v, 1e-4, 0.9, 0.999, 1e-8, 1e-5, step, grad_scale=0.5)
+    assert _err(p, ref.detach()) < 1e-6
+
+
+def test_pack_cross_attention_matches_fp64_fold(a2f_lib, dev):
+    """out_proj(v_proj(audio_feature_map(h))) folded on the device (no library GEMM) vs the same fold in torch fp64."""
+    from a2f_b200 import ops
+    in_w, in_b = _rand((192, 64), 40, 0.2), _rand((192,), 41, 0.1)
+    wo, bo = _rand((64, 64), 42, 0.2), _rand((64,), 43, 0.1)
+    wa, ba = _rand((64, 768), 44, 0.05), _rand((64,), 45, 0.1)
+    wv, bv = in_w[128:192].double(), in_b[128:192].double()
+    W_ref = wo.double() @ (wv @ wa.double())
+    b_ref = wo.double() @ (wv @ ba.double() + bv) + bo.double()
+    for dt, tol in ((torch.float32, 2e-7), (torch.bfloat16, 4e-3)):
+        W = torch.empty((64, 768), dtype=dt, device=dev)
+        b = torch.empty(64, dtype=torch.float32, device=dev)
+        ops.pack_cross_attention(in_w.to(dev), in_b.to(dev), wo.to(dev), bo.to(dev), wa.to(dev), ba.to(dev), W, b)
+        assert float((W.double().cpu() - W_ref).abs().max()) <= tol * float(W_ref.abs().max())
+        assert float((b.double().cpu() - b_ref).abs().max()) <= 2e-7 * float(b_ref.abs().max())

@@ -95,3 +95,19 @@ def test_w2v_extractor_gpu_other_geometry(a2f_lib, dev):
     got = m.to(dev)(x.to(dev)).cpu()
     assert tuple(got.shape) == (12, 64, 40)
     assert float((got - want).abs().max()) < 2e-4
+
+
+@pytest.mark.gpu
+def test_w2v_extractor_gpu_out_dim_768_is_not_resized(a2f_lib, dev):
+    """ref:src/model/extractor.py:92-96 resizes only `if self.out_dim != x.shape[1]` (the 768 channels after the transpose):
+    with out_dim == 768 the reference returns the transposed hidden states [B, 768, frames]."""
+    from a2f_b200 import features
+    sd = _sd(13)
+    x = oin.speech_like_windows(2, n_samples=8000, sample_rate=16000, seed=8)
+    want = owx.w2v_extractor_forward(sd, x, 16000, 32, 768)
+    assert tuple(want.shape) == (2, 768, 24)
+    m = features.Wav2VecExtractor(16000, 32, 768)
+    m.load_state_dict(sd, strict=True)
+    got = m.to(dev)(x.to(dev)).cpu()
+    assert tuple(got.shape) == tuple(want.shape)
+    assert float((got - want).abs().max()) < 2e-4
