@@ -291,6 +291,12 @@ A2F_D void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int 
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+A2F_D void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 A2F_D void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 A2F_D void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all but the most recent bulk store have finished READING their shared-memory source (double-buffered staging)

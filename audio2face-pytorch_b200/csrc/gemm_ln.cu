@@ -1,0 +1,457 @@
+// out = LayerNorm(A W^T + bias + resid) * gamma + beta in ONE kernel (tcgen05 / TMEM / TMA, bf16 in / out, fp32 accumulate).
+//
+// The wav2vec2 encoder layer is post-LN (HF modeling_wav2vec2.py:576-609, reached through ref:src/model/wav2vec.py:174-180):
+//     h = LN(h + out_proj(attn));  h = LN(h + W2 gelu(W1 h))
+// so two of its four GEMMs are followed by a LayerNorm over the full 768-wide row.  A 256-wide accumulator tile holds a
+// third of a row; the statistics of a row therefore live in THREE tiles.  This kernel runs those three tiles at the same
+// time in one thread-block CLUSTER of 3 CTA pairs (6 CTAs; pair p owns columns [256p, 256p+256) of a 256-row block and is
+// a cta_group::2 UMMA pair exactly like gemm_tc2_kernel) and exchanges the per-row (sum, sum of squares) through
+// distributed shared memory:
+//   pass 1  accumulator (TMEM) + bias + residual (TMA -> swizzled staging) -> fp32 sum written BACK into TMEM
+//           (tcgen05.st: TMEM is the row buffer, nothing is recomputed), per-thread partial (s1, s2) of its 128 columns
+//   exchange every epilogue thread stores its partial into the stats slot of the NP CTAs that hold the same rows
+//           (st.shared::cluster) and arrives (release.cluster) on their stats mbarrier; waits (acquire.cluster) on its own
+//   pass 2  TMEM -> (x - mean) * rstd * gamma + beta -> bf16 -> swizzled staging -> TMA store
+// The pre-LayerNorm sum never leaves the SM and is never rounded to bf16 (round 1 stored it in bf16 and re-read it in a
+// separate layernorm_kernel launch: 24 launches per forward, 6 % of the step, and the largest single contribution to the
+// bf16 path's error -- tools/bf16_noise_floor.py: 1.6 % -> 1.0 % of the largest vertex offset).
+// Mainloop, barriers and TMEM double buffering follow gemm_tc2_kernel (gemm_tc.cu); the ring is 4 stages deep here because
+// the stats slots and the LayerNorm parameters need 13 KB of shared memory.
+#include "a2f_common.cuh"
+#include "gemm_params.cuh"
+
+namespace a2f {
+
+namespace {
+
+constexpr int LBM = 128;            // rows per CTA (UMMA M = 256 over the pair)
+constexpr int LBN = 256;            // columns per pair tile
+constexpr int LBK = 64;             // K per stage (one 128-byte swizzle row of bf16)
+constexpr int L_THREADS = 320;      // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int L_STAGES = 4;
+constexpr int L_A_BYTES = LBM * LBK * 2;
+constexpr int L_B_BYTES = (LBN / 2) * LBK * 2;
+constexpr int L_STAGE_BYTES = L_A_BYTES + L_B_BYTES;
+constexpr int L_EPI_BYTES = 16384;  // one 128-row x 128-byte block (64 bf16 columns)
+constexpr int L_SBW = 64;           // columns per staging block
+
+struct LnMaps {
+    CUtensorMap a, b, c, r;
+};
+
+struct LnParams {
+    int M, N, K;
+    int tiles_m, num_k_blocks;
+    const float* bias;
+    const float* gamma;
+    const float* beta;
+    float eps;
+};
+
+template <int NP> struct LnCfg {
+    static constexpr int STATS_BYTES = 2 * (2 * NP) * LBM * 8;      // [parity][source pair x half][row] float2
+    static constexpr int PARAM_BYTES = 3 * LBN * 4;                 // bias | gamma | beta of this pair's 256 columns
+    static constexpr size_t SMEM_BYTES = (size_t)L_STAGES * L_STAGE_BYTES + 4 * L_EPI_BYTES + STATS_BYTES + PARAM_BYTES + 256;
+};
+
+A2F_D uint64_t ln_smem_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_128B: LBO 1 (ignored), SBO 64 (1024 B between 8-row groups), version 1, layout 2
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1u << 16) | ((uint64_t)64u << 32) | ((uint64_t)1u << 46) |
+           ((uint64_t)2u << 61);
+}
+A2F_D void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+A2F_D uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t d;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(saddr), "r"(rank));
+    return d;
+}
+A2F_D void st_cluster_f2(uint32_t daddr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(daddr), "f"(a), "f"(b) : "memory");
+}
+A2F_D void mbar_arrive_cluster_release(uint32_t daddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(daddr) : "memory");
+}
+A2F_D void mbar_wait_cluster_acquire(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (++spins > (1u << 26)) __trap();      // a protocol bug becomes a launch error, not a hung GPU
+    }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(L_THREADS, 1)
+gemm_ln_kernel(const __grid_constant__ LnMaps maps, const LnParams p) {
+    using Cfg = LnCfg<NP>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)L_STAGES * L_A_BYTES;
+    uint8_t* sEpi = smem + (size_t)L_STAGES * L_STAGE_BYTES;                     // [half][buffer] 16 KB each
+    float2* sStats = reinterpret_cast<float2*>(sEpi + 4 * L_EPI_BYTES);          // [2][2*NP][128]
+    float* sParam = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStats) + Cfg::STATS_BYTES);   // bias | gamma | beta
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sParam) + Cfg::PARAM_BYTES);
+    uint64_t* full_bar = bars;                        // [STAGES] leader only
+    uint64_t* empty_bar = bars + L_STAGES;            // [STAGES] both CTAs of the pair (multicast commit)
+    uint64_t* tfull_bar = bars + 2 * L_STAGES;        // [2]      both CTAs (multicast commit)
+    uint64_t* tempty_bar = tfull_bar + 2;             // [2]      leader only: 8 epilogue warps x 2 CTAs
+    uint64_t* rbar = tempty_bar + 2;                  // [2 halves][2 buffers] residual block landed
+    uint64_t* stat_bar = rbar + 4;                    // [2 parities] all partial sums of this CTA's rows landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();          // 0 .. 2*NP-1
+    const int pr = rank >> 1;                         // pair index in the cluster == column block of this pair
+    const int hr = rank & 1;                          // which 128 rows of the 256-row block
+    const bool is_leader = hr == 0;
+    const int cl = (int)cluster_id_x(), n_cl = (int)cluster_count_x();
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.a);
+        tma_prefetch_desc(&maps.b);
+        tma_prefetch_desc(&maps.c);
+        tma_prefetch_desc(&maps.r);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < L_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 16);
+            mbar_init(&stat_bar[i], NP * 256);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();                               // every CTA's barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
+
+    const int n0 = pr * LBN;                          // first column of this pair
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs of the pair) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mb = cl; mb < p.tiles_m; mb += n_cl) {
+                const int row0 = mb * 2 * LBM + hr * LBM;
+                const int wrow0 = n0 + hr * (LBN / 2);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * L_STAGE_BYTES);
+                    tma_load_2d_2sm(sA + (size_t)stage * L_A_BYTES, &maps.a, &full_bar[stage], kb * LBK, row0);
+                    tma_load_2d_2sm(sB + (size_t)stage * L_B_BYTES, &maps.b, &full_bar[stage], kb * LBK, wrow0);
+                    if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA of the pair) =====================
+        if (is_leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LBN >> 3) << 17) |
+                                   ((uint32_t)((2 * LBM) >> 4) << 24);
+            const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int mb = cl; mb < p.tiles_m; mb += n_cl) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * LBN);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = ln_smem_desc(smem_u32(sA + (size_t)stage * L_A_BYTES));
+                    const uint64_t bdesc = ln_smem_desc(smem_u32(sB + (size_t)stage * L_B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < LBK / 16; ++k)
+                        umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(&empty_bar[stage], pair_mask);
+                    if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tfull_bar[acc], pair_mask);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: 8 warps, thread = one row x one column half (2 blocks of 64 columns) ==========
+        const int ew = warp - 2;
+        const int q = warp & 3;                       // TMEM lane quarter
+        const int half = ew >> 2;                     // blocks {half, half + 2} of the tile's four 64-column blocks
+        const bool leader = ((ew & 3) == 0) && lane == 0;
+        const int bar_id = 1 + half;
+        uint8_t* stage_base = sEpi + half * 2 * L_EPI_BYTES;
+        const int r_tile = q * 32 + lane;
+        // bias | gamma | beta of this pair's 256 columns: loaded once (the pair keeps its column block for every tile)
+        {
+            const int c = ew * 32 + lane;             // 256 epilogue threads
+            sParam[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.f;
+            sParam[LBN + c] = __ldg(p.gamma + n0 + c);
+            sParam[2 * LBN + c] = __ldg(p.beta + n0 + c);
+        }
+        named_bar_sync(3, 256);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t it = 0;                              // tiles this CTA has processed
+        const float inv_n = 1.0f / (float)p.N;
+        for (int mb = cl; mb < p.tiles_m; mb += n_cl, ++it) {
+            const int row_base = mb * 2 * LBM + hr * LBM;
+            const uint32_t par = it & 1u, par_phase = (it >> 1) & 1u;
+            // residual blocks of this tile -> the two staging buffers of this half (while the mainloop runs); a buffer is
+            // free once the TMA store that last used it has finished reading it
+            if (leader) {
+                tma_store_wait_read1();
+                mbar_expect_tx(&rbar[half * 2 + 0], L_EPI_BYTES);
+                tma_load_2d(stage_base, &maps.r, &rbar[half * 2 + 0], n0 + half * L_SBW, row_base);
+                tma_store_wait_read();
+                mbar_expect_tx(&rbar[half * 2 + 1], L_EPI_BYTES);
+                tma_load_2d(stage_base + L_EPI_BYTES, &maps.r, &rbar[half * 2 + 1], n0 + (half + 2) * L_SBW, row_base);
+            }
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * LBN);
+
+            // ---- pass 1: x = acc + bias + resid -> TMEM, partial row statistics ----
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+                const int col0 = (half + 2 * j) * L_SBW;
+                const uint8_t* rowp = stage_base + j * L_EPI_BYTES + r_tile * 128;
+                float v[L_SBW];
+                tmem_ld_32x32(t_row + col0, v);
+                tmem_ld_32x32(t_row + col0 + 32, v + 32);
+                mbar_wait(&rbar[half * 2 + j], it & 1u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int ch = 0; ch < L_SBW / 8; ++ch) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16));
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                    const float4 b0 = *reinterpret_cast<const float4*>(sParam + col0 + ch * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(sParam + col0 + ch * 8 + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(h2[e]);
+                        const float x0 = v[ch * 8 + 2 * e] + bb[2 * e] + f.x;
+                        const float x1 = v[ch * 8 + 2 * e + 1] + bb[2 * e + 1] + f.y;
+                        v[ch * 8 + 2 * e] = x0;
+                        v[ch * 8 + 2 * e + 1] = x1;
+                        s1 += x0 + x1;
+                        s2 = fmaf(x0, x0, fmaf(x1, x1, s2));
+                    }
+                }
+                tmem_st_32x32(t_row + col0, v);
+                tmem_st_32x32(t_row + col0 + 32, v + 32);
+            }
+            // ---- exchange: my partial -> the stats slot of every CTA that holds these rows (same hr, all NP pairs) ----
+            {
+                const uint32_t slot = smem_u32(sStats + ((size_t)par * (2 * NP) + (size_t)(pr * 2 + half)) * LBM + r_tile);
+                const uint32_t sbar = smem_u32(&stat_bar[par]);
+#pragma unroll
+                for (int d = 0; d < NP; ++d) {
+                    const uint32_t dst_rank = (uint32_t)(2 * d + hr);
+                    st_cluster_f2(map_to_rank(slot, dst_rank), s1, s2);
+                    mbar_arrive_cluster_release(map_to_rank(sbar, dst_rank));
+                }
+            }
+            tmem_st_wait();
+            mbar_wait_cluster_acquire(&stat_bar[par], par_phase);
+            float S1 = 0.f, S2 = 0.f;
+            {
+                const float2* st = sStats + (size_t)par * (2 * NP) * LBM + r_tile;
+#pragma unroll
+                for (int d = 0; d < 2 * NP; ++d) {
+                    const float2 t = st[(size_t)d * LBM];
+                    S1 += t.x;
+                    S2 += t.y;
+                }
+            }
+            const float mean = S1 * inv_n;
+            const float var = fmaxf(fmaf(-mean, mean, S2 * inv_n), 0.f);
+            const float rstd = rsqrtf(var + p.eps);
+            const float nmr = -mean * rstd;
+
+            // ---- pass 2: normalise, affine, bf16, TMA store ----
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+                const int col0 = (half + 2 * j) * L_SBW;
+                uint8_t* stage_buf = stage_base + j * L_EPI_BYTES;
+                uint8_t* rowp = stage_buf + r_tile * 128;
+                float v[L_SBW];
+                tmem_ld_32x32(t_row + col0, v);
+                tmem_ld_32x32(t_row + col0 + 32, v + 32);
+                tmem_ld_wait();
+                if (j == 1) {
+                    // last read of this accumulator: hand it back to the MMA warp before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+                }
+#pragma unroll
+                for (int ch = 0; ch < L_SBW / 8; ++ch) {
+                    float y[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 4) {
+                        const float4 g = *reinterpret_cast<const float4*>(sParam + LBN + col0 + ch * 8 + e);
+                        const float4 b = *reinterpret_cast<const float4*>(sParam + 2 * LBN + col0 + ch * 8 + e);
+                        y[e + 0] = fmaf(fmaf(v[ch * 8 + e + 0], rstd, nmr), g.x, b.x);
+                        y[e + 1] = fmaf(fmaf(v[ch * 8 + e + 1], rstd, nmr), g.y, b.y);
+                        y[e + 2] = fmaf(fmaf(v[ch * 8 + e + 2], rstd, nmr), g.z, b.z);
+                        y[e + 3] = fmaf(fmaf(v[ch * 8 + e + 3], rstd, nmr), g.w, b.w);
+                    }
+                    uint4 u;
+                    u.x = pack_bf16x2(y[0], y[1]);
+                    u.y = pack_bf16x2(y[2], y[3]);
+                    u.z = pack_bf16x2(y[4], y[5]);
+                    u.w = pack_bf16x2(y[6], y[7]);
+                    *reinterpret_cast<uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16)) = u;
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (leader) {
+                    tma_store_2d(&maps.c, stage_buf, n0 + col0, row_base);
+                    tma_store_commit();
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (leader) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                               // nobody signals a CTA that has left; TMEM reads are complete
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<512>(tmem_base);
+    }
+}
+
+static int g_ln_max_clusters[5] = {0, 0, 0, 0, 0};
+
+template <int NP>
+int launch_gemm_ln(LnMaps& maps, const LnParams& p, cudaStream_t s) {
+    using Cfg = LnCfg<NP>;
+    auto kern = gemm_ln_kernel<NP>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(L_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * NP;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    if (g_ln_max_clusters[NP] == 0) {
+        // clusters of 2*NP CTAs that can be resident at once (one CTA per SM, GPC boundaries): the persistent tile loop is
+        // sized to that, so that no cluster waits for another one to retire
+        cfg.gridDim = dim3(2 * NP * (sm_count() / (2 * NP)), 1, 1);
+        cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = sm_count() / (2 * NP) - (NP > 1 ? 1 : 0);
+            if (n < 1) n = 1;
+        }
+        g_ln_max_clusters[NP] = n;
+    }
+    const int n_clusters = p.tiles_m < g_ln_max_clusters[NP] ? p.tiles_m : g_ln_max_clusters[NP];
+    cfg.gridDim = dim3(2 * NP * n_clusters, 1, 1);
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
+    count_launch();
+    return A2F_OK;
+}
+
+}  // namespace
+
+// A [M,K] bf16 (row stride lda), W [N,K] bf16 (row stride ldw), resid / out [M,N] bf16; N = 256 * NP, NP in {1,2,3}.
+int gemm_ln_tc(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* resid, long long ldr,
+               const float* gamma, const float* beta, float eps, void* out, long long ldo, int M, int N, int K, cudaStream_t s) {
+    if (M <= 0) return A2F_OK;
+    A2F_REQUIRE(N % LBN == 0 && N / LBN >= 1 && N / LBN <= 3, "a2f_gemm_ln: N must be 256, 512 or 768");
+    A2F_REQUIRE(K > 0 && K % 8 == 0, "a2f_gemm_ln: K must be a positive multiple of 8");
+    A2F_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldr % 8 == 0 && ldo % 8 == 0, "a2f_gemm_ln: row strides must be multiples of 8 elements");
+    A2F_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(resid) |
+                  reinterpret_cast<uintptr_t>(out)) & 15) == 0, "a2f_gemm_ln: operands must be 16-byte aligned");
+    LnMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)lda * 2};
+        uint32_t box[2] = {LBK, LBM};
+        int rc = encode_tmap_bf16(&maps.a, A, 2, dims, str, box, 1);
+        if (rc != A2F_OK) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)ldw * 2};
+        uint32_t box[2] = {LBK, LBN / 2};
+        int rc = encode_tmap_bf16(&maps.b, W, 2, dims, str, box, 1);
+        if (rc != A2F_OK) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)ldo * 2};
+        uint32_t box[2] = {L_SBW, LBM};
+        int rc = encode_tmap_bf16(&maps.c, out, 2, dims, str, box, 1);
+        if (rc != A2F_OK) return rc;
+        uint64_t rstr[1] = {(uint64_t)ldr * 2};
+        rc = encode_tmap_bf16(&maps.r, resid, 2, dims, rstr, box, 1);
+        if (rc != A2F_OK) return rc;
+    }
+    LnParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.tiles_m = (M + 2 * LBM - 1) / (2 * LBM);
+    p.num_k_blocks = (K + LBK - 1) / LBK;
+    p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
+    switch (N / LBN) {
+        case 1: return launch_gemm_ln<1>(maps, p, s);
+        case 2: return launch_gemm_ln<2>(maps, p, s);
+        default: return launch_gemm_ln<3>(maps, p, s);
+    }
+}
+
+}  // namespace a2f
+
+extern "C" int a2f_gemm_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* resid,
+                           long long ldr, const float* gamma, const float* beta, float eps, void* out, long long ldo, int M,
+                           int N, int K, void* stream) {
+    int rc = a2f::require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(A && W && resid && gamma && beta && out, "a2f_gemm_ln: A, W, resid, gamma, beta and out must be non-NULL");
+    A2F_REQUIRE(M >= 0 && N > 0 && K > 0, "a2f_gemm_ln: bad M/N/K");
+    return a2f::gemm_ln_tc(A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, out, ldo, M, N, K, a2f::as_stream(stream));
+}

@@ -565,6 +565,9 @@ class Faceformer(_A2FModule):
         # reference's host-side numpy draws (spec_augment.py).  None = follow self.training like the reference does;
         # True / False force it.
         self.spec_augment = None
+        # bf16 inference: run the encoder's 24 post-LayerNorms inside the GEMM epilogues (a2f_gemm_ln); False = the separate
+        # layernorm_kernel launches (A/B switch for profiles/)
+        self.fuse_layernorm = True
         self.dataset = "vocaset"
         self.period = 60
         self.fps = 60
@@ -723,9 +726,20 @@ class Faceformer(_A2FModule):
         att = torch.empty((M, 768), dtype=dt, device=dev)
         pre32 = torch.empty((M, 768), dtype=dt, device=dev)     # pre-LayerNorm sums (bf16 on the tensor-core path)
         ffn = torch.empty((M, 3072), dtype=dt, device=dev)
+        fuse = bf and self.fuse_layernorm
+        h1 = torch.empty((M, 768), dtype=dt, device=dev) if fuse else None
         for blk, W in zip(ae.encoder.layers, P["layers"]):
             ops.gemm(h, W["qkv_w"], qkv, bias=W["qkv_b"], backend=be)
             ops.mha(qkv, att, B, T)
+            if fuse:
+                # both post-LayerNorms run in the epilogue of the GEMM in front of them (a2f_gemm_ln: cluster of three CTA
+                # pairs per 256-row block, row statistics over DSMEM, pre-LN sum kept fp32 in tensor memory)
+                ops.gemm_ln(att, W["o_w"], blk.attention.out_proj.bias.detach(), h, blk.layer_norm.weight.detach(),
+                            blk.layer_norm.bias.detach(), h1)
+                ops.gemm(h1, W["f1_w"], ffn, bias=blk.feed_forward.intermediate_dense.bias.detach(), act=L.ACT_GELU, backend=be)
+                ops.gemm_ln(ffn, W["f2_w"], blk.feed_forward.output_dense.bias.detach(), h1, blk.final_layer_norm.weight.detach(),
+                            blk.final_layer_norm.bias.detach(), h)
+                continue
             ops.gemm(att, W["o_w"], pre32, bias=blk.attention.out_proj.bias.detach(), resid=h, backend=be)
             ops.layernorm(pre32, blk.layer_norm.weight.detach(), blk.layer_norm.bias.detach(), h)
             ops.gemm(h, W["f1_w"], ffn, bias=blk.feed_forward.intermediate_dense.bias.detach(), act=L.ACT_GELU, backend=be)

@@ -103,6 +103,31 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     return out
 
 
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: torch.Tensor, gamma: torch.Tensor,
+            beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """out = LayerNorm(a @ w^T + bias + resid) * gamma + beta in one tcgen05 kernel (a2f_gemm_ln): bf16 [M,K] x [N,K],
+    N in {256, 512, 768}; the pre-LayerNorm sum stays in tensor memory (fp32)."""
+    _dev(a, w, bias, resid, gamma, beta, out)
+    for t in (a, w, resid, out):
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise L.A2FError("gemm_ln takes 2-D bf16 operands with unit column stride")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or tuple(resid.shape) != (M, N) or tuple(out.shape) != (M, N):
+        raise L.A2FError("gemm_ln: shape mismatch")
+    lib = L.load()
+    if PROFILE is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+    L.check(lib.a2f_gemm_ln(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.ptr(bias), resid.data_ptr(), resid.stride(0),
+                            gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(), out.stride(0), M, N, K, _stream()),
+            "a2f_gemm_ln")
+    if PROFILE is not None:
+        e.record()
+        PROFILE.append(("gemm_tc", 2.0 * M * N * K, s, e))
+    return out
+
+
 def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, *, backend: int, M: Optional[int] = None,
                N: Optional[int] = None, K: Optional[int] = None, dy_row_stride: Optional[int] = None,
                dy_batch_stride: int = 0, x_row_stride: Optional[int] = None, x_batch_stride: int = 0,

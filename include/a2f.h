@@ -128,7 +128,18 @@ typedef struct a2f_wgrad_args {
     int x_col_off[4];
     float* dW;
     long long ldw;
-    int x_row_step;     /* != 0: segment s reads rows r + x_row_off[0] + s*x_row_step, columns x_col_off[0].. (the 128
+    int x_row_step;     /* GEMM with the post-LayerNorm of the wav2vec2 encoder layer fused into its epilogue (tcgen05 back end, bf16):
+ *   out[m,:] = LayerNorm(A[m,:] W^T + bias + resid[m,:]) * gamma + beta          (eps inside the square root)
+ * = `h = layer_norm(h + out_proj(attn))` and `h = final_layer_norm(h + output_dense(ffn))` of HF
+ * modeling_wav2vec2.py:576-609, which ref:src/model/wav2vec.py:174-180 runs 12 times per forward.  One thread-block
+ * cluster of N/256 CTA pairs holds a whole 256-row block; row statistics travel through distributed shared memory and
+ * the pre-LayerNorm sum stays in tensor memory (fp32, never rounded).  A [M,K], W [N,K], resid / out [M,N] bf16 with row
+ * strides lda / ldw / ldr / ldo (elements, multiples of 8); N in {256, 512, 768}; bias may be NULL. */
+int a2f_gemm_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* resid,
+                long long ldr, const float* gamma, const float* beta, float eps, void* out, long long ldo, int M, int N,
+                int K, void* stream);
+
+/* != 0: segment s reads rows r + x_row_off[0] + s*x_row_step, columns x_col_off[0].. (the 128
                            taps of the positional conv); the table entries 1..3 are ignored */
 } a2f_wgrad_args;
 int a2f_gemm_wgrad(const a2f_wgrad_args* args, int backend, void* stream);

@@ -195,3 +195,30 @@ def test_tcgen05_wide_scalar_epilogue(a2f_lib, dev, M, N, K, rpt, use_bias):
     err = float((out[:M].cpu().double() - want).abs().max())
     assert err < 2e-4, err
     assert bool((out[M] == 7.0).all()), "the epilogue wrote past the last row"
+
+
+@pytest.mark.parametrize("M,N,K", [(4800, 768, 768), (4800, 768, 3072), (300, 768, 768), (1, 768, 128), (1000, 512, 256),
+                                   (129, 256, 64), (40000, 768, 192)])
+def test_gemm_ln_fused_epilogue(a2f_lib, dev, M, N, K):
+    """a2f_gemm_ln: LayerNorm(A W^T + bias + resid) in the GEMM epilogue (cluster of N/256 CTA pairs, row statistics over
+    distributed shared memory) vs torch fp32 on the same bf16 operands.  Shapes: the two encoder GEMMs at the bench batch,
+    a ragged last row block, a single row, 2- and 1-pair clusters, and more row blocks than resident clusters (persistent
+    loop, parity double-buffering of the stats slots)."""
+    from a2f_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).bfloat16()
+    bias = 0.1 * torch.randn(N, generator=g)
+    resid = torch.randn(M, N, generator=g).bfloat16()
+    gamma, beta = torch.rand(N, generator=g) + 0.5, 0.1 * torch.randn(N, generator=g)
+    want = torch.nn.functional.layer_norm(a.float() @ w.float().t() + bias + resid.float(), (N,), gamma, beta, 1e-5)
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    ops.gemm_ln(a.to(dev), w.to(dev), bias.to(dev), resid.to(dev), gamma.to(dev), beta.to(dev), out)
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - want).abs()
+    tol = 2.0 ** -8 * (want.abs() + 1.0)          # bf16 rounding of the output (2^-9 relative) + fp32 reduction-order noise
+    assert bool((err <= tol).all()), (float(err.max()), int((err > tol).sum()))
+    # run to run deterministic (no atomics on the path)
+    out2 = torch.empty_like(out)
+    ops.gemm_ln(a.to(dev), w.to(dev), bias.to(dev), resid.to(dev), gamma.to(dev), beta.to(dev), out2)
+    assert torch.equal(out, out2)
