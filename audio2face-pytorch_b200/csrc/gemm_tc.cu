@@ -31,6 +31,7 @@ constexpr int EPI_STAGE_BYTES = 16384;   // one 128-row x 128-byte store block (
 struct TmapSet {
     CUtensorMap a[MAX_SEGS];
     CUtensorMap b;
+    CUtensorMap bs;                 // pair kernel: B map of the split tail tiles (box rows = BN / 2 / tail_split)
     CUtensorMap c;
     CUtensorMap r;                  // residual / saved pre-activation (pair kernel, bf16, 16-byte aligned rows)
 };
@@ -43,6 +44,10 @@ struct TcParams {
     int bias_vec_ok;                // 16-byte vector bias loads are legal
     int fast_gelu;                  // bf16 output: A-S erf approximation instead of erff
     int resid_tma;                  // pair kernel: the residual tile arrives by TMA in the store-staging layout
+    // pair kernel, wave quantisation: the first `full_tiles` tiles run at full width; every later tile is cut into
+    // `tail_split` column slices (256 / tail_split wide) that are scheduled as tiles of their own, so the last, partly
+    // filled wave costs 1 / tail_split of a tile time (FFN1 at M=4800: 228 tiles on 74 pairs = 3.08 waves -> 3.25)
+    int full_tiles, tail_split;
     uint32_t lbo_enc, sbo_enc, desc_version, desc_layout;
     unsigned long long* timeline;   // debug (a2f_debug_set_timeline): 8 globaltimer stamps per CTA, else NULL
 };
@@ -663,6 +668,24 @@ template <int BN, typename TC> struct Tc2Cfg {
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + N_EPI_BUF * EPI_STAGE_BYTES + BIAS_BYTES + 256;
 };
 
+// virtual tile `t` of the pair kernel -> (m block, first column, width); see TcParams::tail_split
+struct PairTile { int mb, n_off, n_cols; bool split; };
+A2F_D PairTile pair_tile(int t, const TcParams& p, int BN) {
+    PairTile r;
+    int tile = t, sub = 0;
+    r.split = t >= p.full_tiles;
+    r.n_cols = BN;
+    if (r.split) {
+        const int u = t - p.full_tiles;
+        tile = p.full_tiles + u / p.tail_split;
+        sub = u - (u / p.tail_split) * p.tail_split;
+        r.n_cols = BN / p.tail_split;
+    }
+    r.mb = tile / p.tiles_n;
+    r.n_off = (tile - r.mb * p.tiles_n) * BN + sub * r.n_cols;
+    return r;
+}
+
 template <int BN, typename TC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
@@ -718,21 +741,25 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     if (threadIdx.x == 0) TL_STAMP(1);
 
     const int tiles_m = p.tiles_m_per_batch * p.num_batches;     // pair tiles (256 rows)
-    const int total_tiles = tiles_m * p.tiles_n;
+    const int total_tiles = p.full_tiles + (tiles_m * p.tiles_n - p.full_tiles) * p.tail_split;   // virtual tiles
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
+            if (p.tail_split > 1) tma_prefetch_desc(&maps.bs);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-                const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
+                const PairTile pt = pair_tile(tile, p, BN);
+                const int mb = pt.mb;
                 const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
                 const int row0 = lt * PBM + rank * TBM;           // this CTA's 128 A rows
-                const int wrow0 = nb * BN + rank * (BN / 2);      // this CTA's half of the B tile
+                const int wrow0 = pt.n_off + rank * (pt.n_cols / 2);      // this CTA's half of the B tile
+                const CUtensorMap* bmap = pt.split ? &maps.bs : &maps.b;
+                const uint32_t tx = 2u * (uint32_t)(A_STAGE_BYTES + (pt.n_cols / 2) * TBK * 2);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    if (is_leader) mbar_expect_tx(&full_bar[stage], tx);
                     uint8_t* dstA = sA + (size_t)stage * A_STAGE_BYTES;
                     uint8_t* dstB = sB + (size_t)stage * Cfg::B_HALF_BYTES;
                     const int seg = kb / p.kb_per_seg, kin = (kb - seg * p.kb_per_seg) * TBK;
@@ -741,7 +768,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                                         row0 + p.g.seg_row_off[seg], b);
                     else
                         tma_load_3d_2sm(dstA, &maps.a[seg], &full_bar[stage], kin, row0, b);
-                    tma_load_2d_2sm(dstB, &maps.b, &full_bar[stage], kb * TBK, wrow0);
+                    tma_load_2d_2sm(dstB, bmap, &full_bar[stage], kb * TBK, wrow0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -750,14 +777,17 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (is_leader && lane == 0) {
-            // D=f32, A=B=bf16, K-major, N=BN, M=256 (128 rows per CTA)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)(PBM >> 4) << 24);
+            // D=f32, A=B=bf16, K-major, N = tile width (BN, or BN / tail_split for a tail slice), M=256 (128 rows per CTA)
+            const uint32_t idesc_full = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                        ((uint32_t)(PBM >> 4) << 24);
+            const uint32_t idesc_tail = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((BN / p.tail_split) >> 3) << 17) |
+                                        ((uint32_t)(PBM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+                const uint32_t idesc = tile >= p.full_tiles ? idesc_tail : idesc_full;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
@@ -806,10 +836,11 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         constexpr int SBW = Cfg::SBW;
         constexpr int EPC = 16 / (int)sizeof(TC);
         for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-            const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
+            const PairTile pt = pair_tile(tile, p, BN);
+            const int mb = pt.mb;
             const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
-            const int n_tile0 = nb * BN;
-            const int n_lim = min(BN, g.N - n_tile0);
+            const int n_tile0 = pt.n_off;
+            const int n_lim = min(pt.n_cols, g.N - n_tile0);
             const int n_end = n_tile0 + n_lim;
             const int row_base = lt * PBM + rank * TBM;
 
@@ -948,6 +979,8 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     }
 }
 
+static int g_tail_split = 1;   // debug (a2f_debug_set_umma_field 11): 0 = never split the tail tiles of the pair kernel
+
 template <int BN, typename TC>
 static int launch_tc2(TmapSet& maps, const TcParams& p_in, cudaStream_t s) {
     using Cfg = Tc2Cfg<BN, TC>;
@@ -976,7 +1009,31 @@ static int launch_tc2(TmapSet& maps, const TcParams& p_in, cudaStream_t s) {
     }
     const int total = p.tiles_m_per_batch * p.num_batches * p.tiles_n;
     const int max_pairs = sm_count() / 2;
-    const int pairs = total < max_pairs ? total : max_pairs;
+    // wave quantisation: when the last wave is only partly filled, its tiles are cut into 2 or 4 column slices
+    p.full_tiles = total;
+    p.tail_split = 1;
+    if (g_tail_split && total > max_pairs && g.N % BN == 0) {
+        const int left = total % max_pairs;
+        if (left != 0) {
+            int best = 1;
+            double best_cost = 1.0;
+            for (int sp = 2; sp <= 4; sp *= 2) {
+                const double cost = (double)((left * sp + max_pairs - 1) / max_pairs) / sp;
+                if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+            }
+            if (best > 1) {
+                p.full_tiles = total - left;
+                p.tail_split = best;
+                uint64_t bdims[2] = {(uint64_t)g.K, (uint64_t)g.N};
+                uint64_t bstr[1] = {(uint64_t)g.ldw * 2};
+                uint32_t bbox[2] = {TBK, (uint32_t)(BN / 2 / best)};
+                rc = encode_tmap_bf16(&maps.bs, g.W, 2, bdims, bstr, bbox, 1);
+                if (rc != A2F_OK) return rc;
+            }
+        }
+    }
+    const int vtotal = p.full_tiles + (total - p.full_tiles) * p.tail_split;
+    const int pairs = vtotal < max_pairs ? vtotal : max_pairs;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs, 1, 1);
@@ -1049,6 +1106,8 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
     p.desc_layout = g_umma_fields[3];
     p.fast_gelu = c_bf16 ? 1 : 0;
     p.resid_tma = 0;
+    p.full_tiles = 0;
+    p.tail_split = 1;
     p.timeline = g_timeline;
     TmapSet maps;
     memset(&maps, 0, sizeof(maps));
@@ -1212,6 +1271,10 @@ extern "C" int a2f_debug_set_umma_field(int field, unsigned value) {
     }
     if (field == 10) {  // posconv_tc.cu: exchange the LBO / SBO descriptor fields (bring-up experiment)
         a2f::set_posconv_swap(value ? 1 : 0);
+        return A2F_OK;
+    }
+    if (field == 11) {  // pair kernel: 0 = never cut the tiles of a partly filled last wave into column slices
+        a2f::g_tail_split = value ? 1 : 0;
         return A2F_OK;
     }
     if (field == 4) {   // force tile width (0 = automatic)

@@ -356,7 +356,23 @@ class Ctx:
             dist.init_process_group("nccl", device_id=self.dev)
         self.lib = L.load()
         L.check(self.lib.a2f_device_check(), "a2f_device_check")
+        self.cpu_binding = self._bind_local_cpus()
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+
+    def _bind_local_cpus(self) -> str:
+        """Bind this rank to the CPUs NVML reports as local to its GPU BEFORE any pinned staging buffer is allocated
+        (first touch places the pages on that NUMA node; tools/d2h_ceiling.py measures what the box then gives)."""
+        if self.world == 1:
+            return "unchanged (one rank: every core stays available to the cpu_baseline leg)"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            before = len(os.sched_getaffinity(0))
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.local))
+            cpus = sorted(os.sched_getaffinity(0))
+            return f"{before} -> {len(cpus)} cpus ({cpus[0]}..{cpus[-1]})"
+        except Exception as exc:  # noqa: BLE001
+            return f"unchanged ({type(exc).__name__})"
 
     def barrier(self):
         import torch
@@ -673,7 +689,8 @@ def run_ours(args, ctx):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "pinned host buffers in and out through the drop-in module; D2H of step i overlaps step i+1"},
+                "note": "pinned host buffers in and out through the drop-in module; D2H of step i overlaps step i+1",
+                "cpu_binding": ctx.cpu_binding},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -739,7 +756,7 @@ def run_train(args, ctx):
     model = modules.Faceformer(15069, 12)
     model.load_state_dict(ow.make_state_dict("faceformer", 13), strict=True)
     model = model.to(dev).eval().set_precision("bf16")
-    trainer = tr.FaceformerTrainer(model, lr=1e-4, fps=args.fps)
+    trainer = tr.FaceformerTrainer(model, lr=1e-4, fps=args.fps, wire=args.wire, n_buckets=args.buckets)
     tp = oin.batch_templates(B, 100 + rank, scale=100.0)
     h_in = [oin.audio(B, n, 100 + rank).pin_memory(), oin.one_hot(B, 12, 100 + rank).pin_memory(), tp.pin_memory(),
             oin.gt_like((B, T, 5023, 3), tp[:, None], 200 + rank, scale=100.0).pin_memory()]
@@ -1064,6 +1081,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="default invocation: skip the extra workloads")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph fast path")
+    ap.add_argument("--wire", default=None, choices=["fp32", "bf16"], help="faceformer_train: gradient all-reduce wire format "
+                                                                             "(default: bf16 for the bf16 step)")
+    ap.add_argument("--buckets", type=int, default=4, help="faceformer_train: all-reduce buckets per step (14 = one per stage)")
     args = ap.parse_args()
     with_extras = args.workload is None and not args.no_extra and args.impl == "ours"
     if args.workload is None:

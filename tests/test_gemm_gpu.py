@@ -222,3 +222,29 @@ def test_gemm_ln_fused_epilogue(a2f_lib, dev, M, N, K):
     out2 = torch.empty_like(out)
     ops.gemm_ln(a.to(dev), w.to(dev), bias.to(dev), resid.to(dev), gamma.to(dev), beta.to(dev), out2)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("M,N,K,act,use_resid", [(4800, 3072, 768, 2, False), (4800, 2304, 768, 0, False), (9600, 768, 256, 0, True),
+                                                  (2400, 3072, 128, 0, False), (40000, 512, 192, 2, False)])
+def test_tcgen05_pair_kernel_tail_split(a2f_lib, dev, M, N, K, act, use_resid):
+    """Wave quantisation of the CTA-pair kernel: tiles of a partly filled last wave are cut into 2 or 4 column slices
+    (FFN1: 228 tiles on 74 pairs, QKV: 171).  The sliced schedule must give the SAME bits as the unsliced one (same MMA
+    order per output element) and match the fp64 reference."""
+    from a2f_b200 import ops, lib as L
+    a = _rand((M, K), dev, 31, torch.bfloat16)
+    w = _rand((N, K), dev, 32, torch.bfloat16, scale=K ** -0.5)
+    b = _rand((N,), dev, 33)
+    r = _rand((M, N), dev, 34, torch.bfloat16) if use_resid else None
+    outs = []
+    for split in (1, 0):
+        out = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+        try:
+            L.check(a2f_lib.a2f_debug_set_umma_field(11, split))
+            ops.gemm(a, w, out, bias=b, act=act, resid=r, backend=L.TCGEN05)
+            torch.cuda.synchronize()
+        finally:
+            a2f_lib.a2f_debug_set_umma_field(11, 1)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    want = _ref(a, w, b, act, r)
+    assert bool(((outs[0].cpu().double() - want).abs() <= 2.0 ** -8 * (want.abs() + 1.0)).all())
