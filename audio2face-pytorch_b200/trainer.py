@@ -34,10 +34,12 @@ def _world() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
-def default_buckets(n_stages: int, n_buckets: int = 4) -> List[List[int]]:
+def default_buckets(n_stages: int, n_buckets: int = 7) -> List[List[int]]:
     """Group the backward's stages (0 = finished first) into at most n_buckets all-reduce buckets of consecutive stages.
     The LAST stage (the front end, final only when the backward ends) always travels alone so that nothing else waits
-    for it; the others are split evenly: [[0..4], [5..8], [9..12], [13]] for FaceFormer's 14 stages."""
+    for it; the others are split evenly: [[0,1,2], [3,4], [5,6], [7,8], [9,10], [11,12], [13]] for FaceFormer's 14 stages
+    with the default of 7 -- measured best at 8 GPUs (profiles/r2_train_scaling_8gpu.txt: 7 buckets 13.07 ms, 14 buckets
+    13.27 ms, 4 buckets 15.20 ms: a bucket of four encoder layers starts too late to hide under the backward)."""
     if n_stages <= 1 or n_buckets <= 1:
         return [list(range(n_stages))]
     n_buckets = min(n_buckets, n_stages)
@@ -185,7 +187,7 @@ class FaceformerTrainer:
     FaceFormerLoss; across ranks the gradient is the average of the per-rank gradients (DDP semantics)."""
 
     def __init__(self, model, lr: float = 1e-4, weight_decay: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8,
-                 fps: int = 60, overlap: bool = True, group=None, wire: Optional[str] = None, n_buckets: int = 4):
+                 fps: int = 60, overlap: bool = True, group=None, wire: Optional[str] = None, n_buckets: int = 7):
         from . import training
         if not next(model.parameters()).is_cuda:
             raise L.A2FError("FaceformerTrainer runs on CUDA (sm_100a) only; there is no CPU fallback")

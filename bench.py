@@ -1083,7 +1083,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph fast path")
     ap.add_argument("--wire", default=None, choices=["fp32", "bf16"], help="faceformer_train: gradient all-reduce wire format "
                                                                              "(default: bf16 for the bf16 step)")
-    ap.add_argument("--buckets", type=int, default=4, help="faceformer_train: all-reduce buckets per step (14 = one per stage)")
+    ap.add_argument("--buckets", type=int, default=7, help="faceformer_train: all-reduce buckets per step (14 = one per stage)")
     args = ap.parse_args()
     with_extras = args.workload is None and not args.no_extra and args.impl == "ours"
     if args.workload is None:
