@@ -130,6 +130,10 @@ static int fill_params(const a2f_gemm_args* a, GemmParams* p) {
     p->resid_mode = a->resid_mode;
     A2F_REQUIRE(a->resid_mode == A2F_RESID_ADD || (a->resid_mode == A2F_RESID_DACT && a->resid != nullptr),
                 "a2f_gemm: bad resid_mode");
+    p->C2 = a->C2;
+    p->ldc2 = a->ldc2;
+    A2F_REQUIRE(a->C2 == nullptr || (a->resid == nullptr && a->tmpl == nullptr && a->ldc2 > 0 && a->act != A2F_ACT_NONE),
+                "a2f_gemm: C2 (pre-activation + activation outputs) needs an activation and excludes resid / tmpl");
     return A2F_OK;
 }
 
@@ -146,6 +150,7 @@ int a2f_gemm(const a2f_gemm_args* args, int backend, void* stream) {
     rc = fill_params(args, &p);
     if (rc != A2F_OK) return rc;
     if (backend == A2F_BACKEND_SIMT_F32) {
+        A2F_REQUIRE(p.C2 == nullptr, "a2f_gemm: C2 is a tcgen05 back-end feature");
         return gemm_simt(p, args->a_dtype == A2F_BF16, args->c_dtype == A2F_BF16, as_stream(stream));
     } else if (backend == A2F_BACKEND_TCGEN05) {
         A2F_REQUIRE(args->a_dtype == A2F_BF16, "a2f_gemm: the tcgen05 backend takes bf16 operands");

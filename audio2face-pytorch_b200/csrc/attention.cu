@@ -292,24 +292,27 @@ __global__ void __launch_bounds__(128) mha_bf16_kernel(const bf16* __restrict__ 
 // softmax overlap the V load.
 constexpr int FS_NW = 5;                 // warps per CTA
 constexpr int FS_BM = 16 * FS_NW;        // queries per CTA
-template <int NKT> struct FsCfg {
+// NQB = query blocks of 80 rows a CTA walks through: with T > 80 one CTA takes ALL queries of its (b, h) (NQB = 2), so K and
+// V are loaded once per (b, h) instead of once per 80 queries, and the grid of the bench shape (32 x 12 = 384 CTAs, three
+// resident per SM) is a single wave instead of 768 CTAs in 1.7 waves.
+template <int NKT, int NQB> struct FsCfg {
     static constexpr int KEYS = NKT * 16;
-    static constexpr size_t SMEM_BYTES = (size_t)(FS_BM + 2 * KEYS) * FA_LD * sizeof(bf16);
+    static constexpr size_t SMEM_BYTES = (size_t)(NQB * FS_BM + 2 * KEYS) * FA_LD * sizeof(bf16);
 };
 
-// grid: (ceil(T/80), H, B); 160 threads; T <= NKT*16.
-template <int NKT>
+// grid: (ceil(T/(80*NQB)), H, B); 160 threads; T <= NKT*16.
+template <int NKT, int NQB>
 __global__ void __launch_bounds__(32 * FS_NW, 3) mha_short_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                                    float* __restrict__ lse, float* __restrict__ out32, int T,
                                                                    int H, float scale_log2) {
     constexpr int KEYS = NKT * 16;
     extern __shared__ __align__(16) uint8_t fs_smem[];
     bf16* sQ = reinterpret_cast<bf16*>(fs_smem);
-    bf16* sK = sQ + FS_BM * FA_LD;
+    bf16* sK = sQ + NQB * FS_BM * FA_LD;
     bf16* sV = sK + KEYS * FA_LD;
     pdl_sync();   // PDL: wait for the previous kernel's results, let the next kernel's prologue start
 
-    const int q0 = blockIdx.x * FS_BM, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * (NQB * FS_BM), h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ld = 3 * H * FA_D;
     const bf16* base = qkv + (long long)b * T * ld;
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(32 * FS_NW, 3) mha_short_kernel(const bf16* __
             cp_async_16(dst + r * FA_LD + c, src + (long long)(ok ? row0 + r : 0) * ld + c, ok);
         }
     };
-    load_rows(sQ, gQ, q0, FS_BM);
+    load_rows(sQ, gQ, q0, NQB * FS_BM);
     load_rows(sK, gK, 0, KEYS);
     cp_async_commit();
     load_rows(sV, gV, 0, KEYS);
@@ -333,14 +336,17 @@ __global__ void __launch_bounds__(32 * FS_NW, 3) mha_short_kernel(const bf16* __
     cp_async_wait<1>();
     __syncthreads();
 
-    const bool active = q0 + warp * 16 < T;          // warp-uniform
+#pragma unroll 1
+  for (int qb = 0; qb < NQB; ++qb) {
+    const int qrow = qb * FS_BM + warp * 16;         // first query row of this warp's block inside the CTA's query slab
+    const bool active = q0 + qrow < T;               // warp-uniform
     uint32_t pf[NKT][4];                             // P as A fragments: NKT k-steps of 16 keys
     float rs[2] = {0.f, 0.f}, mx[2] = {-INFINITY, -INFINITY};
     if (active) {
         uint32_t qf[4][4];
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int r = qrow + (lane & 7) + ((lane >> 3) & 1) * 8;
             const int c = ks * 16 + (lane >> 4) * 8;
             ldmatrix_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sQ + r * FA_LD + c);
         }
@@ -389,9 +395,11 @@ __global__ void __launch_bounds__(32 * FS_NW, 3) mha_short_kernel(const bf16* __
             pf[ks][hi * 2 + 1] = pack_bf16x2(p2, p3);
         }
     }
-    cp_async_wait<0>();
-    __syncthreads();                                 // V has landed
-    if (!active) return;
+    if (qb == 0) {
+        cp_async_wait<0>();
+        __syncthreads();                             // V has landed
+    }
+    if (!active) continue;
 
     float o[8][4];
 #pragma unroll
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(32 * FS_NW, 3) mha_short_kernel(const bf16* __
         rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
         rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
     }
-    const int row0 = q0 + warp * 16 + (lane >> 2);
+    const int row0 = q0 + qrow + (lane >> 2);
     const float inv0 = 1.f / rs[0], inv1 = 1.f / rs[1];
     if (lse != nullptr && (lane & 3) == 0) {
         float* lp = lse + ((long long)b * H + h) * T;
@@ -442,20 +450,31 @@ __global__ void __launch_bounds__(32 * FS_NW, 3) mha_short_kernel(const bf16* __
                 *reinterpret_cast<float2*>(o32 + (long long)(row0 + 8) * (H * FA_D) + c) = make_float2(o[nt][2] * inv1, o[nt][3] * inv1);
         }
     }
+  }   // qb
 }
+
+template <int NKT, int NQB>
+static int launch_mha_short_q(const bf16* qkv, bf16* out, float* lse, float* out32, int B, int T, int H, float scale_log2,
+                              cudaStream_t s) {
+    auto kern = mha_short_kernel<NKT, NQB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FsCfg<NKT, NQB>::SMEM_BYTES));
+        attr_done = true;
+    }
+    const dim3 grid((T + NQB * FS_BM - 1) / (NQB * FS_BM), H, B);
+    A2F_CHECK_CUDA(launch_pdl(kern, grid, dim3(32 * FS_NW), FsCfg<NKT, NQB>::SMEM_BYTES, s, qkv, out, lse, out32, T, H, scale_log2));
+    return A2F_OK;
+}
+
+static int g_mha_short_nqb = 0;   // debug: 0 = automatic (2 query blocks per CTA when T > 80), 1 = one block per CTA (round 1)
+void set_mha_short_nqb(int v) { g_mha_short_nqb = v; }
 
 template <int NKT>
 static int launch_mha_short(const bf16* qkv, bf16* out, float* lse, float* out32, int B, int T, int H, float scale_log2,
                             cudaStream_t s) {
-    auto kern = mha_short_kernel<NKT>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FsCfg<NKT>::SMEM_BYTES));
-        attr_done = true;
-    }
-    const dim3 grid((T + FS_BM - 1) / FS_BM, H, B);
-    A2F_CHECK_CUDA(launch_pdl(kern, grid, dim3(32 * FS_NW), FsCfg<NKT>::SMEM_BYTES, s, qkv, out, lse, out32, T, H, scale_log2));
-    return A2F_OK;
+    if (T > FS_BM && g_mha_short_nqb != 1) return launch_mha_short_q<NKT, 2>(qkv, out, lse, out32, B, T, H, scale_log2, s);
+    return launch_mha_short_q<NKT, 1>(qkv, out, lse, out32, B, T, H, scale_log2, s);
 }
 
 

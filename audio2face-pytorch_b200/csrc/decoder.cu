@@ -35,6 +35,7 @@ constexpr int DEC_CLUSTER_T = 900;  // automatic mode: clips from this length on
 struct DecW {
     const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b;
     const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b, *fb_w, *fb_b, *obj_w, *pe;
+    const float *fold_w, *fold_pe;   // a2f_pack_decoder_fold: in_proj @ Wc [192,64], pe @ in_proj^T [period,192]
 };
 
 A2F_D float dot64_smem(const float* w, const float* __restrict__ x) {
@@ -100,8 +101,8 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
     float* x2 = ys + 64;             // [4][64] per-FFN1-warp copies of LN2 output
     float* f1 = x2 + 256;            // [128] relu(linear1)
     float* y3 = f1 + 128;            // [64]  pre-LN3
-    float* dcp = y3 + 64;            // [2][64] per-feedback-warp copies of d_i
-    float* style = dcp + 128;        // [64]
+    float* dcp = y3 + 64;            // [8][64] per-warp copies of d_i (warps 0..5: q|k|v of the next token, 6..7: feedback)
+    float* style = dcp + 512;        // [64]
     float* red = style + 64;         // [4][8] group reductions (max, sum) ; [4][4][16] PV partials after it
     float* pvp = red + 32;           // [4][4][16]
     float* wct = pvp + 256;          // [64][64] feedback matrix transposed: wct[k*64+r] = Wc[r][k]
@@ -122,7 +123,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
     float bias_r = 0.f;
     if (lead) {
         const float* src;
-        if (tid < 192) { src = w.sa_in_w + tid * 64; bias_r = w.sa_in_b[tid]; }
+        if (tid < 192) { src = w.fold_w + tid * 64; }      // bias_r: set below (depends on the style embedding)
         else if (tid < 256) { src = w.sa_out_w + (tid - 192) * 64; bias_r = w.sa_out_b[tid - 192]; }
         else if (tid < 384) { src = w.lin1_w + (tid - 256) * 64; bias_r = w.lin1_b[tid - 256]; }
         else {
@@ -152,12 +153,49 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
     const float* ca_b = ca + (long long)b * T * 64;
     float* D_b = D + (long long)b * T * 64;
 
+    // The feedback e_{i+1} = Wc d_i + bc + style and the in-projection of token i+1 are two Linear layers in a row:
+    //     [q|k|v]_{i+1} = in_proj(e_{i+1} + pe_{i+1}) = (in_proj Wc) d_i + in_proj (bc + style) + b_in + in_proj pe_{i+1}
+    // so q, k, v of the NEXT token come straight from d_i (threads 0..191 hold rows of in_proj Wc, a2f_pack_decoder_fold)
+    // in the same phase that produces e_{i+1}: one matvec + one barrier less on the sequential critical path of every step.
+    // bias_r (threads 0..191) = in_proj (bc + style) + b_in, utterance constant; in_proj pe_pos comes from the packed table.
+    // Token 0 (= style + pe_0, no d yet) takes the plain in-projection once, here.
+    if (lead && tid < 192) {
+        const float* wrow = w.sa_in_w + tid * 64;
+        float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 64; k += 2) {
+            const float w0 = __ldg(wrow + k), w1 = __ldg(wrow + k + 1);
+            a0 = fmaf(w0, xs[k], a0);
+            a1 = fmaf(w1, xs[k + 1], a1);
+            c0 = fmaf(w0, w.fb_b[k] + style[k], c0);
+            c1 = fmaf(w1, w.fb_b[k + 1] + style[k + 1], c1);
+        }
+        const float bin = w.sa_in_b[tid];
+        bias_r = bin + (c0 + c1);
+        const float acc = bin + (a0 + a1);
+        if (tid < 64) {
+            qs[tid] = acc * 0.25f;                                // 1/sqrt(head_dim 16), exact power of two
+            if (CL)
+                for (int rr = 1; rr < CS; ++rr) cluster.map_shared_rank(qs, rr)[tid] = acc * 0.25f;
+        }
+        else if (tid < 128) Kc[tid - 64] = acc;
+        else Vc[tid - 128] = acc;
+        if (TRAIN) {
+            const long long o = ((long long)b * T) * 64 + (tid & 63);
+            if (tid < 64) { sv.Q[o] = acc * 0.25f; sv.X[o] = xs[tid]; }
+            else if (tid < 128) sv.K[o] = acc;
+            else sv.V[o] = acc;
+        }
+    }
+    if (CL) cluster.sync();          // q_0 has landed in every rank's shared memory, K/V row 0 is visible cluster-wide
+    else __syncthreads();
+
     // loop-invariant LayerNorm parameters of the lanes that apply them (norm1/norm2: FFN1 warps, norm3: feedback warps)
     float lnA[4] = {0.f, 0.f, 0.f, 0.f}, lnB[4] = {0.f, 0.f, 0.f, 0.f};
     if (tid >= 256 && tid < 384) {
         lnA[0] = w.n1_w[lane]; lnA[1] = w.n1_w[lane + 32]; lnA[2] = w.n1_b[lane]; lnA[3] = w.n1_b[lane + 32];
         lnB[0] = w.n2_w[lane]; lnB[1] = w.n2_w[lane + 32]; lnB[2] = w.n2_b[lane]; lnB[3] = w.n2_b[lane + 32];
-    } else if (tid >= 192 && tid < 256) {
+    } else if (tid < 256) {          // warps 0..7 each normalise y3 -> d_i for themselves (phase 6)
         lnA[0] = w.n3_w[lane]; lnA[1] = w.n3_w[lane + 32]; lnA[2] = w.n3_b[lane]; lnA[3] = w.n3_b[lane + 32];
     }
 
@@ -170,27 +208,9 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             pre1 = __ldg(ca_b + (long long)i * 64 + lane + 32);
         } else if (tid >= 192 && tid < 256) {
             pre0 = __ldg(w.pe + ((i + 1) % period) * 64 + (tid - 192));
+        } else if (tid < 192) {
+            pre0 = __ldg(w.fold_pe + ((i + 1) % period) * 192 + tid);      // in_proj pe_{i+1}
         }
-        // ---------- phase 1: q, k, v of the new token ----------
-        if (lead && tid < 192) {
-            const float acc = bias_r + dot64_smem(wr, xs);
-            if (tid < 64) {
-                qs[tid] = acc * 0.25f;                            // 1/sqrt(head_dim 16), exact power of two
-                if (CL)
-                    for (int rr = 1; rr < CS; ++rr) cluster.map_shared_rank(qs, rr)[tid] = acc * 0.25f;
-            }
-            else if (tid < 128) Kc[(long long)i * KV_LD + (tid - 64)] = acc;
-            else Vc[(long long)i * KV_LD + (tid - 128)] = acc;
-            if (TRAIN) {
-                const long long o = ((long long)b * T + i) * 64 + (tid & 63);
-                if (tid < 64) { sv.Q[o] = acc * 0.25f; sv.X[o] = xs[tid]; }
-                else if (tid < 128) sv.K[o] = acc;
-                else sv.V[o] = acc;
-            }
-        }
-        if (CL) cluster.sync();      // q has landed in every rank's shared memory, K/V row i is visible cluster-wide
-        else __syncthreads();
-
         // ---------- phase 2: biased causal attention over keys 0..i (threads 0..511, 4 warps per head) ----------
         // Flash-style split: warp wq of head h owns the keys {128m + 32wq + lane} and runs its own softmax
         // (max by one REDUX on order-preserving integers, probabilities and P.V warp-synchronously); the four
@@ -281,7 +301,10 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                     if (u == 0) { dst[0] = m; dst[1] = l; }
                 }
                 cluster.sync();
-                if (!lead) continue;         // ranks > 0 only attend; they meet rank 0 again at the next step's barrier
+                if (!lead) {                 // ranks > 0 only attend; rank 0 now runs phases 3..6 and publishes q_{i+1}, k/v row i+1
+                    cluster.sync();
+                    continue;
+                }
                 if (u < 16) {
                     float m = -INFINITY;
                     for (int rr = 0; rr < CS; ++rr) m = fmaxf(m, cpart[(rr * 4 + h) * 20]);
@@ -358,33 +381,71 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
         }
         __syncthreads();
 
-        // ---------- phase 6: LN3 -> d_i (each feedback warp redundantly), store, feedback to the next input ----------
-        if (tid >= 192 && tid < 256) {
-            const int wl = warp - 6;
+        // ---------- phase 6: LN3 -> d_i (warps 0..7, each for itself), store, then IN ONE STEP the next token's
+        //            decoder input e_{i+1} + pe (warps 6,7: Wc) and its q | k | v (warps 0..5: in_proj Wc) ----------
+        if (tid < 256) {
             float a = y3[lane], c = y3[lane + 32];
             warp_ln64(a, c, lnA[0], lnA[1], lnA[2], lnA[3]);
-            float* dc = dcp + wl * 64;
+            float* dc = dcp + warp * 64;
             dc[lane] = a;
             dc[lane + 32] = c;
-            if (wl == 0) {
+            if (warp == 6) {
                 D_b[(long long)i * 64 + lane] = a;
                 D_b[(long long)i * 64 + lane + 32] = c;
             }
             __syncwarp();
-            const int r = tid - 192;
-            float f0 = 0.f, f1v = 0.f, f2 = 0.f, f3 = 0.f;
+            if (tid >= 192) {
+                const int r = tid - 192;
+                float f0 = 0.f, f1v = 0.f, f2 = 0.f, f3 = 0.f;
 #pragma unroll
-            for (int k = 0; k < 64; k += 4) {
-                const float4 dv = *reinterpret_cast<const float4*>(dc + k);
-                f0 = fmaf(wct[k * 64 + r], dv.x, f0);
-                f1v = fmaf(wct[(k + 1) * 64 + r], dv.y, f1v);
-                f2 = fmaf(wct[(k + 2) * 64 + r], dv.z, f2);
-                f3 = fmaf(wct[(k + 3) * 64 + r], dv.w, f3);
+                for (int k = 0; k < 64; k += 4) {
+                    const float4 dv = *reinterpret_cast<const float4*>(dc + k);
+                    f0 = fmaf(wct[k * 64 + r], dv.x, f0);
+                    f1v = fmaf(wct[(k + 1) * 64 + r], dv.y, f1v);
+                    f2 = fmaf(wct[(k + 2) * 64 + r], dv.z, f2);
+                    f3 = fmaf(wct[(k + 3) * 64 + r], dv.w, f3);
+                }
+                const float e = (fb_bias + ((f0 + f1v) + (f2 + f3))) + style[r];
+                xs[r] = e + pre0;
+                if (TRAIN && i + 1 < T) sv.X[((long long)b * T + i + 1) * 64 + r] = e + pre0;
+            } else if (i + 1 < T) {
+                const float acc = (bias_r + pre0) + dot64_smem(wr, dc);
+                if (tid < 64) {
+                    qs[tid] = acc * 0.25f;
+                    if (CL)
+                        for (int rr = 1; rr < CS; ++rr) cluster.map_shared_rank(qs, rr)[tid] = acc * 0.25f;
+                }
+                else if (tid < 128) Kc[(long long)(i + 1) * KV_LD + (tid - 64)] = acc;
+                else Vc[(long long)(i + 1) * KV_LD + (tid - 128)] = acc;
+                if (TRAIN) {
+                    const long long o = ((long long)b * T + i + 1) * 64 + (tid & 63);
+                    if (tid < 64) sv.Q[o] = acc * 0.25f;
+                    else if (tid < 128) sv.K[o] = acc;
+                    else sv.V[o] = acc;
+                }
             }
-            const float e = (fb_bias + ((f0 + f1v) + (f2 + f3))) + style[r];
-            xs[r] = e + pre0;
         }
-        __syncthreads();
+        if (CL) cluster.sync();      // q_{i+1} has landed in every rank's shared memory, K/V row i+1 is visible cluster-wide
+        else __syncthreads();
+    }
+}
+
+// Operands of the folded step (see the kernel): fold_w = in_proj_weight @ Wc  [192,64],  fold_pe[pos] = in_proj_weight @ pe[pos]
+// [period,192]; fp64 accumulation.  Runs with a2f_pack_feedback whenever a decoder weight changes (Wc must be current).
+__global__ void __launch_bounds__(192) pack_decoder_fold_kernel(const float* __restrict__ in_w, const float* __restrict__ wc,
+                                                                const float* __restrict__ pe, int period,
+                                                                float* __restrict__ fold_w, float* __restrict__ fold_pe) {
+    const int r = threadIdx.x;                 // row of in_proj_weight
+    const int blk = blockIdx.x;                // blocks 0..63: column blk of fold_w; blocks 64..64+period-1: position
+    const float* wrow = in_w + r * 64;
+    double acc = 0.0;
+    if (blk < 64) {
+        for (int k = 0; k < 64; ++k) acc = fma((double)wrow[k], (double)wc[k * 64 + blk], acc);
+        fold_w[r * 64 + blk] = (float)acc;
+    } else {
+        const float* pp = pe + (blk - 64) * 64;
+        for (int k = 0; k < 64; ++k) acc = fma((double)wrow[k], (double)pp[k], acc);
+        fold_pe[(blk - 64) * 192 + r] = (float)acc;
     }
 }
 
@@ -482,7 +543,7 @@ void set_dec_cluster(int v) { g_dec_cluster = v; }
 
 static size_t dec_smem_bytes(int T, bool kv_in_smem, int cluster = 1) {
     const int Tpad = (((T + cluster - 1) / cluster) + 3) & ~3;
-    size_t fl = 64 * 4 + 256 + 128 + 64 + 128 + 64 + 32 + 256 + 4096 + 640 + (size_t)4 * Tpad;
+    size_t fl = 64 * 4 + 256 + 128 + 64 + 512 + 64 + 32 + 256 + 4096 + 640 + (size_t)4 * Tpad;
     if (kv_in_smem) fl += (size_t)2 * T * KV_LD;
     return fl * sizeof(float);
 }
@@ -567,6 +628,8 @@ static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memor
     dw.lin1_w = w->lin1_w; dw.lin1_b = w->lin1_b; dw.lin2_w = w->lin2_w; dw.lin2_b = w->lin2_b;
     dw.n1_w = w->n1_w; dw.n1_b = w->n1_b; dw.n2_w = w->n2_w; dw.n2_b = w->n2_b; dw.n3_w = w->n3_w; dw.n3_b = w->n3_b;
     dw.fb_w = w->fb_w; dw.fb_b = w->fb_b; dw.obj_w = w->obj_w; dw.pe = w->pe;
+    A2F_REQUIRE(w->fold_w != nullptr && w->fold_pe != nullptr, "a2f_decoder_rollout: fold_w / fold_pe (a2f_pack_decoder_fold) missing");
+    dw.fold_w = w->fold_w; dw.fold_pe = w->fold_pe;
     const size_t smem = dec_smem_bytes(T, kv == nullptr);
     // long clips, inference: keys of one utterance spread over a cluster of CS CTAs (largest power of two that still
     // gives every utterance its own cluster in one wave, at most 8 = the portable cluster size)
@@ -660,6 +723,17 @@ int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, 
     A2F_REQUIRE(vm_w && vm_b && vmr_w && vmr_b && Wc && bc && V3 > 0, "a2f_pack_feedback: bad arguments");
     pack_feedback_kernel<<<dim3(FB_SPLIT, 64), 256, 0, as_stream(stream)>>>(vm_w, vm_b, vmr_w, vmr_b, V3, Wc, bc);
     A2F_CHECK_LAUNCH("pack_feedback_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+int a2f_pack_decoder_fold(const float* sa_in_w, const float* wc, const float* pe, int period, float* fold_w, float* fold_pe,
+                          void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(sa_in_w && wc && pe && fold_w && fold_pe && period > 0, "a2f_pack_decoder_fold: bad arguments");
+    pack_decoder_fold_kernel<<<64 + period, 192, 0, as_stream(stream)>>>(sa_in_w, wc, pe, period, fold_w, fold_pe);
+    A2F_CHECK_LAUNCH("pack_decoder_fold_kernel");
     count_launch();
     return A2F_OK;
 }

@@ -46,6 +46,8 @@ struct LnParams {
     const float* gamma;
     const float* beta;
     float eps;
+    bf16* pre_out;                  // training: the pre-LayerNorm sum x (bf16 [M,N], row stride ldp) for the backward; else NULL
+    long long ldp;
 };
 
 template <int NP> struct LnCfg {
@@ -264,6 +266,19 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const LnParams p) {
                 }
                 tmem_st_32x32(t_row + col0, v);
                 tmem_st_32x32(t_row + col0 + 32, v + 32);
+                if (p.pre_out != nullptr && row_base + r_tile < p.M) {
+                    // training: LayerNorm's backward needs its input; every thread writes its own row's 128 bytes
+                    bf16* pp = p.pre_out + (long long)(row_base + r_tile) * p.ldp + n0 + col0;
+#pragma unroll
+                    for (int ch = 0; ch < L_SBW / 8; ++ch) {
+                        uint4 u;
+                        u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+                        u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+                        u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+                        u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+                        *reinterpret_cast<uint4*>(pp + ch * 8) = u;
+                    }
+                }
             }
             // ---- exchange: my partial -> the stats slot of every CTA that holds these rows (same hr, all NP pairs) ----
             {
@@ -399,7 +414,8 @@ int launch_gemm_ln(LnMaps& maps, const LnParams& p, cudaStream_t s) {
 
 // A [M,K] bf16 (row stride lda), W [N,K] bf16 (row stride ldw), resid / out [M,N] bf16; N = 256 * NP, NP in {1,2,3}.
 int gemm_ln_tc(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* resid, long long ldr,
-               const float* gamma, const float* beta, float eps, void* out, long long ldo, int M, int N, int K, cudaStream_t s) {
+               const float* gamma, const float* beta, float eps, void* out, long long ldo, void* pre_out, long long ldp, int M,
+               int N, int K, cudaStream_t s) {
     if (M <= 0) return A2F_OK;
     A2F_REQUIRE(N % LBN == 0 && N / LBN >= 1 && N / LBN <= 3, "a2f_gemm_ln: N must be 256, 512 or 768");
     A2F_REQUIRE(K > 0 && K % 8 == 0, "a2f_gemm_ln: K must be a positive multiple of 8");
@@ -437,6 +453,10 @@ int gemm_ln_tc(const void* A, long long lda, const void* W, long long ldw, const
     p.tiles_m = (M + 2 * LBM - 1) / (2 * LBM);
     p.num_k_blocks = (K + LBK - 1) / LBK;
     p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
+    p.pre_out = static_cast<bf16*>(pre_out);
+    p.ldp = ldp;
+    A2F_REQUIRE(pre_out == nullptr || (ldp % 8 == 0 && ldp >= N && (reinterpret_cast<uintptr_t>(pre_out) & 15) == 0),
+                "a2f_gemm_ln: pre_out must be 16-byte aligned with a row stride that is a multiple of 8 elements");
     switch (N / LBN) {
         case 1: return launch_gemm_ln<1>(maps, p, s);
         case 2: return launch_gemm_ln<2>(maps, p, s);
@@ -447,11 +467,12 @@ int gemm_ln_tc(const void* A, long long lda, const void* W, long long ldw, const
 }  // namespace a2f
 
 extern "C" int a2f_gemm_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* resid,
-                           long long ldr, const float* gamma, const float* beta, float eps, void* out, long long ldo, int M,
-                           int N, int K, void* stream) {
+                           long long ldr, const float* gamma, const float* beta, float eps, void* out, long long ldo,
+                           void* pre_out, long long ldp, int M, int N, int K, void* stream) {
     int rc = a2f::require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(A && W && resid && gamma && beta && out, "a2f_gemm_ln: A, W, resid, gamma, beta and out must be non-NULL");
     A2F_REQUIRE(M >= 0 && N > 0 && K > 0, "a2f_gemm_ln: bad M/N/K");
-    return a2f::gemm_ln_tc(A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, out, ldo, M, N, K, a2f::as_stream(stream));
+    return a2f::gemm_ln_tc(A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, out, ldo, pre_out, ldp, M, N, K,
+                           a2f::as_stream(stream));
 }

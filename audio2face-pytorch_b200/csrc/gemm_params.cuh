@@ -32,6 +32,17 @@ struct GemmParams {
     // SIMT back end only: K range split over gridDim.z (fp32 atomicAdd into a zeroed C), set by gemm_simt itself
     int split_k = 1;
     int k_per_split = 0;
+    // tcgen05 CTA-pair kernel: second output C2 = act(z) while C keeps the pre-activation z (a2f.h a2f_gemm_args::C2)
+    void* C2 = nullptr;
+    long long ldc2 = 0;
+    // tcgen05 vertex head with the reconstruction / velocity loss fused into its epilogue (a2f_vertex_head_loss): gt [M,N]
+    // fp32; the epilogue accumulates sum (y-g)^2 and sum ((y1-y0)-(g1-g0))^2 over row pairs (2k,2k+1) into per-warp fp64
+    // partials, writes dL/dy as bf16 [M, ld_dy] and stores y itself only when C != NULL
+    const float* loss_gt = nullptr;
+    void* loss_dy = nullptr;
+    long long ld_dy = 0;
+    float c_rec = 0.f, c_vel = 0.f;
+    double* loss_partial = nullptr;   // [grid][8 epilogue warps][2]
 };
 
 inline void normalize_gemm(GemmParams& p) {

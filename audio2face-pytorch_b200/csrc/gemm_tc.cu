@@ -33,6 +33,7 @@ struct TmapSet {
     CUtensorMap b;
     CUtensorMap bs;                 // pair kernel: B map of the split tail tiles (box rows = BN / 2 / tail_split)
     CUtensorMap c;
+    CUtensorMap c2;                 // pair kernel: second output act(z) (GemmParams::C2)
     CUtensorMap r;                  // residual / saved pre-activation (pair kernel, bf16, 16-byte aligned rows)
 };
 
@@ -346,7 +347,8 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         const int e_act = g.act;
         const bool e_dact = g.resid_mode == A2F_RESID_DACT;
         // ---- wide scalar epilogue (vertex heads): this warp owns 32 rows x 128 columns of every tile ----
-        const bool wide = WIDE && g.resid == nullptr && g.act == A2F_ACT_NONE && p.mode != 2;
+        const bool wide = WIDE && g.resid == nullptr && g.act == A2F_ACT_NONE && p.mode != 2 && g.loss_gt == nullptr;
+        double loss_rec = 0.0, loss_vel = 0.0;   // fused-loss epilogue: this thread's share of the two sums
         float tadd[WIDE_WR * 4];    // template values of the NEXT WIDE_WR rows x 4 chunks, always in flight
         bool tadd_primed = false;
         const float* fill_tp = nullptr;         // template row the refill stream reads next
@@ -554,6 +556,46 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     const int ncol = n_tile0 + c * 32 + lane;
                     const bool col_ok = ncol < n_end;
                     const float bj = (g.bias && col_ok) ? __ldg(g.bias + ncol) : 0.f;
+                    if (SCALAR && g.loss_gt != nullptr) {
+                        // ---- vertex head + reconstruction / velocity loss (ref:src/loss/loss.py:29-55) in one pass ----
+                        // lane = column, r = row of this warp's 32-row slice; rows (2k, 2k+1) of a velocity pair are
+                        // consecutive r (slices start on even rows and M is even), so the pair never leaves the thread.
+                        // y = W d + b + template is used where it sits in registers: gt is read ONCE, dL/dy leaves as
+                        // bf16 in the layout the backward GEMMs read, y itself is stored only on request.
+                        const float* tp = g.tmpl ? g.tmpl + trow0 * (long long)g.N + ncol : nullptr;
+                        int trem = trem0;
+                        const float* gp = g.loss_gt + m0w * (long long)g.N + ncol;
+                        bf16* dyp = static_cast<bf16*>(g.loss_dy) + m0w * g.ld_dy + ncol;
+                        float racc = 0.f, vacc = 0.f;
+#pragma unroll 4
+                        for (int r = 0; r < 32; r += 2) {
+                            float t0 = 0.f, t1 = 0.f;
+                            if (tp != nullptr) {
+                                if (col_ok && r < rows_left) t0 = __ldg(tp);
+                                if (++trem == g.rows_per_tmpl) { trem = 0; tp += g.N; }
+                                if (col_ok && r + 1 < rows_left) t1 = __ldg(tp);
+                                if (++trem == g.rows_per_tmpl) { trem = 0; tp += g.N; }
+                            }
+                            if (col_ok && r + 1 < rows_left) {
+                                const float y0 = (tr[r * 32 + ((lane + r) & 31)] + bj) + t0;
+                                const float y1 = (tr[(r + 1) * 32 + ((lane + r + 1) & 31)] + bj) + t1;
+                                const float g0 = __ldg(gp + (long long)r * g.N), g1 = __ldg(gp + (long long)(r + 1) * g.N);
+                                const float d0 = y0 - g0, d1 = y1 - g1;
+                                const float dv = (y1 - y0) - (g1 - g0);
+                                racc = fmaf(d0, d0, fmaf(d1, d1, racc));
+                                vacc = fmaf(dv, dv, vacc);
+                                dyp[(long long)r * g.ld_dy] = __float2bfloat16_rn(g.c_rec * d0 - g.c_vel * dv);
+                                dyp[(long long)(r + 1) * g.ld_dy] = __float2bfloat16_rn(g.c_rec * d1 + g.c_vel * dv);
+                                if (g.C != nullptr) {
+                                    reinterpret_cast<float*>(C)[c_row0 + (long long)r * g.ldc + ncol] = y0;
+                                    reinterpret_cast<float*>(C)[c_row0 + (long long)(r + 1) * g.ldc + ncol] = y1;
+                                }
+                            }
+                        }
+                        loss_rec += (double)racc;      // 32 fp32 terms per chunk, then fp64 (deterministic order)
+                        loss_vel += (double)vacc;
+                        continue;
+                    }
                     const bool fast = (n_tile0 + c * 32 + 32 <= n_end) && rows_left >= 32 && g.resid == nullptr &&
                                       g.act == A2F_ACT_NONE;      // warp-uniform: whole 32x32 chunk live, plain epilogue
                     if (fast) {
@@ -638,6 +680,14 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         if (threadIdx.x == 64) TL_STAMP(6);                                 // all tiles' epilogues issued
         if (!SCALAR && leader) tma_store_wait_all();
         if (threadIdx.x == 64) TL_STAMP(7);                                 // stores drained
+        if (SCALAR && g.loss_partial != nullptr) {
+            loss_rec = warp_sum_d(loss_rec);
+            loss_vel = warp_sum_d(loss_vel);
+            if (lane == 0) {
+                g.loss_partial[((long long)blockIdx.x * 8 + ew) * 2] = loss_rec;
+                g.loss_partial[((long long)blockIdx.x * 8 + ew) * 2 + 1] = loss_vel;
+            }
+        }
     }
 
     tc_fence_before();
@@ -832,6 +882,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         const int e_act = g.act;
         const bool e_dact = g.resid_mode == A2F_RESID_DACT;
         const bool rtma = p.resid_tma != 0;
+        const bool dual = g.C2 != nullptr;                             // C = z (pre-activation), C2 = act(z)
         const bool fast_dgelu = e_dact && p.fast_gelu && e_act == A2F_ACT_GELU;    // bf16 output: MUFU-based GELU'
         constexpr int SBW = Cfg::SBW;
         constexpr int EPC = 16 / (int)sizeof(TC);
@@ -884,7 +935,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                             v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
                         }
                     }
-                    epi_bias_act<SBW>(v, nullptr, 0, ncol0, n_end, e_act, p.fast_gelu);
+                    if (!dual) epi_bias_act<SBW>(v, nullptr, 0, ncol0, n_end, e_act, p.fast_gelu);
                 }
                 if (rtma) {
                     mbar_wait(&rbar[half], sb & 1);                    // residual block landed (and the buffer is ours)
@@ -952,6 +1003,39 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                 if (leader) {
                     tma_store_3d(&maps.c, stage_buf, ncol0, row_base, b);
                     tma_store_commit();
+                }
+                if (dual) {
+                    // second output: act(z) through the OTHER staging buffer (the block behaves like two blocks in a row)
+                    epi_bias_act<SBW>(v, nullptr, 0, ncol0, n_end, e_act, p.fast_gelu);
+                    uint8_t* rowp2 = stage_base + (sb & 1) * EPI_STAGE_BYTES + r_tile * 128;
+                    if (leader) tma_store_wait_read1();
+                    named_bar_sync(bar_id, 128);
+#pragma unroll
+                    for (int ch = 0; ch < SBW / EPC; ++ch) {
+                        const int pch = ch ^ (r_tile & 7);
+                        uint4 u;
+                        if (sizeof(TC) == 2) {
+                            u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+                            u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+                            u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+                            u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+                        } else {
+                            u.x = __float_as_uint(v[ch * EPC + 0]);
+                            u.y = __float_as_uint(v[ch * EPC + 1]);
+                            u.z = __float_as_uint(v[ch * EPC + 2]);
+                            u.w = __float_as_uint(v[ch * EPC + 3]);
+                        }
+                        *reinterpret_cast<uint4*>(rowp2 + pch * 16) = u;
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (leader) {
+                        tma_store_3d(&maps.c2, stage_base + (sb & 1) * EPI_STAGE_BYTES, ncol0, row_base, b);
+                        tma_store_commit();
+                    }
+                    ++sb;
+                }
+                if (leader) {
                     if (rtma && col0 + 2 * SBW < n_lim) {              // next block of this tile: fetch its residual now
                         tma_store_wait_read1();
                         mbar_expect_tx(&rbar[half], EPI_STAGE_BYTES);
@@ -992,6 +1076,15 @@ static int launch_tc2(TmapSet& maps, const TcParams& p_in, cudaStream_t s) {
     if (rc != A2F_OK) return rc;
     TcParams p = p_in;
     p.resid_tma = 0;
+    if (g.C2 != nullptr) {
+        A2F_REQUIRE(reinterpret_cast<uintptr_t>(g.C2) % 16 == 0 && (g.ldc2 * (long long)sizeof(TC)) % 16 == 0 && g.ldc > 0 &&
+                    (g.c_batch_stride * g.ldc2) % g.ldc == 0, "gemm_tc: C2 must be 16-byte aligned with a layout proportional to C");
+        const long long c2_batch = g.c_batch_stride / g.ldc * g.ldc2;
+        A2F_REQUIRE((c2_batch * (long long)sizeof(TC)) % 16 == 0, "gemm_tc: C2 batch stride must be a multiple of 16 bytes");
+        uint64_t strides2[2] = {(uint64_t)g.ldc2 * sizeof(TC), (uint64_t)c2_batch * sizeof(TC)};
+        rc = encode_tmap(&maps.c2, g.C2, (int)sizeof(TC), 3, dims, strides2, box, 1);
+        if (rc != A2F_OK) return rc;
+    }
     if (g.resid != nullptr && g.resid_bf16 && sizeof(TC) == 2 && reinterpret_cast<uintptr_t>(g.resid) % 16 == 0 &&
         (g.ldr * 2) % 16 == 0 && (g.r_batch_stride * 2) % 16 == 0) {
         uint64_t rdims[3] = {(uint64_t)g.N, (uint64_t)g.rows_per_batch, (uint64_t)p.num_batches};
@@ -1147,7 +1240,8 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
             const size_t csz0 = c_bf16 ? 2 : 4;
             const bool c_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((g.ldc * (long long)csz0) % 16 == 0) &&
                               ((g.c_batch_stride * (long long)csz0) % 16 == 0);
-            use_pair = g_pair_mode && BN == 256 && g.tmpl == nullptr && c_ok && g.rows_per_batch > TBM && sm_count() >= 2;
+            use_pair = g_pair_mode && BN == 256 && g.tmpl == nullptr && g.loss_gt == nullptr && c_ok && g.rows_per_batch > TBM &&
+                       sm_count() >= 2;
             if (use_pair) p.tiles_m_per_batch = (g.rows_per_batch + 2 * TBM - 1) / (2 * TBM);
         }
         p.tiles_n = (g.N + BN - 1) / BN;
@@ -1207,7 +1301,7 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
     }
     // scalar (transposing) epilogue: outputs whose rows are not 16-byte aligned (the 15069-wide vertex head) and the
     // template-add epilogue.  fp32 output only.
-    const bool scalar = (g.tmpl != nullptr) || !c_tma_ok;
+    const bool scalar = (g.tmpl != nullptr) || !c_tma_ok || g.loss_gt != nullptr;
     if (scalar) {
         A2F_REQUIRE(g.resid_mode == A2F_RESID_ADD, "gemm_tc: the activation-backward epilogue needs 16-byte aligned outputs");
         A2F_REQUIRE(!c_bf16, "gemm_tc: template-add / unaligned outputs are fp32 only");
@@ -1219,6 +1313,8 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
         if (c_bf16) return launch_tc2<256, bf16>(maps, p, s);
         return launch_tc2<256, float>(maps, p, s);
     }
+    A2F_REQUIRE(g.C2 == nullptr, "gemm_tc: the two-output epilogue (C2) needs the CTA-pair kernel (N > 128, more than 128 rows "
+                                 "per batch, 16-byte aligned outputs)");
     switch (BN) {
         case 256: return dispatch_out<256>(maps, p, c_bf16, scalar, s);
         case 128: return dispatch_out<128>(maps, p, c_bf16, scalar, s);
@@ -1233,6 +1329,7 @@ int gemm_tc(const GemmParams& g_in, int c_bf16, int mode, cudaStream_t s) {
 namespace a2f {
 void set_mha_impl(int v);
 void set_mha_tc_min_t(int v);
+void set_mha_short_nqb(int v);
 void set_dec_cluster(int v);
 void set_posconv_impl(int v);
 void set_posconv_swap(int v);
@@ -1271,6 +1368,10 @@ extern "C" int a2f_debug_set_umma_field(int field, unsigned value) {
     }
     if (field == 10) {  // posconv_tc.cu: exchange the LBO / SBO descriptor fields (bring-up experiment)
         a2f::set_posconv_swap(value ? 1 : 0);
+        return A2F_OK;
+    }
+    if (field == 12) {  // short-clip attention: 0 = automatic, 1 = one 80-query block per CTA (round-1 schedule)
+        a2f::set_mha_short_nqb((int)value);
         return A2F_OK;
     }
     if (field == 11) {  // pair kernel: 0 = never cut the tiles of a partly filled last wave into column slices

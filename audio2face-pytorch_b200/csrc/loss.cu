@@ -4,6 +4,7 @@
 //   loss = k_rec*rec + k_vel*vel                  (ref loss.py:51-55)
 // Deterministic: per-CTA fp64 partials in the workspace, summed by a second single-CTA kernel (no atomics).
 #include "a2f_common.cuh"
+#include "gemm_params.cuh"
 
 namespace a2f {
 
@@ -121,6 +122,48 @@ int a2f_voca_loss_bwd(const float* pred, const float* gt, long long rows, int V3
     loss_bwd_kernel<<<loss_grid(), LOSS_THREADS, 0, as_stream(stream)>>>(pred, gt, rows / 2, V3, c_rec, c_vel, gscale,
                                                                          dpred);
     A2F_CHECK_LAUNCH("loss_bwd_kernel");
+    count_launch();
+    return A2F_OK;
+}
+
+/* ---- vertex head with the loss fused into its epilogue (tcgen05 path) ---- */
+size_t a2f_vertex_head_loss_workspace_bytes(void) { return (size_t)sm_count() * 8 * 2 * sizeof(double); }
+
+int a2f_vertex_head_loss(const void* z3, const void* w3, int K3, const float* bias, const float* tmpl, int rows_per_tmpl,
+                         const float* gt, long long rows, int V3, float k_rec, float k_vel, float* pred, void* dy_bf16,
+                         long long ld_dy, float* out3, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(z3 && w3 && gt && dy_bf16 && out3 && workspace, "a2f_vertex_head_loss: NULL argument");
+    A2F_REQUIRE(rows > 0 && rows % 2 == 0 && rows < (1LL << 30), "a2f_vertex_head_loss: rows must be positive and even");
+    A2F_REQUIRE(V3 > 0 && V3 % 3 == 0 && K3 > 0 && K3 % 8 == 0, "a2f_vertex_head_loss: bad V3 / K");
+    A2F_REQUIRE(ld_dy >= V3, "a2f_vertex_head_loss: ld_dy must cover V3 columns");
+    A2F_REQUIRE(tmpl == nullptr || rows_per_tmpl > 0, "a2f_vertex_head_loss: rows_per_tmpl must be positive");
+    const int n_part = sm_count() * 8;
+    A2F_REQUIRE(workspace_bytes >= (size_t)n_part * 2 * sizeof(double), "a2f_vertex_head_loss: workspace too small");
+    A2F_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 8 == 0, "a2f_vertex_head_loss: workspace must be 8-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    A2F_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_part * 2 * sizeof(double), s));
+    const double nv = (double)(V3 / 3);
+    GemmParams p;
+    p.M = (int)rows; p.N = V3; p.K = K3;
+    p.A = z3; p.a_row_stride = K3; p.a_batch_stride = 0; p.rows_per_batch = (int)rows;
+    p.W = w3; p.ldw = K3;
+    p.bias = bias; p.act = A2F_ACT_NONE;
+    p.resid = nullptr; p.resid_bf16 = 0; p.ldr = 0;
+    p.tmpl = tmpl; p.rows_per_tmpl = tmpl ? rows_per_tmpl : 1;
+    p.C = pred; p.ldc = V3; p.c_batch_stride = 0;
+    p.loss_gt = gt;
+    p.loss_dy = dy_bf16;
+    p.ld_dy = ld_dy;
+    p.c_rec = (float)(2.0 * k_rec / ((double)rows * nv));
+    p.c_vel = (float)(2.0 * k_vel / ((double)(rows / 2) * nv));
+    p.loss_partial = static_cast<double*>(workspace);
+    rc = gemm_tc(p, 0, 0, s);
+    if (rc != A2F_OK) return rc;
+    loss_final_kernel<<<1, 32, 0, s>>>(static_cast<const double*>(workspace), n_part, 1.0 / ((double)rows * nv),
+                                       1.0 / ((double)(rows / 2) * nv), k_rec, k_vel, out3);
+    A2F_CHECK_LAUNCH("loss_final_kernel");
     count_launch();
     return A2F_OK;
 }

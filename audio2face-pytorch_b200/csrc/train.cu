@@ -704,7 +704,15 @@ __global__ void posconv_pack_dgrad_kernel(const float* __restrict__ gw, const fl
 template <typename G>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const G* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, float lr, float b1, float b2,
-                                                   float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+                                                   float eps, float wd, float bc1, float bc2_sqrt, float gscale,
+                                                   const int* __restrict__ step_dev) {
+    if (step_dev != nullptr) {
+        // step count kept on the device (a captured CUDA graph replays the same launch for every step): bias corrections
+        // 1 - beta^t are evaluated here instead of on the host
+        const float t = (float)__ldg(step_dev);
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    }
     const float step = lr / bc1;
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1051,10 +1059,11 @@ int a2f_pack_posconv_dgrad_weight(const float* g, const float* v, void* out, int
 }
 
 static int adam_launch(float* p, const void* g, int g_bf16, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                       float eps, float weight_decay, int step, float grad_scale, void* stream) {
+                       float eps, float weight_decay, int step, float grad_scale, void* stream, const int* step_dev = nullptr) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
-    A2F_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "a2f_adam_step: bad arguments");
+    A2F_REQUIRE(p && g && m && v && n >= 0 && (step >= 1 || step_dev != nullptr), "a2f_adam_step: bad arguments");
+    if (step < 1) step = 1;
     if (n == 0) return A2F_OK;
     A2F_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(g) & (g_bf16 ? 7 : 15)) == 0, "a2f_adam_step: buffers must be 16-byte aligned");
@@ -1062,10 +1071,10 @@ static int adam_launch(float* p, const void* g, int g_bf16, float* m, float* v, 
     const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
     if (g_bf16)
         adam_kernel<bf16><<<ew_grid(n, 4), 256, 0, as_stream(stream)>>>(p, static_cast<const bf16*>(g), m, v, n, lr, beta1, beta2, eps,
-                                                                       weight_decay, bc1, bc2s, grad_scale);
+                                                                       weight_decay, bc1, bc2s, grad_scale, step_dev);
     else
         adam_kernel<float><<<ew_grid(n, 4), 256, 0, as_stream(stream)>>>(p, static_cast<const float*>(g), m, v, n, lr, beta1, beta2,
-                                                                        eps, weight_decay, bc1, bc2s, grad_scale);
+                                                                        eps, weight_decay, bc1, bc2s, grad_scale, step_dev);
     A2F_CHECK_LAUNCH("adam_kernel");
     count_launch();
     return A2F_OK;
@@ -1079,6 +1088,13 @@ int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 int a2f_adam_step_bf16g(float* p, const void* g_bf16, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, int step, float grad_scale, void* stream) {
     return adam_launch(p, g_bf16, 1, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream);
+}
+
+int a2f_adam_step_dev(float* p, const void* g, int g_dtype, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, const int* step_dev, float grad_scale, void* stream) {
+    A2F_REQUIRE(step_dev != nullptr, "a2f_adam_step_dev: step_dev is NULL");
+    A2F_REQUIRE(g_dtype == A2F_F32 || g_dtype == A2F_BF16, "a2f_adam_step_dev: gradient dtype must be fp32 or bf16");
+    return adam_launch(p, g, g_dtype == A2F_BF16, m, v, n, lr, beta1, beta2, eps, weight_decay, 0, grad_scale, stream, step_dev);
 }
 
 int a2f_spec_mask_fwd(void* h, int dtype, const unsigned char* mask, const float* embed, long long rows, int cols,

@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("C", c_void_p), ("c_dtype", c_int), ("ldc", c_ll), ("c_batch_stride", c_ll),
         ("a_rows", c_int), ("n_seg", c_int), ("seg_row_off", c_int * 4), ("seg_col_off", c_int * 4),
         ("r_batch_stride", c_ll), ("resid_mode", c_int),
+        ("C2", c_void_p), ("ldc2", c_ll),
     ]
 
 
@@ -63,7 +64,7 @@ class DecoderWeights(C.Structure):
     _names = [
         "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b", "ca_in_w", "ca_in_b", "ca_out_w", "ca_out_b",
         "lin1_w", "lin1_b", "lin2_w", "lin2_b", "n1_w", "n1_b", "n2_w", "n2_b", "n3_w", "n3_b",
-        "fb_w", "fb_b", "obj_w", "pe",
+        "fb_w", "fb_b", "obj_w", "pe", "fold_w", "fold_pe",
     ]
     _fields_ = [(n, c_void_p) for n in _names]
 
@@ -85,7 +86,7 @@ _SIGNATURES = {
     "a2f_gemm": (c_int, [C.POINTER(GemmArgs), c_int, c_void_p]),
     "a2f_gemm_wgrad": (c_int, [C.POINTER(WgradArgs), c_int, c_void_p]),
     "a2f_gemm_ln": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_ll,
-                            c_int, c_int, c_int, c_void_p]),
+                            c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "a2f_posconv": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "a2f_pack_posconv_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "a2f_pack_conv1d_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -121,6 +122,7 @@ _SIGNATURES = {
                                         c_void_p, c_size_t, c_void_p]),
     "a2f_ln64_param_grad": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
     "a2f_pack_feedback": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "a2f_pack_decoder_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "a2f_pack_cross_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                          c_void_p, c_void_p]),
     "a2f_voca_trunk": (c_int, [C.POINTER(VocaWeights), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
@@ -131,6 +133,9 @@ _SIGNATURES = {
     "a2f_voca_loss_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_void_p, c_void_p, c_size_t,
                                   c_void_p]),
     "a2f_voca_loss_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "a2f_vertex_head_loss_workspace_bytes": (c_size_t, []),
+    "a2f_vertex_head_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_int, c_float, c_float,
+                                     c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_size_t, c_void_p]),
     "a2f_debug_set_umma_field": (c_int, [c_int, C.c_uint]),
     "a2f_debug_set_timeline": (c_int, [c_void_p]),
     "a2f_act_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
@@ -183,6 +188,8 @@ _SIGNATURES = {
                               c_int, c_float, c_void_p]),
     "a2f_adam_step_bf16g": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                                     c_int, c_float, c_void_p]),
+    "a2f_adam_step_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
+                                  c_void_p, c_float, c_void_p]),
 }
 
 DEC_SAVE_FIELDS = ("X", "Q", "K", "V", "CTX", "Y1PRE", "Y2PRE", "Y2", "HID", "Y3PRE", "LSE")      # a2f.h A2F_DEC_*

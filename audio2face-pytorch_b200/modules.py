@@ -120,6 +120,14 @@ class _A2FModule(nn.Module):
         if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
             raise L.A2FError("autograd through this module is not available; call it under torch.no_grad()")
 
+    def _head_operand(self, weight: nn.Parameter, k_live: int) -> torch.Tensor:
+        """bf16x3 split [V3, 192] of the vertex-head weight (zero-padded to 64 input columns), cached per weight version."""
+        def build():
+            w = torch.zeros((weight.shape[0], 64), dtype=torch.float32, device=weight.device)
+            w[:, :k_live] = weight.detach()
+            return ops.split_bf16x3(w, True)
+        return self._cache.get("head_bf16x3", (weight,), build)
+
     def _vertex_head(self, z: torch.Tensor, weight: nn.Parameter, bias: nn.Parameter, template2d: torch.Tensor,
                      rows_per_tmpl: int, k_live: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Shared K11 head: out = z @ W^T + b + template, out [M, V3] fp32.  z: fp32 [M, 64] (columns >= k_live zero).
@@ -130,11 +138,7 @@ class _A2FModule(nn.Module):
         if out is None:
             out = torch.empty((M, v3), dtype=torch.float32, device=z.device)
         if self.precision == "bf16":
-            def build():
-                w = torch.zeros((v3, 64), dtype=torch.float32, device=weight.device)
-                w[:, :k_live] = weight.detach()
-                return ops.split_bf16x3(w, True)
-            wp = self._cache.get("head_bf16x3", (weight,), build)
+            wp = self._head_operand(weight, k_live)
             z3 = ops.split_bf16x3(z, False)
             ops.gemm(z3, wp, out, bias=bias.detach(), tmpl=template2d, rows_per_tmpl=rows_per_tmpl, backend=L.TCGEN05, K=192,
                      alg_K=k_live)
@@ -648,6 +652,9 @@ class Faceformer(_A2FModule):
             wc = torch.empty((64, 64), dtype=torch.float32, device=dev)
             bc = torch.empty((64,), dtype=torch.float32, device=dev)
             P["fb"] = (wc, bc)
+            # feedback and next-token in-projection applied as one matvec by the rollout kernels (a2f_pack_decoder_fold)
+            fold_w = torch.empty((192, 64), dtype=torch.float32, device=dev)
+            fold_pe = torch.empty((self.period, 192), dtype=torch.float32, device=dev)
             d = self.transformer_decoder.layers[0]
             dw = L.DecoderWeights()
             keep = {
@@ -658,7 +665,7 @@ class Faceformer(_A2FModule):
                 "lin1_w": d.linear1.weight, "lin1_b": d.linear1.bias, "lin2_w": d.linear2.weight, "lin2_b": d.linear2.bias,
                 "n1_w": d.norm1.weight, "n1_b": d.norm1.bias, "n2_w": d.norm2.weight, "n2_b": d.norm2.bias,
                 "n3_w": d.norm3.weight, "n3_b": d.norm3.bias, "fb_w": wc, "fb_b": bc,
-                "obj_w": self.obj_vector.weight, "pe": self.PPE.pe,
+                "obj_w": self.obj_vector.weight, "pe": self.PPE.pe, "fold_w": fold_w, "fold_pe": fold_pe,
             }
             for k_, v_ in keep.items():
                 if not v_.is_contiguous():
@@ -676,6 +683,7 @@ class Faceformer(_A2FModule):
                 ops.pack_posconv_weight(pz.original0.detach().reshape(-1), pz.original1.detach(), dt, out=P["pos_w"])
                 ops.pack_feedback(self.vertice_map.weight.detach(), self.vertice_map.bias.detach(),
                                   self.vertice_map_r.weight.detach(), self.vertice_map_r.bias.detach(), out=(wc, bc))
+                ops.pack_decoder_fold(d.self_attn.in_proj_weight.detach(), wc, self.PPE.pe.detach(), self.period, fold_w, fold_pe)
 
             for p_ in (self.vertice_map.weight, self.vertice_map_r.weight, pz.original0, pz.original1):
                 if not p_.is_contiguous():

@@ -55,7 +55,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
          a_row_stride: Optional[int] = None, a_batch_stride: int = 0, rows_per_batch: Optional[int] = None,
          N: Optional[int] = None, ldw: Optional[int] = None, ldc: Optional[int] = None, c_batch_stride: int = 0,
          c_offset: int = 0, a_rows: int = 0, segs=None, resid_mode: int = 0, ldr: Optional[int] = None,
-         r_batch_stride: int = 0, r_offset: int = 0, alg_K: Optional[int] = None) -> torch.Tensor:
+         r_batch_stride: int = 0, r_offset: int = 0, alg_K: Optional[int] = None,
+         out2: Optional[torch.Tensor] = None, ldc2: Optional[int] = None) -> torch.Tensor:
     """out[m,n] = act(sum_k a[m,k] w[n,k] + bias[n]) + resid[m,n] + tmpl[m // rows_per_tmpl, n]  (a2f_gemm)."""
     _dev(a, w, out, bias, resid, tmpl)
     lib = L.load()
@@ -85,6 +86,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     g.C, g.c_dtype = out.data_ptr() + int(c_offset) * out.element_size(), _dt(out)
     g.ldc = int(ldc if ldc is not None else out.stride(0))
     g.c_batch_stride = int(c_batch_stride)
+    if out2 is not None:                       # out = pre-activation z, out2 = act(z) (tcgen05 pair kernel, a2f.h C2)
+        _dev(out2)
+        if out2.dtype != out.dtype:
+            raise L.A2FError("out2 must have the dtype of out")
+        g.C2, g.ldc2 = out2.data_ptr() + int(c_offset) * out2.element_size(), int(ldc2 if ldc2 is not None else g.ldc)
     if bias is not None and bias.dtype != torch.float32:
         raise L.A2FError("bias must be fp32")
     if tmpl is not None and tmpl.dtype != torch.float32:
@@ -104,11 +110,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
 
 
 def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: torch.Tensor, gamma: torch.Tensor,
-            beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+            beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5, pre_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = LayerNorm(a @ w^T + bias + resid) * gamma + beta in one tcgen05 kernel (a2f_gemm_ln): bf16 [M,K] x [N,K],
-    N in {256, 512, 768}; the pre-LayerNorm sum stays in tensor memory (fp32)."""
-    _dev(a, w, bias, resid, gamma, beta, out)
-    for t in (a, w, resid, out):
+    N in {256, 512, 768}; the pre-LayerNorm sum stays in tensor memory (fp32).  pre_out (training): also store that sum as
+    bf16 [M,N] for the LayerNorm backward."""
+    _dev(a, w, bias, resid, gamma, beta, out, pre_out)
+    for t in (a, w, resid, out) + ((pre_out,) if pre_out is not None else ()):
         if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
             raise L.A2FError("gemm_ln takes 2-D bf16 operands with unit column stride")
     M, K = a.shape
@@ -120,7 +127,8 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resi
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
     L.check(lib.a2f_gemm_ln(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.ptr(bias), resid.data_ptr(), resid.stride(0),
-                            gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(), out.stride(0), M, N, K, _stream()),
+                            gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(), out.stride(0), L.ptr(pre_out),
+                            pre_out.stride(0) if pre_out is not None else 0, M, N, K, _stream()),
             "a2f_gemm_ln")
     if PROFILE is not None:
         e.record()
@@ -206,6 +214,28 @@ def voca_loss_bwd(pred: torch.Tensor, gt: torch.Tensor, rows: int, v3: int, k_re
     L.check(L.load().a2f_voca_loss_bwd(pred.data_ptr(), gt.data_ptr(), rows, v3, k_rec, k_vel, L.ptr(gscale),
                                        dpred.data_ptr(), _stream()), "a2f_voca_loss_bwd")
     return dpred
+
+
+def vertex_head_loss(z3: torch.Tensor, w3: torch.Tensor, bias: Optional[torch.Tensor], tmpl: Optional[torch.Tensor],
+                     rows_per_tmpl: int, gt: torch.Tensor, dy: torch.Tensor, k_rec: float = 1.0, k_vel: float = 10.0,
+                     pred: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Vertex head + VocaLoss in one pass (a2f_vertex_head_loss): z3 [rows,192] / w3 [V3,192] bf16x3 splits, gt [rows,V3] fp32,
+    dy [rows, ld >= V3] bf16 receives d loss / d y (pad columns untouched).  -> out3 = (loss, rec, vel)."""
+    _dev(z3, w3, bias, tmpl, gt, dy, pred, ws)
+    rows, V3 = gt.shape
+    if z3.dtype != torch.bfloat16 or w3.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16 or gt.dtype != torch.float32:
+        raise L.A2FError("vertex_head_loss: z3 / w3 / dy bf16, gt fp32")
+    if not (z3.is_contiguous() and w3.is_contiguous() and gt.is_contiguous()) or dy.stride(1) != 1 or z3.shape[0] != rows \
+            or w3.shape[0] != V3 or dy.shape[0] != rows or z3.shape[1] != w3.shape[1]:
+        raise L.A2FError("vertex_head_loss: shape / layout mismatch")
+    lib = L.load()
+    if ws is None:
+        ws = torch.empty((lib.a2f_vertex_head_loss_workspace_bytes() + 7) // 8, dtype=torch.float64, device=gt.device)
+    out3 = torch.empty(3, dtype=torch.float32, device=gt.device)
+    L.check(lib.a2f_vertex_head_loss(z3.data_ptr(), w3.data_ptr(), z3.shape[1], L.ptr(bias), L.ptr(tmpl), int(rows_per_tmpl),
+                                     gt.data_ptr(), rows, V3, float(k_rec), float(k_vel), L.ptr(pred), dy.data_ptr(), dy.stride(0),
+                                     out3.data_ptr(), ws.data_ptr(), ws.numel() * 8, _stream()), "a2f_vertex_head_loss")
+    return out3
 
 
 def split_bf16x3(x: torch.Tensor, is_weight: bool) -> torch.Tensor:
@@ -404,6 +434,16 @@ def pack_feedback(vm_w, vm_b, vmr_w, vmr_b, out=None):
     L.check(L.load().a2f_pack_feedback(vm_w.data_ptr(), vm_b.data_ptr(), vmr_w.data_ptr(), vmr_b.data_ptr(),
                                        vmr_w.shape[0], wc.data_ptr(), bc.data_ptr(), _stream()), "a2f_pack_feedback")
     return wc, bc
+
+
+def pack_decoder_fold(sa_in_w: torch.Tensor, wc: torch.Tensor, pe: torch.Tensor, period: int, fold_w: torch.Tensor,
+                      fold_pe: torch.Tensor) -> None:
+    """fold_w [192,64] = in_proj @ Wc, fold_pe [period,192] = pe @ in_proj^T (a2f_pack_decoder_fold; run after pack_feedback)."""
+    _dev(sa_in_w, wc, pe, fold_w, fold_pe)
+    if tuple(fold_w.shape) != (192, 64) or tuple(fold_pe.shape) != (period, 192) or pe.reshape(-1).numel() < period * 64:
+        raise L.A2FError("pack_decoder_fold: shape mismatch")
+    L.check(L.load().a2f_pack_decoder_fold(sa_in_w.data_ptr(), wc.data_ptr(), pe.data_ptr(), int(period), fold_w.data_ptr(),
+                                           fold_pe.data_ptr(), _stream()), "a2f_pack_decoder_fold")
 
 
 def pack_cross_attention(in_proj_w, in_proj_b, out_w, out_b, afm_w, afm_b, W: torch.Tensor, b: torch.Tensor) -> None:
@@ -718,10 +758,18 @@ def mha_bwd(qkv, out, dout, lse, B, T, H=12, D=64, scale=0.125, out_f32: Optiona
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
-    """fused Adam (+ L2 weight decay) over flat fp32 buffers; `g` fp32, or bf16 as it comes off a bf16 all-reduce."""
+    """fused Adam (+ L2 weight decay) over flat fp32 buffers; `g` fp32, or bf16 as it comes off a bf16 all-reduce.
+    `step`: the step count t >= 1 as an int, or a 1-element int32 CUDA tensor holding it (graph-capturable form)."""
     _dev(p, g, m, v)
     if g.numel() != p.numel():
         raise L.A2FError("adam_step: gradient and parameter buffers differ in length")
+    if isinstance(step, torch.Tensor):
+        _dev(step)
+        if step.dtype != torch.int32 or step.numel() != 1 or g.dtype not in (torch.bfloat16, torch.float32):
+            raise L.A2FError("adam_step: device step counter must be one int32; gradient fp32 or bf16")
+        L.check(L.load().a2f_adam_step_dev(p.data_ptr(), g.data_ptr(), _dt(g), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1,
+                                           beta2, eps, weight_decay, step.data_ptr(), grad_scale, _stream()), "a2f_adam_step_dev")
+        return
     fn = L.load().a2f_adam_step_bf16g if g.dtype == torch.bfloat16 else L.load().a2f_adam_step
     if g.dtype not in (torch.bfloat16, torch.float32):
         raise L.A2FError("adam_step: gradient must be fp32 or bf16")

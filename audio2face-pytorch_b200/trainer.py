@@ -209,6 +209,10 @@ class FaceformerTrainer:
         self.flat.broadcast_params(0, group)
         self.flat.bump_versions()
         self._ws = None
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.flat.params.device)
+        self.fuse_loss = True          # bf16 path: vertex head + losses in one kernel (False = head, loss_fwd, loss_bwd, cast)
+        self._dy = None
+        self._ws_head = None
 
     # -- one optimisation step -------------------------------------------------------------------------------------
     def forward_backward(self, audio, one_hot, template, gt) -> torch.Tensor:
@@ -221,6 +225,29 @@ class FaceformerTrainer:
         one_hot = one_hot.reshape(B, -1).contiguous().float()
         tmpl = template.reshape(B, -1).contiguous().float()
         self.flat.zero_grads()
+        hook = (lambda st: self.flat.all_reduce_stage(st, self.group)) if (self.overlap and _world() > 1) else None
+        T = audio.shape[1] * self.fps // 16000
+        if self.fuse_loss and m.precision == "bf16" and T >= 2 and T % 2 == 0:
+            # tensor-core path, even clip length: the vertex head runs with the losses fused into its epilogue
+            # (a2f_vertex_head_loss): gt is read once, dL/dy leaves as bf16 in the layout the backward GEMMs read, the
+            # 60 KB/frame prediction is never written.  (Odd clips drop their last frame from the loss, ref loss.py:12-15,
+            # and take the unfused path below.)
+            with torch.no_grad():
+                _, tape = training.forward_train(m, audio, one_hot, tmpl, self.fps, with_head=False)
+                V3, M = m.vertice_dim, B * T
+                g = gt.reshape(M, V3)
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = g.contiguous().float()
+                if self._dy is None or tuple(self._dy.shape) != (M, training.V3PAD):
+                    self._dy = torch.zeros((M, training.V3PAD), dtype=torch.bfloat16, device=audio.device)   # pad columns stay 0
+                if self._ws_head is None:
+                    n = L.load().a2f_vertex_head_loss_workspace_bytes()
+                    self._ws_head = torch.empty((n + 7) // 8, dtype=torch.float64, device=audio.device)
+                z3 = ops.split_bf16x3(tape["D"].view(M, 64), False)
+                out3 = ops.vertex_head_loss(z3, m._head_operand(m.vertice_map_r.weight, 64), m.vertice_map_r.bias.detach(), tmpl, T,
+                                            g, self._dy, 1.0, 10.0, ws=self._ws_head)
+                training.backward(m, tape, None, on_ready=hook, dYb=self._dy)
+            return out3
         with torch.no_grad():
             out, tape = training.forward_train(m, audio, one_hot, tmpl, self.fps)
             T, V3 = out.shape[1], m.vertice_dim
@@ -243,7 +270,6 @@ class FaceformerTrainer:
                 dfull = torch.zeros((B, T, V3), dtype=torch.float32, device=audio.device)
                 dfull[:, :Te] = dpred
                 dpred = dfull
-            hook = (lambda st: self.flat.all_reduce_stage(st, self.group)) if (self.overlap and _world() > 1) else None
             training.backward(m, tape, dpred, on_ready=hook)
         return out3
 
@@ -251,8 +277,10 @@ class FaceformerTrainer:
         from . import ops
         self.flat.finish_all_reduce(self.group)
         self.steps += 1
+        # the step count lives on the device (incremented on the stream) so that the whole step can be replayed as a graph
+        self._step_dev.add_(1)
         ops.adam_step(self.flat.params, self.flat.reduced_grads(), self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
-                      self.betas[1], self.eps, self.weight_decay, self.steps, grad_scale=1.0 / _world())
+                      self.betas[1], self.eps, self.weight_decay, self._step_dev, grad_scale=1.0 / _world())
         self.flat.bump_versions()
 
     def wire_description(self) -> str:
@@ -270,6 +298,46 @@ class FaceformerTrainer:
         """batch keys as produced by the reference's dataset (ref:src/dataset/vocaset.py:72-77)."""
         verts, tmpl = batch["verts"] * 100, batch["template_vert"] * 100        # ref lightning_model.py:145-148
         return self.step(batch["audio"], batch["one_hot"], tmpl, verts)
+
+    def graphed(self, audio, one_hot, template, gt) -> "GraphedTrainStep":
+        """Capture one whole optimisation step for these shapes as a CUDA graph (see GraphedTrainStep)."""
+        return GraphedTrainStep(self, audio, one_hot, template, gt)
+
+
+class GraphedTrainStep:
+    """One FaceformerTrainer.step -- weight re-packing, forward, fused head + loss, backward, the bucketed gradient
+    all-reduce and the fused Adam update -- captured as ONE CUDA graph for fixed shapes.  A step is ~330 launches of mostly
+    small kernels; replaying the graph takes the Python / ctypes launch path (15-25 us per launch on the host) off the
+    critical path.  Call it like `step`: inputs are copied into the captured buffers; the returned loss tensors are the
+    captured outputs (overwritten by the next replay).  Requirements: eval-mode arithmetic (no host-side SpecAugment draw
+    inside the step) and shapes equal to the captured ones."""
+
+    def __init__(self, trainer: "FaceformerTrainer", audio, one_hot, template, gt, warmup: int = 2):
+        from . import training
+        if training.spec_augment_active(trainer.model):
+            raise L.A2FError("GraphedTrainStep: SpecAugment draws its mask on the host every step; capture needs it off")
+        self.trainer = trainer
+        self.static_in = [audio.clone(), one_hot.clone(), template.clone(), gt.clone()]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):          # allocator pools, packed-operand caches, NCCL channels
+                trainer.step(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.load().a2f_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.static_out = trainer.step(*self.static_in)
+        self.launches_per_replay = int(L.load().a2f_launch_count() - n0)
+
+    def __call__(self, audio, one_hot, template, gt) -> Dict[str, torch.Tensor]:
+        for dst, src in zip(self.static_in, (audio, one_hot, template, gt)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.trainer.steps += 1                      # host-side bookkeeping; the Adam kernel reads the device-side counter
+        return self.static_out
 
 
 class ConvModelTrainer:

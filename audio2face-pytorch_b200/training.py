@@ -16,7 +16,7 @@ parameter gradients.
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
@@ -169,8 +169,9 @@ def packed_backward_weights(model) -> Dict:
 # ---------------------------------------------------------------------------------------------------------------
 # forward with tape
 # ---------------------------------------------------------------------------------------------------------------
-def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch.Tensor, fps: int):
-    """Same arithmetic as Faceformer.forward; returns (out [B,T,5023,3] fp32, tape)."""
+def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch.Tensor, fps: int, with_head: bool = True):
+    """Same arithmetic as Faceformer.forward; returns (out [B,T,5023,3] fp32, tape).  with_head=False stops at the decoder
+    states (tape["D"]) and returns out = None: the caller runs the vertex head fused with the loss (ops.vertex_head_loss)."""
     P = model._packed()
     bf = model.precision == "bf16"
     dt = torch.bfloat16 if bf else torch.float32
@@ -190,9 +191,15 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
     for i, k in enumerate((3, 3, 3, 3, 2, 2)):
         L_out = (L_in - k) // 2 + 1
         z = torch.empty((B, L_out, 512), dtype=dt, device=dev)
-        ops.gemm(x, P["convs"][i], z, backend=be, M=B * L_out, K=k * 512, a_row_stride=1024, a_batch_stride=L_in * 512,
-                 rows_per_batch=L_out, ldc=512)
-        y = ops.act_fwd(z, GELU, out=ops.padded_rows(B, L_out, 512, dt, dev))     # read by the next layer's wgrad
+        y = ops.padded_rows(B, L_out, 512, dt, dev)                               # read by the next layer's wgrad
+        if bf and L_out > 128:
+            # tensor-core path: ONE launch writes the pre-activation z (kept for the GELU backward) and gelu(z)
+            ops.gemm(x, P["convs"][i], z, act=GELU, out2=y, backend=be, M=B * L_out, K=k * 512, a_row_stride=1024,
+                     a_batch_stride=L_in * 512, rows_per_batch=L_out, ldc=512)
+        else:
+            ops.gemm(x, P["convs"][i], z, backend=be, M=B * L_out, K=k * 512, a_row_stride=1024, a_batch_stride=L_in * 512,
+                     rows_per_batch=L_out, ldc=512)
+            ops.act_fwd(z, GELU, out=y)
         Z.append(z)
         A.append(y)
         x, L_in = y, L_out
@@ -215,6 +222,7 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
     ops.layernorm(pre, ae.encoder.layer_norm.weight.detach(), ae.encoder.layer_norm.bias.detach(), h)
     tp.update(xi=xi, h0=h0, pc=pc, pre=pre)
     layers = []
+    fuse_ln = bf and getattr(model, "fuse_layernorm", True)
     for blk, W in zip(ae.encoder.layers, P["layers"]):
         s = {"h_in": h}
         qkv = torch.empty((M, 2304), dtype=dt, device=dev)
@@ -224,16 +232,28 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
         att32 = torch.empty((M, 768), dtype=torch.float32, device=dev) if bf else None
         ops.mha_lse(qkv, att, lse, B, T, out_f32=att32)
         pre1 = torch.empty((M, 768), dtype=dt, device=dev)
-        ops.gemm(att, W["o_w"], pre1, bias=blk.attention.out_proj.bias.detach(), resid=h, backend=be)
         h1 = torch.empty((M, 768), dtype=dt, device=dev)
-        ops.layernorm(pre1, blk.layer_norm.weight.detach(), blk.layer_norm.bias.detach(), h1)
+        if fuse_ln:      # LayerNorm in the GEMM epilogue; the pre-LN sum is written once (bf16) for the backward
+            ops.gemm_ln(att, W["o_w"], blk.attention.out_proj.bias.detach(), h, blk.layer_norm.weight.detach(),
+                        blk.layer_norm.bias.detach(), h1, pre_out=pre1)
+        else:
+            ops.gemm(att, W["o_w"], pre1, bias=blk.attention.out_proj.bias.detach(), resid=h, backend=be)
+            ops.layernorm(pre1, blk.layer_norm.weight.detach(), blk.layer_norm.bias.detach(), h1)
         fpre = torch.empty((M, 3072), dtype=dt, device=dev)
-        ops.gemm(h1, W["f1_w"], fpre, bias=blk.feed_forward.intermediate_dense.bias.detach(), backend=be)
-        f = ops.act_fwd(fpre, GELU)
+        if bf and M > 128:
+            f = torch.empty((M, 3072), dtype=dt, device=dev)
+            ops.gemm(h1, W["f1_w"], fpre, bias=blk.feed_forward.intermediate_dense.bias.detach(), act=GELU, out2=f, backend=be)
+        else:
+            ops.gemm(h1, W["f1_w"], fpre, bias=blk.feed_forward.intermediate_dense.bias.detach(), backend=be)
+            f = ops.act_fwd(fpre, GELU)
         pre2 = torch.empty((M, 768), dtype=dt, device=dev)
-        ops.gemm(f, W["f2_w"], pre2, bias=blk.feed_forward.output_dense.bias.detach(), resid=h1, backend=be)
         h = torch.empty((M, 768), dtype=dt, device=dev)
-        ops.layernorm(pre2, blk.final_layer_norm.weight.detach(), blk.final_layer_norm.bias.detach(), h)
+        if fuse_ln:
+            ops.gemm_ln(f, W["f2_w"], blk.feed_forward.output_dense.bias.detach(), h1, blk.final_layer_norm.weight.detach(),
+                        blk.final_layer_norm.bias.detach(), h, pre_out=pre2)
+        else:
+            ops.gemm(f, W["f2_w"], pre2, bias=blk.feed_forward.output_dense.bias.detach(), resid=h1, backend=be)
+            ops.layernorm(pre2, blk.final_layer_norm.weight.detach(), blk.final_layer_norm.bias.detach(), h)
         s.update(qkv=qkv, att=att, att32=att32, lse=lse, pre1=pre1, h1=h1, fpre=fpre, f=f, pre2=pre2)
         layers.append(s)
     tp["layers"], tp["hs"] = layers, h
@@ -241,6 +261,8 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
     ops.gemm(h, P["afm_w"], memory, bias=model.audio_feature_map.bias.detach(), backend=be)
     D, dtape = ops.decoder_rollout_train(P["dec"][0], memory, one_hot, model.period, B, T)
     tp["memory"], tp["D"], tp["dtape"] = memory, D, dtape
+    if not with_head:
+        return None, tp
     out = model._vertex_head(D.view(M, 64), model.vertice_map_r.weight, model.vertice_map_r.bias, tmpl, T, 64)
     return out.view(B, T, -1, 3), tp
 
@@ -248,8 +270,9 @@ def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch
 # ---------------------------------------------------------------------------------------------------------------
 # backward
 # ---------------------------------------------------------------------------------------------------------------
-def backward(model, tp: Dict, dout: torch.Tensor, on_ready=None) -> None:
-    """dout: dL/d(out) [B,T,5023,3] fp32.  Accumulates dL/d(parameter) into every parameter's .grad.
+def backward(model, tp: Dict, dout: Optional[torch.Tensor], on_ready=None, dYb: Optional[torch.Tensor] = None) -> None:
+    """dout: dL/d(out) [B,T,5023,3] fp32 -- or, on the bf16 path, dYb: the same gradient already as bf16 [B*T, V3PAD] with
+    zero pad columns (what the fused head + loss epilogue writes).  Accumulates dL/d(parameter) into every parameter's .grad.
 
     on_ready(stage): called (host side, after the stage's kernels are enqueued) when every gradient of a stage is
     final -- stage 0 = vertex head + decoder + audio_feature_map, 1..12 = encoder layers 11..0, 13 = the rest (the
@@ -263,21 +286,28 @@ def backward(model, tp: Dict, dout: torch.Tensor, on_ready=None) -> None:
     ae = model.audio_encoder
     B, N, T = tp["B"], tp["N"], tp["T"]
     M = B * T
-    dev = dout.device
     V3 = model.vertice_dim
-    dY32 = dout.reshape(M, V3)
-    if not dY32.is_contiguous():
-        dY32 = dY32.contiguous()
     D = tp["D"].view(M, 64)
+    dev = D.device
     dtape = tp["dtape"]
     wr, br = model.vertice_map_r.weight, model.vertice_map_r.bias
     wm, bm = model.vertice_map.weight, model.vertice_map.bias
 
     # ---- vertex head: Y = D Wr^T + br + template ----
-    ops.colsum(dY32, _grad(br))
+    if dYb is not None:
+        if not bf or tuple(dYb.shape) != (M, V3PAD) or dYb.dtype != torch.bfloat16:
+            raise L.A2FError("backward: dYb is the bf16 path's [B*T, V3PAD] gradient")
+        ops.colsum(dYb, _grad(br), cols=V3)
+        dY32 = None
+    else:
+        dY32 = dout.reshape(M, V3)
+        if not dY32.is_contiguous():
+            dY32 = dY32.contiguous()
+        ops.colsum(dY32, _grad(br))
     gD = torch.empty((M, 64), dtype=torch.float32, device=dev)
     if bf:
-        dYb = ops.cast_rows(dY32, torch.bfloat16, V3PAD)
+        if dYb is None:
+            dYb = ops.cast_rows(dY32, torch.bfloat16, V3PAD)
         Db = ops.cast_rows(D, torch.bfloat16, 64)
         ops.gemm_wgrad(dYb, Db, _grad(wr), backend=be, N=V3)
         ops.gemm(dYb, PB["head_t"], gD, backend=be)

@@ -293,7 +293,8 @@ def workload_config(args):
                 "stochastic_ops": "off (dropout / LayerDrop / SpecAugment; eval-mode arithmetic, DESIGN.md)",
                 "weights": "random-init (oracle.weights seed 13, heads de-zeroed)",
                 "l2": "flushed between timed steps (256 MiB device memset outside the per-step event pairs)",
-                "template_units": "centimetres (x100, ref lightning_model.py:145-148)", "launch": "eager"}
+                "template_units": "centimetres (x100, ref lightning_model.py:145-148)",
+                "launch": "eager" if args.no_graph else "one CUDA graph per optimisation step (the line's `launch` says if capture fell back)"}
     if args.workload == "audio2mesh":
         return {"workload": f"audio2mesh_inference_b{args.batch}_windows (BASELINE.json configs[1])", "batch_per_gpu": args.batch,
                 "window": "52 x 32 MFCC", "vertices": 5023, "weights": "random-init (oracle.weights seed 12, randomised BatchNorm stats)",
@@ -590,12 +591,13 @@ def run_ours(args, ctx):
         # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's tcgen05 GEMM launches)
         # from the committed ncu pass of this same shape; null for any other shape
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic_infer.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic_infer.json")
         if os.path.exists(tpath) and B == 32 and args.fps == 30 and args.seconds == 5.0:
             tj = json.load(open(tpath))
             traffic = tj["gemm_tc_all"]["dram_bytes_per_launch"]
-            traffic_src = "profiles/r1_traffic_infer.json (bytes per launch, mean over %d launches)" % tj["gemm_tc_all"]["launches"]
-        roofline = {"bound": "tensor", "kernel": "a2f::gemm_tc2_kernel / gemm_tc_kernel (tcgen05/TMEM/TMA GEMMs, all launches of a step)",
+            traffic_src = "profiles/r2_traffic_infer.json (bytes per launch, mean over %d launches)" % tj["gemm_tc_all"]["launches"]
+        roofline = {"bound": "tensor", "kernel": "a2f::gemm_tc2_kernel / gemm_ln_kernel / gemm_tc_kernel / posconv_tc_kernel (tcgen05/TMEM/TMA "
+                                                 "GEMMs incl. the LayerNorm-fused ones, all launches of a step)",
                     "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"] + ", sustained bf16",
                     "launches_per_step": len(gem) // 2, "kernel_share_of_step": (g_time / 2) / (dev_s / args.steps),
@@ -778,10 +780,21 @@ def run_train(args, ctx):
         parity = train_parity(args, l_gpu, h_in)
 
     n0 = lib.a2f_launch_count()
-    loss0 = trainer.step(*d_in)["loss"]
+    loss0 = float(trainer.step(*d_in)["loss"])
     launches_per_step = int(lib.a2f_launch_count() - n0)
+    # the product's fixed-shape fast path: the whole optimisation step (re-pack, forward, fused head + loss, backward, gradient
+    # all-reduce, Adam) captured as ONE CUDA graph (trainer.GraphedTrainStep); --no-graph = eager launches
+    step_fn, launch_mode = trainer.step, "eager"
+    if not args.no_graph:
+        try:
+            gstep = trainer.graphed(*d_in)
+            step_fn, launch_mode = gstep, "one CUDA graph per optimisation step (trainer.GraphedTrainStep)"
+            launches_per_step = gstep.launches_per_replay
+        except Exception as exc:  # noqa: BLE001
+            launch_mode = f"eager (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
+            torch.cuda.synchronize()
     for _ in range(max(3, args.warmup) - 1):
-        trainer.step(*d_in)
+        step_fn(*d_in)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -791,7 +804,7 @@ def run_train(args, ctx):
     for s, e in ev:
         flush.zero_()
         s.record()
-        out = trainer.step(*d_in)
+        out = step_fn(*d_in)
         e.record()
     barrier()
     dev_s = sum(s.elapsed_time(e) for s, e in ev) * 1e-3
@@ -825,7 +838,7 @@ def run_train(args, ctx):
         if i + 1 < args.steps:
             upload(slot ^ 1)
         comp.wait_event(up_done[slot])
-        o = trainer.step(*d_buf[slot])
+        o = step_fn(*d_buf[slot])
         consumed[slot].record(comp)
         h_loss.copy_(torch.stack([o["loss"], o["rec_loss"], o["vel_loss"]]), non_blocking=True)
     t1.record()
@@ -876,6 +889,7 @@ def run_train(args, ctx):
                 "note": "pinned host batch (audio, one-hot, template, ground-truth vertices) in, loss scalars out; the upload of step i+1 overlaps step i (copy stream, double-buffered device batch)"},
         "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "loss_first_step": float(loss0), "loss_last_timed_step": loss_last, "parity": parity, "gradient_exchange": comm,
+        "launch": launch_mode,
     }
     return line
 

@@ -98,6 +98,10 @@ typedef struct a2f_gemm_args {
     int resid_mode;           /* A2F_RESID_ADD (default), or A2F_RESID_DACT: resid holds the forward PRE-activation z and
                                  the result is multiplied by act'(z) (act = the forward activation; bias is ignored):
                                  fuses the activation backward into the data-gradient GEMM */
+    void* C2;                 /* optional second output (tcgen05 CTA-pair kernel, 16-byte aligned bf16/fp32 like C, no resid / tmpl):
+                               * C receives the PRE-activation z = A W^T + bias, C2 receives act(z) -- the forward of a training
+                               * step keeps z for the activation backward and feeds act(z) to the next GEMM, in one pass */
+    long long ldc2;           /* row stride of C2 in elements (batch stride: c_batch_stride scaled by ldc2 / ldc) */
 } a2f_gemm_args;
 
 #define A2F_RESID_ADD 0
@@ -134,10 +138,12 @@ typedef struct a2f_wgrad_args {
  * modeling_wav2vec2.py:576-609, which ref:src/model/wav2vec.py:174-180 runs 12 times per forward.  One thread-block
  * cluster of N/256 CTA pairs holds a whole 256-row block; row statistics travel through distributed shared memory and
  * the pre-LayerNorm sum stays in tensor memory (fp32, never rounded).  A [M,K], W [N,K], resid / out [M,N] bf16 with row
- * strides lda / ldw / ldr / ldo (elements, multiples of 8); N in {256, 512, 768}; bias may be NULL. */
+ * strides lda / ldw / ldr / ldo (elements, multiples of 8); N in {256, 512, 768}; bias may be NULL.
+ * pre_out (may be NULL): training -- also store the pre-LayerNorm sum (bf16 [M,N], row stride ldp), the input of
+ * a2f_layernorm_bwd. */
 int a2f_gemm_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* resid,
-                long long ldr, const float* gamma, const float* beta, float eps, void* out, long long ldo, int M, int N,
-                int K, void* stream);
+                long long ldr, const float* gamma, const float* beta, float eps, void* out, long long ldo, void* pre_out,
+                long long ldp, int M, int N, int K, void* stream);
 
 /* != 0: segment s reads rows r + x_row_off[0] + s*x_row_step, columns x_col_off[0].. (the 128
                            taps of the positional conv); the table entries 1..3 are ignored */
@@ -249,6 +255,8 @@ typedef struct a2f_decoder_weights {
     const float* fb_b;  /* [64] bc */
     const float* obj_w; /* [64,n_onehot] obj_vector.weight (no bias) */
     const float* pe;    /* [period,64] first period rows of PPE.pe */
+    const float* fold_w;  /* [192,64]      self_attn.in_proj_weight @ Wc          (a2f_pack_decoder_fold) */
+    const float* fold_pe; /* [period,192]  pe[pos] @ self_attn.in_proj_weight^T   (a2f_pack_decoder_fold) */
 } a2f_decoder_weights;
 
 size_t a2f_decoder_workspace_bytes(int B, int T);
@@ -312,6 +320,12 @@ int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, 
  *   W[64,Kin] = wo wv wa,  b[64] = wo (wv ba + bv) + bo
  * wv / bv: rows 128..191 of multihead_attn.in_proj_{weight,bias}; wo / bo: multihead_attn.out_proj; wa [64,Kin] / ba:
  * audio_feature_map.  W is written as fp32 or bf16 (w_dtype). */
+/* The feedback e_{i+1} = Wc d_i + bc + style (+ pe_{i+1}) and the self-attention in-projection of token i+1 are two Linear
+ * layers in a row; the rollout kernels apply them as ONE matvec from d_i.  This packs its operands (fp64 accumulation):
+ *   fold_w[192,64] = sa_in_w @ Wc,   fold_pe[pos,192] = sa_in_w @ pe[pos]  for pos < period.
+ * Call after a2f_pack_feedback (Wc must be current) whenever self_attn.in_proj_weight, vertice_map(_r) or PPE change. */
+int a2f_pack_decoder_fold(const float* sa_in_w, const float* wc, const float* pe, int period, float* fold_w, float* fold_pe,
+                          void* stream);
 int a2f_pack_cross_attention(const float* wv, const float* bv, const float* wo, const float* bo, const float* wa,
                              const float* ba, int Kin, void* W, int w_dtype, float* b, void* stream);
 
@@ -408,6 +422,19 @@ int a2f_voca_loss_bwd(const float* pred, const float* gt, long long rows, int V3
                       const float* gscale /* device scalar d(out)/d(loss), or NULL = 1 */, float* dpred,
                       void* stream);
 
+/* Vertex head with the losses fused into its epilogue (tensor-core path; north_star: "vertex-offset regression Linear ...
+ * fused with the template add and the reconstruction/velocity losses", ref:src/model/faceformer.py:181-188 +
+ * ref:src/loss/loss.py:29-55):
+ *     y = z W^T + bias + tmpl[m / rows_per_tmpl];   out3 = {loss, rec, vel} of (y, gt) as a2f_voca_loss_fwd defines them;
+ *     dy[m, :V3] = d loss / d y  (bf16, row stride ld_dy >= V3; columns >= V3 are left untouched: keep them zero)
+ * z3 [rows, K3] / w3 [V3, K3]: the error-compensated bf16 splits of a2f_split_bf16x3 (K3 = 3 x 64).  gt [rows, V3] fp32 is
+ * read once; y is stored (fp32 [rows, V3]) only when pred != NULL.  rows even (pairs of consecutive frames).  Deterministic:
+ * per-warp fp64 partials in the workspace, summed in a fixed order. */
+size_t a2f_vertex_head_loss_workspace_bytes(void);
+int a2f_vertex_head_loss(const void* z3, const void* w3, int K3, const float* bias, const float* tmpl, int rows_per_tmpl,
+                         const float* gt, long long rows, int V3, float k_rec, float k_vel, float* pred, void* dy_bf16,
+                         long long ld_dy, float* out3, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training step (BASELINE.json configs[3]): the backward pass of the path above.  The reference gets it from
  * torch.autograd over ref:src/model/faceformer.py:139-188 + HF Wav2Vec2Model inside Lightning's training_step
@@ -497,6 +524,11 @@ int a2f_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
  * trainer.FlatBuffers wire="bf16": half the bytes on NVLink; masters, moments and the update stay fp32). */
 int a2f_adam_step_bf16g(float* p, const void* g_bf16, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* same step with the step count t (>= 1) read from DEVICE memory, so that the launch can sit in a captured CUDA graph that is
+ * replayed for every optimisation step (the caller increments *step_dev on the stream before this call); g_dtype A2F_F32 or
+ * A2F_BF16. */
+int a2f_adam_step_dev(float* p, const void* g, int g_dtype, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, const int* step_dev, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * MFCC feature extractor (replaces ref:src/model/extractor.py:10-60 = torchaudio.transforms.MFCC

@@ -71,7 +71,7 @@ def traffic(path, note=""):
         elif metric in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
             k["read" if "read" in metric else "write"] += v * scale
-    gem = [v for n, v in per.items() if "gemm_tc" in n or "posconv_tc" in n]
+    gem = [v for n, v in per.items() if "gemm_tc" in n or "posconv_tc" in n or "gemm_ln" in n]
     tot = sum(v["read"] + v["write"] for v in gem)
     n = sum(v["launches"] for v in gem)
     out = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; "
@@ -96,8 +96,10 @@ def kernel(path):
     hi = next((i for i, r in enumerate(rows) if r and r[0] == "Address"), None)
     if hi is None:
         return
-    hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) == len(rows[hi])]
+    hdr = rows[hi]
     ix = {h: i for i, h in enumerate(hdr)}
+    # a report with several kernels repeats the header row per kernel: keep the data rows only
+    data = [r for r in rows[hi + 1:] if len(r) == len(hdr) and r[ix["# Samples"]].strip().isdigit()]
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
     agg = sorted(((sum(int(r[ix[h]]) for r in data), h) for h in stalls), reverse=True)[:6]

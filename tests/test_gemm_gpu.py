@@ -218,10 +218,13 @@ def test_gemm_ln_fused_epilogue(a2f_lib, dev, M, N, K):
     err = (out.float().cpu() - want).abs()
     tol = 2.0 ** -8 * (want.abs() + 1.0)          # bf16 rounding of the output (2^-9 relative) + fp32 reduction-order noise
     assert bool((err <= tol).all()), (float(err.max()), int((err > tol).sum()))
-    # run to run deterministic (no atomics on the path)
+    # run to run deterministic (no atomics on the path); the training variant also stores the pre-LayerNorm sum
     out2 = torch.empty_like(out)
-    ops.gemm_ln(a.to(dev), w.to(dev), bias.to(dev), resid.to(dev), gamma.to(dev), beta.to(dev), out2)
+    pre = torch.empty_like(out)
+    ops.gemm_ln(a.to(dev), w.to(dev), bias.to(dev), resid.to(dev), gamma.to(dev), beta.to(dev), out2, pre_out=pre)
     assert torch.equal(out, out2)
+    x = a.float() @ w.float().t() + bias + resid.float()
+    assert bool(((pre.float().cpu() - x).abs() <= 2.0 ** -8 * (x.abs() + 1.0)).all())
 
 
 @pytest.mark.parametrize("M,N,K,act,use_resid", [(4800, 3072, 768, 2, False), (4800, 2304, 768, 0, False), (9600, 768, 256, 0, True),

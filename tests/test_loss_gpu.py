@@ -65,3 +65,40 @@ def test_mse_error_any_frame_count(a2f_lib, dev, rows):
     want = orm.mse_error(pred, gt)
     got = modules.mse_error(pred.to(dev), gt.to(dev)).cpu()
     assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))
+
+
+@pytest.mark.parametrize("B,T", [(1, 2), (2, 24), (3, 150)])
+def test_vertex_head_with_fused_loss(a2f_lib, dev, B, T):
+    """a2f_vertex_head_loss (head + template add + rec / vel loss + dL/dy in ONE kernel) vs the separate kernels
+    (a2f_gemm head, a2f_voca_loss_fwd, a2f_voca_loss_bwd) and vs the oracle loss of the same prediction."""
+    from a2f_b200 import ops, lib as L
+    V3, M = 15069, B * T
+    g = torch.Generator().manual_seed(900 + M)
+    z = torch.zeros(M, 64)
+    z[:, :64] = torch.randn(M, 64, generator=g)
+    w = 0.02 * torch.randn(V3, 64, generator=g)
+    bias = 0.01 * torch.randn(V3, generator=g)
+    tmpl = torch.randn(B, V3, generator=g)
+    gt = (tmpl[:, None] + 0.2 * torch.randn(B, T, V3, generator=g)).reshape(M, V3).contiguous()
+    z3, w3 = ops.split_bf16x3(z.to(dev), False), ops.split_bf16x3(w.to(dev), True)
+    # separate kernels
+    pred = torch.empty((M, V3), device=dev)
+    ops.gemm(z3, w3, pred, bias=bias.to(dev), tmpl=tmpl.to(dev), rows_per_tmpl=T, backend=L.TCGEN05, K=192)
+    want3 = ops.voca_loss_fwd(pred, gt.to(dev), M, V3, 1.0, 10.0)
+    dpred = torch.empty_like(pred)
+    ops.voca_loss_bwd(pred, gt.to(dev), M, V3, 1.0, 10.0, None, dpred)
+    # fused
+    dy = torch.zeros((M, 15072), dtype=torch.bfloat16, device=dev)
+    pred2 = torch.empty((M, V3), device=dev)
+    got3 = ops.vertex_head_loss(z3, w3, bias.to(dev), tmpl.to(dev), T, gt.to(dev), dy, 1.0, 10.0, pred=pred2)
+    got3_nopred = ops.vertex_head_loss(z3, w3, bias.to(dev), tmpl.to(dev), T, gt.to(dev), torch.zeros_like(dy), 1.0, 10.0)
+    torch.cuda.synchronize()
+    assert torch.equal(pred2, pred)                                     # same y, bit for bit
+    assert torch.equal(got3, got3_nopred)                               # deterministic, independent of the optional store
+    for j in range(3):
+        assert abs(float(got3[j]) - float(want3[j])) < 2e-6 * abs(float(want3[j]))
+    ref = orm.voca_loss(pred.cpu().view(M, -1, 3), gt.view(M, -1, 3))
+    assert abs(float(got3[0]) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    d = dy[:, :V3].float()
+    assert bool(((d - dpred).abs() <= 2.0 ** -8 * dpred.abs() + 1e-12).all())
+    assert float(dy[:, V3:].abs().max()) == 0.0                         # pad columns untouched
