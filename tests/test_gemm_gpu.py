@@ -251,3 +251,27 @@ def test_tcgen05_pair_kernel_tail_split(a2f_lib, dev, M, N, K, act, use_resid):
     assert torch.equal(outs[0], outs[1])
     want = _ref(a, w, b, act, r)
     assert bool(((outs[0].cpu().double() - want).abs() <= 2.0 ** -8 * (want.abs() + 1.0)).all())
+
+
+@pytest.mark.parametrize("M,N,K,batches", [(2400, 3072, 768, 1), (4800, 3072, 768, 1), (300, 512, 256, 1), (1998, 512, 1536, 2)])
+def test_tcgen05_pair_kernel_two_outputs(a2f_lib, dev, M, N, K, batches):
+    """a2f_gemm_args::C2: one launch writes the pre-activation z = A W^T + b (kept for the activation backward) AND gelu(z)
+    (the operand of the next GEMM).  Must equal the two-launch sequence GEMM + a2f_act_fwd bit for bit."""
+    from a2f_b200 import ops, lib as L
+    a = _rand((M, K), dev, 41, torch.bfloat16)
+    w = _rand((N, K), dev, 42, torch.bfloat16, scale=K ** -0.5)
+    b = _rand((N,), dev, 43)
+    rpb = M // batches
+    kw = dict(M=M, rows_per_batch=rpb, a_batch_stride=rpb * K, c_batch_stride=rpb * N)
+    z1 = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, z1, bias=b, backend=L.TCGEN05, **kw)
+    y1 = ops.act_fwd(z1, L.ACT_GELU)
+    z2, y2 = torch.empty_like(z1), torch.empty_like(z1)
+    ops.gemm(a, w, z2, bias=b, act=L.ACT_GELU, out2=y2, backend=L.TCGEN05, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(z1, z2)
+    # act_fwd applies GELU to the bf16-ROUNDED z, the fused epilogue to the fp32 z: the two bf16 results can sit two ulps apart
+    err = (y1.float() - y2.float()).abs()
+    assert bool((err <= 2.0 ** -6 * (y1.float().abs() + 0.05)).all()), float(err.max())
+    want = _ref(a, w, b, 2)
+    assert bool(((y2.cpu().double() - want).abs() <= 2.0 ** -7 * (want.abs() + 0.05)).all())
