@@ -562,26 +562,33 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                         // consecutive r (slices start on even rows and M is even), so the pair never leaves the thread.
                         // y = W d + b + template is used where it sits in registers: gt is read ONCE, dL/dy leaves as
                         // bf16 in the layout the backward GEMMs read, y itself is stored only on request.
-                        const float* tp = g.tmpl ? g.tmpl + trow0 * (long long)g.N + ncol : nullptr;
-                        int trem = trem0;
                         const float* gp = g.loss_gt + m0w * (long long)g.N + ncol;
                         bf16* dyp = static_cast<bf16*>(g.loss_dy) + m0w * g.ld_dy + ncol;
-                        float racc = 0.f, vacc = 0.f;
-#pragma unroll 4
-                        for (int r = 0; r < 32; r += 2) {
-                            float t0 = 0.f, t1 = 0.f;
-                            if (tp != nullptr) {
-                                if (col_ok && r < rows_left) t0 = __ldg(tp);
-                                if (++trem == g.rows_per_tmpl) { trem = 0; tp += g.N; }
-                                if (col_ok && r + 1 < rows_left) t1 = __ldg(tp);
+                        // all 32 ground-truth values (and the template values) of this lane's column are requested before
+                        // anything is consumed: 64 independent loads in flight per lane instead of 4 dependent rounds
+                        float gv[32], tv[32];
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) gv[r] = (col_ok && r < rows_left) ? __ldg(gp + (long long)r * g.N) : 0.f;
+                        if (g.tmpl != nullptr) {
+                            const float* tp = g.tmpl + trow0 * (long long)g.N + ncol;
+                            int trem = trem0;
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) {
+                                tv[r] = (col_ok && r < rows_left) ? __ldg(tp) : 0.f;
                                 if (++trem == g.rows_per_tmpl) { trem = 0; tp += g.N; }
                             }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) tv[r] = 0.f;
+                        }
+                        float racc = 0.f, vacc = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 32; r += 2) {
                             if (col_ok && r + 1 < rows_left) {
-                                const float y0 = (tr[r * 32 + ((lane + r) & 31)] + bj) + t0;
-                                const float y1 = (tr[(r + 1) * 32 + ((lane + r + 1) & 31)] + bj) + t1;
-                                const float g0 = __ldg(gp + (long long)r * g.N), g1 = __ldg(gp + (long long)(r + 1) * g.N);
-                                const float d0 = y0 - g0, d1 = y1 - g1;
-                                const float dv = (y1 - y0) - (g1 - g0);
+                                const float y0 = (tr[r * 32 + ((lane + r) & 31)] + bj) + tv[r];
+                                const float y1 = (tr[(r + 1) * 32 + ((lane + r + 1) & 31)] + bj) + tv[r + 1];
+                                const float d0 = y0 - gv[r], d1 = y1 - gv[r + 1];
+                                const float dv = (y1 - y0) - (gv[r + 1] - gv[r]);
                                 racc = fmaf(d0, d0, fmaf(d1, d1, racc));
                                 vacc = fmaf(dv, dv, vacc);
                                 dyp[(long long)r * g.ld_dy] = __float2bfloat16_rn(g.c_rec * d0 - g.c_vel * dv);

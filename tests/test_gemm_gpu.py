@@ -274,4 +274,5 @@ def test_tcgen05_pair_kernel_two_outputs(a2f_lib, dev, M, N, K, batches):
     err = (y1.float() - y2.float()).abs()
     assert bool((err <= 2.0 ** -6 * (y1.float().abs() + 0.05)).all()), float(err.max())
     want = _ref(a, w, b, 2)
-    assert bool(((y2.cpu().double() - want).abs() <= 2.0 ** -7 * (want.abs() + 0.05)).all())
+    # vs fp64 erf-GELU: bf16 rounding of the output + the tanh-form GELU of the bf16 path (|tanh form - erf form| <= 4.7e-4)
+    assert bool(((y2.cpu().double() - want).abs() <= 2.0 ** -7 * want.abs() + 2e-3).all())
