@@ -211,7 +211,9 @@ A2F_D void wide_rows(float (&tadd)[WIDE_WR * 4], const float* trw, const float (
     }
 }
 
-template <int BN, typename TC, bool SCALAR>
+// LOSS: the fused vertex-head + loss epilogue (a2f_vertex_head_loss) is its own instantiation, so that its registers and code
+// do not weigh on the inference head (an earlier version shared one kernel: the VOCA head lost 7 % to spills).
+template <int BN, typename TC, bool SCALAR, bool LOSS = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
     constexpr bool WIDE = tc_wide_v<BN, TC, SCALAR>;
@@ -347,7 +349,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         const int e_act = g.act;
         const bool e_dact = g.resid_mode == A2F_RESID_DACT;
         // ---- wide scalar epilogue (vertex heads): this warp owns 32 rows x 128 columns of every tile ----
-        const bool wide = WIDE && g.resid == nullptr && g.act == A2F_ACT_NONE && p.mode != 2 && g.loss_gt == nullptr;
+        const bool wide = !LOSS && WIDE && g.resid == nullptr && g.act == A2F_ACT_NONE && p.mode != 2;
         double loss_rec = 0.0, loss_vel = 0.0;   // fused-loss epilogue: this thread's share of the two sums
         float tadd[WIDE_WR * 4];    // template values of the NEXT WIDE_WR rows x 4 chunks, always in flight
         bool tadd_primed = false;
@@ -556,7 +558,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
                     const int ncol = n_tile0 + c * 32 + lane;
                     const bool col_ok = ncol < n_end;
                     const float bj = (g.bias && col_ok) ? __ldg(g.bias + ncol) : 0.f;
-                    if (SCALAR && g.loss_gt != nullptr) {
+                    if (LOSS && SCALAR) {
                         // ---- vertex head + reconstruction / velocity loss (ref:src/loss/loss.py:29-55) in one pass ----
                         // lane = column, r = row of this warp's 32-row slice; rows (2k, 2k+1) of a velocity pair are
                         // consecutive r (slices start on even rows and M is even), so the pair never leaves the thread.
@@ -687,7 +689,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         if (threadIdx.x == 64) TL_STAMP(6);                                 // all tiles' epilogues issued
         if (!SCALAR && leader) tma_store_wait_all();
         if (threadIdx.x == 64) TL_STAMP(7);                                 // stores drained
-        if (SCALAR && g.loss_partial != nullptr) {
+        if (LOSS && SCALAR && g.loss_partial != nullptr) {
             loss_rec = warp_sum_d(loss_rec);
             loss_vel = warp_sum_d(loss_vel);
             if (lane == 0) {
@@ -1154,10 +1156,10 @@ static int launch_tc2(TmapSet& maps, const TcParams& p_in, cudaStream_t s) {
     return A2F_OK;
 }
 
-template <int BN, typename TC, bool SCALAR>
+template <int BN, typename TC, bool SCALAR, bool LOSS = false>
 static int launch_tc(const TmapSet& maps, const TcParams& p, cudaStream_t s) {
     using Cfg = TcCfg<BN, TC, tc_wide_v<BN, TC, SCALAR>>;
-    auto kern = gemm_tc_kernel<BN, TC, SCALAR>;
+    auto kern = gemm_tc_kernel<BN, TC, SCALAR, LOSS>;
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
         A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -1173,6 +1175,10 @@ static int launch_tc(const TmapSet& maps, const TcParams& p, cudaStream_t s) {
 template <int BN, typename TC>
 static int encode_c_and_launch(TmapSet& maps, const TcParams& p, bool scalar, cudaStream_t s) {
     using Cfg = TcCfg<BN, TC>;
+    if (scalar && p.g.loss_gt != nullptr) {
+        if (BN == 256 && sizeof(TC) == 4) return launch_tc<256, float, true, true>(maps, p, s);
+        return set_error(A2F_EINVAL, "gemm_tc: the fused-loss epilogue is the 256-wide fp32 vertex head only");
+    }
     if (scalar) return launch_tc<BN, TC, true>(maps, p, s);
     const GemmParams& g = p.g;
     const int ncols_total = (p.mode == 2) ? 768 : g.N;
