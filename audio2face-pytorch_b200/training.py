@@ -29,6 +29,7 @@ GELU = L.ACT_GELU
 V3PAD = 15072          # 15069 rounded up to a multiple of 8 (16-byte bf16 rows for TMA)
 
 
+_WARNED_DROPOUT = False
 _GRAD_SINK = None      # set by collect_grads(): id(param) -> buffer the explicit backward accumulates into instead of .grad
 
 
@@ -172,6 +173,15 @@ def packed_backward_weights(model) -> Dict:
 def forward_train(model, audio: torch.Tensor, one_hot: torch.Tensor, tmpl: torch.Tensor, fps: int, with_head: bool = True):
     """Same arithmetic as Faceformer.forward; returns (out [B,T,5023,3] fp32, tape).  with_head=False stops at the decoder
     states (tape["D"]) and returns out = None: the caller runs the vertex head fused with the loss (ops.vertex_head_loss)."""
+    global _WARNED_DROPOUT
+    if model.training and not _WARNED_DROPOUT:
+        # the reference's train() mode also enables dropout 0.1 (PPE, decoder layer, wav2vec2 hidden / activation / attention)
+        # and LayerDrop 0.1; this path applies SpecAugment only.  Said once, loudly, because a drop-in must not hide it.
+        import warnings
+        warnings.warn("a2f_b200 Faceformer in train() mode: SpecAugment is applied like the reference's, but dropout (p=0.1) and "
+                      "LayerDrop are NOT -- the training kernels run eval-mode arithmetic for those ops (INTEGRATION.md 2c)",
+                      RuntimeWarning, stacklevel=3)
+        _WARNED_DROPOUT = True
     P = model._packed()
     bf = model.precision == "bf16"
     dt = torch.bfloat16 if bf else torch.float32
