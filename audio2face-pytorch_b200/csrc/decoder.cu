@@ -78,7 +78,11 @@ template <bool CL> A2F_D float4 ld_kv4(const float* p) {
     return CL ? __ldcg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
 }
 
-template <bool TRAIN, bool CL>
+// debug (a2f_debug_set_decoder_timing): when non-NULL, thread 0 of CTA 0 accumulates the clock64() cycles between the block
+// barriers of a step into [0..4] = attention, out_proj, LN1/LN2/linear1, linear2, LN3/feedback/in-projection; [5] = steps
+__device__ unsigned long long* g_dec_timing_dev = nullptr;
+
+template <bool TRAIN, bool CL, bool TIMING = false>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-attn vectors*/,
                        const float* __restrict__ one_hot, int n_onehot, int period, float* __restrict__ D, int T,
@@ -199,6 +203,10 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
         lnA[0] = w.n3_w[lane]; lnA[1] = w.n3_w[lane + 32]; lnA[2] = w.n3_b[lane]; lnA[3] = w.n3_b[lane + 32];
     }
 
+    unsigned long long* const tl = (TIMING && blockIdx.x == 0 && tid == 0) ? g_dec_timing_dev : nullptr;
+    unsigned long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = (TIMING && tl) ? clock64() : 0;
+#define DEC_TSTAMP(k) do { if (TIMING && tl) { const long long tn = clock64(); tacc[k] += (unsigned long long)(tn - tprev); tprev = tn; } } while (0)
     for (int i = 0; i < T; ++i) {
         // prefetch this step's global operands so that their latency hides behind phases 1-3
         float pre0 = 0.f, pre1 = 0.f;
@@ -245,6 +253,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 sch[n] = s;
                 lmax = fmaxf(lmax, s);
             }
+            DEC_TSTAMP(0);
             const float wmax = warp_max_redux(lmax);                  // -inf when this warp owns no key yet
             float lsum = 0.f;
             for (int n = u; n <= n_max; n += 128) {
@@ -253,6 +262,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 lsum += pj;
             }
             __syncwarp();
+            DEC_TSTAMP(1);
             // P.V over this warp's keys: lane = (key slot kg, 4-wide column group dg); conflict-free float4 reads
             const int kg = lane & 7, dg = lane >> 3;
             float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
@@ -286,7 +296,9 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 red[h * 8 + wq] = wmax;
                 red[h * 8 + 4 + wq] = lsum;
             }
+            DEC_TSTAMP(2);
             named_bar_sync(1 + h, 128);
+            DEC_TSTAMP(3);
             if (CL) {
                 // this rank's (max, sum, unnormalised P.V) of head h -> rank 0's shared memory
                 if (u < 16) {
@@ -331,7 +343,9 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 }
             }
         }
+        DEC_TSTAMP(4);
         __syncthreads();
+        DEC_TSTAMP(5);
 
         // ---------- phase 3: self-attn out_proj + residual ----------
         if (tid >= 192 && tid < 256) {
@@ -341,6 +355,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             if (TRAIN) sv.Y1PRE[((long long)b * T + i) * 64 + r] = yv;
         }
         __syncthreads();
+        DEC_TSTAMP(6);
 
         // ---------- phase 4: LN1, + cross-attention vector, LN2 (each FFN1 warp redundantly), linear1 + ReLU ----------
         if (tid >= 256 && tid < 384) {
@@ -367,6 +382,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             if (TRAIN) sv.HID[((long long)b * T + i) * 128 + (tid - 256)] = hv;
         }
         __syncthreads();
+        DEC_TSTAMP(7);
 
         // ---------- phase 5: linear2 (two half-rows per output) + residual ----------
         if (tid >= 384 && tid < 512) {
@@ -380,6 +396,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             }
         }
         __syncthreads();
+        DEC_TSTAMP(8);
 
         // ---------- phase 6: LN3 -> d_i (warps 0..7, each for itself), store, then IN ONE STEP the next token's
         //            decoder input e_{i+1} + pe (warps 6,7: Wc) and its q | k | v (warps 0..5: in_proj Wc) ----------
@@ -394,6 +411,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 D_b[(long long)i * 64 + lane + 32] = c;
             }
             __syncwarp();
+            DEC_TSTAMP(9);
             if (tid >= 192) {
                 const int r = tid - 192;
                 float f0 = 0.f, f1v = 0.f, f2 = 0.f, f3 = 0.f;
@@ -425,8 +443,15 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 }
             }
         }
+        DEC_TSTAMP(10);
         if (CL) cluster.sync();      // q_{i+1} has landed in every rank's shared memory, K/V row i+1 is visible cluster-wide
         else __syncthreads();
+        DEC_TSTAMP(11);
+    }
+#undef DEC_TSTAMP
+    if (TIMING && tl) {
+        for (int k = 0; k < 12; ++k) tl[k] = tacc[k];
+        tl[12] = (unsigned long long)T;
     }
 }
 
@@ -538,6 +563,7 @@ pack_cross_attention_kernel(const float* __restrict__ wv, const float* __restric
     }
 }
 
+static bool g_dec_timing_on = false;   // debug (a2f_debug_set_decoder_timing): launch the instantiations with cycle counters
 static int g_dec_cluster = 0;      // debug (a2f_debug_set_umma_field 8): 0 = automatic, 1 = never, 2/4/8 = forced cluster size
 void set_dec_cluster(int v) { g_dec_cluster = v; }
 
@@ -690,8 +716,13 @@ static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memor
         A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, dw, ca_use, one_hot, n_onehot, period, D, T, kv, none));
     } else if (saves == nullptr) {
         DecSaves none = {};
+        if (g_dec_timing_on) {      // debug instantiation with the per-phase cycle counters (tools/decoder_phases.py)
+            A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false, false, true>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca_use, one_hot, n_onehot, period, D, T, kv, none));
+        } else {
         A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca_use, one_hot, n_onehot, period, D, T, kv, none));
+        }
     } else {
         DecSaves sv;
         const size_t bt = (size_t)B * T;
@@ -702,8 +733,13 @@ static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memor
         sv.Y2PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y2PRE); sv.Y2 = f + bt * a2f_decoder_save_offset(A2F_DEC_Y2);
         sv.HID = f + bt * a2f_decoder_save_offset(A2F_DEC_HID); sv.Y3PRE = f + bt * a2f_decoder_save_offset(A2F_DEC_Y3PRE);
         sv.LSE = f + bt * a2f_decoder_save_offset(A2F_DEC_LSE);
+        if (g_dec_timing_on) {
+            A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<true, false, true>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca_use, one_hot, n_onehot, period, D, T, kv, sv));
+        } else {
         A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<true, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca_use, one_hot, n_onehot, period, D, T, kv, sv));
+        }
     }
     A2F_CHECK_LAUNCH("decoder_rollout_kernel");
     count_launch();
@@ -724,6 +760,14 @@ int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, 
     pack_feedback_kernel<<<dim3(FB_SPLIT, 64), 256, 0, as_stream(stream)>>>(vm_w, vm_b, vmr_w, vmr_b, V3, Wc, bc);
     A2F_CHECK_LAUNCH("pack_feedback_kernel");
     count_launch();
+    return A2F_OK;
+}
+
+int a2f_debug_set_decoder_timing(void* dev_ptr) {
+    unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
+    g_dec_timing_on = p != nullptr;
+    cudaError_t e = cudaMemcpyToSymbol(g_dec_timing_dev, &p, sizeof(p));
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemcpyToSymbol(g_dec_timing_dev)");
     return A2F_OK;
 }
 

@@ -138,6 +138,7 @@ _SIGNATURES = {
                                      c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_size_t, c_void_p]),
     "a2f_debug_set_umma_field": (c_int, [c_int, C.c_uint]),
     "a2f_debug_set_timeline": (c_int, [c_void_p]),
+    "a2f_debug_set_decoder_timing": (c_int, [c_void_p]),
     "a2f_act_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "a2f_act_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "a2f_cast_rows": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_ll, c_int, c_void_p]),

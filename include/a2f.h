@@ -324,6 +324,10 @@ int a2f_pack_feedback(const float* vm_w, const float* vm_b, const float* vmr_w, 
  * layers in a row; the rollout kernels apply them as ONE matvec from d_i.  This packs its operands (fp64 accumulation):
  *   fold_w[192,64] = sa_in_w @ Wc,   fold_pe[pos,192] = sa_in_w @ pe[pos]  for pos < period.
  * Call after a2f_pack_feedback (Wc must be current) whenever self_attn.in_proj_weight, vertice_map(_r) or PPE change. */
+/* debug: device buffer of 13 uint64 (or NULL to switch off) that receives, from thread 0 of CTA 0 of every following
+ * single-CTA rollout launch, the clock cycles it spent in 12 sections of the step loop ([12] = number of steps; the sections
+ * are listed in tools/decoder_phases.py).  Launches a separate instantiation of the kernel: production code is unaffected. */
+int a2f_debug_set_decoder_timing(void* dev_ptr);
 int a2f_pack_decoder_fold(const float* sa_in_w, const float* wc, const float* pe, int period, float* fold_w, float* fold_pe,
                           void* stream);
 int a2f_pack_cross_attention(const float* wv, const float* bv, const float* wo, const float* bo, const float* wa,
