@@ -1,8 +1,8 @@
 """Bring-up / measurement helper for gpurun sessions (not a pytest file).  Each stage runs in its own process so that
 a trapped kernel (poisoned CUDA context) cannot hide later stages:
 
-    python tests/gpu_bringup.py all          # runs every stage in subprocesses, prints a summary
-    python tests/gpu_bringup.py <stage>
+    python tools/gpu_bringup.py all          # runs every stage in subprocesses, prints a summary
+    python tools/gpu_bringup.py <stage>
 """
 from __future__ import annotations
 

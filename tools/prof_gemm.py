@@ -1,4 +1,4 @@
-"""One GEMM shape, a few launches: target for ncu captures (python tests/prof_gemm.py M N K [tmpl])."""
+"""One GEMM shape, a few launches: target for ncu captures (python tools/prof_gemm.py M N K [tmpl])."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
