@@ -38,6 +38,16 @@ struct DecW {
     const float *fold_w, *fold_pe;   // a2f_pack_decoder_fold: in_proj @ Wc [192,64], pe @ in_proj^T [period,192]
 };
 
+// exp() on the sequential critical path of the rollout: MUFU.EX2 on x * log2(e) (2 instructions, relative error 2^-22 -- three
+// orders of magnitude inside the fp32 path's 1e-5 m budget) instead of expf()'s ~15-instruction sequence; exp(-inf) = 0.
+A2F_D float dec_exp(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+// floor(d / period) for 0 <= d < 2^16 without an integer division: high word of d * ceil(2^32 / period)
+A2F_D int dec_div(int d, unsigned magic) { return (int)__umulhi((unsigned)d, magic); }
+
 A2F_D float dot64_smem(const float* w, const float* __restrict__ x) {
     // four independent accumulators: the 64-term dependent FMA chain (64 x 4 cycles) was the matvec critical path
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -156,6 +166,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
 
     const float* ca_b = ca + (long long)b * T * 64;
     float* D_b = D + (long long)b * T * 64;
+    const unsigned pmagic = 0xFFFFFFFFu / (unsigned)period + 1u;      // dec_div: floor((i - j) / period) without a division
 
     // The feedback e_{i+1} = Wc d_i + bc + style and the in-projection of token i+1 are two Linear layers in a row:
     //     [q|k|v]_{i+1} = in_proj(e_{i+1} + pe_{i+1}) = (in_proj Wc) d_i + in_proj (bc + style) + b_in + in_proj pe_{i+1}
@@ -249,7 +260,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                     a2 = fmaf(qh[d + 2], f.z, a2);
                     a3 = fmaf(qh[d + 3], f.w, a3);
                 }
-                const float s = ((a0 + a1) + (a2 + a3)) - slope * (float)((i - j) / period);
+                const float s = ((a0 + a1) + (a2 + a3)) - slope * (float)dec_div(i - j, pmagic);
                 sch[n] = s;
                 lmax = fmaxf(lmax, s);
             }
@@ -257,7 +268,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             const float wmax = warp_max_redux(lmax);                  // -inf when this warp owns no key yet
             float lsum = 0.f;
             for (int n = u; n <= n_max; n += 128) {
-                const float pj = expf(sch[n] - wmax);
+                const float pj = dec_exp(sch[n] - wmax);
                 sch[n] = pj;
                 lsum += pj;
             }
@@ -304,8 +315,8 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 if (u < 16) {
                     const float m0 = red[h * 8], m1 = red[h * 8 + 1], m2 = red[h * 8 + 2], m3 = red[h * 8 + 3];
                     const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                    const float e0 = m0 == -INFINITY ? 0.f : expf(m0 - m), e1 = m1 == -INFINITY ? 0.f : expf(m1 - m);
-                    const float e2 = m2 == -INFINITY ? 0.f : expf(m2 - m), e3 = m3 == -INFINITY ? 0.f : expf(m3 - m);
+                    const float e0 = m0 == -INFINITY ? 0.f : dec_exp(m0 - m), e1 = m1 == -INFINITY ? 0.f : dec_exp(m1 - m);
+                    const float e2 = m2 == -INFINITY ? 0.f : dec_exp(m2 - m), e3 = m3 == -INFINITY ? 0.f : dec_exp(m3 - m);
                     const float l = (e0 * red[h * 8 + 4] + e1 * red[h * 8 + 5]) + (e2 * red[h * 8 + 6] + e3 * red[h * 8 + 7]);
                     const float* pp = pvp + h * 64 + u;
                     float* dst = cluster.map_shared_rank(cpart, 0) + (rank * 4 + h) * 20;
@@ -323,7 +334,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                     float l = 0.f, cv = 0.f;
                     for (int rr = 0; rr < CS; ++rr) {
                         const float* cp = cpart + (rr * 4 + h) * 20;
-                        const float e = cp[0] == -INFINITY ? 0.f : expf(cp[0] - m);
+                        const float e = cp[0] == -INFINITY ? 0.f : dec_exp(cp[0] - m);
                         l = fmaf(e, cp[1], l);
                         cv = fmaf(e, cp[2 + u], cv);
                     }
@@ -332,7 +343,7 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
             } else if (u < 16) {
                 const float m0 = red[h * 8], m1 = red[h * 8 + 1], m2 = red[h * 8 + 2], m3 = red[h * 8 + 3];
                 const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                const float e0 = expf(m0 - m), e1 = expf(m1 - m), e2 = expf(m2 - m), e3 = expf(m3 - m);
+                const float e0 = dec_exp(m0 - m), e1 = dec_exp(m1 - m), e2 = dec_exp(m2 - m), e3 = dec_exp(m3 - m);
                 const float l = (e0 * red[h * 8 + 4] + e1 * red[h * 8 + 5]) + (e2 * red[h * 8 + 6] + e3 * red[h * 8 + 7]);
                 const float* pp = pvp + h * 64 + u;
                 const float cv = ((e0 * pp[0] + e1 * pp[16]) + (e2 * pp[32] + e3 * pp[48])) / l;

@@ -28,6 +28,15 @@ struct DecBwdOut {
     float *GD, *G3, *GHID, *GY2, *G2, *G1, *GQKV, *DEFB, *DSTYLE;
 };
 
+// same fast exp / division-free floor((i - j) / period) as the forward rollout (decoder.cu): the recomputed probabilities must
+// be the ones the forward produced
+A2F_D float dec_exp(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+A2F_D int dec_div(int d, unsigned magic) { return (int)__umulhi((unsigned)d, magic); }
+
 A2F_D float dot64(const float* w, const float* __restrict__ x) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -132,6 +141,7 @@ decoder_bwd_kernel(DecBwdW w, DecBwdIn in, DecBwdOut out, int T, int period, flo
     float dstyle0 = 0.f, dstyle1 = 0.f;
     __syncthreads();
 
+    const unsigned pmagic = 0xFFFFFFFFu / (unsigned)period + 1u;
     const long long bt0 = (long long)b * T;
     const float* Kg = in.K + bt0 * 64;
     const float* Vg = in.V + bt0 * 64;
@@ -249,8 +259,8 @@ decoder_bwd_kernel(DecBwdW w, DecBwdIn in, DecBwdOut out, int T, int period, flo
                     s = fmaf(qh[d], kk[d], s);
                     dp = fmaf(dch[d], vv[d], dp);
                 }
-                s -= slope * (float)((i - j) / period);
-                const float p = expf(s - lse);
+                s -= slope * (float)dec_div(i - j, pmagic);
+                const float p = dec_exp(s - lse);
                 const float ds = p * (dp - Dh);
                 sch[j] = ds;
                 float* dkp = dKa + (long long)j * ald + h * 16;
