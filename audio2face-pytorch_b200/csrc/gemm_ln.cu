@@ -22,6 +22,8 @@
 
 namespace a2f {
 
+unsigned long long* debug_timeline();   // gemm_tc.cu (a2f_debug_set_timeline)
+
 namespace {
 
 constexpr int LBM = 128;            // rows per CTA (UMMA M = 256 over the pair)
@@ -90,6 +92,147 @@ A2F_D void mbar_wait_cluster_acquire(uint64_t* bar, uint32_t parity) {
             : "memory");
         if (ok) return;
         if (++spins > (1u << 26)) __trap();      // a protocol bug becomes a launch error, not a hung GPU
+    }
+}
+
+// One 128-row x 256-column tile of the LayerNorm epilogue (8 epilogue warps of one CTA; see the header): residual fetch,
+// pass 1, statistics exchange over the cluster, pass 2, TMA store.  Shared by gemm_ln_kernel and ffn_ln_kernel.
+template <int NP>
+A2F_D void ln_tile_epilogue(const CUtensorMap* map_r, const CUtensorMap* map_c, const float* sParam, float2* sStats,
+                            uint64_t* rbar, uint64_t* stat_bar, uint64_t* tfull, uint32_t tfull_phase, uint64_t* tempty,
+                            uint32_t t_acc, int n0, int pr, int hr, int half, int q, int lane, bool leader, int bar_id,
+                            uint8_t* stage_base, int row_base, uint32_t it, float inv_n, float eps, bf16* pre_out,
+                            long long ldp, int M) {
+    const int r_tile = q * 32 + lane;
+    const uint32_t par = it & 1u, par_phase = (it >> 1) & 1u;
+    // residual blocks of this tile -> the two staging buffers of this half (while the mainloop runs); a buffer is
+    // free once the TMA store that last used it has finished reading it
+    if (leader) {
+        tma_store_wait_read1();
+        mbar_expect_tx(&rbar[half * 2 + 0], L_EPI_BYTES);
+        tma_load_2d(stage_base, map_r, &rbar[half * 2 + 0], n0 + half * L_SBW, row_base);
+        tma_store_wait_read();
+        mbar_expect_tx(&rbar[half * 2 + 1], L_EPI_BYTES);
+        tma_load_2d(stage_base + L_EPI_BYTES, map_r, &rbar[half * 2 + 1], n0 + (half + 2) * L_SBW, row_base);
+    }
+    mbar_wait(tfull, tfull_phase);
+    tc_fence_after();
+    const uint32_t t_row = t_acc + ((uint32_t)(q * 32) << 16);
+
+    // ---- pass 1: x = acc + bias + resid -> TMEM, partial row statistics ----
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+        const int col0 = (half + 2 * j) * L_SBW;
+        const uint8_t* rowp = stage_base + j * L_EPI_BYTES + r_tile * 128;
+        float v[L_SBW];
+        tmem_ld_32x32(t_row + col0, v);
+        tmem_ld_32x32(t_row + col0 + 32, v + 32);
+        mbar_wait(&rbar[half * 2 + j], it & 1u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < L_SBW / 8; ++ch) {
+            const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const float4 b0 = *reinterpret_cast<const float4*>(sParam + col0 + ch * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sParam + col0 + ch * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                const float x0 = v[ch * 8 + 2 * e] + bb[2 * e] + f.x;
+                const float x1 = v[ch * 8 + 2 * e + 1] + bb[2 * e + 1] + f.y;
+                v[ch * 8 + 2 * e] = x0;
+                v[ch * 8 + 2 * e + 1] = x1;
+                s1 += x0 + x1;
+                s2 = fmaf(x0, x0, fmaf(x1, x1, s2));
+            }
+        }
+        tmem_st_32x32(t_row + col0, v);
+        tmem_st_32x32(t_row + col0 + 32, v + 32);
+        if (pre_out != nullptr && row_base + r_tile < M) {
+            // training: LayerNorm's backward needs its input; every thread writes its own row's 128 bytes
+            bf16* pp = pre_out + (long long)(row_base + r_tile) * ldp + n0 + col0;
+#pragma unroll
+            for (int ch = 0; ch < L_SBW / 8; ++ch) {
+                uint4 u;
+                u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+                u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+                u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+                u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+                *reinterpret_cast<uint4*>(pp + ch * 8) = u;
+            }
+        }
+    }
+    // ---- exchange: my partial -> the stats slot of every CTA that holds these rows (same hr, all NP pairs) ----
+    {
+        const uint32_t slot = smem_u32(sStats + ((size_t)par * (2 * NP) + (size_t)(pr * 2 + half)) * LBM + r_tile);
+        const uint32_t sbar = smem_u32(&stat_bar[par]);
+#pragma unroll
+        for (int d = 0; d < NP; ++d) {
+            const uint32_t dst_rank = (uint32_t)(2 * d + hr);
+            st_cluster_f2(map_to_rank(slot, dst_rank), s1, s2);
+            mbar_arrive_cluster_release(map_to_rank(sbar, dst_rank));
+        }
+    }
+    tmem_st_wait();
+    mbar_wait_cluster_acquire(&stat_bar[par], par_phase);
+    float S1 = 0.f, S2 = 0.f;
+    {
+        const float2* st = sStats + (size_t)par * (2 * NP) * LBM + r_tile;
+#pragma unroll
+        for (int d = 0; d < 2 * NP; ++d) {
+            const float2 t = st[(size_t)d * LBM];
+            S1 += t.x;
+            S2 += t.y;
+        }
+    }
+    const float mean = S1 * inv_n;
+    const float var = fmaxf(fmaf(-mean, mean, S2 * inv_n), 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float nmr = -mean * rstd;
+
+    // ---- pass 2: normalise, affine, bf16, TMA store ----
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+        const int col0 = (half + 2 * j) * L_SBW;
+        uint8_t* stage_buf = stage_base + j * L_EPI_BYTES;
+        uint8_t* rowp = stage_buf + r_tile * 128;
+        float v[L_SBW];
+        tmem_ld_32x32(t_row + col0, v);
+        tmem_ld_32x32(t_row + col0 + 32, v + 32);
+        tmem_ld_wait();
+        if (j == 1) {
+            // last read of this accumulator: hand it back to the MMA warp before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty);
+        }
+#pragma unroll
+        for (int ch = 0; ch < L_SBW / 8; ++ch) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; e += 4) {
+                const float4 g = *reinterpret_cast<const float4*>(sParam + LBN + col0 + ch * 8 + e);
+                const float4 b = *reinterpret_cast<const float4*>(sParam + 2 * LBN + col0 + ch * 8 + e);
+                y[e + 0] = fmaf(fmaf(v[ch * 8 + e + 0], rstd, nmr), g.x, b.x);
+                y[e + 1] = fmaf(fmaf(v[ch * 8 + e + 1], rstd, nmr), g.y, b.y);
+                y[e + 2] = fmaf(fmaf(v[ch * 8 + e + 2], rstd, nmr), g.z, b.z);
+                y[e + 3] = fmaf(fmaf(v[ch * 8 + e + 3], rstd, nmr), g.w, b.w);
+            }
+            uint4 u;
+            u.x = pack_bf16x2(y[0], y[1]);
+            u.y = pack_bf16x2(y[2], y[3]);
+            u.z = pack_bf16x2(y[4], y[5]);
+            u.w = pack_bf16x2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16)) = u;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (leader) {
+            tma_store_2d(map_c, stage_buf, n0 + col0, row_base);
+            tma_store_commit();
+        }
     }
 }
 
@@ -205,7 +348,6 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const LnParams p) {
         const bool leader = ((ew & 3) == 0) && lane == 0;
         const int bar_id = 1 + half;
         uint8_t* stage_base = sEpi + half * 2 * L_EPI_BYTES;
-        const int r_tile = q * 32 + lane;
         // bias | gamma | beta of this pair's 256 columns: loaded once (the pair keeps its column block for every tile)
         {
             const int c = ew * 32 + lane;             // 256 epilogue threads
@@ -219,137 +361,9 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const LnParams p) {
         uint32_t it = 0;                              // tiles this CTA has processed
         const float inv_n = 1.0f / (float)p.N;
         for (int mb = cl; mb < p.tiles_m; mb += n_cl, ++it) {
-            const int row_base = mb * 2 * LBM + hr * LBM;
-            const uint32_t par = it & 1u, par_phase = (it >> 1) & 1u;
-            // residual blocks of this tile -> the two staging buffers of this half (while the mainloop runs); a buffer is
-            // free once the TMA store that last used it has finished reading it
-            if (leader) {
-                tma_store_wait_read1();
-                mbar_expect_tx(&rbar[half * 2 + 0], L_EPI_BYTES);
-                tma_load_2d(stage_base, &maps.r, &rbar[half * 2 + 0], n0 + half * L_SBW, row_base);
-                tma_store_wait_read();
-                mbar_expect_tx(&rbar[half * 2 + 1], L_EPI_BYTES);
-                tma_load_2d(stage_base + L_EPI_BYTES, &maps.r, &rbar[half * 2 + 1], n0 + (half + 2) * L_SBW, row_base);
-            }
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * LBN);
-
-            // ---- pass 1: x = acc + bias + resid -> TMEM, partial row statistics ----
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                const int col0 = (half + 2 * j) * L_SBW;
-                const uint8_t* rowp = stage_base + j * L_EPI_BYTES + r_tile * 128;
-                float v[L_SBW];
-                tmem_ld_32x32(t_row + col0, v);
-                tmem_ld_32x32(t_row + col0 + 32, v + 32);
-                mbar_wait(&rbar[half * 2 + j], it & 1u);
-                tmem_ld_wait();
-#pragma unroll
-                for (int ch = 0; ch < L_SBW / 8; ++ch) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16));
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-                    const float4 b0 = *reinterpret_cast<const float4*>(sParam + col0 + ch * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(sParam + col0 + ch * 8 + 4);
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 f = __bfloat1622float2(h2[e]);
-                        const float x0 = v[ch * 8 + 2 * e] + bb[2 * e] + f.x;
-                        const float x1 = v[ch * 8 + 2 * e + 1] + bb[2 * e + 1] + f.y;
-                        v[ch * 8 + 2 * e] = x0;
-                        v[ch * 8 + 2 * e + 1] = x1;
-                        s1 += x0 + x1;
-                        s2 = fmaf(x0, x0, fmaf(x1, x1, s2));
-                    }
-                }
-                tmem_st_32x32(t_row + col0, v);
-                tmem_st_32x32(t_row + col0 + 32, v + 32);
-                if (p.pre_out != nullptr && row_base + r_tile < p.M) {
-                    // training: LayerNorm's backward needs its input; every thread writes its own row's 128 bytes
-                    bf16* pp = p.pre_out + (long long)(row_base + r_tile) * p.ldp + n0 + col0;
-#pragma unroll
-                    for (int ch = 0; ch < L_SBW / 8; ++ch) {
-                        uint4 u;
-                        u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
-                        u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
-                        u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
-                        u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
-                        *reinterpret_cast<uint4*>(pp + ch * 8) = u;
-                    }
-                }
-            }
-            // ---- exchange: my partial -> the stats slot of every CTA that holds these rows (same hr, all NP pairs) ----
-            {
-                const uint32_t slot = smem_u32(sStats + ((size_t)par * (2 * NP) + (size_t)(pr * 2 + half)) * LBM + r_tile);
-                const uint32_t sbar = smem_u32(&stat_bar[par]);
-#pragma unroll
-                for (int d = 0; d < NP; ++d) {
-                    const uint32_t dst_rank = (uint32_t)(2 * d + hr);
-                    st_cluster_f2(map_to_rank(slot, dst_rank), s1, s2);
-                    mbar_arrive_cluster_release(map_to_rank(sbar, dst_rank));
-                }
-            }
-            tmem_st_wait();
-            mbar_wait_cluster_acquire(&stat_bar[par], par_phase);
-            float S1 = 0.f, S2 = 0.f;
-            {
-                const float2* st = sStats + (size_t)par * (2 * NP) * LBM + r_tile;
-#pragma unroll
-                for (int d = 0; d < 2 * NP; ++d) {
-                    const float2 t = st[(size_t)d * LBM];
-                    S1 += t.x;
-                    S2 += t.y;
-                }
-            }
-            const float mean = S1 * inv_n;
-            const float var = fmaxf(fmaf(-mean, mean, S2 * inv_n), 0.f);
-            const float rstd = rsqrtf(var + p.eps);
-            const float nmr = -mean * rstd;
-
-            // ---- pass 2: normalise, affine, bf16, TMA store ----
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                const int col0 = (half + 2 * j) * L_SBW;
-                uint8_t* stage_buf = stage_base + j * L_EPI_BYTES;
-                uint8_t* rowp = stage_buf + r_tile * 128;
-                float v[L_SBW];
-                tmem_ld_32x32(t_row + col0, v);
-                tmem_ld_32x32(t_row + col0 + 32, v + 32);
-                tmem_ld_wait();
-                if (j == 1) {
-                    // last read of this accumulator: hand it back to the MMA warp before the stores
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
-                }
-#pragma unroll
-                for (int ch = 0; ch < L_SBW / 8; ++ch) {
-                    float y[8];
-#pragma unroll
-                    for (int e = 0; e < 8; e += 4) {
-                        const float4 g = *reinterpret_cast<const float4*>(sParam + LBN + col0 + ch * 8 + e);
-                        const float4 b = *reinterpret_cast<const float4*>(sParam + 2 * LBN + col0 + ch * 8 + e);
-                        y[e + 0] = fmaf(fmaf(v[ch * 8 + e + 0], rstd, nmr), g.x, b.x);
-                        y[e + 1] = fmaf(fmaf(v[ch * 8 + e + 1], rstd, nmr), g.y, b.y);
-                        y[e + 2] = fmaf(fmaf(v[ch * 8 + e + 2], rstd, nmr), g.z, b.z);
-                        y[e + 3] = fmaf(fmaf(v[ch * 8 + e + 3], rstd, nmr), g.w, b.w);
-                    }
-                    uint4 u;
-                    u.x = pack_bf16x2(y[0], y[1]);
-                    u.y = pack_bf16x2(y[2], y[3]);
-                    u.z = pack_bf16x2(y[4], y[5]);
-                    u.w = pack_bf16x2(y[6], y[7]);
-                    *reinterpret_cast<uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16)) = u;
-                }
-                fence_proxy_async_smem();
-                named_bar_sync(bar_id, 128);
-                if (leader) {
-                    tma_store_2d(&maps.c, stage_buf, n0 + col0, row_base);
-                    tma_store_commit();
-                }
-            }
+            ln_tile_epilogue<NP>(&maps.r, &maps.c, sParam, sStats, rbar, stat_bar, &tfull_bar[acc], acc_phase, &tempty_bar[acc],
+                                 tmem_base + (uint32_t)(acc * LBN), n0, pr, hr, half, q, lane, leader, bar_id, stage_base,
+                                 mb * 2 * LBM + hr * LBM, it, inv_n, p.eps, p.pre_out, p.ldp, p.M);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -358,6 +372,295 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const LnParams p) {
 
     tc_fence_before();
     cluster_sync_all();                               // nobody signals a CTA that has left; TMEM reads are complete
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<512>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole feed-forward block of an encoder layer in ONE kernel:
+//     out = LayerNorm(x + W2 gelu(W1 x + b1) + b2) * gamma + beta          (HF modeling_wav2vec2.py:551-609)
+// Same cluster of NP CTA pairs per 256-row block as gemm_ln_kernel.  Per row block every pair runs
+//   phase 1  TP = F / (256 NP) tiles of  f = gelu(x W1^T + b1)  (tile t of pair p = columns [256 (t NP + p), +256) of f), each
+//            stored (bf16, TMA) to the scratch f [M, F];  after the stores of tile t have COMPLETED the two epilogue leaders
+//            arrive (release.cluster) on f_bar[t] of the NP CTAs that own the same 128 rows
+//   phase 2  one 256-column tile of  f W2^T  over K = F: its producer waits (acquire.cluster) on f_bar[t] before the first
+//            k-block of columns [768 t, 768 t + 768) -- round t of ALL pairs -- so only the last round is ever waited for,
+//            and that one finished while the first three quarters of the K loop ran;  then the LayerNorm epilogue.
+// The five tiles of a row block go through the same smem ring and the same two TMEM accumulators back to back: the tensor
+// pipe never drains between the two GEMMs, there is one launch / prologue / tail instead of two, and the kernel uses
+// 19 x 6 = 114 SMs for the whole block instead of 148 SMs with a 3.08-wave quantisation followed by 114.
+// f makes the L2 round trip (1.5 MB per row block: too large for shared memory), exactly like between two launches.
+struct FfnMaps {
+    CUtensorMap x, w1, f, w2, c, r;
+};
+
+struct FfnParams {
+    int M, N, F, K1;
+    int tiles_m, kb1, kb2, tp;      // row blocks; k-blocks of phase 1 / 2; phase-1 tiles per pair
+    const float* bias1;
+    const float* bias2;
+    const float* gamma;
+    const float* beta;
+    float eps;
+    unsigned long long* timeline;   // debug (a2f_debug_set_timeline): 16 clock64 stamps per CTA
+};
+
+A2F_D unsigned long long ffn_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FFN_STAMP(slot) do { if (p.timeline) { p.timeline[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
+                                                p.timeline[(gridDim.x + blockIdx.x) * 16 + (slot)] = ffn_gtimer(); } } while (0)
+
+constexpr int FFN_MAX_TP = 4;
+
+template <int NP> struct FfnCfg {
+    static constexpr int STATS_BYTES = LnCfg<NP>::STATS_BYTES;
+    static constexpr int PARAM_BYTES = (3 + FFN_MAX_TP) * LBN * 4;   // bias2 | gamma | beta | bias1 of the pair's TP tiles
+    static constexpr size_t SMEM_BYTES = (size_t)L_STAGES * L_STAGE_BYTES + 4 * L_EPI_BYTES + STATS_BYTES + PARAM_BYTES + 256;
+};
+
+A2F_D void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int NP>
+__global__ void __launch_bounds__(L_THREADS, 1)
+ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
+    using Cfg = FfnCfg<NP>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)L_STAGES * L_A_BYTES;
+    uint8_t* sEpi = smem + (size_t)L_STAGES * L_STAGE_BYTES;
+    float2* sStats = reinterpret_cast<float2*>(sEpi + 4 * L_EPI_BYTES);
+    float* sParam = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStats) + Cfg::STATS_BYTES);
+    float* sBias1 = sParam + 3 * LBN;                                            // [TP][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sParam) + Cfg::PARAM_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + L_STAGES;
+    uint64_t* tfull_bar = bars + 2 * L_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* rbar = tempty_bar + 2;
+    uint64_t* stat_bar = rbar + 4;
+    uint64_t* f_bar = stat_bar + 2;                   // [TP] round t of f (this CTA's 128 rows, all F/TP columns) is in L2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(f_bar + FFN_MAX_TP);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int pr = rank >> 1;
+    const int hr = rank & 1;
+    const bool is_leader = hr == 0;
+    const int cl = (int)cluster_id_x(), n_cl = (int)cluster_count_x();
+    const int TP = p.tp;
+
+    if (threadIdx.x == 0) FFN_STAMP(0);
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.x);
+        tma_prefetch_desc(&maps.w1);
+        tma_prefetch_desc(&maps.f);
+        tma_prefetch_desc(&maps.w2);
+        tma_prefetch_desc(&maps.c);
+        tma_prefetch_desc(&maps.r);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < L_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 16);
+            mbar_init(&stat_bar[i], NP * 256);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
+        for (int i = 0; i < FFN_MAX_TP; ++i) mbar_init(&f_bar[i], 2 * NP);      // 2 epilogue leaders x NP CTAs with these rows
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
+    if (threadIdx.x == 0) FFN_STAMP(1);
+
+    const int n0 = pr * LBN;                          // this pair's columns of the OUTPUT (phase 2)
+    const int kb_round = (NP * LBN) / LBK;            // k-blocks of phase 2 per round of f
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int mb = cl; mb < p.tiles_m; mb += n_cl, ++it) {
+                const int row0 = mb * 2 * LBM + hr * LBM;
+                for (int t = 0; t < TP; ++t) {
+                    const int wrow0 = (t * NP + pr) * LBN + hr * (LBN / 2);
+                    for (int kb = 0; kb < p.kb1; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * L_STAGE_BYTES);
+                        tma_load_2d_2sm(sA + (size_t)stage * L_A_BYTES, &maps.x, &full_bar[stage], kb * LBK, row0);
+                        tma_load_2d_2sm(sB + (size_t)stage * L_B_BYTES, &maps.w1, &full_bar[stage], kb * LBK, wrow0);
+                        if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                const int wrow0 = n0 + hr * (LBN / 2);
+                for (int kb = 0; kb < p.kb2; ++kb) {
+                    if (kb % kb_round == 0) {
+                        // round kb / kb_round of f: written by TMA stores of the NP CTAs with these rows, read by TMA here
+                        mbar_wait_cluster_acquire(&f_bar[kb / kb_round], it & 1u);
+                        fence_proxy_async_all();
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * L_STAGE_BYTES);
+                    tma_load_2d_2sm(sA + (size_t)stage * L_A_BYTES, &maps.f, &full_bar[stage], kb * LBK, row0);
+                    tma_load_2d_2sm(sB + (size_t)stage * L_B_BYTES, &maps.w2, &full_bar[stage], kb * LBK, wrow0);
+                    if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA of the pair) =====================
+        if (is_leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LBN >> 3) << 17) |
+                                   ((uint32_t)((2 * LBM) >> 4) << 24);
+            const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int mb = cl; mb < p.tiles_m; mb += n_cl) {
+                for (int t = 0; t <= TP; ++t) {
+                    const int nkb = t < TP ? p.kb1 : p.kb2;
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * LBN);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (mb == cl && t == 0 && kb == 0) FFN_STAMP(2);
+                        const uint64_t adesc = ln_smem_desc(smem_u32(sA + (size_t)stage * L_A_BYTES));
+                        const uint64_t bdesc = ln_smem_desc(smem_u32(sB + (size_t)stage * L_B_BYTES));
+#pragma unroll
+                        for (int k = 0; k < LBK / 16; ++k)
+                            umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair(&empty_bar[stage], pair_mask);
+                        if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_pair(&tfull_bar[acc], pair_mask);
+                    if (mb == cl) FFN_STAMP(3 + t);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const bool leader = ((ew & 3) == 0) && lane == 0;
+        const int bar_id = 1 + half;
+        uint8_t* stage_base = sEpi + half * 2 * L_EPI_BYTES;
+        const int r_tile = q * 32 + lane;
+        {
+            const int c = ew * 32 + lane;
+            sParam[c] = p.bias2 ? __ldg(p.bias2 + n0 + c) : 0.f;
+            sParam[LBN + c] = __ldg(p.gamma + n0 + c);
+            sParam[2 * LBN + c] = __ldg(p.beta + n0 + c);
+            for (int t = 0; t < TP; ++t) sBias1[t * LBN + c] = p.bias1 ? __ldg(p.bias1 + (t * NP + pr) * LBN + c) : 0.f;
+        }
+        named_bar_sync(3, 256);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t it = 0;
+        const float inv_n = 1.0f / (float)p.N;
+        for (int mb = cl; mb < p.tiles_m; mb += n_cl, ++it) {
+            const int row_base = mb * 2 * LBM + hr * LBM;
+            // ---- phase 1: TP tiles of gelu(x W1^T + b1) -> f ----
+            for (int t = 0; t < TP; ++t) {
+                const int fcol0 = (t * NP + pr) * LBN;
+                const float* tb = sBias1 + t * LBN;
+                if (leader) tma_store_wait_read();                 // both staging buffers of this half are free again
+                named_bar_sync(bar_id, 128);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * LBN);
+#pragma unroll 1
+                for (int j = 0; j < 2; ++j) {
+                    const int col0 = (half + 2 * j) * L_SBW;
+                    uint8_t* stage_buf = stage_base + j * L_EPI_BYTES;
+                    uint8_t* rowp = stage_buf + r_tile * 128;
+                    float v[L_SBW];
+                    tmem_ld_32x32(t_row + col0, v);
+                    tmem_ld_32x32(t_row + col0 + 32, v + 32);
+                    tmem_ld_wait();
+                    if (j == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < L_SBW; e += 4) {
+                        const float4 f = *reinterpret_cast<const float4*>(tb + col0 + e);
+                        v[e] += f.x; v[e + 1] += f.y; v[e + 2] += f.z; v[e + 3] += f.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < L_SBW; e += 2) {
+                        const float2 r = gelu_fast2(make_float2(v[e], v[e + 1]));
+                        v[e] = r.x;
+                        v[e + 1] = r.y;
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < L_SBW / 8; ++ch) {
+                        uint4 u;
+                        u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+                        u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+                        u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+                        u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+                        *reinterpret_cast<uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16)) = u;
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(bar_id, 128);
+                    if (leader) {
+                        tma_store_2d(&maps.f, stage_buf, fcol0 + col0, row_base);
+                        tma_store_commit();
+                    }
+                }
+                if (leader) {
+                    // the two blocks are in L2 (writes complete, not only read out of shared memory): publish round t to
+                    // the producers of the NP CTAs that hold these rows
+                    tma_store_wait_all();
+                    fence_proxy_async_all();
+                    const uint32_t fb = smem_u32(&f_bar[t]);
+#pragma unroll
+                    for (int d = 0; d < NP; ++d) mbar_arrive_cluster_release(map_to_rank(fb, (uint32_t)(2 * d + hr)));
+                    if (mb == cl && half == 0) FFN_STAMP(8 + t);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+            // ---- phase 2: LayerNorm(x + f W2^T + b2) ----
+            if (mb == cl && threadIdx.x == 64) FFN_STAMP(12);
+            ln_tile_epilogue<NP>(&maps.r, &maps.c, sParam, sStats, rbar, stat_bar, &tfull_bar[acc], acc_phase, &tempty_bar[acc],
+                                 tmem_base + (uint32_t)(acc * LBN), n0, pr, hr, half, q, lane, leader, bar_id, stage_base,
+                                 row_base, it, inv_n, p.eps, nullptr, 0, p.M);
+            if (mb == cl && threadIdx.x == 64) FFN_STAMP(13);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (leader) tma_store_wait_all();
+        if (threadIdx.x == 64) FFN_STAMP(14);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (threadIdx.x == 0) FFN_STAMP(15);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_2sm<512>(tmem_base);
@@ -408,6 +711,57 @@ int launch_gemm_ln(LnMaps& maps, const LnParams& p, cudaStream_t s) {
     A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
     count_launch();
     return A2F_OK;
+}
+
+
+template <int NP>
+int launch_ffn_ln(FfnMaps& maps, const FfnParams& p, cudaStream_t s) {
+    using Cfg = FfnCfg<NP>;
+    auto kern = ffn_ln_kernel<NP>;
+    static bool attr_done = false;
+    static int max_clusters = 0;
+    if (!attr_done) {
+        A2F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(L_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * NP;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    if (max_clusters == 0) {
+        cfg.gridDim = dim3(2 * NP * (sm_count() / (2 * NP)), 1, 1);
+        cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = sm_count() / (2 * NP) - (NP > 1 ? 1 : 0);
+            if (n < 1) n = 1;
+        }
+        max_clusters = n;
+    }
+    const int n_clusters = p.tiles_m < max_clusters ? p.tiles_m : max_clusters;
+    cfg.gridDim = dim3(2 * NP * n_clusters, 1, 1);
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
+    count_launch();
+    return A2F_OK;
+}
+
+static int ln_map2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, long long ld, uint32_t box_rows) {
+    uint64_t dims[2] = {cols, rows};
+    uint64_t str[1] = {(uint64_t)ld * 2};
+    uint32_t box[2] = {LBK, box_rows};
+    return encode_tmap_bf16(m, ptr, 2, dims, str, box, 1);
 }
 
 }  // namespace
@@ -464,6 +818,44 @@ int gemm_ln_tc(const void* A, long long lda, const void* W, long long ldw, const
     }
 }
 
+
+// x [M,K1], W1 [F,K1], W2 [N,F], resid / out [M,N], scratch f [M,F]; all bf16.  N = 256 NP, F a multiple of 256 NP (at most 4).
+int ffn_ln_tc(const void* X, long long ldx, const void* W1, long long ldw1, const float* bias1, const void* W2, long long ldw2,
+              const float* bias2, const void* resid, long long ldr, const float* gamma, const float* beta, float eps,
+              void* scratch, long long ldf, void* out, long long ldo, int M, int N, int F, int K1, cudaStream_t s) {
+    if (M <= 0) return A2F_OK;
+    A2F_REQUIRE(N % LBN == 0 && N / LBN >= 1 && N / LBN <= 3, "a2f_ffn_ln: N must be 256, 512 or 768");
+    A2F_REQUIRE(F > 0 && F % N == 0 && F / N <= FFN_MAX_TP, "a2f_ffn_ln: F must be N, 2N, 3N or 4N");
+    A2F_REQUIRE(K1 > 0 && K1 % 8 == 0, "a2f_ffn_ln: K1 must be a positive multiple of 8");
+    A2F_REQUIRE(ldx % 8 == 0 && ldw1 % 8 == 0 && ldw2 % 8 == 0 && ldr % 8 == 0 && ldf % 8 == 0 && ldo % 8 == 0,
+                "a2f_ffn_ln: row strides must be multiples of 8 elements");
+    A2F_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(W2) |
+                  reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(scratch) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "a2f_ffn_ln: operands must be 16-byte aligned");
+    FfnMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    if ((rc = ln_map2d(&maps.x, X, (uint64_t)K1, (uint64_t)M, ldx, LBM)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.w1, W1, (uint64_t)K1, (uint64_t)F, ldw1, LBN / 2)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.f, scratch, (uint64_t)F, (uint64_t)M, ldf, LBM)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.w2, W2, (uint64_t)F, (uint64_t)N, ldw2, LBN / 2)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.c, out, (uint64_t)N, (uint64_t)M, ldo, LBM)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.r, resid, (uint64_t)N, (uint64_t)M, ldr, LBM)) != A2F_OK) return rc;
+    FfnParams p;
+    p.M = M; p.N = N; p.F = F; p.K1 = K1;
+    p.tiles_m = (M + 2 * LBM - 1) / (2 * LBM);
+    p.kb1 = (K1 + LBK - 1) / LBK;
+    p.kb2 = F / LBK;
+    p.tp = F / N;
+    p.bias1 = bias1; p.bias2 = bias2; p.gamma = gamma; p.beta = beta; p.eps = eps;
+    p.timeline = debug_timeline();
+    switch (N / LBN) {
+        case 1: return launch_ffn_ln<1>(maps, p, s);
+        case 2: return launch_ffn_ln<2>(maps, p, s);
+        default: return launch_ffn_ln<3>(maps, p, s);
+    }
+}
+
 }  // namespace a2f
 
 extern "C" int a2f_gemm_ln(const void* A, long long lda, const void* W, long long ldw, const float* bias, const void* resid,
@@ -475,4 +867,16 @@ extern "C" int a2f_gemm_ln(const void* A, long long lda, const void* W, long lon
     A2F_REQUIRE(M >= 0 && N > 0 && K > 0, "a2f_gemm_ln: bad M/N/K");
     return a2f::gemm_ln_tc(A, lda, W, ldw, bias, resid, ldr, gamma, beta, eps, out, ldo, pre_out, ldp, M, N, K,
                            a2f::as_stream(stream));
+}
+
+extern "C" int a2f_ffn_ln(const void* X, long long ldx, const void* W1, long long ldw1, const float* bias1, const void* W2,
+                          long long ldw2, const float* bias2, const void* resid, long long ldr, const float* gamma,
+                          const float* beta, float eps, void* scratch, long long ldf, void* out, long long ldo, int M, int N,
+                          int F, int K1, void* stream) {
+    int rc = a2f::require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(X && W1 && W2 && resid && gamma && beta && scratch && out, "a2f_ffn_ln: NULL operand");
+    A2F_REQUIRE(M >= 0 && N > 0 && F > 0 && K1 > 0, "a2f_ffn_ln: bad M/N/F/K1");
+    return a2f::ffn_ln_tc(X, ldx, W1, ldw1, bias1, W2, ldw2, bias2, resid, ldr, gamma, beta, eps, scratch, ldf, out, ldo, M, N,
+                          F, K1, a2f::as_stream(stream));
 }

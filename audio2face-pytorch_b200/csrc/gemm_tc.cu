@@ -1347,6 +1347,9 @@ void set_dec_cluster(int v);
 void set_posconv_impl(int v);
 void set_posconv_swap(int v);
 }
+namespace a2f {
+unsigned long long* debug_timeline() { return g_timeline; }
+}
 extern "C" int a2f_debug_set_timeline(void* dev_ptr) {
     a2f::g_timeline = static_cast<unsigned long long*>(dev_ptr);
     return A2F_OK;

@@ -572,6 +572,9 @@ class Faceformer(_A2FModule):
         # bf16 inference: run the encoder's 24 post-LayerNorms inside the GEMM epilogues (a2f_gemm_ln); False = the separate
         # layernorm_kernel launches (A/B switch for profiles/)
         self.fuse_layernorm = True
+        # ... and the whole feed-forward block (W1, GELU, W2, residual, LayerNorm) as ONE kernel (a2f_ffn_ln); False = GEMM +
+        # a2f_gemm_ln (bit-identical results; A/B switch for profiles/)
+        self.fuse_ffn = True
         self.dataset = "vocaset"
         self.period = 60
         self.fps = 60
@@ -744,6 +747,11 @@ class Faceformer(_A2FModule):
                 # pairs per 256-row block, row statistics over DSMEM, pre-LN sum kept fp32 in tensor memory)
                 ops.gemm_ln(att, W["o_w"], blk.attention.out_proj.bias.detach(), h, blk.layer_norm.weight.detach(),
                             blk.layer_norm.bias.detach(), h1)
+                if self.fuse_ffn:
+                    ops.ffn_ln(h1, W["f1_w"], blk.feed_forward.intermediate_dense.bias.detach(), W["f2_w"],
+                               blk.feed_forward.output_dense.bias.detach(), h1, blk.final_layer_norm.weight.detach(),
+                               blk.final_layer_norm.bias.detach(), ffn, h)
+                    continue
                 ops.gemm(h1, W["f1_w"], ffn, bias=blk.feed_forward.intermediate_dense.bias.detach(), act=L.ACT_GELU, backend=be)
                 ops.gemm_ln(ffn, W["f2_w"], blk.feed_forward.output_dense.bias.detach(), h1, blk.final_layer_norm.weight.detach(),
                             blk.final_layer_norm.bias.detach(), h)

@@ -109,6 +109,34 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     return out
 
 
+def ffn_ln(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
+           resid: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, scratch: torch.Tensor, out: torch.Tensor,
+           eps: float = 1e-5) -> torch.Tensor:
+    """out = LayerNorm(resid + gelu(x @ w1^T + b1) @ w2^T + b2) * gamma + beta in one tcgen05 kernel (a2f_ffn_ln): the
+    feed-forward block of a post-LN encoder layer.  bf16 operands; scratch [M,F] holds gelu(.) between the two GEMMs."""
+    _dev(x, w1, b1, w2, b2, resid, gamma, beta, scratch, out)
+    for t in (x, w1, w2, resid, scratch, out):
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise L.A2FError("ffn_ln takes 2-D bf16 operands with unit column stride")
+    M, K1 = x.shape
+    F, N = w1.shape[0], w2.shape[0]
+    if w1.shape[1] != K1 or w2.shape[1] != F or tuple(resid.shape) != (M, N) or tuple(out.shape) != (M, N) or \
+            scratch.shape[0] < M or scratch.shape[1] != F:
+        raise L.A2FError("ffn_ln: shape mismatch")
+    lib = L.load()
+    if PROFILE is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+    L.check(lib.a2f_ffn_ln(x.data_ptr(), x.stride(0), w1.data_ptr(), w1.stride(0), L.ptr(b1), w2.data_ptr(), w2.stride(0),
+                           L.ptr(b2), resid.data_ptr(), resid.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
+                           scratch.data_ptr(), scratch.stride(0), out.data_ptr(), out.stride(0), M, N, F, K1, _stream()),
+            "a2f_ffn_ln")
+    if PROFILE is not None:
+        e.record()
+        PROFILE.append(("gemm_tc", 2.0 * M * F * (K1 + N), s, e))
+    return out
+
+
 def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: torch.Tensor, gamma: torch.Tensor,
             beta: torch.Tensor, out: torch.Tensor, eps: float = 1e-5, pre_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = LayerNorm(a @ w^T + bias + resid) * gamma + beta in one tcgen05 kernel (a2f_gemm_ln): bf16 [M,K] x [N,K],

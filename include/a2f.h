@@ -132,7 +132,12 @@ typedef struct a2f_wgrad_args {
     int x_col_off[4];
     float* dW;
     long long ldw;
-    int x_row_step;     /* GEMM with the post-LayerNorm of the wav2vec2 encoder layer fused into its epilogue (tcgen05 back end, bf16):
+    int x_row_step;     /* != 0: segment s reads rows r + x_row_off[0] + s*x_row_step, columns x_col_off[0].. (the 128
+                           taps of the positional conv); the table entries 1..3 are ignored */
+} a2f_wgrad_args;
+int a2f_gemm_wgrad(const a2f_wgrad_args* args, int backend, void* stream);
+
+/* GEMM with the post-LayerNorm of the wav2vec2 encoder layer fused into its epilogue (tcgen05 back end, bf16):
  *   out[m,:] = LayerNorm(A[m,:] W^T + bias + resid[m,:]) * gamma + beta          (eps inside the square root)
  * = `h = layer_norm(h + out_proj(attn))` and `h = final_layer_norm(h + output_dense(ffn))` of HF
  * modeling_wav2vec2.py:576-609, which ref:src/model/wav2vec.py:174-180 runs 12 times per forward.  One thread-block
@@ -145,10 +150,17 @@ int a2f_gemm_ln(const void* A, long long lda, const void* W, long long ldw, cons
                 long long ldr, const float* gamma, const float* beta, float eps, void* out, long long ldo, void* pre_out,
                 long long ldp, int M, int N, int K, void* stream);
 
-/* != 0: segment s reads rows r + x_row_off[0] + s*x_row_step, columns x_col_off[0].. (the 128
-                           taps of the positional conv); the table entries 1..3 are ignored */
-} a2f_wgrad_args;
-int a2f_gemm_wgrad(const a2f_wgrad_args* args, int backend, void* stream);
+/* The whole feed-forward block of a post-LN encoder layer in one kernel (tcgen05 back end, bf16):
+ *   out = LayerNorm(resid + gelu(X W1^T + bias1) W2^T + bias2) * gamma + beta      (HF modeling_wav2vec2.py:551-609)
+ * Same cluster layout as a2f_gemm_ln; the intermediate gelu(.) [M,F] goes through `scratch` (bf16, row stride ldf, stays in
+ * L2) and both GEMMs share one smem ring / TMEM double buffer, so the tensor pipe does not drain between them.
+ * X [M,K1], W1 [F,K1], W2 [N,F], resid / out [M,N]; N in {256, 512, 768}; F in {N, 2N, 3N, 4N}; gelu = the tanh-form
+ * approximation the bf16 back end uses everywhere (|err| below bf16 resolution).  Results are bit-identical to
+ * a2f_gemm (GELU epilogue) followed by a2f_gemm_ln. */
+int a2f_ffn_ln(const void* X, long long ldx, const void* W1, long long ldw1, const float* bias1, const void* W2,
+               long long ldw2, const float* bias2, const void* resid, long long ldr, const float* gamma, const float* beta,
+               float eps, void* scratch, long long ldf, void* out, long long ldo, int M, int N, int F, int K1, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------------------
  * wav2vec2 positional conv embedding (HF modeling_wav2vec2.py:326-379,690-693 via ref:src/model/wav2vec.py:174):

@@ -20,6 +20,21 @@ def test_header_symbols_exported(a2f_lib):
     assert not missing, f"declared in include/a2f.h but not exported: {missing}"
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/a2f.h must compile as C (a declaration that slipped inside a struct body would
+    still be valid C++, and did go unnoticed once)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "a2f.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_binding_covers_header():
     import a2f_b200
 

@@ -227,6 +227,42 @@ def test_gemm_ln_fused_epilogue(a2f_lib, dev, M, N, K):
     assert bool(((pre.float().cpu() - x).abs() <= 2.0 ** -8 * (x.abs() + 1.0)).all())
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,F", [(4800, 768, 3072), (257, 768, 3072), (1, 768, 3072), (9000, 768, 3072), (12000, 768, 3072),
+                                   (700, 512, 1024), (300, 256, 1024), (300, 256, 256)])
+def test_ffn_ln_one_kernel_equals_two(a2f_lib, dev, M, N, F):
+    """a2f_ffn_ln (W1 + GELU + W2 + residual + LayerNorm in one kernel; the intermediate goes TMA store -> L2 -> TMA load
+    between CTAs of a cluster, ordered by cluster-scope mbarriers) must give the SAME bits as a2f_gemm(GELU) followed by
+    a2f_gemm_ln, and match torch fp32.  Shapes: the bench batch, ragged / single-row blocks, more row blocks than resident
+    clusters (the per-round barriers wrap their parity), 2- and 1-pair clusters, 1 to 4 phase-1 tiles per pair."""
+    from a2f_b200 import ops, lib as L
+    g = torch.Generator().manual_seed(M + N + F)
+    x = torch.randn(M, N, generator=g).bfloat16().to(dev)
+    w1 = (torch.randn(F, N, generator=g) * N ** -0.5).bfloat16().to(dev)
+    w2 = (torch.randn(N, F, generator=g) * F ** -0.5).bfloat16().to(dev)
+    b1, b2 = (0.1 * torch.randn(F, generator=g)).to(dev), (0.1 * torch.randn(N, generator=g)).to(dev)
+    gamma, beta = (torch.rand(N, generator=g) + 0.5).to(dev), (0.1 * torch.randn(N, generator=g)).to(dev)
+    f_ref = torch.empty((M, F), dtype=torch.bfloat16, device=dev)
+    want = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    ops.gemm(x, w1, f_ref, bias=b1, act=L.ACT_GELU, backend=L.TCGEN05)
+    ops.gemm_ln(f_ref, w2, b2, x, gamma, beta, want)
+    for rep in range(3):                                # repeated: a stale scratch from the previous run must not be read
+        scratch = torch.full((M, F), float("nan"), dtype=torch.bfloat16, device=dev) if rep == 0 else scratch
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+        ops.ffn_ln(x, w1, b1, w2, b2, x, gamma, beta, scratch, out)
+        torch.cuda.synchronize()
+        assert torch.equal(scratch, f_ref), rep
+        assert torch.equal(out, want), (rep, float((out.float() - want.float()).abs().max()))
+        scratch.add_(1.0)                               # poison: the next run has to overwrite every element it reads
+    xf = x.float()
+    ref = torch.nn.functional.layer_norm(
+        xf + torch.nn.functional.gelu(xf @ w1.float().t() + b1, approximate="tanh").bfloat16().float() @ w2.float().t() + b2,
+        (N,), gamma, beta, 1e-5)
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -7 * (ref.abs() + 1.0)
+    assert bool((err <= tol).all()), float(err.max())
+
+
 @pytest.mark.parametrize("M,N,K,act,use_resid", [(4800, 3072, 768, 2, False), (4800, 2304, 768, 0, False), (9600, 768, 256, 0, True),
                                                   (2400, 3072, 128, 0, False), (40000, 512, 192, 2, False)])
 def test_tcgen05_pair_kernel_tail_split(a2f_lib, dev, M, N, K, act, use_resid):
