@@ -1,0 +1,69 @@
+// Throughput of the special-function unit flavours a GELU can be built from, in results per clock per SM (sm_100a).
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/mufu_rates tools/mb/mufu_rates.cu && /tmp/mufu_rates
+// Every thread runs 8 independent chains of the op (no memory traffic); 148 x 8 CTAs of 256 threads.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+enum { EX2 = 0, RCP = 1, TANH = 2, TANH_H2 = 3, TANH_BF2 = 4, EX2_H2 = 5, FMA = 6, FMA2 = 7 };
+
+template <int OP> __device__ __forceinline__ unsigned step(unsigned v) {
+    unsigned r;
+    float f = __uint_as_float(v), g;
+    if (OP == EX2) { asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(f)); return __float_as_uint(g); }
+    if (OP == RCP) { asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(f)); return __float_as_uint(g); }
+    if (OP == TANH) { asm volatile("tanh.approx.f32 %0, %1;" : "=f"(g) : "f"(f)); return __float_as_uint(g); }
+    if (OP == TANH_H2) { asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+    if (OP == TANH_BF2) { asm volatile("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+    if (OP == EX2_H2) { asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+    if (OP == FMA) { asm volatile("fma.rn.f32 %0, %1, %1, %1;" : "=f"(g) : "f"(f)); return __float_as_uint(g); }
+    return v;
+}
+
+template <int OP> __global__ void __launch_bounds__(256) k(unsigned* out, int iters, unsigned seed) {
+    unsigned v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = seed + threadIdx.x * 8 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = step<OP>(v[i]);
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s ^= v[i];
+    if (s == 0x12345678u) out[0] = s;
+}
+
+template <int OP> void run(const char* name, int per_op, int sms, double mhz) {
+    unsigned* d;
+    cudaMalloc(&d, 4);
+    const int iters = 4096, grid = sms * 8;
+    k<OP><<<grid, 256>>>(d, 16, 0x3f000000u);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    k<OP><<<grid, 256>>>(d, iters, 0x3f000000u);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    const double ops = (double)grid * 256 * 8 * iters * per_op;
+    printf("%-22s %8.3f ms  %7.2f results/clk/SM (at %.0f MHz)\n", name, ms, ops / (ms * 1e-3) / (mhz * 1e6) / sms, mhz);
+    cudaFree(d);
+}
+
+int main() {
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, 0);
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    const double mhz = khz / 1e3;
+    const int sms = p.multiProcessorCount;
+    run<FMA>("fma.f32 (reference)", 1, sms, mhz);
+    run<EX2>("ex2.approx.f32", 1, sms, mhz);
+    run<RCP>("rcp.approx.f32", 1, sms, mhz);
+    run<TANH>("tanh.approx.f32", 1, sms, mhz);
+    run<TANH_H2>("tanh.approx.f16x2", 2, sms, mhz);
+    run<TANH_BF2>("tanh.approx.bf16x2", 2, sms, mhz);
+    run<EX2_H2>("ex2.approx.f16x2", 2, sms, mhz);
+    return 0;
+}
