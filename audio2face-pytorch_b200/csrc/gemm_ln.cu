@@ -96,7 +96,7 @@ A2F_D void mbar_wait_cluster_acquire(uint64_t* bar, uint32_t parity) {
 }
 
 // One 128-row x 256-column tile of the LayerNorm epilogue (8 epilogue warps of one CTA; see the header): residual fetch,
-// pass 1, statistics exchange over the cluster, pass 2, TMA store.  Shared by gemm_ln_kernel and ffn_ln_kernel.
+// pass 1, statistics exchange over the cluster, pass 2, TMA store.  Shared by gemm_ln_kernel and enc_block_kernel.
 template <int NP>
 A2F_D void ln_tile_epilogue(const CUtensorMap* map_r, const CUtensorMap* map_c, const float* sParam, float2* sStats,
                             uint64_t* rbar, uint64_t* stat_bar, uint64_t* tfull, uint32_t tfull_phase, uint64_t* tempty,
@@ -379,72 +379,149 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const LnParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The whole feed-forward block of an encoder layer in ONE kernel:
-//     out = LayerNorm(x + W2 gelu(W1 x + b1) + b2) * gamma + beta          (HF modeling_wav2vec2.py:551-609)
-// Same cluster of NP CTA pairs per 256-row block as gemm_ln_kernel.  Per row block every pair runs
-//   phase 1  TP = F / (256 NP) tiles of  f = gelu(x W1^T + b1)  (tile t of pair p = columns [256 (t NP + p), +256) of f), each
-//            stored (bf16, TMA) to the scratch f [M, F];  after the stores of tile t have COMPLETED the two epilogue leaders
-//            arrive (release.cluster) on f_bar[t] of the NP CTAs that own the same 128 rows
-//   phase 2  one 256-column tile of  f W2^T  over K = F: its producer waits (acquire.cluster) on f_bar[t] before the first
-//            k-block of columns [768 t, 768 t + 768) -- round t of ALL pairs -- so only the last round is ever waited for,
-//            and that one finished while the first three quarters of the K loop ran;  then the LayerNorm epilogue.
-// The five tiles of a row block go through the same smem ring and the same two TMEM accumulators back to back: the tensor
-// pipe never drains between the two GEMMs, there is one launch / prologue / tail instead of two, and the kernel uses
-// 19 x 6 = 114 SMs for the whole block instead of 148 SMs with a 3.08-wave quantisation followed by 114.
-// f makes the L2 round trip (1.5 MB per row block: too large for shared memory), exactly like between two launches.
-struct FfnMaps {
-    CUtensorMap x, w1, f, w2, c, r;
+// Everything of an encoder layer that is local to a block of rows, in ONE kernel  (HF modeling_wav2vec2.py:551-609):
+//     h1    = LayerNorm(h_in + att Wo^T + bo)                    phase 0   (optional)
+//     f     = gelu(h1 W1^T + b1)                                 phase 1   TP = F / (256 NP) tiles per pair
+//     h_out = LayerNorm(h1 + f W2^T + b2)                        phase 2
+//     qkv   = h_out Wq^T + bq   (in-projection of the NEXT layer) phase 3   (optional) NQT = NQ / (256 NP) tiles per pair
+// Only the attention itself mixes rows, so a layer is two launches: attention, then this kernel.  Same cluster of NP CTA
+// pairs per 256-row block as gemm_ln_kernel; pair p owns columns [256 p, +256) of the LayerNorm tiles and tile t of a
+// multi-tile phase = columns [256 (t NP + p), +256).  The tiles of a row block go through the same smem ring and the same two
+// TMEM accumulators back to back: the tensor pipe only drains where the algorithm forces it (the two LayerNorms: every
+// column of a row has to exist before the next GEMM can read the row).
+// Hand-over between phases: a phase's output is stored with TMA (bf16, stays in L2); when the stores of a tile have
+// COMPLETED the two epilogue leaders arrive (release.cluster) on a `pub` mbarrier of the NP CTAs that own the same 128
+// rows; the producer warp of those CTAs waits (acquire.cluster) before its first TMA load of that data.  f is published
+// per round t (columns [768 t, +768) = tile t of all pairs) and phase 2 waits for round t only at k-block 12 t, so the
+// last round is waited for while three quarters of the K loop are still ahead.
+// Results are bit-identical to a2f_gemm_ln / a2f_gemm(GELU) / a2f_gemm_ln / a2f_gemm run one after the other.
+struct BlkMaps {
+    CUtensorMap att, wo, hin, h1, w1, f, w2, c, wq, q;
 };
 
-struct FfnParams {
-    int M, N, F, K1;
-    int tiles_m, kb1, kb2, tp;      // row blocks; k-blocks of phase 1 / 2; phase-1 tiles per pair
+struct BlkParams {
+    int M, N;
+    int tiles_m;
+    int kb0, kb1, kb2, kb3;         // k-blocks of the four phases
+    int tp, nqt;                    // tiles per pair in phases 1 and 3
+    int has_p0, has_p3;
+    const float* bias_o; const float* gamma1; const float* beta1;
     const float* bias1;
-    const float* bias2;
-    const float* gamma;
-    const float* beta;
+    const float* bias2; const float* gamma2; const float* beta2;
+    const float* bias_q;
     float eps;
-    unsigned long long* timeline;   // debug (a2f_debug_set_timeline): 16 clock64 stamps per CTA
+    unsigned long long* timeline;   // debug (a2f_debug_set_timeline): 16 stamps per CTA (clock64, then globaltimer)
 };
 
-A2F_D unsigned long long ffn_gtimer() {
+A2F_D unsigned long long blk_gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define FFN_STAMP(slot) do { if (p.timeline) { p.timeline[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
-                                                p.timeline[(gridDim.x + blockIdx.x) * 16 + (slot)] = ffn_gtimer(); } } while (0)
+#define BLK_STAMP(slot) do { if (p.timeline) { p.timeline[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
+                                                p.timeline[(gridDim.x + blockIdx.x) * 16 + (slot)] = blk_gtimer(); } } while (0)
 
-constexpr int FFN_MAX_TP = 4;
+constexpr int BLK_MAX_TP = 4;       // phase-1 tiles per pair (F <= 4 N)
+constexpr int BLK_MAX_NQT = 3;      // phase-3 tiles per pair (NQ <= 3 N)
 
-template <int NP> struct FfnCfg {
+template <int NP> struct BlkCfg {
     static constexpr int STATS_BYTES = LnCfg<NP>::STATS_BYTES;
-    static constexpr int PARAM_BYTES = (3 + FFN_MAX_TP) * LBN * 4;   // bias2 | gamma | beta | bias1 of the pair's TP tiles
+    // bias_o | gamma1 | beta1 | bias2 | gamma2 | beta2 | bias1 [TP] | bias_q [NQT], 256 floats each
+    static constexpr int PARAM_BYTES = (6 + BLK_MAX_TP + BLK_MAX_NQT) * LBN * 4;
     static constexpr size_t SMEM_BYTES = (size_t)L_STAGES * L_STAGE_BYTES + 4 * L_EPI_BYTES + STATS_BYTES + PARAM_BYTES + 256;
 };
 
 A2F_D void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// epilogue leader: the TMA stores of this half are in L2 -> tell the producers of the NP CTAs that hold the same rows
+template <int NP> A2F_D void blk_publish(uint64_t* bar, int hr) {
+    tma_store_wait_all();                              // writes complete, not only read out of shared memory
+    fence_proxy_async_all();
+    const uint32_t b = smem_u32(bar);
+#pragma unroll
+    for (int d = 0; d < NP; ++d) mbar_arrive_cluster_release(map_to_rank(b, (uint32_t)(2 * d + hr)));
+}
+
+// One 128 x 256 tile of a plain epilogue (8 epilogue warps): out = act(acc + bias) -> bf16 -> TMA store at (col_base, row_base)
+template <bool GELU>
+A2F_D void blk_plain_tile(const CUtensorMap* map_out, const float* tb, uint64_t* tfull, uint32_t tfull_phase, uint64_t* tempty,
+                          uint32_t t_acc, int col_base, int row_base, int half, int q, int lane, bool leader, int bar_id,
+                          uint8_t* stage_base) {
+    const int r_tile = q * 32 + lane;
+    if (leader) tma_store_wait_read();                 // both staging buffers of this half are free again
+    named_bar_sync(bar_id, 128);
+    mbar_wait(tfull, tfull_phase);
+    tc_fence_after();
+    const uint32_t t_row = t_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+        const int col0 = (half + 2 * j) * L_SBW;
+        uint8_t* stage_buf = stage_base + j * L_EPI_BYTES;
+        uint8_t* rowp = stage_buf + r_tile * 128;
+        float v[L_SBW];
+        tmem_ld_32x32(t_row + col0, v);
+        tmem_ld_32x32(t_row + col0 + 32, v + 32);
+        tmem_ld_wait();
+        if (j == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty);
+        }
+#pragma unroll
+        for (int e = 0; e < L_SBW; e += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(tb + col0 + e);
+            v[e] += f.x; v[e + 1] += f.y; v[e + 2] += f.z; v[e + 3] += f.w;
+        }
+        if (GELU) {
+#pragma unroll
+            for (int e = 0; e < L_SBW; e += 2) {
+                const float2 r = gelu_fast2(make_float2(v[e], v[e + 1]));
+                v[e] = r.x;
+                v[e + 1] = r.y;
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < L_SBW / 8; ++ch) {
+            uint4 u;
+            u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+            u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+            u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+            u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+            *reinterpret_cast<uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16)) = u;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (leader) {
+            tma_store_2d(map_out, stage_buf, col_base + col0, row_base);
+            tma_store_commit();
+        }
+    }
+}
+
 template <int NP>
 __global__ void __launch_bounds__(L_THREADS, 1)
-ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
-    using Cfg = FfnCfg<NP>;
+enc_block_kernel(const __grid_constant__ BlkMaps maps, const BlkParams p) {
+    using Cfg = BlkCfg<NP>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)L_STAGES * L_A_BYTES;
     uint8_t* sEpi = smem + (size_t)L_STAGES * L_STAGE_BYTES;
     float2* sStats = reinterpret_cast<float2*>(sEpi + 4 * L_EPI_BYTES);
-    float* sParam = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStats) + Cfg::STATS_BYTES);
-    float* sBias1 = sParam + 3 * LBN;                                            // [TP][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sParam) + Cfg::PARAM_BYTES);
+    float* sP0 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStats) + Cfg::STATS_BYTES);   // bias_o | gamma1 | beta1
+    float* sP2 = sP0 + 3 * LBN;                                                  // bias2 | gamma2 | beta2
+    float* sBias1 = sP2 + 3 * LBN;                                               // [TP][256]
+    float* sBiasQ = sBias1 + BLK_MAX_TP * LBN;                                   // [NQT][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sP0) + Cfg::PARAM_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + L_STAGES;
     uint64_t* tfull_bar = bars + 2 * L_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* rbar = tempty_bar + 2;
     uint64_t* stat_bar = rbar + 4;
-    uint64_t* f_bar = stat_bar + 2;                   // [TP] round t of f (this CTA's 128 rows, all F/TP columns) is in L2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(f_bar + FFN_MAX_TP);
+    uint64_t* f_bar = stat_bar + 2;                   // [TP] round t of f (this CTA's 128 rows, 256 NP columns) is in L2
+    uint64_t* h1_bar = f_bar + BLK_MAX_TP;            // h1 (this CTA's 128 rows, all columns) is in L2
+    uint64_t* h2_bar = h1_bar + 1;                    // h_out likewise
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h2_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
@@ -452,17 +529,26 @@ ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
     const int hr = rank & 1;
     const bool is_leader = hr == 0;
     const int cl = (int)cluster_id_x(), n_cl = (int)cluster_count_x();
-    const int TP = p.tp;
+    const int TP = p.tp, NQT = p.has_p3 ? p.nqt : 0;
+    const bool has_p0 = p.has_p0 != 0;
 
-    if (threadIdx.x == 0) FFN_STAMP(0);
+    if (threadIdx.x == 0) BLK_STAMP(0);
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&maps.x);
+        tma_prefetch_desc(&maps.h1);
         tma_prefetch_desc(&maps.w1);
         tma_prefetch_desc(&maps.f);
         tma_prefetch_desc(&maps.w2);
         tma_prefetch_desc(&maps.c);
-        tma_prefetch_desc(&maps.r);
+        if (has_p0) {
+            tma_prefetch_desc(&maps.att);
+            tma_prefetch_desc(&maps.wo);
+            tma_prefetch_desc(&maps.hin);
+        }
+        if (NQT) {
+            tma_prefetch_desc(&maps.wq);
+            tma_prefetch_desc(&maps.q);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < L_STAGES; ++i) {
@@ -475,7 +561,7 @@ ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
             mbar_init(&stat_bar[i], NP * 256);
         }
         for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
-        for (int i = 0; i < FFN_MAX_TP; ++i) mbar_init(&f_bar[i], 2 * NP);      // 2 epilogue leaders x NP CTAs with these rows
+        for (int i = 0; i < BLK_MAX_TP + 2; ++i) mbar_init(&f_bar[i], 2 * NP);  // 2 epilogue leaders x NP CTAs with these rows
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
@@ -484,9 +570,9 @@ ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_sync();
-    if (threadIdx.x == 0) FFN_STAMP(1);
+    if (threadIdx.x == 0) BLK_STAMP(1);
 
-    const int n0 = pr * LBN;                          // this pair's columns of the OUTPUT (phase 2)
+    const int n0 = pr * LBN;                          // this pair's columns of the LayerNorm tiles
     const int kb_round = (NP * LBN) / LBK;            // k-blocks of phase 2 per round of f
 
     if (warp == 0) {
@@ -495,30 +581,39 @@ ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
+            auto load = [&](const CUtensorMap* ma, const CUtensorMap* mbm, int kb, int arow, int brow) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * L_STAGE_BYTES);
+                tma_load_2d_2sm(sA + (size_t)stage * L_A_BYTES, ma, &full_bar[stage], kb * LBK, arow);
+                tma_load_2d_2sm(sB + (size_t)stage * L_B_BYTES, mbm, &full_bar[stage], kb * LBK, brow);
+                if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
+            };
             for (int mb = cl; mb < p.tiles_m; mb += n_cl, ++it) {
                 const int row0 = mb * 2 * LBM + hr * LBM;
+                const int wrow_ln = n0 + hr * (LBN / 2);
+                if (has_p0) {
+                    for (int kb = 0; kb < p.kb0; ++kb) load(&maps.att, &maps.wo, kb, row0, wrow_ln);
+                    mbar_wait_cluster_acquire(h1_bar, it & 1u);   // h1: TMA stores of the NP CTAs with these rows, TMA loads here
+                    fence_proxy_async_all();
+                }
                 for (int t = 0; t < TP; ++t) {
                     const int wrow0 = (t * NP + pr) * LBN + hr * (LBN / 2);
-                    for (int kb = 0; kb < p.kb1; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * L_STAGE_BYTES);
-                        tma_load_2d_2sm(sA + (size_t)stage * L_A_BYTES, &maps.x, &full_bar[stage], kb * LBK, row0);
-                        tma_load_2d_2sm(sB + (size_t)stage * L_B_BYTES, &maps.w1, &full_bar[stage], kb * LBK, wrow0);
-                        if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
-                    }
+                    for (int kb = 0; kb < p.kb1; ++kb) load(&maps.h1, &maps.w1, kb, row0, wrow0);
                 }
-                const int wrow0 = n0 + hr * (LBN / 2);
                 for (int kb = 0; kb < p.kb2; ++kb) {
                     if (kb % kb_round == 0) {
-                        // round kb / kb_round of f: written by TMA stores of the NP CTAs with these rows, read by TMA here
                         mbar_wait_cluster_acquire(&f_bar[kb / kb_round], it & 1u);
                         fence_proxy_async_all();
                     }
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * L_STAGE_BYTES);
-                    tma_load_2d_2sm(sA + (size_t)stage * L_A_BYTES, &maps.f, &full_bar[stage], kb * LBK, row0);
-                    tma_load_2d_2sm(sB + (size_t)stage * L_B_BYTES, &maps.w2, &full_bar[stage], kb * LBK, wrow0);
-                    if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
+                    load(&maps.f, &maps.w2, kb, row0, wrow_ln);
+                }
+                if (NQT) {
+                    mbar_wait_cluster_acquire(h2_bar, it & 1u);
+                    fence_proxy_async_all();
+                    for (int t = 0; t < NQT; ++t) {
+                        const int wrow0 = (t * NP + pr) * LBN + hr * (LBN / 2);
+                        for (int kb = 0; kb < p.kb3; ++kb) load(&maps.c, &maps.wq, kb, row0, wrow0);
+                    }
                 }
             }
         }
@@ -533,16 +628,17 @@ ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            const int t_p1 = has_p0 ? 1 : 0, t_p2 = t_p1 + TP, n_tiles = t_p2 + 1 + NQT;
             for (int mb = cl; mb < p.tiles_m; mb += n_cl) {
-                for (int t = 0; t <= TP; ++t) {
-                    const int nkb = t < TP ? p.kb1 : p.kb2;
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int nkb = t < t_p1 ? p.kb0 : t < t_p2 ? p.kb1 : t == t_p2 ? p.kb2 : p.kb3;
                     mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * LBN);
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        if (mb == cl && t == 0 && kb == 0) FFN_STAMP(2);
+                        if (mb == cl && t == 0 && kb == 0) BLK_STAMP(2);
                         const uint64_t adesc = ln_smem_desc(smem_u32(sA + (size_t)stage * L_A_BYTES));
                         const uint64_t bdesc = ln_smem_desc(smem_u32(sB + (size_t)stage * L_B_BYTES));
 #pragma unroll
@@ -552,7 +648,12 @@ ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
                         if (++stage == L_STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit_pair(&tfull_bar[acc], pair_mask);
-                    if (mb == cl) FFN_STAMP(3 + t);
+                    if (mb == cl) {                    // stamps: 3 = phase 0, 4 = last phase-1 tile, 5 = phase 2, 6 = last phase-3 tile
+                        if (t < t_p1) BLK_STAMP(3);
+                        else if (t == t_p2 - 1) BLK_STAMP(4);
+                        else if (t == t_p2) BLK_STAMP(5);
+                        else if (t == n_tiles - 1) BLK_STAMP(6);
+                    }
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
@@ -567,100 +668,80 @@ ffn_ln_kernel(const __grid_constant__ FfnMaps maps, const FfnParams p) {
         const bool leader = ((ew & 3) == 0) && lane == 0;
         const int bar_id = 1 + half;
         uint8_t* stage_base = sEpi + half * 2 * L_EPI_BYTES;
-        const int r_tile = q * 32 + lane;
         {
             const int c = ew * 32 + lane;
-            sParam[c] = p.bias2 ? __ldg(p.bias2 + n0 + c) : 0.f;
-            sParam[LBN + c] = __ldg(p.gamma + n0 + c);
-            sParam[2 * LBN + c] = __ldg(p.beta + n0 + c);
+            if (has_p0) {
+                sP0[c] = p.bias_o ? __ldg(p.bias_o + n0 + c) : 0.f;
+                sP0[LBN + c] = __ldg(p.gamma1 + n0 + c);
+                sP0[2 * LBN + c] = __ldg(p.beta1 + n0 + c);
+            }
+            sP2[c] = p.bias2 ? __ldg(p.bias2 + n0 + c) : 0.f;
+            sP2[LBN + c] = __ldg(p.gamma2 + n0 + c);
+            sP2[2 * LBN + c] = __ldg(p.beta2 + n0 + c);
             for (int t = 0; t < TP; ++t) sBias1[t * LBN + c] = p.bias1 ? __ldg(p.bias1 + (t * NP + pr) * LBN + c) : 0.f;
+            for (int t = 0; t < NQT; ++t) sBiasQ[t * LBN + c] = p.bias_q ? __ldg(p.bias_q + (t * NP + pr) * LBN + c) : 0.f;
         }
         named_bar_sync(3, 256);
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint32_t it = 0;
+        uint32_t it = 0, ln_it = 0;
         const float inv_n = 1.0f / (float)p.N;
-        for (int mb = cl; mb < p.tiles_m; mb += n_cl, ++it) {
-            const int row_base = mb * 2 * LBM + hr * LBM;
-            // ---- phase 1: TP tiles of gelu(x W1^T + b1) -> f ----
-            for (int t = 0; t < TP; ++t) {
-                const int fcol0 = (t * NP + pr) * LBN;
-                const float* tb = sBias1 + t * LBN;
-                if (leader) tma_store_wait_read();                 // both staging buffers of this half are free again
-                named_bar_sync(bar_id, 128);
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * LBN);
-#pragma unroll 1
-                for (int j = 0; j < 2; ++j) {
-                    const int col0 = (half + 2 * j) * L_SBW;
-                    uint8_t* stage_buf = stage_base + j * L_EPI_BYTES;
-                    uint8_t* rowp = stage_buf + r_tile * 128;
-                    float v[L_SBW];
-                    tmem_ld_32x32(t_row + col0, v);
-                    tmem_ld_32x32(t_row + col0 + 32, v + 32);
-                    tmem_ld_wait();
-                    if (j == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
-                    }
-#pragma unroll
-                    for (int e = 0; e < L_SBW; e += 4) {
-                        const float4 f = *reinterpret_cast<const float4*>(tb + col0 + e);
-                        v[e] += f.x; v[e + 1] += f.y; v[e + 2] += f.z; v[e + 3] += f.w;
-                    }
-#pragma unroll
-                    for (int e = 0; e < L_SBW; e += 2) {
-                        const float2 r = gelu_fast2(make_float2(v[e], v[e + 1]));
-                        v[e] = r.x;
-                        v[e + 1] = r.y;
-                    }
-#pragma unroll
-                    for (int ch = 0; ch < L_SBW / 8; ++ch) {
-                        uint4 u;
-                        u.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
-                        u.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
-                        u.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
-                        u.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
-                        *reinterpret_cast<uint4*>(rowp + ((ch ^ (r_tile & 7)) * 16)) = u;
-                    }
-                    fence_proxy_async_smem();
-                    named_bar_sync(bar_id, 128);
-                    if (leader) {
-                        tma_store_2d(&maps.f, stage_buf, fcol0 + col0, row_base);
-                        tma_store_commit();
-                    }
-                }
-                if (leader) {
-                    // the two blocks are in L2 (writes complete, not only read out of shared memory): publish round t to
-                    // the producers of the NP CTAs that hold these rows
-                    tma_store_wait_all();
-                    fence_proxy_async_all();
-                    const uint32_t fb = smem_u32(&f_bar[t]);
-#pragma unroll
-                    for (int d = 0; d < NP; ++d) mbar_arrive_cluster_release(map_to_rank(fb, (uint32_t)(2 * d + hr)));
-                    if (mb == cl && half == 0) FFN_STAMP(8 + t);
-                }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
-            }
-            // ---- phase 2: LayerNorm(x + f W2^T + b2) ----
-            if (mb == cl && threadIdx.x == 64) FFN_STAMP(12);
-            ln_tile_epilogue<NP>(&maps.r, &maps.c, sParam, sStats, rbar, stat_bar, &tfull_bar[acc], acc_phase, &tempty_bar[acc],
-                                 tmem_base + (uint32_t)(acc * LBN), n0, pr, hr, half, q, lane, leader, bar_id, stage_base,
-                                 row_base, it, inv_n, p.eps, nullptr, 0, p.M);
-            if (mb == cl && threadIdx.x == 64) FFN_STAMP(13);
+        auto next_acc = [&]() {
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+        };
+        for (int mb = cl; mb < p.tiles_m; mb += n_cl, ++it) {
+            const int row_base = mb * 2 * LBM + hr * LBM;
+            const bool first = mb == cl && half == 0;
+            // ---- phase 0: h1 = LayerNorm(h_in + att Wo^T + bo) ----
+            if (has_p0) {
+                ln_tile_epilogue<NP>(&maps.hin, &maps.h1, sP0, sStats, rbar, stat_bar, &tfull_bar[acc], acc_phase, &tempty_bar[acc],
+                                     tmem_base + (uint32_t)(acc * LBN), n0, pr, hr, half, q, lane, leader, bar_id, stage_base,
+                                     row_base, ln_it, inv_n, p.eps, nullptr, 0, p.M);
+                ++ln_it;
+                if (leader) {
+                    blk_publish<NP>(h1_bar, hr);
+                    if (first) BLK_STAMP(7);
+                }
+                next_acc();
+            }
+            // ---- phase 1: TP tiles of gelu(h1 W1^T + b1) -> f ----
+            for (int t = 0; t < TP; ++t) {
+                blk_plain_tile<true>(&maps.f, sBias1 + t * LBN, &tfull_bar[acc], acc_phase, &tempty_bar[acc],
+                                     tmem_base + (uint32_t)(acc * LBN), (t * NP + pr) * LBN, row_base, half, q, lane, leader, bar_id,
+                                     stage_base);
+                if (leader) {
+                    blk_publish<NP>(&f_bar[t], hr);
+                    if (first) BLK_STAMP(8 + t);
+                }
+                next_acc();
+            }
+            // ---- phase 2: h_out = LayerNorm(h1 + f W2^T + b2) ----
+            if (mb == cl && threadIdx.x == 64) BLK_STAMP(12);
+            ln_tile_epilogue<NP>(&maps.h1, &maps.c, sP2, sStats, rbar, stat_bar, &tfull_bar[acc], acc_phase, &tempty_bar[acc],
+                                 tmem_base + (uint32_t)(acc * LBN), n0, pr, hr, half, q, lane, leader, bar_id, stage_base,
+                                 row_base, ln_it, inv_n, p.eps, nullptr, 0, p.M);
+            ++ln_it;
+            if (mb == cl && threadIdx.x == 64) BLK_STAMP(13);
+            next_acc();
+            // ---- phase 3: qkv of the next layer = h_out Wq^T + bq ----
+            if (NQT) {
+                if (leader) blk_publish<NP>(h2_bar, hr);
+                for (int t = 0; t < NQT; ++t) {
+                    blk_plain_tile<false>(&maps.q, sBiasQ + t * LBN, &tfull_bar[acc], acc_phase, &tempty_bar[acc],
+                                          tmem_base + (uint32_t)(acc * LBN), (t * NP + pr) * LBN, row_base, half, q, lane, leader,
+                                          bar_id, stage_base);
+                    next_acc();
+                }
+            }
         }
         if (leader) tma_store_wait_all();
-        if (threadIdx.x == 64) FFN_STAMP(14);
+        if (threadIdx.x == 64) BLK_STAMP(14);
     }
 
     tc_fence_before();
     cluster_sync_all();
-    if (threadIdx.x == 0) FFN_STAMP(15);
+    if (threadIdx.x == 0) BLK_STAMP(15);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_2sm<512>(tmem_base);
@@ -715,9 +796,9 @@ int launch_gemm_ln(LnMaps& maps, const LnParams& p, cudaStream_t s) {
 
 
 template <int NP>
-int launch_ffn_ln(FfnMaps& maps, const FfnParams& p, cudaStream_t s) {
-    using Cfg = FfnCfg<NP>;
-    auto kern = ffn_ln_kernel<NP>;
+int launch_enc_block(BlkMaps& maps, const BlkParams& p, cudaStream_t s) {
+    using Cfg = BlkCfg<NP>;
+    auto kern = enc_block_kernel<NP>;
     static bool attr_done = false;
     static int max_clusters = 0;
     if (!attr_done) {
@@ -819,40 +900,60 @@ int gemm_ln_tc(const void* A, long long lda, const void* W, long long ldw, const
 }
 
 
-// x [M,K1], W1 [F,K1], W2 [N,F], resid / out [M,N], scratch f [M,F]; all bf16.  N = 256 NP, F a multiple of 256 NP (at most 4).
-int ffn_ln_tc(const void* X, long long ldx, const void* W1, long long ldw1, const float* bias1, const void* W2, long long ldw2,
-              const float* bias2, const void* resid, long long ldr, const float* gamma, const float* beta, float eps,
-              void* scratch, long long ldf, void* out, long long ldo, int M, int N, int F, int K1, cudaStream_t s) {
+// All operands bf16 with 16-byte aligned bases and row strides that are multiples of 8 elements (a2f.h: a2f_encoder_block_args).
+int enc_block_tc(const a2f_encoder_block_args& g, cudaStream_t s) {
+    const int M = g.M, N = g.N, F = g.F;
     if (M <= 0) return A2F_OK;
-    A2F_REQUIRE(N % LBN == 0 && N / LBN >= 1 && N / LBN <= 3, "a2f_ffn_ln: N must be 256, 512 or 768");
-    A2F_REQUIRE(F > 0 && F % N == 0 && F / N <= FFN_MAX_TP, "a2f_ffn_ln: F must be N, 2N, 3N or 4N");
-    A2F_REQUIRE(K1 > 0 && K1 % 8 == 0, "a2f_ffn_ln: K1 must be a positive multiple of 8");
-    A2F_REQUIRE(ldx % 8 == 0 && ldw1 % 8 == 0 && ldw2 % 8 == 0 && ldr % 8 == 0 && ldf % 8 == 0 && ldo % 8 == 0,
-                "a2f_ffn_ln: row strides must be multiples of 8 elements");
-    A2F_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(W2) |
-                  reinterpret_cast<uintptr_t>(resid) | reinterpret_cast<uintptr_t>(scratch) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
-                "a2f_ffn_ln: operands must be 16-byte aligned");
-    FfnMaps maps;
+    const bool p0 = g.att != nullptr, p3 = g.wq != nullptr;
+    A2F_REQUIRE(N % LBN == 0 && N / LBN >= 1 && N / LBN <= 3, "a2f_encoder_block: N must be 256, 512 or 768");
+    A2F_REQUIRE(F > 0 && F % N == 0 && F / N <= BLK_MAX_TP, "a2f_encoder_block: F must be N, 2N, 3N or 4N");
+    A2F_REQUIRE(g.h1 && g.w1 && g.f && g.w2 && g.h_out && g.ln2_g && g.ln2_b, "a2f_encoder_block: NULL operand");
+    A2F_REQUIRE(!p0 || (g.wo && g.h_in && g.ln1_g && g.ln1_b), "a2f_encoder_block: att given without wo / h_in / ln1");
+    A2F_REQUIRE(!p3 || (g.qkv && g.NQ > 0 && g.NQ % N == 0 && g.NQ / N <= BLK_MAX_NQT),
+                "a2f_encoder_block: wq given without qkv, or NQ not N, 2N or 3N");
+    const long long lds[] = {g.ld_h1, g.ld_w1, g.ld_f, g.ld_w2, g.ld_hout, p0 ? g.ld_att : 8, p0 ? g.ld_wo : 8, p0 ? g.ld_hin : 8,
+                             p3 ? g.ld_wq : 8, p3 ? g.ld_qkv : 8};
+    for (long long ld : lds) A2F_REQUIRE(ld > 0 && ld % 8 == 0, "a2f_encoder_block: row strides must be positive multiples of 8 elements");
+    const void* ptrs[] = {g.h1, g.w1, g.f, g.w2, g.h_out, g.att, g.wo, g.h_in, g.wq, g.qkv};
+    for (const void* q : ptrs) A2F_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "a2f_encoder_block: operands must be 16-byte aligned");
+    A2F_REQUIRE(g.h_out != g.h1 && g.f != g.h1 && g.f != g.h_out, "a2f_encoder_block: h1, f and h_out must be distinct buffers");
+    BlkMaps maps;
     memset(&maps, 0, sizeof(maps));
     int rc;
-    if ((rc = ln_map2d(&maps.x, X, (uint64_t)K1, (uint64_t)M, ldx, LBM)) != A2F_OK) return rc;
-    if ((rc = ln_map2d(&maps.w1, W1, (uint64_t)K1, (uint64_t)F, ldw1, LBN / 2)) != A2F_OK) return rc;
-    if ((rc = ln_map2d(&maps.f, scratch, (uint64_t)F, (uint64_t)M, ldf, LBM)) != A2F_OK) return rc;
-    if ((rc = ln_map2d(&maps.w2, W2, (uint64_t)F, (uint64_t)N, ldw2, LBN / 2)) != A2F_OK) return rc;
-    if ((rc = ln_map2d(&maps.c, out, (uint64_t)N, (uint64_t)M, ldo, LBM)) != A2F_OK) return rc;
-    if ((rc = ln_map2d(&maps.r, resid, (uint64_t)N, (uint64_t)M, ldr, LBM)) != A2F_OK) return rc;
-    FfnParams p;
-    p.M = M; p.N = N; p.F = F; p.K1 = K1;
+    if ((rc = ln_map2d(&maps.h1, g.h1, (uint64_t)N, (uint64_t)M, g.ld_h1, LBM)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.w1, g.w1, (uint64_t)N, (uint64_t)F, g.ld_w1, LBN / 2)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.f, g.f, (uint64_t)F, (uint64_t)M, g.ld_f, LBM)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.w2, g.w2, (uint64_t)F, (uint64_t)N, g.ld_w2, LBN / 2)) != A2F_OK) return rc;
+    if ((rc = ln_map2d(&maps.c, g.h_out, (uint64_t)N, (uint64_t)M, g.ld_hout, LBM)) != A2F_OK) return rc;
+    if (p0) {
+        if ((rc = ln_map2d(&maps.att, g.att, (uint64_t)N, (uint64_t)M, g.ld_att, LBM)) != A2F_OK) return rc;
+        if ((rc = ln_map2d(&maps.wo, g.wo, (uint64_t)N, (uint64_t)N, g.ld_wo, LBN / 2)) != A2F_OK) return rc;
+        if ((rc = ln_map2d(&maps.hin, g.h_in, (uint64_t)N, (uint64_t)M, g.ld_hin, LBM)) != A2F_OK) return rc;
+    }
+    if (p3) {
+        if ((rc = ln_map2d(&maps.wq, g.wq, (uint64_t)N, (uint64_t)g.NQ, g.ld_wq, LBN / 2)) != A2F_OK) return rc;
+        if ((rc = ln_map2d(&maps.q, g.qkv, (uint64_t)g.NQ, (uint64_t)M, g.ld_qkv, LBM)) != A2F_OK) return rc;
+    }
+    BlkParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N;
     p.tiles_m = (M + 2 * LBM - 1) / (2 * LBM);
-    p.kb1 = (K1 + LBK - 1) / LBK;
+    p.kb0 = p.kb1 = p.kb3 = N / LBK;
     p.kb2 = F / LBK;
     p.tp = F / N;
-    p.bias1 = bias1; p.bias2 = bias2; p.gamma = gamma; p.beta = beta; p.eps = eps;
+    p.nqt = p3 ? g.NQ / N : 0;
+    p.has_p0 = p0 ? 1 : 0;
+    p.has_p3 = p3 ? 1 : 0;
+    p.bias_o = g.bo; p.gamma1 = g.ln1_g; p.beta1 = g.ln1_b;
+    p.bias1 = g.b1;
+    p.bias2 = g.b2; p.gamma2 = g.ln2_g; p.beta2 = g.ln2_b;
+    p.bias_q = g.bq;
+    p.eps = g.eps;
     p.timeline = debug_timeline();
     switch (N / LBN) {
-        case 1: return launch_ffn_ln<1>(maps, p, s);
-        case 2: return launch_ffn_ln<2>(maps, p, s);
-        default: return launch_ffn_ln<3>(maps, p, s);
+        case 1: return launch_enc_block<1>(maps, p, s);
+        case 2: return launch_enc_block<2>(maps, p, s);
+        default: return launch_enc_block<3>(maps, p, s);
     }
 }
 
@@ -869,14 +970,26 @@ extern "C" int a2f_gemm_ln(const void* A, long long lda, const void* W, long lon
                            a2f::as_stream(stream));
 }
 
-extern "C" int a2f_ffn_ln(const void* X, long long ldx, const void* W1, long long ldw1, const float* bias1, const void* W2,
-                          long long ldw2, const float* bias2, const void* resid, long long ldr, const float* gamma,
-                          const float* beta, float eps, void* scratch, long long ldf, void* out, long long ldo, int M, int N,
-                          int F, int K1, void* stream) {
+extern "C" int a2f_encoder_block(const a2f_encoder_block_args* args, void* stream) {
     int rc = a2f::require_sm100();
     if (rc != A2F_OK) return rc;
-    A2F_REQUIRE(X && W1 && W2 && resid && gamma && beta && scratch && out, "a2f_ffn_ln: NULL operand");
-    A2F_REQUIRE(M >= 0 && N > 0 && F > 0 && K1 > 0, "a2f_ffn_ln: bad M/N/F/K1");
-    return a2f::ffn_ln_tc(X, ldx, W1, ldw1, bias1, W2, ldw2, bias2, resid, ldr, gamma, beta, eps, scratch, ldf, out, ldo, M, N,
-                          F, K1, a2f::as_stream(stream));
+    A2F_REQUIRE(args != nullptr, "a2f_encoder_block: NULL args");
+    A2F_REQUIRE(args->M >= 0 && args->N > 0 && args->F > 0, "a2f_encoder_block: bad M/N/F");
+    return a2f::enc_block_tc(*args, a2f::as_stream(stream));
+}
+
+extern "C" int a2f_ffn_ln(const void* X, long long ldx, const void* W1, long long ldw1, const float* bias1, const void* W2,
+                          long long ldw2, const float* bias2, const float* gamma, const float* beta, float eps, void* scratch,
+                          long long ldf, void* out, long long ldo, int M, int N, int F, void* stream) {
+    a2f_encoder_block_args g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = N; g.F = F;
+    g.h1 = const_cast<void*>(X); g.ld_h1 = ldx;
+    g.w1 = W1; g.ld_w1 = ldw1; g.b1 = bias1;
+    g.f = scratch; g.ld_f = ldf;
+    g.w2 = W2; g.ld_w2 = ldw2; g.b2 = bias2;
+    g.ln2_g = gamma; g.ln2_b = beta;
+    g.h_out = out; g.ld_hout = ldo;
+    g.eps = eps;
+    return a2f_encoder_block(&g, stream);
 }

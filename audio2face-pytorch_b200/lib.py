@@ -60,6 +60,24 @@ class CopyJob(C.Structure):
     ]
 
 
+class EncoderBlockArgs(C.Structure):
+    """a2f_encoder_block_args (include/a2f.h)"""
+    _fields_ = [
+        ("M", c_int), ("N", c_int), ("F", c_int),
+        ("att", c_void_p), ("ld_att", c_ll), ("wo", c_void_p), ("ld_wo", c_ll), ("bo", c_void_p),
+        ("h_in", c_void_p), ("ld_hin", c_ll), ("ln1_g", c_void_p), ("ln1_b", c_void_p),
+        ("h1", c_void_p), ("ld_h1", c_ll),
+        ("w1", c_void_p), ("ld_w1", c_ll), ("b1", c_void_p),
+        ("f", c_void_p), ("ld_f", c_ll),
+        ("w2", c_void_p), ("ld_w2", c_ll), ("b2", c_void_p),
+        ("ln2_g", c_void_p), ("ln2_b", c_void_p),
+        ("h_out", c_void_p), ("ld_hout", c_ll),
+        ("wq", c_void_p), ("ld_wq", c_ll), ("bq", c_void_p), ("NQ", c_int),
+        ("qkv", c_void_p), ("ld_qkv", c_ll),
+        ("eps", c_float),
+    ]
+
+
 class DecoderWeights(C.Structure):
     _names = [
         "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b", "ca_in_w", "ca_in_b", "ca_out_w", "ca_out_b",
@@ -87,8 +105,9 @@ _SIGNATURES = {
     "a2f_gemm_wgrad": (c_int, [C.POINTER(WgradArgs), c_int, c_void_p]),
     "a2f_gemm_ln": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_ll,
                             c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
-    "a2f_ffn_ln": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p,
-                           c_float, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "a2f_encoder_block": (c_int, [C.POINTER(EncoderBlockArgs), c_void_p]),
+    "a2f_ffn_ln": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_float,
+                           c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "a2f_posconv": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "a2f_pack_posconv_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "a2f_pack_conv1d_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

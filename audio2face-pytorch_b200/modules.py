@@ -572,9 +572,10 @@ class Faceformer(_A2FModule):
         # bf16 inference: run the encoder's 24 post-LayerNorms inside the GEMM epilogues (a2f_gemm_ln); False = the separate
         # layernorm_kernel launches (A/B switch for profiles/)
         self.fuse_layernorm = True
-        # ... and the whole feed-forward block (W1, GELU, W2, residual, LayerNorm) as ONE kernel (a2f_ffn_ln); False = GEMM +
-        # a2f_gemm_ln (bit-identical results; A/B switch for profiles/)
+        # ... and everything of a layer except the attention as ONE kernel (a2f_encoder_block); False = GEMM and a2f_gemm_ln
+        # launches (bit-identical results; A/B switch for profiles/)
         self.fuse_ffn = True
+        self.fuse_block = "attn_ffn_qkv"
         self.dataset = "vocaset"
         self.period = 60
         self.fps = 60
@@ -739,7 +740,35 @@ class Faceformer(_A2FModule):
         ffn = torch.empty((M, 3072), dtype=dt, device=dev)
         fuse = bf and self.fuse_layernorm
         h1 = torch.empty((M, 768), dtype=dt, device=dev) if fuse else None
-        for blk, W in zip(ae.encoder.layers, P["layers"]):
+        layers = list(zip(ae.encoder.layers, P["layers"]))
+        if fuse and self.fuse_ffn:
+            # Everything of a layer that is local to a block of rows can run as ONE kernel (a2f_encoder_block; cluster of three
+            # CTA pairs per 256-row block): fuse_block selects the phases -- "ffn" (W1, GELU, W2, residual, LayerNorm),
+            # "attn_ffn" (+ attention out-projection and its LayerNorm in front), "attn_ffn_qkv" (+ the NEXT layer's q|k|v
+            # projection behind).  All variants give the same bits; DESIGN.md section 4 has the timings.
+            with_o = self.fuse_block in ("attn_ffn", "attn_ffn_qkv")
+            with_q = self.fuse_block in ("ffn_qkv", "attn_ffn_qkv")
+            h2 = torch.empty((M, 768), dtype=dt, device=dev)
+            for i, (blk, W) in enumerate(layers):
+                if i == 0 or not with_q:
+                    ops.gemm(h, W["qkv_w"], qkv, bias=W["qkv_b"], backend=be)
+                ops.mha(qkv, att, B, T)
+                nxt = layers[i + 1][1] if (with_q and i + 1 < len(layers)) else None
+                kw = {}
+                if with_o:
+                    kw.update(att=att, wo=W["o_w"], bo=blk.attention.out_proj.bias.detach(), h_in=h,
+                              ln1_g=blk.layer_norm.weight.detach(), ln1_b=blk.layer_norm.bias.detach())
+                else:
+                    ops.gemm_ln(att, W["o_w"], blk.attention.out_proj.bias.detach(), h, blk.layer_norm.weight.detach(),
+                                blk.layer_norm.bias.detach(), h1)
+                if nxt is not None:
+                    kw.update(wq=nxt["qkv_w"], bq=nxt["qkv_b"], qkv=qkv)
+                ops.encoder_block(h1, W["f1_w"], blk.feed_forward.intermediate_dense.bias.detach(), W["f2_w"],
+                                  blk.feed_forward.output_dense.bias.detach(), blk.final_layer_norm.weight.detach(),
+                                  blk.final_layer_norm.bias.detach(), ffn, h2, **kw)
+                h, h2 = h2, h
+            return h
+        for blk, W in layers:
             ops.gemm(h, W["qkv_w"], qkv, bias=W["qkv_b"], backend=be)
             ops.mha(qkv, att, B, T)
             if fuse:
@@ -747,11 +776,6 @@ class Faceformer(_A2FModule):
                 # pairs per 256-row block, row statistics over DSMEM, pre-LN sum kept fp32 in tensor memory)
                 ops.gemm_ln(att, W["o_w"], blk.attention.out_proj.bias.detach(), h, blk.layer_norm.weight.detach(),
                             blk.layer_norm.bias.detach(), h1)
-                if self.fuse_ffn:
-                    ops.ffn_ln(h1, W["f1_w"], blk.feed_forward.intermediate_dense.bias.detach(), W["f2_w"],
-                               blk.feed_forward.output_dense.bias.detach(), h1, blk.final_layer_norm.weight.detach(),
-                               blk.final_layer_norm.bias.detach(), ffn, h)
-                    continue
                 ops.gemm(h1, W["f1_w"], ffn, bias=blk.feed_forward.intermediate_dense.bias.detach(), act=L.ACT_GELU, backend=be)
                 ops.gemm_ln(ffn, W["f2_w"], blk.feed_forward.output_dense.bias.detach(), h1, blk.final_layer_norm.weight.detach(),
                             blk.final_layer_norm.bias.detach(), h)

@@ -109,32 +109,68 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     return out
 
 
-def ffn_ln(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
-           resid: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, scratch: torch.Tensor, out: torch.Tensor,
-           eps: float = 1e-5) -> torch.Tensor:
-    """out = LayerNorm(resid + gelu(x @ w1^T + b1) @ w2^T + b2) * gamma + beta in one tcgen05 kernel (a2f_ffn_ln): the
-    feed-forward block of a post-LN encoder layer.  bf16 operands; scratch [M,F] holds gelu(.) between the two GEMMs."""
-    _dev(x, w1, b1, w2, b2, resid, gamma, beta, scratch, out)
-    for t in (x, w1, w2, resid, scratch, out):
-        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
-            raise L.A2FError("ffn_ln takes 2-D bf16 operands with unit column stride")
-    M, K1 = x.shape
-    F, N = w1.shape[0], w2.shape[0]
-    if w1.shape[1] != K1 or w2.shape[1] != F or tuple(resid.shape) != (M, N) or tuple(out.shape) != (M, N) or \
-            scratch.shape[0] < M or scratch.shape[1] != F:
-        raise L.A2FError("ffn_ln: shape mismatch")
+def _bf16_2d(*ts):
+    for t in ts:
+        if t is not None and (t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1):
+            raise L.A2FError("expected 2-D bf16 operands with unit column stride")
+
+
+def encoder_block(h1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
+                  ln2_g: torch.Tensor, ln2_b: torch.Tensor, scratch: torch.Tensor, h_out: torch.Tensor, *,
+                  att: Optional[torch.Tensor] = None, wo: Optional[torch.Tensor] = None, bo: Optional[torch.Tensor] = None,
+                  h_in: Optional[torch.Tensor] = None, ln1_g: Optional[torch.Tensor] = None, ln1_b: Optional[torch.Tensor] = None,
+                  wq: Optional[torch.Tensor] = None, bq: Optional[torch.Tensor] = None, qkv: Optional[torch.Tensor] = None,
+                  eps: float = 1e-5) -> torch.Tensor:
+    """The row-local part of a post-LN encoder layer in one tcgen05 kernel (a2f_encoder_block, include/a2f.h):
+    [h1 = LN(h_in + att wo^T + bo)] -> f = gelu(h1 w1^T + b1) -> h_out = LN(h1 + f w2^T + b2) [-> qkv = h_out wq^T + bq].
+    The bracketed phases run when att / wq are given."""
+    _dev(h1, w1, b1, w2, b2, ln2_g, ln2_b, scratch, h_out, att, wo, bo, h_in, ln1_g, ln1_b, wq, bq, qkv)
+    _bf16_2d(h1, w1, w2, scratch, h_out, att, wo, h_in, wq, qkv)
+    M, N = h1.shape
+    F = w1.shape[0]
+    if w1.shape[1] != N or tuple(w2.shape) != (N, F) or tuple(h_out.shape) != (M, N) or scratch.shape[0] < M or scratch.shape[1] != F:
+        raise L.A2FError("encoder_block: shape mismatch")
+    g = L.EncoderBlockArgs()
+    g.M, g.N, g.F = M, N, F
+    g.h1, g.ld_h1 = h1.data_ptr(), h1.stride(0)
+    g.w1, g.ld_w1, g.b1 = w1.data_ptr(), w1.stride(0), L.ptr(b1)
+    g.f, g.ld_f = scratch.data_ptr(), scratch.stride(0)
+    g.w2, g.ld_w2, g.b2 = w2.data_ptr(), w2.stride(0), L.ptr(b2)
+    g.ln2_g, g.ln2_b = ln2_g.data_ptr(), ln2_b.data_ptr()
+    g.h_out, g.ld_hout = h_out.data_ptr(), h_out.stride(0)
+    g.eps = float(eps)
+    flops = 4.0 * M * N * F
+    if att is not None:
+        if wo is None or h_in is None or ln1_g is None or ln1_b is None or tuple(att.shape) != (M, N) or \
+                tuple(wo.shape) != (N, N) or tuple(h_in.shape) != (M, N):
+            raise L.A2FError("encoder_block: the attention-output phase needs att, wo, h_in [M,N] and ln1")
+        g.att, g.ld_att = att.data_ptr(), att.stride(0)
+        g.wo, g.ld_wo, g.bo = wo.data_ptr(), wo.stride(0), L.ptr(bo)
+        g.h_in, g.ld_hin = h_in.data_ptr(), h_in.stride(0)
+        g.ln1_g, g.ln1_b = ln1_g.data_ptr(), ln1_b.data_ptr()
+        flops += 2.0 * M * N * N
+    if wq is not None:
+        NQ = wq.shape[0]
+        if qkv is None or wq.shape[1] != N or tuple(qkv.shape) != (M, NQ):
+            raise L.A2FError("encoder_block: the in-projection phase needs wq [NQ,N] and qkv [M,NQ]")
+        g.wq, g.ld_wq, g.bq, g.NQ = wq.data_ptr(), wq.stride(0), L.ptr(bq), NQ
+        g.qkv, g.ld_qkv = qkv.data_ptr(), qkv.stride(0)
+        flops += 2.0 * M * N * NQ
     lib = L.load()
     if PROFILE is not None:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-    L.check(lib.a2f_ffn_ln(x.data_ptr(), x.stride(0), w1.data_ptr(), w1.stride(0), L.ptr(b1), w2.data_ptr(), w2.stride(0),
-                           L.ptr(b2), resid.data_ptr(), resid.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
-                           scratch.data_ptr(), scratch.stride(0), out.data_ptr(), out.stride(0), M, N, F, K1, _stream()),
-            "a2f_ffn_ln")
+    L.check(lib.a2f_encoder_block(C.byref(g), _stream()), "a2f_encoder_block")
     if PROFILE is not None:
         e.record()
-        PROFILE.append(("gemm_tc", 2.0 * M * F * (K1 + N), s, e))
-    return out
+        PROFILE.append(("gemm_tc", flops, s, e))
+    return h_out
+
+
+def ffn_ln(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor, b2: Optional[torch.Tensor],
+           gamma: torch.Tensor, beta: torch.Tensor, scratch: torch.Tensor, out: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """out = LayerNorm(x + gelu(x @ w1^T + b1) @ w2^T + b2) * gamma + beta: the feed-forward half of encoder_block."""
+    return encoder_block(x, w1, b1, w2, b2, gamma, beta, scratch, out, eps=eps)
 
 
 def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: torch.Tensor, gamma: torch.Tensor,

@@ -150,16 +150,44 @@ int a2f_gemm_ln(const void* A, long long lda, const void* W, long long ldw, cons
                 long long ldr, const float* gamma, const float* beta, float eps, void* out, long long ldo, void* pre_out,
                 long long ldp, int M, int N, int K, void* stream);
 
-/* The whole feed-forward block of a post-LN encoder layer in one kernel (tcgen05 back end, bf16):
- *   out = LayerNorm(resid + gelu(X W1^T + bias1) W2^T + bias2) * gamma + beta      (HF modeling_wav2vec2.py:551-609)
- * Same cluster layout as a2f_gemm_ln; the intermediate gelu(.) [M,F] goes through `scratch` (bf16, row stride ldf, stays in
- * L2) and both GEMMs share one smem ring / TMEM double buffer, so the tensor pipe does not drain between them.
- * X [M,K1], W1 [F,K1], W2 [N,F], resid / out [M,N]; N in {256, 512, 768}; F in {N, 2N, 3N, 4N}; gelu = the tanh-form
- * approximation the bf16 back end uses everywhere (|err| below bf16 resolution).  Results are bit-identical to
- * a2f_gemm (GELU epilogue) followed by a2f_gemm_ln. */
+/* Everything of a post-LN encoder layer that is local to a block of rows, in ONE kernel (tcgen05 back end, bf16;
+ * HF modeling_wav2vec2.py:551-609 through ref:src/model/wav2vec.py:174-180):
+ *   h1    = LayerNorm(h_in + att Wo^T + bo) * ln1_g + ln1_b          skipped when att == NULL (h1 is then an input)
+ *   f     = gelu(h1 W1^T + b1)                                         scratch [M,F], stays in L2
+ *   h_out = LayerNorm(h1 + f W2^T + b2) * ln2_g + ln2_b
+ *   qkv   = h_out Wq^T + bq                                            the NEXT layer's in-projection; skipped when wq == NULL
+ * so that an encoder layer is two launches: the attention and this.  Same cluster layout as a2f_gemm_ln (N/256 CTA
+ * pairs per 256-row block); all GEMMs of a row block share one smem ring and the TMEM double buffer, phase outputs are
+ * handed over inside the cluster through L2 with cluster-scope mbarriers.  Results are bit-identical to a2f_gemm_ln,
+ * a2f_gemm (GELU), a2f_gemm_ln, a2f_gemm run one after the other.
+ * All matrices bf16, row strides in elements (multiples of 8), bases 16-byte aligned; N in {256,512,768}; F in {N..4N};
+ * NQ in {N,2N,3N}; gelu = the tanh form the bf16 back end uses everywhere.  h1, f, h_out must be distinct buffers. */
+typedef struct a2f_encoder_block_args {
+    int M, N, F;
+    const void* att; long long ld_att;      /* [M,N] attention output (heads merged); NULL = no attention-output phase */
+    const void* wo; long long ld_wo;        /* [N,N] */
+    const float* bo;
+    const void* h_in; long long ld_hin;     /* [M,N] layer input (residual of the attention block) */
+    const float* ln1_g; const float* ln1_b;
+    void* h1; long long ld_h1;              /* [M,N] out (in when att == NULL) */
+    const void* w1; long long ld_w1;        /* [F,N] */
+    const float* b1;
+    void* f; long long ld_f;                /* [M,F] scratch */
+    const void* w2; long long ld_w2;        /* [N,F] */
+    const float* b2;
+    const float* ln2_g; const float* ln2_b;
+    void* h_out; long long ld_hout;         /* [M,N] out */
+    const void* wq; long long ld_wq;        /* [NQ,N]; NULL = no in-projection phase */
+    const float* bq;
+    int NQ;
+    void* qkv; long long ld_qkv;            /* [M,NQ] out */
+    float eps;
+} a2f_encoder_block_args;
+int a2f_encoder_block(const a2f_encoder_block_args* args, void* stream);
+/* The feed-forward half alone: out = LayerNorm(X + gelu(X W1^T + bias1) W2^T + bias2) * gamma + beta. */
 int a2f_ffn_ln(const void* X, long long ldx, const void* W1, long long ldw1, const float* bias1, const void* W2,
-               long long ldw2, const float* bias2, const void* resid, long long ldr, const float* gamma, const float* beta,
-               float eps, void* scratch, long long ldf, void* out, long long ldo, int M, int N, int F, int K1, void* stream);
+               long long ldw2, const float* bias2, const float* gamma, const float* beta, float eps, void* scratch,
+               long long ldf, void* out, long long ldo, int M, int N, int F, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -245,6 +245,31 @@ def test_faceformer_bf16_matches_oracle(ff_model, ff_sd, dev):
     assert err_cm / 100.0 < 5e-4                   # north_star: 5e-4 m on the bf16 path
 
 
+def test_faceformer_bf16_encoder_fusion_variants_agree(ff_model, ff_sd, dev):
+    """bf16 encoder: separate LayerNorm launches, LayerNorm in the GEMM epilogue, and every phase selection of the one-kernel
+    encoder block (a2f_encoder_block).  The fused variants must agree bit for bit with each other (same arithmetic, other
+    launch structure); the unfused one rounds the pre-LayerNorm sum to bf16 and only has to meet the oracle tolerance."""
+    B, n = 3, 24000                                    # 3 x 90 frames: 270 rows = one full and one ragged 256-row block
+    audio, oh, tp = oin.audio(B, n, 31), oin.one_hot(B, 12, 31), oin.batch_templates(B, 31, scale=100.0)
+    want = orm.faceformer_forward_batch(ff_sd, audio, oh, tp)
+    m = ff_model.set_precision("bf16")
+    saved = (m.fuse_layernorm, m.fuse_ffn, m.fuse_block)
+    outs = {}
+    try:
+        for name, (ln, ffn, blk) in {"separate": (False, False, "ffn"), "gemm_ln": (True, False, "ffn"), "ffn": (True, True, "ffn"),
+                                     "attn_ffn": (True, True, "attn_ffn"), "ffn_qkv": (True, True, "ffn_qkv"),
+                                     "attn_ffn_qkv": (True, True, "attn_ffn_qkv")}.items():
+            m.fuse_layernorm, m.fuse_ffn, m.fuse_block = ln, ffn, blk
+            with torch.no_grad():
+                outs[name] = m(audio.to(dev), oh.to(dev), tp.to(dev)).cpu()
+    finally:
+        m.fuse_layernorm, m.fuse_ffn, m.fuse_block = saved
+    for name, got in outs.items():
+        assert _maxerr(got, want) / 100.0 < 5e-4, name
+    for name in ("ffn", "attn_ffn", "ffn_qkv", "attn_ffn_qkv"):
+        assert torch.equal(outs[name], outs["gemm_ln"]), name
+
+
 def test_faceformer_batch_equals_per_utterance(ff_model, ff_sd, dev):
     """Batch extension: every utterance of a batch gets the reference's batch-1 result."""
     B, n = 3, 12000

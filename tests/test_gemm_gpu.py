@@ -249,7 +249,7 @@ def test_ffn_ln_one_kernel_equals_two(a2f_lib, dev, M, N, F):
     for rep in range(3):                                # repeated: a stale scratch from the previous run must not be read
         scratch = torch.full((M, F), float("nan"), dtype=torch.bfloat16, device=dev) if rep == 0 else scratch
         out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
-        ops.ffn_ln(x, w1, b1, w2, b2, x, gamma, beta, scratch, out)
+        ops.ffn_ln(x, w1, b1, w2, b2, gamma, beta, scratch, out)
         torch.cuda.synchronize()
         assert torch.equal(scratch, f_ref), rep
         assert torch.equal(out, want), (rep, float((out.float() - want.float()).abs().max()))
@@ -261,6 +261,53 @@ def test_ffn_ln_one_kernel_equals_two(a2f_lib, dev, M, N, F):
     err = (out.float() - ref).abs()
     tol = 2.0 ** -7 * (ref.abs() + 1.0)
     assert bool((err <= tol).all()), float(err.max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,F,NQ,p0,p3", [(4800, 768, 3072, 2304, True, True), (4800, 768, 3072, 2304, True, False),
+                                            (4800, 768, 3072, 2304, False, True), (130, 768, 3072, 2304, True, True),
+                                            (12000, 768, 3072, 2304, True, True), (9000, 768, 1536, 768, True, True),
+                                            (700, 512, 1024, 1536, True, True), (300, 256, 1024, 512, True, True)])
+def test_encoder_block_one_kernel_equals_four(a2f_lib, dev, M, N, F, NQ, p0, p3):
+    """a2f_encoder_block (attention out-projection + LayerNorm, FFN, LayerNorm, next layer's q|k|v projection in one kernel,
+    phase outputs handed over inside the cluster through L2) must give the SAME bits as the four separate launches.
+    Shapes: the bench batch with and without the optional phases, a ragged block, more row blocks than resident clusters
+    (every hand-over barrier wraps its parity), 2- and 1-pair clusters, fewer tiles per pair in phases 1 / 3."""
+    from a2f_b200 import ops, lib as L
+    g = torch.Generator().manual_seed(M + N + F + NQ)
+    rnd = lambda *sh, s=1.0: (torch.randn(*sh, generator=g) * s)
+    att, h_in = rnd(M, N).bfloat16().to(dev), rnd(M, N).bfloat16().to(dev)
+    wo, w1 = rnd(N, N, s=N ** -0.5).bfloat16().to(dev), rnd(F, N, s=N ** -0.5).bfloat16().to(dev)
+    w2, wq = rnd(N, F, s=F ** -0.5).bfloat16().to(dev), rnd(NQ, N, s=N ** -0.5).bfloat16().to(dev)
+    bo, b1, b2, bq = (0.1 * rnd(N)).to(dev), (0.1 * rnd(F)).to(dev), (0.1 * rnd(N)).to(dev), (0.1 * rnd(NQ)).to(dev)
+    g1, be1 = (torch.rand(N, generator=g) + 0.5).to(dev), (0.1 * rnd(N)).to(dev)
+    g2, be2 = (torch.rand(N, generator=g) + 0.5).to(dev), (0.1 * rnd(N)).to(dev)
+    bf = lambda *sh: torch.empty(sh, dtype=torch.bfloat16, device=dev)
+    # reference: four launches
+    h1_ref, f_ref, ho_ref, q_ref = bf(M, N), bf(M, F), bf(M, N), bf(M, NQ)
+    if p0:
+        ops.gemm_ln(att, wo, bo, h_in, g1, be1, h1_ref)
+    else:
+        h1_ref.copy_(h_in)
+    ops.gemm(h1_ref, w1, f_ref, bias=b1, act=L.ACT_GELU, backend=L.TCGEN05)
+    ops.gemm_ln(f_ref, w2, b2, h1_ref, g2, be2, ho_ref)
+    ops.gemm(ho_ref, wq, q_ref, bias=bq, backend=L.TCGEN05)
+    nan = float("nan")
+    for rep in range(3):
+        h1 = torch.full((M, N), nan, dtype=torch.bfloat16, device=dev) if p0 else h1_ref.clone()
+        f, ho, q = torch.full((M, F), nan, dtype=torch.bfloat16, device=dev), bf(M, N), bf(M, NQ)
+        kw = {}
+        if p0:
+            kw.update(att=att, wo=wo, bo=bo, h_in=h_in, ln1_g=g1, ln1_b=be1)
+        if p3:
+            kw.update(wq=wq, bq=bq, qkv=q)
+        ops.encoder_block(h1, w1, b1, w2, b2, g2, be2, f, ho, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(h1, h1_ref), ("h1", rep)
+        assert torch.equal(f, f_ref), ("f", rep)
+        assert torch.equal(ho, ho_ref), ("h_out", rep, float((ho.float() - ho_ref.float()).abs().max()))
+        if p3:
+            assert torch.equal(q, q_ref), ("qkv", rep)
 
 
 @pytest.mark.parametrize("M,N,K,act,use_resid", [(4800, 3072, 768, 2, False), (4800, 2304, 768, 0, False), (9600, 768, 256, 0, True),

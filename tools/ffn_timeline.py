@@ -1,31 +1,48 @@
-"""In-kernel timeline of a2f_ffn_ln (one launch at the bench shape M=4800): clock64 stamps of the leader CTAs.
-    python tools/ffn_timeline.py
-Slots: 0 entry, 1 setup done (barriers, TMEM, cluster sync, griddepcontrol.wait), 2 first operands landed,
-3..6 MMAs of phase-1 tile t issued, 7 MMAs of the phase-2 tile issued, 8..11 phase-1 tile t stored and published,
-12 epilogue enters the LayerNorm tile, 13 LayerNorm stores issued, 14 stores drained, 15 after the final cluster sync."""
-import sys, os
+"""In-kernel timeline of a2f_encoder_block at the bench shape (M=4800, d=768, ff=3072, all four phases): stamps of the
+leader CTAs, and launch-to-launch gaps of four back-to-back launches (globaltimer).
+    python tools/ffn_timeline.py [ffn]        ("ffn": only the feed-forward phases, as a2f_ffn_ln)
+Slots: 0 entry, 1 setup done (barriers, TMEM, cluster sync, griddepcontrol.wait), 2 first operands landed, 3 MMAs of phase 0
+issued, 4 MMAs of the last phase-1 tile issued, 5 MMAs of phase 2 issued, 6 MMAs of the last phase-3 tile issued, 7 h1
+published, 8..11 phase-1 tile t stored and published, 12 epilogue enters the second LayerNorm tile, 13 its stores issued,
+14 all stores drained, 15 after the final cluster sync."""
+import os
+import sys
+
 import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from a2f_b200 import ops, lib as L
 
+only_ffn = len(sys.argv) > 1 and sys.argv[1] == "ffn"
 dev = torch.device("cuda:0")
-M, N, F = 4800, 768, 3072
+M, N, F, NQ = 4800, 768, 3072, 2304
 g = torch.Generator().manual_seed(1)
-x = torch.randn(M, N, generator=g).bfloat16().to(dev)
-w1 = (torch.randn(F, N, generator=g) * N ** -0.5).bfloat16().to(dev)
-w2 = (torch.randn(N, F, generator=g) * F ** -0.5).bfloat16().to(dev)
-b1, b2 = torch.randn(F, generator=g).to(dev), torch.randn(N, generator=g).to(dev)
-gamma, beta = torch.rand(N, generator=g).to(dev), torch.randn(N, generator=g).to(dev)
-f = torch.empty((M, F), dtype=torch.bfloat16, device=dev)
-out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+rnd = lambda *sh, s=1.0: (torch.randn(*sh, generator=g) * s)
+att, h_in = rnd(M, N).bfloat16().to(dev), rnd(M, N).bfloat16().to(dev)
+wo, w1 = rnd(N, N, s=N ** -0.5).bfloat16().to(dev), rnd(F, N, s=N ** -0.5).bfloat16().to(dev)
+w2, wq = rnd(N, F, s=F ** -0.5).bfloat16().to(dev), rnd(NQ, N, s=N ** -0.5).bfloat16().to(dev)
+bo, b1, b2, bq = rnd(N).to(dev), rnd(F).to(dev), rnd(N).to(dev), rnd(NQ).to(dev)
+g1, be1, g2, be2 = torch.rand(N, generator=g).to(dev), rnd(N).to(dev), torch.rand(N, generator=g).to(dev), rnd(N).to(dev)
+bf = lambda *sh: torch.empty(sh, dtype=torch.bfloat16, device=dev)
+h1, f, ho, q = (h_in.clone() if only_ffn else bf(M, N)), bf(M, F), bf(M, N), bf(M, NQ)
+
+
+def run():
+    if only_ffn:
+        ops.ffn_ln(h1, w1, b1, w2, b2, g2, be2, f, ho)
+    else:
+        ops.encoder_block(h1, w1, b1, w2, b2, g2, be2, f, ho, att=att, wo=wo, bo=bo, h_in=h_in, ln1_g=g1, ln1_b=be1,
+                          wq=wq, bq=bq, qkv=q)
+
+
 lib = L.load()
 n_cta = 6 * 19
 tls = [torch.zeros(2 * n_cta * 16, dtype=torch.int64, device=dev) for _ in range(4)]
 for _ in range(3):
-    ops.ffn_ln(x, w1, b1, w2, b2, x, gamma, beta, f, out)
+    run()
 for tl_i in tls:                        # four launches back to back, each with its own stamp buffer
     lib.a2f_debug_set_timeline(tl_i.data_ptr())
-    ops.ffn_ln(x, w1, b1, w2, b2, x, gamma, beta, f, out)
+    run()
 lib.a2f_debug_set_timeline(None)
 torch.cuda.synchronize()
 gt = [tl_i.view(2, n_cta, 16)[1].cpu().double() for tl_i in tls]     # globaltimer (ns)
@@ -37,10 +54,13 @@ for i, g_ in enumerate(gt):
 t = tls[1].view(2, n_cta, 16)[0].cpu().double()
 t = (t - t[:, :1])                      # cycles since this CTA's entry
 lead = t[0::2]                          # leader CTAs (MMA stamps live there)
-names = ["entry", "setup done", "first operands", "mma t0", "mma t1", "mma t2", "mma t3", "mma phase2", "pub t0", "pub t1",
-         "pub t2", "pub t3", "enter LN", "LN stores issued", "stores drained", "after cluster sync"]
-clk = torch.cuda.clock_rate() if hasattr(torch.cuda, "clock_rate") else 1900
-print(f"cycles since CTA entry, leaders of {lead.shape[0]} pairs (median / min / max); ~{clk} MHz")
+names = ["entry", "setup done", "first operands", "mma phase 0", "mma phase 1 (last)", "mma phase 2", "mma phase 3 (last)",
+         "pub h1", "pub f0", "pub f1", "pub f2", "pub f3", "enter LN 2", "LN 2 stores issued", "stores drained",
+         "after cluster sync"]
+clk = 1965.0
+print(f"cycles since CTA entry, leaders of {lead.shape[0]} pairs (median / min / max); us at {clk:.0f} MHz")
 for i, nme in enumerate(names):
     col = lead[:, i]
-    print(f"{i:2d} {nme:18s} {col.median():9.0f} {col.min():9.0f} {col.max():9.0f}   {col.median() / clk:7.2f} us")
+    if float(col.max()) <= 0 and i > 0:
+        continue
+    print(f"{i:2d} {nme:20s} {col.median():9.0f} {col.min():9.0f} {col.max():9.0f}   {col.median() / clk:7.2f} us")
