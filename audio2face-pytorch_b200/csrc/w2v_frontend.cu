@@ -21,8 +21,22 @@ __global__ void __launch_bounds__(1024) audio_stats_kernel(const float* __restri
     const float* x = audio + (long long)blockIdx.x * N;
     __shared__ double sh[32];
     __shared__ double s_mean;
+    // float4 loads, 8 in flight per thread: the two passes are latency-bound (one CTA per utterance), not bandwidth-bound
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const long long n4 = vec ? N / 4 : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
     double s = 0.0;
-    for (long long i = threadIdx.x; i < N; i += blockDim.x) s += (double)x[i];
+    for (long long i0 = threadIdx.x; i0 < n4; i0 += 8LL * blockDim.x) {
+        float4 a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long i = i0 + (long long)u * blockDim.x;
+            a[u] = i < n4 ? __ldg(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += ((double)a[u].x + (double)a[u].y) + ((double)a[u].z + (double)a[u].w);
+    }
+    for (long long i = 4 * n4 + threadIdx.x; i < N; i += blockDim.x) s += (double)x[i];
     s = warp_sum_d(s);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
@@ -35,7 +49,20 @@ __global__ void __launch_bounds__(1024) audio_stats_kernel(const float* __restri
     // numpy: mean in fp32, then var = mean(|x - mean|^2): centre with the fp32-rounded mean like the reference does
     const float meanf = (float)s_mean;
     double v = 0.0;
-    for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+    for (long long i0 = threadIdx.x; i0 < n4; i0 += 8LL * blockDim.x) {
+        float4 a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long i = i0 + (long long)u * blockDim.x;
+            a[u] = i < n4 ? __ldg(x4 + i) : make_float4(meanf, meanf, meanf, meanf);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float d0 = a[u].x - meanf, d1 = a[u].y - meanf, d2 = a[u].z - meanf, d3 = a[u].w - meanf;
+            v += ((double)(d0 * d0) + (double)(d1 * d1)) + ((double)(d2 * d2) + (double)(d3 * d3));
+        }
+    }
+    for (long long i = 4 * n4 + threadIdx.x; i < N; i += blockDim.x) {
         const float d = x[i] - meanf;
         v += (double)(d * d);
     }
@@ -163,6 +190,11 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
     // bf16 path: GroupNorm affine folded to one FMA (y = conv*A + Bc) and the MUFU.TANH GELU; fp32 path: literal form
     const float2 Aff = make_float2(g0.y * ga0, g1.y * ga1);
     const float2 Bff = make_float2(be0 - g0.x * Aff.x, be1 - g1.x * Aff.y);
+    if (sizeof(TO) == 2) {                // ... and A folded into the taps, Bc into the accumulator's start value
+#pragma unroll
+        for (int k = 0; k < 10; ++k) wp[k] = fmul2(wp[k], Aff);
+    }
+    const float2 a_init = sizeof(TO) == 2 ? Bff : make_float2(0.f, 0.f);
     __syncthreads();
     TO* o = out + (long long)b * out_batch_stride;
     const int tn = min(C0_TCH, L0 - t0);
@@ -177,12 +209,12 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (t4 + u >= tn) break;
-            float2 a = make_float2(0.f, 0.f);
+            float2 a = a_init;
 #pragma unroll
             for (int k = 0; k < 10; ++k) a = ffma2(wp[k], make_float2(xw[5 * u + k], xw[5 * u + k]), a);
             TO* p = o + (long long)(t0 + t4 + u) * 512 + c;
             if (sizeof(TO) == 2) {
-                const float2 y = gelu_fast2(ffma2(a, Aff, Bff));
+                const float2 y = gelu_fast2(a);
                 *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(y.x, y.y);
             } else {
                 const float y0 = gelu_erf((a.x - g0.x) * g0.y * ga0 + be0);
