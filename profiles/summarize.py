@@ -71,7 +71,7 @@ def traffic(path, note=""):
         elif metric in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
             k["read" if "read" in metric else "write"] += v * scale
-    gem = [v for n, v in per.items() if "gemm_tc" in n or "posconv_tc" in n or "gemm_ln" in n]
+    gem = [v for n, v in per.items() if "gemm_tc" in n or "posconv_tc" in n or "gemm_ln" in n or "enc_block" in n]
     tot = sum(v["read"] + v["write"] for v in gem)
     n = sum(v["launches"] for v in gem)
     out = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; "
