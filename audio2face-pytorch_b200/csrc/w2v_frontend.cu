@@ -206,6 +206,25 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
             const float4 f = *reinterpret_cast<const float4*>(xs + 5 * t4 + 4 * qd);
             xw[4 * qd] = f.x; xw[4 * qd + 1] = f.y; xw[4 * qd + 2] = f.z; xw[4 * qd + 3] = f.w;
         }
+        if (sizeof(TO) == 2 && t4 + 4 <= tn) {
+            // complete group of four steps (all but the last group of an utterance): no per-step exit test, so the four
+            // tap chains and GELUs are independent instruction streams the scheduler can interleave
+            float2 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = a_init;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = ffma2(wp[k], make_float2(xw[5 * u + k], xw[5 * u + k]), a[u]);
+            }
+            TO* p = o + (long long)(t0 + t4) * 512 + c;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 y = gelu_fast2(a[u]);
+                *reinterpret_cast<uint32_t*>(p + u * 512) = pack_bf16x2(y.x, y.y);
+            }
+            continue;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (t4 + u >= tn) break;

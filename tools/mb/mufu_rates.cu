@@ -19,6 +19,43 @@ template <int OP> __device__ __forceinline__ unsigned step(unsigned v) {
     return v;
 }
 
+// packed fp32: 8 independent chains of fma.rn.f32x2 (two results per instruction), and the same mixed 1:1 with scalar FFMA
+template <int MIX> __global__ void __launch_bounds__(256) k2(unsigned long long* out, int iters, unsigned long long seed) {
+    unsigned long long v[8];
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = seed + threadIdx.x * 8 + i; s[i] = (float)i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            asm volatile("fma.rn.f32x2 %0, %0, %0, %0;" : "+l"(v[i]));
+            if (MIX) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(s[i]));
+        }
+    }
+    unsigned long long r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= v[i] + (unsigned long long)__float_as_uint(s[i]);
+    if (r == 0x12345678ull) out[0] = r;
+}
+
+template <int MIX> void run2(const char* name, int sms, double mhz) {
+    unsigned long long* d;
+    cudaMalloc(&d, 8);
+    const int iters = 4096, grid = sms * 8;
+    k2<MIX><<<grid, 256>>>(d, 16, 0x3f0000003f000000ull);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    k2<MIX><<<grid, 256>>>(d, iters, 0x3f0000003f000000ull);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    const double ops = (double)grid * 256 * 8 * iters * (MIX ? 3 : 2);
+    printf("%-22s %8.3f ms  %7.2f results/clk/SM (at %.0f MHz)\n", name, ms, ops / (ms * 1e-3) / (mhz * 1e6) / sms, mhz);
+    cudaFree(d);
+}
+
 template <int OP> __global__ void __launch_bounds__(256) k(unsigned* out, int iters, unsigned seed) {
     unsigned v[8];
 #pragma unroll
@@ -59,6 +96,8 @@ int main() {
     const double mhz = khz / 1e3;
     const int sms = p.multiProcessorCount;
     run<FMA>("fma.f32 (reference)", 1, sms, mhz);
+    run2<0>("fma.rn.f32x2", sms, mhz);
+    run2<1>("f32x2 + f32 1:1", sms, mhz);
     run<EX2>("ex2.approx.f32", 1, sms, mhz);
     run<RCP>("rcp.approx.f32", 1, sms, mhz);
     run<TANH>("tanh.approx.f32", 1, sms, mhz);
