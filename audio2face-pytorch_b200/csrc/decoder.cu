@@ -81,6 +81,12 @@ A2F_D void warp_ln64(float& a, float& b, float g0, float g1, float b0, float b1)
 // Activations the backward pass (decoder_bwd.cu) needs, all [B,T,width] fp32; written only by the TRAIN instantiation.
 struct DecSaves {
     float *X, *Q, *K, *V, *CTX, *Y1PRE, *Y2PRE, *Y2, *HID, *Y3PRE, *LSE;
+    // inference, streaming hand-over to the vertex head (a2f_decoder_rollout_stream): d_i is ALSO written as the head's
+    // bf16 operand (hi | lo | hi, 192 columns) at row i * zB + b of zs ("frame-major"), and frames_done[i] is incremented
+    // (release) once per utterance -- the head kernel, running at the same time on the idle SMs, waits on it
+    bf16* zs;
+    unsigned* frames_done;
+    int zB;
 };
 
 // K/V rows written by another SM of the cluster: read through L2 (L1 is not coherent across SMs)
@@ -91,6 +97,28 @@ template <bool CL> A2F_D float4 ld_kv4(const float* p) {
 // debug (a2f_debug_set_decoder_timing): when non-NULL, thread 0 of CTA 0 accumulates the clock64() cycles between the block
 // barriers of a step into [0..4] = attention, out_proj, LN1/LN2/linear1, linear2, LN3/feedback/in-projection; [5] = steps
 __device__ unsigned long long* g_dec_timing_dev = nullptr;
+
+// Streaming hand-over to the vertex head (a2f_decoder_rollout_stream), spread over two warps that idle through phase 6 so that
+// nothing is added to the step's critical path (in warp 6, behind the D store, the gpu-scope release alone cost 0.6 us per
+// step; one idle warp doing load + stores + release in one go still overran the phase by 0.3 us):
+//   dec_store_frame   (warp 9, step i)    decoder state of frame i-1 (written to D by warp 6 a step ago, re-read from L2) ->
+//                                         row (i-1) * zB + b of the frame-major bf16 operand: hi | lo | hi with the rounding
+//                                         of split_bf16x3_kernel (api_gemm.cu): hi = bf16(x), lo = bf16(x - hi)
+//   dec_release_frame (warp 8, step i+1)  frames_done[i-1] += 1, release.gpu: warp 9's stores were ordered before this thread
+//                                         by the barrier that ended step i (the release is cumulative)
+// The head sees a frame two steps (5 us) late.
+A2F_D void dec_store_frame(const DecSaves& sv, const float* D_b, int f, int b, int lane) {
+    const float a = __ldcg(D_b + (long long)f * 64 + lane), c = __ldcg(D_b + (long long)f * 64 + lane + 32);
+    bf16* zr = sv.zs + ((long long)f * sv.zB + b) * 192;
+    const bf16 ha = __float2bfloat16_rn(a), hc = __float2bfloat16_rn(c);
+    const bf16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lc = __float2bfloat16_rn(c - __bfloat162float(hc));
+    zr[lane] = ha; zr[lane + 32] = hc;
+    zr[64 + lane] = la; zr[96 + lane] = lc;
+    zr[128 + lane] = ha; zr[160 + lane] = hc;
+}
+A2F_D void dec_release_frame(const DecSaves& sv, int f) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sv.frames_done + f) : "memory");
+}
 
 template <bool TRAIN, bool CL, bool TIMING = false>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
@@ -454,12 +482,24 @@ decoder_rollout_kernel(DecW w, const float* __restrict__ ca /*[B,T,64] cross-att
                 }
             }
         }
+        else if (!TRAIN && !CL && sv.zs != nullptr) {
+            if (warp == 9 && i > 0) dec_store_frame(sv, D_b, i - 1, b, lane);
+            else if (tid == 256 && i > 1) dec_release_frame(sv, i - 2);
+        }
         DEC_TSTAMP(10);
         if (CL) cluster.sync();      // q_{i+1} has landed in every rank's shared memory, K/V row i+1 is visible cluster-wide
         else __syncthreads();
         DEC_TSTAMP(11);
     }
 #undef DEC_TSTAMP
+    if (!TRAIN && !CL && sv.zs != nullptr) {                    // the last two frames (uniform branch: every thread takes it)
+        if (warp == 9) dec_store_frame(sv, D_b, T - 1, b, lane);
+        __syncthreads();
+        if (tid == 256) {
+            if (T > 1) dec_release_frame(sv, T - 2);
+            dec_release_frame(sv, T - 1);
+        }
+    }
     if (TIMING && tl) {
         for (int k = 0; k < 12; ++k) tl[k] = tacc[k];
         tl[12] = (unsigned long long)T;
@@ -609,7 +649,7 @@ int a2f_decoder_save_offset(int field) {
 
 static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memory, int memory_is_ca, const float* one_hot,
                                 int n_onehot, int period, float* D, int B, int T, void* workspace, size_t workspace_bytes,
-                                float* saves, void* stream);
+                                float* saves, void* stream, void* zs = nullptr, unsigned* frames_done = nullptr);
 
 int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
                               int period, float* D, int B, int T, void* workspace, size_t workspace_bytes, float* saves,
@@ -622,9 +662,19 @@ int a2f_decoder_rollout_ca(const a2f_decoder_weights* w, const float* ca, const 
     return decoder_rollout_impl(w, ca, 1, one_hot, n_onehot, period, D, B, T, workspace, workspace_bytes, nullptr, stream);
 }
 
+int a2f_decoder_rollout_stream(const a2f_decoder_weights* w, const float* ca, const float* one_hot, int n_onehot, int period,
+                               float* D, int B, int T, void* workspace, size_t workspace_bytes, void* z3_frame_major,
+                               unsigned* frames_done, void* stream) {
+    A2F_REQUIRE(z3_frame_major && frames_done, "a2f_decoder_rollout_stream: NULL z3 / frames_done");
+    A2F_REQUIRE(reinterpret_cast<uintptr_t>(z3_frame_major) % 16 == 0 && reinterpret_cast<uintptr_t>(frames_done) % 4 == 0,
+                "a2f_decoder_rollout_stream: z3 must be 16-byte aligned");
+    return decoder_rollout_impl(w, ca, 1, one_hot, n_onehot, period, D, B, T, workspace, workspace_bytes, nullptr, stream,
+                                z3_frame_major, frames_done);
+}
+
 static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memory, int memory_is_ca, const float* one_hot,
                                 int n_onehot, int period, float* D, int B, int T, void* workspace, size_t workspace_bytes,
-                                float* saves, void* stream) {
+                                float* saves, void* stream, void* zs, unsigned* frames_done) {
     int rc = require_sm100();
     if (rc != A2F_OK) return rc;
     A2F_REQUIRE(w && memory && one_hot && D && workspace, "a2f_decoder_rollout: NULL argument");
@@ -673,7 +723,7 @@ static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memor
     // Measured (profiles/r1_sweep_long.txt): the two cluster barriers cost ~0.8 us per step, the single CTA's L2-bound
     // attention ~0.5 us per 100 keys: the cluster wins from T ~ 800 on.
     int CS = 1;
-    if (saves == nullptr && kv != nullptr && g_dec_cluster != 1) {
+    if (saves == nullptr && kv != nullptr && g_dec_cluster != 1 && zs == nullptr) {
         if (g_dec_cluster > 1) CS = g_dec_cluster;
         else if (T >= DEC_CLUSTER_T) {
             // largest cluster size whose B clusters are all co-resident: a cluster needs CS free SMs inside ONE GPC, so
@@ -727,6 +777,9 @@ static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memor
         A2F_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, dw, ca_use, one_hot, n_onehot, period, D, T, kv, none));
     } else if (saves == nullptr) {
         DecSaves none = {};
+        none.zs = static_cast<bf16*>(zs);
+        none.frames_done = frames_done;
+        none.zB = B;
         if (g_dec_timing_on) {      // debug instantiation with the per-phase cycle counters (tools/decoder_phases.py)
             A2F_CHECK_CUDA(cudaFuncSetAttribute(decoder_rollout_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false, false, true>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca_use, one_hot, n_onehot, period, D, T, kv, none));
@@ -735,7 +788,7 @@ static int decoder_rollout_impl(const a2f_decoder_weights* w, const float* memor
         A2F_CHECK_CUDA(launch_pdl(decoder_rollout_kernel<false, false>, dim3(B), dim3(DEC_THREADS), smem, s, dw, ca_use, one_hot, n_onehot, period, D, T, kv, none));
         }
     } else {
-        DecSaves sv;
+        DecSaves sv = {};
         const size_t bt = (size_t)B * T;
         float* f = saves;
         sv.X = f + bt * a2f_decoder_save_offset(A2F_DEC_X); sv.Q = f + bt * a2f_decoder_save_offset(A2F_DEC_Q);

@@ -43,6 +43,17 @@ struct GemmParams {
     long long ld_dy = 0;
     float c_rec = 0.f, c_vel = 0.f;
     double* loss_partial = nullptr;   // [grid][8 epilogue warps][2]
+    // tcgen05 vertex head that follows the decoder rollout (a2f_vertex_head_stream).  A is "frame-major": row
+    // r = frame * perm_rows + utterance; a batch (rows_per_batch = 128 rows) is a group of 128 / perm_rows frames.  The
+    // wide scalar epilogue sends row r of batch b to C + b * c_batch_stride + (r / perm_rows) * perm_stride +
+    // (r % perm_rows) * ldc and adds template row r % perm_rows; rows at or beyond live_rows are not stored.  The producer
+    // of a tile of batch b waits until wait_counters[min(wait_n, (b + 1) * wait_per_batch) - 1] >= wait_target (acquire).
+    int perm_rows = 0;
+    long long perm_stride = 0;
+    long long live_rows = 0;
+    const unsigned* wait_counters = nullptr;
+    int wait_target = 0, wait_per_batch = 0, wait_n = 0;
+    int max_ctas = 0;                 // 0 = one CTA per SM; else the grid is capped (SMs left to the kernel that is waited for)
 };
 
 inline void normalize_gemm(GemmParams& p) {

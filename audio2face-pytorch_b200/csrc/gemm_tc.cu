@@ -268,9 +268,28 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int waited = -1;                      // last counter index known to have reached its target
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
                 const int b = mb / p.tiles_m_per_batch, lt = mb % p.tiles_m_per_batch;
+                if (p.g.wait_counters != nullptr) {
+                    // rows of this batch are being produced by a kernel that runs at the same time (decoder rollout):
+                    // generic-proxy stores + red.release there, ld.acquire here, then the async proxy (TMA) may read
+                    const int f = min(p.g.wait_n, (b + 1) * p.g.wait_per_batch) - 1;
+                    if (f > waited) {
+                        const unsigned* cnt = p.g.wait_counters + f;
+                        uint32_t spins = 0;
+                        for (;;) {
+                            unsigned v;
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                            if (v >= (unsigned)p.g.wait_target) break;
+                            __nanosleep(200);
+                            if (++spins > (1u << 24)) __trap();     // ~3 s: a missing producer becomes a launch error
+                        }
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        waited = f;
+                    }
+                }
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -367,6 +386,14 @@ gemm_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
             ncol_ = nb_ * BN + half * 128 + lane;
             m0_ = (long long)b_ * g.rows_per_batch + r0_;
             cp_ = reinterpret_cast<float*>(g.C) + (long long)b_ * g.c_batch_stride + (long long)r0_ * g.ldc + ncol_;
+            if (g.perm_rows != 0) {
+                // frame-major rows (a2f_vertex_head_stream): this 32-row slice = utterances ut..ut+31 of frame fr of the group
+                const int fr = r0_ / g.perm_rows, ut = r0_ - fr * g.perm_rows;
+                if (m0_ >= g.live_rows) rows_ = 0;
+                cp_ = reinterpret_cast<float*>(g.C) + (long long)b_ * g.c_batch_stride + (long long)fr * g.perm_stride +
+                      (long long)ut * g.ldc + ncol_;
+                m0_ = ut;                                     // template row = utterance
+            }
         };
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
@@ -1166,7 +1193,8 @@ static int launch_tc(const TmapSet& maps, const TcParams& p, cudaStream_t s) {
         attr_done = true;
     }
     const int total = p.tiles_m_per_batch * p.num_batches * p.tiles_n;
-    const int grid = total < sm_count() ? total : sm_count();
+    int grid = total < sm_count() ? total : sm_count();
+    if (p.g.max_ctas > 0 && grid > p.g.max_ctas) grid = p.g.max_ctas;
     A2F_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, maps, p));
     count_launch();
     return A2F_OK;

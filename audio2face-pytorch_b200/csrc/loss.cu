@@ -168,4 +168,41 @@ int a2f_vertex_head_loss(const void* z3, const void* w3, int K3, const float* bi
     return A2F_OK;
 }
 
+/* ---- vertex head that follows the decoder rollout frame group by frame group (inference, tcgen05 path) ---- */
+int a2f_vertex_head_stream_rows(int B, int T) {
+    if (B <= 0 || T <= 0 || 128 % B != 0 || B % 32 != 0) return 0;
+    const int fg = 128 / B;
+    return (T + fg - 1) / fg * 128;
+}
+
+int a2f_vertex_head_stream(const void* z3_frame_major, const void* w3, int K3, const float* bias, const float* tmpl, int B, int T,
+                           int V3, float* out, const unsigned* frames_done, int reserve_sms, void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(z3_frame_major && w3 && out && frames_done, "a2f_vertex_head_stream: NULL argument");
+    A2F_REQUIRE(B > 0 && B % 32 == 0 && 128 % B == 0, "a2f_vertex_head_stream: B must be 32, 64 or 128");
+    A2F_REQUIRE(T > 0 && V3 > 0 && K3 > 0 && K3 % 8 == 0, "a2f_vertex_head_stream: bad T / V3 / K");
+    A2F_REQUIRE((long long)T * V3 < (1LL << 25), "a2f_vertex_head_stream: T * V3 must stay below 2^25 (row stride of the epilogue)");
+    A2F_REQUIRE(reserve_sms >= 0 && reserve_sms < sm_count(), "a2f_vertex_head_stream: reserve_sms out of range");
+    const int fg = 128 / B;                                   // frames per 128-row group
+    GemmParams p;
+    p.M = a2f_vertex_head_stream_rows(B, T); p.N = V3; p.K = K3;
+    p.A = z3_frame_major; p.a_row_stride = K3; p.a_batch_stride = 128LL * K3; p.rows_per_batch = 128;
+    p.W = w3; p.ldw = K3;
+    p.bias = bias; p.act = A2F_ACT_NONE;
+    p.resid = nullptr; p.resid_bf16 = 0; p.ldr = 0;
+    p.tmpl = tmpl; p.rows_per_tmpl = 1;
+    p.C = out; p.ldc = (long long)T * V3;                     // utterance u -> out + u * T * V3
+    p.c_batch_stride = (long long)fg * V3;                    // frame group g -> frames g * fg ...
+    p.perm_rows = B;
+    p.perm_stride = V3;                                       // ... frame f of the group -> + f * V3
+    p.live_rows = (long long)T * B;
+    p.wait_counters = frames_done;
+    p.wait_target = B;
+    p.wait_per_batch = fg;
+    p.wait_n = T;
+    p.max_ctas = sm_count() - reserve_sms;
+    return gemm_tc(p, 0, 0, as_stream(stream));
+}
+
 }  // extern "C"

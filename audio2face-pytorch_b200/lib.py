@@ -134,6 +134,11 @@ _SIGNATURES = {
                                     c_int, c_void_p, c_size_t, c_void_p]),
     "a2f_decoder_rollout": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                     c_int, c_void_p, c_size_t, c_void_p]),
+    "a2f_decoder_rollout_stream": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                           c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "a2f_vertex_head_stream_rows": (c_int, [c_int, c_int]),
+    "a2f_vertex_head_stream": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_int, c_void_p]),
     "a2f_decoder_save_offset": (c_int, [c_int]),
     "a2f_decoder_rollout_train": (c_int, [C.POINTER(DecoderWeights), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                           c_int, c_void_p, c_size_t, c_void_p, c_void_p]),

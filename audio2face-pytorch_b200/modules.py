@@ -576,6 +576,9 @@ class Faceformer(_A2FModule):
         # launches (bit-identical results; A/B switch for profiles/)
         self.fuse_ffn = True
         self.fuse_block = "attn_ffn_qkv"
+        # bf16 inference, 32 / 64 / 128 utterances: the vertex head runs concurrently with the decoder rollout on the SMs the
+        # rollout leaves idle (ops.rollout_and_head_stream); False = rollout, then head
+        self.stream_head = True
         self.dataset = "vocaset"
         self.period = 60
         self.fps = 60
@@ -823,8 +826,15 @@ class Faceformer(_A2FModule):
             h = self.encode(audio[b0:b1], frame_num)
             ops.gemm(h, P["ca_w"], memory[b0 * frame_num:b1 * frame_num], bias=P["ca_b"], backend=self._backend())
             del h
-        D = ops.decoder_rollout(P["dec"][0], memory, one_hot, self.period, B, frame_num, memory_is_ca=True)
         out = torch.empty((M, self.vertice_dim), dtype=torch.float32, device=audio.device)
+        if self.stream_head and self.precision == "bf16" and ops.head_stream_supported(B, frame_num, self.vertice_dim):
+            # rollout (one SM per utterance, T dependent steps) and vertex head (all other SMs, following frame group by
+            # frame group) run at the same time; same bits as the two launches below
+            ops.rollout_and_head_stream(P["dec"][0], memory, one_hot, self.period, B, frame_num,
+                                        self._head_operand(self.vertice_map_r.weight, 64), self.vertice_map_r.bias.detach(),
+                                        tmpl, out)
+            return out.view(B, frame_num, -1, 3)
+        D = ops.decoder_rollout(P["dec"][0], memory, one_hot, self.period, B, frame_num, memory_is_ca=True)
         hp = max(1, (1 << 17) // frame_num)                            # utterances per vertex-head launch (int32 offsets)
         for b0 in range(0, B, hp):
             b1 = min(B, b0 + hp)

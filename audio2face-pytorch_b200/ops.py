@@ -537,6 +537,56 @@ def decoder_rollout(wstruct: "L.DecoderWeights", memory: torch.Tensor, one_hot: 
     return D
 
 
+def head_stream_supported(B: int, T: int, v3: int) -> bool:
+    """The streamed vertex head (rollout_and_head_stream) takes 32, 64 or 128 utterances and T * V3 < 2^25."""
+    return L.load().a2f_vertex_head_stream_rows(int(B), int(T)) > 0 and T * v3 < (1 << 25) and \
+        B + 8 <= torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
+class _StreamPair:
+    """The side stream (per device) on which the vertex head follows the rollout."""
+    _side = {}
+
+    @classmethod
+    def side(cls, device) -> "torch.cuda.Stream":
+        key = torch.device(device).index
+        if key not in cls._side:
+            cls._side[key] = torch.cuda.Stream(device=device)
+        return cls._side[key]
+
+
+def rollout_and_head_stream(wstruct: "L.DecoderWeights", ca: torch.Tensor, one_hot: torch.Tensor, period: int, B: int, T: int,
+                            w3: torch.Tensor, bias: torch.Tensor, tmpl: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """Decoder rollout and vertex head as two kernels that run AT THE SAME TIME (a2f_decoder_rollout_stream on the current
+    stream, a2f_vertex_head_stream on a side stream): the rollout keeps one SM per utterance busy for T dependent steps, the
+    head follows it frame group by frame group on the other SMs, so only the last group's tiles remain when the rollout
+    ends.  ca [B*T,64] fp32 cross-attention vectors, w3 [V3,192] bf16 (hi|hi|lo), tmpl [B,V3] fp32, out [B*T,V3] fp32 dense.
+    Returns D [B,T,64].  Works inside CUDA-graph capture (the side stream forks from and joins the capturing stream)."""
+    _dev(ca, one_hot, w3, bias, tmpl, out)
+    lib = L.load()
+    v3 = w3.shape[0]
+    rows = lib.a2f_vertex_head_stream_rows(B, T)
+    if rows <= 0 or out.stride(0) != v3 or not out.is_contiguous() or tuple(tmpl.shape) != (B, v3) or w3.shape[1] != 192:
+        raise L.A2FError("rollout_and_head_stream: unsupported shapes")
+    dev = ca.device
+    nbytes = lib.a2f_decoder_workspace_bytes(B, T)
+    ws = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.float32, device=dev)
+    D = torch.empty((B, T, 64), dtype=torch.float32, device=dev)
+    z3 = torch.empty((rows, 192), dtype=torch.bfloat16, device=dev)     # (rows past T*B feed accumulator rows nobody stores)
+    done = torch.zeros(T, dtype=torch.int32, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    side = _StreamPair.side(dev)
+    side.wait_stream(cur)                                   # fork: operands, zeroed counters
+    L.check(lib.a2f_decoder_rollout_stream(C.byref(wstruct), ca.data_ptr(), one_hot.data_ptr(), one_hot.shape[1], period,
+                                           D.data_ptr(), B, T, ws.data_ptr(), ws.numel() * 4, z3.data_ptr(), done.data_ptr(),
+                                           cur.cuda_stream), "a2f_decoder_rollout_stream")
+    with torch.cuda.stream(side):
+        L.check(lib.a2f_vertex_head_stream(z3.data_ptr(), w3.data_ptr(), 192, L.ptr(bias), tmpl.data_ptr(), B, T, v3,
+                                           out.data_ptr(), done.data_ptr(), B, side.cuda_stream), "a2f_vertex_head_stream")
+    cur.wait_stream(side)                                   # join (every tensor used on the side stream is released after it)
+    return D
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # training step (backward-pass kernels, csrc/train.cu / attention.cu / decoder_bwd.cu)
 # ---------------------------------------------------------------------------------------------------------------

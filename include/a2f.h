@@ -317,18 +317,38 @@ int a2f_decoder_rollout(const a2f_decoder_weights* w, const float* memory /*[B,T
 #define A2F_DEC_Y2 7     /* LN2 output                      64 */
 #define A2F_DEC_HID 8    /* relu(linear1)                  128 */
 #define A2F_DEC_Y3PRE 9  /* LN3 input                       64 */
-#define A2F_DEC_LSE 10   /* a2f_decoder_rollout with the cross-attention vectors already computed: ca [B,T,64] = out_proj(v_proj(memory)).  Because
- * memory = audio_feature_map(h) is itself linear, a caller can fold the three Linear layers into ONE [64, 768] GEMM from the
- * encoder states (modules.Faceformer does, for inference); the two 64x64 SIMT GEMM launches of a2f_decoder_rollout
- * disappear.  Same workspace contract. */
-int a2f_decoder_rollout_ca(const a2f_decoder_weights* w, const float* ca, const float* one_hot, int n_onehot, int period,
-                           float* D, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
-/* self-attn log-sum-exp per head   4 */
+#define A2F_DEC_LSE 10   /* self-attn log-sum-exp per head   4 */
 #define A2F_DEC_NFIELDS 11
 int a2f_decoder_save_offset(int field);
 int a2f_decoder_rollout_train(const a2f_decoder_weights* w, const float* memory, const float* one_hot, int n_onehot,
                               int period, float* D, int B, int T, void* workspace, size_t workspace_bytes, float* saves,
                               void* stream);
+
+/* a2f_decoder_rollout with the cross-attention vectors already computed: ca [B,T,64] = out_proj(v_proj(memory)).  Because
+ * memory = audio_feature_map(h) is itself linear, a caller can fold the three Linear layers into ONE [64, 768] GEMM from the
+ * encoder states (modules.Faceformer does, for inference); the two 64x64 SIMT GEMM launches of a2f_decoder_rollout
+ * disappear.  Same workspace contract. */
+int a2f_decoder_rollout_ca(const a2f_decoder_weights* w, const float* ca, const float* one_hot, int n_onehot, int period,
+                           float* D, int B, int T, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Inference rollout that hands its result to the vertex head WHILE it runs (one CTA per utterance: 116 of the 148 SMs of a
+ * B200 are idle during a 32-utterance rollout).  Besides D, every finished frame i is written as the head's bf16 operand
+ * (hi | lo | hi of a2f_split_bf16x3, 192 columns) to row i * B + b of z3_frame_major, then frames_done[i] is incremented
+ * with release semantics, once per utterance.  z3_frame_major: a2f_vertex_head_stream_rows(B, T) rows x 192 bf16;
+ * frames_done: T zeroed counters.  Always the single-CTA-per-utterance kernel. */
+int a2f_decoder_rollout_stream(const a2f_decoder_weights* w, const float* ca, const float* one_hot, int n_onehot, int period,
+                               float* D, int B, int T, void* workspace, size_t workspace_bytes, void* z3_frame_major,
+                               unsigned* frames_done, void* stream);
+/* The consumer: out[b, t, :] = W3 z3[t * B + b, :] + bias + tmpl[b, :] for B in {32, 64, 128} utterances (ref:
+ * src/model/faceformer.py:181-188), launched on a SECOND stream at the same time as a2f_decoder_rollout_stream.  The
+ * tcgen05 vertex-head kernel processes groups of 128 / B frames in frame order; the producer warp of a tile waits
+ * (ld.acquire.gpu) until frames_done of the group's last frame has reached B.  The grid is capped at #SMs - reserve_sms
+ * so that the rollout's CTAs are resident whatever order the two kernels start in (reserve_sms >= B).  Same bits as
+ * a2f_gemm on the utterance-major operand. */
+int a2f_vertex_head_stream_rows(int B, int T);   /* rows of z3_frame_major (0 = this B is not supported) */
+int a2f_vertex_head_stream(const void* z3_frame_major, const void* w3, int K3, const float* bias, const float* tmpl, int B, int T,
+                           int V3, float* out, const unsigned* frames_done, int reserve_sms, void* stream);
+
 /* Backward through the rollout (BPTT; the reference trains by free rollout, ref:src/model/faceformer.py:154-185, so
  * gradients flow through the fed-back embeddings).  One persistent CTA per utterance walks the frames in reverse.
  * gD: [B,T,64] dL/dd_i from the vertex head.  grads (fp32): field f is a dense [B,T,width_f] block at float offset

@@ -270,6 +270,34 @@ def test_faceformer_bf16_encoder_fusion_variants_agree(ff_model, ff_sd, dev):
         assert torch.equal(outs[name], outs["gemm_ln"]), name
 
 
+@pytest.mark.parametrize("B,n", [(32, 8000), (32, 19800), (64, 4000)])
+def test_faceformer_streamed_head_equals_sequential(ff_model, ff_sd, dev, B, n):
+    """bf16 inference with 32 / 64 utterances: the vertex head runs on a side stream WHILE the rollout runs (frame-major
+    operand written by the rollout, frames_done counters, ld.acquire in the head's producer warp).  Must give the same bits
+    as rollout-then-head, eagerly and inside a CUDA graph, also when the last frame group is partly filled (T = 37)."""
+    T = n * 30 // 16000
+    audio, oh, tp = oin.audio(B, n, 41), oin.one_hot(B, 12, 41), oin.batch_templates(B, 41, scale=100.0)
+    m = ff_model.set_precision("bf16")
+    d_in = [audio.to(dev), oh.to(dev), tp.to(dev)]
+    saved = m.stream_head
+    try:
+        with torch.no_grad():
+            m.stream_head = False
+            want = m(*d_in, fps=30).clone()
+            m.stream_head = True
+            got = m(*d_in, fps=30).clone()
+            got2 = m(*d_in, fps=30).clone()
+            g = m.graphed(*d_in, fps=30)
+            rep = g(*g.static_in).clone()
+            rep2 = g(*g.static_in).clone()
+        torch.cuda.synchronize()
+    finally:
+        m.stream_head = saved
+    assert tuple(want.shape) == (B, T, 5023, 3)
+    assert torch.equal(got, want) and torch.equal(got2, want)
+    assert torch.equal(rep, want) and torch.equal(rep2, want)
+
+
 def test_faceformer_batch_equals_per_utterance(ff_model, ff_sd, dev):
     """Batch extension: every utterance of a batch gets the reference's batch-1 result."""
     B, n = 3, 12000
