@@ -538,9 +538,12 @@ def decoder_rollout(wstruct: "L.DecoderWeights", memory: torch.Tensor, one_hot: 
 
 
 def head_stream_supported(B: int, T: int, v3: int) -> bool:
-    """The streamed vertex head (rollout_and_head_stream) takes 32, 64 or 128 utterances and T * V3 < 2^25."""
-    return L.load().a2f_vertex_head_stream_rows(int(B), int(T)) > 0 and T * v3 < (1 << 25) and \
-        B + 8 <= torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    """When the streamed vertex head (rollout_and_head_stream) pays: 32 or 64 utterances (the head gets the SMs the rollout
+    leaves idle: with 128 utterances that would be 20 of 148) and clips below 900 frames (from there on the rollout spreads an
+    utterance over a CTA cluster, which the streaming kernel does not do); the kernel itself needs T * V3 < 2^25."""
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return B in (32, 64) and T < 900 and L.load().a2f_vertex_head_stream_rows(int(B), int(T)) > 0 and \
+        T * v3 < (1 << 25) and 2 * B <= sms
 
 
 class _StreamPair:
