@@ -160,6 +160,136 @@ __global__ void __launch_bounds__(512) conv0_gn_stats_kernel(const double* __res
     gn[b * 512 + c] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
 }
 
+// ------------------------------------------------------------------------------------------------ raw moments (inference)
+// The processor statistics (a2f_audio_stats) and the conv0 moments in ONE pass over the RAW audio: besides the 10 lag sums
+// and 55 lag products of conv0_moments_kernel, every chunk also sums x and x^2 of its samples.  conv0_gn_stats_auto_kernel
+// then derives mean / rstd of the utterance and the moments of the NORMALISED audio algebraically (fp64):
+//     S'[k] = r (S[k] - L0 m),     R'[k,k'] = r^2 (R[k,k'] - m (S[k] + S[k']) + L0 m^2),     x' = (x - m) r
+// which removes one launch and one full pass from the dependent chain in front of conv0 (audio_stats 24 us + moments 29 us at
+// the bench shape, both latency-bound).  m is the fp32-rounded mean and r = 1/sqrt(var + 1e-7) in fp32 like the processor
+// (ref:src/model/faceformer.py:142-144 through Wav2Vec2Processor); var = (sum x^2 - 2 m sum x + N m^2) / N in fp64.
+constexpr int RAW_N = MOM_N + 2;    // + sum x, sum x^2
+
+__global__ void __launch_bounds__(256) conv0_raw_moments_kernel(const float* __restrict__ audio, long long N, int L0, int nchunk,
+                                                                double* __restrict__ partial) {
+    pdl_sync();
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const float* x = audio + (long long)b * N;
+    __shared__ __align__(16) float xs[5 * MOM_TCH + 16];
+    __shared__ double sh[8][RAW_N];
+    const int t0 = chunk * MOM_TCH;
+    const int tn = min(MOM_TCH, L0 - t0);                     // conv outputs of this chunk
+    const long long s0 = 5LL * t0;                            // first sample of the chunk
+    // samples the lag windows touch: [s0, s0 + 5 tn + 5); samples this chunk OWNS for sum x / sum x^2: [s0, s0 + 5 tn), the last
+    // chunk also owns everything up to N
+    const int n_win = 5 * tn + 5;
+    const long long own_end = (chunk == nchunk - 1) ? N : s0 + 5LL * tn;
+    float sx = 0.f, sxx = 0.f;
+    for (int i = threadIdx.x; i < n_win; i += 256) {
+        const long long gi = s0 + i;
+        const float v = gi < N ? __ldg(x + gi) : 0.f;
+        xs[i] = v;
+        if (gi < own_end) { sx += v; sxx = fmaf(v, v, sxx); }
+    }
+    for (long long gi = s0 + n_win + threadIdx.x; gi < own_end; gi += 256) {      // tail of the last chunk (at most a few samples)
+        const float v = __ldg(x + gi);
+        sx += v; sxx = fmaf(v, v, sxx);
+    }
+    __syncthreads();
+    float acc[MOM_N];
+#pragma unroll
+    for (int i = 0; i < MOM_N; ++i) acc[i] = 0.f;
+    for (int t = threadIdx.x; t < tn; t += 256) {
+        float v[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = xs[5 * t + k];    // stride 5 over the lanes: conflict-free
+        int idx = 10;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            acc[k] += v[k];
+#pragma unroll
+            for (int k2 = k; k2 < 10; ++k2) {
+                acc[idx] = fmaf(v[k], v[k2], acc[idx]);
+                ++idx;
+            }
+        }
+    }
+    // at most 4 fp32 terms per thread and 32 per warp are summed in fp32, everything above that in fp64
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < MOM_N; ++i) {
+        const float d = warp_sum(acc[i]);
+        if (lane == 0) sh[warp][i] = (double)d;
+    }
+    {
+        const double d0 = warp_sum_d((double)sx), d1 = warp_sum_d((double)sxx);
+        if (lane == 0) { sh[warp][MOM_N] = d0; sh[warp][MOM_N + 1] = d1; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RAW_N; i += 256) {
+        double d = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) d += sh[w][i];
+        partial[((long long)b * nchunk + chunk) * RAW_N + i] = d;
+    }
+}
+
+// per utterance: processor statistics -> stats[2b], stats[2b+1]; per (utterance, channel): mean and rstd of the conv output
+__global__ void __launch_bounds__(512) conv0_gn_stats_auto_kernel(const double* __restrict__ partial, int nchunk,
+                                                                  const float* __restrict__ w, long long N, int L0,
+                                                                  float* __restrict__ stats, float2* __restrict__ gn) {
+    pdl_sync();
+    const int b = blockIdx.x, c = threadIdx.x;
+    __shared__ double raw[RAW_N];
+    __shared__ double mom[MOM_N];
+    for (int i = threadIdx.x; i < RAW_N; i += blockDim.x) {
+        double d = 0.0;
+        for (int k = 0; k < nchunk; ++k) d += partial[((long long)b * nchunk + k) * RAW_N + i];
+        raw[i] = d;
+    }
+    __syncthreads();
+    const float meanf = (float)(raw[MOM_N] / (double)N);
+    const double m = (double)meanf;
+    const float var = (float)((raw[MOM_N + 1] - 2.0 * m * raw[MOM_N] + (double)N * m * m) / (double)N);
+    const float rstdf = 1.0f / sqrtf(fmaxf(var, 0.f) + 1e-7f);
+    const double r = (double)rstdf;
+    if (threadIdx.x == 0) {
+        stats[2 * b] = meanf;
+        stats[2 * b + 1] = rstdf;
+    }
+    if (threadIdx.x < MOM_N) {
+        const int i = threadIdx.x;
+        if (i < 10) {
+            mom[i] = r * (raw[i] - (double)L0 * m);
+        } else {
+            // upper-triangular index i -> (k, k2) in the order of the accumulation loop
+            int k = 0, base = 10;
+            while (i >= base + (10 - k)) { base += 10 - k; ++k; }
+            const int k2 = k + (i - base);
+            mom[i] = r * r * (raw[i] - m * (raw[k] + raw[k2]) + (double)L0 * m * m);
+        }
+    }
+    __syncthreads();
+    double wc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) wc[k] = (double)w[c * 10 + k];
+    double s1 = 0.0, s2 = 0.0;
+    int idx = 10;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        s1 += wc[k] * mom[k];
+#pragma unroll
+        for (int k2 = k; k2 < 10; ++k2) {
+            const double term = wc[k] * wc[k2] * mom[idx++];
+            s2 += (k2 == k) ? term : 2.0 * term;
+        }
+    }
+    const double mean = s1 / L0;
+    double v2 = s2 / L0 - mean * mean;
+    if (v2 < 0.0) v2 = 0.0;
+    gn[b * 512 + c] = make_float2((float)mean, (float)(1.0 / sqrt(v2 + 1e-5)));
+}
+
 // ------------------------------------------------------------------------------------------------ conv0 apply
 constexpr int C0_TCH = 64;   // time steps per CTA
 
@@ -429,6 +559,46 @@ int a2f_conv0_gn_gelu(const float* audio, const float* stats, const float* w, co
     else
         A2F_CHECK_CUDA(launch_pdl(conv0_apply_kernel<float>, dim3(grid), dim3(256), 0, s, audio, stats, w, gn, gamma, beta, static_cast<float*>(out), N, L0,
                                                        L0_pad * 512));
+    A2F_CHECK_LAUNCH("conv0_apply_kernel");
+    count_launch(3);
+    return A2F_OK;
+}
+
+/* inference: processor statistics and conv0 from the raw audio (stats_out [B,2] is written, not read) */
+size_t a2f_conv0_auto_workspace_bytes(int B, long long N) {
+    if (B <= 0 || N < 10) return 0;
+    return (size_t)B * conv0_nchunk(N) * RAW_N * sizeof(double) + (size_t)B * 512 * sizeof(float2) + 64;
+}
+
+int a2f_conv0_gn_gelu_auto(const float* audio, float* stats_out, const float* w, const float* gamma, const float* beta,
+                           void* out, int out_dtype, int B, long long N, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    int rc = require_sm100();
+    if (rc != A2F_OK) return rc;
+    A2F_REQUIRE(audio && stats_out && w && gamma && beta && out && workspace, "a2f_conv0_gn_gelu_auto: NULL argument");
+    A2F_REQUIRE(B > 0 && N >= 10, "a2f_conv0_gn_gelu_auto: need B > 0 and N >= 10 samples");
+    A2F_REQUIRE(workspace_bytes >= a2f_conv0_auto_workspace_bytes(B, N), "a2f_conv0_gn_gelu_auto: workspace too small");
+    A2F_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 8 == 0, "a2f_conv0_gn_gelu_auto: workspace must be 8-byte aligned");
+    const long long L0ll = (N - 10) / 5 + 1;
+    A2F_REQUIRE(L0ll < (1LL << 30), "a2f_conv0_gn_gelu_auto: utterance too long");
+    const int L0 = (int)L0ll;
+    const int nchunk = conv0_nchunk(N);
+    double* partial = static_cast<double*>(workspace);
+    float2* gn = reinterpret_cast<float2*>(partial + (size_t)B * nchunk * RAW_N);
+    cudaStream_t s = as_stream(stream);
+    A2F_CHECK_CUDA(launch_pdl(conv0_raw_moments_kernel, dim3(nchunk, B), dim3(256), 0, s, audio, N, L0, nchunk, partial));
+    A2F_CHECK_LAUNCH("conv0_raw_moments_kernel");
+    A2F_CHECK_CUDA(launch_pdl(conv0_gn_stats_auto_kernel, dim3(B), dim3(512), 0, s, (const double*)partial, nchunk, w, N, L0,
+                              stats_out, gn));
+    A2F_CHECK_LAUNCH("conv0_gn_stats_auto_kernel");
+    const dim3 grid((L0 + C0_TCH - 1) / C0_TCH, B);
+    const long long L0_pad = L0;
+    if (out_dtype == A2F_BF16)
+        A2F_CHECK_CUDA(launch_pdl(conv0_apply_kernel<bf16>, dim3(grid), dim3(256), 0, s, audio, (const float*)stats_out, w,
+                                  (const float2*)gn, gamma, beta, static_cast<bf16*>(out), N, L0, L0_pad * 512));
+    else
+        A2F_CHECK_CUDA(launch_pdl(conv0_apply_kernel<float>, dim3(grid), dim3(256), 0, s, audio, (const float*)stats_out, w,
+                                  (const float2*)gn, gamma, beta, static_cast<float*>(out), N, L0, L0_pad * 512));
     A2F_CHECK_LAUNCH("conv0_apply_kernel");
     count_launch(3);
     return A2F_OK;

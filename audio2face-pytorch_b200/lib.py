@@ -118,6 +118,9 @@ _SIGNATURES = {
     "a2f_conv0_workspace_bytes": (c_size_t, [c_int, c_ll]),
     "a2f_conv0_gn_gelu": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll,
                                   c_void_p, c_size_t, c_void_p]),
+    "a2f_conv0_auto_workspace_bytes": (c_size_t, [c_int, c_ll]),
+    "a2f_conv0_gn_gelu_auto": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll,
+                                       c_void_p, c_size_t, c_void_p]),
     "a2f_interp_ln": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int,
                               c_int, c_void_p]),
     "a2f_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int, c_ll,

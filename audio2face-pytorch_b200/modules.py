@@ -579,6 +579,9 @@ class Faceformer(_A2FModule):
         # bf16 inference, 32 / 64 / 128 utterances: the vertex head runs concurrently with the decoder rollout on the SMs the
         # rollout leaves idle (ops.rollout_and_head_stream); False = rollout, then head
         self.stream_head = True
+        # inference front end: audio statistics and conv0 moments in one pass over the raw audio; False = a2f_audio_stats, then
+        # the moments of the normalised audio (two passes, one launch more)
+        self.raw_moments = True
         self.dataset = "vocaset"
         self.period = 60
         self.fps = 60
@@ -716,10 +719,14 @@ class Faceformer(_A2FModule):
         ae = self.audio_encoder
         B, N = audio.shape
         dev = audio.device
-        if stats is None:
-            stats = ops.audio_stats(audio)
         gn = ae.feature_extractor.conv_layers[0].layer_norm
-        x = ops.conv0_gn_gelu(audio, stats, P["conv0_w"], gn.weight.detach(), gn.bias.detach(), dt)   # [B,L0,512]
+        if stats is None and self.raw_moments:
+            # processor statistics and conv0 moments from ONE pass over the raw audio (a2f_conv0_gn_gelu_auto)
+            x, stats = ops.conv0_gn_gelu_auto(audio, P["conv0_w"], gn.weight.detach(), gn.bias.detach(), dt)
+        else:
+            if stats is None:
+                stats = ops.audio_stats(audio)
+            x = ops.conv0_gn_gelu(audio, stats, P["conv0_w"], gn.weight.detach(), gn.bias.detach(), dt)   # [B,L0,512]
         L_in = x.shape[1]
         for i, k in enumerate((3, 3, 3, 3, 2, 2)):
             L_out = (L_in - k) // 2 + 1

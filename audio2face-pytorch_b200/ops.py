@@ -776,6 +776,23 @@ def padded_rows(B: int, rows: int, C_: int, dtype: torch.dtype, device) -> torch
     return flat[: B * rows * C_].view(B, rows, C_)
 
 
+def conv0_gn_gelu_auto(audio: torch.Tensor, w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dtype: torch.dtype):
+    """Processor normalisation + conv0 + GroupNorm + GELU from one pass over the raw audio (a2f_conv0_gn_gelu_auto).
+    -> (channels-last [B, L0, 512], stats [B,2])"""
+    _dev(audio, w, gamma, beta)
+    B, N = audio.shape
+    L0 = (N - 10) // 5 + 1
+    lib = L.load()
+    nbytes = lib.a2f_conv0_auto_workspace_bytes(B, N)
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=audio.device)
+    stats = torch.empty((B, 2), dtype=torch.float32, device=audio.device)
+    out = torch.empty((B, L0, 512), dtype=dtype, device=audio.device)
+    L.check(lib.a2f_conv0_gn_gelu_auto(audio.data_ptr(), stats.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                       out.data_ptr(), _dt(out), B, N, ws.data_ptr(), ws.numel() * 8, _stream()),
+            "a2f_conv0_gn_gelu_auto")
+    return out, stats
+
+
 def conv0_gn_gelu_train(audio, stats, w, gamma, beta, dtype):
     """conv0_gn_gelu that also returns the workspace (it holds the GroupNorm statistics the backward needs)."""
     _dev(audio, stats, w, gamma, beta)

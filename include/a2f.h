@@ -232,6 +232,13 @@ size_t a2f_conv0_workspace_bytes(int B, long long N);
 int a2f_conv0_gn_gelu(const float* audio, const float* stats, const float* w /*[512,10]*/, const float* gamma,
                       const float* beta, void* out, int out_dtype, int B, long long N, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* a2f_audio_stats + a2f_conv0_gn_gelu from ONE pass over the raw audio (inference): the moments of the normalised audio follow
+ * algebraically from raw lag sums / products and sum x, sum x^2 (fp64); stats_out [B,2] (mean, rstd) is WRITTEN.  One launch
+ * and one pass less in the dependent chain in front of conv0. */
+size_t a2f_conv0_auto_workspace_bytes(int B, long long N);
+int a2f_conv0_gn_gelu_auto(const float* audio, float* stats_out, const float* w /*[512,10]*/, const float* gamma,
+                           const float* beta, void* out, int out_dtype, int B, long long N, void* workspace,
+                           size_t workspace_bytes, void* stream);
 int a2f_interp_ln(const void* in, int in_dtype, const float* gamma, const float* beta, float eps, void* out,
                   int out_dtype, int B, int S, int T, int C, void* stream);
 /* LayerNorm over the last dim (C <= 4096, C % 4 == 0): out = (x-mean)*rstd*gamma+beta, stats in fp32.

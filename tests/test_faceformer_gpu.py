@@ -42,6 +42,31 @@ def test_audio_stats_matches_processor(a2f_lib, dev):
         assert abs(float(st[b, 1]) - float(1.0 / np.sqrt(x.var() + 1e-7))) < 2e-5 * float(st[b, 1])
 
 
+@pytest.mark.parametrize("B,n", [(1, 4000), (3, 16000), (2, 11205), (2, 80000), (1, 5123)])
+def test_conv0_from_raw_moments_matches_two_pass(a2f_lib, dev, B, n):
+    """a2f_conv0_gn_gelu_auto (processor statistics + conv0 moments from one pass over the RAW audio, normalised moments
+    derived algebraically in fp64) against a2f_audio_stats + a2f_conv0_gn_gelu: the statistics agree to fp32 rounding and
+    the conv0 output to 1e-5 relative (fp32) -- lengths that are / are not multiples of 5 and of the chunk size, a tail of
+    samples no conv window covers, audio with a DC offset (the cancellation case of the algebra)."""
+    from a2f_b200 import ops
+    g = torch.Generator().manual_seed(n + B)
+    audio = (0.1 * torch.randn(B, n, generator=g) + 0.05).to(dev)
+    w = (0.3 * torch.randn(512, 10, generator=g)).to(dev)
+    gamma, beta = (torch.rand(512, generator=g) + 0.5).to(dev), (0.1 * torch.randn(512, generator=g)).to(dev)
+    stats = ops.audio_stats(audio)
+    want = ops.conv0_gn_gelu(audio, stats, w, gamma, beta, torch.float32)
+    got, stats2 = ops.conv0_gn_gelu_auto(audio, w, gamma, beta, torch.float32)
+    torch.cuda.synchronize()
+    ref_mean = audio.double().mean(dim=1)
+    assert float((stats2[:, 0].double() - ref_mean).abs().max()) < 1e-7
+    assert float(((stats2[:, 1] - stats[:, 1]).abs() / stats[:, 1]).max()) < 1e-6
+    err = (got - want).abs()
+    assert float((err / (want.abs() + 1.0)).max()) < 1e-5, float(err.max())
+    got16, _ = ops.conv0_gn_gelu_auto(audio, w, gamma, beta, torch.bfloat16)
+    want16 = ops.conv0_gn_gelu(audio, stats, w, gamma, beta, torch.bfloat16)
+    assert float(((got16.float() - want16.float()).abs() / (want16.float().abs() + 1.0)).max()) < 2.0 ** -7
+
+
 @pytest.mark.parametrize("n_samples", [4000, 16000, 11205])
 def test_feature_extractor_fp32(a2f_lib, dev, ff_sd, ff_model, n_samples):
     """conv0+GroupNorm+GELU and the six implicit-GEMM convs vs F.conv1d / F.group_norm (HF feature encoder)."""
