@@ -10,7 +10,7 @@
 //   pass 1  accumulator (TMEM) + bias + residual (TMA -> swizzled staging) -> fp32 sum written BACK into TMEM
 //           (tcgen05.st: TMEM is the row buffer, nothing is recomputed), per-thread partial (s1, s2) of its 128 columns
 //   exchange every epilogue thread stores its partial into the stats slot of the NP CTAs that hold the same rows
-//           (st.shared::cluster) and arrives (release.cluster) on their stats mbarrier; waits (acquire.cluster) on its own
+//           (st.shared::cluster), one lane per warp arrives (release.cluster) on their stats mbarrier; waits (acquire.cluster) on its own
 //   pass 2  TMEM -> (x - mean) * rstd * gamma + beta -> bf16 -> swizzled staging -> TMA store
 // The pre-LayerNorm sum never leaves the SM and is never rounded to bf16 (round 1 stored it in bf16 and re-read it in a
 // separate layernorm_kernel launch: 24 launches per forward, 6 % of the step, and the largest single contribution to the
@@ -169,10 +169,13 @@ A2F_D void ln_tile_epilogue(const CUtensorMap* map_r, const CUtensorMap* map_c, 
         const uint32_t slot = smem_u32(sStats + ((size_t)par * (2 * NP) + (size_t)(pr * 2 + half)) * LBM + r_tile);
         const uint32_t sbar = smem_u32(&stat_bar[par]);
 #pragma unroll
-        for (int d = 0; d < NP; ++d) {
-            const uint32_t dst_rank = (uint32_t)(2 * d + hr);
-            st_cluster_f2(map_to_rank(slot, dst_rank), s1, s2);
-            mbar_arrive_cluster_release(map_to_rank(sbar, dst_rank));
+        for (int d = 0; d < NP; ++d) st_cluster_f2(map_to_rank(slot, (uint32_t)(2 * d + hr)), s1, s2);
+        // one arrive per warp and destination (release.cluster, cumulative over the warp's stores through __syncwarp): 8 x NP
+        // remote arrives per CTA and tile instead of 256 x NP
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < NP; ++d) mbar_arrive_cluster_release(map_to_rank(sbar, (uint32_t)(2 * d + hr)));
         }
     }
     tmem_st_wait();
@@ -277,7 +280,7 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const LnParams p) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 16);
-            mbar_init(&stat_bar[i], NP * 256);
+            mbar_init(&stat_bar[i], NP * 8);
         }
         for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
         fence_mbar_init();
@@ -558,7 +561,7 @@ enc_block_kernel(const __grid_constant__ BlkMaps maps, const BlkParams p) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 16);
-            mbar_init(&stat_bar[i], NP * 256);
+            mbar_init(&stat_bar[i], NP * 8);
         }
         for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
         for (int i = 0; i < BLK_MAX_TP + 2; ++i) mbar_init(&f_bar[i], 2 * NP);  // 2 epilogue leaders x NP CTAs with these rows
