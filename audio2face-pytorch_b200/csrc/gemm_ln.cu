@@ -17,6 +17,10 @@
 // bf16 path's error -- tools/bf16_noise_floor.py: 1.6 % -> 1.0 % of the largest vertex offset).
 // Mainloop, barriers and TMEM double buffering follow gemm_tc2_kernel (gemm_tc.cu); the ring is 4 stages deep here because
 // the stats slots and the LayerNorm parameters need 13 KB of shared memory.
+//
+// Two kernels live here: gemm_ln_kernel (one GEMM + LayerNorm: a2f_gemm_ln, used by the training forward, which also stores
+// the pre-LayerNorm sum) and enc_block_kernel further down (up to four GEMM phases of an encoder layer back to back in the
+// same cluster: a2f_encoder_block / a2f_ffn_ln, the inference path).  Both use ln_tile_epilogue for their LayerNorm tiles.
 #include "a2f_common.cuh"
 #include "gemm_params.cuh"
 
